@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py — the Raycaster micro-bench of BASELINE.json configs[1] on B200 (SURVEY.md §8d "C2").
+
+Workload (one "step"): a 1,002,528-triangle displaced grid, reference-order BVH; 4,194,304 coherent primary rays and
+4,194,304 incoherent bounce rays, each traced closest-hit (Raycaster::intersects) AND any-hit
+(Raycaster::intersectsAny): 16,777,216 ray queries per step and per GPU. Metric: Mrays/s.
+
+  value : device-resident — rays and hit buffers already in HBM, CUDA-event time on the launching stream.
+  e2e   : the same step through the host-pointer C ABI (rb_raycaster_intersect / _intersect_any) with pinned host
+          buffers: H2D of the rays and D2H of the Raycaster::Hit records inside the timed region.
+  roofline     : dominant kernel, algorithmic bytes / live CUDA-event duration vs measured HBM peak.
+  cpu_baseline : the reference's own CPU code (oracle/_ref, else the C oracle) on a bounded sample, host threads stated.
+
+`--impl reference` times the reference CPU implementation alone (same metric/config, bounded sample per step).
+Launch: python bench.py [--gpus N --steps K --warmup W]; for N>1 under torchrun (one rank per GPU, weak scaling:
+every rank traces the full ray sets against its own replica of the scene; no data-path collective).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GRID_N = 708          # 2*708^2 = 1,002,528 triangles
+RES = 2048            # 2048^2 = 4,194,304 rays per set
+MINI, MAXI = 1e-4, 1e8
+SAMPLE_ROW_STRIDE = 16  # CPU legs trace every 16th row of each set: 262,144 rays per set
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def sample_rows():
+    return np.arange(0, RES, SAMPLE_ROW_STRIDE)
+
+
+def sample_index():
+    rows = sample_rows()
+    return (rows[:, None] * RES + np.arange(RES)[None, :]).reshape(-1)
+
+
+# ------------------------------------------------------------------------------------------ CPU legs
+def cpu_tracer(pos, idx):
+    """The reference's own Raycaster when oracle/_ref was built, else the C restatement."""
+    from oracle import ref
+    if ref.available():
+        r = ref.RefRaycaster()
+        r.add_mesh(pos, idx)
+        r.build()
+        threads = ref.threads_default()  # the reference's policy: hardware_concurrency()-1 (System.hpp:82)
+
+        def closest(o, d):
+            return r.intersect(o, d, MINI, MAXI, threads=threads)
+
+        def anyhit(o, d):
+            return r.intersect_any(o, d, MINI, MAXI, threads=threads)[0]
+        return "reference", threads, closest, anyhit
+    from oracle import oracle as orc
+    o_ = orc.OracleRaycaster()
+    o_.add_mesh(pos, idx)
+    o_.build()
+    threads = max((os.cpu_count() or 2) - 1, 1)
+
+    def closest(o, d):
+        h = o_.intersect(o, d, MINI, MAXI, threads=threads)
+        return dict(hit=h["hit"], dist=h["dist"], local_id=h["localId"])
+
+    def anyhit(o, d):
+        return o_.intersect_any(o, d, MINI, MAXI, threads=threads)
+    return "port", threads, closest, anyhit
+
+
+def cpu_sample_sets(pos, idx, closest):
+    from rendu_b200 import workloads as wl
+    sel = sample_index()
+    co, cd = wl.coherent_rays(RES)
+    co, cd = np.ascontiguousarray(co[sel]), np.ascontiguousarray(cd[sel])
+    h = closest(co, cd)
+    nrm = wl.triangle_normals(pos, idx, np.where(h["hit"] == 1, h["local_id"], 0))
+    io, idr = wl.incoherent_rays(co, cd, h["hit"], h["dist"], nrm, seed=1234, index_base=0)
+    return co, cd, np.ascontiguousarray(io), np.ascontiguousarray(idr)
+
+
+def cpu_step(sets, closest, anyhit):
+    co, cd, io, idr = sets
+    t0 = time.perf_counter()
+    closest(co, cd)
+    anyhit(co, cd)
+    closest(io, idr)
+    anyhit(io, idr)
+    return time.perf_counter() - t0, 4 * co.shape[0]
+
+
+def config_dict(n_gpus):
+    return {"workload": "C2 raycaster micro-bench: 1,002,528-triangle displaced grid (N=708), reference-order BVH, "
+                        "4,194,304 coherent + 4,194,304 incoherent rays, closest-hit and any-hit (16,777,216 queries/step/GPU)",
+            "triangles": 2 * GRID_N * GRID_N, "rays_per_set": RES * RES, "queries_per_step_per_gpu": 4 * RES * RES,
+            "mini": MINI, "maxi": MAXI, "trace_mode": "exact (reference traversal order, bit-identical hits)",
+            "parallelism": "replicated scene, %d independent rank(s), no collective" % n_gpus,
+            "l2": "no explicit flush: one step streams ~0.7 GB (rays 201 MB + Hit records 403 MB + any flags 8 MB + 82 MB tree) through a 126 MB L2"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from rendu_b200 import workloads as wl
+    pos, idx = wl.displaced_grid(GRID_N)
+    kind, threads, closest, anyhit = cpu_tracer(pos, idx)
+    sets = cpu_sample_sets(pos, idx, closest)
+    for _ in range(args.warmup):
+        cpu_step(sets, closest, anyhit)
+    total_t, total_q = 0.0, 0
+    for _ in range(args.steps):
+        t, q = cpu_step(sets, closest, anyhit)
+        total_t += t
+        total_q += q
+    value = total_q / total_t / 1e6
+    sample = "every %dth row of both ray sets (%d rays/set, %d queries/step), closest+any" % (SAMPLE_ROW_STRIDE, sets[0].shape[0], 4 * sets[0].shape[0])
+    line = {"impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config_dict(args.gpus),
+            "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import rendu_b200 as rb
+    from rendu_b200 import workloads as wl
+    from rendu_b200._capi import check, lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if rb.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device — rendu_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    check(lib().rb_set_device(local_rank))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    t_setup = time.time()
+    pos, idx = wl.displaced_grid(GRID_N)
+    rc = rb.Raycaster()
+    rc.addMesh(pos, idx)
+    rc.updateHierarchy(rb.BUILD_REFERENCE)
+    co, cd = wl.coherent_rays(RES)
+    n = co.shape[0]
+    stream = torch.cuda.current_stream()
+    sh = stream.cuda_stream
+
+    def dev_f32(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+    d_co, d_cd = dev_f32(co), dev_f32(cd)
+    d_hit_c = torch.empty(n * 48, dtype=torch.uint8, device=dev)
+    d_hit_i = torch.empty(n * 48, dtype=torch.uint8, device=dev)
+    d_any_c = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_any_i = torch.empty(n, dtype=torch.uint8, device=dev)
+    # Incoherent set: bounce rays from the coherent set's closest hits (traced by the CUDA path itself).
+    rc.intersects_device(d_co.data_ptr(), d_cd.data_ptr(), n, d_hit_c.data_ptr(), MINI, MAXI, sh)
+    torch.cuda.synchronize()
+    hits = d_hit_c.cpu().numpy().view(rb.HIT_DTYPE)
+    nrm = wl.triangle_normals(pos, idx, np.where(hits["hit"] == 1, hits["localId"], 0))
+    io, idr = wl.incoherent_rays(co, cd, hits["hit"], hits["dist"], nrm, seed=1234, index_base=0)
+    d_io, d_id = dev_f32(io), dev_f32(idr)
+    log("[bench] rank %d setup %.1fs: %d tris, %d nodes, coherent hit rate %.3f" % (rank, time.time() - t_setup, rc.sizes()["tris"], rc.sizes()["nodes"], float((hits["hit"] == 1).mean())))
+
+    launches = [
+        ("closest_coherent", lambda: rc.intersects_device(d_co.data_ptr(), d_cd.data_ptr(), n, d_hit_c.data_ptr(), MINI, MAXI, sh)),
+        ("any_coherent", lambda: rc.intersectsAny_device(d_co.data_ptr(), d_cd.data_ptr(), n, d_any_c.data_ptr(), MINI, MAXI, sh)),
+        ("closest_incoherent", lambda: rc.intersects_device(d_io.data_ptr(), d_id.data_ptr(), n, d_hit_i.data_ptr(), MINI, MAXI, sh)),
+        ("any_incoherent", lambda: rc.intersectsAny_device(d_io.data_ptr(), d_id.data_ptr(), n, d_any_i.data_ptr(), MINI, MAXI, sh)),
+    ]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        for _, f in launches:
+            f()
+    barrier()
+
+    # ---- timed region 1: device-resident (value)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in launches] for _ in range(args.steps)]
+    l0 = rc.launch_count()
+    e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e_start.record(stream)
+    for s in range(args.steps):
+        for k, (_, f) in enumerate(launches):
+            ev[s][k][0].record(stream)
+            f()
+            ev[s][k][1].record(stream)
+    e_stop.record(stream)
+    barrier()
+    total_ms = e_start.elapsed_time(e_stop)
+    gpu_launches = rc.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    per_kernel_ms = [float(np.mean([ev[s][k][0].elapsed_time(ev[s][k][1]) for s in range(args.steps)])) for k in range(len(launches))]
+
+    # ---- timed region 2: end to end through the host-pointer ABI with pinned buffers (e2e)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
+    h_co, h_cd, h_io, h_id = pin(co), pin(cd), pin(io), pin(idr)
+    h_hits = torch.empty(n * 48, dtype=torch.uint8).pin_memory()
+    h_any = torch.empty(n, dtype=torch.uint8).pin_memory()
+    L = lib()
+
+    def e2e_step():
+        for o_, d_ in ((h_co, h_cd), (h_io, h_id)):
+            check(L.rb_raycaster_intersect(rc._h, o_.data_ptr(), d_.data_ptr(), MINI, MAXI, n, h_hits.data_ptr()))
+            check(L.rb_raycaster_intersect_any(rc._h, o_.data_ptr(), d_.data_ptr(), MINI, MAXI, n, h_any.data_ptr()))
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d = 4 * n * 24
+    d2h = 2 * n * 48 + 2 * n
+
+    # ---- max over ranks
+    times = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(times[0]), float(times[1])
+    queries_step = 4 * n
+    value = world * queries_step * args.steps / (total_ms * 1e-3) / 1e6
+    e2e_value = world * queries_step * e2e_steps / (e2e_ms * 1e-3) / 1e6
+
+    if rank == 0:
+        # Work counters (instrumented kernel, outside the timed regions) -> algorithmic bytes per launch.
+        work = []
+        for (name, _), (o_, d_, anyh) in zip(launches, ((d_co, d_cd, False), (d_co, d_cd, True), (d_io, d_id, False), (d_io, d_id, True))):
+            w = rc.count_work_device(o_.data_ptr(), d_.data_ptr(), n, anyh, MINI, MAXI, sh)
+            out_b = 1 if anyh else 48
+            w["bytes"] = n * (24 + out_b) + 64 * w["interior"] + 48 * w["tris"] + 32 * w["roots"]
+            w["name"] = name
+            work.append(w)
+        dom = int(np.argmax(per_kernel_ms))
+        peak, peak_src = measured_hbm_peak()
+        achieved = work[dom]["bytes"] / (per_kernel_ms[dom] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "rb_k_closest<exact>" if "closest" in work[dom]["name"] else "rb_k_any<exact>", "launch": work[dom]["name"],
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": work[dom]["bytes"], "avg_launch_ms": per_kernel_ms[dom],
+                    "per_ray": {"interior_nodes": work[dom]["interior"] / n, "triangle_tests": work[dom]["tris"] / n,
+                                "bytes": work[dom]["bytes"] / n},
+                    "note": "the 82 MB tree is L2-resident, so bytes/s above is served mostly by L2, not HBM; see profiles/"}
+        per_launch = {w["name"]: {"ms": per_kernel_ms[k], "mrays_s": n / (per_kernel_ms[k] * 1e-3) / 1e6,
+                                  "interior_per_ray": w["interior"] / n, "tri_tests_per_ray": w["tris"] / n,
+                                  "gbs": w["bytes"] / (per_kernel_ms[k] * 1e-3) / 1e9} for k, w in enumerate(work)}
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            kind, threads, closest, anyhit = cpu_tracer(pos, idx)
+            sets = cpu_sample_sets(pos, idx, closest)
+            cpu_step(sets, closest, anyhit)
+            tt, qq = 0.0, 0
+            while tt < 10.0:
+                t, q = cpu_step(sets, closest, anyhit)
+                tt += t
+                qq += q
+            cpu = {"value": qq / tt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": kind, "host_cpus": os.cpu_count(),
+                   "sample": "every %dth row of both ray sets (%d rays/set), closest+any, repeated for %.1f s" % (SAMPLE_ROW_STRIDE, sets[0].shape[0], tt)}
+        line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config_dict(world), "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                        "api": "rb_raycaster_intersect / rb_raycaster_intersect_any with pinned host buffers"},
+                "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu, "per_launch": per_launch}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

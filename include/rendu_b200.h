@@ -1,0 +1,281 @@
+/*
+ * rendu_b200.h — C ABI of the B200-native replacement for Rendu's offline path-tracer hot path.
+ *
+ * This is the drop-in boundary: the entry points below are exactly what a C++ `Raycaster` / `PathTracer`
+ * (reference: src/engine/raycaster/Raycaster.hpp, src/apps/pathtracer/PathTracer.hpp) forwards to once its CPU
+ * bodies are removed. Plain pointers and sizes only; no torch, glm or STL types cross this line.
+ *
+ * Conventions
+ *  - Every function returns rb_status (0 = RB_OK). On failure rb_last_error() gives a thread-local message.
+ *    The reference has no error channel on this path (it logs and returns, PathTracer.cpp:162-173); the C++
+ *    wrappers translate a non-zero status into Log::Error() and keep their void signatures.
+ *  - "host" entry points take host pointers and are blocking: they copy in, launch, copy out, and never keep a
+ *    caller pointer. "_device" entry points take device pointers plus a cudaStream_t (passed as void*) and only
+ *    enqueue work on that stream.
+ *  - There is no CPU fallback. Without a CUDA device every compute entry point returns RB_ERR_NO_DEVICE.
+ *  - Query functions are safe to call concurrently from several host threads on one handle (the reference calls
+ *    Raycaster::intersects from many threads, PathTracer.cpp:186,204); build / add / upload are not.
+ *  - Matrices are column-major 4x4 (glm::mat4 memory order). Vectors are tightly packed float[3].
+ */
+#ifndef RENDU_B200_H
+#define RENDU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define RB_API __declspec(dllexport)
+#else
+#define RB_API __attribute__((visibility("default")))
+#endif
+
+typedef int rb_status;
+enum {
+	RB_OK				= 0,
+	RB_ERR_INVALID		= 1, /* bad argument / call order */
+	RB_ERR_NO_DEVICE	= 2, /* no CUDA device: this library never computes on the CPU */
+	RB_ERR_CUDA			= 3, /* CUDA runtime failure, message in rb_last_error() */
+	RB_ERR_UNSUPPORTED	= 4
+};
+
+/* ------------------------------------------------------------------------------------------------ records
+ * The three records below are bit-compatible with the reference's own structs so that a C++ wrapper can pass
+ * `_hierarchy.data()` / `_triangles.data()` and receive `Raycaster::Hit` arrays without repacking. */
+
+/* Raycaster::Hit (Raycaster.hpp:16-42): {bool hit; float dist,u,v,w; ulong localId, meshId; ulong internalId}.
+ * Miss: hit=0, dist=FLT_MAX, everything else 0 (Raycaster.cpp:6-8). Hit: w = 1-u-v (Raycaster.cpp:10-12).
+ * internalId (always 0 in the reference) carries the index of the triangle in the raycaster's own order. */
+typedef struct rb_hit {
+	uint32_t hit; /* 0 or 1; byte 0 is the reference's bool */
+	float dist, u, v, w;
+	uint32_t _pad;
+	uint64_t localId;
+	uint64_t meshId;
+	uint64_t internalId;
+} rb_hit; /* 48 bytes */
+
+/* Raycaster::Node (Raycaster.hpp:127-132): leaf ? (left = first triangle, right = count) : child node ids. */
+typedef struct rb_node {
+	float bmin[3], bmax[3];
+	uint64_t left, right;
+	uint8_t leaf;
+	uint8_t _pad[7];
+} rb_node; /* 48 bytes */
+
+/* Raycaster::TriangleInfos (Raycaster.hpp:117-124). v0..v2 index the merged world-space vertex array. */
+typedef struct rb_tri {
+	float bmin[3], bmax[3];
+	uint64_t v0, v1, v2;
+	uint64_t localId;
+	uint32_t meshId;
+	uint32_t _pad;
+} rb_tri; /* 64 bytes */
+
+/* ------------------------------------------------------------------------------------------------ library */
+
+RB_API const char * rb_last_error(void);
+RB_API const char * rb_version(void);
+/* Number of visible CUDA devices (0 when none, never an error). */
+RB_API int rb_device_count(void);
+/* Select the CUDA device used by handles created afterwards on this host thread (default: current device). */
+RB_API rb_status rb_set_device(int device);
+
+/* ------------------------------------------------------------------------------------------------ raycaster
+ * Replaces class Raycaster (src/engine/raycaster/Raycaster.{hpp,cpp}). */
+
+typedef struct rb_raycaster rb_raycaster;
+
+typedef enum rb_build_mode {
+	/* Raycaster::updateHierarchy (Raycaster.cpp:54-142) restated on the host: same split rules, same libstdc++
+	 * partition / nth_element calls, hence the same node numbering and triangle order as the reference; then
+	 * uploaded. This is the mode in which hits are bit-identical to the reference. */
+	RB_BUILD_REFERENCE = 0,
+	/* GPU LBVH: Morton codes on triangle-box centroids, radix sort, Karras hierarchy, bottom-up AABB fit.
+	 * One tree over all meshes. Same closest hits except exact-distance ties / box-edge grazing (documented). */
+	RB_BUILD_LBVH = 1
+} rb_build_mode;
+
+typedef enum rb_trace_mode {
+	/* Reference traversal order (LIFO, right child first, roots in reverse) and the reference's arithmetic,
+	 * operation for operation, no FMA contraction: results are bit-identical to Raycaster::intersects. */
+	RB_TRACE_EXACT = 0,
+	/* Near-child-first ordered traversal on the same tree, same triangle test. Same hit except where the
+	 * reference's non-watertight box test makes the result depend on visiting order. */
+	RB_TRACE_ORDERED = 1
+} rb_trace_mode;
+
+RB_API rb_status rb_raycaster_create(rb_raycaster ** out);
+RB_API void rb_raycaster_destroy(rb_raycaster * rc);
+
+/* Raycaster::addMesh (Raycaster.cpp:14-52). positions: nverts*3 floats, indices: nindices (multiple of 3) u32,
+ * model: 16 floats or NULL for identity. Vertices are transformed once, as `vec3(model * vec4(v,1))`, unless the
+ * matrix is exactly identity. The mesh index (meshId of its triangles) is the number of earlier calls. */
+RB_API rb_status rb_raycaster_add_mesh(rb_raycaster * rc, const float * positions, size_t nverts, const uint32_t * indices, size_t nindices, const float * model);
+
+/* Raycaster::updateHierarchy (Raycaster.cpp:54-142). */
+RB_API rb_status rb_raycaster_build(rb_raycaster * rc, rb_build_mode mode);
+
+/* Upload path for a hierarchy built elsewhere (e.g. by the reference itself): arrays exactly as the reference
+ * holds them in _hierarchy / _triangles / _vertices / _meshCount (Raycaster.hpp:152-156). Replaces any geometry
+ * previously added. */
+RB_API rb_status rb_raycaster_upload_bvh(rb_raycaster * rc, const rb_node * nodes, size_t nnodes, const rb_tri * tris, size_t ntris, const float * vertices, size_t nverts, uint32_t mesh_count);
+
+/* Sizes of the host-format hierarchy: out[0]=nodes, out[1]=triangles, out[2]=vertices, out[3]=meshes, out[4]=max depth. */
+RB_API rb_status rb_raycaster_sizes(const rb_raycaster * rc, uint64_t out[5]);
+
+/* Read the hierarchy back in the reference's format (any pointer may be NULL). After an LBVH build this
+ * downloads the device tree; it is what RaycasterVisualisation (RaycasterVisualisation.cpp:15-30) needs. */
+RB_API rb_status rb_raycaster_download_bvh(const rb_raycaster * rc, rb_node * nodes, rb_tri * tris, float * vertices);
+
+/* Re-fit all boxes after the vertices moved (same topology): positions replace the merged world-space vertex
+ * array (nverts must match). Device-side bottom-up refit; the tree order is kept. */
+RB_API rb_status rb_raycaster_refit(rb_raycaster * rc, const float * world_positions, size_t nverts);
+
+RB_API rb_status rb_raycaster_set_trace_mode(rb_raycaster * rc, rb_trace_mode mode);
+
+/* Raycaster::intersects (Raycaster.cpp:144-185), batched: origins/directions are nrays*3 floats (directions need
+ * not be normalised, Intersection.cpp:3-5). Reference defaults: mini = 1e-4f, maxi = 1e8f (Raycaster.hpp:65). */
+RB_API rb_status rb_raycaster_intersect(const rb_raycaster * rc, const float * origins, const float * directions, float mini, float maxi, size_t nrays, rb_hit * out);
+
+/* Raycaster::intersectsAny (Raycaster.cpp:187-224), batched: out[i] = 1 if any triangle is hit. */
+RB_API rb_status rb_raycaster_intersect_any(const rb_raycaster * rc, const float * origins, const float * directions, float mini, float maxi, size_t nrays, uint8_t * out);
+
+/* Raycaster::visible (Raycaster.cpp:226-230), batched: out[i] = 1 if the segment p0[i]..p1[i] is free. */
+RB_API rb_status rb_raycaster_visible(const rb_raycaster * rc, const float * p0, const float * p1, size_t n, uint8_t * out);
+
+/* Device-pointer variants: enqueue on `stream` (a cudaStream_t), no host synchronisation. */
+RB_API rb_status rb_raycaster_intersect_device(const rb_raycaster * rc, const float * d_origins, const float * d_directions, float mini, float maxi, size_t nrays, rb_hit * d_out, void * stream);
+RB_API rb_status rb_raycaster_intersect_any_device(const rb_raycaster * rc, const float * d_origins, const float * d_directions, float mini, float maxi, size_t nrays, uint8_t * d_out, void * stream);
+
+/* Work counters of a batch, measured by an instrumented copy of the traversal kernel (not the timed one):
+ * counters[0] = interior nodes visited (both children box-tested, 64 B fetched each),
+ * counters[1] = triangle tests (48 B fetched each), counters[2] = root boxes tested, counters[3] = max stack depth.
+ * These define the algorithmic bytes per ray used for the roofline. any_hit selects the loop. */
+RB_API rb_status rb_raycaster_count_work_device(const rb_raycaster * rc, const float * d_origins, const float * d_directions, float mini, float maxi, size_t nrays, int any_hit, uint64_t counters[4], void * stream);
+
+/* Kernel launches issued by this handle so far (for bench.py's gpu_launches). */
+RB_API uint64_t rb_raycaster_launch_count(const rb_raycaster * rc);
+
+/* ------------------------------------------------------------------------------------------------ scene
+ * Read-only data PathTracer::render touches: Scene::objects / lights / background, Object::mesh /
+ * model / material / useTexCoords, Material::textures / type / masked, Mesh attribute arrays. Flattened by the
+ * caller into plain arrays; copied to the device at rb_scene_commit. */
+
+typedef struct rb_scene rb_scene;
+
+typedef enum rb_light_kind { RB_LIGHT_POINT = 0, RB_LIGHT_SPOT = 1, RB_LIGHT_DIRECTIONAL = 2 } rb_light_kind;
+/* Scene::Background (src/engine/scene/Scene.hpp): COLOR, IMAGE, SKYBOX, ATMOSPHERE. */
+typedef enum rb_background_mode { RB_BG_COLOR = 0, RB_BG_IMAGE = 1, RB_BG_SKYBOX = 2, RB_BG_ATMOSPHERE = 3 } rb_background_mode;
+
+typedef struct rb_object_desc {
+	const float * positions;  /* nverts*3, model space (Mesh::positions) */
+	const float * normals;	  /* nverts*3 */
+	const float * tangents;	  /* nverts*3 */
+	const float * bitangents; /* nverts*3 */
+	const float * texcoords;  /* nverts*2 or NULL */
+	size_t nverts;
+	const uint32_t * indices; /* Mesh::indices */
+	size_t nindices;
+	float model[16];		  /* Object::model() */
+	int32_t tex_albedo;		  /* Material::textures()[0]: albedo / emissive colour + alpha */
+	int32_t tex_normal;		  /* [1]: normal map */
+	int32_t tex_rmao;		  /* [2]: roughness, metalness, ao */
+	uint32_t emissive;		  /* Material::type() == Emissive */
+	uint32_t masked;		  /* Material::masked() */
+	uint32_t use_texcoords;	  /* Object::useTexCoords() */
+} rb_object_desc;
+
+typedef struct rb_light_desc {
+	uint32_t kind;		   /* rb_light_kind */
+	uint32_t casts_shadow; /* Light::castsShadow() */
+	float intensity[3];	   /* Light::intensity() */
+	float position[3];	   /* point, spot */
+	float direction[3];	   /* spot, directional (normalised as the reference stores it) */
+	float radius;		   /* point, spot */
+	float inner_angle, outer_angle; /* spot: SpotLight::angles() (half-angles, radians) */
+} rb_light_desc;
+
+RB_API rb_status rb_scene_create(rb_scene ** out);
+RB_API void rb_scene_destroy(rb_scene * sc);
+/* Image as the reference holds it on the CPU: float pixels, row-major, `components` (3 or 4) per texel. */
+RB_API rb_status rb_scene_add_texture(rb_scene * sc, const float * pixels, uint32_t width, uint32_t height, uint32_t components, int32_t * out_id);
+/* Objects must be added in scene->objects order (PathTracer.cpp:13-18): the call index is the meshId. */
+RB_API rb_status rb_scene_add_object(rb_scene * sc, const rb_object_desc * desc);
+RB_API rb_status rb_scene_add_light(rb_scene * sc, const rb_light_desc * desc);
+/* color: background Material::parameters()[0] (COLOR). textures: 1 id (IMAGE) or 6 ids px,nx,py,ny,pz,nz (SKYBOX).
+ * sun_direction: Sky::direction() (ATMOSPHERE). sky_lut: id of the "scattering-precomputed" table or -1. */
+RB_API rb_status rb_scene_set_background(rb_scene * sc, uint32_t mode, const float color[3], const int32_t * textures, uint32_t ntextures, const float sun_direction[3], int32_t sky_lut);
+/* Upload everything and build the raycaster (addMesh per object + updateHierarchy, PathTracer.cpp:11-21). */
+RB_API rb_status rb_scene_commit(rb_scene * sc, rb_build_mode mode);
+/* The scene's raycaster (owned by the scene) — PathTracer::raycaster(). */
+RB_API rb_raycaster * rb_scene_raycaster(rb_scene * sc);
+
+/* ------------------------------------------------------------------------------------------------ path tracer
+ * Replaces PathTracer::render (src/apps/pathtracer/PathTracer.cpp:159-299). */
+
+typedef struct rb_pathtracer rb_pathtracer;
+
+/* What render() derives from the Camera on the host (PathTracer.cpp:177,197; Camera.cpp:42-49). */
+typedef struct rb_camera {
+	float eye[3];	 /* Camera::position() */
+	float corner[3]; /* Camera::pixelShifts */
+	float dx[3];
+	float dy[3];
+} rb_camera;
+
+typedef struct rb_render_opts {
+	uint64_t seed;		 /* counter-based RNG key; same seed => same image, whatever the GPU count */
+	/* Tile split: only rows y with (y / tile_rows) % tile_count == tile_index are rendered (others untouched).
+	 * tile_count <= 1 renders everything. */
+	uint32_t tile_rows, tile_index, tile_count;
+	/* Sample split: only stratification cells sid with sid % sample_count == sample_index are traced; the sum is
+	 * still normalised by the full `samples`, so per-GPU images add up to the full estimate. */
+	uint32_t sample_index, sample_count;
+	uint32_t trace_mode; /* rb_trace_mode used for primary, bounce and shadow rays */
+	uint32_t max_paths_in_flight; /* 0 = default; bounds the wavefront buffers */
+	uint32_t _reserved[5];
+} rb_render_opts;
+
+typedef struct rb_render_stats {
+	uint64_t rays_closest; /* primary + bounce queries (Raycaster::intersects from render) */
+	uint64_t rays_shadow;  /* queries issued by checkVisibility (PathTracer.cpp:128) */
+	uint64_t samples;	   /* pixel samples traced */
+	uint64_t shaded_hits;
+	uint64_t kernel_launches;
+	double device_seconds; /* CUDA-event time of the device work of the last render */
+} rb_render_stats;
+
+RB_API rb_status rb_pathtracer_create(rb_scene * scene, rb_pathtracer ** out);
+RB_API void rb_pathtracer_destroy(rb_pathtracer * pt);
+
+/* PathTracer::render: `pixels` is the caller's Image::pixels (width*height*components floats, components >= 3).
+ * As in the reference the result is accumulated into it (`+=` then `/= samples`, PathTracer.cpp:288-292), so the
+ * caller zero-fills; samples is rounded to the nearest power of two (PathTracer.cpp:169-173). opts may be NULL. */
+RB_API rb_status rb_pathtracer_render(rb_pathtracer * pt, const rb_camera * camera, uint32_t width, uint32_t height, uint32_t samples, uint32_t depth, uint32_t components, float * pixels, const rb_render_opts * opts);
+
+/* Device variant for multi-GPU plumbing: writes per-pixel SUMS of clamped sample radiance (not yet divided) into
+ * d_sum (width*height*3 floats, overwritten) on `stream`; rb_pathtracer_resolve_device then applies the reference's
+ * `pixels = (pixels + sum) / samples` to a device image. Between the two a caller may reduce d_sum across ranks. */
+RB_API rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_camera * camera, uint32_t width, uint32_t height, uint32_t samples, uint32_t depth, float * d_sum, const rb_render_opts * opts, void * stream);
+RB_API rb_status rb_pathtracer_resolve_device(rb_pathtracer * pt, const float * d_sum, uint32_t width, uint32_t height, uint32_t samples, uint32_t components, float * d_pixels, const rb_render_opts * opts, void * stream);
+RB_API rb_status rb_pathtracer_stats(const rb_pathtracer * pt, rb_render_stats * out);
+
+/* ------------------------------------------------------------------------------------------------ device KATs
+ * Known-answer hooks: evaluate the device versions of the reference's scalar building blocks on arrays (host
+ * pointers). Used only by the parity tests; they launch real kernels and have no CPU path. */
+RB_API rb_status rb_kat_ggx_eval(const float * wo, const float * base, const float * rough, const float * metal, const float * wi, size_t n, float * out3);
+RB_API rb_status rb_kat_ggx_sample(const float * wo, const float * base, const float * rough, const float * metal, const float * u3, size_t n, float * out_wi3, float * out_eval3);
+RB_API rb_status rb_kat_image_sample(const float * rgba, uint32_t width, uint32_t height, const float * uv, size_t n, float * out4);
+RB_API rb_status rb_kat_cubemap_sample(const float * faces, uint32_t width, uint32_t height, const float * dirs, size_t n, float * out3);
+RB_API rb_status rb_kat_light_sample(const rb_light_desc * light, const float * positions, size_t n, float * out5);
+RB_API rb_status rb_kat_sky_eval(const float * lut_rgba, uint32_t width, uint32_t height, const float * origins, const float * dirs, const float sun[3], size_t n, float * out3);
+RB_API rb_status rb_kat_box_test(const float * origins, const float * dirs, const float * boxes6, float mini, float maxi, size_t n, uint8_t * out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RENDU_B200_H */

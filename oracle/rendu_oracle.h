@@ -1,0 +1,60 @@
+/* TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+ * rendu_oracle: a plain-C CPU restatement of the reference's path-tracer hot path (kosua20/Rendu), used ONLY as the
+ * checker by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs. Nothing under
+ * rendu_b200/ includes, links or loads it. Every function cites the reference file:line it follows.
+ *
+ * Pinning: the reference ships no tests, golden vectors or fixtures for this path, so the
+ * oracle is pinned against the reference ITSELF: oracle/_ref/librendu_ref.so is the reference's own translation
+ * units compiled unmodified (oracle/build_ref.sh); tests/test_oracle_vs_reference.py checks every function here
+ * against it bit for bit (rays, hierarchy, scalar kernels, and whole renders with the same mt19937 stream), and
+ * tests/golden/ holds vectors generated from it (tests/golden/make_golden.py) for machines without /root/reference.
+ */
+#ifndef RENDU_ORACLE_H
+#define RENDU_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Same memory layout as the reference's Raycaster::Node / TriangleInfos (Raycaster.hpp:117-132). */
+typedef struct { float bmin[3], bmax[3]; uint64_t left, right; uint8_t leaf; uint8_t pad[7]; } orc_node;
+typedef struct { float bmin[3], bmax[3]; uint64_t v0, v1, v2, localId; uint32_t meshId; uint32_t pad; } orc_tri;
+/* Raycaster::Hit (Raycaster.hpp:16-42). */
+typedef struct { uint32_t hit; float dist, u, v, w; uint32_t pad; uint64_t localId, meshId, internalId; } orc_hit;
+
+typedef struct {
+	const orc_node * nodes; size_t nnodes;
+	const orc_tri * tris; size_t ntris;
+	const float * verts; size_t nverts;
+	uint32_t meshCount;
+} orc_bvh;
+
+/* Ray::Ray (Intersection.cpp:3-5): out9 = pos, dir, invdir. */
+void orc_ray(const float * origin, const float * direction, float * out9);
+/* Intersection::box (Intersection.cpp:22-32). */
+int orc_box(const float * ray9, const float * bmin, const float * bmax, float mini, float maxi);
+/* Raycaster::intersects(ray, tri, mini, maxi) (Raycaster.cpp:232-262). Returns 1 on hit and fills t,u,v. */
+int orc_tri_test(const orc_bvh * b, const float * ray9, const orc_tri * tri, float mini, float maxi, float * t, float * u, float * v);
+/* Raycaster::intersects (Raycaster.cpp:144-185). */
+orc_hit orc_intersect(const orc_bvh * b, const float * origin, const float * direction, float mini, float maxi);
+/* Raycaster::intersectsAny (Raycaster.cpp:187-224). */
+int orc_intersect_any(const orc_bvh * b, const float * origin, const float * direction, float mini, float maxi);
+/* Raycaster::visible (Raycaster.cpp:226-230). */
+int orc_visible(const orc_bvh * b, const float * p0, const float * p1);
+/* Batches, optionally over `threads` pthreads with static contiguous blocks (System.hpp:72-104). */
+void orc_intersect_batch(const orc_bvh * b, const float * org, const float * dir, float mini, float maxi, size_t n, int threads, orc_hit * out);
+void orc_intersect_any_batch(const orc_bvh * b, const float * org, const float * dir, float mini, float maxi, size_t n, int threads, uint8_t * out);
+
+/* Raycaster::addMesh (Raycaster.cpp:14-52) on plain arrays: appends to caller-sized outputs; returns triangles added. */
+size_t orc_add_mesh(const float * positions, size_t nverts, const uint32_t * indices, size_t nindices, const float * model16,
+	float * vertsOut, size_t vertOffset, orc_tri * trisOut, uint32_t meshId);
+/* Raycaster::updateHierarchy (Raycaster.cpp:54-142); C++ because the tree is defined by libstdc++'s std::partition /
+ * std::nth_element (rendu_oracle_build.cpp). tris is reordered in place; nodesOut must hold 2*ntris+meshCount entries;
+ * meshFirst/meshTris give each mesh's triangle range. Returns the node count. */
+size_t orc_build(orc_tri * tris, size_t ntris, const uint64_t * meshFirst, const uint64_t * meshTris, uint32_t meshCount, orc_node * nodesOut);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

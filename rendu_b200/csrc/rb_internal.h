@@ -1,0 +1,86 @@
+// rb_internal.h — handle layouts and helpers shared by the translation units of librendu_b200.so.
+#pragma once
+#include "../../include/rendu_b200.h"
+#include "rb_types.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+// ---------------------------------------------------------------- errors
+void rb_set_error(const char * fmt, ...);
+rb_status rb_fail(rb_status code, const char * fmt, ...);
+bool rb_have_device();
+
+#define RB_CUDA(call)                                                                                              \
+	do {                                                                                                           \
+		cudaError_t _e = (call);                                                                                   \
+		if(_e != cudaSuccess) {                                                                                    \
+			return rb_fail(RB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+		}                                                                                                          \
+	} while(0)
+
+#define RB_REQUIRE_DEVICE()                                                                                     \
+	do {                                                                                                        \
+		if(!rb_have_device()) return rb_fail(RB_ERR_NO_DEVICE, "no CUDA device available (no CPU fallback)");     \
+	} while(0)
+
+// ---------------------------------------------------------------- raycaster handle
+struct rb_raycaster {
+	// Host mirror in the reference's own format (kept so RaycasterVisualisation-style consumers can read it back).
+	std::vector<float> verts; // merged world-space vertices, xyz
+	std::vector<rb_tri> tris;
+	std::vector<rb_node> nodes;
+	uint32_t meshCount = 0;
+	std::vector<uint64_t> meshFirst, meshTris; // per mesh: first triangle and triangle count (stable across rebuilds)
+	int maxDepth	   = 0; // max number of interior nodes on a root-to-leaf path
+	bool built		   = false;
+	bool hostMirrorStale = false; // device tree newer than the host mirror (after LBVH build / refit)
+
+	// Device tree.
+	int device		  = 0;
+	float4 * d_nodes  = nullptr;
+	float4 * d_tris	  = nullptr;
+	float4 * d_roots  = nullptr;
+	size_t nInterior  = 0;
+	size_t nTris	  = 0;
+	RbDeviceBvh dev	  = {};
+	// LBVH bookkeeping (device): parent links and leaf->node map for refits, world-space vertices, vertex ids.
+	int * d_parent	   = nullptr;
+	float * d_verts	   = nullptr;
+	uint32_t * d_triVerts = nullptr; // 3 vertex ids per triangle in hierarchy order
+	size_t nVerts	   = 0;
+	int buildMode	   = RB_BUILD_REFERENCE;
+
+	int traceMode = RB_TRACE_EXACT;
+	mutable std::atomic<uint64_t> launches{0};
+};
+
+// Host builder mirroring Raycaster::updateHierarchy (rb_bvh_host.cpp).
+void rb_host_build_reference(rb_raycaster * rc);
+// Depth of the host-format tree (max interior nodes on a path) or -1 if malformed.
+int rb_host_tree_depth(const rb_raycaster * rc, std::string * why);
+
+// Flatten the host-format tree into the device layout (host arrays of float4 packed as floats).
+struct RbFlatBvh {
+	std::vector<float> nodes; // 16 floats per interior node
+	std::vector<float> tris;  // 12 floats per triangle
+	std::vector<float> roots; // 8 floats per root
+	std::vector<uint32_t> triVerts;
+	std::vector<int> parent;  // parent interior index per interior node (-1 for roots' children handled on device)
+};
+bool rb_host_flatten(const rb_raycaster * rc, RbFlatBvh & out, std::string * why);
+
+// Upload a flattened tree into the handle (rb_raycaster.cu).
+rb_status rb_raycaster_upload_flat(rb_raycaster * rc, const RbFlatBvh & flat);
+void rb_raycaster_free_device(rb_raycaster * rc);
+
+// GPU LBVH build / refit (rb_lbvh.cu).
+rb_status rb_lbvh_build(rb_raycaster * rc);
+rb_status rb_lbvh_refit(rb_raycaster * rc, const float * worldPositions, size_t nverts);
+rb_status rb_lbvh_download(const rb_raycaster * rc, rb_node * nodes, rb_tri * tris, float * verts);
+
+// Launch helpers used by the path tracer (rb_raycaster.cu).
+size_t rb_trace_smem_bytes(const rb_raycaster * rc, int blockThreads);

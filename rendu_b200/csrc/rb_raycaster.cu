@@ -1,0 +1,598 @@
+// rb_raycaster.cu — the Raycaster half of the C ABI (include/rendu_b200.h) and its sm_100a kernels.
+// Reference behaviour: src/engine/raycaster/Raycaster.cpp (addMesh :14-52, updateHierarchy :54-142,
+// intersects :144-185, intersectsAny :187-224, visible :226-230).
+#include "rb_internal.h"
+#include "rb_trace.cuh"
+
+#include <cstring>
+#include <mutex>
+
+// ---------------------------------------------------------------- error plumbing
+static thread_local std::string g_lastError;
+
+void rb_set_error(const char * fmt, ...) {
+	char buf[1024];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	g_lastError = buf;
+}
+
+rb_status rb_fail(rb_status code, const char * fmt, ...) {
+	char buf[1024];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	g_lastError = buf;
+	return code;
+}
+
+bool rb_have_device() {
+	static int count = -1;
+	static std::once_flag once;
+	std::call_once(once, [] {
+		int n = 0;
+		if(cudaGetDeviceCount(&n) != cudaSuccess) {
+			cudaGetLastError();
+			n = 0;
+		}
+		count = n;
+	});
+	return count > 0;
+}
+
+extern "C" const char * rb_last_error(void) {
+	return g_lastError.c_str();
+}
+
+extern "C" const char * rb_version(void) {
+	return "rendu_b200 0.1 (sm_100a)";
+}
+
+extern "C" int rb_device_count(void) {
+	if(!rb_have_device()) return 0;
+	int n = 0;
+	cudaGetDeviceCount(&n);
+	return n;
+}
+
+extern "C" rb_status rb_set_device(int device) {
+	RB_REQUIRE_DEVICE();
+	RB_CUDA(cudaSetDevice(device));
+	return RB_OK;
+}
+
+// ---------------------------------------------------------------- kernels
+
+#define RB_TRACE_BLOCK 128
+
+// Reads ray i from tightly packed float3 arrays.
+RB_D void rb_load_ray(const float * org, const float * dir, size_t i, V3 & o, V3 & d) {
+	o = V3{__ldg(org + 3 * i), __ldg(org + 3 * i + 1), __ldg(org + 3 * i + 2)};
+	d = V3{__ldg(dir + 3 * i), __ldg(dir + 3 * i + 1), __ldg(dir + 3 * i + 2)};
+}
+
+// Raycaster::Hit constructors (Raycaster.cpp:6-12) written as three 16-byte stores.
+RB_D void rb_store_hit(rb_hit * out, size_t i, const RbDeviceBvh & bvh, const RbHitRec & h) {
+	uint4 a, b, c;
+	if(h.tri >= 0) {
+		const float4 t0 = rb_ldg4(bvh.tris + 3 * (size_t)h.tri);
+		const float4 t1 = rb_ldg4(bvh.tris + 3 * (size_t)h.tri + 1);
+		const float w	= 1.0f - h.u - h.v;
+		a = make_uint4(1u, __float_as_uint(h.t), __float_as_uint(h.u), __float_as_uint(h.v));
+		b = make_uint4(__float_as_uint(w), 0u, __float_as_uint(t0.w), 0u);
+		c = make_uint4(__float_as_uint(t1.w), 0u, (unsigned int)h.tri, 0u);
+	} else {
+		a = make_uint4(0u, __float_as_uint(FLT_MAX), 0u, 0u);
+		b = make_uint4(0u, 0u, 0u, 0u);
+		c = make_uint4(0u, 0u, 0u, 0u);
+	}
+	uint4 * o = reinterpret_cast<uint4 *>(out + i);
+	o[0] = a;
+	o[1] = b;
+	o[2] = c;
+}
+
+// One ray per thread. The traversal stack lives in shared memory, one column per thread (bank-conflict free).
+template<bool ORDERED>
+__global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_closest(RbDeviceBvh bvh, const float * __restrict__ org, const float * __restrict__ dir, float mini, float maxi, size_t n, rb_hit * __restrict__ out) {
+	extern __shared__ int s_stack[];
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	V3 o, d;
+	rb_load_ray(org, dir, i, o, d);
+	const RbRay ray = rb_make_ray(o, d);
+	RbHitRec best;
+	if(ORDERED) rb_trace_ordered<false, false>(bvh, ray, mini, maxi, s_stack + threadIdx.x, blockDim.x, best, nullptr);
+	else rb_trace_exact<false, false>(bvh, ray, mini, maxi, s_stack + threadIdx.x, blockDim.x, best, nullptr);
+	rb_store_hit(out, i, bvh, best);
+}
+
+template<bool ORDERED>
+__global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_any(RbDeviceBvh bvh, const float * __restrict__ org, const float * __restrict__ dir, float mini, float maxi, size_t n, uint8_t * __restrict__ out) {
+	extern __shared__ int s_stack[];
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	V3 o, d;
+	rb_load_ray(org, dir, i, o, d);
+	const RbRay ray = rb_make_ray(o, d);
+	RbHitRec best;
+	bool any;
+	if(ORDERED) any = rb_trace_ordered<true, false>(bvh, ray, mini, maxi, s_stack + threadIdx.x, blockDim.x, best, nullptr);
+	else any = rb_trace_exact<true, false>(bvh, ray, mini, maxi, s_stack + threadIdx.x, blockDim.x, best, nullptr);
+	out[i] = any ? 1 : 0;
+}
+
+// Raycaster::visible (Raycaster.cpp:226-230): !intersectsAny(p0, p1-p0, 1e-4, length(p1-p0)).
+__global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_visible(RbDeviceBvh bvh, const float * __restrict__ p0, const float * __restrict__ p1, size_t n, uint8_t * __restrict__ out) {
+	extern __shared__ int s_stack[];
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	V3 a, b;
+	rb_load_ray(p0, p1, i, a, b);
+	const V3 direction = b - a;
+	const float maxi   = length3(direction);
+	const RbRay ray	   = rb_make_ray(a, direction);
+	RbHitRec best;
+	const bool any = rb_trace_exact<true, false>(bvh, ray, 0.0001f, maxi, s_stack + threadIdx.x, blockDim.x, best, nullptr);
+	out[i] = any ? 0 : 1;
+}
+
+// Instrumented copy: same loops, counts the work that defines the algorithmic bytes per ray.
+template<bool ANY, bool ORDERED>
+__global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_count(RbDeviceBvh bvh, const float * __restrict__ org, const float * __restrict__ dir, float mini, float maxi, size_t n, unsigned long long * __restrict__ counters) {
+	extern __shared__ int s_stack[];
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	RbWork w = {0u, 0u, 0u, 0u};
+	if(i < n) {
+		V3 o, d;
+		rb_load_ray(org, dir, i, o, d);
+		const RbRay ray = rb_make_ray(o, d);
+		RbHitRec best;
+		if(ORDERED) rb_trace_ordered<ANY, true>(bvh, ray, mini, maxi, s_stack + threadIdx.x, blockDim.x, best, &w);
+		else rb_trace_exact<ANY, true>(bvh, ray, mini, maxi, s_stack + threadIdx.x, blockDim.x, best, &w);
+	}
+	// Warp-level reduction, one atomic per warp and counter.
+	unsigned int a = w.interior, b = w.tris, c = w.roots, m = w.maxStack;
+	for(int off = 16; off > 0; off >>= 1) {
+		a += __shfl_down_sync(0xffffffffu, a, off);
+		b += __shfl_down_sync(0xffffffffu, b, off);
+		c += __shfl_down_sync(0xffffffffu, c, off);
+		m = max(m, __shfl_down_sync(0xffffffffu, m, off));
+	}
+	if((threadIdx.x & 31) == 0) {
+		atomicAdd(counters + 0, (unsigned long long)a);
+		atomicAdd(counters + 1, (unsigned long long)b);
+		atomicAdd(counters + 2, (unsigned long long)c);
+		atomicMax(counters + 3, (unsigned long long)m);
+	}
+}
+
+// ---------------------------------------------------------------- handle management
+
+size_t rb_trace_smem_bytes(const rb_raycaster * rc, int blockThreads) {
+	const int depth = rc->dev.stackDepth > 0 ? rc->dev.stackDepth : 1;
+	return size_t(depth) * size_t(blockThreads) * sizeof(int);
+}
+
+void rb_raycaster_free_device(rb_raycaster * rc) {
+	if(!rb_have_device()) return;
+	cudaSetDevice(rc->device);
+	cudaFree(rc->d_nodes);
+	cudaFree(rc->d_tris);
+	cudaFree(rc->d_roots);
+	cudaFree(rc->d_parent);
+	cudaFree(rc->d_verts);
+	cudaFree(rc->d_triVerts);
+	rc->d_nodes = rc->d_tris = rc->d_roots = nullptr;
+	rc->d_parent   = nullptr;
+	rc->d_verts	   = nullptr;
+	rc->d_triVerts = nullptr;
+	rc->dev		   = RbDeviceBvh{};
+}
+
+rb_status rb_raycaster_upload_flat(rb_raycaster * rc, const RbFlatBvh & flat) {
+	RB_REQUIRE_DEVICE();
+	rb_raycaster_free_device(rc);
+	RB_CUDA(cudaGetDevice(&rc->device));
+	rc->nInterior = flat.nodes.size() / 16;
+	rc->nTris	  = flat.tris.size() / 12;
+	rc->nVerts	  = rc->verts.size() / 3;
+	// Allocations are padded so that empty arrays still give valid pointers.
+	RB_CUDA(cudaMalloc(&rc->d_nodes, flat.nodes.size() * sizeof(float) + 64));
+	RB_CUDA(cudaMalloc(&rc->d_tris, flat.tris.size() * sizeof(float) + 64));
+	RB_CUDA(cudaMalloc(&rc->d_roots, flat.roots.size() * sizeof(float) + 64));
+	RB_CUDA(cudaMalloc(&rc->d_parent, flat.parent.size() * sizeof(int) + 64));
+	RB_CUDA(cudaMalloc(&rc->d_verts, rc->verts.size() * sizeof(float) + 64));
+	RB_CUDA(cudaMalloc(&rc->d_triVerts, flat.triVerts.size() * sizeof(uint32_t) + 64));
+	RB_CUDA(cudaMemcpy(rc->d_nodes, flat.nodes.data(), flat.nodes.size() * sizeof(float), cudaMemcpyHostToDevice));
+	RB_CUDA(cudaMemcpy(rc->d_tris, flat.tris.data(), flat.tris.size() * sizeof(float), cudaMemcpyHostToDevice));
+	RB_CUDA(cudaMemcpy(rc->d_roots, flat.roots.data(), flat.roots.size() * sizeof(float), cudaMemcpyHostToDevice));
+	RB_CUDA(cudaMemcpy(rc->d_parent, flat.parent.data(), flat.parent.size() * sizeof(int), cudaMemcpyHostToDevice));
+	RB_CUDA(cudaMemcpy(rc->d_verts, rc->verts.data(), rc->verts.size() * sizeof(float), cudaMemcpyHostToDevice));
+	RB_CUDA(cudaMemcpy(rc->d_triVerts, flat.triVerts.data(), flat.triVerts.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+	rc->dev.nodes	   = rc->d_nodes;
+	rc->dev.tris	   = rc->d_tris;
+	rc->dev.roots	   = rc->d_roots;
+	rc->dev.nroots	   = int(rc->meshCount);
+	rc->dev.stackDepth = rc->maxDepth + 1;
+	rc->built		   = true;
+	rc->hostMirrorStale = false;
+	return RB_OK;
+}
+
+extern "C" rb_status rb_raycaster_create(rb_raycaster ** out) {
+	if(!out) return rb_fail(RB_ERR_INVALID, "rb_raycaster_create: null output");
+	*out = new rb_raycaster();
+	return RB_OK;
+}
+
+extern "C" void rb_raycaster_destroy(rb_raycaster * rc) {
+	if(!rc) return;
+	rb_raycaster_free_device(rc);
+	delete rc;
+}
+
+extern "C" rb_status rb_raycaster_add_mesh(rb_raycaster * rc, const float * positions, size_t nverts, const uint32_t * indices, size_t nindices, const float * model) {
+	if(!rc || (!positions && nverts) || (!indices && nindices)) return rb_fail(RB_ERR_INVALID, "rb_raycaster_add_mesh: null argument");
+	static const float identity[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+	// `model != glm::mat4(1.0f)` (Raycaster.cpp:22): element-wise float comparison.
+	bool isIdentity = true;
+	if(model) {
+		for(int k = 0; k < 16; ++k) isIdentity = isIdentity && (model[k] == identity[k]);
+	}
+	const size_t indexOffset = rc->verts.size() / 3;
+	rc->verts.resize((indexOffset + nverts) * 3);
+	float * dst = rc->verts.data() + indexOffset * 3;
+	if(isIdentity) {
+		if(nverts) std::memcpy(dst, positions, nverts * 3 * sizeof(float));
+	} else {
+		// vec3(model * vec4(v, 1)): glm evaluates (m0*x + m1*y) + (m2*z + m3*w) per component (type_mat4x4.inl:561-571).
+		const float * m = model;
+		for(size_t v = 0; v < nverts; ++v) {
+			const float x = positions[3 * v], y = positions[3 * v + 1], z = positions[3 * v + 2];
+			for(int r = 0; r < 3; ++r) {
+				const float a0 = m[0 + r] * x + m[4 + r] * y;
+				const float a1 = m[8 + r] * z + m[12 + r] * 1.0f;
+				dst[3 * v + r] = a0 + a1;
+			}
+		}
+	}
+	const size_t ntri		  = nindices / 3;
+	const size_t startTriangle = rc->tris.size();
+	rc->tris.resize(startTriangle + ntri);
+	const size_t nvTotal = rc->verts.size() / 3;
+	for(size_t t = 0; t < ntri; ++t) {
+		rb_tri & ti = rc->tris[startTriangle + t];
+		std::memset(&ti, 0, sizeof(ti));
+		ti.v0	   = indexOffset + indices[3 * t + 0];
+		ti.v1	   = indexOffset + indices[3 * t + 1];
+		ti.v2	   = indexOffset + indices[3 * t + 2];
+		ti.localId = 3 * t;
+		ti.meshId  = rc->meshCount;
+		if(ti.v0 >= nvTotal || ti.v1 >= nvTotal || ti.v2 >= nvTotal) {
+			rc->tris.resize(startTriangle);
+			rc->verts.resize(indexOffset * 3);
+			return rb_fail(RB_ERR_INVALID, "rb_raycaster_add_mesh: index out of range in triangle %zu", t);
+		}
+		const float * a = rc->verts.data() + 3 * ti.v0;
+		const float * b = rc->verts.data() + 3 * ti.v1;
+		const float * c = rc->verts.data() + 3 * ti.v2;
+		// BoundingBox(v0,v1,v2) (Bounds.cpp:12-15): min(min(v0,v1),v2), glm::min(x,y) = (y<x)?y:x.
+		for(int k = 0; k < 3; ++k) {
+			const float mn01 = (b[k] < a[k]) ? b[k] : a[k];
+			const float mx01 = (a[k] < b[k]) ? b[k] : a[k];
+			ti.bmin[k]		 = (c[k] < mn01) ? c[k] : mn01;
+			ti.bmax[k]		 = (mx01 < c[k]) ? c[k] : mx01;
+		}
+	}
+	// One root per mesh, appended after the existing roots: a rebuild restarts from these (Raycaster.cpp:43-46).
+	rc->meshFirst.push_back(startTriangle);
+	rc->meshTris.push_back(ntri);
+	rc->meshCount++;
+	rc->built = false;
+	return RB_OK;
+}
+
+extern "C" rb_status rb_raycaster_build(rb_raycaster * rc, rb_build_mode mode) {
+	if(!rc) return rb_fail(RB_ERR_INVALID, "rb_raycaster_build: null handle");
+	rc->buildMode = mode;
+	if(mode == RB_BUILD_REFERENCE) {
+		// The host mirror is built first so that it can be read back (rb_raycaster_download_bvh) even on a machine
+		// without a GPU; tracing still needs the device copy.
+		rb_host_build_reference(rc);
+		RB_REQUIRE_DEVICE();
+		RbFlatBvh flat;
+		std::string why;
+		if(!rb_host_flatten(rc, flat, &why)) return rb_fail(RB_ERR_INVALID, "rb_raycaster_build: %s", why.c_str());
+		return rb_raycaster_upload_flat(rc, flat);
+	}
+	if(mode == RB_BUILD_LBVH) {
+		RB_REQUIRE_DEVICE();
+		return rb_lbvh_build(rc);
+	}
+	return rb_fail(RB_ERR_INVALID, "rb_raycaster_build: unknown mode %d", int(mode));
+}
+
+extern "C" rb_status rb_raycaster_upload_bvh(rb_raycaster * rc, const rb_node * nodes, size_t nnodes, const rb_tri * tris, size_t ntris, const float * vertices, size_t nverts, uint32_t mesh_count) {
+	if(!rc || (!nodes && nnodes) || (!tris && ntris) || (!vertices && nverts)) return rb_fail(RB_ERR_INVALID, "rb_raycaster_upload_bvh: null argument");
+	RB_REQUIRE_DEVICE();
+	rc->nodes.assign(nodes, nodes + nnodes);
+	rc->meshFirst.clear();
+	rc->meshTris.clear();
+	rc->tris.assign(tris, tris + ntris);
+	rc->verts.assign(vertices, vertices + nverts * 3);
+	rc->meshCount = mesh_count;
+	rc->buildMode = RB_BUILD_REFERENCE;
+	std::string why;
+	const int depth = rb_host_tree_depth(rc, &why);
+	if(depth < 0) return rb_fail(RB_ERR_INVALID, "rb_raycaster_upload_bvh: %s", why.c_str());
+	rc->maxDepth = depth;
+	RbFlatBvh flat;
+	if(!rb_host_flatten(rc, flat, &why)) return rb_fail(RB_ERR_INVALID, "rb_raycaster_upload_bvh: %s", why.c_str());
+	return rb_raycaster_upload_flat(rc, flat);
+}
+
+extern "C" rb_status rb_raycaster_sizes(const rb_raycaster * rc, uint64_t out[5]) {
+	if(!rc || !out) return rb_fail(RB_ERR_INVALID, "rb_raycaster_sizes: null argument");
+	if(rc->buildMode == RB_BUILD_LBVH && rc->built) {
+		const uint64_t nt = rc->nTris;
+		out[0] = nt ? 2 * nt - 1 : 0;
+	} else {
+		out[0] = rc->nodes.size();
+	}
+	out[1] = rc->tris.size();
+	out[2] = rc->verts.size() / 3;
+	out[3] = rc->meshCount;
+	out[4] = uint64_t(rc->maxDepth);
+	return RB_OK;
+}
+
+extern "C" rb_status rb_raycaster_download_bvh(const rb_raycaster * rc, rb_node * nodes, rb_tri * tris, float * vertices) {
+	if(!rc) return rb_fail(RB_ERR_INVALID, "rb_raycaster_download_bvh: null handle");
+	if(rc->built && (rc->buildMode == RB_BUILD_LBVH || rc->hostMirrorStale)) {
+		return rb_lbvh_download(rc, nodes, tris, vertices);
+	}
+	if(nodes && !rc->nodes.empty()) std::memcpy(nodes, rc->nodes.data(), rc->nodes.size() * sizeof(rb_node));
+	if(tris && !rc->tris.empty()) std::memcpy(tris, rc->tris.data(), rc->tris.size() * sizeof(rb_tri));
+	if(vertices && !rc->verts.empty()) std::memcpy(vertices, rc->verts.data(), rc->verts.size() * sizeof(float));
+	return RB_OK;
+}
+
+extern "C" rb_status rb_raycaster_refit(rb_raycaster * rc, const float * world_positions, size_t nverts) {
+	if(!rc || !world_positions) return rb_fail(RB_ERR_INVALID, "rb_raycaster_refit: null argument");
+	RB_REQUIRE_DEVICE();
+	if(!rc->built) return rb_fail(RB_ERR_INVALID, "rb_raycaster_refit: hierarchy not built");
+	return rb_lbvh_refit(rc, world_positions, nverts);
+}
+
+extern "C" rb_status rb_raycaster_set_trace_mode(rb_raycaster * rc, rb_trace_mode mode) {
+	if(!rc) return rb_fail(RB_ERR_INVALID, "rb_raycaster_set_trace_mode: null handle");
+	if(mode != RB_TRACE_EXACT && mode != RB_TRACE_ORDERED) return rb_fail(RB_ERR_INVALID, "unknown trace mode %d", int(mode));
+	rc->traceMode = mode;
+	return RB_OK;
+}
+
+extern "C" uint64_t rb_raycaster_launch_count(const rb_raycaster * rc) {
+	return rc ? rc->launches.load() : 0;
+}
+
+// ---------------------------------------------------------------- queries
+
+static rb_status rb_check_query(const rb_raycaster * rc, const char * what) {
+	if(!rc) return rb_fail(RB_ERR_INVALID, "%s: null handle", what);
+	RB_REQUIRE_DEVICE();
+	if(!rc->built) return rb_fail(RB_ERR_INVALID, "%s: hierarchy not built (call rb_raycaster_build)", what);
+	return RB_OK;
+}
+
+template<typename K>
+static rb_status rb_prepare_kernel(K kernel, size_t smem) {
+	if(smem > 48 * 1024) {
+		RB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+	}
+	return RB_OK;
+}
+
+extern "C" rb_status rb_raycaster_intersect_device(const rb_raycaster * rc, const float * d_origins, const float * d_directions, float mini, float maxi, size_t nrays, rb_hit * d_out, void * stream) {
+	rb_status st = rb_check_query(rc, "rb_raycaster_intersect_device");
+	if(st) return st;
+	if(nrays == 0) return RB_OK;
+	cudaStream_t s	  = static_cast<cudaStream_t>(stream);
+	const size_t smem = rb_trace_smem_bytes(rc, RB_TRACE_BLOCK);
+	const unsigned grid = unsigned((nrays + RB_TRACE_BLOCK - 1) / RB_TRACE_BLOCK);
+	if(rc->traceMode == RB_TRACE_ORDERED) {
+		st = rb_prepare_kernel(rb_k_closest<true>, smem);
+		if(st) return st;
+		rb_k_closest<true><<<grid, RB_TRACE_BLOCK, smem, s>>>(rc->dev, d_origins, d_directions, mini, maxi, nrays, d_out);
+	} else {
+		st = rb_prepare_kernel(rb_k_closest<false>, smem);
+		if(st) return st;
+		rb_k_closest<false><<<grid, RB_TRACE_BLOCK, smem, s>>>(rc->dev, d_origins, d_directions, mini, maxi, nrays, d_out);
+	}
+	RB_CUDA(cudaGetLastError());
+	rc->launches++;
+	return RB_OK;
+}
+
+extern "C" rb_status rb_raycaster_intersect_any_device(const rb_raycaster * rc, const float * d_origins, const float * d_directions, float mini, float maxi, size_t nrays, uint8_t * d_out, void * stream) {
+	rb_status st = rb_check_query(rc, "rb_raycaster_intersect_any_device");
+	if(st) return st;
+	if(nrays == 0) return RB_OK;
+	cudaStream_t s	  = static_cast<cudaStream_t>(stream);
+	const size_t smem = rb_trace_smem_bytes(rc, RB_TRACE_BLOCK);
+	const unsigned grid = unsigned((nrays + RB_TRACE_BLOCK - 1) / RB_TRACE_BLOCK);
+	if(rc->traceMode == RB_TRACE_ORDERED) {
+		st = rb_prepare_kernel(rb_k_any<true>, smem);
+		if(st) return st;
+		rb_k_any<true><<<grid, RB_TRACE_BLOCK, smem, s>>>(rc->dev, d_origins, d_directions, mini, maxi, nrays, d_out);
+	} else {
+		st = rb_prepare_kernel(rb_k_any<false>, smem);
+		if(st) return st;
+		rb_k_any<false><<<grid, RB_TRACE_BLOCK, smem, s>>>(rc->dev, d_origins, d_directions, mini, maxi, nrays, d_out);
+	}
+	RB_CUDA(cudaGetLastError());
+	rc->launches++;
+	return RB_OK;
+}
+
+extern "C" rb_status rb_raycaster_count_work_device(const rb_raycaster * rc, const float * d_origins, const float * d_directions, float mini, float maxi, size_t nrays, int any_hit, uint64_t counters[4], void * stream) {
+	rb_status st = rb_check_query(rc, "rb_raycaster_count_work_device");
+	if(st) return st;
+	if(!counters) return rb_fail(RB_ERR_INVALID, "rb_raycaster_count_work_device: null counters");
+	cudaStream_t s = static_cast<cudaStream_t>(stream);
+	unsigned long long * d_c = nullptr;
+	RB_CUDA(cudaMallocAsync(&d_c, 4 * sizeof(unsigned long long), s));
+	RB_CUDA(cudaMemsetAsync(d_c, 0, 4 * sizeof(unsigned long long), s));
+	if(nrays) {
+		const size_t smem	= rb_trace_smem_bytes(rc, RB_TRACE_BLOCK);
+		const unsigned grid = unsigned((nrays + RB_TRACE_BLOCK - 1) / RB_TRACE_BLOCK);
+		const bool ordered	= rc->traceMode == RB_TRACE_ORDERED;
+#define RB_LAUNCH_COUNT(A, O)                                                                                   \
+	do {                                                                                                        \
+		st = rb_prepare_kernel(rb_k_count<A, O>, smem);                                                         \
+		if(st) return st;                                                                                       \
+		rb_k_count<A, O><<<grid, RB_TRACE_BLOCK, smem, s>>>(rc->dev, d_origins, d_directions, mini, maxi, nrays, d_c); \
+	} while(0)
+		if(any_hit && ordered) RB_LAUNCH_COUNT(true, true);
+		else if(any_hit) RB_LAUNCH_COUNT(true, false);
+		else if(ordered) RB_LAUNCH_COUNT(false, true);
+		else RB_LAUNCH_COUNT(false, false);
+#undef RB_LAUNCH_COUNT
+		RB_CUDA(cudaGetLastError());
+		rc->launches++;
+	}
+	unsigned long long h[4];
+	RB_CUDA(cudaMemcpyAsync(h, d_c, sizeof(h), cudaMemcpyDeviceToHost, s));
+	RB_CUDA(cudaStreamSynchronize(s));
+	RB_CUDA(cudaFreeAsync(d_c, s));
+	for(int k = 0; k < 4; ++k) counters[k] = h[k];
+	return RB_OK;
+}
+
+// Host-pointer entry points: stage through stream-ordered allocations on the calling thread's own stream, so that
+// concurrent callers (the reference traces from many threads) never share scratch memory.
+namespace {
+struct Scratch {
+	cudaStream_t s;
+	std::vector<void *> ptrs;
+	explicit Scratch(cudaStream_t st) : s(st) {}
+	~Scratch() {
+		for(void * p : ptrs) cudaFreeAsync(p, s);
+	}
+	template<typename T>
+	cudaError_t alloc(T ** p, size_t bytes) {
+		void * raw		= nullptr;
+		cudaError_t e = cudaMallocAsync(&raw, bytes ? bytes : 16, s);
+		if(e == cudaSuccess) ptrs.push_back(raw);
+		*p = static_cast<T *>(raw);
+		return e;
+	}
+};
+} // namespace
+
+extern "C" rb_status rb_raycaster_intersect(const rb_raycaster * rc, const float * origins, const float * directions, float mini, float maxi, size_t nrays, rb_hit * out) {
+	rb_status st = rb_check_query(rc, "rb_raycaster_intersect");
+	if(st) return st;
+	if(nrays == 0) return RB_OK;
+	if(!origins || !directions || !out) return rb_fail(RB_ERR_INVALID, "rb_raycaster_intersect: null argument");
+	RB_CUDA(cudaSetDevice(rc->device));
+	cudaStream_t s = cudaStreamPerThread;
+	Scratch scratch(s);
+	float *d_o = nullptr, *d_d = nullptr;
+	rb_hit * d_h = nullptr;
+	RB_CUDA(scratch.alloc(&d_o, nrays * 3 * sizeof(float)));
+	RB_CUDA(scratch.alloc(&d_d, nrays * 3 * sizeof(float)));
+	RB_CUDA(scratch.alloc(&d_h, nrays * sizeof(rb_hit)));
+	RB_CUDA(cudaMemcpyAsync(d_o, origins, nrays * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+	RB_CUDA(cudaMemcpyAsync(d_d, directions, nrays * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+	st = rb_raycaster_intersect_device(rc, d_o, d_d, mini, maxi, nrays, d_h, s);
+	if(st) return st;
+	RB_CUDA(cudaMemcpyAsync(out, d_h, nrays * sizeof(rb_hit), cudaMemcpyDeviceToHost, s));
+	RB_CUDA(cudaStreamSynchronize(s));
+	return RB_OK;
+}
+
+extern "C" rb_status rb_raycaster_intersect_any(const rb_raycaster * rc, const float * origins, const float * directions, float mini, float maxi, size_t nrays, uint8_t * out) {
+	rb_status st = rb_check_query(rc, "rb_raycaster_intersect_any");
+	if(st) return st;
+	if(nrays == 0) return RB_OK;
+	if(!origins || !directions || !out) return rb_fail(RB_ERR_INVALID, "rb_raycaster_intersect_any: null argument");
+	RB_CUDA(cudaSetDevice(rc->device));
+	cudaStream_t s = cudaStreamPerThread;
+	Scratch scratch(s);
+	float *d_o = nullptr, *d_d = nullptr;
+	uint8_t * d_r = nullptr;
+	RB_CUDA(scratch.alloc(&d_o, nrays * 3 * sizeof(float)));
+	RB_CUDA(scratch.alloc(&d_d, nrays * 3 * sizeof(float)));
+	RB_CUDA(scratch.alloc(&d_r, nrays));
+	RB_CUDA(cudaMemcpyAsync(d_o, origins, nrays * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+	RB_CUDA(cudaMemcpyAsync(d_d, directions, nrays * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+	st = rb_raycaster_intersect_any_device(rc, d_o, d_d, mini, maxi, nrays, d_r, s);
+	if(st) return st;
+	RB_CUDA(cudaMemcpyAsync(out, d_r, nrays, cudaMemcpyDeviceToHost, s));
+	RB_CUDA(cudaStreamSynchronize(s));
+	return RB_OK;
+}
+
+extern "C" rb_status rb_raycaster_visible(const rb_raycaster * rc, const float * p0, const float * p1, size_t n, uint8_t * out) {
+	rb_status st = rb_check_query(rc, "rb_raycaster_visible");
+	if(st) return st;
+	if(n == 0) return RB_OK;
+	if(!p0 || !p1 || !out) return rb_fail(RB_ERR_INVALID, "rb_raycaster_visible: null argument");
+	RB_CUDA(cudaSetDevice(rc->device));
+	cudaStream_t s = cudaStreamPerThread;
+	Scratch scratch(s);
+	float *d_a = nullptr, *d_b = nullptr;
+	uint8_t * d_r = nullptr;
+	RB_CUDA(scratch.alloc(&d_a, n * 3 * sizeof(float)));
+	RB_CUDA(scratch.alloc(&d_b, n * 3 * sizeof(float)));
+	RB_CUDA(scratch.alloc(&d_r, n));
+	RB_CUDA(cudaMemcpyAsync(d_a, p0, n * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+	RB_CUDA(cudaMemcpyAsync(d_b, p1, n * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+	const size_t smem	= rb_trace_smem_bytes(rc, RB_TRACE_BLOCK);
+	const unsigned grid = unsigned((n + RB_TRACE_BLOCK - 1) / RB_TRACE_BLOCK);
+	st = rb_prepare_kernel(rb_k_visible, smem);
+	if(st) return st;
+	rb_k_visible<<<grid, RB_TRACE_BLOCK, smem, s>>>(rc->dev, d_a, d_b, n, d_r);
+	RB_CUDA(cudaGetLastError());
+	rc->launches++;
+	RB_CUDA(cudaMemcpyAsync(out, d_r, n, cudaMemcpyDeviceToHost, s));
+	RB_CUDA(cudaStreamSynchronize(s));
+	return RB_OK;
+}
+
+// ---------------------------------------------------------------- KAT: Ray::Ray + Intersection::box on arrays
+__global__ void rb_k_kat_box(const float * __restrict__ org, const float * __restrict__ dir, const float * __restrict__ boxes, float mini, float maxi, size_t n, uint8_t * __restrict__ out) {
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	V3 o, d;
+	rb_load_ray(org, dir, i, o, d);
+	const RbRay ray = rb_make_ray(o, d);
+	const float * b = boxes + 6 * i;
+	out[i] = rb_box_test(ray, b[0], b[1], b[2], b[3], b[4], b[5], mini, maxi) ? 1 : 0;
+}
+
+extern "C" rb_status rb_kat_box_test(const float * origins, const float * dirs, const float * boxes6, float mini, float maxi, size_t n, uint8_t * out) {
+	RB_REQUIRE_DEVICE();
+	if(n == 0) return RB_OK;
+	if(!origins || !dirs || !boxes6 || !out) return rb_fail(RB_ERR_INVALID, "rb_kat_box_test: null argument");
+	cudaStream_t s = cudaStreamPerThread;
+	Scratch scratch(s);
+	float *d_o = nullptr, *d_d = nullptr, *d_b = nullptr;
+	uint8_t * d_r = nullptr;
+	RB_CUDA(scratch.alloc(&d_o, n * 3 * sizeof(float)));
+	RB_CUDA(scratch.alloc(&d_d, n * 3 * sizeof(float)));
+	RB_CUDA(scratch.alloc(&d_b, n * 6 * sizeof(float)));
+	RB_CUDA(scratch.alloc(&d_r, n));
+	RB_CUDA(cudaMemcpyAsync(d_o, origins, n * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+	RB_CUDA(cudaMemcpyAsync(d_d, dirs, n * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+	RB_CUDA(cudaMemcpyAsync(d_b, boxes6, n * 6 * sizeof(float), cudaMemcpyHostToDevice, s));
+	rb_k_kat_box<<<unsigned((n + 127) / 128), 128, 0, s>>>(d_o, d_d, d_b, mini, maxi, n, d_r);
+	RB_CUDA(cudaGetLastError());
+	RB_CUDA(cudaMemcpyAsync(out, d_r, n, cudaMemcpyDeviceToHost, s));
+	RB_CUDA(cudaStreamSynchronize(s));
+	return RB_OK;
+}

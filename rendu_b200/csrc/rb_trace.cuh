@@ -1,0 +1,289 @@
+// rb_trace.cuh — device-side BVH traversal: the B200 restatement of Raycaster::intersects / intersectsAny
+// (reference: src/engine/raycaster/Raycaster.cpp:144-262, src/engine/raycaster/Intersection.cpp:3-5,22-32).
+//
+// Device layout (all 16-byte aligned, fetched with 128-bit loads through the read-only path):
+//   nodes : 4 x float4 per INTERIOR node (64 B): both child boxes and both child references live in the parent, so
+//           one visit = one 64-byte fetch instead of the reference's two dependent 48-byte Node loads.
+//             n0 = (L.min.x, L.min.y, L.min.z, L.max.x)   n1 = (L.max.y, L.max.z, R.min.x, R.min.y)
+//             n2 = (R.min.z, R.max.x, R.max.y, R.max.z)   n3 = (bits(leftRef), bits(rightRef), 0, 0)
+//   tris  : 3 x float4 per triangle (48 B) in hierarchy order, vertices pre-gathered:
+//             t0 = (v0.xyz, bits(localId))  t1 = (v1-v0, bits(meshId))  t2 = (v2-v0, 0)
+//           v1-v0 / v2-v0 are the reference's `v01`/`v02` (Raycaster.cpp:235-236) computed once at upload; fp32
+//           subtraction is deterministic so the stored values equal what the reference recomputes per test.
+//   roots : 2 x float4 per mesh root: (min.xyz, bits(ref)) (max.xyz, 0); tested linearly as the reference does
+//           (Raycaster.cpp:149-155).
+//   A child reference is >= 0 for an interior node index, < 0 for a leaf: ~ref = (firstTriangle << 3) | (count-1).
+#pragma once
+#include "rb_math.cuh"
+#include "rb_types.h"
+#include <stdint.h>
+
+struct RbRay {
+	V3 pos, dir, inv;
+	bool regular; // every component of pos and inv is finite: min/max can never see a NaN
+};
+
+// Ray::Ray (Intersection.cpp:3-5): dir = normalize(d), invdir = 1.0f / normalize(d).
+RB_D RbRay rb_make_ray(V3 origin, V3 direction) {
+	RbRay r;
+	r.pos = origin;
+	r.dir = normalize3(direction);
+	r.inv = V3{1.0f / r.dir.x, 1.0f / r.dir.y, 1.0f / r.dir.z};
+	r.regular = isfinite(r.inv.x) && isfinite(r.inv.y) && isfinite(r.inv.z) && isfinite(origin.x) && isfinite(origin.y) && isfinite(origin.z);
+	return r;
+}
+
+// Intersection::box (Intersection.cpp:22-32). The literal form keeps the reference's NaN behaviour (0*inf when a ray
+// is parallel to a slab and starts on it); when no NaN can occur (regular ray, finite box) fminf/fmaxf select the
+// same operands, so the cheaper FMNMX form returns the same boolean.
+RB_D bool rb_box_test(const RbRay & ray, float bminx, float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz, float mini, float maxi) {
+	const float minRx = (bminx - ray.pos.x) * ray.inv.x;
+	const float minRy = (bminy - ray.pos.y) * ray.inv.y;
+	const float minRz = (bminz - ray.pos.z) * ray.inv.z;
+	const float maxRx = (bmaxx - ray.pos.x) * ray.inv.x;
+	const float maxRy = (bmaxy - ray.pos.y) * ray.inv.y;
+	const float maxRz = (bmaxz - ray.pos.z) * ray.inv.z;
+	if(ray.regular) {
+		const float closest	 = fmaxf(fmaxf(fminf(minRx, maxRx), fminf(minRy, maxRy)), fmaxf(fminf(minRz, maxRz), mini));
+		const float furthest = fminf(fminf(fmaxf(minRx, maxRx), fmaxf(minRy, maxRy)), fminf(fmaxf(minRz, maxRz), maxi));
+		return closest <= furthest;
+	}
+	const float minFx = glm_min(minRx, maxRx), minFy = glm_min(minRy, maxRy), minFz = glm_min(minRz, maxRz);
+	const float maxFx = glm_max(minRx, maxRx), maxFy = glm_max(minRy, maxRy), maxFz = glm_max(minRz, maxRz);
+	const float closest	 = std_max(minFx, std_max(minFy, minFz));
+	const float furthest = std_min(maxFx, std_min(maxFy, maxFz));
+	return std_max(closest, mini) <= std_min(furthest, maxi);
+}
+
+// Raycaster::intersects(ray, tri, mini, maxi) (Raycaster.cpp:232-262), Möller-Trumbore with the reference's
+// comparisons written literally (their outcome under NaN matters).
+RB_D bool rb_tri_test(const RbRay & ray, V3 v0, V3 v01, V3 v02, float mini, float maxi, float & t, float & u, float & v) {
+	const V3 p		= cross3(ray.dir, v02);
+	const float det = dot3(v01, p);
+	if(fabsf(det) < FLT_EPSILON) {
+		return false;
+	}
+	const float invDet = 1.0f / det;
+	const V3 q		   = ray.pos - v0;
+	u				   = invDet * dot3(q, p);
+	if(u < 0.0f || u > 1.0f) {
+		return false;
+	}
+	const V3 r = cross3(q, v01);
+	v		   = invDet * dot3(ray.dir, r);
+	if(v < 0.0f || (u + v) > 1.0f) {
+		return false;
+	}
+	t = invDet * dot3(v02, r);
+	return (t > mini && t < maxi);
+}
+
+struct RbHitRec {
+	float t, u, v;
+	int tri; // index in hierarchy order, -1 = miss
+};
+
+struct RbWork {
+	unsigned int interior, tris, roots, maxStack;
+};
+
+RB_D float4 rb_ldg4(const float4 * p) {
+	return __ldg(p);
+}
+
+// Closest hit / any hit in the REFERENCE ORDER: roots pre-tested against the caller's (mini, maxi) and consumed last
+// mesh first, depth-first with the right child popped before the left, `maxi` shrinking on every accepted hit
+// (strict <, so the first triangle found wins exact ties). Equivalent, decision for decision, to the std::stack loop
+// of Raycaster.cpp:144-185 (closest) and :187-224 (any): the reference pushes left then right and pops right; here
+// the right child is followed directly and only the left one is stored. Roots are box-tested lazily but with the
+// ORIGINAL maxi, which is the value the reference used when it pre-pushed them.
+// `stack` points at this thread's column of a shared-memory array, entries `stride` ints apart.
+template<bool ANY, bool COUNT>
+RB_D bool rb_trace_exact(const RbDeviceBvh & bvh, const RbRay & ray, float mini, float maxi, int * stack, int stride, RbHitRec & best, RbWork * work) {
+	const float maxi0 = maxi;
+	best.t	 = FLT_MAX;
+	best.u	 = 0.0f;
+	best.v	 = 0.0f;
+	best.tri = -1;
+	int root = bvh.nroots;
+	int sp	 = 0;
+	int cur	 = RB_REF_NONE;
+	for(;;) {
+		if(cur == RB_REF_NONE) {
+			if(sp > 0) {
+				--sp;
+				cur = stack[sp * stride];
+			} else {
+				// Next accepted root, last mesh first.
+				while(root > 0) {
+					--root;
+					const float4 r0 = rb_ldg4(bvh.roots + 2 * root);
+					const float4 r1 = rb_ldg4(bvh.roots + 2 * root + 1);
+					if(COUNT) work->roots++;
+					if(rb_box_test(ray, r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, mini, maxi0)) {
+						cur = __float_as_int(r0.w);
+						break;
+					}
+				}
+				if(cur == RB_REF_NONE) {
+					break;
+				}
+			}
+		}
+		// Descend while on interior nodes.
+		while(cur >= 0 && cur != RB_REF_NONE) {
+			const float4 * n = bvh.nodes + 4 * (size_t)cur;
+			const float4 n0 = rb_ldg4(n), n1 = rb_ldg4(n + 1), n2 = rb_ldg4(n + 2), n3 = rb_ldg4(n + 3);
+			if(COUNT) work->interior++;
+			const bool hitL = rb_box_test(ray, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, mini, maxi);
+			const bool hitR = rb_box_test(ray, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, mini, maxi);
+			const int refL = __float_as_int(n3.x), refR = __float_as_int(n3.y);
+			if(hitR) {
+				if(hitL) {
+					stack[sp * stride] = refL;
+					++sp;
+					if(COUNT) work->maxStack = max(work->maxStack, (unsigned int)sp);
+				}
+				cur = refR;
+			} else if(hitL) {
+				cur = refL;
+			} else if(sp > 0) {
+				--sp;
+				cur = stack[sp * stride];
+			} else {
+				cur = RB_REF_NONE;
+			}
+		}
+		if(cur < 0) {
+			const int code	= ~cur;
+			const int first = code >> RB_LEAF_BITS;
+			const int count = (code & (RB_LEAF_MAX_TRIS - 1)) + 1;
+			for(int k = 0; k < count; ++k) {
+				const float4 * tp = bvh.tris + 3 * (size_t)(first + k);
+				const float4 t0 = rb_ldg4(tp), t1 = rb_ldg4(tp + 1), t2 = rb_ldg4(tp + 2);
+				if(COUNT) work->tris++;
+				float t, u, v;
+				if(rb_tri_test(ray, V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, mini, maxi, t, u, v)) {
+					if(ANY) {
+						best.t = t; best.u = u; best.v = v; best.tri = first + k;
+						return true;
+					}
+					if(t < best.t) {
+						best.t = t; best.u = u; best.v = v; best.tri = first + k;
+						maxi = t;
+					}
+				}
+			}
+			cur = RB_REF_NONE;
+		}
+	}
+	return best.tri >= 0;
+}
+
+// Near-child-first traversal of the same tree (RB_TRACE_ORDERED): both children are box-tested exactly as above, the
+// one whose slab entry distance is smaller is visited first, so `maxi` shrinks sooner and far subtrees are culled.
+// All roots are still considered (in reverse order). Same triangle test; the closest hit is the same triangle except
+// where two triangles are hit at exactly the same distance or where the reference's non-watertight box test makes
+// the outcome order-dependent ("ordered mode").
+RB_D bool rb_box_test_dist(const RbRay & ray, float bminx, float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz, float mini, float maxi, float & entry) {
+	const float minRx = (bminx - ray.pos.x) * ray.inv.x;
+	const float minRy = (bminy - ray.pos.y) * ray.inv.y;
+	const float minRz = (bminz - ray.pos.z) * ray.inv.z;
+	const float maxRx = (bmaxx - ray.pos.x) * ray.inv.x;
+	const float maxRy = (bmaxy - ray.pos.y) * ray.inv.y;
+	const float maxRz = (bmaxz - ray.pos.z) * ray.inv.z;
+	if(ray.regular) {
+		const float closest	 = fmaxf(fmaxf(fminf(minRx, maxRx), fminf(minRy, maxRy)), fmaxf(fminf(minRz, maxRz), mini));
+		const float furthest = fminf(fminf(fmaxf(minRx, maxRx), fmaxf(minRy, maxRy)), fminf(fmaxf(minRz, maxRz), maxi));
+		entry = closest;
+		return closest <= furthest;
+	}
+	const float minFx = glm_min(minRx, maxRx), minFy = glm_min(minRy, maxRy), minFz = glm_min(minRz, maxRz);
+	const float maxFx = glm_max(minRx, maxRx), maxFy = glm_max(minRy, maxRy), maxFz = glm_max(minRz, maxRz);
+	const float closest	 = std_max(minFx, std_max(minFy, minFz));
+	const float furthest = std_min(maxFx, std_min(maxFy, maxFz));
+	entry = std_max(closest, mini);
+	return entry <= std_min(furthest, maxi);
+}
+
+template<bool ANY, bool COUNT>
+RB_D bool rb_trace_ordered(const RbDeviceBvh & bvh, const RbRay & ray, float mini, float maxi, int * stack, int stride, RbHitRec & best, RbWork * work) {
+	best.t	 = FLT_MAX;
+	best.u	 = 0.0f;
+	best.v	 = 0.0f;
+	best.tri = -1;
+	int root = bvh.nroots;
+	int sp	 = 0;
+	int cur	 = RB_REF_NONE;
+	for(;;) {
+		if(cur == RB_REF_NONE) {
+			if(sp > 0) {
+				--sp;
+				cur = stack[sp * stride];
+			} else {
+				while(root > 0) {
+					--root;
+					const float4 r0 = rb_ldg4(bvh.roots + 2 * root);
+					const float4 r1 = rb_ldg4(bvh.roots + 2 * root + 1);
+					if(COUNT) work->roots++;
+					if(rb_box_test(ray, r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, mini, maxi)) {
+						cur = __float_as_int(r0.w);
+						break;
+					}
+				}
+				if(cur == RB_REF_NONE) {
+					break;
+				}
+			}
+		}
+		while(cur >= 0 && cur != RB_REF_NONE) {
+			const float4 * n = bvh.nodes + 4 * (size_t)cur;
+			const float4 n0 = rb_ldg4(n), n1 = rb_ldg4(n + 1), n2 = rb_ldg4(n + 2), n3 = rb_ldg4(n + 3);
+			if(COUNT) work->interior++;
+			float dL, dR;
+			const bool hitL = rb_box_test_dist(ray, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, mini, maxi, dL);
+			const bool hitR = rb_box_test_dist(ray, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, mini, maxi, dR);
+			int refL = __float_as_int(n3.x), refR = __float_as_int(n3.y);
+			if(hitL && hitR) {
+				// Visit the nearer child first; on equal entry distance keep the reference's order (right first).
+				const bool leftFirst = dL < dR;
+				stack[sp * stride]	 = leftFirst ? refR : refL;
+				++sp;
+				if(COUNT) work->maxStack = max(work->maxStack, (unsigned int)sp);
+				cur = leftFirst ? refL : refR;
+			} else if(hitR) {
+				cur = refR;
+			} else if(hitL) {
+				cur = refL;
+			} else if(sp > 0) {
+				--sp;
+				cur = stack[sp * stride];
+			} else {
+				cur = RB_REF_NONE;
+			}
+		}
+		if(cur < 0) {
+			const int code	= ~cur;
+			const int first = code >> RB_LEAF_BITS;
+			const int count = (code & (RB_LEAF_MAX_TRIS - 1)) + 1;
+			for(int k = 0; k < count; ++k) {
+				const float4 * tp = bvh.tris + 3 * (size_t)(first + k);
+				const float4 t0 = rb_ldg4(tp), t1 = rb_ldg4(tp + 1), t2 = rb_ldg4(tp + 2);
+				if(COUNT) work->tris++;
+				float t, u, v;
+				if(rb_tri_test(ray, V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, mini, maxi, t, u, v)) {
+					if(ANY) {
+						best.t = t; best.u = u; best.v = v; best.tri = first + k;
+						return true;
+					}
+					if(t < best.t) {
+						best.t = t; best.u = u; best.v = v; best.tri = first + k;
+						maxi = t;
+					}
+				}
+			}
+			cur = RB_REF_NONE;
+		}
+	}
+	return best.tri >= 0;
+}

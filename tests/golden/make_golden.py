@@ -1,0 +1,115 @@
+"""Generates tests/golden/*.npz from the REAL reference (oracle/_ref/librendu_ref.so, i.e. the unmodified Rendu
+translation units built by oracle/build_ref.sh). Run here, where /root/reference exists:
+
+    python tests/golden/make_golden.py
+
+The vectors pin the oracle (and through it the CUDA path) on machines that have neither /root/reference nor
+oracle/_ref. Inputs are seeded; the file records them next to the reference's outputs.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref  # noqa: E402
+from rendu_b200 import workloads as wl  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+F = np.float32
+
+
+def translate(t):
+    m = np.eye(4, dtype=F)
+    m[3, :3] = t  # column-major: translation lives in the 4th column = row 3 of the numpy view
+    return m.reshape(16)
+
+
+def rot_scale(angle, s, t):
+    c, sn = np.cos(angle), np.sin(angle)
+    m = np.array([[c * s, 0, -sn * s, 0], [0, s, 0, 0], [sn * s, 0, c * s, 0], [t[0], t[1], t[2], 1]], F)  # rows = glm columns
+    return m.reshape(16)
+
+
+def edge_rays():
+    """Rays that exercise the NaN / inf corners of Intersection::box: axis-parallel directions, origins exactly on box
+    planes, zero-length and denormal direction components, rays inside flat boxes."""
+    o, d = [], []
+    for ax in range(3):
+        for sgn in (1.0, -1.0):
+            for off in (0.0, 0.25, -1.0, 1.0, 0.5):
+                dd = np.zeros(3, F)
+                dd[ax] = sgn
+                oo = np.array([off, 0.5, off], F)
+                oo[ax] = -3.0 * sgn
+                o.append(oo)
+                d.append(dd)
+    for k in range(16):
+        dd = np.array([1e-41 if k & 1 else 0.3, -1.0, 1e-39 if k & 2 else -0.2], F)
+        o.append(np.array([-1.0 + 0.125 * k, 2.0, 1.0 - 0.125 * k], F))
+        d.append(dd)
+    o.append(np.array([0, 1, 0], F)); d.append(np.array([0, 0, 0], F))  # zero direction -> NaN ray
+    o.append(np.array([0, np.inf, 0], F)); d.append(np.array([0, -1, 0], F))
+    return np.array(o, F), np.array(d, F)
+
+
+def raycast_case(name, meshes, nrand, seed, mini=1e-4, maxi=1e8):
+    r = ref.RefRaycaster()
+    for pos, idx, model in meshes:
+        r.add_mesh(pos, idx, model)
+    r.build()
+    dump = r.dump()
+    ro, rd = wl.random_rays(nrand, seed)
+    co, cd = wl.coherent_rays(48)
+    eo, ed = edge_rays()
+    org = np.concatenate([ro, co, eo]).astype(F)
+    dirs = np.concatenate([rd, cd, ed]).astype(F)
+    h = r.intersect(org, dirs, mini, maxi)
+    any_hit, _ = r.intersect_any(org, dirs, mini, maxi)
+    h2 = r.intersect(org, dirs, 0.05, 1.7)
+    any2, _ = r.intersect_any(org, dirs, 0.05, 1.7)
+    p1 = (org + dirs).astype(F)
+    vis = r.visible(org[:512], p1[:512])
+    save = dict(org=org, dirs=dirs, mini=F(mini), maxi=F(maxi), hit=h["hit"], dist=h["dist"], u=h["u"], v=h["v"], w=h["w"],
+                local_id=h["local_id"], mesh_id=h["mesh_id"], any=any_hit,
+                hit_b=h2["hit"], dist_b=h2["dist"], local_b=h2["local_id"], mesh_b=h2["mesh_id"], any_b=any2, visible=vis,
+                node_box=dump["node_box"], node_left=dump["node_left"], node_right=dump["node_right"], node_leaf=dump["node_leaf"],
+                tri_v=dump["tri_v"], tri_local=dump["tri_local"], tri_mesh=dump["tri_mesh"], verts=dump["verts"], mesh_count=np.uint32(dump["mesh_count"]))
+    for i, (pos, idx, model) in enumerate(meshes):
+        save["mesh%d_pos" % i] = pos
+        save["mesh%d_idx" % i] = idx
+        save["mesh%d_model" % i] = np.eye(4, dtype=F).reshape(16) if model is None else model
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **save)
+    print(name, "rays", org.shape[0], "hits", int(h["hit"].sum()), "nodes", dump["node_left"].size)
+
+
+def main():
+    pos, idx = wl.displaced_grid(37)
+    raycast_case("raycast_grid37", [(pos, idx, None)], 3000, 7)
+    # Several meshes: transformed copies, a 2-triangle quad (its root is a leaf), a single triangle, overlapping geometry.
+    p8, i8 = wl.displaced_grid(8)
+    quad = (np.array([[-1, 0.6, -1], [1, 0.6, -1], [1, 0.6, 1], [-1, 0.6, 1]], F), np.array([0, 1, 2, 0, 2, 3], np.uint32))
+    tri = (np.array([[0, 0.9, 0], [0.5, 0.9, 0], [0, 0.9, 0.5]], F), np.array([0, 1, 2], np.uint32))
+    raycast_case("raycast_multimesh", [(p8, i8, None), (p8, i8, rot_scale(0.7, 0.5, (0.2, 0.4, -0.1))), (quad[0], quad[1], None),
+                                       (tri[0], tri[1], translate((0.1, 0.0, 0.1))), (p8, i8, translate((0.0, 0.0, 0.0)))], 3000, 11)
+    # Box test KAT on the edge rays against assorted boxes.
+    eo, ed = edge_rays()
+    rng = np.random.RandomState(5)
+    boxes = []
+    for k in range(eo.shape[0]):
+        lo = rng.uniform(-1, 0.5, 3).astype(F)
+        hi = (lo + rng.uniform(0, 1.5, 3)).astype(F)
+        if k % 3 == 0:
+            hi[k % 3] = lo[k % 3]  # flat box
+        if k % 4 == 0:
+            lo[(k // 4) % 3] = eo[k][(k // 4) % 3]  # origin exactly on a slab plane
+        boxes.append(np.concatenate([lo, hi]))
+    boxes = np.array(boxes, F)
+    res, rays = ref.box_test(eo, ed, boxes, 1e-4, 1e8)
+    np.savez_compressed(os.path.join(OUT, "box_kat.npz"), org=eo, dirs=ed, boxes=boxes, result=res, rays=rays)
+    print("box_kat", res.sum(), "/", res.size)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,97 @@
+"""CPU tests (no GPU): the C oracle against (a) golden vectors generated from the real reference and (b) the real
+reference itself when oracle/_ref is present; plus the product's host-side BVH builder against both."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from oracle import ref
+from rendu_b200 import workloads as wl
+from util import case_meshes, load_case
+
+CASES = ["raycast_grid37", "raycast_multimesh"]
+
+
+def build_oracle(case):
+    o = orc.OracleRaycaster()
+    for pos, idx, model in case_meshes(case):
+        o.add_mesh(pos, idx, model)
+    o.build()
+    return o
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_build_matches_golden(name):
+    c = load_case(name)
+    o = build_oracle(c)
+    assert o.nodes.size == c["node_left"].size
+    assert np.array_equal(o.nodes["left"], c["node_left"])
+    assert np.array_equal(o.nodes["right"], c["node_right"])
+    assert np.array_equal(o.nodes["leaf"], c["node_leaf"])
+    assert np.array_equal(np.concatenate([o.nodes["bmin"], o.nodes["bmax"]], 1).view(np.uint32), c["node_box"].view(np.uint32))
+    assert np.array_equal(o.tris["localId"], c["tri_local"])
+    assert np.array_equal(o.tris["meshId"], c["tri_mesh"])
+    assert np.array_equal(np.stack([o.tris["v0"], o.tris["v1"], o.tris["v2"]], 1), c["tri_v"])
+    assert np.array_equal(o.verts.view(np.uint32), c["verts"].view(np.uint32))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_hits_match_golden(name):
+    c = load_case(name)
+    o = build_oracle(c)
+    h = o.intersect(c["org"], c["dirs"], float(c["mini"]), float(c["maxi"]))
+    assert np.array_equal(h["hit"], c["hit"])
+    for k in ("dist", "u", "v", "w"):
+        assert np.array_equal(h[k].view(np.uint32), c[k].view(np.uint32)), k
+    assert np.array_equal(h["localId"], c["local_id"]) and np.array_equal(h["meshId"], c["mesh_id"])
+    assert np.array_equal(o.intersect_any(c["org"], c["dirs"], float(c["mini"]), float(c["maxi"])), c["any"])
+    hb = o.intersect(c["org"], c["dirs"], 0.05, 1.7)
+    assert np.array_equal(hb["hit"], c["hit_b"]) and np.array_equal(hb["dist"].view(np.uint32), c["dist_b"].view(np.uint32))
+    assert np.array_equal(hb["localId"], c["local_b"]) and np.array_equal(hb["meshId"], c["mesh_b"])
+    assert np.array_equal(o.intersect_any(c["org"], c["dirs"], 0.05, 1.7), c["any_b"])
+    p1 = (c["org"] + c["dirs"]).astype(np.float32)
+    assert np.array_equal(o.visible(c["org"][:512], p1[:512]), c["visible"])
+
+
+def test_oracle_box_kat():
+    c = load_case("box_kat")
+    res, rays = orc.box_test(c["org"], c["dirs"], c["boxes"], 1e-4, 1e8)
+    assert np.array_equal(res, c["result"])
+    assert np.array_equal(rays.view(np.uint32), c["rays"].view(np.uint32))  # Ray::Ray incl. NaN/inf patterns
+
+
+def test_oracle_threads_agree():
+    pos, idx = wl.displaced_grid(24)
+    o = orc.OracleRaycaster()
+    o.add_mesh(pos, idx)
+    o.build()
+    ro, rd = wl.random_rays(2000, 3)
+    a = o.intersect(ro, rd, threads=1)
+    b = o.intersect(ro, rd, threads=5)
+    assert a.tobytes() == b.tobytes()
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_matches_live_reference_large():
+    """Oracle vs the real reference on a larger mesh and fresh seeds (not only the committed vectors)."""
+    pos, idx = wl.displaced_grid(150)
+    r = ref.RefRaycaster()
+    r.add_mesh(pos, idx)
+    r.build()
+    d = r.dump()
+    o = orc.OracleRaycaster()
+    o.add_mesh(pos, idx)
+    o.build()
+    assert np.array_equal(o.nodes["left"], d["node_left"]) and np.array_equal(o.nodes["right"], d["node_right"])
+    assert np.array_equal(o.tris["localId"], d["tri_local"])
+    ro, rd = wl.random_rays(20000, 99)
+    co, cd = wl.coherent_rays(96)
+    org, dirs = np.concatenate([ro, co]), np.concatenate([rd, cd])
+    hr = r.intersect(org, dirs, threads=4)
+    ho = o.intersect(org, dirs, threads=4)
+    assert np.array_equal(ho["hit"], hr["hit"])
+    assert np.array_equal(ho["dist"].view(np.uint32), hr["dist"].view(np.uint32))
+    assert np.array_equal(ho["u"].view(np.uint32), hr["u"].view(np.uint32))
+    assert np.array_equal(ho["localId"], hr["local_id"])
+    any_r, _ = r.intersect_any(org, dirs, threads=4)
+    assert np.array_equal(o.intersect_any(org, dirs, threads=4), any_r)
+    assert hr["hit"].sum() > 5000
