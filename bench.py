@@ -351,6 +351,69 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_explore(args):
+    """Developer aid (not a bench line): times scheduler / mode variants of the traversal kernels on the C2 sets and
+    checks on the device that every variant returns the same hit records as the first one."""
+    import torch
+    import rendu_b200 as rb
+    from rendu_b200 import workloads as wl
+    dev = torch.device("cuda", 0)
+    pos, idx = wl.displaced_grid(GRID_N)
+    co, cd = wl.coherent_rays(RES)
+    n = co.shape[0]
+    sh = torch.cuda.current_stream().cuda_stream
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    d_co, d_cd = to(co), to(cd)
+    variants = [("simple", {"RB_PERSISTENT": "0"}, rb.TRACE_EXACT)]
+    for thr in (1, 8, 16, 20, 24, 28, 32):
+        variants.append(("persistent_t%d" % thr, {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": str(thr)}, rb.TRACE_EXACT))
+    variants.append(("ordered_simple", {"RB_PERSISTENT": "0"}, rb.TRACE_ORDERED))
+    variants.append(("ordered_persistent_t20", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "20"}, rb.TRACE_ORDERED))
+    base, d_io, d_id, results = None, None, None, {}
+    for name, env, mode in variants:
+        os.environ.update(env)
+        rc = rb.Raycaster()
+        rc.addMesh(pos, idx)
+        rc.updateHierarchy()
+        rc.set_trace_mode(mode)
+        bufs = {k: torch.empty(n * 48, dtype=torch.uint8, device=dev) for k in ("cc", "ci")}
+        anys = {k: torch.empty(n, dtype=torch.uint8, device=dev) for k in ("ac", "ai")}
+        if d_io is None:
+            rc.intersects_device(d_co.data_ptr(), d_cd.data_ptr(), n, bufs["cc"].data_ptr(), MINI, MAXI, sh)
+            torch.cuda.synchronize()
+            hits = bufs["cc"].cpu().numpy().view(rb.HIT_DTYPE)
+            nrm = wl.triangle_normals(pos, idx, np.where(hits["hit"] == 1, hits["localId"], 0))
+            io, idr = wl.incoherent_rays(co, cd, hits["hit"], hits["dist"], nrm, seed=1234)
+            d_io, d_id = to(io), to(idr)
+        runs = [("cc", lambda: rc.intersects_device(d_co.data_ptr(), d_cd.data_ptr(), n, bufs["cc"].data_ptr(), MINI, MAXI, sh)),
+                ("ac", lambda: rc.intersectsAny_device(d_co.data_ptr(), d_cd.data_ptr(), n, anys["ac"].data_ptr(), MINI, MAXI, sh)),
+                ("ci", lambda: rc.intersects_device(d_io.data_ptr(), d_id.data_ptr(), n, bufs["ci"].data_ptr(), MINI, MAXI, sh)),
+                ("ai", lambda: rc.intersectsAny_device(d_io.data_ptr(), d_id.data_ptr(), n, anys["ai"].data_ptr(), MINI, MAXI, sh))]
+        res = {}
+        for key, f in runs:
+            for _ in range(2):
+                f()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                f()
+            e1.record()
+            torch.cuda.synchronize()
+            res[key + "_ms"] = e0.elapsed_time(e1) / 5
+        res["total_ms"] = sum(res[k] for k in ("cc_ms", "ac_ms", "ci_ms", "ai_ms"))
+        res["mrays_s"] = 4 * n / res["total_ms"] / 1e3
+        snap = {k: v.clone() for k, v in list(bufs.items()) + list(anys.items())}
+        if base is None:
+            base = snap
+        res["mismatch_vs_first"] = {k: int((snap[k].view(-1, 48 if k in bufs else 1) != base[k].view(-1, 48 if k in bufs else 1)).any(dim=1).sum()) for k in snap}
+        results[name] = res
+        log("[explore] %-24s %s" % (name, json.dumps({k: (round(v, 4) if isinstance(v, float) else v) for k, v in res.items()})))
+        del rc
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(results, open(os.path.join(ROOT, "gpurun_out", "explore.json"), "w"), indent=1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -358,8 +421,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--explore", action="store_true", help="developer aid: time kernel variants, no bench line")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.explore:
+        run_explore(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)

@@ -55,6 +55,8 @@ struct rb_raycaster {
 	int buildMode	   = RB_BUILD_REFERENCE;
 
 	int traceMode = RB_TRACE_EXACT;
+	bool persistent	   = true; // persistent threads + warp work queue (false: one ray per thread)
+	int fetchThreshold = 20;   // refill a warp from the queue when fewer lanes than this are still traversing
 	mutable std::atomic<uint64_t> launches{0};
 };
 

@@ -4,6 +4,7 @@
 #include "rb_internal.h"
 #include "rb_trace.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -140,6 +141,64 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_visible(RbDeviceBvh bvh, 
 	out[i] = any ? 0 : 1;
 }
 
+// Persistent threads with a warp-level work queue: the grid is sized to fill the machine once (SMs x resident CTAs),
+// every warp pulls rays from a global cursor and refills the lanes whose ray has finished as soon as fewer than
+// `threshold` lanes are still traversing (one atomicAdd per refill, lanes ranked with __ballot/__popc). Rays finish
+// after very different numbers of steps; without the refill a warp runs at the pace of its slowest lane.
+RB_D void rb_store_any(uint8_t * out, size_t i, const RbDeviceBvh &, const RbHitRec & h) {
+	out[i] = h.tri >= 0 ? 1 : 0;
+}
+
+template<bool ANY, bool ORDERED>
+__global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_persistent(RbDeviceBvh bvh, const float * __restrict__ org, const float * __restrict__ dir, float mini, float maxi, unsigned int n, void * __restrict__ out, unsigned int * __restrict__ cursor, int threshold) {
+	extern __shared__ int s_stack[];
+	int * stack			   = s_stack + threadIdx.x;
+	const int stride	   = blockDim.x;
+	const unsigned int lane = threadIdx.x & 31u;
+	bool active	   = false;
+	bool exhausted = false; // warp-uniform: the queue has no more rays
+	unsigned int rayIdx = 0;
+	RbRay ray;
+	RbTraversal T;
+	for(;;) {
+		if(!exhausted) {
+			const unsigned int idle = __ballot_sync(0xffffffffu, !active);
+			if(idle) {
+				const int nIdle	 = __popc(idle);
+				const int leader = __ffs(idle) - 1;
+				unsigned int base = 0;
+				if((int)lane == leader) base = atomicAdd(cursor, (unsigned int)nIdle);
+				base = __shfl_sync(0xffffffffu, base, leader);
+				if(!active) {
+					const unsigned int idx = base + __popc(idle & ((1u << lane) - 1u));
+					if(idx < n) {
+						V3 o, d;
+						rb_load_ray(org, dir, idx, o, d);
+						ray = rb_make_ray(o, d);
+						rb_traversal_init(T, bvh, mini, maxi);
+						rayIdx = idx;
+						active = true;
+					}
+				}
+				exhausted = (base + (unsigned int)nIdle) >= n;
+			}
+		}
+		if(!__any_sync(0xffffffffu, active)) break;
+		bool more;
+		do {
+			if(active) {
+				if(rb_step<ANY, false, ORDERED>(T, bvh, ray, stack, stride, nullptr)) {
+					if(ANY) rb_store_any(static_cast<uint8_t *>(out), rayIdx, bvh, T.best);
+					else rb_store_hit(static_cast<rb_hit *>(out), rayIdx, bvh, T.best);
+					active = false;
+				}
+			}
+			const int nActive = __popc(__ballot_sync(0xffffffffu, active));
+			more = exhausted ? (nActive > 0) : (nActive >= threshold);
+		} while(more);
+	}
+}
+
 // Instrumented copy: same loops, counts the work that defines the algorithmic bytes per ray.
 template<bool ANY, bool ORDERED>
 __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_count(RbDeviceBvh bvh, const float * __restrict__ org, const float * __restrict__ dir, float mini, float maxi, size_t n, unsigned long long * __restrict__ counters) {
@@ -226,6 +285,10 @@ rb_status rb_raycaster_upload_flat(rb_raycaster * rc, const RbFlatBvh & flat) {
 extern "C" rb_status rb_raycaster_create(rb_raycaster ** out) {
 	if(!out) return rb_fail(RB_ERR_INVALID, "rb_raycaster_create: null output");
 	*out = new rb_raycaster();
+	// Scheduler tuning (DESIGN.md "traversal kernels"): RB_PERSISTENT=0 selects one ray per thread,
+	// RB_FETCH_THRESHOLD the number of live lanes below which a warp refills from the queue.
+	if(const char * e = getenv("RB_PERSISTENT")) (*out)->persistent = atoi(e) != 0;
+	if(const char * e = getenv("RB_FETCH_THRESHOLD")) (*out)->fetchThreshold = atoi(e);
 	return RB_OK;
 }
 
@@ -396,46 +459,66 @@ static rb_status rb_prepare_kernel(K kernel, size_t smem) {
 	return RB_OK;
 }
 
-extern "C" rb_status rb_raycaster_intersect_device(const rb_raycaster * rc, const float * d_origins, const float * d_directions, float mini, float maxi, size_t nrays, rb_hit * d_out, void * stream) {
-	rb_status st = rb_check_query(rc, "rb_raycaster_intersect_device");
-	if(st) return st;
-	if(nrays == 0) return RB_OK;
-	cudaStream_t s	  = static_cast<cudaStream_t>(stream);
-	const size_t smem = rb_trace_smem_bytes(rc, RB_TRACE_BLOCK);
+// Launch of the traversal kernels. Two schedulers exist and are selected per handle (rb_internal.h: `persistent`):
+// one ray per thread, or persistent threads with the warp-level work queue above.
+template<bool ANY>
+static rb_status rb_launch_trace(const rb_raycaster * rc, const float * d_origins, const float * d_directions, float mini, float maxi, size_t nrays, void * d_out, cudaStream_t s) {
+	const size_t smem	= rb_trace_smem_bytes(rc, RB_TRACE_BLOCK);
+	const bool ordered	= rc->traceMode == RB_TRACE_ORDERED;
+	rb_status st;
+	if(rc->persistent) {
+		auto kernel = ordered ? rb_k_trace_persistent<ANY, true> : rb_k_trace_persistent<ANY, false>;
+		st = rb_prepare_kernel(kernel, smem);
+		if(st) return st;
+		int perSm = 0, sms = 0;
+		RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, RB_TRACE_BLOCK, smem));
+		RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, rc->device));
+		if(perSm < 1) return rb_fail(RB_ERR_CUDA, "traversal kernel does not fit on an SM (stack depth %d)", rc->dev.stackDepth);
+		unsigned int * d_cursor = nullptr;
+		RB_CUDA(cudaMallocAsync(&d_cursor, sizeof(unsigned int), s));
+		const size_t chunkMax = 0xC0000000ull; // cursor is 32 bit
+		for(size_t done = 0; done < nrays; done += chunkMax) {
+			const size_t n = (nrays - done < chunkMax) ? (nrays - done) : chunkMax;
+			const size_t blocksNeeded = (n + RB_TRACE_BLOCK - 1) / RB_TRACE_BLOCK;
+			const unsigned grid = unsigned(blocksNeeded < size_t(perSm) * sms ? blocksNeeded : size_t(perSm) * sms);
+			RB_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned int), s));
+			void * outp = ANY ? static_cast<void *>(static_cast<uint8_t *>(d_out) + done) : static_cast<void *>(static_cast<rb_hit *>(d_out) + done);
+			kernel<<<grid, RB_TRACE_BLOCK, smem, s>>>(rc->dev, d_origins + 3 * done, d_directions + 3 * done, mini, maxi, (unsigned int)n, outp, d_cursor, rc->fetchThreshold);
+			RB_CUDA(cudaGetLastError());
+			rc->launches++;
+		}
+		RB_CUDA(cudaFreeAsync(d_cursor, s));
+		return RB_OK;
+	}
 	const unsigned grid = unsigned((nrays + RB_TRACE_BLOCK - 1) / RB_TRACE_BLOCK);
-	if(rc->traceMode == RB_TRACE_ORDERED) {
-		st = rb_prepare_kernel(rb_k_closest<true>, smem);
+	if(ANY) {
+		auto kernel = ordered ? rb_k_any<true> : rb_k_any<false>;
+		st = rb_prepare_kernel(kernel, smem);
 		if(st) return st;
-		rb_k_closest<true><<<grid, RB_TRACE_BLOCK, smem, s>>>(rc->dev, d_origins, d_directions, mini, maxi, nrays, d_out);
+		kernel<<<grid, RB_TRACE_BLOCK, smem, s>>>(rc->dev, d_origins, d_directions, mini, maxi, nrays, static_cast<uint8_t *>(d_out));
 	} else {
-		st = rb_prepare_kernel(rb_k_closest<false>, smem);
+		auto kernel = ordered ? rb_k_closest<true> : rb_k_closest<false>;
+		st = rb_prepare_kernel(kernel, smem);
 		if(st) return st;
-		rb_k_closest<false><<<grid, RB_TRACE_BLOCK, smem, s>>>(rc->dev, d_origins, d_directions, mini, maxi, nrays, d_out);
+		kernel<<<grid, RB_TRACE_BLOCK, smem, s>>>(rc->dev, d_origins, d_directions, mini, maxi, nrays, static_cast<rb_hit *>(d_out));
 	}
 	RB_CUDA(cudaGetLastError());
 	rc->launches++;
 	return RB_OK;
 }
 
+extern "C" rb_status rb_raycaster_intersect_device(const rb_raycaster * rc, const float * d_origins, const float * d_directions, float mini, float maxi, size_t nrays, rb_hit * d_out, void * stream) {
+	rb_status st = rb_check_query(rc, "rb_raycaster_intersect_device");
+	if(st) return st;
+	if(nrays == 0) return RB_OK;
+	return rb_launch_trace<false>(rc, d_origins, d_directions, mini, maxi, nrays, d_out, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" rb_status rb_raycaster_intersect_any_device(const rb_raycaster * rc, const float * d_origins, const float * d_directions, float mini, float maxi, size_t nrays, uint8_t * d_out, void * stream) {
 	rb_status st = rb_check_query(rc, "rb_raycaster_intersect_any_device");
 	if(st) return st;
 	if(nrays == 0) return RB_OK;
-	cudaStream_t s	  = static_cast<cudaStream_t>(stream);
-	const size_t smem = rb_trace_smem_bytes(rc, RB_TRACE_BLOCK);
-	const unsigned grid = unsigned((nrays + RB_TRACE_BLOCK - 1) / RB_TRACE_BLOCK);
-	if(rc->traceMode == RB_TRACE_ORDERED) {
-		st = rb_prepare_kernel(rb_k_any<true>, smem);
-		if(st) return st;
-		rb_k_any<true><<<grid, RB_TRACE_BLOCK, smem, s>>>(rc->dev, d_origins, d_directions, mini, maxi, nrays, d_out);
-	} else {
-		st = rb_prepare_kernel(rb_k_any<false>, smem);
-		if(st) return st;
-		rb_k_any<false><<<grid, RB_TRACE_BLOCK, smem, s>>>(rc->dev, d_origins, d_directions, mini, maxi, nrays, d_out);
-	}
-	RB_CUDA(cudaGetLastError());
-	rc->launches++;
-	return RB_OK;
+	return rb_launch_trace<true>(rc, d_origins, d_directions, mini, maxi, nrays, d_out, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" rb_status rb_raycaster_count_work_device(const rb_raycaster * rc, const float * d_origins, const float * d_directions, float mini, float maxi, size_t nrays, int any_hit, uint64_t counters[4], void * stream) {
@@ -493,26 +576,84 @@ struct Scratch {
 };
 } // namespace
 
+// Host-pointer batches are cut into chunks that flow through a small ring of device buffers, each slot on its own
+// stream, so that the upload of chunk c+1, the traversal of chunk c and the download of chunk c-1 overlap (two copy
+// engines + SMs). The ring belongs to the calling host thread: concurrent callers never share buffers or streams.
+namespace {
+constexpr size_t kPipeChunk = size_t(1) << 19; // rays per chunk
+constexpr int kPipeSlots	= 3;
+
+struct HostPipe {
+	int device = -1;
+	cudaStream_t stream[kPipeSlots] = {};
+	cudaEvent_t done[kPipeSlots]	= {};
+	float * d_org[kPipeSlots]		= {};
+	float * d_dir[kPipeSlots]		= {};
+	void * d_out[kPipeSlots]		= {};
+	bool ready = false;
+
+	rb_status ensure(int dev) {
+		if(ready && dev == device) return RB_OK;
+		release();
+		device = dev;
+		for(int k = 0; k < kPipeSlots; ++k) {
+			RB_CUDA(cudaStreamCreateWithFlags(&stream[k], cudaStreamNonBlocking));
+			RB_CUDA(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+			RB_CUDA(cudaMalloc(&d_org[k], kPipeChunk * 3 * sizeof(float)));
+			RB_CUDA(cudaMalloc(&d_dir[k], kPipeChunk * 3 * sizeof(float)));
+			RB_CUDA(cudaMalloc(&d_out[k], kPipeChunk * sizeof(rb_hit)));
+		}
+		ready = true;
+		return RB_OK;
+	}
+	void release() {
+		if(!ready) return;
+		for(int k = 0; k < kPipeSlots; ++k) {
+			cudaStreamDestroy(stream[k]);
+			cudaEventDestroy(done[k]);
+			cudaFree(d_org[k]);
+			cudaFree(d_dir[k]);
+			cudaFree(d_out[k]);
+		}
+		ready = false;
+	}
+	~HostPipe() {
+		// The CUDA context may already be gone at thread/process exit; leaking a few buffers there is harmless.
+	}
+};
+
+thread_local HostPipe t_pipe;
+
+template<bool ANY>
+rb_status rb_host_batch(const rb_raycaster * rc, const float * origins, const float * directions, float mini, float maxi, size_t nrays, void * out) {
+	RB_CUDA(cudaSetDevice(rc->device));
+	rb_status st = t_pipe.ensure(rc->device);
+	if(st) return st;
+	const size_t outStride = ANY ? sizeof(uint8_t) : sizeof(rb_hit);
+	size_t chunkIdx = 0;
+	for(size_t begin = 0; begin < nrays; begin += kPipeChunk, ++chunkIdx) {
+		const int k		= int(chunkIdx % kPipeSlots);
+		const size_t n	= (nrays - begin < kPipeChunk) ? (nrays - begin) : kPipeChunk;
+		cudaStream_t s	= t_pipe.stream[k];
+		// The slot's previous chunk must have left the device before its buffers are overwritten: same stream, so
+		// stream order already guarantees it.
+		RB_CUDA(cudaMemcpyAsync(t_pipe.d_org[k], origins + 3 * begin, n * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+		RB_CUDA(cudaMemcpyAsync(t_pipe.d_dir[k], directions + 3 * begin, n * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+		st = rb_launch_trace<ANY>(rc, t_pipe.d_org[k], t_pipe.d_dir[k], mini, maxi, n, t_pipe.d_out[k], s);
+		if(st) return st;
+		RB_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(out) + begin * outStride, t_pipe.d_out[k], n * outStride, cudaMemcpyDeviceToHost, s));
+	}
+	for(int k = 0; k < kPipeSlots; ++k) RB_CUDA(cudaStreamSynchronize(t_pipe.stream[k]));
+	return RB_OK;
+}
+} // namespace
+
 extern "C" rb_status rb_raycaster_intersect(const rb_raycaster * rc, const float * origins, const float * directions, float mini, float maxi, size_t nrays, rb_hit * out) {
 	rb_status st = rb_check_query(rc, "rb_raycaster_intersect");
 	if(st) return st;
 	if(nrays == 0) return RB_OK;
 	if(!origins || !directions || !out) return rb_fail(RB_ERR_INVALID, "rb_raycaster_intersect: null argument");
-	RB_CUDA(cudaSetDevice(rc->device));
-	cudaStream_t s = cudaStreamPerThread;
-	Scratch scratch(s);
-	float *d_o = nullptr, *d_d = nullptr;
-	rb_hit * d_h = nullptr;
-	RB_CUDA(scratch.alloc(&d_o, nrays * 3 * sizeof(float)));
-	RB_CUDA(scratch.alloc(&d_d, nrays * 3 * sizeof(float)));
-	RB_CUDA(scratch.alloc(&d_h, nrays * sizeof(rb_hit)));
-	RB_CUDA(cudaMemcpyAsync(d_o, origins, nrays * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
-	RB_CUDA(cudaMemcpyAsync(d_d, directions, nrays * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
-	st = rb_raycaster_intersect_device(rc, d_o, d_d, mini, maxi, nrays, d_h, s);
-	if(st) return st;
-	RB_CUDA(cudaMemcpyAsync(out, d_h, nrays * sizeof(rb_hit), cudaMemcpyDeviceToHost, s));
-	RB_CUDA(cudaStreamSynchronize(s));
-	return RB_OK;
+	return rb_host_batch<false>(rc, origins, directions, mini, maxi, nrays, out);
 }
 
 extern "C" rb_status rb_raycaster_intersect_any(const rb_raycaster * rc, const float * origins, const float * directions, float mini, float maxi, size_t nrays, uint8_t * out) {
@@ -520,21 +661,7 @@ extern "C" rb_status rb_raycaster_intersect_any(const rb_raycaster * rc, const f
 	if(st) return st;
 	if(nrays == 0) return RB_OK;
 	if(!origins || !directions || !out) return rb_fail(RB_ERR_INVALID, "rb_raycaster_intersect_any: null argument");
-	RB_CUDA(cudaSetDevice(rc->device));
-	cudaStream_t s = cudaStreamPerThread;
-	Scratch scratch(s);
-	float *d_o = nullptr, *d_d = nullptr;
-	uint8_t * d_r = nullptr;
-	RB_CUDA(scratch.alloc(&d_o, nrays * 3 * sizeof(float)));
-	RB_CUDA(scratch.alloc(&d_d, nrays * 3 * sizeof(float)));
-	RB_CUDA(scratch.alloc(&d_r, nrays));
-	RB_CUDA(cudaMemcpyAsync(d_o, origins, nrays * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
-	RB_CUDA(cudaMemcpyAsync(d_d, directions, nrays * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
-	st = rb_raycaster_intersect_any_device(rc, d_o, d_d, mini, maxi, nrays, d_r, s);
-	if(st) return st;
-	RB_CUDA(cudaMemcpyAsync(out, d_r, nrays, cudaMemcpyDeviceToHost, s));
-	RB_CUDA(cudaStreamSynchronize(s));
-	return RB_OK;
+	return rb_host_batch<true>(rc, origins, directions, mini, maxi, nrays, out);
 }
 
 extern "C" rb_status rb_raycaster_visible(const rb_raycaster * rc, const float * p0, const float * p1, size_t n, uint8_t * out) {

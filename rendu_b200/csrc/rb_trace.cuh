@@ -36,14 +36,15 @@ RB_D RbRay rb_make_ray(V3 origin, V3 direction) {
 // Intersection::box (Intersection.cpp:22-32). The literal form keeps the reference's NaN behaviour (0*inf when a ray
 // is parallel to a slab and starts on it); when no NaN can occur (regular ray, finite box) fminf/fmaxf select the
 // same operands, so the cheaper FMNMX form returns the same boolean.
-RB_D bool rb_box_test(const RbRay & ray, float bminx, float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz, float mini, float maxi) {
+template<bool REGULAR>
+RB_D bool rb_box_test_t(const RbRay & ray, float bminx, float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz, float mini, float maxi) {
 	const float minRx = (bminx - ray.pos.x) * ray.inv.x;
 	const float minRy = (bminy - ray.pos.y) * ray.inv.y;
 	const float minRz = (bminz - ray.pos.z) * ray.inv.z;
 	const float maxRx = (bmaxx - ray.pos.x) * ray.inv.x;
 	const float maxRy = (bmaxy - ray.pos.y) * ray.inv.y;
 	const float maxRz = (bmaxz - ray.pos.z) * ray.inv.z;
-	if(ray.regular) {
+	if(REGULAR) {
 		const float closest	 = fmaxf(fmaxf(fminf(minRx, maxRx), fminf(minRy, maxRy)), fmaxf(fminf(minRz, maxRz), mini));
 		const float furthest = fminf(fminf(fmaxf(minRx, maxRx), fmaxf(minRy, maxRy)), fminf(fmaxf(minRz, maxRz), maxi));
 		return closest <= furthest;
@@ -53,6 +54,11 @@ RB_D bool rb_box_test(const RbRay & ray, float bminx, float bminy, float bminz, 
 	const float closest	 = std_max(minFx, std_max(minFy, minFz));
 	const float furthest = std_min(maxFx, std_min(maxFy, maxFz));
 	return std_max(closest, mini) <= std_min(furthest, maxi);
+}
+
+RB_D bool rb_box_test(const RbRay & ray, float bminx, float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz, float mini, float maxi) {
+	return ray.regular ? rb_box_test_t<true>(ray, bminx, bminy, bminz, bmaxx, bmaxy, bmaxz, mini, maxi)
+					   : rb_box_test_t<false>(ray, bminx, bminy, bminz, bmaxx, bmaxy, bmaxz, mini, maxi);
 }
 
 // Raycaster::intersects(ray, tri, mini, maxi) (Raycaster.cpp:232-262), Möller-Trumbore with the reference's
@@ -97,94 +103,113 @@ RB_D float4 rb_ldg4(const float4 * p) {
 // of Raycaster.cpp:144-185 (closest) and :187-224 (any): the reference pushes left then right and pops right; here
 // the right child is followed directly and only the left one is stored. Roots are box-tested lazily but with the
 // ORIGINAL maxi, which is the value the reference used when it pre-pushed them.
+//
+// The traversal is a resumable state machine (RbTraversal + rb_step_*) so that the one-ray-per-thread kernels and
+// the persistent dynamic-fetch kernels share one body. One step = take the next pending node (stack, else next
+// accepted root), descend while on interior nodes, then test the triangles of the leaf reached.
 // `stack` points at this thread's column of a shared-memory array, entries `stride` ints apart.
-template<bool ANY, bool COUNT>
-RB_D bool rb_trace_exact(const RbDeviceBvh & bvh, const RbRay & ray, float mini, float maxi, int * stack, int stride, RbHitRec & best, RbWork * work) {
-	const float maxi0 = maxi;
-	best.t	 = FLT_MAX;
-	best.u	 = 0.0f;
-	best.v	 = 0.0f;
-	best.tri = -1;
-	int root = bvh.nroots;
-	int sp	 = 0;
-	int cur	 = RB_REF_NONE;
-	for(;;) {
-		if(cur == RB_REF_NONE) {
-			if(sp > 0) {
-				--sp;
-				cur = stack[sp * stride];
-			} else {
-				// Next accepted root, last mesh first.
-				while(root > 0) {
-					--root;
-					const float4 r0 = rb_ldg4(bvh.roots + 2 * root);
-					const float4 r1 = rb_ldg4(bvh.roots + 2 * root + 1);
-					if(COUNT) work->roots++;
-					if(rb_box_test(ray, r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, mini, maxi0)) {
-						cur = __float_as_int(r0.w);
-						break;
-					}
-				}
-				if(cur == RB_REF_NONE) {
+struct RbTraversal {
+	RbHitRec best;
+	float mini, maxi, maxi0;
+	int cur, sp, root;
+};
+
+RB_D void rb_traversal_init(RbTraversal & T, const RbDeviceBvh & bvh, float mini, float maxi) {
+	T.best.t   = FLT_MAX;
+	T.best.u   = 0.0f;
+	T.best.v   = 0.0f;
+	T.best.tri = -1;
+	T.mini	   = mini;
+	T.maxi	   = maxi;
+	T.maxi0	   = maxi;
+	T.cur	   = RB_REF_NONE;
+	T.sp	   = 0;
+	T.root	   = bvh.nroots;
+}
+
+// Returns true when the traversal is finished (for ANY: also as soon as a triangle is accepted).
+template<bool ANY, bool COUNT, bool REGULAR>
+RB_D bool rb_step_exact(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ray, int * stack, int stride, RbWork * work) {
+	int cur = T.cur;
+	if(cur == RB_REF_NONE) {
+		if(T.sp > 0) {
+			--T.sp;
+			cur = stack[T.sp * stride];
+		} else {
+			// Next accepted root, last mesh first.
+			while(T.root > 0) {
+				--T.root;
+				const float4 r0 = rb_ldg4(bvh.roots + 2 * T.root);
+				const float4 r1 = rb_ldg4(bvh.roots + 2 * T.root + 1);
+				if(COUNT) work->roots++;
+				if(rb_box_test(ray, r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, T.mini, T.maxi0)) {
+					cur = __float_as_int(r0.w);
 					break;
 				}
 			}
-		}
-		// Descend while on interior nodes.
-		while(cur >= 0 && cur != RB_REF_NONE) {
-			const float4 * n = bvh.nodes + 4 * (size_t)cur;
-			const float4 n0 = rb_ldg4(n), n1 = rb_ldg4(n + 1), n2 = rb_ldg4(n + 2), n3 = rb_ldg4(n + 3);
-			if(COUNT) work->interior++;
-			const bool hitL = rb_box_test(ray, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, mini, maxi);
-			const bool hitR = rb_box_test(ray, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, mini, maxi);
-			const int refL = __float_as_int(n3.x), refR = __float_as_int(n3.y);
-			if(hitR) {
-				if(hitL) {
-					stack[sp * stride] = refL;
-					++sp;
-					if(COUNT) work->maxStack = max(work->maxStack, (unsigned int)sp);
-				}
-				cur = refR;
-			} else if(hitL) {
-				cur = refL;
-			} else if(sp > 0) {
-				--sp;
-				cur = stack[sp * stride];
-			} else {
-				cur = RB_REF_NONE;
+			if(cur == RB_REF_NONE) {
+				return true;
 			}
 		}
-		if(cur < 0) {
-			const int code	= ~cur;
-			const int first = code >> RB_LEAF_BITS;
-			const int count = (code & (RB_LEAF_MAX_TRIS - 1)) + 1;
-			for(int k = 0; k < count; ++k) {
-				const float4 * tp = bvh.tris + 3 * (size_t)(first + k);
-				const float4 t0 = rb_ldg4(tp), t1 = rb_ldg4(tp + 1), t2 = rb_ldg4(tp + 2);
-				if(COUNT) work->tris++;
-				float t, u, v;
-				if(rb_tri_test(ray, V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, mini, maxi, t, u, v)) {
-					if(ANY) {
-						best.t = t; best.u = u; best.v = v; best.tri = first + k;
-						return true;
-					}
-					if(t < best.t) {
-						best.t = t; best.u = u; best.v = v; best.tri = first + k;
-						maxi = t;
-					}
-				}
+	}
+	// Descend while on interior nodes.
+	while(cur >= 0 && cur != RB_REF_NONE) {
+		const float4 * n = bvh.nodes + 4 * (size_t)cur;
+		const float4 n0 = rb_ldg4(n), n1 = rb_ldg4(n + 1), n2 = rb_ldg4(n + 2), n3 = rb_ldg4(n + 3);
+		if(COUNT) work->interior++;
+		const bool hitL = rb_box_test_t<REGULAR>(ray, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, T.mini, T.maxi);
+		const bool hitR = rb_box_test_t<REGULAR>(ray, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, T.mini, T.maxi);
+		const int refL = __float_as_int(n3.x), refR = __float_as_int(n3.y);
+		if(hitR) {
+			if(hitL) {
+				stack[T.sp * stride] = refL;
+				++T.sp;
+				if(COUNT) work->maxStack = max(work->maxStack, (unsigned int)T.sp);
 			}
+			cur = refR;
+		} else if(hitL) {
+			cur = refL;
+		} else if(T.sp > 0) {
+			--T.sp;
+			cur = stack[T.sp * stride];
+		} else {
 			cur = RB_REF_NONE;
 		}
 	}
-	return best.tri >= 0;
+	if(cur < 0) {
+		const int code	= ~cur;
+		const int first = code >> RB_LEAF_BITS;
+		const int count = (code & (RB_LEAF_MAX_TRIS - 1)) + 1;
+		for(int k = 0; k < count; ++k) {
+			const float4 * tp = bvh.tris + 3 * (size_t)(first + k);
+			const float4 t0 = rb_ldg4(tp), t1 = rb_ldg4(tp + 1), t2 = rb_ldg4(tp + 2);
+			if(COUNT) work->tris++;
+			float t, u, v;
+			if(rb_tri_test(ray, V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, T.mini, T.maxi, t, u, v)) {
+				if(ANY) {
+					T.best.t = t; T.best.u = u; T.best.v = v; T.best.tri = first + k;
+					T.cur = RB_REF_NONE;
+					return true;
+				}
+				if(t < T.best.t) {
+					T.best.t = t; T.best.u = u; T.best.v = v; T.best.tri = first + k;
+					T.maxi = t;
+				}
+			}
+		}
+		cur = RB_REF_NONE;
+	}
+	T.cur = cur;
+	return false;
 }
+
 
 // Near-child-first traversal of the same tree (RB_TRACE_ORDERED): both children are box-tested exactly as above, the
 // one whose slab entry distance is smaller is visited first, so `maxi` shrinks sooner and far subtrees are culled.
 // All roots are still considered (in reverse order). Same triangle test; the closest hit is the same triangle except
 // where two triangles are hit at exactly the same distance or where the reference's non-watertight box test makes
 // the outcome order-dependent ("ordered mode").
+template<bool REGULAR>
 RB_D bool rb_box_test_dist(const RbRay & ray, float bminx, float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz, float mini, float maxi, float & entry) {
 	const float minRx = (bminx - ray.pos.x) * ray.inv.x;
 	const float minRy = (bminy - ray.pos.y) * ray.inv.y;
@@ -192,7 +217,7 @@ RB_D bool rb_box_test_dist(const RbRay & ray, float bminx, float bminy, float bm
 	const float maxRx = (bmaxx - ray.pos.x) * ray.inv.x;
 	const float maxRy = (bmaxy - ray.pos.y) * ray.inv.y;
 	const float maxRz = (bmaxz - ray.pos.z) * ray.inv.z;
-	if(ray.regular) {
+	if(REGULAR) {
 		const float closest	 = fmaxf(fmaxf(fminf(minRx, maxRx), fminf(minRy, maxRy)), fmaxf(fminf(minRz, maxRz), mini));
 		const float furthest = fminf(fminf(fmaxf(minRx, maxRx), fmaxf(minRy, maxRy)), fminf(fmaxf(minRz, maxRz), maxi));
 		entry = closest;
@@ -206,84 +231,111 @@ RB_D bool rb_box_test_dist(const RbRay & ray, float bminx, float bminy, float bm
 	return entry <= std_min(furthest, maxi);
 }
 
-template<bool ANY, bool COUNT>
-RB_D bool rb_trace_ordered(const RbDeviceBvh & bvh, const RbRay & ray, float mini, float maxi, int * stack, int stride, RbHitRec & best, RbWork * work) {
-	best.t	 = FLT_MAX;
-	best.u	 = 0.0f;
-	best.v	 = 0.0f;
-	best.tri = -1;
-	int root = bvh.nroots;
-	int sp	 = 0;
-	int cur	 = RB_REF_NONE;
-	for(;;) {
-		if(cur == RB_REF_NONE) {
-			if(sp > 0) {
-				--sp;
-				cur = stack[sp * stride];
-			} else {
-				while(root > 0) {
-					--root;
-					const float4 r0 = rb_ldg4(bvh.roots + 2 * root);
-					const float4 r1 = rb_ldg4(bvh.roots + 2 * root + 1);
-					if(COUNT) work->roots++;
-					if(rb_box_test(ray, r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, mini, maxi)) {
-						cur = __float_as_int(r0.w);
-						break;
-					}
-				}
-				if(cur == RB_REF_NONE) {
+template<bool ANY, bool COUNT, bool REGULAR>
+RB_D bool rb_step_ordered(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ray, int * stack, int stride, RbWork * work) {
+	int cur = T.cur;
+	if(cur == RB_REF_NONE) {
+		if(T.sp > 0) {
+			--T.sp;
+			cur = stack[T.sp * stride];
+		} else {
+			while(T.root > 0) {
+				--T.root;
+				const float4 r0 = rb_ldg4(bvh.roots + 2 * T.root);
+				const float4 r1 = rb_ldg4(bvh.roots + 2 * T.root + 1);
+				if(COUNT) work->roots++;
+				if(rb_box_test(ray, r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, T.mini, T.maxi)) {
+					cur = __float_as_int(r0.w);
 					break;
 				}
 			}
-		}
-		while(cur >= 0 && cur != RB_REF_NONE) {
-			const float4 * n = bvh.nodes + 4 * (size_t)cur;
-			const float4 n0 = rb_ldg4(n), n1 = rb_ldg4(n + 1), n2 = rb_ldg4(n + 2), n3 = rb_ldg4(n + 3);
-			if(COUNT) work->interior++;
-			float dL, dR;
-			const bool hitL = rb_box_test_dist(ray, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, mini, maxi, dL);
-			const bool hitR = rb_box_test_dist(ray, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, mini, maxi, dR);
-			int refL = __float_as_int(n3.x), refR = __float_as_int(n3.y);
-			if(hitL && hitR) {
-				// Visit the nearer child first; on equal entry distance keep the reference's order (right first).
-				const bool leftFirst = dL < dR;
-				stack[sp * stride]	 = leftFirst ? refR : refL;
-				++sp;
-				if(COUNT) work->maxStack = max(work->maxStack, (unsigned int)sp);
-				cur = leftFirst ? refL : refR;
-			} else if(hitR) {
-				cur = refR;
-			} else if(hitL) {
-				cur = refL;
-			} else if(sp > 0) {
-				--sp;
-				cur = stack[sp * stride];
-			} else {
-				cur = RB_REF_NONE;
+			if(cur == RB_REF_NONE) {
+				return true;
 			}
 		}
-		if(cur < 0) {
-			const int code	= ~cur;
-			const int first = code >> RB_LEAF_BITS;
-			const int count = (code & (RB_LEAF_MAX_TRIS - 1)) + 1;
-			for(int k = 0; k < count; ++k) {
-				const float4 * tp = bvh.tris + 3 * (size_t)(first + k);
-				const float4 t0 = rb_ldg4(tp), t1 = rb_ldg4(tp + 1), t2 = rb_ldg4(tp + 2);
-				if(COUNT) work->tris++;
-				float t, u, v;
-				if(rb_tri_test(ray, V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, mini, maxi, t, u, v)) {
-					if(ANY) {
-						best.t = t; best.u = u; best.v = v; best.tri = first + k;
-						return true;
-					}
-					if(t < best.t) {
-						best.t = t; best.u = u; best.v = v; best.tri = first + k;
-						maxi = t;
-					}
-				}
-			}
+	}
+	while(cur >= 0 && cur != RB_REF_NONE) {
+		const float4 * n = bvh.nodes + 4 * (size_t)cur;
+		const float4 n0 = rb_ldg4(n), n1 = rb_ldg4(n + 1), n2 = rb_ldg4(n + 2), n3 = rb_ldg4(n + 3);
+		if(COUNT) work->interior++;
+		float dL, dR;
+		const bool hitL = rb_box_test_dist<REGULAR>(ray, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, T.mini, T.maxi, dL);
+		const bool hitR = rb_box_test_dist<REGULAR>(ray, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, T.mini, T.maxi, dR);
+		const int refL = __float_as_int(n3.x), refR = __float_as_int(n3.y);
+		if(hitL && hitR) {
+			// Visit the nearer child first; on equal entry distance keep the reference's order (right first).
+			const bool leftFirst = dL < dR;
+			stack[T.sp * stride] = leftFirst ? refR : refL;
+			++T.sp;
+			if(COUNT) work->maxStack = max(work->maxStack, (unsigned int)T.sp);
+			cur = leftFirst ? refL : refR;
+		} else if(hitR) {
+			cur = refR;
+		} else if(hitL) {
+			cur = refL;
+		} else if(T.sp > 0) {
+			--T.sp;
+			cur = stack[T.sp * stride];
+		} else {
 			cur = RB_REF_NONE;
 		}
 	}
+	if(cur < 0) {
+		const int code	= ~cur;
+		const int first = code >> RB_LEAF_BITS;
+		const int count = (code & (RB_LEAF_MAX_TRIS - 1)) + 1;
+		for(int k = 0; k < count; ++k) {
+			const float4 * tp = bvh.tris + 3 * (size_t)(first + k);
+			const float4 t0 = rb_ldg4(tp), t1 = rb_ldg4(tp + 1), t2 = rb_ldg4(tp + 2);
+			if(COUNT) work->tris++;
+			float t, u, v;
+			if(rb_tri_test(ray, V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, T.mini, T.maxi, t, u, v)) {
+				if(ANY) {
+					T.best.t = t; T.best.u = u; T.best.v = v; T.best.tri = first + k;
+					T.cur = RB_REF_NONE;
+					return true;
+				}
+				if(t < T.best.t) {
+					T.best.t = t; T.best.u = u; T.best.v = v; T.best.tri = first + k;
+					T.maxi = t;
+				}
+			}
+		}
+		cur = RB_REF_NONE;
+	}
+	T.cur = cur;
+	return false;
+}
+
+
+// One traversal step. The NaN-faithful box test is only compiled into the copy taken by irregular rays (a direction
+// component that is zero or denormal, or a non-finite origin); every other ray runs the FMNMX form.
+template<bool ANY, bool COUNT, bool ORDERED>
+RB_D bool rb_step(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ray, int * stack, int stride, RbWork * work) {
+	if(ray.regular) {
+		if(ORDERED) return rb_step_ordered<ANY, COUNT, true>(T, bvh, ray, stack, stride, work);
+		return rb_step_exact<ANY, COUNT, true>(T, bvh, ray, stack, stride, work);
+	}
+	if(ORDERED) return rb_step_ordered<ANY, COUNT, false>(T, bvh, ray, stack, stride, work);
+	return rb_step_exact<ANY, COUNT, false>(T, bvh, ray, stack, stride, work);
+}
+
+template<bool ANY, bool COUNT>
+RB_D bool rb_trace_exact(const RbDeviceBvh & bvh, const RbRay & ray, float mini, float maxi, int * stack, int stride, RbHitRec & best, RbWork * work) {
+	RbTraversal T;
+	rb_traversal_init(T, bvh, mini, maxi);
+	while(!rb_step<ANY, COUNT, false>(T, bvh, ray, stack, stride, work)) {
+	}
+	best = T.best;
+	return best.tri >= 0;
+}
+
+template<bool ANY, bool COUNT>
+RB_D bool rb_trace_ordered(const RbDeviceBvh & bvh, const RbRay & ray, float mini, float maxi, int * stack, int stride, RbHitRec & best, RbWork * work) {
+	RbTraversal T;
+	rb_traversal_init(T, bvh, mini, maxi);
+	while(!rb_step<ANY, COUNT, true>(T, bvh, ray, stack, stride, work)) {
+	}
+	best = T.best;
 	return best.tri >= 0;
 }
