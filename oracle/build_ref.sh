@@ -64,7 +64,7 @@ compile "$HERE/ref_harness/ref_shim.cpp" "$OUT/obj/ref_shim.o" "$CXX" "$CXXFLAGS
 for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
 
 WRAP="_ZNK9Raycaster10intersectsERKN3glm3vecILi3EfLNS0_9qualifierE0EEES5_ff"
-$CXX -shared -o "$OUT/librendu_ref.so" "$OUT"/obj/*.o -Wl,--wrap=$WRAP -Wl,--no-undefined -Wl,-Bsymbolic -lpthread
+$CXX -shared -o "$OUT/librendu_ref.so" "$OUT"/obj/*.o -Wl,--wrap=$WRAP -Wl,--wrap=_ZNSt6thread20hardware_concurrencyEv -Wl,--no-undefined -Wl,-Bsymbolic -lpthread
 
 # Run-time data of the reference (not source code): scenes, meshes, textures.
 mkdir -p "$OUT/resources"

@@ -129,3 +129,172 @@ def box_test(org, dirs, boxes, mini, maxi):
         L.orc_ray(_p(org[i:i + 1]), _p(dirs[i:i + 1]), _p(rays[i:i + 1]))
         out[i] = L.orc_box(_p(rays[i:i + 1]), _p(boxes[i, 0:3].copy()), _p(boxes[i, 3:6].copy()), C.c_float(mini), C.c_float(maxi))
     return out, rays
+
+
+# ------------------------------------------------------------------------------------------------ path tracer
+class Image(C.Structure):
+    _fields_ = [("pixels", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("components", C.c_uint32)]
+
+
+class Object(C.Structure):
+    _fields_ = [("positions", C.c_void_p), ("normals", C.c_void_p), ("tangents", C.c_void_p), ("bitangents", C.c_void_p), ("texcoords", C.c_void_p),
+                ("nverts", C.c_size_t), ("indices", C.c_void_p), ("nindices", C.c_size_t), ("model", C.c_float * 16), ("tex", C.c_int32 * 3),
+                ("emissive", C.c_uint32), ("masked", C.c_uint32), ("useTexCoords", C.c_uint32)]
+
+
+class Light(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("castsShadow", C.c_uint32), ("intensity", C.c_float * 3), ("position", C.c_float * 3),
+                ("direction", C.c_float * 3), ("radius", C.c_float), ("inner", C.c_float), ("outer", C.c_float)]
+
+
+class SceneStruct(C.Structure):
+    _fields_ = [("objects", C.c_void_p), ("nobjects", C.c_size_t), ("lights", C.c_void_p), ("nlights", C.c_size_t), ("images", C.c_void_p),
+                ("nimages", C.c_size_t), ("bgMode", C.c_uint32), ("bgColor", C.c_float * 3), ("bgTex", C.c_int32 * 6), ("sunDir", C.c_float * 3),
+                ("skyLut", C.c_int32), ("bvh", Bvh)]
+
+
+class RenderArgs(C.Structure):
+    _fields_ = [("eye", C.c_float * 3), ("corner", C.c_float * 3), ("dx", C.c_float * 3), ("dy", C.c_float * 3), ("width", C.c_uint32),
+                ("height", C.c_uint32), ("samples", C.c_uint32), ("depth", C.c_uint32), ("components", C.c_uint32), ("seed", C.c_uint64),
+                ("sampleIndex", C.c_uint32), ("sampleCount", C.c_uint32)]
+
+
+def make_light(l):
+    d = Light()
+    d.kind, d.castsShadow = int(l["kind"]), 1 if l["casts_shadow"] else 0
+    d.intensity = (C.c_float * 3)(*[float(x) for x in l["intensity"]])
+    d.position = (C.c_float * 3)(*[float(x) for x in l["position"]])
+    d.direction = (C.c_float * 3)(*[float(x) for x in l["direction"]])
+    d.radius, d.inner, d.outer = float(l["radius"]), float(l["inner"]), float(l["outer"])
+    return d
+
+
+def make_image(a):
+    a = np.ascontiguousarray(a, np.float32)
+    return Image(_p(a), a.shape[1], a.shape[0], a.shape[2] if a.ndim == 3 else 1), a
+
+
+class OracleScene:
+    """Flattened scene (same dict the product's rendu_b200.pathtracer.Scene takes) for the oracle path tracer."""
+
+    def __init__(self, description):
+        self._keep = []
+        self.rc = OracleRaycaster()
+        for o in description["objects"]:
+            self.rc.add_mesh(o["positions"], o["indices"], o["model"])
+        self.rc.build()
+        imgs = (Image * max(1, len(description["textures"])))()
+        for i, t in enumerate(description["textures"]):
+            imgs[i], arr = make_image(t)
+            self._keep.append(arr)
+        objs = (Object * len(description["objects"]))()
+        for i, o in enumerate(description["objects"]):
+            arrs = [np.ascontiguousarray(o[k], np.float32) for k in ("positions", "normals", "tangents", "bitangents", "texcoords")]
+            idx = np.ascontiguousarray(o["indices"], np.uint32)
+            self._keep += arrs + [idx]
+            d = objs[i]
+            d.positions, d.normals, d.tangents, d.bitangents, d.texcoords = [_p(a) for a in arrs]
+            d.nverts, d.indices, d.nindices = arrs[0].shape[0], _p(idx), idx.size
+            d.model = (C.c_float * 16)(*[float(x) for x in np.asarray(o["model"], np.float32).reshape(16)])
+            texs = list(o["textures"]) + [-1, -1, -1]
+            d.tex = (C.c_int32 * 3)(*[int(t) for t in texs[:3]])
+            d.emissive = 1 if o["material_type"] == 8 else 0
+            d.masked, d.useTexCoords = (1 if o["masked"] else 0), (1 if o["use_uv"] else 0)
+        lights = (Light * max(1, len(description["lights"])))()
+        for i, l in enumerate(description["lights"]):
+            lights[i] = make_light(l)
+        bg = description["background"]
+        s = SceneStruct()
+        s.objects, s.nobjects = C.cast(objs, C.c_void_p), len(description["objects"])
+        s.lights, s.nlights = C.cast(lights, C.c_void_p), len(description["lights"])
+        s.images, s.nimages = C.cast(imgs, C.c_void_p), len(description["textures"])
+        s.bgMode = int(bg["mode"])
+        s.bgColor = (C.c_float * 3)(*[float(x) for x in bg.get("color", (0, 0, 0))])
+        s.sunDir = (C.c_float * 3)(*[float(x) for x in bg.get("sun", (0, 1, 0))])
+        texs = list(bg.get("textures", [])) + [-1] * 6
+        s.bgTex = (C.c_int32 * 6)(*[int(t) for t in texs[:6]])
+        s.skyLut = int(bg.get("sky_lut", -1))
+        s.bvh = self.rc._bvh()
+        self._keep += [objs, lights, imgs]
+        self.struct = s
+
+    def render(self, camera, width, height, samples, depth, seed=0, rng="counter", threads=1, components=3, sample_split=None, image=None):
+        """PathTracer::render. rng='counter': the CUDA path's generator; rng='mt': the reference's mt19937 stream as seen
+        by the single forParallel worker after Random::seed(seed) (single thread). Returns (image, ray count)."""
+        L = lib()
+        L.orc_render.restype = C.c_uint64
+        L.orc_mt_create.restype = C.c_void_p
+        L.orc_mt_stream.restype = C.c_void_p
+        a = RenderArgs()
+        for k in ("eye", "corner", "dx", "dy"):
+            setattr(a, k, (C.c_float * 3)(*[float(x) for x in camera[k]]))
+        a.width, a.height, a.samples, a.depth, a.components, a.seed = width, height, samples, depth, components, seed
+        a.sampleIndex, a.sampleCount = sample_split if sample_split else (0, 1)
+        px = np.zeros((height, width, components), np.float32) if image is None else image
+        if rng == "mt":
+            st = C.c_void_p(L.orc_mt_create(C.c_uint(seed)))
+            rays = L.orc_render(C.byref(self.struct), C.byref(a), C.c_void_p(L.orc_mt_stream()), st, 1, _p(px))
+            L.orc_mt_destroy(st)
+        else:
+            rays = L.orc_render(C.byref(self.struct), C.byref(a), None, None, int(threads), _p(px))
+        return px, int(rays)
+
+
+def ggx_eval(wo, base, rough, metal, wi):
+    wo, base, wi = [np.ascontiguousarray(a, np.float32).reshape(-1, 3) for a in (wo, base, wi)]
+    rough, metal = [np.ascontiguousarray(a, np.float32).reshape(-1) for a in (rough, metal)]
+    out = np.zeros_like(wo)
+    lib().orc_ggx_eval(_p(wo), _p(base), _p(rough), _p(metal), _p(wi), C.c_size_t(wo.shape[0]), _p(out))
+    return out
+
+
+def ggx_sample(wo, base, rough, metal, u3):
+    wo, base, u3 = [np.ascontiguousarray(a, np.float32).reshape(-1, 3) for a in (wo, base, u3)]
+    rough, metal = [np.ascontiguousarray(a, np.float32).reshape(-1) for a in (rough, metal)]
+    wi, ev = np.zeros_like(wo), np.zeros_like(wo)
+    lib().orc_ggx_sample(_p(wo), _p(base), _p(rough), _p(metal), _p(u3), C.c_size_t(wo.shape[0]), _p(wi), _p(ev))
+    return wi, ev
+
+
+def image_rgbal(img, uv):
+    im, keep = make_image(img)
+    uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+    out = np.zeros((uv.shape[0], 4), np.float32)
+    lib().orc_image_rgbal(C.byref(im), _p(uv), C.c_size_t(uv.shape[0]), _p(out))
+    return out
+
+
+def cubemap(faces, dirs):
+    arr = (Image * 6)()
+    keep = []
+    for i in range(6):
+        arr[i], a = make_image(faces[i])
+        keep.append(a)
+    dirs = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+    out = np.zeros_like(dirs)
+    lib().orc_cubemap(arr, _p(dirs), C.c_size_t(dirs.shape[0]), _p(out))
+    return out
+
+
+def light_sample(light, pos):
+    l = make_light(light)
+    pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+    out = np.zeros((pos.shape[0], 5), np.float32)
+    lib().orc_light_sample(C.byref(l), _p(pos), C.c_size_t(pos.shape[0]), _p(out))
+    return out
+
+
+def sky_eval(lut, org, dirs, sun):
+    im, keep = make_image(lut)
+    org = np.ascontiguousarray(org, np.float32).reshape(-1, 3)
+    dirs = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+    sun = np.ascontiguousarray(sun, np.float32).reshape(3)
+    out = np.zeros_like(org)
+    lib().orc_sky_eval(C.byref(im), _p(org), _p(dirs), _p(sun), C.c_size_t(org.shape[0]), _p(out))
+    return out
+
+
+def mt_floats(seed, n):
+    out = np.zeros(n, np.float32)
+    lib().orc_mt_floats(C.c_uint(seed), C.c_size_t(n), _p(out))
+    return out

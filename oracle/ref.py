@@ -57,8 +57,10 @@ def seed(s):
     lib().ref_seed(C.c_uint(s))
 
 
-def pin_single_cpu(on):
-    return lib().ref_pin_single_cpu(1 if on else 0)
+def set_concurrency(n):
+    """Override what std::thread::hardware_concurrency() reports to the reference (0 restores the real value).
+    set_concurrency(1) makes System::forParallel use one worker, so a seeded render is reproducible."""
+    lib().ref_set_concurrency(C.c_uint(n))
 
 
 class RefRaycaster:
@@ -307,11 +309,27 @@ class RefScene:
         L.ref_scene_background(self._h, _p(mode), _p(col), _p(sun))
         bg = dict(mode=int(mode[0]), color=col[:3].copy(), sun=sun.copy(), textures=[])
         SIZE_MAX = (1 << 64) - 1
+        bg["sky_lut"] = -1
+        if bg["mode"] == 3:
+            bg["sky_lut"] = len(textures)
+            textures.append(sky_lut())
         if bg["mode"] == 1:
             bg["textures"] = [tex(SIZE_MAX, 0, 0)]
         elif bg["mode"] == 2:
             bg["textures"] = [tex(SIZE_MAX, 0, f) for f in range(6)]
         return dict(objects=objects, lights=lights, background=bg, textures=textures)
+
+
+def sky_lut():
+    add_default_resources()
+    L = lib()
+    L.ref_sky_lut.restype = C.c_void_p
+    info = np.zeros(3, np.uint64)
+    if not L.ref_sky_lut(_p(info), None):
+        raise RuntimeError("scattering-precomputed table not found in resources/common")
+    px = np.zeros((int(info[1]), int(info[0]), int(info[2])), np.float32)
+    L.ref_sky_lut(_p(info), _p(px))
+    return px
 
 
 def sky_eval(org, dirs, sun):

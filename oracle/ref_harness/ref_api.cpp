@@ -165,13 +165,14 @@ extern "C" {
 
 /* ---------------------------------------------------------------- misc */
 
+unsigned int __wrap__ZNSt6thread20hardware_concurrencyEv();
 int ref_hardware_threads() {
-	return int(std::thread::hardware_concurrency());
+	return int(__wrap__ZNSt6thread20hardware_concurrencyEv());
 }
 
 /* Number of worker threads System::forParallel will use (System.hpp:82). */
 int ref_forparallel_threads() {
-	return std::max(int(std::thread::hardware_concurrency()) - 1, 1);
+	return std::max(int(__wrap__ZNSt6thread20hardware_concurrencyEv()) - 1, 1);
 }
 
 void ref_seed(unsigned int s) {
@@ -182,7 +183,19 @@ void ref_set_verbose(int on) {
 	Log::setDefaultVerbose(on != 0);
 }
 
-/* Restrict this process to one CPU so that forParallel spawns a single worker and a seeded render is reproducible. */
+/* std::thread::hardware_concurrency() as seen by the reference objects (linked with --wrap): 0 = the real value,
+ * otherwise the override. With an override of 1 or 2 System::forParallel (System.hpp:82) spawns a single worker, which
+ * makes a seeded reference render reproducible (Random.cpp:72-80 hands out per-thread seeds in lock order). */
+static unsigned int g_concurrencyOverride = 0;
+unsigned int __real__ZNSt6thread20hardware_concurrencyEv();
+unsigned int __wrap__ZNSt6thread20hardware_concurrencyEv() {
+	return g_concurrencyOverride ? g_concurrencyOverride : __real__ZNSt6thread20hardware_concurrencyEv();
+}
+void ref_set_concurrency(unsigned int n) {
+	g_concurrencyOverride = n;
+}
+
+/* Restrict this process to one CPU (kept for experiments; hardware_concurrency ignores affinity on this libstdc++). */
 int ref_pin_single_cpu(int on) {
 	static cpu_set_t saved;
 	static bool haveSaved = false;
@@ -479,6 +492,16 @@ void ref_scene_background(void * h, uint64_t * mode, float * color4, float * sun
 	for(int k = 0; k < 4; ++k) color4[k] = mat.parameters().empty() ? 0.0f : mat.parameters()[0][k];
 	const Sky * sky = dynamic_cast<const Sky *>(s.background.get());
 	for(int k = 0; k < 3; ++k) sunDir3[k] = sky ? sky->direction()[k] : 0.0f;
+}
+
+/* The 512x512 "scattering-precomputed" table MaterialSky::eval fetches through Resources (MaterialSky.cpp:10). */
+const void * ref_sky_lut(uint64_t * out3, float * pixels) {
+	const Texture * t = Resources::manager().getTexture("scattering-precomputed", Layout::RGBA32F, Storage::CPU);
+	if(!t || t->images.empty()) return nullptr;
+	const Image & im = t->images[0];
+	out3[0] = im.width; out3[1] = im.height; out3[2] = im.components;
+	if(pixels) std::memcpy(pixels, im.pixels.data(), im.pixels.size() * sizeof(float));
+	return t;
 }
 
 /* Light i: kind (0 point, 1 spot, 2 directional), castsShadow, intensity(3); parameters recovered through the encode() text

@@ -54,6 +54,56 @@ size_t orc_add_mesh(const float * positions, size_t nverts, const uint32_t * ind
  * meshFirst/meshTris give each mesh's triangle range. Returns the node count. */
 size_t orc_build(orc_tri * tris, size_t ntris, const uint64_t * meshFirst, const uint64_t * meshTris, uint32_t meshCount, orc_node * nodesOut);
 
+/* ------------------------------------------------------------------------------------------------ path tracer
+ * Plain-array scene: what PathTracer::render reads from Scene / Object / Material / Mesh / Light. */
+typedef struct { const float * pixels; uint32_t width, height, components; } orc_image; /* Image (Image.hpp:143-146) */
+typedef struct {
+	const float * positions; const float * normals; const float * tangents; const float * bitangents; const float * texcoords;
+	size_t nverts; const uint32_t * indices; size_t nindices; float model[16];
+	int32_t tex[3]; /* Material::textures()[0..2] */
+	uint32_t emissive, masked, useTexCoords;
+} orc_object;
+typedef struct { uint32_t kind, castsShadow; float intensity[3], position[3], direction[3], radius, inner, outer; } orc_light;
+typedef struct {
+	const orc_object * objects; size_t nobjects;
+	const orc_light * lights; size_t nlights;
+	const orc_image * images; size_t nimages;
+	uint32_t bgMode; float bgColor[3]; int32_t bgTex[6]; float sunDir[3]; int32_t skyLut;
+	orc_bvh bvh;
+} orc_scene;
+typedef struct {
+	float eye[3], corner[3], dx[3], dy[3];
+	uint32_t width, height, samples, depth, components;
+	uint64_t seed;
+	uint32_t sampleIndex, sampleCount; /* sampleCount <= 1: all stratification cells */
+} orc_render_args;
+/* Sequential random source (the reference's per-thread mt19937, Random.cpp:21-27,72-80). */
+typedef struct { float (*next_float)(void *); int (*next_int)(void *, int lo, int hi); } orc_rng_stream;
+
+/* Counter-based generator shared with the CUDA path (rendu_b200/csrc/rb_shade.cuh). */
+uint64_t orc_rng_key(uint64_t seed, uint32_t pixel, uint32_t sid);
+float orc_rng_float(uint64_t key, uint32_t dim);
+
+/* PathTracer::render (PathTracer.cpp:159-299): accumulates into `pixels` (+=, then / samples). stream == NULL selects
+ * the counter-based generator (any thread count); otherwise draws are sequential and one thread is used. Returns the
+ * number of Raycaster::intersects queries issued. */
+uint64_t orc_render(const orc_scene * scene, const orc_render_args * args, const orc_rng_stream * stream, void * streamState, int threads, float * pixels);
+
+/* Scalar building blocks on arrays (KATs). */
+void orc_image_rgbal(const orc_image * im, const float * uv, size_t n, float * out4);          /* Image.cpp:86-106 */
+void orc_cubemap(const orc_image * faces6, const float * dirs, size_t n, float * out3);         /* Texture.cpp:141-191 */
+void orc_light_sample(const orc_light * l, const float * pos, size_t n, float * out5);          /* PointLight/SpotLight/DirectionalLight::sample */
+void orc_ggx_eval(const float * wo, const float * base, const float * rough, const float * metal, const float * wi, size_t n, float * out3); /* MaterialGGX.cpp:94-101 */
+void orc_ggx_sample(const float * wo, const float * base, const float * rough, const float * metal, const float * u3, size_t n, float * outWi, float * outEval); /* :54-92 */
+void orc_sky_eval(const orc_image * lut, const float * org, const float * dirs, const float * sun, size_t n, float * out3); /* MaterialSky.cpp:6-98 */
+
+/* The reference's random stream (rendu_oracle_std.cpp, libstdc++ <random>): state after Random::seed(seed) as seen by the
+ * single worker thread System::forParallel spawns when one CPU is available. */
+void * orc_mt_create(unsigned int seed);
+void orc_mt_destroy(void * state);
+const orc_rng_stream * orc_mt_stream(void);
+void orc_mt_floats(unsigned int seed, size_t n, float * out); /* Random::seed(seed) then n x Random::Float() on the seeding thread */
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,9 +1,13 @@
 /* TEST INFRASTRUCTURE — NOT PRODUCT CODE. See rendu_oracle.h.
+ * The two pieces of the reference's behaviour that are *defined by libstdc++* and therefore restated with the same
+ * library calls instead of plain C: the BVH build order (std::partition / std::nth_element) and the random stream
+ * (std::mt19937 + std::uniform_*_distribution, Random.cpp:21-27,72-80).
  * Raycaster::updateHierarchy (Raycaster.cpp:54-142) restated. This one function is C++ because the reference's tree is
  * *defined* by libstdc++: its triangle order is whatever std::partition (:107) and std::nth_element (:122) produce on
  * the 64-byte TriangleInfos records, so the oracle calls the same algorithms on the same record type. */
 #include "rendu_oracle.h"
 #include <algorithm>
+#include <random>
 #include <vector>
 
 namespace {
@@ -62,4 +66,31 @@ extern "C" size_t orc_build(orc_tri * tris, size_t ntris, const uint64_t * meshF
 		remaining.push_back({rightPos, cur.begin + split, cur.count - split});
 	}
 	return nnodes;
+}
+
+/* ---------------------------------------------------------------- Random (src/engine/generation/Random.cpp) */
+namespace {
+struct MtState { std::mt19937 mt; };
+float mtFloat(void * s) { return std::uniform_real_distribution<float>(0.0f, 1.0f)(static_cast<MtState *>(s)->mt); } /* Random.cpp:25-27 */
+int mtInt(void * s, int lo, int hi) { return std::uniform_int_distribution<int>(lo, hi)(static_cast<MtState *>(s)->mt); } /* :21-23 */
+const orc_rng_stream kMtStream = {mtFloat, mtInt};
+}
+
+/* Random::seed(seed) (Random.cpp:9-15) seeds the shared generator and re-creates the CALLING thread's generator, which
+ * draws the first local seed (LocalMT19937, :72-80). The worker thread forParallel then spawns draws the second one. */
+extern "C" void * orc_mt_create(unsigned int seed) {
+	std::mt19937 shared(seed);
+	(void)std::uniform_int_distribution<>()(shared);
+	const int workerSeed = std::uniform_int_distribution<>()(shared);
+	MtState * st = new MtState();
+	st->mt = std::mt19937(workerSeed);
+	return st;
+}
+extern "C" void orc_mt_destroy(void * state) { delete static_cast<MtState *>(state); }
+extern "C" const orc_rng_stream * orc_mt_stream(void) { return &kMtStream; }
+extern "C" void orc_mt_floats(unsigned int seed, size_t n, float * out) {
+	std::mt19937 shared(seed);
+	MtState st;
+	st.mt = std::mt19937(std::uniform_int_distribution<>()(shared));
+	for(size_t i = 0; i < n; ++i) out[i] = mtFloat(&st);
 }

@@ -1,0 +1,716 @@
+// rb_pathtracer.cu — PathTracer::render (reference: src/apps/pathtracer/PathTracer.cpp:159-299) as a wavefront of
+// sm_100a kernels: ray generation, closest-hit traversal, shading (+ NEE set-up + BSDF sampling), shadow traversal,
+// per-pixel accumulation and resolve. One path = one (pixel, stratification cell) pair; its state lives in SoA float4
+// arrays in HBM between kernels, and the two traversal kernels are persistent with a warp-level work queue.
+//
+// The estimator is the reference's, term for term (SURVEY.md §7 "quirk fidelity"): stratified jittered pixel samples
+// (:57-84), one uniformly chosen light per bounce with NEE at every depth including the last (:248-271), lobe-mixture
+// BSDF sampling without MIS or Russian roulette (MaterialGGX.cpp:54-92), masked hits that consume a depth level
+// (:223-226), emissive hits that add the raw texel and stop (:228-234), background only on escape (:206-209), the
+// per-SAMPLE clamp min(sampleColor, 5) before accumulation (:288) and the final division by the sample count (:291).
+// Two things differ by design (north_star): the RNG is counter-based (rb_shade.cuh) and a path whose attenuation has
+// become exactly zero is dropped instead of being traced further (everything it could still add is multiplied by 0).
+#include "rb_scene.h"
+#include "rb_trace.cuh"
+
+#include <cmath>
+#include <cstring>
+
+#define RB_PT_BLOCK 128
+
+struct RbFrame {
+	float eye[3], corner[3], dx[3], dy[3];
+	uint32_t width, height;
+	uint32_t samples;		 // full (rounded) sample count: grid + normalisation
+	uint32_t cellsX, cellsY; // getSampleGrid
+	float cellSizeX, cellSizeY;
+	uint32_t depth;
+	uint64_t seed;
+	uint32_t tileRows, tileIndex, tileCount; // rows rendered by this call
+	uint32_t sampleIndex, sampleCount;		 // stratification cells traced by this call
+	uint32_t localRows;						 // number of rows selected by the tile split
+};
+
+struct RbBatch {
+	uint32_t pixel0;  // first local pixel (row-major over the selected rows)
+	uint32_t npixels; // pixels in this batch
+	uint32_t sample0; // first local sample
+	uint32_t schunk;  // samples per pixel in this batch
+};
+
+struct RbPathBuffers {
+	float4 * rayO;
+	float4 * rayD;
+	float4 * atten;
+	float4 * color;
+	float4 * hit;
+	uint32_t * queue[2];
+	float4 * shO; // origin, maxDist
+	float4 * shD; // direction, slot
+	float4 * shC; // contribution
+	uint32_t * counters; // see RbCounterLayout
+};
+
+// Device counters of one batch (zeroed once per batch): queue sizes and work-queue cursors per bounce.
+RB_HD uint32_t rb_cnt_queue(uint32_t did) { return 4 * did + 0; }	// paths entering bounce `did`
+RB_HD uint32_t rb_cnt_shadow(uint32_t did) { return 4 * did + 1; }	// shadow rays of bounce `did`
+RB_HD uint32_t rb_cnt_cursor_t(uint32_t did) { return 4 * did + 2; }
+RB_HD uint32_t rb_cnt_cursor_s(uint32_t did) { return 4 * did + 3; }
+
+// Local row -> image row for the tile split (rows come in bands of tileRows, dealt round-robin to tileCount ranks).
+RB_HD uint32_t rb_tile_row(const RbFrame & f, uint32_t localRow) {
+	if(f.tileCount <= 1) return localRow;
+	const uint32_t band = localRow / f.tileRows;
+	return (band * f.tileCount + f.tileIndex) * f.tileRows + localRow % f.tileRows;
+}
+
+struct RbPathId {
+	uint32_t x, y, pixel, sid;
+};
+
+RB_D RbPathId rb_path_id(const RbFrame & f, const RbBatch & b, uint32_t slot) {
+	const uint32_t p	  = b.pixel0 + slot / b.schunk;
+	const uint32_t s	  = b.sample0 + slot % b.schunk;
+	const uint32_t lrow = p / f.width;
+	RbPathId id;
+	id.x	 = p % f.width;
+	id.y	 = rb_tile_row(f, lrow);
+	id.pixel = id.y * f.width + id.x;
+	id.sid	 = f.sampleIndex + s * f.sampleCount;
+	return id;
+}
+
+// getSamplePosition (PathTracer.cpp:71-84) + the screen -> NDC step of render (:191-193).
+RB_D void rb_sample_ndc(const RbFrame & f, const RbPathId & id, uint64_t key, float & ndcx, float & ndcy) {
+	const int sidy = int(id.sid) / int(f.cellsX);
+	const int sidx = int(id.sid) % int(f.cellsX);
+	const float jx = rb_rng_float(key, 0);
+	const float jy = rb_rng_float(key, 1);
+	const float gx = float(sidx) + jx, gy = float(sidy) + jy;
+	const float lx = gx * f.cellSizeX, ly = gy * f.cellSizeY;
+	const float sx = float(id.x) + lx, sy = float(id.y) + ly;
+	ndcx = sx / float(f.width);
+	ndcy = sy / float(f.height);
+}
+
+// ------------------------------------------------------------------------------------------------ ray generation
+__global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_raygen(RbFrame f, RbBatch b, RbPathBuffers pb) {
+	const uint32_t n = b.npixels * b.schunk;
+	for(uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
+		const RbPathId id = rb_path_id(f, b, slot);
+		const uint64_t key = rb_rng_key(f.seed, id.pixel, id.sid);
+		float ndcx, ndcy;
+		rb_sample_ndc(f, id, key, ndcx, ndcy);
+		const V3 corner = V3{f.corner[0], f.corner[1], f.corner[2]}, dx = V3{f.dx[0], f.dx[1], f.dx[2]}, dy = V3{f.dy[0], f.dy[1], f.dy[2]};
+		const V3 eye	= V3{f.eye[0], f.eye[1], f.eye[2]};
+		const V3 worldPos = corner + ndcx * dx + ndcy * dy; // PathTracer.cpp:195
+		const V3 rayDir	  = normalize3(worldPos - eye);		 // :198
+		pb.rayO[slot]	  = make_float4(eye.x, eye.y, eye.z, 0.0f);
+		pb.rayD[slot]	  = make_float4(rayDir.x, rayDir.y, rayDir.z, 0.0f);
+		pb.atten[slot]	  = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+		pb.color[slot]	  = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		pb.queue[0][slot] = slot;
+	}
+	if(blockIdx.x == 0 && threadIdx.x == 0) pb.counters[rb_cnt_queue(0)] = n;
+}
+
+// ------------------------------------------------------------------------------------------------ closest-hit wavefront
+// `_raycaster.intersects(rayPos, rayDir)` with the reference's default bounds (PathTracer.cpp:204, Raycaster.hpp:65).
+template<bool ORDERED>
+__global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_trace(RbDeviceBvh bvh, RbPathBuffers pb, const uint32_t * __restrict__ queue, uint32_t did, int threshold, unsigned long long * __restrict__ stats) {
+	extern __shared__ int s_stack[];
+	int * stack				= s_stack + threadIdx.x;
+	const int stride		= blockDim.x;
+	const unsigned int lane = threadIdx.x & 31u;
+	const unsigned int n	= pb.counters[rb_cnt_queue(did)];
+	unsigned int * cursor	= pb.counters + rb_cnt_cursor_t(did);
+	if(blockIdx.x == 0 && threadIdx.x == 0 && stats) atomicAdd(stats + 0, (unsigned long long)n);
+	bool active = false, exhausted = false;
+	unsigned int slot = 0;
+	RbRay ray;
+	RbTraversal T;
+	for(;;) {
+		if(!exhausted) {
+			const unsigned int idle = __ballot_sync(0xffffffffu, !active);
+			if(idle) {
+				const int nIdle	 = __popc(idle);
+				const int leader = __ffs(idle) - 1;
+				unsigned int base = 0;
+				if((int)lane == leader) base = atomicAdd(cursor, (unsigned int)nIdle);
+				base = __shfl_sync(0xffffffffu, base, leader);
+				if(!active) {
+					const unsigned int idx = base + __popc(idle & ((1u << lane) - 1u));
+					if(idx < n) {
+						slot = queue[idx];
+						const float4 o = pb.rayO[slot], d = pb.rayD[slot];
+						ray = rb_make_ray(V3{o.x, o.y, o.z}, V3{d.x, d.y, d.z});
+						rb_traversal_init(T, bvh, 0.0001f, 1e8f);
+						active = true;
+					}
+				}
+				exhausted = (base + (unsigned int)nIdle) >= n;
+			}
+		}
+		if(!__any_sync(0xffffffffu, active)) break;
+		bool more;
+		do {
+			if(active) {
+				if(rb_step<false, false, ORDERED>(T, bvh, ray, stack, stride, nullptr)) {
+					pb.hit[slot] = make_float4(T.best.t, T.best.u, T.best.v, __int_as_float(T.best.tri));
+					active = false;
+				}
+			}
+			const int nActive = __popc(__ballot_sync(0xffffffffu, active));
+			more = exhausted ? (nActive > 0) : (nActive >= threshold);
+		} while(more);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ shading
+RB_D void rb_queue_push(uint32_t * queue, uint32_t * counter, bool want, uint32_t value) {
+	// Warp-aggregated append: one atomicAdd per warp, lanes ranked with __ballot/__popc.
+	const unsigned int active = __activemask();
+	const unsigned int mask	  = __ballot_sync(active, want);
+	if(mask == 0) return;
+	const unsigned int lane	  = threadIdx.x & 31u;
+	const int leader		  = __ffs(mask) - 1;
+	unsigned int base		  = 0;
+	if((int)lane == leader) base = atomicAdd(counter, (unsigned int)__popc(mask));
+	base = __shfl_sync(active, base, leader);
+	if(want) queue[base + __popc(mask & ((1u << lane) - 1u))] = value;
+}
+
+__global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shade(RbFrame f, RbBatch b, RbPathBuffers pb, RbSceneDev sc, uint32_t did, unsigned long long * __restrict__ stats) {
+	const uint32_t n		 = pb.counters[rb_cnt_queue(did)];
+	const uint32_t * queue	 = pb.queue[did & 1u];
+	uint32_t * nextQueue	 = pb.queue[(did + 1u) & 1u];
+	uint32_t * nextCounter	 = pb.counters + rb_cnt_queue(did + 1u);
+	uint32_t * shadowCounter = pb.counters + rb_cnt_shadow(did);
+	const bool lastBounce	 = (did + 1u >= f.depth);
+	// Whole warps iterate together so that the warp-aggregated pushes see converged lanes.
+	const uint32_t nRounded = (n + 31u) & ~31u;
+	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nRounded; i += gridDim.x * blockDim.x) {
+		const bool valid = i < n;
+		bool continues = false, wantShadow = false;
+		uint32_t slot = 0;
+		float4 shO = make_float4(0, 0, 0, 0), shD = shO, shC = shO;
+		if(valid) {
+			slot = queue[i];
+			const float4 h	= pb.hit[slot];
+			const float4 ro = pb.rayO[slot], rd = pb.rayD[slot], at = pb.atten[slot], cl = pb.color[slot];
+			V3 rayPos = V3{ro.x, ro.y, ro.z}, rayDir = V3{rd.x, rd.y, rd.z};
+			V3 attenuation = V3{at.x, at.y, at.z}, sampleColor = V3{cl.x, cl.y, cl.z};
+			const RbPathId id  = rb_path_id(f, b, slot);
+			const uint64_t key = rb_rng_key(f.seed, id.pixel, id.sid);
+			const int tri	   = __float_as_int(h.w);
+			if(tri < 0) {
+				// No hit: background, then the path ends (PathTracer.cpp:206-209).
+				float ndcx = 0.0f, ndcy = 0.0f;
+				if(did == 0 && sc.bgMode == RB_BG_IMAGE) rb_sample_ndc(f, id, key, ndcx, ndcy);
+				sampleColor += attenuation * rb_eval_background(sc, rayDir, rayPos, ndcx, ndcy, did == 0);
+				pb.color[slot] = make_float4(sampleColor.x, sampleColor.y, sampleColor.z, 0.0f);
+			} else {
+				const uint4 ta	   = sc.triAttr[tri];
+				const RbObject obj = sc.objects[ta.w];
+				const V3 p		   = rayPos + h.x * rayDir; // :214
+				RbSurface surf;
+				rb_fetch_surface(sc, ta, h.y, h.z, surf);
+				const bool noUVs = !(obj.flags & RB_OBJ_USE_UV);
+				if(noUVs) {
+					surf.u = 0.5f;
+					surf.v = 0.5f;
+				}
+				const float4 bCol = rb_image_rgbal(sc, obj.texAlbedo, surf.u, surf.v);
+				if((obj.flags & RB_OBJ_MASKED) && bCol.w < 0.01f) {
+					// Alpha cut-out: move to the hit point and keep casting; this spends one depth level (:223-226).
+					pb.rayO[slot] = make_float4(p.x, p.y, p.z, 0.0f);
+					continues	  = !lastBounce;
+				} else if(obj.flags & RB_OBJ_EMISSIVE) {
+					sampleColor += attenuation * V3{bCol.x, bCol.y, bCol.z}; // :228-234
+					pb.color[slot] = make_float4(sampleColor.x, sampleColor.y, sampleColor.z, 0.0f);
+				} else {
+					const M3 tbn		 = rb_build_local_frame(sc, obj, surf, rayDir);
+					const V3 wo			 = normalize3(mulT(tbn, -rayDir));									// :241
+					const V3 baseColor	 = V3{powf(bCol.x, 2.2f), powf(bCol.y, 2.2f), powf(bCol.z, 2.2f)}; // :242
+					const float4 rmao	 = rb_image_rgbal(sc, obj.texRmao, surf.u, surf.v);
+					const uint32_t dim0 = 8u * (did + 1u);
+					if(sc.nLights > 0) {
+						// Direct light sampling (:248-271): one light picked uniformly.
+						const float ul = rb_rng_float(key, dim0 + 0u);
+						int lid		   = int(ul * float(sc.nLights));
+						lid			   = lid < sc.nLights ? lid : sc.nLights - 1;
+						const RbLight light = sc.lights[lid];
+						const V3 pShift		= p + 0.001f * tbn.c[2];
+						float maxDist, falloff;
+						const V3 direction = rb_light_sample(light, pShift, maxDist, falloff);
+						if(falloff > 0.0f) {
+							const V3 lwi		= normalize3(mulT(tbn, direction));
+							const V3 evalLight	= rb_ggx_eval(wo, baseColor, rmao.x, rmao.y, lwi);
+							const float lightPdf = 1.0f / float(sc.nLights);
+							const V3 illumination = ((falloff * evalLight) * V3{light.intensity[0], light.intensity[1], light.intensity[2]}) / lightPdf;
+							const V3 contrib	  = attenuation * illumination;
+							if(light.castsShadow) {
+								// The visibility walk runs in the shadow kernel; a contribution of exactly zero needs no ray.
+								if(contrib.x != 0.0f || contrib.y != 0.0f || contrib.z != 0.0f) {
+									wantShadow = true;
+									shO = make_float4(pShift.x, pShift.y, pShift.z, maxDist);
+									shD = make_float4(direction.x, direction.y, direction.z, __uint_as_float(slot));
+									shC = make_float4(contrib.x, contrib.y, contrib.z, 0.0f);
+								}
+							} else {
+								sampleColor += contrib;
+							}
+						}
+					}
+					if(!lastBounce) {
+						// Next direction from the BSDF (:274-285). On the last level the reference still draws it but
+						// never uses the result.
+						V3 wi;
+						const V3 eval = rb_ggx_sample_and_eval(wo, baseColor, rmao.x, rmao.y, rb_rng_float(key, dim0 + 1u), rb_rng_float(key, dim0 + 2u), rb_rng_float(key, dim0 + 3u), wi);
+						const V3 nextRayDir = normalize3(mul(tbn, wi));
+						attenuation *= eval;
+						const V3 newDir = normalize3(nextRayDir);
+						pb.rayO[slot]	= make_float4(p.x, p.y, p.z, 0.0f);
+						pb.rayD[slot]	= make_float4(newDir.x, newDir.y, newDir.z, 0.0f);
+						pb.atten[slot]	= make_float4(attenuation.x, attenuation.y, attenuation.z, 0.0f);
+						continues		= (attenuation.x != 0.0f || attenuation.y != 0.0f || attenuation.z != 0.0f);
+					}
+					pb.color[slot] = make_float4(sampleColor.x, sampleColor.y, sampleColor.z, 0.0f);
+				}
+			}
+		}
+		rb_queue_push(nextQueue, nextCounter, continues, slot);
+		// Shadow entries: same aggregation, three float4 per entry.
+		{
+			const unsigned int mask = __ballot_sync(0xffffffffu, wantShadow);
+			if(mask) {
+				const unsigned int lane = threadIdx.x & 31u;
+				const int leader		= __ffs(mask) - 1;
+				unsigned int base		= 0;
+				if((int)lane == leader) base = atomicAdd(shadowCounter, (unsigned int)__popc(mask));
+				base = __shfl_sync(0xffffffffu, base, leader);
+				if(wantShadow) {
+					const unsigned int e = base + __popc(mask & ((1u << lane) - 1u));
+					pb.shO[e] = shO;
+					pb.shD[e] = shD;
+					pb.shC[e] = shC;
+				}
+			}
+		}
+	}
+	if(blockIdx.x == 0 && threadIdx.x == 0 && stats) atomicAdd(stats + 2, (unsigned long long)n);
+}
+
+// ------------------------------------------------------------------------------------------------ shadow wavefront
+// PathTracer::checkVisibility (PathTracer.cpp:124-157): closest-hit queries with (mini = 0.001, maxi = maxDist); an
+// unmasked (or UV-less) occluder blocks, a masked one is looked up in its alpha channel and walked through when
+// alpha < 0.01. When no object of the scene is masked the walk degenerates to "is there any hit", so the any-hit
+// traversal (identical accept/reject decisions, early exit) is used instead (MASKED = false).
+template<bool MASKED, bool ORDERED>
+__global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shadow(RbDeviceBvh bvh, RbPathBuffers pb, RbSceneDev sc, uint32_t did, int threshold, unsigned long long * __restrict__ stats) {
+	extern __shared__ int s_stack[];
+	int * stack				= s_stack + threadIdx.x;
+	const int stride		= blockDim.x;
+	const unsigned int lane = threadIdx.x & 31u;
+	const unsigned int n	= pb.counters[rb_cnt_shadow(did)];
+	unsigned int * cursor	= pb.counters + rb_cnt_cursor_s(did);
+	bool active = false, exhausted = false;
+	unsigned int slot = 0;
+	unsigned int queries = 0;
+	V3 lpos = v3(0.0f), dir = v3(0.0f), contrib = v3(0.0f);
+	float maxDist = 0.0f;
+	RbRay ray;
+	RbTraversal T;
+	for(;;) {
+		if(!exhausted) {
+			const unsigned int idle = __ballot_sync(0xffffffffu, !active);
+			if(idle) {
+				const int nIdle	 = __popc(idle);
+				const int leader = __ffs(idle) - 1;
+				unsigned int base = 0;
+				if((int)lane == leader) base = atomicAdd(cursor, (unsigned int)nIdle);
+				base = __shfl_sync(0xffffffffu, base, leader);
+				if(!active) {
+					const unsigned int idx = base + __popc(idle & ((1u << lane) - 1u));
+					if(idx < n) {
+						const float4 o = pb.shO[idx], d = pb.shD[idx], c = pb.shC[idx];
+						lpos	= V3{o.x, o.y, o.z};
+						maxDist = o.w;
+						dir		= V3{d.x, d.y, d.z};
+						slot	= __float_as_uint(d.w);
+						contrib = V3{c.x, c.y, c.z};
+						if(maxDist > 0.0f) {
+							ray = rb_make_ray(lpos, dir);
+							rb_traversal_init(T, bvh, 0.001f, maxDist);
+							active = true;
+							++queries;
+						} else {
+							// `while(maxDist > 0.0f)` never entered: visible (:127, :156).
+							float4 cl = pb.color[slot];
+							cl.x += contrib.x; cl.y += contrib.y; cl.z += contrib.z;
+							pb.color[slot] = cl;
+						}
+					}
+				}
+				exhausted = (base + (unsigned int)nIdle) >= n;
+			}
+		}
+		if(!__any_sync(0xffffffffu, active)) break;
+		bool more;
+		do {
+			if(active) {
+				if(rb_step<!MASKED, false, ORDERED>(T, bvh, ray, stack, stride, nullptr)) {
+					bool visible = false, finished = true;
+					if(T.best.tri < 0) {
+						visible = true;
+					} else if(MASKED) {
+						const uint4 ta	   = sc.triAttr[T.best.tri];
+						const RbObject obj = sc.objects[ta.w];
+						if((obj.flags & RB_OBJ_MASKED) && (obj.flags & RB_OBJ_USE_UV)) {
+							float lu, lv;
+							rb_fetch_uv(sc, ta, T.best.u, T.best.v, lu, lv);
+							const float alpha = rb_image_rgbal(sc, obj.texAlbedo, lu, lv).w;
+							if(alpha < 0.01f) {
+								// Transparent texel: shift to the hit, shorten the segment, cast again (:149-151).
+								maxDist = maxDist - T.best.t;
+								lpos	= lpos + T.best.t * dir;
+								if(maxDist > 0.0f) {
+									ray = rb_make_ray(lpos, dir);
+									rb_traversal_init(T, bvh, 0.001f, maxDist);
+									finished = false;
+									++queries;
+								} else {
+									visible = true;
+								}
+							}
+						}
+					}
+					if(finished) {
+						if(visible) {
+							float4 cl = pb.color[slot];
+							cl.x += contrib.x; cl.y += contrib.y; cl.z += contrib.z;
+							pb.color[slot] = cl;
+						}
+						active = false;
+					}
+				}
+			}
+			const int nActive = __popc(__ballot_sync(0xffffffffu, active));
+			more = exhausted ? (nActive > 0) : (nActive >= threshold);
+		} while(more);
+	}
+	if(stats) {
+		for(int off = 16; off > 0; off >>= 1) queries += __shfl_down_sync(0xffffffffu, queries, off);
+		if(lane == 0 && queries) atomicAdd(stats + 1, (unsigned long long)queries);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ accumulation
+// `render.rgb(x,y) += glm::min(sampleColor, 5.0f)` (PathTracer.cpp:288): one warp per pixel sums the clamped samples of
+// the batch in a fixed order (lane-strided, then a shuffle tree), so the image is reproducible bit for bit.
+__global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_accumulate(RbFrame f, RbBatch b, RbPathBuffers pb, float * __restrict__ sum) {
+	const unsigned int lane	 = threadIdx.x & 31u;
+	const unsigned int warp	 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const unsigned int nwarp = (gridDim.x * blockDim.x) >> 5;
+	for(uint32_t p = warp; p < b.npixels; p += nwarp) {
+		float r = 0.0f, g = 0.0f, bl = 0.0f;
+		for(uint32_t s = lane; s < b.schunk; s += 32u) {
+			const float4 c = pb.color[p * b.schunk + s];
+			r += (5.0f < c.x) ? 5.0f : c.x; // glm::min(x, 5.0f)
+			g += (5.0f < c.y) ? 5.0f : c.y;
+			bl += (5.0f < c.z) ? 5.0f : c.z;
+		}
+		for(int off = 16; off > 0; off >>= 1) {
+			r += __shfl_down_sync(0xffffffffu, r, off);
+			g += __shfl_down_sync(0xffffffffu, g, off);
+			bl += __shfl_down_sync(0xffffffffu, bl, off);
+		}
+		if(lane == 0) {
+			const uint32_t lp	= b.pixel0 + p;
+			const uint32_t y	= rb_tile_row(f, lp / f.width);
+			const size_t pixel = size_t(y) * f.width + lp % f.width;
+			sum[3 * pixel + 0] += r;
+			sum[3 * pixel + 1] += g;
+			sum[3 * pixel + 2] += bl;
+		}
+	}
+}
+
+// `render.rgb(x,y) / float(samples)` (PathTracer.cpp:291-292) on the rows of this call's tile.
+__global__ void rb_k_pt_resolve(RbFrame f, const float * __restrict__ sum, uint32_t components, float * __restrict__ pixels) {
+	const uint32_t n = f.localRows * f.width;
+	for(uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < n; lp += gridDim.x * blockDim.x) {
+		const uint32_t y   = rb_tile_row(f, lp / f.width);
+		const size_t pixel = size_t(y) * f.width + lp % f.width;
+		for(int c = 0; c < 3; ++c) {
+			const float v = pixels[pixel * components + c] + sum[3 * pixel + c];
+			pixels[pixel * components + c] = v / float(f.samples);
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct rb_pathtracer {
+	rb_scene * scene = nullptr;
+	RbPathBuffers pb = {};
+	size_t capacity	 = 0;
+	unsigned long long * d_stats = nullptr;
+	rb_render_stats stats = {};
+	int sms = 0;
+};
+
+static void rb_pt_free(rb_pathtracer * pt) {
+	cudaFree(pt->pb.rayO);
+	cudaFree(pt->pb.rayD);
+	cudaFree(pt->pb.atten);
+	cudaFree(pt->pb.color);
+	cudaFree(pt->pb.hit);
+	cudaFree(pt->pb.queue[0]);
+	cudaFree(pt->pb.queue[1]);
+	cudaFree(pt->pb.shO);
+	cudaFree(pt->pb.shD);
+	cudaFree(pt->pb.shC);
+	cudaFree(pt->pb.counters);
+	pt->pb		 = RbPathBuffers{};
+	pt->capacity = 0;
+}
+
+#define RB_PT_MAX_DEPTH 64
+
+static rb_status rb_pt_reserve(rb_pathtracer * pt, size_t paths) {
+	if(paths <= pt->capacity) return RB_OK;
+	rb_pt_free(pt);
+	RB_CUDA(cudaMalloc(&pt->pb.rayO, paths * sizeof(float4)));
+	RB_CUDA(cudaMalloc(&pt->pb.rayD, paths * sizeof(float4)));
+	RB_CUDA(cudaMalloc(&pt->pb.atten, paths * sizeof(float4)));
+	RB_CUDA(cudaMalloc(&pt->pb.color, paths * sizeof(float4)));
+	RB_CUDA(cudaMalloc(&pt->pb.hit, paths * sizeof(float4)));
+	RB_CUDA(cudaMalloc(&pt->pb.queue[0], paths * sizeof(uint32_t)));
+	RB_CUDA(cudaMalloc(&pt->pb.queue[1], paths * sizeof(uint32_t)));
+	RB_CUDA(cudaMalloc(&pt->pb.shO, paths * sizeof(float4)));
+	RB_CUDA(cudaMalloc(&pt->pb.shD, paths * sizeof(float4)));
+	RB_CUDA(cudaMalloc(&pt->pb.shC, paths * sizeof(float4)));
+	RB_CUDA(cudaMalloc(&pt->pb.counters, 4 * (RB_PT_MAX_DEPTH + 1) * sizeof(uint32_t)));
+	pt->capacity = paths;
+	return RB_OK;
+}
+
+extern "C" rb_status rb_pathtracer_create(rb_scene * scene, rb_pathtracer ** out) {
+	if(!scene || !out) return rb_fail(RB_ERR_INVALID, "rb_pathtracer_create: null argument");
+	RB_REQUIRE_DEVICE();
+	if(!scene->committed) return rb_fail(RB_ERR_INVALID, "rb_pathtracer_create: call rb_scene_commit first");
+	rb_pathtracer * pt = new rb_pathtracer();
+	pt->scene		   = scene;
+	cudaDeviceGetAttribute(&pt->sms, cudaDevAttrMultiProcessorCount, scene->raycaster->device);
+	if(cudaMalloc(&pt->d_stats, 4 * sizeof(unsigned long long)) != cudaSuccess) {
+		delete pt;
+		return rb_fail(RB_ERR_CUDA, "rb_pathtracer_create: cudaMalloc failed");
+	}
+	*out = pt;
+	return RB_OK;
+}
+
+extern "C" void rb_pathtracer_destroy(rb_pathtracer * pt) {
+	if(!pt) return;
+	if(rb_have_device()) {
+		rb_pt_free(pt);
+		cudaFree(pt->d_stats);
+	}
+	delete pt;
+}
+
+static uint32_t rb_round_samples(uint32_t samples) {
+	// size_t(std::pow(2, std::round(std::log2(float(samples))))) (PathTracer.cpp:169-170)
+	if(samples == 0) return 1;
+	return uint32_t(std::pow(2.0, std::round(std::log2(float(samples)))));
+}
+
+static rb_status rb_pt_frame(const rb_camera * cam, uint32_t width, uint32_t height, uint32_t samples, uint32_t depth, const rb_render_opts * opts, RbFrame & f) {
+	if(!cam) return rb_fail(RB_ERR_INVALID, "render: null camera");
+	if(width == 0 || height == 0) return rb_fail(RB_ERR_INVALID, "render: empty image");
+	if(depth > RB_PT_MAX_DEPTH) return rb_fail(RB_ERR_UNSUPPORTED, "render: depth %u exceeds %d", depth, RB_PT_MAX_DEPTH);
+	std::memcpy(f.eye, cam->eye, sizeof(f.eye));
+	std::memcpy(f.corner, cam->corner, sizeof(f.corner));
+	std::memcpy(f.dx, cam->dx, sizeof(f.dx));
+	std::memcpy(f.dy, cam->dy, sizeof(f.dy));
+	f.width	  = width;
+	f.height  = height;
+	f.samples = rb_round_samples(samples);
+	// getSampleGrid (PathTracer.cpp:57-69)
+	const int k = int(std::floor(std::log2(double(f.samples))));
+	f.cellsX = f.cellsY = uint32_t(std::pow(2, k / 2));
+	if(k % 2 == 1) {
+		f.cellsX = uint32_t(std::pow(2, (k + 1) / 2));
+		f.cellsY = uint32_t(std::pow(2, (k - 1) / 2));
+	}
+	f.cellSizeX = 1.0f / float(int(f.cellsX)); // 1.0f / glm::vec2(cellCount) (:179)
+	f.cellSizeY = 1.0f / float(int(f.cellsY));
+	f.depth		= depth;
+	f.seed		= opts ? opts->seed : 0;
+	f.tileRows	= (opts && opts->tile_rows) ? opts->tile_rows : 1;
+	f.tileCount = (opts && opts->tile_count) ? opts->tile_count : 1;
+	f.tileIndex = opts ? opts->tile_index : 0;
+	if(f.tileIndex >= f.tileCount) return rb_fail(RB_ERR_INVALID, "render: tile_index %u >= tile_count %u", f.tileIndex, f.tileCount);
+	f.sampleCount = (opts && opts->sample_count) ? opts->sample_count : 1;
+	f.sampleIndex = opts ? opts->sample_index : 0;
+	if(f.sampleIndex >= f.sampleCount) return rb_fail(RB_ERR_INVALID, "render: sample_index %u >= sample_count %u", f.sampleIndex, f.sampleCount);
+	uint32_t rows = 0;
+	for(uint32_t y = 0; y < height; ++y) {
+		if(f.tileCount <= 1 || (y / f.tileRows) % f.tileCount == f.tileIndex) ++rows;
+	}
+	f.localRows = rows;
+	return RB_OK;
+}
+
+template<typename K>
+static rb_status rb_pt_grid(K kernel, size_t smem, int sms, unsigned & grid) {
+	if(smem > 48 * 1024) RB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+	int perSm = 0;
+	RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, RB_PT_BLOCK, smem));
+	if(perSm < 1) return rb_fail(RB_ERR_CUDA, "path-tracer kernel does not fit on an SM");
+	grid = unsigned(perSm * sms);
+	return RB_OK;
+}
+
+extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_camera * camera, uint32_t width, uint32_t height, uint32_t samples, uint32_t depth, float * d_sum, const rb_render_opts * opts, void * stream) {
+	if(!pt || !d_sum) return rb_fail(RB_ERR_INVALID, "rb_pathtracer_render_device: null argument");
+	RB_REQUIRE_DEVICE();
+	RbFrame f;
+	rb_status st = rb_pt_frame(camera, width, height, samples, depth, opts, f);
+	if(st) return st;
+	cudaStream_t s		 = static_cast<cudaStream_t>(stream);
+	rb_scene * sc		 = pt->scene;
+	rb_raycaster * rc	 = sc->raycaster;
+	const bool ordered	 = opts ? (opts->trace_mode == RB_TRACE_ORDERED) : false;
+	const int threshold = rc->fetchThreshold;
+	RB_CUDA(cudaSetDevice(rc->device));
+	RB_CUDA(cudaMemsetAsync(d_sum, 0, size_t(width) * height * 3 * sizeof(float), s));
+	RB_CUDA(cudaMemsetAsync(pt->d_stats, 0, 4 * sizeof(unsigned long long), s));
+
+	const uint32_t localSamples = (f.samples > f.sampleIndex) ? (f.samples - f.sampleIndex + f.sampleCount - 1) / f.sampleCount : 0;
+	const uint64_t localPixels	= uint64_t(f.localRows) * width;
+	uint64_t launches = 0;
+	if(localSamples && localPixels && depth) {
+		size_t maxPaths = (opts && opts->max_paths_in_flight) ? opts->max_paths_in_flight : (size_t(1) << 22);
+		if(maxPaths < 1024) maxPaths = 1024;
+		const uint32_t schunk	  = uint32_t(localSamples < maxPaths ? localSamples : maxPaths);
+		uint64_t pixelsPerBatch = maxPaths / schunk;
+		if(pixelsPerBatch < 1) pixelsPerBatch = 1;
+		if(pixelsPerBatch > localPixels) pixelsPerBatch = localPixels;
+		st = rb_pt_reserve(pt, size_t(pixelsPerBatch) * schunk);
+		if(st) return st;
+
+		const size_t smem = rb_trace_smem_bytes(rc, RB_PT_BLOCK);
+		unsigned gridTrace = 0, gridShadow = 0, gridFlat = unsigned(pt->sms * 8);
+		auto kTrace = ordered ? rb_k_pt_trace<true> : rb_k_pt_trace<false>;
+		st = rb_pt_grid(kTrace, smem, pt->sms, gridTrace);
+		if(st) return st;
+		const bool masked = sc->dev.anyMasked != 0;
+		auto kShadow = masked ? (ordered ? rb_k_pt_shadow<true, true> : rb_k_pt_shadow<true, false>) : (ordered ? rb_k_pt_shadow<false, true> : rb_k_pt_shadow<false, false>);
+		st = rb_pt_grid(kShadow, smem, pt->sms, gridShadow);
+		if(st) return st;
+
+		for(uint32_t sample0 = 0; sample0 < localSamples; sample0 += schunk) {
+			const uint32_t sc_n = (localSamples - sample0 < schunk) ? (localSamples - sample0) : schunk;
+			for(uint64_t pixel0 = 0; pixel0 < localPixels; pixel0 += pixelsPerBatch) {
+				RbBatch b;
+				b.pixel0  = uint32_t(pixel0);
+				b.npixels = uint32_t((localPixels - pixel0 < pixelsPerBatch) ? (localPixels - pixel0) : pixelsPerBatch);
+				b.sample0 = sample0;
+				b.schunk  = sc_n;
+				RB_CUDA(cudaMemsetAsync(pt->pb.counters, 0, 4 * (RB_PT_MAX_DEPTH + 1) * sizeof(uint32_t), s));
+				rb_k_pt_raygen<<<gridFlat, RB_PT_BLOCK, 0, s>>>(f, b, pt->pb);
+				++launches;
+				for(uint32_t did = 0; did < depth; ++did) {
+					kTrace<<<gridTrace, RB_PT_BLOCK, smem, s>>>(rc->dev, pt->pb, pt->pb.queue[did & 1u], did, threshold, pt->d_stats);
+					rb_k_pt_shade<<<gridFlat, RB_PT_BLOCK, 0, s>>>(f, b, pt->pb, sc->dev, did, pt->d_stats);
+					launches += 2;
+					if(sc->dev.nLights > 0) {
+						kShadow<<<gridShadow, RB_PT_BLOCK, smem, s>>>(rc->dev, pt->pb, sc->dev, did, threshold, pt->d_stats);
+						++launches;
+					}
+				}
+				rb_k_pt_accumulate<<<gridFlat, RB_PT_BLOCK, 0, s>>>(f, b, pt->pb, d_sum);
+				++launches;
+				RB_CUDA(cudaGetLastError());
+			}
+		}
+	}
+	pt->stats.kernel_launches = launches;
+	pt->stats.samples		  = localPixels * localSamples;
+	return RB_OK;
+}
+
+extern "C" rb_status rb_pathtracer_resolve_device(rb_pathtracer * pt, const float * d_sum, uint32_t width, uint32_t height, uint32_t samples, uint32_t components, float * d_pixels, const rb_render_opts * opts, void * stream) {
+	if(!pt || !d_sum || !d_pixels) return rb_fail(RB_ERR_INVALID, "rb_pathtracer_resolve_device: null argument");
+	RB_REQUIRE_DEVICE();
+	if(components < 3) return rb_fail(RB_ERR_INVALID, "rb_pathtracer_resolve_device: expected at least 3 components");
+	RbFrame f;
+	rb_camera cam;
+	std::memset(&cam, 0, sizeof(cam));
+	rb_status st = rb_pt_frame(&cam, width, height, samples, 1, opts, f);
+	if(st) return st;
+	rb_k_pt_resolve<<<unsigned(pt->sms * 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(f, d_sum, components, d_pixels);
+	RB_CUDA(cudaGetLastError());
+	pt->stats.kernel_launches += 1;
+	return RB_OK;
+}
+
+extern "C" rb_status rb_pathtracer_render(rb_pathtracer * pt, const rb_camera * camera, uint32_t width, uint32_t height, uint32_t samples, uint32_t depth, uint32_t components, float * pixels, const rb_render_opts * opts) {
+	if(!pt || !pixels) return rb_fail(RB_ERR_INVALID, "rb_pathtracer_render: null argument");
+	RB_REQUIRE_DEVICE();
+	if(components < 3) return rb_fail(RB_ERR_INVALID, "rb_pathtracer_render: expected an RGB image (components >= 3)"); // PathTracer.cpp:166-168
+	RB_CUDA(cudaSetDevice(pt->scene->raycaster->device));
+	cudaStream_t s = cudaStreamPerThread;
+	const size_t npx = size_t(width) * height;
+	float *d_sum = nullptr, *d_pixels = nullptr;
+	RB_CUDA(cudaMalloc(&d_sum, npx * 3 * sizeof(float)));
+	if(cudaMalloc(&d_pixels, npx * components * sizeof(float)) != cudaSuccess) {
+		cudaFree(d_sum);
+		return rb_fail(RB_ERR_CUDA, "rb_pathtracer_render: cudaMalloc failed");
+	}
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0);
+	cudaEventCreate(&e1);
+	rb_status st = RB_OK;
+	do {
+		if(cudaMemcpyAsync(d_pixels, pixels, npx * components * sizeof(float), cudaMemcpyHostToDevice, s) != cudaSuccess) { st = rb_fail(RB_ERR_CUDA, "upload failed"); break; }
+		cudaEventRecord(e0, s);
+		st = rb_pathtracer_render_device(pt, camera, width, height, samples, depth, d_sum, opts, s);
+		if(st) break;
+		st = rb_pathtracer_resolve_device(pt, d_sum, width, height, samples, components, d_pixels, opts, s);
+		if(st) break;
+		cudaEventRecord(e1, s);
+		if(cudaMemcpyAsync(pixels, d_pixels, npx * components * sizeof(float), cudaMemcpyDeviceToHost, s) != cudaSuccess) { st = rb_fail(RB_ERR_CUDA, "download failed"); break; }
+		unsigned long long hs[4] = {0, 0, 0, 0};
+		cudaMemcpyAsync(hs, pt->d_stats, sizeof(hs), cudaMemcpyDeviceToHost, s);
+		const cudaError_t e = cudaStreamSynchronize(s);
+		if(e != cudaSuccess) { st = rb_fail(RB_ERR_CUDA, "render failed: %s", cudaGetErrorString(e)); break; }
+		float ms = 0.0f;
+		cudaEventElapsedTime(&ms, e0, e1);
+		pt->stats.rays_closest	 = hs[0];
+		pt->stats.rays_shadow	 = hs[1];
+		pt->stats.shaded_hits	 = hs[2];
+		pt->stats.device_seconds = double(ms) * 1e-3;
+	} while(false);
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(d_sum);
+	cudaFree(d_pixels);
+	return st;
+}
+
+extern "C" rb_status rb_pathtracer_stats(const rb_pathtracer * pt, rb_render_stats * out) {
+	if(!pt || !out) return rb_fail(RB_ERR_INVALID, "rb_pathtracer_stats: null argument");
+	*out = pt->stats;
+	if(rb_have_device() && pt->d_stats) {
+		// Counters of the last render_device call (blocks until that work has finished).
+		unsigned long long hs[4] = {0, 0, 0, 0};
+		RB_CUDA(cudaDeviceSynchronize());
+		RB_CUDA(cudaMemcpy(hs, pt->d_stats, sizeof(hs), cudaMemcpyDeviceToHost));
+		out->rays_closest = hs[0];
+		out->rays_shadow  = hs[1];
+		out->shaded_hits  = hs[2];
+	}
+	return RB_OK;
+}

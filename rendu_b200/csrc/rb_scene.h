@@ -1,0 +1,39 @@
+// rb_scene.h — host-side scene and path-tracer handles (internal).
+#pragma once
+#include "rb_internal.h"
+#include "rb_shade.cuh"
+
+struct RbHostObject {
+	std::vector<float> positions; // model space, handed to the raycaster at commit
+	float model[16];
+	size_t nverts = 0, nindices = 0;
+	uint32_t vertOffset = 0, indexOffset = 0;
+	RbObject dev;
+};
+
+struct rb_scene {
+	std::vector<float> texels; // RGBA fp32 pool
+	std::vector<RbTexInfo> textures;
+	std::vector<RbHostObject> objects;
+	std::vector<RbLight> lights;
+	std::vector<float> vertexAttr; // 12 floats per vertex
+	std::vector<uint32_t> indices;
+	uint32_t bgMode	 = RB_BG_COLOR;
+	float bgColor[3] = {0, 0, 0};
+	float sunDir[3]	 = {0, 1, 0};
+	int32_t bgTex[6] = {-1, -1, -1, -1, -1, -1};
+	int32_t skyLut	 = -1;
+	bool committed	 = false;
+
+	rb_raycaster * raycaster = nullptr;
+	float * d_texels		 = nullptr;
+	RbTexInfo * d_textures	 = nullptr;
+	RbObject * d_objects	 = nullptr;
+	RbLight * d_lights		 = nullptr;
+	float * d_vertexAttr	 = nullptr;
+	uint4 * d_triAttr		 = nullptr;
+	uint32_t * d_indices	 = nullptr;
+	uint32_t * d_objVertOffset	= nullptr;
+	uint32_t * d_objIndexOffset = nullptr;
+	RbSceneDev dev = {};
+};

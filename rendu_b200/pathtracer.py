@@ -1,0 +1,202 @@
+"""Python mirror of the reference ``PathTracer`` (src/apps/pathtracer/PathTracer.hpp:10-75) and of the read-only scene
+data it consumes, over the C ABI. ``Scene`` takes the flattened description (plain numpy arrays: objects in
+``scene->objects`` order, textures as float images, lights, background) and uploads it; ``PathTracer.render`` follows
+the reference signature ``render(camera, samples, depth, image)`` and accumulates into the caller's image.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import Camera, LightDesc, ObjectDesc, RenderOpts, RenderStats, check, lib, ptr
+from .raycaster import BUILD_REFERENCE, Raycaster
+
+BG_COLOR, BG_IMAGE, BG_SKYBOX, BG_ATMOSPHERE = 0, 1, 2, 3
+LIGHT_POINT, LIGHT_SPOT, LIGHT_DIRECTIONAL = 0, 1, 2
+MATERIAL_EMISSIVE = 8  # Material::Type::Emissive
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+class Scene:
+    """Scene::objects / lights / background flattened."""
+
+    def __init__(self, description, build_mode=BUILD_REFERENCE):
+        h = C.c_void_p()
+        check(lib().rb_scene_create(C.byref(h)))
+        self._h = h
+        self._keep = []
+        L = lib()
+        tex_ids = []
+        for t in description["textures"]:
+            t = np.ascontiguousarray(t, np.float32)
+            out = C.c_int32(-1)
+            check(L.rb_scene_add_texture(self._h, ptr(t), t.shape[1], t.shape[0], t.shape[2] if t.ndim == 3 else 1, C.byref(out)))
+            tex_ids.append(out.value)
+
+        def tid(i):
+            return tex_ids[i] if i is not None and i >= 0 else -1
+
+        for o in description["objects"]:
+            d = ObjectDesc()
+            arrs = {}
+            for key, width in (("positions", 3), ("normals", 3), ("tangents", 3), ("bitangents", 3), ("texcoords", 2)):
+                a = np.ascontiguousarray(o[key], np.float32).reshape(-1, width)
+                arrs[key] = a
+            idx = np.ascontiguousarray(o["indices"], np.uint32).reshape(-1)
+            nverts = arrs["positions"].shape[0]
+            for key in ("normals", "tangents", "bitangents"):
+                if arrs[key].shape[0] != nverts:
+                    raise _capi.RenduError(1, "object lacks per-vertex %s (the path tracer requires local tangent frames)" % key)
+            d.positions, d.normals, d.tangents, d.bitangents = [arrs[k].ctypes.data for k in ("positions", "normals", "tangents", "bitangents")]
+            d.texcoords = arrs["texcoords"].ctypes.data if arrs["texcoords"].shape[0] == nverts else None
+            d.nverts, d.indices, d.nindices = nverts, idx.ctypes.data, idx.size
+            d.model = (C.c_float * 16)(*[float(x) for x in np.asarray(o["model"], np.float32).reshape(16)])
+            texs = list(o["textures"]) + [-1, -1, -1]
+            d.tex_albedo, d.tex_normal, d.tex_rmao = tid(texs[0]), tid(texs[1]), tid(texs[2])
+            d.emissive = 1 if o["material_type"] == MATERIAL_EMISSIVE else 0
+            d.masked = 1 if o["masked"] else 0
+            d.use_texcoords = 1 if o["use_uv"] else 0
+            self._keep.append((arrs, idx))
+            check(L.rb_scene_add_object(self._h, C.byref(d)))
+        for l in description["lights"]:
+            d = LightDesc()
+            d.kind, d.casts_shadow = int(l["kind"]), 1 if l["casts_shadow"] else 0
+            d.intensity, d.position, d.direction = _f3(l["intensity"]), _f3(l["position"]), _f3(l["direction"])
+            d.radius, d.inner_angle, d.outer_angle = float(l["radius"]), float(l["inner"]), float(l["outer"])
+            check(L.rb_scene_add_light(self._h, C.byref(d)))
+        bg = description["background"]
+        texs = np.array([tid(i) for i in bg.get("textures", [])], np.int32)
+        color = np.asarray(bg.get("color", (0, 0, 0)), np.float32)
+        sun = np.asarray(bg.get("sun", (0, 1, 0)), np.float32)
+        lut = tid(bg.get("sky_lut", -1))
+        check(L.rb_scene_set_background(self._h, int(bg["mode"]), ptr(color), ptr(texs) if texs.size else None, texs.size, ptr(sun), lut))
+        check(L.rb_scene_commit(self._h, int(build_mode)))
+        self._keep = []
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            try:
+                lib().rb_scene_destroy(self._h)
+            except Exception:
+                pass
+            self._h = None
+
+    def raycaster(self):
+        return Raycaster(_handle=lib().rb_scene_raycaster(self._h), _owner=self)
+
+
+def make_camera(eye, corner, dx, dy):
+    c = Camera()
+    c.eye, c.corner, c.dx, c.dy = _f3(eye), _f3(corner), _f3(dx), _f3(dy)
+    return c
+
+
+def make_opts(seed=0, tile=None, samples=None, trace_mode=0, max_paths=0):
+    o = RenderOpts()
+    o.seed = int(seed)
+    if tile is not None:
+        o.tile_rows, o.tile_index, o.tile_count = [int(x) for x in tile]
+    if samples is not None:
+        o.sample_index, o.sample_count = [int(x) for x in samples]
+    o.trace_mode = int(trace_mode)
+    o.max_paths_in_flight = int(max_paths)
+    return o
+
+
+class PathTracer:
+    """PathTracer(scene); render(camera, samples, depth, image); raycaster()."""
+
+    def __init__(self, scene):
+        self._scene = scene
+        h = C.c_void_p()
+        check(lib().rb_pathtracer_create(scene._h, C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            try:
+                lib().rb_pathtracer_destroy(self._h)
+            except Exception:
+                pass
+            self._h = None
+
+    def raycaster(self):
+        return self._scene.raycaster()
+
+    def render(self, camera, samples, depth, image, opts=None):
+        """`image` is the caller's float32 (H, W, C>=3) array; as in the reference the result is accumulated into it and
+        divided by the sample count, so pass zeros (PathTracer.cpp:288-292). `camera` is a dict/struct with eye, corner,
+        dx, dy — what Camera::pixelShifts / position give on the host."""
+        if not (isinstance(image, np.ndarray) and image.dtype == np.float32 and image.ndim == 3 and image.flags["C_CONTIGUOUS"]):
+            raise ValueError("image must be a C-contiguous float32 array of shape (H, W, C)")
+        cam = camera if isinstance(camera, Camera) else make_camera(camera["eye"], camera["corner"], camera["dx"], camera["dy"])
+        h, w, c = image.shape
+        check(lib().rb_pathtracer_render(self._h, C.byref(cam), w, h, int(samples), int(depth), c, ptr(image), C.byref(opts) if opts is not None else None))
+        return image
+
+    def render_device(self, camera, width, height, samples, depth, d_sum, opts=None, stream=0):
+        cam = camera if isinstance(camera, Camera) else make_camera(camera["eye"], camera["corner"], camera["dx"], camera["dy"])
+        check(lib().rb_pathtracer_render_device(self._h, C.byref(cam), width, height, int(samples), int(depth), d_sum, C.byref(opts) if opts is not None else None, stream))
+
+    def resolve_device(self, d_sum, width, height, samples, components, d_pixels, opts=None, stream=0):
+        check(lib().rb_pathtracer_resolve_device(self._h, d_sum, width, height, int(samples), components, d_pixels, C.byref(opts) if opts is not None else None, stream))
+
+    def stats(self):
+        s = RenderStats()
+        check(lib().rb_pathtracer_stats(self._h, C.byref(s)))
+        return dict(rays_closest=int(s.rays_closest), rays_shadow=int(s.rays_shadow), samples=int(s.samples), shaded=int(s.shaded_hits),
+                    kernel_launches=int(s.kernel_launches), device_seconds=float(s.device_seconds))
+
+
+def save_scene(path, description):
+    """Flattened scene -> one compressed .npz (used for golden fixtures)."""
+    out = {"n_objects": len(description["objects"]), "n_lights": len(description["lights"]), "n_textures": len(description["textures"])}
+    for i, t in enumerate(description["textures"]):
+        out["tex%d" % i] = t
+    for i, o in enumerate(description["objects"]):
+        for k in ("positions", "normals", "tangents", "bitangents", "texcoords", "indices", "model"):
+            out["obj%d_%s" % (i, k)] = o[k]
+        out["obj%d_meta" % i] = np.array([o["use_uv"], o["material_type"], o["masked"]] + list(o["textures"]) + [-1] * (3 - len(o["textures"])), np.int64)
+    for i, l in enumerate(description["lights"]):
+        out["light%d" % i] = np.concatenate([[l["kind"], l["casts_shadow"]], l["intensity"], l["position"], l["direction"], [l["radius"], l["inner"], l["outer"]]]).astype(np.float64)
+    bg = description["background"]
+    out["bg_meta"] = np.array([bg["mode"], bg.get("sky_lut", -1)] + list(bg.get("textures", [])), np.int64)
+    out["bg_color"], out["bg_sun"] = np.asarray(bg["color"], np.float32), np.asarray(bg["sun"], np.float32)
+    np.savez_compressed(path, **out)
+
+
+def load_scene(path):
+    z = np.load(path)
+    textures = [z["tex%d" % i] for i in range(int(z["n_textures"]))]
+    objects = []
+    for i in range(int(z["n_objects"])):
+        meta = z["obj%d_meta" % i]
+        o = {k: z["obj%d_%s" % (i, k)] for k in ("positions", "normals", "tangents", "bitangents", "texcoords", "indices", "model")}
+        o.update(use_uv=bool(meta[0]), material_type=int(meta[1]), masked=bool(meta[2]), textures=[int(x) for x in meta[3:6]])
+        objects.append(o)
+    lights = []
+    for i in range(int(z["n_lights"])):
+        a = z["light%d" % i]
+        lights.append(dict(kind=int(a[0]), casts_shadow=bool(a[1]), intensity=a[2:5].astype(np.float32), position=a[5:8].astype(np.float32),
+                           direction=a[8:11].astype(np.float32), radius=float(np.float32(a[11])), inner=float(np.float32(a[12])), outer=float(np.float32(a[13]))))
+    m = z["bg_meta"]
+    bg = dict(mode=int(m[0]), sky_lut=int(m[1]), textures=[int(x) for x in m[2:]], color=z["bg_color"], sun=z["bg_sun"])
+    return dict(objects=objects, lights=lights, background=bg, textures=textures)
+
+
+def smoke():
+    """Tiny render used by __graft_entry__.smoke(): a two-quad scene with one point light, checked for sanity here and
+    against the oracle in the tests."""
+    from . import workloads as wl
+    desc = wl.tiny_scene()
+    sc = Scene(desc)
+    pt = PathTracer(sc)
+    img = np.zeros((32, 32, 3), np.float32)
+    pt.render(wl.tiny_camera(), 16, 4, img, make_opts(seed=3))
+    if not (np.isfinite(img).all() and img.max() > 0.0):
+        raise RuntimeError("path tracer smoke render is empty or non-finite")
+    st = pt.stats()
+    print("path tracer smoke ok: mean %.4f, %d closest + %d shadow rays, %d launches" % (float(img.mean()), st["rays_closest"], st["rays_shadow"], st["kernel_launches"]))

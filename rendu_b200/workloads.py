@@ -108,3 +108,144 @@ def random_rays(n, seed, lo=(-1.2, -0.3, -1.2), hi=(1.2, 1.6, 1.2)):
     ph = F(2 * np.pi) * uniform01(seed, idx, 4)
     d = np.stack([st * np.cos(ph), st * np.sin(ph), ct], -1)
     return o.astype(F), d.astype(F)
+
+
+# ------------------------------------------------------------------------------------------------ scenes (host-side data only)
+def camera_shifts(eye, center, up, fov, ratio):
+    """Camera::pose (Camera.cpp:10-18) + Camera::pixelShifts (Camera.cpp:42-49) in fp32: what PathTracer::render reads
+    from the Camera on the host (PathTracer.cpp:177,197)."""
+    eye, center, up = [np.asarray(v, F) for v in (eye, center, up)]
+
+    def nrm(v):
+        return (v * (F(1) / np.sqrt(F(v[0] * v[0] + v[1] * v[1] + v[2] * v[2])))).astype(F)
+
+    def cross(x, y):
+        return np.array([x[1] * y[2] - y[1] * x[2], x[2] * y[0] - y[2] * x[0], x[0] * y[1] - y[0] * x[1]], F)
+
+    upn = nrm(up)
+    view = nrm((center - eye).astype(F))
+    right = cross(view, upn)
+    up2 = cross(right, view)
+    hs = F(np.tan(F(0.5) * F(fov)))
+    ws = F(ratio) * hs
+    d = (eye - center).astype(F)
+    dist = F(np.sqrt(F(d[0] * d[0] + d[1] * d[1] + d[2] * d[2])))
+    corner = (center + dist * (-ws * right + hs * up2)).astype(F)
+    dx = (F(2) * ws * dist * right).astype(F)
+    dy = (F(-2) * hs * dist * up2).astype(F)
+    return dict(eye=eye, corner=corner, dx=dx, dy=dy)
+
+
+def _const_tex(rgba, res=8):
+    t = np.empty((res, res, 4), F)
+    t[:] = np.asarray(rgba, F)
+    return t
+
+
+def _quad(p0, p1, p2, p3, uv_scale=1.0):
+    """Quad (two triangles) with a flat tangent frame: positions, normals, tangents, bitangents, texcoords, indices."""
+    P = np.array([p0, p1, p2, p3], F)
+    t = P[1] - P[0]
+    b = P[3] - P[0]
+    n = np.cross(t, b)
+    t, b, n = [(v / np.linalg.norm(v)).astype(F) for v in (t, b, n)]
+    uv = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], F) * F(uv_scale)
+    idx = np.array([0, 1, 2, 0, 2, 3], np.uint32)
+    return dict(positions=P, normals=np.tile(n, (4, 1)), tangents=np.tile(t, (4, 1)), bitangents=np.tile(b, (4, 1)), texcoords=uv, indices=idx)
+
+
+def _obj(geom, textures, model=None, use_uv=False, emissive=False, masked=False):
+    o = dict(geom)
+    o.update(model=np.eye(4, dtype=F).reshape(16) if model is None else np.asarray(model, F).reshape(16), use_uv=use_uv,
+             material_type=8 if emissive else 1, masked=masked, textures=list(textures))
+    return o
+
+
+def tiny_scene():
+    """Floor + back wall + a small emissive panel, one point light, constant textures: enough to exercise every kernel."""
+    tex = [_const_tex((0.8, 0.8, 0.8, 1)), _const_tex((0.5, 0.5, 1.0, 1)), _const_tex((0.6, 0.0, 1.0, 1)), _const_tex((2.0, 1.5, 1.0, 1)),
+           _const_tex((0.7, 0.2, 0.2, 1))]
+    objs = [_obj(_quad((-1, 0, 1), (1, 0, 1), (1, 0, -1), (-1, 0, -1)), [0, 1, 2]),
+            _obj(_quad((-1, 0, -1), (1, 0, -1), (1, 2, -1), (-1, 2, -1)), [4, 1, 2]),
+            _obj(_quad((-0.3, 1.99, -0.3), (0.3, 1.99, -0.3), (0.3, 1.99, 0.3), (-0.3, 1.99, 0.3)), [3, 1, 2], emissive=True)]
+    lights = [dict(kind=0, casts_shadow=True, intensity=np.array([4, 4, 3.5], F), position=np.array([0.2, 1.5, 0.3], F), direction=np.zeros(3, F), radius=4.0, inner=0.0, outer=0.0)]
+    return dict(objects=objs, lights=lights, textures=tex, background=dict(mode=0, color=np.array([0.05, 0.06, 0.08], F), sun=np.array([0, 1, 0], F), textures=[], sky_lut=-1))
+
+
+def tiny_camera(ratio=1.0):
+    return camera_shifts((0, 1, 2.6), (0, 1, 0), (0, 1, 0), 0.9, ratio)
+
+
+def _grid_object(n, y0=0.0, amp=1.0, uv_scale=4.0):
+    """Displaced grid with analytic normals / tangent frame (the C2 mesh as a shaded floor)."""
+    pos, idx = displaced_grid(n)
+    pos = pos.copy()
+    x, z = pos[:, 0].astype(np.float64), pos[:, 2].astype(np.float64)
+    pos[:, 1] = (F(amp) * pos[:, 1] + F(y0)).astype(F)
+    dydx = amp * (0.9 * np.cos(9 * x) * np.cos(7 * z) + 0.02 * 53 * np.cos(53 * x + 31 * z))
+    dydz = amp * (-0.7 * np.sin(9 * x) * np.sin(7 * z) + 0.02 * 31 * np.cos(53 * x + 31 * z))
+    t = np.stack([np.ones_like(x), dydx, np.zeros_like(x)], -1)
+    b = np.stack([np.zeros_like(x), dydz, np.ones_like(x)], -1)
+    nrm = np.cross(b, t)
+    t, b, nrm = [(v / np.linalg.norm(v, axis=1, keepdims=True)).astype(F) for v in (t, b, nrm)]
+    uv = (np.stack([x, z], -1) * 0.5 + 0.5).astype(F) * F(uv_scale)
+    return dict(positions=pos, normals=nrm, tangents=t, bitangents=b, texcoords=uv, indices=idx)
+
+
+def _procedural_textures(res):
+    """Albedo checker with an alpha channel of 1, a bumpy tangent-space normal map, and a roughness/metalness/ao map."""
+    u = (np.arange(res, dtype=F) + F(0.5)) / F(res)
+    U, V = np.meshgrid(u, u, indexing="xy")
+    checker = ((np.floor(U * 8) + np.floor(V * 8)) % 2).astype(F)
+    albedo = np.stack([F(0.35) + F(0.5) * checker, F(0.4) + F(0.35) * checker, F(0.45) + F(0.2) * (1 - checker), np.ones_like(U)], -1).astype(F)
+    nx, ny = F(0.25) * np.sin(F(2 * np.pi * 6) * U), F(0.25) * np.cos(F(2 * np.pi * 5) * V)
+    nz = np.sqrt(np.maximum(F(0), F(1) - nx * nx - ny * ny))
+    normal = np.stack([nx * F(0.5) + F(0.5), ny * F(0.5) + F(0.5), nz * F(0.5) + F(0.5), np.ones_like(U)], -1).astype(F)
+    rmao = np.stack([F(0.25) + F(0.5) * checker, F(0.8) * (1 - checker) * (U > 0.5), np.ones_like(U), np.ones_like(U)], -1).astype(F)
+    return albedo, normal, rmao
+
+
+def _procedural_cubemap(res):
+    """Six fp32 RGBA faces (px,nx,py,ny,pz,nz) of a sky gradient with a warm sun lobe."""
+    u = (np.arange(res, dtype=F) + F(0.5)) / F(res) * F(2) - F(1)
+    A, B = np.meshgrid(u, u, indexing="xy")
+    one = np.ones_like(A)
+    dirs = [np.stack([one, -B, -A], -1), np.stack([-one, -B, A], -1), np.stack([A, one, B], -1), np.stack([A, -one, -B], -1),
+            np.stack([A, -B, one], -1), np.stack([-A, -B, -one], -1)]
+    sun = np.array([0.4, 0.7, 0.3], F)
+    sun /= np.linalg.norm(sun)
+    faces = []
+    for d in dirs:
+        d = d / np.linalg.norm(d, axis=-1, keepdims=True)
+        up = np.clip(d[..., 1] * 0.5 + 0.5, 0, 1)
+        sky = np.stack([0.25 + 0.35 * up, 0.35 + 0.45 * up, 0.55 + 0.6 * up], -1)
+        lobe = np.clip((d * sun).sum(-1), 0, 1) ** 64
+        col = sky + lobe[..., None] * np.array([6.0, 5.0, 3.5])
+        faces.append(np.concatenate([col, np.ones_like(col[..., :1])], -1).astype(F))
+    return faces
+
+
+def cornell_synthetic(grid_n=708, tex_res=512, cube_res=256):
+    """C3/C4 scene built from nothing but numpy: textured GGX+Lambert Cornell-style room whose floor is
+    the displaced grid (2*grid_n^2 triangles), open front, cubemap environment, one emissive panel, one shadow-casting
+    point light. Object order is the scene->objects order (regular materials first, emissive last, Scene.cpp:101-104)."""
+    albedo, normal, rmao = _procedural_textures(tex_res)
+    faces = _procedural_cubemap(cube_res)
+    tex = [albedo, normal, rmao, _const_tex((0.75, 0.2, 0.2, 1)), _const_tex((0.2, 0.7, 0.25, 1)), _const_tex((0.5, 0.5, 1.0, 1)),
+           _const_tex((0.6, 0.0, 1.0, 1)), _const_tex((0.15, 1.0, 1.0, 1)), _const_tex((8.0, 7.0, 5.5, 1))] + faces
+    cube0 = 9
+    floor = _grid_object(grid_n, y0=0.0, amp=0.5)
+    objs = [_obj(floor, [0, 1, 2], use_uv=True),
+            _obj(_quad((-1, 0, -1), (1, 0, -1), (1, 2, -1), (-1, 2, -1), 2.0), [0, 1, 2], use_uv=True),          # back wall, textured
+            _obj(_quad((-1, 0, 1), (-1, 0, -1), (-1, 2, -1), (-1, 2, 1)), [3, 5, 6]),                             # left, red
+            _obj(_quad((1, 0, -1), (1, 0, 1), (1, 2, 1), (1, 2, -1)), [4, 5, 6]),                                 # right, green
+            _obj(_quad((-1, 2, -1), (1, 2, -1), (1, 2, 1), (-1, 2, 1)), [0, 1, 2], use_uv=True),                  # ceiling
+            _obj(_quad((-0.45, 0.35, 0.1), (0.25, 0.35, -0.15), (0.25, 1.05, -0.15), (-0.45, 1.05, 0.1)), [4, 5, 7]),  # metal panel
+            _obj(_quad((-0.35, 1.98, -0.35), (0.35, 1.98, -0.35), (0.35, 1.98, 0.35), (-0.35, 1.98, 0.35)), [8, 5, 6], emissive=True)]
+    lights = [dict(kind=0, casts_shadow=True, intensity=np.array([5, 4.6, 4.0], F), position=np.array([0.3, 1.6, 0.4], F), direction=np.zeros(3, F), radius=4.0, inner=0.0, outer=0.0)]
+    bg = dict(mode=2, color=np.zeros(3, F), sun=np.array([0, 1, 0], F), textures=list(range(cube0, cube0 + 6)), sky_lut=-1)
+    return dict(objects=objs, lights=lights, textures=tex, background=bg)
+
+
+def cornell_camera(ratio):
+    return camera_shifts((0.0, 1.0, 3.4), (0.0, 0.9, 0.0), (0, 1, 0), 0.75, ratio)
