@@ -176,6 +176,10 @@ int ref_forparallel_threads() {
 }
 
 void ref_seed(unsigned int s) {
+	/* Touch the calling thread's generator first: its thread_local construction draws from the shared generator
+	 * (Random.cpp:72-80), and if that happened INSIDE Random::seed the number of draws consumed before the worker
+	 * thread is seeded would depend on whether this thread had used Random before. */
+	(void)Random::Float();
 	Random::seed(s);
 }
 
@@ -340,6 +344,7 @@ void ref_ggx_eval(const float * wo, const float * base, const float * rough, con
  * MaterialGGX::sampleAndEval. outU: 3 floats, outWi: 3 floats, outEval: 3 floats. */
 void ref_ggx_sample(const float * wo, const float * base, const float * rough, const float * metal, const uint32_t * seeds, size_t n, float * outU, float * outWi, float * outEval) {
 	for(size_t i = 0; i < n; ++i) {
+		(void)Random::Float();
 		Random::seed(seeds[i]);
 		for(int k = 0; k < 3; ++k) outU[3 * i + k] = Random::Float();
 		Random::seed(seeds[i]);
@@ -354,16 +359,19 @@ void ref_ggx_sample(const float * wo, const float * base, const float * rough, c
 
 /* Draw n uniforms / ints after seeding (pins the oracle's mt19937 + distribution restatement). */
 void ref_random_floats(unsigned int seed, size_t n, float * out) {
+	(void)Random::Float();
 	Random::seed(seed);
 	for(size_t i = 0; i < n; ++i) out[i] = Random::Float();
 }
 
 void ref_random_ints(unsigned int seed, int lo, int hi, size_t n, int * out) {
+	(void)Random::Float();
 	Random::seed(seed);
 	for(size_t i = 0; i < n; ++i) out[i] = Random::Int(lo, hi);
 }
 
 void ref_cosine_hemisphere(unsigned int seed, size_t n, float * out3) {
+	(void)Random::Float();
 	Random::seed(seed);
 	for(size_t i = 0; i < n; ++i) {
 		const glm::vec3 d = Random::sampleCosineHemisphere();

@@ -111,5 +111,65 @@ def main():
     print("box_kat", res.sum(), "/", res.size)
 
 
+def pathtracer_goldens():
+    from rendu_b200 import pathtracer as rpt
+    rng = np.random.RandomState(77)
+    # Flattened bundled scenes whose textures are tiny (constant 8x8 / 32x32 images).
+    for name in ("cornellbox", "cornellbox-emissive"):
+        sc = ref.RefScene(name)
+        desc = sc.flatten()
+        rpt.save_scene(os.path.join(OUT, "scene_%s.npz" % name), desc)
+        cam = sc.camera(1.0)
+        # (1) reproducible reference render: one forParallel worker, seeded -> pins the oracle's mt19937 mode bit for bit.
+        ref.set_concurrency(1)
+        ref.seed(5)
+        img, _, rays = sc.render(48, 48, 16, 5)
+        ref.set_concurrency(0)
+        # (2) converged reference image for the statistical gate on the CUDA path.
+        ref.seed(11)
+        conv, _, _ = sc.render(64, 64, 2048, 5)
+        np.savez_compressed(os.path.join(OUT, "render_%s.npz" % name), cam_eye=cam["eye"], cam_corner=cam["corner"], cam_dx=cam["dx"], cam_dy=cam["dy"],
+                            mt_seed=np.uint32(5), mt_image=img, mt_rays=np.uint64(rays), converged=conv, converged_spp=np.uint32(2048))
+        print("render", name, "mt mean", img.mean(), "rays", rays, "converged mean", conv.mean())
+    # Scalar KATs straight from the reference functions.
+    n = 4096
+    wo = rng.normal(size=(n, 3)).astype(F)
+    wo /= np.linalg.norm(wo, axis=1, keepdims=True)
+    wo[: n // 8, 2] *= -1  # some below the surface
+    wi = rng.normal(size=(n, 3)).astype(F)
+    wi /= np.linalg.norm(wi, axis=1, keepdims=True)
+    base = rng.uniform(0, 1, (n, 3)).astype(F)
+    rough = rng.uniform(0, 1, n).astype(F)
+    rough[:64] = 0.0
+    metal = (rng.uniform(0, 1, n) > 0.5).astype(F) * rng.uniform(0.5, 1, n).astype(F)
+    ev = ref.ggx_eval(wo, base, rough, metal, wi)
+    seeds = np.arange(1000, 1000 + n, dtype=np.uint32)
+    u3, swi, sev = ref.ggx_sample(wo, base, rough, metal, seeds)
+    img8 = rng.uniform(0, 1, (13, 9, 4)).astype(F)
+    uv = rng.uniform(-1.5, 2.5, (n, 2)).astype(F)
+    uv[:16] = np.array([[0, 0], [1, 1], [0.5, 0.5], [1, 0]] * 4, F)
+    i4, i3 = ref.image_sample(img8, uv)
+    faces = rng.uniform(0, 2, (6, 8, 8, 4)).astype(F)
+    dirs = rng.normal(size=(n, 3)).astype(F)
+    dirs[:6] = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], F)
+    dirs[6:12] = np.array([[1, 1, 0], [1, 0, 1], [0, 1, 1], [1, 1, 1], [-1, 1, -1], [1, -1, 1]], F)
+    cube = ref.cubemap_sample(faces, dirs)
+    lights = {}
+    for scene_name in ("cornellbox", "cornellbox-cutout", "gallery-materials"):
+        sc = ref.RefScene(scene_name)
+        d = sc.flatten()
+        pos = rng.uniform(-2.5, 2.5, (512, 3)).astype(F)
+        for li, l in enumerate(d["lights"]):
+            key = "%s_%d" % (scene_name.replace("-", "_"), li)
+            lights[key + "_desc"] = np.concatenate([[l["kind"], l["casts_shadow"]], l["intensity"], l["position"], l["direction"], [l["radius"], l["inner"], l["outer"]]]).astype(np.float64)
+            lights[key + "_pos"] = pos
+            lights[key + "_out"] = sc.light_sample(li, pos)
+    np.savez_compressed(os.path.join(OUT, "shading_kat.npz"), wo=wo, wi=wi, base=base, rough=rough, metal=metal, ggx_eval=ev, sample_u3=u3, sample_wi=swi,
+                        sample_eval=sev, img=img8, uv=uv, img_rgba=i4, img_rgb=i3, faces=faces, dirs=dirs, cube=cube,
+                        mt_floats=ref.random_floats(42, 256), mt_ints=ref.random_ints(42, 0, 24, 256), cos_hemi=ref.cosine_hemisphere(9, 256), **lights)
+    print("shading_kat", ev.shape, len(lights) // 3, "lights")
+
+
 if __name__ == "__main__":
     main()
+    pathtracer_goldens()

@@ -1,0 +1,190 @@
+"""GPU parity tests of the CUDA path tracer (through the C ABI) against the oracle.
+
+Two kinds of gates:
+ * per-pixel: the oracle is run with the SAME counter-based generator as the kernels, so both trace the same paths;
+   differences come only from libm (powf/expf/sincos) and are bounded per pixel (tolerances stated in each test);
+ * statistical: against the reference's own converged image (golden, 2048 spp), relative L2 within
+   1.5 x 0.43 x sqrt(1/N + 1/M) and image means within 1 %.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import rendu_b200 as rb
+from rendu_b200 import pathtracer as rpt
+from rendu_b200 import workloads as wl
+from rendu_b200._capi import LightDesc, check, lib, ptr
+from oracle import oracle as orc
+from oracle import ref
+from util import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def kat():
+    return dict(np.load(os.path.join(GOLDEN, "shading_kat.npz")))
+
+
+def golden_scene(name):
+    desc = rpt.load_scene(os.path.join(GOLDEN, "scene_%s.npz" % name))
+    g = dict(np.load(os.path.join(GOLDEN, "render_%s.npz" % name)))
+    cam = dict(eye=g["cam_eye"], corner=g["cam_corner"], dx=g["cam_dx"], dy=g["cam_dy"])
+    return desc, cam, g
+
+
+def gpu_render(desc, cam, w, h, samples, depth, seed=0, components=3, image=None, **kw):
+    sc = rpt.Scene(desc)
+    pt = rpt.PathTracer(sc)
+    img = np.zeros((h, w, components), np.float32) if image is None else image
+    pt.render(cam, samples, depth, img, rpt.make_opts(seed=seed, **kw))
+    return img, pt
+
+
+def assert_same_paths(gpu, cpu, frac_tol=0.01, abs_tol=2e-3):
+    """Same RNG, same estimator: almost every pixel agrees to libm precision; a handful may differ where a 1-ulp
+    difference flips a discrete decision (lobe pick, a hit at a grazing angle)."""
+    assert np.isfinite(gpu).all()
+    diff = np.abs(gpu - cpu).max(axis=2)
+    bad = (diff > abs_tol).mean()
+    assert bad <= frac_tol, "fraction of pixels off by > %g: %g (max %g)" % (abs_tol, bad, diff.max())
+    assert abs(gpu.mean() - cpu.mean()) <= 2e-3 * max(cpu.mean(), 1e-3)
+
+
+# ------------------------------------------------------------------------------------------------ scalar KATs
+def test_kat_ggx_eval_and_sample():
+    k = kat()
+    n = k["wo"].shape[0]
+    out = np.zeros((n, 3), np.float32)
+    arrs = [np.ascontiguousarray(k[x], np.float32) for x in ("wo", "base", "rough", "metal", "wi")]
+    check(lib().rb_kat_ggx_eval(*[ptr(a) for a in arrs], n, ptr(out)))
+    np.testing.assert_allclose(out, k["ggx_eval"], rtol=2e-5, atol=1e-7)  # powf(1-VdotH,5), sqrtf
+    wi, ev = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+    u3 = np.ascontiguousarray(k["sample_u3"], np.float32)
+    check(lib().rb_kat_ggx_sample(ptr(arrs[0]), ptr(arrs[1]), ptr(arrs[2]), ptr(arrs[3]), ptr(u3), n, ptr(wi), ptr(ev)))
+    np.testing.assert_allclose(wi, k["sample_wi"], rtol=0, atol=2e-6)  # sincos / sqrtf
+    same_lobe = np.isclose(ev, k["sample_eval"], rtol=2e-3, atol=1e-5).all(axis=1)
+    assert same_lobe.mean() > 0.999
+
+
+def test_kat_image_cubemap_lights_exact():
+    k = kat()
+    n = k["uv"].shape[0]
+    img = np.ascontiguousarray(k["img"], np.float32)
+    out4 = np.zeros((n, 4), np.float32)
+    check(lib().rb_kat_image_sample(ptr(img), img.shape[1], img.shape[0], ptr(np.ascontiguousarray(k["uv"])), n, ptr(out4)))
+    assert np.array_equal(out4.view(np.uint32), k["img_rgba"].view(np.uint32))  # no transcendental: bit-exact
+    faces = np.ascontiguousarray(k["faces"], np.float32)
+    out3 = np.zeros((n, 3), np.float32)
+    check(lib().rb_kat_cubemap_sample(ptr(faces), faces.shape[2], faces.shape[1], ptr(np.ascontiguousarray(k["dirs"])), n, ptr(out3)))
+    assert np.array_equal(out3.view(np.uint32), k["cube"].view(np.uint32))
+    for name in [x[:-5] for x in k if x.endswith("_desc")]:
+        a = k[name + "_desc"]
+        d = LightDesc()
+        d.kind, d.casts_shadow = int(a[0]), int(a[1])
+        d.intensity, d.position, d.direction = [(C.c_float * 3)(*[float(np.float32(v)) for v in a[i:i + 3]]) for i in (2, 5, 8)]
+        d.radius, d.inner_angle, d.outer_angle = [float(np.float32(v)) for v in a[11:14]]
+        pos = np.ascontiguousarray(k[name + "_pos"], np.float32)
+        out5 = np.zeros((pos.shape[0], 5), np.float32)
+        check(lib().rb_kat_light_sample(C.byref(d), ptr(pos), pos.shape[0], ptr(out5)))
+        assert np.array_equal(out5.view(np.uint32), k[name + "_out"].view(np.uint32)), name
+
+
+def test_kat_sky_eval():
+    rng = np.random.RandomState(8)
+    lut = rng.uniform(0.2, 1.0, (64, 64, 4)).astype(np.float32)
+    d = rng.normal(size=(512, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    o = rng.uniform(-2, 2, (512, 3)).astype(np.float32)
+    sun = np.array([0.3, 0.8, 0.52], np.float32)
+    sun /= np.linalg.norm(sun)
+    want = orc.sky_eval(lut, o, d, sun)
+    got = np.zeros_like(want)
+    check(lib().rb_kat_sky_eval(ptr(lut), 64, 64, ptr(o), ptr(d), ptr(sun), 512, ptr(got)))
+    np.testing.assert_allclose(got, want, rtol=2e-4, atol=1e-6)  # 48 expf + powf per sample
+    assert want.max() > 0
+
+
+# ------------------------------------------------------------------------------------------------ renders
+@pytest.mark.parametrize("name", ["cornellbox", "cornellbox-emissive"])
+def test_render_matches_oracle_path_for_path(name):
+    desc, cam, _ = golden_scene(name)
+    gpu, pt = gpu_render(desc, cam, 64, 64, 64, 5, seed=9)
+    cpu, rays = orc.OracleScene(desc).render(cam, 64, 64, 64, 5, seed=9, rng="counter", threads=8)
+    assert_same_paths(gpu, cpu)
+    st = pt.stats()
+    # The CUDA path drops paths whose attenuation reached exactly zero, so it never casts more rays than the reference.
+    assert 0 < st["rays_closest"] + st["rays_shadow"] <= rays
+    assert st["samples"] == 64 * 64 * 64 and st["kernel_launches"] > 0
+
+
+@pytest.mark.parametrize("name", ["cornellbox", "cornellbox-emissive"])
+def test_render_converges_to_reference_image(name):
+    desc, cam, g = golden_scene(name)
+    n = 256
+    gpu, _ = gpu_render(desc, cam, 64, 64, n, 5, seed=21)
+    conv, m = g["converged"], int(g["converged_spp"])
+    assert abs(gpu.mean() - conv.mean()) / conv.mean() < 0.01
+    rel = np.linalg.norm(gpu - conv) / np.linalg.norm(conv)
+    assert rel < 1.5 * 0.43 * np.sqrt(1.0 / n + 1.0 / m), rel
+
+
+def test_synthetic_c3_scene_small(monkeypatch):
+    """The C3/C4 benchmark scene at reduced size: textures with UVs, normal map, cubemap environment, emissive panel,
+    shadowed point light, displaced-grid floor."""
+    desc = wl.cornell_synthetic(24, 64, 16)
+    cam = wl.cornell_camera(16 / 9)
+    gpu, _ = gpu_render(desc, cam, 96, 54, 32, 6, seed=4)
+    cpu, _ = orc.OracleScene(desc).render(cam, 96, 54, 32, 6, seed=4, rng="counter", threads=8)
+    assert_same_paths(gpu, cpu, frac_tol=0.02)
+    assert gpu.mean() > 0.05
+
+
+@pytest.mark.skipif(not ref.available(), reason="bundled scenes need oracle/_ref/resources")
+@pytest.mark.parametrize("name", ["cornellbox-textured", "cornellbox-cutout", "cornellbox-reflections", "boxes"])
+def test_bundled_scenes_match_oracle(name):
+    """Cubemap + normal maps; masked leaves (alpha pass-through in render and in the shadow walk) + spot lights;
+    atmosphere sky; 443 roots + 25 lights."""
+    sc = ref.RefScene(name)
+    desc, cam = sc.flatten(), sc.camera(1.0)
+    gpu, _ = gpu_render(desc, cam, 48, 48, 32, 5, seed=2)
+    cpu, _ = orc.OracleScene(desc).render(cam, 48, 48, 32, 5, seed=2, rng="counter", threads=8)
+    assert_same_paths(gpu, cpu, frac_tol=0.02)
+    assert gpu.mean() > 0.01
+
+
+def test_seed_determinism_tiles_and_sample_split():
+    desc, cam, _ = golden_scene("cornellbox")
+    a, _ = gpu_render(desc, cam, 64, 40, 16, 5, seed=5)
+    b, _ = gpu_render(desc, cam, 64, 40, 16, 5, seed=5, max_paths=4096)  # different batching, same image
+    c, _ = gpu_render(desc, cam, 64, 40, 16, 5, seed=6)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert not np.array_equal(a, c)
+    # Tile split: three ranks render interleaved bands of 8 rows into one image -> bit-identical to the full render.
+    tiled = np.zeros_like(a)
+    for r in range(3):
+        gpu_render(desc, cam, 64, 40, 16, 5, seed=5, image=tiled, tile=(8, r, 3))
+    assert np.array_equal(tiled.view(np.uint32), a.view(np.uint32))
+    # Sample split: per-rank partial images (each normalised by the FULL sample count) add up to the full image.
+    parts = [gpu_render(desc, cam, 64, 40, 16, 5, seed=5, samples=(r, 4))[0] for r in range(4)]
+    np.testing.assert_allclose(sum(parts), a, rtol=0, atol=2e-6)
+
+
+def test_image_contract_components_accumulation_and_rounding():
+    desc, cam, _ = golden_scene("cornellbox-emissive")
+    base, _ = gpu_render(desc, cam, 32, 32, 16, 4, seed=1)
+    # 4-component image (PathTracerApp passes RGBA, Image.cpp:34-36): alpha is left alone.
+    rgba = np.full((32, 32, 4), 0.0, np.float32)
+    rgba[..., 3] = 7.0
+    gpu_render(desc, cam, 32, 32, 16, 4, seed=1, components=4, image=rgba)
+    assert np.array_equal(rgba[..., :3].view(np.uint32), base.view(np.uint32)) and (rgba[..., 3] == 7.0).all()
+    # The result is accumulated into the caller's image and the SUM is divided (PathTracer.cpp:288-292).
+    pre = np.full((32, 32, 3), 1.6, np.float32)
+    gpu_render(desc, cam, 32, 32, 16, 4, seed=1, image=pre)
+    np.testing.assert_allclose(pre, base + 1.6 / 16, rtol=0, atol=1e-6)
+    # Non power-of-two sample counts are rounded like the reference: 12 -> 2^round(log2 12) = 16 (PathTracer.cpp:169-173).
+    r12, pt = gpu_render(desc, cam, 32, 32, 12, 4, seed=1)
+    assert np.array_equal(r12.view(np.uint32), base.view(np.uint32)) and pt.stats()["samples"] == 32 * 32 * 16
+    with pytest.raises(rb.RenduError):
+        gpu_render(desc, cam, 32, 32, 16, 4, components=2, image=np.zeros((32, 32, 2), np.float32))
