@@ -124,7 +124,9 @@ RB_API rb_status rb_raycaster_build(rb_raycaster * rc, rb_build_mode mode);
  * previously added. */
 RB_API rb_status rb_raycaster_upload_bvh(rb_raycaster * rc, const rb_node * nodes, size_t nnodes, const rb_tri * tris, size_t ntris, const float * vertices, size_t nverts, uint32_t mesh_count);
 
-/* Sizes of the host-format hierarchy: out[0]=nodes, out[1]=triangles, out[2]=vertices, out[3]=meshes, out[4]=max depth. */
+/* Sizes of the hierarchy in the reference format: out[0]=nodes, out[1]=triangles, out[2]=vertices, out[3]=roots (one per
+ * mesh for RB_BUILD_REFERENCE, a single one for RB_BUILD_LBVH; pass it as mesh_count to rb_raycaster_upload_bvh),
+ * out[4]=max depth. */
 RB_API rb_status rb_raycaster_sizes(const rb_raycaster * rc, uint64_t out[5]);
 
 /* Read the hierarchy back in the reference's format (any pointer may be NULL). After an LBVH build this

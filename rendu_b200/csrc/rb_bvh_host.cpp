@@ -193,6 +193,14 @@ bool rb_host_flatten(const rb_raycaster * rc, RbFlatBvh & out, std::string * why
 	};
 	out.nodes.assign(nInterior * 16, 0.0f);
 	out.parent.assign(nInterior, -1);
+	out.leafParent.clear();
+	out.leafCode.clear();
+	auto addLeaf = [&](size_t id, int link) {
+		const rb_node & n = rc->nodes[id];
+		if(n.right == 0) return;
+		out.leafParent.push_back(link);
+		out.leafCode.push_back(int((uint32_t(n.left) << RB_LEAF_BITS) | uint32_t(n.right - 1)));
+	};
 	for(size_t i = 0; i < nn; ++i) {
 		const rb_node & n = rc->nodes[i];
 		if(n.leaf) continue;
@@ -204,8 +212,8 @@ bool rb_host_flatten(const rb_raycaster * rc, RbFlatBvh & out, std::string * why
 		d[8] = R.bmin[2]; d[9] = R.bmax[0]; d[10] = R.bmax[1]; d[11] = R.bmax[2];
 		d[12] = asFloat(childRef(n.left));
 		d[13] = asFloat(childRef(n.right));
-		if(!L.leaf) out.parent[interiorIndex[n.left]] = (interiorIndex[i] << 1) | 0;
-		if(!R.leaf) out.parent[interiorIndex[n.right]] = (interiorIndex[i] << 1) | 1;
+		if(!L.leaf) out.parent[interiorIndex[n.left]] = (interiorIndex[i] << 1) | 0; else addLeaf(n.left, (interiorIndex[i] << 1) | 0);
+		if(!R.leaf) out.parent[interiorIndex[n.right]] = (interiorIndex[i] << 1) | 1; else addLeaf(n.right, (interiorIndex[i] << 1) | 1);
 	}
 	out.roots.assign(size_t(rc->meshCount) * 8, 0.0f);
 	for(size_t m = 0; m < rc->meshCount; ++m) {
@@ -216,6 +224,7 @@ bool rb_host_flatten(const rb_raycaster * rc, RbFlatBvh & out, std::string * why
 		d[4] = n.bmax[0]; d[5] = n.bmax[1]; d[6] = n.bmax[2];
 		d[7] = 0.0f;
 		if(!n.leaf) out.parent[interiorIndex[m]] = ~int(m); // negative: a root, ~value = root slot
+		else addLeaf(m, ~int(m));
 		if(n.right == 0 && n.leaf) {
 			// Empty mesh: inverted box, never accepted.
 			d[0] = d[1] = d[2] = 1.0f;
@@ -224,6 +233,7 @@ bool rb_host_flatten(const rb_raycaster * rc, RbFlatBvh & out, std::string * why
 	}
 	out.tris.assign(nt * 12, 0.0f);
 	out.triVerts.resize(nt * 3);
+	out.triIds.resize(nt * 2);
 	const float * V = rc->verts.data();
 	const size_t nv = rc->verts.size() / 3;
 	for(size_t i = 0; i < nt; ++i) {
@@ -245,6 +255,8 @@ bool rb_host_flatten(const rb_raycaster * rc, RbFlatBvh & out, std::string * why
 		out.triVerts[3 * i + 0] = uint32_t(t.v0);
 		out.triVerts[3 * i + 1] = uint32_t(t.v1);
 		out.triVerts[3 * i + 2] = uint32_t(t.v2);
+		out.triIds[2 * i + 0]	= uint32_t(t.localId);
+		out.triIds[2 * i + 1]	= t.meshId;
 	}
 	return true;
 }

@@ -48,10 +48,15 @@ struct rb_raycaster {
 	size_t nTris	  = 0;
 	RbDeviceBvh dev	  = {};
 	// LBVH bookkeeping (device): parent links and leaf->node map for refits, world-space vertices, vertex ids.
-	int * d_parent	   = nullptr;
+	int * d_parent	   = nullptr;	 // per interior node: (parent << 1) | side, or ~rootSlot
+	int * d_leafParent = nullptr;	 // per leaf: same encoding
+	int * d_leafCode   = nullptr;	 // per leaf: (first triangle << 3) | (count - 1)
+	unsigned int * d_flags = nullptr; // per interior node: arrival counter of the bottom-up fit
 	float * d_verts	   = nullptr;
 	uint32_t * d_triVerts = nullptr; // 3 vertex ids per triangle in hierarchy order
+	uint32_t * d_triIds	  = nullptr; // (localId, meshId) per triangle in hierarchy order
 	size_t nVerts	   = 0;
+	size_t nLeaves	   = 0;
 	int buildMode	   = RB_BUILD_REFERENCE;
 
 	int traceMode = RB_TRACE_EXACT;
@@ -71,7 +76,10 @@ struct RbFlatBvh {
 	std::vector<float> tris;  // 12 floats per triangle
 	std::vector<float> roots; // 8 floats per root
 	std::vector<uint32_t> triVerts;
-	std::vector<int> parent;  // parent interior index per interior node (-1 for roots' children handled on device)
+	std::vector<int> parent;	 // per interior node: (parent << 1) | side, or ~rootSlot for a root
+	std::vector<int> leafParent; // per leaf, same encoding
+	std::vector<int> leafCode;	 // per leaf: (first triangle << 3) | (count - 1)
+	std::vector<uint32_t> triIds; // (localId, meshId) per triangle
 };
 bool rb_host_flatten(const rb_raycaster * rc, RbFlatBvh & out, std::string * why);
 
@@ -84,5 +92,6 @@ rb_status rb_lbvh_build(rb_raycaster * rc);
 rb_status rb_lbvh_refit(rb_raycaster * rc, const float * worldPositions, size_t nverts);
 rb_status rb_lbvh_download(const rb_raycaster * rc, rb_node * nodes, rb_tri * tris, float * verts);
 
+#define RB_TRACE_BLOCK_THREADS 128
 // Launch helpers used by the path tracer (rb_raycaster.cu).
 size_t rb_trace_smem_bytes(const rb_raycaster * rc, int blockThreads);

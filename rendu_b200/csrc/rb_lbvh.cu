@@ -1,5 +1,552 @@
-// placeholder, replaced below
+// rb_lbvh.cu — GPU hierarchy build and refit (north_star "GPU LBVH build: Morton codes, radix sort, Karras hierarchy,
+// SAH-free refit"). It sits beside RB_BUILD_REFERENCE (rb_bvh_host.cpp), which reproduces the reference's own tree
+// (Raycaster::updateHierarchy, src/engine/raycaster/Raycaster.cpp:54-142); this file has no reference counterpart.
+//
+//   build : triangle boxes + centroid bounds -> 63-bit Morton codes -> LSD radix sort (8 passes of 8 bits, hand-written:
+//           per-block histograms, one scan over the digit-major table, stable scatter ranked with __match_any_sync)
+//           -> Karras 2012 hierarchy, one thread per internal node -> bottom-up AABB fit with one atomic flag per
+//           node -> triangles re-gathered in sorted order. One tree over all meshes, one triangle per leaf.
+//   refit : same bottom-up pass over the existing topology (either build mode) after the vertices moved.
+// Boxes are unions of exact fp32 triangle boxes (min/max only), so a box is bit-identical to what the reference's
+// BoundingBox::merge chain (Bounds.cpp:12-20) would give for the same triangle set.
 #include "rb_internal.h"
-rb_status rb_lbvh_build(rb_raycaster *) { return rb_fail(RB_ERR_UNSUPPORTED, "lbvh: not built yet"); }
-rb_status rb_lbvh_refit(rb_raycaster *, const float *, size_t) { return rb_fail(RB_ERR_UNSUPPORTED, "lbvh: not built yet"); }
-rb_status rb_lbvh_download(const rb_raycaster *, rb_node *, rb_tri *, float *) { return rb_fail(RB_ERR_UNSUPPORTED, "lbvh: not built yet"); }
+#include "rb_math.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#define RB_SORT_BLOCK 256
+#define RB_SORT_ITEMS 4
+#define RB_SORT_TILE (RB_SORT_BLOCK * RB_SORT_ITEMS)
+
+// ------------------------------------------------------------------------------------------------ radix sort
+__global__ void __launch_bounds__(RB_SORT_BLOCK) rb_k_sort_hist(const uint64_t * __restrict__ keys, uint32_t n, int shift, uint32_t * __restrict__ table, uint32_t nblocks) {
+	__shared__ uint32_t hist[256];
+	hist[threadIdx.x] = 0;
+	__syncthreads();
+	const uint32_t base = blockIdx.x * RB_SORT_TILE;
+	for(int j = 0; j < RB_SORT_ITEMS; ++j) {
+		const uint32_t i = base + j * RB_SORT_BLOCK + threadIdx.x;
+		if(i < n) atomicAdd(&hist[(keys[i] >> shift) & 255u], 1u);
+	}
+	__syncthreads();
+	table[threadIdx.x * nblocks + blockIdx.x] = hist[threadIdx.x]; // digit-major: a scan gives global offsets
+}
+
+// Exclusive scan of a u32 array in three steps (tile sums, scan of the sums by one block, add back).
+#define RB_SCAN_TILE 2048
+__global__ void __launch_bounds__(256) rb_k_scan_tiles(uint32_t * __restrict__ data, uint32_t n, uint32_t * __restrict__ sums) {
+	__shared__ uint32_t s[256];
+	const uint32_t base = blockIdx.x * RB_SCAN_TILE + threadIdx.x * 8;
+	uint32_t v[8], total = 0;
+	for(int k = 0; k < 8; ++k) {
+		v[k] = (base + k < n) ? data[base + k] : 0u;
+		total += v[k];
+	}
+	s[threadIdx.x] = total;
+	__syncthreads();
+	for(int off = 1; off < 256; off <<= 1) {
+		const uint32_t t = (threadIdx.x >= off) ? s[threadIdx.x - off] : 0u;
+		__syncthreads();
+		s[threadIdx.x] += t;
+		__syncthreads();
+	}
+	uint32_t run = s[threadIdx.x] - total;
+	for(int k = 0; k < 8; ++k) {
+		if(base + k < n) data[base + k] = run;
+		run += v[k];
+	}
+	if(threadIdx.x == 255) sums[blockIdx.x] = s[255];
+}
+__global__ void __launch_bounds__(256) rb_k_scan_sums(uint32_t * __restrict__ sums, uint32_t n) {
+	__shared__ uint32_t s[256];
+	__shared__ uint32_t carry;
+	if(threadIdx.x == 0) carry = 0;
+	__syncthreads();
+	for(uint32_t base = 0; base < n; base += 256) {
+		const uint32_t i = base + threadIdx.x;
+		const uint32_t v = (i < n) ? sums[i] : 0u;
+		s[threadIdx.x]	 = v;
+		__syncthreads();
+		for(int off = 1; off < 256; off <<= 1) {
+			const uint32_t t = (threadIdx.x >= off) ? s[threadIdx.x - off] : 0u;
+			__syncthreads();
+			s[threadIdx.x] += t;
+			__syncthreads();
+		}
+		if(i < n) sums[i] = carry + s[threadIdx.x] - v;
+		__syncthreads();
+		if(threadIdx.x == 255) carry += s[255];
+		__syncthreads();
+	}
+}
+__global__ void __launch_bounds__(256) rb_k_scan_add(uint32_t * __restrict__ data, uint32_t n, const uint32_t * __restrict__ sums) {
+	const uint32_t base = blockIdx.x * RB_SCAN_TILE + threadIdx.x * 8;
+	const uint32_t add	= sums[blockIdx.x];
+	for(int k = 0; k < 8; ++k) {
+		if(base + k < n) data[base + k] += add;
+	}
+}
+
+// Stable scatter of one digit. Keys of a tile are visited warp by warp, and inside a warp in 32-wide stripes, so the
+// running per-warp digit counts give each key its rank among equal digits in input order.
+__global__ void __launch_bounds__(RB_SORT_BLOCK) rb_k_sort_scatter(const uint64_t * __restrict__ keysIn, const uint32_t * __restrict__ valsIn, uint64_t * __restrict__ keysOut, uint32_t * __restrict__ valsOut, uint32_t n, int shift, const uint32_t * __restrict__ table, uint32_t nblocks) {
+	__shared__ uint32_t warpHist[RB_SORT_BLOCK / 32][256];
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	for(int w = 0; w < RB_SORT_BLOCK / 32; ++w) warpHist[w][threadIdx.x] = 0;
+	__syncthreads();
+	const uint32_t warpBase = blockIdx.x * RB_SORT_TILE + warp * (32 * RB_SORT_ITEMS);
+	uint64_t key[RB_SORT_ITEMS];
+	uint32_t val[RB_SORT_ITEMS], rank[RB_SORT_ITEMS], digit[RB_SORT_ITEMS];
+	for(int j = 0; j < RB_SORT_ITEMS; ++j) {
+		const uint32_t i = warpBase + j * 32 + lane;
+		const bool valid = i < n;
+		key[j]	 = valid ? keysIn[i] : ~0ull;
+		val[j]	 = valid ? valsIn[i] : 0u;
+		digit[j] = valid ? uint32_t((key[j] >> shift) & 255u) : 256u; // 256: padding lanes match only each other
+		const uint32_t peers = __match_any_sync(0xffffffffu, digit[j]);
+		uint32_t before = 0;
+		if(valid) before = warpHist[warp][digit[j]];
+		__syncwarp();
+		rank[j] = before + __popc(peers & ((1u << lane) - 1u));
+		if(valid && lane == uint32_t(__ffs(peers) - 1)) warpHist[warp][digit[j]] = before + __popc(peers);
+		__syncwarp();
+	}
+	__syncthreads();
+	// Exclusive prefix over the warps for digit = threadIdx.x, plus the block's global offset for that digit.
+	{
+		uint32_t run = table[threadIdx.x * nblocks + blockIdx.x];
+		for(int w = 0; w < RB_SORT_BLOCK / 32; ++w) {
+			const uint32_t c	   = warpHist[w][threadIdx.x];
+			warpHist[w][threadIdx.x] = run;
+			run += c;
+		}
+	}
+	__syncthreads();
+	for(int j = 0; j < RB_SORT_ITEMS; ++j) {
+		if(digit[j] < 256u) {
+			const uint32_t dst = warpHist[warp][digit[j]] + rank[j];
+			keysOut[dst] = key[j];
+			valsOut[dst] = val[j];
+		}
+	}
+}
+
+struct RbSortScratch {
+	uint64_t * keysAlt = nullptr;
+	uint32_t * valsAlt = nullptr;
+	uint32_t * table   = nullptr;
+	uint32_t * sums	   = nullptr;
+};
+
+// Sorts (keys, vals) ascending by the low `bits` bits of the key; the result ends in the input buffers.
+static rb_status rb_radix_sort(uint64_t * keys, uint32_t * vals, uint32_t n, int bits, cudaStream_t s, uint64_t * launches) {
+	if(n < 2) return RB_OK;
+	const uint32_t nblocks = (n + RB_SORT_TILE - 1) / RB_SORT_TILE;
+	const uint32_t tableN  = 256u * nblocks;
+	const uint32_t ntiles  = (tableN + RB_SCAN_TILE - 1) / RB_SCAN_TILE;
+	RbSortScratch sc;
+	RB_CUDA(cudaMalloc(&sc.keysAlt, size_t(n) * sizeof(uint64_t)));
+	RB_CUDA(cudaMalloc(&sc.valsAlt, size_t(n) * sizeof(uint32_t)));
+	RB_CUDA(cudaMalloc(&sc.table, size_t(tableN) * sizeof(uint32_t)));
+	RB_CUDA(cudaMalloc(&sc.sums, size_t(ntiles) * sizeof(uint32_t)));
+	uint64_t *kin = keys, *kout = sc.keysAlt;
+	uint32_t *vin = vals, *vout = sc.valsAlt;
+	int passes = (bits + 7) / 8;
+	if(passes & 1) ++passes; // an even number of passes leaves the result in the caller's buffers
+	for(int p = 0; p < passes; ++p) {
+		const int shift = 8 * p;
+		rb_k_sort_hist<<<nblocks, RB_SORT_BLOCK, 0, s>>>(kin, n, shift, sc.table, nblocks);
+		rb_k_scan_tiles<<<ntiles, 256, 0, s>>>(sc.table, tableN, sc.sums);
+		rb_k_scan_sums<<<1, 256, 0, s>>>(sc.sums, ntiles);
+		rb_k_scan_add<<<ntiles, 256, 0, s>>>(sc.table, tableN, sc.sums);
+		rb_k_sort_scatter<<<nblocks, RB_SORT_BLOCK, 0, s>>>(kin, vin, kout, vout, n, shift, sc.table, nblocks);
+		std::swap(kin, kout);
+		std::swap(vin, vout);
+		*launches += 5;
+	}
+	cudaError_t e = cudaStreamSynchronize(s);
+	cudaFree(sc.keysAlt);
+	cudaFree(sc.valsAlt);
+	cudaFree(sc.table);
+	cudaFree(sc.sums);
+	if(e != cudaSuccess) return rb_fail(RB_ERR_CUDA, "radix sort failed: %s", cudaGetErrorString(e));
+	return RB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ build kernels
+RB_D unsigned int rb_float_ordered(float f) { // monotone float -> uint map for atomicMin/Max
+	const unsigned int u = __float_as_uint(f);
+	return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+RB_D float rb_float_unordered(unsigned int u) {
+	return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+RB_D void rb_tri_box(const float * __restrict__ verts, uint32_t a, uint32_t b, uint32_t c, V3 & lo, V3 & hi) {
+	const V3 va = V3{verts[3 * a], verts[3 * a + 1], verts[3 * a + 2]};
+	const V3 vb = V3{verts[3 * b], verts[3 * b + 1], verts[3 * b + 2]};
+	const V3 vc = V3{verts[3 * c], verts[3 * c + 1], verts[3 * c + 2]};
+	lo = glm_min3(glm_min3(va, vb), vc); // BoundingBox(v0,v1,v2), Bounds.cpp:12-15
+	hi = glm_max3(glm_max3(va, vb), vc);
+}
+
+__global__ void rb_k_lbvh_bounds(const float * __restrict__ verts, const uint32_t * __restrict__ triVerts, uint32_t ntris, unsigned int * __restrict__ bounds6) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= ntris) return;
+	V3 lo, hi;
+	rb_tri_box(verts, triVerts[3 * i], triVerts[3 * i + 1], triVerts[3 * i + 2], lo, hi);
+	const V3 c = 0.5f * (lo + hi);
+	atomicMin(bounds6 + 0, rb_float_ordered(c.x)); atomicMin(bounds6 + 1, rb_float_ordered(c.y)); atomicMin(bounds6 + 2, rb_float_ordered(c.z));
+	atomicMax(bounds6 + 3, rb_float_ordered(c.x)); atomicMax(bounds6 + 4, rb_float_ordered(c.y)); atomicMax(bounds6 + 5, rb_float_ordered(c.z));
+}
+
+RB_D uint64_t rb_expand21(uint64_t v) { // spread 21 bits so that two zero bits separate consecutive bits
+	v &= 0x1fffffull;
+	v = (v | (v << 32)) & 0x1f00000000ffffull;
+	v = (v | (v << 16)) & 0x1f0000ff0000ffull;
+	v = (v | (v << 8)) & 0x100f00f00f00f00full;
+	v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
+	v = (v | (v << 2)) & 0x1249249249249249ull;
+	return v;
+}
+
+__global__ void rb_k_lbvh_morton(const float * __restrict__ verts, const uint32_t * __restrict__ triVerts, uint32_t ntris, const unsigned int * __restrict__ bounds6, uint64_t * __restrict__ keys, uint32_t * __restrict__ vals) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= ntris) return;
+	V3 lo, hi;
+	rb_tri_box(verts, triVerts[3 * i], triVerts[3 * i + 1], triVerts[3 * i + 2], lo, hi);
+	const V3 c	= 0.5f * (lo + hi);
+	const V3 bl = V3{rb_float_unordered(bounds6[0]), rb_float_unordered(bounds6[1]), rb_float_unordered(bounds6[2])};
+	const V3 bh = V3{rb_float_unordered(bounds6[3]), rb_float_unordered(bounds6[4]), rb_float_unordered(bounds6[5])};
+	const float ex = fmaxf(bh.x - bl.x, 1e-30f), ey = fmaxf(bh.y - bl.y, 1e-30f), ez = fmaxf(bh.z - bl.z, 1e-30f);
+	const double scale = 2097151.0; // 2^21 - 1
+	const uint64_t qx = uint64_t(fmin(fmax(double(c.x - bl.x) / double(ex) * scale, 0.0), scale));
+	const uint64_t qy = uint64_t(fmin(fmax(double(c.y - bl.y) / double(ey) * scale, 0.0), scale));
+	const uint64_t qz = uint64_t(fmin(fmax(double(c.z - bl.z) / double(ez) * scale, 0.0), scale));
+	keys[i] = (rb_expand21(qx) << 2) | (rb_expand21(qy) << 1) | rb_expand21(qz);
+	vals[i] = i;
+}
+
+// Karras 2012, "Maximizing parallelism in the construction of BVHs": common-prefix length with the index as tie-break.
+RB_D int rb_delta(const uint64_t * __restrict__ keys, int n, int i, int j) {
+	if(j < 0 || j >= n) return -1;
+	const uint64_t a = keys[i], b = keys[j];
+	if(a == b) return 64 + __clz(i ^ j);
+	return __clzll((long long)(a ^ b));
+}
+
+// One thread per internal node: children and parent links. Child references use the traversal encoding (rb_types.h).
+__global__ void rb_k_lbvh_hierarchy(const uint64_t * __restrict__ keys, int n, int * __restrict__ childRefs /* 2 per internal */, int * __restrict__ interiorParent, int * __restrict__ leafParent) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n - 1) return;
+	const int d		  = (rb_delta(keys, n, i, i + 1) - rb_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+	const int deltaMin = rb_delta(keys, n, i, i - d);
+	int lmax = 2;
+	while(rb_delta(keys, n, i, i + lmax * d) > deltaMin) lmax <<= 1;
+	int l = 0;
+	for(int t = lmax >> 1; t >= 1; t >>= 1) {
+		if(rb_delta(keys, n, i, i + (l + t) * d) > deltaMin) l += t;
+	}
+	const int j			= i + l * d;
+	const int deltaNode = rb_delta(keys, n, i, j);
+	int s = 0;
+	int t = l;
+	do {
+		t = (t + 1) >> 1;
+		if(rb_delta(keys, n, i, i + (s + t) * d) > deltaNode) s += t;
+	} while(t > 1);
+	const int split = i + s * d + min(d, 0);
+	const int lo = min(i, j), hi = max(i, j);
+	const bool leftLeaf = (lo == split), rightLeaf = (hi == split + 1);
+	childRefs[2 * i + 0] = leftLeaf ? ~(split << RB_LEAF_BITS) : split;
+	childRefs[2 * i + 1] = rightLeaf ? ~((split + 1) << RB_LEAF_BITS) : (split + 1);
+	if(leftLeaf) leafParent[split] = (i << 1) | 0; else interiorParent[split] = (i << 1) | 0;
+	if(rightLeaf) leafParent[split + 1] = (i << 1) | 1; else interiorParent[split + 1] = (i << 1) | 1;
+	if(i == 0) interiorParent[0] = ~0; // root slot 0
+}
+
+// Re-gather the triangles in hierarchy order: records for the traversal (v0, v1-v0, v2-v0 + ids) and vertex ids for refits.
+__global__ void rb_k_lbvh_gather(const uint32_t * __restrict__ order, const uint32_t * __restrict__ triVertsIn, const uint32_t * __restrict__ triIdsIn, uint32_t ntris, uint32_t * __restrict__ triVertsOut, uint32_t * __restrict__ triIdsOut) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= ntris) return;
+	const uint32_t src = order ? order[i] : i;
+	for(int k = 0; k < 3; ++k) triVertsOut[3 * i + k] = triVertsIn[3 * src + k];
+	triIdsOut[2 * i + 0] = triIdsIn[2 * src + 0];
+	triIdsOut[2 * i + 1] = triIdsIn[2 * src + 1];
+}
+
+RB_D void rb_write_child_box(float4 * nodes, int parent, int side, V3 lo, V3 hi) {
+	float * f = reinterpret_cast<float *>(nodes + 4 * size_t(parent)) + (side ? 6 : 0);
+	f[0] = lo.x; f[1] = lo.y; f[2] = lo.z; f[3] = hi.x; f[4] = hi.y; f[5] = hi.z;
+}
+RB_D void rb_read_child_box(const float4 * nodes, int node, int side, V3 & lo, V3 & hi) {
+	const volatile float * f = reinterpret_cast<const volatile float *>(nodes + 4 * size_t(node)) + (side ? 6 : 0);
+	lo = V3{f[0], f[1], f[2]};
+	hi = V3{f[3], f[4], f[5]};
+}
+
+// Bottom-up fit / refit. One thread per leaf: rebuild its triangle records from the current vertices, take the union of
+// their boxes, store it in the parent's child slot and climb; at every internal node the first thread to arrive stops,
+// the second one (which therefore sees both child boxes) continues. Roots write into the root table.
+__global__ void rb_k_fit(const float * __restrict__ verts, const uint32_t * __restrict__ triVerts, const uint32_t * __restrict__ triIds, const int * __restrict__ leafCode, const int * __restrict__ leafParent, const int * __restrict__ interiorParent, int nleaves, float4 * __restrict__ nodes, float4 * __restrict__ tris, float4 * __restrict__ roots, unsigned int * __restrict__ flags, unsigned int * __restrict__ maxDepth) {
+	const int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+	if(leaf >= nleaves) return;
+	const int code	= leafCode[leaf];
+	const int first = code >> RB_LEAF_BITS;
+	const int count = (code & (RB_LEAF_MAX_TRIS - 1)) + 1;
+	V3 lo = v3(0.0f), hi = v3(0.0f);
+	for(int k = 0; k < count; ++k) {
+		const int t = first + k;
+		const uint32_t a = triVerts[3 * t], b = triVerts[3 * t + 1], c = triVerts[3 * t + 2];
+		const V3 va = V3{verts[3 * a], verts[3 * a + 1], verts[3 * a + 2]};
+		const V3 vb = V3{verts[3 * b], verts[3 * b + 1], verts[3 * b + 2]};
+		const V3 vc = V3{verts[3 * c], verts[3 * c + 1], verts[3 * c + 2]};
+		const V3 e1 = vb - va, e2 = vc - va;
+		tris[3 * size_t(t) + 0] = make_float4(va.x, va.y, va.z, __uint_as_float(triIds[2 * t]));
+		tris[3 * size_t(t) + 1] = make_float4(e1.x, e1.y, e1.z, __uint_as_float(triIds[2 * t + 1]));
+		tris[3 * size_t(t) + 2] = make_float4(e2.x, e2.y, e2.z, 0.0f);
+		const V3 tlo = glm_min3(glm_min3(va, vb), vc), thi = glm_max3(glm_max3(va, vb), vc);
+		if(k == 0) { lo = tlo; hi = thi; } else { lo = glm_min3(lo, tlo); hi = glm_max3(hi, thi); } // BoundingBox::merge
+	}
+	int link = leafParent[leaf];
+	unsigned int depth = 0;
+	for(;;) {
+		if(link < 0) {
+			// A root: its box lives in the root table.
+			const int slot = ~link;
+			float * r = reinterpret_cast<float *>(roots + 2 * size_t(slot));
+			r[0] = lo.x; r[1] = lo.y; r[2] = lo.z;
+			r[4] = hi.x; r[5] = hi.y; r[6] = hi.z;
+			break;
+		}
+		const int parent = link >> 1, side = link & 1;
+		rb_write_child_box(nodes, parent, side, lo, hi);
+		__threadfence();
+		++depth;
+		if(atomicAdd(flags + parent, 1u) == 0u) break; // first to arrive: the sibling will finish this node
+		V3 slo, shi;
+		rb_read_child_box(nodes, parent, side ^ 1, slo, shi);
+		lo	 = glm_min3(lo, slo);
+		hi	 = glm_max3(hi, shi);
+		link = interiorParent[parent];
+	}
+	// Depth of the deepest leaf (interior nodes on its path): every leaf climbs at least partially, so a separate walk
+	// up the parent links gives the exact value.
+	unsigned int d = 0;
+	for(int l2 = leafParent[leaf]; l2 >= 0; l2 = interiorParent[l2 >> 1]) ++d;
+	atomicMax(maxDepth, d);
+	(void)depth;
+}
+
+__global__ void rb_k_lbvh_write_refs(const int * __restrict__ childRefs, int ninterior, float4 * __restrict__ nodes) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= ninterior) return;
+	nodes[4 * size_t(i) + 3] = make_float4(__int_as_float(childRefs[2 * i]), __int_as_float(childRefs[2 * i + 1]), 0.0f, 0.0f);
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static unsigned rb_blocks(size_t n, unsigned block) { return unsigned((n + block - 1) / block); }
+
+static rb_status rb_run_fit(rb_raycaster * rc, cudaStream_t s) {
+	const int nleaves = int(rc->nLeaves);
+	unsigned int * d_depth = nullptr;
+	RB_CUDA(cudaMalloc(&d_depth, sizeof(unsigned int)));
+	RB_CUDA(cudaMemsetAsync(d_depth, 0, sizeof(unsigned int), s));
+	RB_CUDA(cudaMemsetAsync(rc->d_flags, 0, (rc->nInterior + 1) * sizeof(unsigned int), s));
+	if(nleaves) {
+		rb_k_fit<<<rb_blocks(nleaves, 128), 128, 0, s>>>(rc->d_verts, rc->d_triVerts, rc->d_triIds, rc->d_leafCode, rc->d_leafParent, rc->d_parent, nleaves, rc->d_nodes, rc->d_tris, rc->d_roots, rc->d_flags, d_depth);
+		rc->launches++;
+	}
+	unsigned int depth = 0;
+	cudaError_t e = cudaMemcpyAsync(&depth, d_depth, sizeof(depth), cudaMemcpyDeviceToHost, s);
+	if(e == cudaSuccess) e = cudaStreamSynchronize(s);
+	cudaFree(d_depth);
+	if(e != cudaSuccess) return rb_fail(RB_ERR_CUDA, "hierarchy fit failed: %s", cudaGetErrorString(e));
+	rc->maxDepth	   = int(depth);
+	rc->dev.stackDepth = rc->maxDepth + 1;
+	return RB_OK;
+}
+
+rb_status rb_lbvh_build(rb_raycaster * rc) {
+	RB_REQUIRE_DEVICE();
+	const size_t ntris = rc->tris.size();
+	if(ntris == 0) return rb_fail(RB_ERR_INVALID, "rb_raycaster_build: no triangle to build a hierarchy on");
+	if(ntris >= (size_t(1) << (31 - RB_LEAF_BITS))) return rb_fail(RB_ERR_UNSUPPORTED, "too many triangles for 32-bit leaf references");
+	rb_raycaster_free_device(rc);
+	RB_CUDA(cudaGetDevice(&rc->device));
+	cudaStream_t s = cudaStreamPerThread;
+	const uint32_t n = uint32_t(ntris);
+	// Input triangles in addMesh order: vertex ids and (localId, meshId).
+	std::vector<uint32_t> triVerts(ntris * 3), triIds(ntris * 2);
+	for(size_t i = 0; i < ntris; ++i) {
+		triVerts[3 * i] = uint32_t(rc->tris[i].v0); triVerts[3 * i + 1] = uint32_t(rc->tris[i].v1); triVerts[3 * i + 2] = uint32_t(rc->tris[i].v2);
+		triIds[2 * i] = uint32_t(rc->tris[i].localId); triIds[2 * i + 1] = rc->tris[i].meshId;
+	}
+	uint32_t *d_tvIn = nullptr, *d_idIn = nullptr, *d_vals = nullptr;
+	uint64_t * d_keys = nullptr;
+	unsigned int * d_bounds = nullptr;
+	int * d_childRefs = nullptr;
+	rc->nInterior = ntris - 1;
+	rc->nTris	  = ntris;
+	rc->nLeaves	  = ntris;
+	rc->nVerts	  = rc->verts.size() / 3;
+	RB_CUDA(cudaMalloc(&rc->d_verts, rc->verts.size() * sizeof(float) + 64));
+	RB_CUDA(cudaMemcpyAsync(rc->d_verts, rc->verts.data(), rc->verts.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+	RB_CUDA(cudaMalloc(&d_tvIn, triVerts.size() * sizeof(uint32_t)));
+	RB_CUDA(cudaMalloc(&d_idIn, triIds.size() * sizeof(uint32_t)));
+	RB_CUDA(cudaMemcpyAsync(d_tvIn, triVerts.data(), triVerts.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+	RB_CUDA(cudaMemcpyAsync(d_idIn, triIds.data(), triIds.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+	RB_CUDA(cudaMalloc(&d_keys, ntris * sizeof(uint64_t)));
+	RB_CUDA(cudaMalloc(&d_vals, ntris * sizeof(uint32_t)));
+	RB_CUDA(cudaMalloc(&d_bounds, 6 * sizeof(unsigned int)));
+	RB_CUDA(cudaMalloc(&d_childRefs, (2 * rc->nInterior + 2) * sizeof(int)));
+	RB_CUDA(cudaMalloc(&rc->d_nodes, (rc->nInterior + 1) * 64));
+	RB_CUDA(cudaMalloc(&rc->d_tris, ntris * 48 + 64));
+	RB_CUDA(cudaMalloc(&rc->d_roots, 64));
+	RB_CUDA(cudaMalloc(&rc->d_parent, (rc->nInterior + 1) * sizeof(int)));
+	RB_CUDA(cudaMalloc(&rc->d_leafParent, ntris * sizeof(int)));
+	RB_CUDA(cudaMalloc(&rc->d_leafCode, ntris * sizeof(int)));
+	RB_CUDA(cudaMalloc(&rc->d_triVerts, ntris * 3 * sizeof(uint32_t)));
+	RB_CUDA(cudaMalloc(&rc->d_triIds, ntris * 2 * sizeof(uint32_t)));
+	RB_CUDA(cudaMalloc(&rc->d_flags, (rc->nInterior + 1) * sizeof(unsigned int)));
+	RB_CUDA(cudaMemsetAsync(rc->d_nodes, 0, (rc->nInterior + 1) * 64, s));
+	const unsigned int initBounds[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+	RB_CUDA(cudaMemcpyAsync(d_bounds, initBounds, sizeof(initBounds), cudaMemcpyHostToDevice, s));
+	uint64_t launches = 0;
+	rb_k_lbvh_bounds<<<rb_blocks(n, 256), 256, 0, s>>>(rc->d_verts, d_tvIn, n, d_bounds);
+	rb_k_lbvh_morton<<<rb_blocks(n, 256), 256, 0, s>>>(rc->d_verts, d_tvIn, n, d_bounds, d_keys, d_vals);
+	launches += 2;
+	rb_status st = rb_radix_sort(d_keys, d_vals, n, 63, s, &launches);
+	if(st == RB_OK) {
+		rb_k_lbvh_gather<<<rb_blocks(n, 256), 256, 0, s>>>(d_vals, d_tvIn, d_idIn, n, rc->d_triVerts, rc->d_triIds);
+		++launches;
+		if(n > 1) {
+			rb_k_lbvh_hierarchy<<<rb_blocks(n - 1, 128), 128, 0, s>>>(d_keys, int(n), d_childRefs, rc->d_parent, rc->d_leafParent);
+			rb_k_lbvh_write_refs<<<rb_blocks(n - 1, 256), 256, 0, s>>>(d_childRefs, int(n - 1), rc->d_nodes);
+			launches += 2;
+		}
+		// Leaf table: leaf j holds triangle j. A single triangle is a root that is itself a leaf.
+		std::vector<int> leafCode(ntris);
+		for(size_t j = 0; j < ntris; ++j) leafCode[j] = int(j << RB_LEAF_BITS);
+		RB_CUDA(cudaMemcpyAsync(rc->d_leafCode, leafCode.data(), ntris * sizeof(int), cudaMemcpyHostToDevice, s));
+		float rootRec[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+		int rootRef = (n > 1) ? 0 : ~0;
+		std::memcpy(&rootRec[3], &rootRef, 4);
+		RB_CUDA(cudaMemcpyAsync(rc->d_roots, rootRec, sizeof(rootRec), cudaMemcpyHostToDevice, s));
+		if(n == 1) {
+			const int rootLink = ~0;
+			RB_CUDA(cudaMemcpyAsync(rc->d_leafParent, &rootLink, sizeof(int), cudaMemcpyHostToDevice, s));
+		}
+		RB_CUDA(cudaStreamSynchronize(s));
+		rc->dev.nodes  = rc->d_nodes;
+		rc->dev.tris   = rc->d_tris;
+		rc->dev.roots  = rc->d_roots;
+		rc->dev.nroots = 1;
+		st = rb_run_fit(rc, s);
+		++launches;
+	}
+	cudaFree(d_tvIn);
+	cudaFree(d_idIn);
+	cudaFree(d_keys);
+	cudaFree(d_vals);
+	cudaFree(d_bounds);
+	cudaFree(d_childRefs);
+	if(st) return st;
+	if(size_t(rc->dev.stackDepth) * RB_TRACE_BLOCK_THREADS * sizeof(int) > 160 * 1024) {
+		return rb_fail(RB_ERR_UNSUPPORTED, "LBVH depth %d needs a traversal stack larger than shared memory", rc->maxDepth);
+	}
+	rc->launches += launches;
+	rc->built			= true;
+	rc->hostMirrorStale = true;
+	return RB_OK;
+}
+
+rb_status rb_lbvh_refit(rb_raycaster * rc, const float * worldPositions, size_t nverts) {
+	RB_REQUIRE_DEVICE();
+	if(nverts != rc->nVerts) return rb_fail(RB_ERR_INVALID, "rb_raycaster_refit: %zu vertices given, hierarchy has %zu", nverts, rc->nVerts);
+	RB_CUDA(cudaSetDevice(rc->device));
+	cudaStream_t s = cudaStreamPerThread;
+	RB_CUDA(cudaMemcpyAsync(rc->d_verts, worldPositions, nverts * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+	rc->verts.assign(worldPositions, worldPositions + nverts * 3);
+	rb_status st = rb_run_fit(rc, s);
+	if(st) return st;
+	rc->hostMirrorStale = true;
+	return RB_OK;
+}
+
+// Device tree -> the reference's Node / TriangleInfos arrays (what RaycasterVisualisation reads). Roots come first
+// (slots 0..nroots-1), then every other node in a depth-first order; a leaf keeps (first triangle, count).
+rb_status rb_lbvh_download(const rb_raycaster * rc, rb_node * nodesOut, rb_tri * trisOut, float * vertsOut) {
+	RB_REQUIRE_DEVICE();
+	RB_CUDA(cudaSetDevice(rc->device));
+	RB_CUDA(cudaDeviceSynchronize());
+	const size_t ni = rc->nInterior, nt = rc->nTris, nr = size_t(rc->dev.nroots);
+	std::vector<float> nodes(ni * 16 + 16), roots(nr * 8 + 8), verts(rc->nVerts * 3);
+	std::vector<uint32_t> triVerts(nt * 3), triIds(nt * 2);
+	if(ni) RB_CUDA(cudaMemcpy(nodes.data(), rc->d_nodes, ni * 64, cudaMemcpyDeviceToHost));
+	if(nr) RB_CUDA(cudaMemcpy(roots.data(), rc->d_roots, nr * 32, cudaMemcpyDeviceToHost));
+	if(nt) RB_CUDA(cudaMemcpy(triVerts.data(), rc->d_triVerts, nt * 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	if(nt) RB_CUDA(cudaMemcpy(triIds.data(), rc->d_triIds, nt * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	if(rc->nVerts) RB_CUDA(cudaMemcpy(verts.data(), rc->d_verts, rc->nVerts * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+	if(vertsOut && rc->nVerts) std::memcpy(vertsOut, verts.data(), rc->nVerts * 3 * sizeof(float));
+	if(trisOut) {
+		for(size_t i = 0; i < nt; ++i) {
+			rb_tri & t = trisOut[i];
+			std::memset(&t, 0, sizeof(t));
+			t.v0 = triVerts[3 * i]; t.v1 = triVerts[3 * i + 1]; t.v2 = triVerts[3 * i + 2];
+			t.localId = triIds[2 * i];
+			t.meshId  = triIds[2 * i + 1];
+			const float *a = &verts[3 * t.v0], *b = &verts[3 * t.v1], *c = &verts[3 * t.v2];
+			for(int k = 0; k < 3; ++k) {
+				const float mn = (b[k] < a[k]) ? b[k] : a[k], mx = (a[k] < b[k]) ? b[k] : a[k];
+				t.bmin[k] = (c[k] < mn) ? c[k] : mn;
+				t.bmax[k] = (mx < c[k]) ? c[k] : mx;
+			}
+		}
+	}
+	if(nodesOut) {
+		struct Item { int ref; size_t slot; float box[6]; };
+		std::vector<Item> todo;
+		size_t next = nr;
+		for(size_t r = 0; r < nr; ++r) {
+			Item it;
+			std::memcpy(&it.ref, &roots[8 * r + 3], 4);
+			it.slot = r;
+			for(int k = 0; k < 3; ++k) { it.box[k] = roots[8 * r + k]; it.box[3 + k] = roots[8 * r + 4 + k]; }
+			todo.push_back(it);
+		}
+		while(!todo.empty()) {
+			const Item it = todo.back();
+			todo.pop_back();
+			rb_node & nd = nodesOut[it.slot];
+			std::memset(&nd, 0, sizeof(nd));
+			std::memcpy(nd.bmin, it.box, 12);
+			std::memcpy(nd.bmax, it.box + 3, 12);
+			if(it.ref < 0 || it.ref == RB_REF_NONE) {
+				nd.leaf = 1;
+				if(it.ref != RB_REF_NONE) {
+					const int code = ~it.ref;
+					nd.left	 = uint64_t(code >> RB_LEAF_BITS);
+					nd.right = uint64_t((code & (RB_LEAF_MAX_TRIS - 1)) + 1);
+				}
+				continue;
+			}
+			const float * f = &nodes[size_t(it.ref) * 16];
+			Item l, r;
+			std::memcpy(&l.ref, &f[12], 4);
+			std::memcpy(&r.ref, &f[13], 4);
+			std::memcpy(l.box, f, 24);
+			std::memcpy(r.box, f + 6, 24);
+			l.slot = next++;
+			r.slot = next++;
+			nd.leaf	 = 0;
+			nd.left	 = l.slot;
+			nd.right = r.slot;
+			todo.push_back(l);
+			todo.push_back(r);
+		}
+	}
+	return RB_OK;
+}

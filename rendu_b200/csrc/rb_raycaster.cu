@@ -67,7 +67,7 @@ extern "C" rb_status rb_set_device(int device) {
 
 // ---------------------------------------------------------------- kernels
 
-#define RB_TRACE_BLOCK 128
+#define RB_TRACE_BLOCK RB_TRACE_BLOCK_THREADS
 
 // Reads ray i from tightly packed float3 arrays.
 RB_D void rb_load_ray(const float * org, const float * dir, size_t i, V3 & o, V3 & d) {
@@ -243,12 +243,20 @@ void rb_raycaster_free_device(rb_raycaster * rc) {
 	cudaFree(rc->d_tris);
 	cudaFree(rc->d_roots);
 	cudaFree(rc->d_parent);
+	cudaFree(rc->d_leafParent);
+	cudaFree(rc->d_leafCode);
+	cudaFree(rc->d_flags);
 	cudaFree(rc->d_verts);
 	cudaFree(rc->d_triVerts);
+	cudaFree(rc->d_triIds);
 	rc->d_nodes = rc->d_tris = rc->d_roots = nullptr;
-	rc->d_parent   = nullptr;
-	rc->d_verts	   = nullptr;
-	rc->d_triVerts = nullptr;
+	rc->d_parent	 = nullptr;
+	rc->d_leafParent = nullptr;
+	rc->d_leafCode	 = nullptr;
+	rc->d_flags		 = nullptr;
+	rc->d_verts		 = nullptr;
+	rc->d_triVerts	 = nullptr;
+	rc->d_triIds	 = nullptr;
 	rc->dev		   = RbDeviceBvh{};
 }
 
@@ -266,12 +274,20 @@ rb_status rb_raycaster_upload_flat(rb_raycaster * rc, const RbFlatBvh & flat) {
 	RB_CUDA(cudaMalloc(&rc->d_parent, flat.parent.size() * sizeof(int) + 64));
 	RB_CUDA(cudaMalloc(&rc->d_verts, rc->verts.size() * sizeof(float) + 64));
 	RB_CUDA(cudaMalloc(&rc->d_triVerts, flat.triVerts.size() * sizeof(uint32_t) + 64));
+	RB_CUDA(cudaMalloc(&rc->d_triIds, flat.triIds.size() * sizeof(uint32_t) + 64));
+	RB_CUDA(cudaMalloc(&rc->d_leafParent, flat.leafParent.size() * sizeof(int) + 64));
+	RB_CUDA(cudaMalloc(&rc->d_leafCode, flat.leafCode.size() * sizeof(int) + 64));
+	RB_CUDA(cudaMalloc(&rc->d_flags, (flat.parent.size() + 1) * sizeof(unsigned int)));
+	rc->nLeaves = flat.leafCode.size();
 	RB_CUDA(cudaMemcpy(rc->d_nodes, flat.nodes.data(), flat.nodes.size() * sizeof(float), cudaMemcpyHostToDevice));
 	RB_CUDA(cudaMemcpy(rc->d_tris, flat.tris.data(), flat.tris.size() * sizeof(float), cudaMemcpyHostToDevice));
 	RB_CUDA(cudaMemcpy(rc->d_roots, flat.roots.data(), flat.roots.size() * sizeof(float), cudaMemcpyHostToDevice));
 	RB_CUDA(cudaMemcpy(rc->d_parent, flat.parent.data(), flat.parent.size() * sizeof(int), cudaMemcpyHostToDevice));
 	RB_CUDA(cudaMemcpy(rc->d_verts, rc->verts.data(), rc->verts.size() * sizeof(float), cudaMemcpyHostToDevice));
 	RB_CUDA(cudaMemcpy(rc->d_triVerts, flat.triVerts.data(), flat.triVerts.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+	RB_CUDA(cudaMemcpy(rc->d_triIds, flat.triIds.data(), flat.triIds.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+	RB_CUDA(cudaMemcpy(rc->d_leafParent, flat.leafParent.data(), flat.leafParent.size() * sizeof(int), cudaMemcpyHostToDevice));
+	RB_CUDA(cudaMemcpy(rc->d_leafCode, flat.leafCode.data(), flat.leafCode.size() * sizeof(int), cudaMemcpyHostToDevice));
 	rc->dev.nodes	   = rc->d_nodes;
 	rc->dev.tris	   = rc->d_tris;
 	rc->dev.roots	   = rc->d_roots;
@@ -403,12 +419,13 @@ extern "C" rb_status rb_raycaster_sizes(const rb_raycaster * rc, uint64_t out[5]
 	if(rc->buildMode == RB_BUILD_LBVH && rc->built) {
 		const uint64_t nt = rc->nTris;
 		out[0] = nt ? 2 * nt - 1 : 0;
+		out[3] = 1; // one tree over all meshes
 	} else {
 		out[0] = rc->nodes.size();
+		out[3] = rc->meshCount;
 	}
 	out[1] = rc->tris.size();
 	out[2] = rc->verts.size() / 3;
-	out[3] = rc->meshCount;
 	out[4] = uint64_t(rc->maxDepth);
 	return RB_OK;
 }

@@ -1,0 +1,158 @@
+"""GPU tests of the LBVH build, the refit and the hierarchy download (north_star: "GPU LBVH build ... sits alongside
+an upload path for the reference's host-built BVH"). An LBVH tree is a different tree than the reference's, so the
+bar is: same hit/miss for every ray, the same triangle except where two triangles are hit at exactly the same
+distance (shared edges), and bit-identical dist/u/v whenever the triangle is the same (same triangle test)."""
+import numpy as np
+import pytest
+
+import rendu_b200 as rb
+from rendu_b200 import workloads as wl
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def rays_for_tests(n=20000, seed=5):
+    ro, rd = wl.random_rays(n, seed)
+    co, cd = wl.coherent_rays(96)
+    return np.concatenate([ro, co]), np.concatenate([rd, cd])
+
+
+def compare_with_oracle(h, ho, max_ties):
+    assert np.array_equal(h["hit"], ho["hit"])
+    hit = h["hit"] == 1
+    same = (h["localId"] == ho["localId"]) & (h["meshId"] == ho["meshId"])
+    ties = hit & ~same
+    assert ties.sum() <= max_ties, ties.sum()
+    # A different triangle may only win at (numerically) the same distance.
+    if ties.any():
+        assert np.allclose(h["dist"][ties], ho["dist"][ties], rtol=1e-5, atol=0)
+    ok = hit & same
+    for k in ("dist", "u", "v", "w"):
+        assert np.array_equal(h[k][ok].view(np.uint32), ho[k][ok].view(np.uint32)), k
+
+
+@pytest.mark.parametrize("n", [1, 3, 40, 150])
+def test_lbvh_hits_match_reference_tree(n):
+    pos, idx = wl.displaced_grid(n)
+    o = orc.OracleRaycaster()
+    o.add_mesh(pos, idx)
+    o.build()
+    r = rb.Raycaster()
+    r.addMesh(pos, idx)
+    r.updateHierarchy(rb.BUILD_LBVH)
+    org, dirs = rays_for_tests()
+    h = r.intersects(org, dirs)
+    ho = o.intersect(org, dirs, threads=8)
+    compare_with_oracle(h, ho, max_ties=20)
+    assert np.array_equal(r.intersectsAny(org, dirs).astype(np.uint8), o.intersect_any(org, dirs, threads=8))
+    s = r.sizes()
+    assert s["nodes"] == 2 * s["tris"] - 1 and s["meshes"] == 1 and s["depth"] >= 1
+
+
+def test_lbvh_multi_mesh_single_triangle_and_download_roundtrip():
+    rng = np.random.RandomState(3)
+    meshes = []
+    for k in range(12):
+        p, i = wl.displaced_grid(2 + k % 5)
+        m = np.eye(4, dtype=np.float32)
+        m[3, :3] = rng.uniform(-0.6, 0.6, 3)
+        m[0, 0] = m[1, 1] = m[2, 2] = 0.4
+        meshes.append((p, i, m.reshape(16)))
+    meshes.append((np.array([[0, 1.2, 0], [0.6, 1.2, 0], [0, 1.2, 0.6]], np.float32), np.array([0, 1, 2], np.uint32), None))
+    o = orc.OracleRaycaster()
+    r = rb.Raycaster()
+    for p, i, m in meshes:
+        o.add_mesh(p, i, m)
+        r.addMesh(p, i, m)
+    o.build()
+    r.updateHierarchy(rb.BUILD_LBVH)
+    org, dirs = rays_for_tests(30000, 9)
+    h = r.intersects(org, dirs)
+    compare_with_oracle(h, o.intersect(org, dirs, threads=8), max_ties=30)
+    # Download in the reference's format: a proper binary tree over every triangle, parents enclose children.
+    nodes, tris, verts = r.download_bvh()
+    assert nodes.size == 2 * tris.size - 1
+    leaves = nodes[nodes["leaf"] == 1]
+    covered = np.zeros(tris.size, np.int32)
+    for lf in leaves:
+        covered[int(lf["left"]):int(lf["left"] + lf["right"])] += 1
+    assert (covered == 1).all()
+    inner = nodes[nodes["leaf"] == 0]
+    for side in ("left", "right"):
+        ch = nodes[inner[side].astype(np.int64)]
+        assert (ch["bmin"] >= inner["bmin"]).all() and (ch["bmax"] <= inner["bmax"]).all()
+    assert sorted(zip(tris["meshId"].tolist(), tris["localId"].tolist())) == sorted(zip(o.tris["meshId"].tolist(), o.tris["localId"].tolist()))
+    # ... and it goes back in through the upload path, giving the same hits.
+    r2 = rb.Raycaster()
+    r2.upload_bvh(nodes, tris, verts, r.sizes()["meshes"])
+    h2 = r2.intersects(org, dirs)
+    assert h2[["hit", "dist", "u", "v", "localId", "meshId"]].tobytes() == h[["hit", "dist", "u", "v", "localId", "meshId"]].tobytes()
+    # Single triangle: the root is a leaf.
+    r3 = rb.Raycaster()
+    r3.addMesh(*meshes[-1][:2])
+    r3.updateHierarchy(rb.BUILD_LBVH)
+    one = r3.intersects(np.array([0.1, 2, 0.1], np.float32), np.array([0, -1, 0], np.float32))
+    assert one["hit"] == 1 and abs(float(one["dist"]) - 0.8) < 1e-6
+
+
+@pytest.mark.parametrize("mode", [rb.BUILD_REFERENCE, rb.BUILD_LBVH])
+def test_refit_after_vertices_moved(mode):
+    pos, idx = wl.displaced_grid(64)
+    r = rb.Raycaster()
+    r.addMesh(pos, idx)
+    r.updateHierarchy(mode)
+    org, dirs = rays_for_tests(20000, 13)
+    before = r.intersects(org, dirs)
+    # Refit with unchanged vertices: bottom-up unions reproduce the boxes, results are bit-identical.
+    r.refit(pos)
+    same = r.intersects(org, dirs)
+    assert same.tobytes() == before.tobytes()
+    # Re-displace (same topology): results must equal a fresh build on the moved mesh.
+    moved = pos.copy()
+    moved[:, 1] = (moved[:, 1] * np.float32(2.5) + np.float32(0.05) * np.sin(np.float32(11) * moved[:, 0])).astype(np.float32)
+    r.refit(moved)
+    h = r.intersects(org, dirs)
+    o = orc.OracleRaycaster()
+    o.add_mesh(moved, idx)
+    o.build()
+    compare_with_oracle(h, o.intersect(org, dirs, threads=8), max_ties=20)
+    nodes, tris, verts = r.download_bvh()
+    assert np.array_equal(verts, moved)
+    inner = nodes[nodes["leaf"] == 0]
+    ch = nodes[inner["left"].astype(np.int64)]
+    assert (ch["bmin"] >= inner["bmin"]).all() and (ch["bmax"] <= inner["bmax"]).all()
+
+
+def test_lbvh_large_build_depth_and_ordered_mode():
+    pos, idx = wl.displaced_grid(500)  # 500k triangles
+    r = rb.Raycaster()
+    r.addMesh(pos, idx)
+    r.updateHierarchy(rb.BUILD_LBVH)
+    s = r.sizes()
+    assert s["tris"] == 500000 and 18 <= s["depth"] <= 64
+    co, cd = wl.coherent_rays(256)
+    h = r.intersects(co, cd)
+    r.set_trace_mode(rb.TRACE_ORDERED)
+    h2 = r.intersects(co, cd)
+    assert np.array_equal(h["hit"], h2["hit"])
+    assert ((h["localId"] != h2["localId"]) & (h["hit"] == 1)).sum() <= 8
+    ref_tree = rb.Raycaster()
+    ref_tree.addMesh(pos, idx)
+    ref_tree.updateHierarchy(rb.BUILD_REFERENCE)
+    h3 = ref_tree.intersects(co, cd)
+    assert np.array_equal(h["hit"], h3["hit"]) and ((h["localId"] != h3["localId"]) & (h["hit"] == 1)).sum() <= 8
+
+
+def test_path_tracer_on_lbvh_tree():
+    from rendu_b200 import pathtracer as rpt
+    desc = wl.cornell_synthetic(24, 64, 16)
+    cam = wl.cornell_camera(1.5)
+    imgs = []
+    for mode in (rb.BUILD_REFERENCE, rb.BUILD_LBVH):
+        pt = rpt.PathTracer(rpt.Scene(desc, build_mode=mode))
+        img = np.zeros((48, 72, 3), np.float32)
+        pt.render(cam, 16, 5, img, rpt.make_opts(seed=8))
+        imgs.append(img)
+    off = (np.abs(imgs[0] - imgs[1]).max(axis=2) > 2e-3).mean()
+    assert off < 0.01, off
