@@ -34,11 +34,11 @@ def golden_scene(name):
     return desc, cam, g
 
 
-def gpu_render(desc, cam, w, h, samples, depth, seed=0, components=3, image=None, **kw):
+def gpu_render(desc, cam, w, h, spp, depth, seed=0, components=3, image=None, **kw):
     sc = rpt.Scene(desc)
     pt = rpt.PathTracer(sc)
     img = np.zeros((h, w, components), np.float32) if image is None else image
-    pt.render(cam, samples, depth, img, rpt.make_opts(seed=seed, **kw))
+    pt.render(cam, spp, depth, img, rpt.make_opts(seed=seed, **kw))
     return img, pt
 
 
