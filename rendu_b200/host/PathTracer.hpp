@@ -1,0 +1,37 @@
+#pragma once
+// Drop-in for the reference's src/apps/pathtracer/PathTracer.hpp: PathTracer(scene), render(camera, samples, depth,
+// image), raycaster() — rendered by the CUDA wavefront path tracer through include/rendu_b200.h.
+#include "Raycaster.hpp"
+#include "scene/Scene.hpp"
+#include "Common.hpp"
+
+struct rb_scene;
+struct rb_pathtracer;
+
+class PathTracer {
+public:
+	PathTracer() = default;
+	explicit PathTracer(const std::shared_ptr<Scene> & scene);
+	~PathTracer();
+	PathTracer(const PathTracer &) = delete;
+	PathTracer & operator=(const PathTracer &) = delete;
+
+	// Accumulates into `render` (caller zero-fills) and divides by the sample count, like the reference.
+	void render(const Camera & camera, size_t samples, size_t depth, Image & render);
+	const Raycaster & raycaster() const { return _raycaster; }
+
+	// Extensions: RNG seed of the counter-based generator, and the share of the frame this process renders
+	// (tile split: rows (y / tileRows) % tileCount == tileIndex; sample split: cells sid % sampleCount == sampleIndex).
+	void setSeed(unsigned long long seed) { _seed = seed; }
+	void setTile(unsigned int rows, unsigned int index, unsigned int count) { _tile[0] = rows; _tile[1] = index; _tile[2] = count; }
+	void setSampleSplit(unsigned int index, unsigned int count) { _split[0] = index; _split[1] = count; }
+
+private:
+	Raycaster _raycaster;
+	std::shared_ptr<Scene> _scene;
+	rb_scene * _deviceScene = nullptr;
+	rb_pathtracer * _device = nullptr;
+	unsigned long long _seed = 0;
+	unsigned int _tile[3]	 = {0, 0, 0};
+	unsigned int _split[2]	 = {0, 0};
+};
