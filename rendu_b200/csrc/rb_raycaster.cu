@@ -199,6 +199,65 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_persistent(RbDevice
 	}
 }
 
+// Phase-voting scheduler. Every live lane is waiting either for a node step or for a leaf step; the warp executes
+// the leaf phase once at least `leafVotes` lanes wait for it (or nobody wants a node), otherwise the node phase. Lanes
+// of the other kind idle for that iteration instead of the whole warp running at the pace of one lane's descent.
+template<bool ANY, bool ORDERED>
+__global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_phased(RbDeviceBvh bvh, const float * __restrict__ org, const float * __restrict__ dir, float mini, float maxi, unsigned int n, void * __restrict__ out, unsigned int * __restrict__ cursor, int threshold, int leafVotes) {
+	extern __shared__ int s_stack[];
+	int * stack				= s_stack + threadIdx.x;
+	const int stride		= blockDim.x;
+	const unsigned int lane = threadIdx.x & 31u;
+	bool active = false, exhausted = false;
+	unsigned int rayIdx = 0;
+	RbRay ray;
+	RbTraversal T;
+	for(;;) {
+		if(!exhausted) {
+			const unsigned int idle = __ballot_sync(0xffffffffu, !active);
+			if(idle) {
+				const int nIdle	 = __popc(idle);
+				const int leader = __ffs(idle) - 1;
+				unsigned int base = 0;
+				if((int)lane == leader) base = atomicAdd(cursor, (unsigned int)nIdle);
+				base = __shfl_sync(0xffffffffu, base, leader);
+				if(!active) {
+					const unsigned int idx = base + __popc(idle & ((1u << lane) - 1u));
+					if(idx < n) {
+						V3 o, d;
+						rb_load_ray(org, dir, idx, o, d);
+						ray = rb_make_ray(o, d);
+						rb_traversal_init(T, bvh, mini, maxi);
+						rayIdx = idx;
+						active = true;
+					}
+				}
+				exhausted = (base + (unsigned int)nIdle) >= n;
+			}
+		}
+		if(!__any_sync(0xffffffffu, active)) break;
+		bool more;
+		do {
+			const bool wantsLeaf	  = active && rb_wants_leaf(T);
+			const unsigned int leafM  = __ballot_sync(0xffffffffu, wantsLeaf);
+			const unsigned int nodeM  = __ballot_sync(0xffffffffu, active && !wantsLeaf);
+			bool finished = false;
+			if(__popc(leafM) >= leafVotes || nodeM == 0u) {
+				if(wantsLeaf) finished = rb_phase_leaf<ANY, false>(T, bvh, ray, nullptr);
+			} else {
+				if(active && !wantsLeaf) finished = rb_phase_node<false, ORDERED>(T, bvh, ray, stack, stride, nullptr);
+			}
+			if(finished) {
+				if(ANY) rb_store_any(static_cast<uint8_t *>(out), rayIdx, bvh, T.best);
+				else rb_store_hit(static_cast<rb_hit *>(out), rayIdx, bvh, T.best);
+				active = false;
+			}
+			const int nActive = __popc(__ballot_sync(0xffffffffu, active));
+			more = exhausted ? (nActive > 0) : (nActive >= threshold);
+		} while(more);
+	}
+}
+
 // Instrumented copy: same loops, counts the work that defines the algorithmic bytes per ray.
 template<bool ANY, bool ORDERED>
 __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_count(RbDeviceBvh bvh, const float * __restrict__ org, const float * __restrict__ dir, float mini, float maxi, size_t n, unsigned long long * __restrict__ counters) {
@@ -305,6 +364,7 @@ extern "C" rb_status rb_raycaster_create(rb_raycaster ** out) {
 	// RB_FETCH_THRESHOLD the number of live lanes below which a warp refills from the queue.
 	if(const char * e = getenv("RB_PERSISTENT")) (*out)->persistent = atoi(e) != 0;
 	if(const char * e = getenv("RB_FETCH_THRESHOLD")) (*out)->fetchThreshold = atoi(e);
+	if(const char * e = getenv("RB_LEAF_VOTES")) (*out)->leafVotes = atoi(e);
 	return RB_OK;
 }
 
@@ -483,6 +543,30 @@ static rb_status rb_launch_trace(const rb_raycaster * rc, const float * d_origin
 	const size_t smem	= rb_trace_smem_bytes(rc, RB_TRACE_BLOCK);
 	const bool ordered	= rc->traceMode == RB_TRACE_ORDERED;
 	rb_status st;
+	if(rc->persistent && rc->leafVotes > 0) {
+		auto kernel = ordered ? rb_k_trace_phased<ANY, true> : rb_k_trace_phased<ANY, false>;
+		st = rb_prepare_kernel(kernel, smem);
+		if(st) return st;
+		int perSm = 0, sms = 0;
+		RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, RB_TRACE_BLOCK, smem));
+		RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, rc->device));
+		if(perSm < 1) return rb_fail(RB_ERR_CUDA, "traversal kernel does not fit on an SM (stack depth %d)", rc->dev.stackDepth);
+		unsigned int * d_cursor = nullptr;
+		RB_CUDA(cudaMallocAsync(&d_cursor, sizeof(unsigned int), s));
+		const size_t chunkMax = 0xC0000000ull;
+		for(size_t done = 0; done < nrays; done += chunkMax) {
+			const size_t n = (nrays - done < chunkMax) ? (nrays - done) : chunkMax;
+			const size_t blocksNeeded = (n + RB_TRACE_BLOCK - 1) / RB_TRACE_BLOCK;
+			const unsigned grid = unsigned(blocksNeeded < size_t(perSm) * sms ? blocksNeeded : size_t(perSm) * sms);
+			RB_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned int), s));
+			void * outp = ANY ? static_cast<void *>(static_cast<uint8_t *>(d_out) + done) : static_cast<void *>(static_cast<rb_hit *>(d_out) + done);
+			kernel<<<grid, RB_TRACE_BLOCK, smem, s>>>(rc->dev, d_origins + 3 * done, d_directions + 3 * done, mini, maxi, (unsigned int)n, outp, d_cursor, rc->fetchThreshold, rc->leafVotes);
+			RB_CUDA(cudaGetLastError());
+			rc->launches++;
+		}
+		RB_CUDA(cudaFreeAsync(d_cursor, s));
+		return RB_OK;
+	}
 	if(rc->persistent) {
 		auto kernel = ordered ? rb_k_trace_persistent<ANY, true> : rb_k_trace_persistent<ANY, false>;
 		st = rb_prepare_kernel(kernel, smem);

@@ -308,6 +308,105 @@ RB_D bool rb_step_ordered(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay 
 }
 
 
+// ---------------------------------------------------------------------------------------------- phase-split steps
+// The same traversal cut into its two kinds of work so that a warp can decide, by vote, which kind to execute next:
+//   node phase : take the pending node if none is current (stack, else next accepted root), then — if it is an interior
+//                node — box-test its two children and choose the next node;
+//   leaf phase : test the triangles of the current leaf.
+// Order of operations per ray is unchanged (a ray never starts a node before finishing its pending leaf), so results
+// are identical to rb_step_*; only the interleaving BETWEEN rays of a warp differs.
+RB_D bool rb_wants_leaf(const RbTraversal & T) { return T.cur < 0; }
+
+// Returns true when the traversal has finished (no node left).
+template<bool COUNT, bool ORDERED, bool REGULAR>
+RB_D bool rb_phase_node_t(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ray, int * stack, int stride, RbWork * work) {
+	int cur = T.cur;
+	if(cur == RB_REF_NONE) {
+		if(T.sp > 0) {
+			--T.sp;
+			cur = stack[T.sp * stride];
+		} else {
+			while(T.root > 0) {
+				--T.root;
+				const float4 r0 = rb_ldg4(bvh.roots + 2 * T.root);
+				const float4 r1 = rb_ldg4(bvh.roots + 2 * T.root + 1);
+				if(COUNT) work->roots++;
+				if(rb_box_test_t<REGULAR>(ray, r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, T.mini, ORDERED ? T.maxi : T.maxi0)) {
+					cur = __float_as_int(r0.w);
+					break;
+				}
+			}
+			if(cur == RB_REF_NONE) return true;
+		}
+	}
+	if(cur >= 0) {
+		const float4 * n = bvh.nodes + 4 * (size_t)cur;
+		const float4 n0 = rb_ldg4(n), n1 = rb_ldg4(n + 1), n2 = rb_ldg4(n + 2), n3 = rb_ldg4(n + 3);
+		if(COUNT) work->interior++;
+		const int refL = __float_as_int(n3.x), refR = __float_as_int(n3.y);
+		if(ORDERED) {
+			float dL, dR;
+			const bool hitL = rb_box_test_dist<REGULAR>(ray, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, T.mini, T.maxi, dL);
+			const bool hitR = rb_box_test_dist<REGULAR>(ray, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, T.mini, T.maxi, dR);
+			if(hitL && hitR) {
+				const bool leftFirst = dL < dR;
+				stack[T.sp * stride] = leftFirst ? refR : refL;
+				++T.sp;
+				cur = leftFirst ? refL : refR;
+			} else {
+				cur = hitR ? refR : (hitL ? refL : RB_REF_NONE);
+			}
+		} else {
+			const bool hitL = rb_box_test_t<REGULAR>(ray, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, T.mini, T.maxi);
+			const bool hitR = rb_box_test_t<REGULAR>(ray, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, T.mini, T.maxi);
+			if(hitR) {
+				if(hitL) {
+					stack[T.sp * stride] = refL;
+					++T.sp;
+				}
+				cur = refR;
+			} else {
+				cur = hitL ? refL : RB_REF_NONE;
+			}
+		}
+		if(COUNT) work->maxStack = max(work->maxStack, (unsigned int)T.sp);
+	}
+	T.cur = cur;
+	return false;
+}
+
+// Returns true when an ANY query has found its hit.
+template<bool ANY, bool COUNT>
+RB_D bool rb_phase_leaf(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ray, RbWork * work) {
+	const int code	= ~T.cur;
+	const int first = code >> RB_LEAF_BITS;
+	const int count = (code & (RB_LEAF_MAX_TRIS - 1)) + 1;
+	T.cur = RB_REF_NONE;
+	for(int k = 0; k < count; ++k) {
+		const float4 * tp = bvh.tris + 3 * (size_t)(first + k);
+		const float4 t0 = rb_ldg4(tp), t1 = rb_ldg4(tp + 1), t2 = rb_ldg4(tp + 2);
+		if(COUNT) work->tris++;
+		float t, u, v;
+		if(rb_tri_test(ray, V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, T.mini, T.maxi, t, u, v)) {
+			if(ANY) {
+				T.best.t = t; T.best.u = u; T.best.v = v; T.best.tri = first + k;
+				return true;
+			}
+			if(t < T.best.t) {
+				T.best.t = t; T.best.u = u; T.best.v = v; T.best.tri = first + k;
+				T.maxi = t;
+			}
+		}
+	}
+	return false;
+}
+
+template<bool COUNT, bool ORDERED>
+RB_D bool rb_phase_node(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ray, int * stack, int stride, RbWork * work) {
+	if(ray.regular) return rb_phase_node_t<COUNT, ORDERED, true>(T, bvh, ray, stack, stride, work);
+	return rb_phase_node_t<COUNT, ORDERED, false>(T, bvh, ray, stack, stride, work);
+}
+
 // One traversal step. The NaN-faithful box test is only compiled into the copy taken by irregular rays (a direction
 // component that is zero or denormal, or a non-finite origin); every other ray runs the FMNMX form.
 template<bool ANY, bool COUNT, bool ORDERED>
