@@ -505,15 +505,14 @@ def run_explore(args):
     sh = torch.cuda.current_stream().cuda_stream
     to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
     d_co, d_cd = to(co), to(cd)
-    variants = [("simple", {"RB_PERSISTENT": "0", "RB_LEAF_VOTES": "0"}, rb.TRACE_EXACT)]
+    variants = [("simple", {"RB_PERSISTENT": "0", "RB_LEAF_VOTES": "0", "RB_DUAL": "0"}, rb.TRACE_EXACT)]
     for thr in (8, 20, 28):
         variants.append(("persistent_t%d" % thr, {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": str(thr), "RB_LEAF_VOTES": "0"}, rb.TRACE_EXACT))
-    for votes in (1, 4, 8, 12, 16, 24):
-        variants.append(("phased_v%d_t20" % votes, {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "20", "RB_LEAF_VOTES": str(votes)}, rb.TRACE_EXACT))
-    variants.append(("phased_v8_t28", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "28", "RB_LEAF_VOTES": "8"}, rb.TRACE_EXACT))
-    variants.append(("phased_v8_t12", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "12", "RB_LEAF_VOTES": "8"}, rb.TRACE_EXACT))
-    variants.append(("ordered_phased_v8_t20", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "20", "RB_LEAF_VOTES": "8"}, rb.TRACE_ORDERED))
-    variants.append(("ordered_simple", {"RB_PERSISTENT": "0", "RB_LEAF_VOTES": "0"}, rb.TRACE_ORDERED))
+    variants.append(("phased_v4_t20", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "20", "RB_LEAF_VOTES": "4", "RB_DUAL": "0"}, rb.TRACE_EXACT))
+    for votes, refill in ((8, 8), (16, 8), (20, 8), (24, 8), (28, 8), (20, 4), (20, 16), (24, 16), (16, 1)):
+        variants.append(("dual_v%d_r%d" % (votes, refill), {"RB_PERSISTENT": "1", "RB_DUAL": "1", "RB_LEAF_VOTES": str(votes), "RB_DUAL_REFILL": str(refill)}, rb.TRACE_EXACT))
+    variants.append(("ordered_dual_v20_r8", {"RB_PERSISTENT": "1", "RB_DUAL": "1", "RB_LEAF_VOTES": "20", "RB_DUAL_REFILL": "8"}, rb.TRACE_ORDERED))
+    variants.append(("ordered_simple", {"RB_PERSISTENT": "0", "RB_LEAF_VOTES": "0", "RB_DUAL": "0"}, rb.TRACE_ORDERED))
     variants.append(("ordered_persistent_t20", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "20", "RB_LEAF_VOTES": "0"}, rb.TRACE_ORDERED))
     base, d_io, d_id, results = None, None, None, {}
     for name, env, mode in variants:

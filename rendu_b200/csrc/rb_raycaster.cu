@@ -258,6 +258,87 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_phased(RbDeviceBvh 
 	}
 }
 
+// Two rays per lane. The profile of the kernels above shows why a warp is slow: in the node loop only ~11 of 32 lanes
+// are busy, the others have reached a leaf and wait for the slowest descent (and in the leaf phase the reverse). Here
+// every lane owns two independent rays: while one of them waits for the warp's next leaf phase the lane keeps
+// descending with the other, so node phases run with nearly all lanes and leaf phases are postponed until most lanes
+// have a leaf pending. Per ray, the order of operations is untouched, hence identical results.
+struct RbSlot {
+	RbRay ray;
+	RbTraversal T;
+	unsigned int rayIdx;
+	int stackOff;
+	bool live;
+};
+
+RB_D void rb_swap_slots(RbSlot & a, RbSlot & b) {
+	const RbSlot t = a;
+	a = b;
+	b = t;
+}
+
+template<bool ANY, bool ORDERED>
+__global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_dual(RbDeviceBvh bvh, const float * __restrict__ org, const float * __restrict__ dir, float mini, float maxi, unsigned int n, void * __restrict__ out, unsigned int * __restrict__ cursor, int refillLanes, int leafVotes) {
+	extern __shared__ int s_stack[];
+	const int stride		= 2 * blockDim.x;
+	const unsigned int lane = threadIdx.x & 31u;
+	RbSlot X, Y;
+	X.live = false;
+	Y.live = false;
+	X.stackOff = threadIdx.x;
+	Y.stackOff = threadIdx.x + blockDim.x;
+	X.rayIdx = Y.rayIdx = 0;
+	bool exhausted = false;
+	for(;;) {
+		if(!exhausted) {
+			// Lanes with a free slot (kept in Y) take new rays once enough of them are waiting.
+			if(!X.live && Y.live) rb_swap_slots(X, Y);
+			const unsigned int freeM = __ballot_sync(0xffffffffu, !Y.live);
+			const int nFree = __popc(freeM);
+			const bool allIdle = !__any_sync(0xffffffffu, X.live);
+			if(nFree >= refillLanes || allIdle) {
+				const int leader = __ffs(freeM) - 1;
+				unsigned int base = 0;
+				if((int)lane == leader) base = atomicAdd(cursor, (unsigned int)nFree);
+				base = __shfl_sync(0xffffffffu, base, leader);
+				if(!Y.live) {
+					const unsigned int idx = base + __popc(freeM & ((1u << lane) - 1u));
+					if(idx < n) {
+						V3 o, d;
+						rb_load_ray(org, dir, idx, o, d);
+						Y.ray = rb_make_ray(o, d);
+						rb_traversal_init(Y.T, bvh, mini, maxi);
+						Y.rayIdx = idx;
+						Y.live	 = true;
+					}
+				}
+				exhausted = (base + (unsigned int)nFree) >= n;
+			}
+		}
+		const bool xLeaf = X.live && rb_wants_leaf(X.T), yLeaf = Y.live && rb_wants_leaf(Y.T);
+		const bool xNode = X.live && !xLeaf, yNode = Y.live && !yLeaf;
+		const unsigned int leafM = __ballot_sync(0xffffffffu, xLeaf || yLeaf);
+		const unsigned int nodeM = __ballot_sync(0xffffffffu, xNode || yNode);
+		if((leafM | nodeM) == 0u) {
+			if(exhausted) break;
+			continue;
+		}
+		bool finished = false;
+		if(__popc(leafM) >= leafVotes || nodeM == 0u) {
+			if(!xLeaf && yLeaf) rb_swap_slots(X, Y);
+			if(xLeaf || yLeaf) finished = rb_phase_leaf<ANY, false>(X.T, bvh, X.ray, nullptr);
+		} else {
+			if(!xNode && yNode) rb_swap_slots(X, Y);
+			if(xNode || yNode) finished = rb_phase_node<false, ORDERED>(X.T, bvh, X.ray, s_stack + X.stackOff, stride, nullptr);
+		}
+		if(finished) {
+			if(ANY) rb_store_any(static_cast<uint8_t *>(out), X.rayIdx, bvh, X.T.best);
+			else rb_store_hit(static_cast<rb_hit *>(out), X.rayIdx, bvh, X.T.best);
+			X.live = false;
+		}
+	}
+}
+
 // Instrumented copy: same loops, counts the work that defines the algorithmic bytes per ray.
 template<bool ANY, bool ORDERED>
 __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_count(RbDeviceBvh bvh, const float * __restrict__ org, const float * __restrict__ dir, float mini, float maxi, size_t n, unsigned long long * __restrict__ counters) {
@@ -365,6 +446,8 @@ extern "C" rb_status rb_raycaster_create(rb_raycaster ** out) {
 	if(const char * e = getenv("RB_PERSISTENT")) (*out)->persistent = atoi(e) != 0;
 	if(const char * e = getenv("RB_FETCH_THRESHOLD")) (*out)->fetchThreshold = atoi(e);
 	if(const char * e = getenv("RB_LEAF_VOTES")) (*out)->leafVotes = atoi(e);
+	if(const char * e = getenv("RB_DUAL")) (*out)->dual = atoi(e) != 0;
+	if(const char * e = getenv("RB_DUAL_REFILL")) (*out)->dualRefill = atoi(e);
 	return RB_OK;
 }
 
@@ -543,6 +626,31 @@ static rb_status rb_launch_trace(const rb_raycaster * rc, const float * d_origin
 	const size_t smem	= rb_trace_smem_bytes(rc, RB_TRACE_BLOCK);
 	const bool ordered	= rc->traceMode == RB_TRACE_ORDERED;
 	rb_status st;
+	if(rc->persistent && rc->dual) {
+		auto kernel = ordered ? rb_k_trace_dual<ANY, true> : rb_k_trace_dual<ANY, false>;
+		const size_t smem2 = 2 * smem;
+		st = rb_prepare_kernel(kernel, smem2);
+		if(st) return st;
+		int perSm = 0, sms = 0;
+		RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, RB_TRACE_BLOCK, smem2));
+		RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, rc->device));
+		if(perSm < 1) return rb_fail(RB_ERR_CUDA, "traversal kernel does not fit on an SM (stack depth %d)", rc->dev.stackDepth);
+		unsigned int * d_cursor = nullptr;
+		RB_CUDA(cudaMallocAsync(&d_cursor, sizeof(unsigned int), s));
+		const size_t chunkMax = 0xC0000000ull;
+		for(size_t done = 0; done < nrays; done += chunkMax) {
+			const size_t n = (nrays - done < chunkMax) ? (nrays - done) : chunkMax;
+			const size_t blocksNeeded = (n + 2 * RB_TRACE_BLOCK - 1) / (2 * RB_TRACE_BLOCK);
+			const unsigned grid = unsigned(blocksNeeded < size_t(perSm) * sms ? blocksNeeded : size_t(perSm) * sms);
+			RB_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned int), s));
+			void * outp = ANY ? static_cast<void *>(static_cast<uint8_t *>(d_out) + done) : static_cast<void *>(static_cast<rb_hit *>(d_out) + done);
+			kernel<<<grid, RB_TRACE_BLOCK, smem2, s>>>(rc->dev, d_origins + 3 * done, d_directions + 3 * done, mini, maxi, (unsigned int)n, outp, d_cursor, rc->dualRefill, rc->leafVotes > 0 ? rc->leafVotes : 20);
+			RB_CUDA(cudaGetLastError());
+			rc->launches++;
+		}
+		RB_CUDA(cudaFreeAsync(d_cursor, s));
+		return RB_OK;
+	}
 	if(rc->persistent && rc->leafVotes > 0) {
 		auto kernel = ordered ? rb_k_trace_phased<ANY, true> : rb_k_trace_phased<ANY, false>;
 		st = rb_prepare_kernel(kernel, smem);
