@@ -509,9 +509,9 @@ def run_explore(args):
     for thr in (8, 20, 28):
         variants.append(("persistent_t%d" % thr, {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": str(thr), "RB_LEAF_VOTES": "0"}, rb.TRACE_EXACT))
     variants.append(("phased_v4_t20", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "20", "RB_LEAF_VOTES": "4", "RB_DUAL": "0"}, rb.TRACE_EXACT))
-    for votes, refill in ((8, 8), (16, 8), (20, 8), (24, 8), (28, 8), (20, 4), (20, 16), (24, 16), (16, 1)):
+    for votes, refill in ((8, 16), (16, 16), (24, 16), (32, 16), (40, 16), (24, 8), (24, 24), (32, 32), (16, 4)):
         variants.append(("dual_v%d_r%d" % (votes, refill), {"RB_PERSISTENT": "1", "RB_DUAL": "1", "RB_LEAF_VOTES": str(votes), "RB_DUAL_REFILL": str(refill)}, rb.TRACE_EXACT))
-    variants.append(("ordered_dual_v20_r8", {"RB_PERSISTENT": "1", "RB_DUAL": "1", "RB_LEAF_VOTES": "20", "RB_DUAL_REFILL": "8"}, rb.TRACE_ORDERED))
+    variants.append(("ordered_dual_v24_r16", {"RB_PERSISTENT": "1", "RB_DUAL": "1", "RB_LEAF_VOTES": "24", "RB_DUAL_REFILL": "16"}, rb.TRACE_ORDERED))
     variants.append(("ordered_simple", {"RB_PERSISTENT": "0", "RB_LEAF_VOTES": "0", "RB_DUAL": "0"}, rb.TRACE_ORDERED))
     variants.append(("ordered_persistent_t20", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "20", "RB_LEAF_VOTES": "0"}, rb.TRACE_ORDERED))
     base, d_io, d_id, results = None, None, None, {}

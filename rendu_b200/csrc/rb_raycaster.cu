@@ -258,83 +258,83 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_phased(RbDeviceBvh 
 	}
 }
 
-// Two rays per lane. The profile of the kernels above shows why a warp is slow: in the node loop only ~11 of 32 lanes
-// are busy, the others have reached a leaf and wait for the slowest descent (and in the leaf phase the reverse). Here
-// every lane owns two independent rays: while one of them waits for the warp's next leaf phase the lane keeps
-// descending with the other, so node phases run with nearly all lanes and leaf phases are postponed until most lanes
-// have a leaf pending. Per ray, the order of operations is untouched, hence identical results.
+// Two rays per lane. The profile of the kernels above (profiles/) shows why a warp is slow: in the node loop only ~11
+// of 32 lanes are busy — the others have reached a leaf and wait for the slowest descent. Here every lane owns two
+// independent rays, A and B, each with its own registers and stack column; one iteration runs the node phase for the A
+// rays that want it and then for the B rays that want it, so a lane whose A ray waits for a leaf phase keeps
+// descending with B. Leaf phases are postponed until `leafVotes` of the warp's 64 slots have a leaf pending. Per ray,
+// the order of operations is untouched, hence identical results. (A first version kept one "working" slot and swapped
+// the register sets; the swap code, executed for two or three lanes at a time, cost more than it saved.)
 struct RbSlot {
 	RbRay ray;
 	RbTraversal T;
 	unsigned int rayIdx;
-	int stackOff;
 	bool live;
 };
 
-RB_D void rb_swap_slots(RbSlot & a, RbSlot & b) {
-	const RbSlot t = a;
-	a = b;
-	b = t;
+template<bool ANY>
+RB_D void rb_slot_finish(RbSlot & S, const RbDeviceBvh & bvh, void * out) {
+	if(ANY) rb_store_any(static_cast<uint8_t *>(out), S.rayIdx, bvh, S.T.best);
+	else rb_store_hit(static_cast<rb_hit *>(out), S.rayIdx, bvh, S.T.best);
+	S.live = false;
+}
+
+RB_D void rb_slot_start(RbSlot & S, const RbDeviceBvh & bvh, const float * org, const float * dir, unsigned int idx, float mini, float maxi) {
+	V3 o, d;
+	rb_load_ray(org, dir, idx, o, d);
+	S.ray = rb_make_ray(o, d);
+	rb_traversal_init(S.T, bvh, mini, maxi);
+	S.rayIdx = idx;
+	S.live	 = true;
 }
 
 template<bool ANY, bool ORDERED>
-__global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_dual(RbDeviceBvh bvh, const float * __restrict__ org, const float * __restrict__ dir, float mini, float maxi, unsigned int n, void * __restrict__ out, unsigned int * __restrict__ cursor, int refillLanes, int leafVotes) {
+__global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_dual(RbDeviceBvh bvh, const float * __restrict__ org, const float * __restrict__ dir, float mini, float maxi, unsigned int n, void * __restrict__ out, unsigned int * __restrict__ cursor, int refillSlots, int leafVotes) {
 	extern __shared__ int s_stack[];
 	const int stride		= 2 * blockDim.x;
+	int * stackA			= s_stack + threadIdx.x;
+	int * stackB			= s_stack + threadIdx.x + blockDim.x;
 	const unsigned int lane = threadIdx.x & 31u;
-	RbSlot X, Y;
-	X.live = false;
-	Y.live = false;
-	X.stackOff = threadIdx.x;
-	Y.stackOff = threadIdx.x + blockDim.x;
-	X.rayIdx = Y.rayIdx = 0;
+	const unsigned int below = (1u << lane) - 1u;
+	RbSlot A, B;
+	A.live = false;
+	B.live = false;
+	A.rayIdx = B.rayIdx = 0;
 	bool exhausted = false;
 	for(;;) {
 		if(!exhausted) {
-			// Lanes with a free slot (kept in Y) take new rays once enough of them are waiting.
-			if(!X.live && Y.live) rb_swap_slots(X, Y);
-			const unsigned int freeM = __ballot_sync(0xffffffffu, !Y.live);
-			const int nFree = __popc(freeM);
-			const bool allIdle = !__any_sync(0xffffffffu, X.live);
-			if(nFree >= refillLanes || allIdle) {
-				const int leader = __ffs(freeM) - 1;
+			const unsigned int freeA = __ballot_sync(0xffffffffu, !A.live);
+			const unsigned int freeB = __ballot_sync(0xffffffffu, !B.live);
+			const int nA = __popc(freeA), nB = __popc(freeB);
+			if(nA + nB >= refillSlots) {
 				unsigned int base = 0;
-				if((int)lane == leader) base = atomicAdd(cursor, (unsigned int)nFree);
-				base = __shfl_sync(0xffffffffu, base, leader);
-				if(!Y.live) {
-					const unsigned int idx = base + __popc(freeM & ((1u << lane) - 1u));
-					if(idx < n) {
-						V3 o, d;
-						rb_load_ray(org, dir, idx, o, d);
-						Y.ray = rb_make_ray(o, d);
-						rb_traversal_init(Y.T, bvh, mini, maxi);
-						Y.rayIdx = idx;
-						Y.live	 = true;
-					}
+				if(lane == 0) base = atomicAdd(cursor, (unsigned int)(nA + nB));
+				base = __shfl_sync(0xffffffffu, base, 0);
+				if(!A.live) {
+					const unsigned int idx = base + __popc(freeA & below);
+					if(idx < n) rb_slot_start(A, bvh, org, dir, idx, mini, maxi);
 				}
-				exhausted = (base + (unsigned int)nFree) >= n;
+				if(!B.live) {
+					const unsigned int idx = base + (unsigned int)nA + __popc(freeB & below);
+					if(idx < n) rb_slot_start(B, bvh, org, dir, idx, mini, maxi);
+				}
+				exhausted = (base + (unsigned int)(nA + nB)) >= n;
 			}
 		}
-		const bool xLeaf = X.live && rb_wants_leaf(X.T), yLeaf = Y.live && rb_wants_leaf(Y.T);
-		const bool xNode = X.live && !xLeaf, yNode = Y.live && !yLeaf;
-		const unsigned int leafM = __ballot_sync(0xffffffffu, xLeaf || yLeaf);
-		const unsigned int nodeM = __ballot_sync(0xffffffffu, xNode || yNode);
-		if((leafM | nodeM) == 0u) {
+		const bool aLeaf = A.live && rb_wants_leaf(A.T), bLeaf = B.live && rb_wants_leaf(B.T);
+		const bool aNode = A.live && !aLeaf, bNode = B.live && !bLeaf;
+		const int nLeaf = __popc(__ballot_sync(0xffffffffu, aLeaf)) + __popc(__ballot_sync(0xffffffffu, bLeaf));
+		const int nNode = __popc(__ballot_sync(0xffffffffu, aNode)) + __popc(__ballot_sync(0xffffffffu, bNode));
+		if(nLeaf + nNode == 0) {
 			if(exhausted) break;
 			continue;
 		}
-		bool finished = false;
-		if(__popc(leafM) >= leafVotes || nodeM == 0u) {
-			if(!xLeaf && yLeaf) rb_swap_slots(X, Y);
-			if(xLeaf || yLeaf) finished = rb_phase_leaf<ANY, false>(X.T, bvh, X.ray, nullptr);
+		if(nLeaf >= leafVotes || nNode == 0) {
+			if(aLeaf && rb_phase_leaf<ANY, false>(A.T, bvh, A.ray, nullptr)) rb_slot_finish<ANY>(A, bvh, out);
+			if(bLeaf && rb_phase_leaf<ANY, false>(B.T, bvh, B.ray, nullptr)) rb_slot_finish<ANY>(B, bvh, out);
 		} else {
-			if(!xNode && yNode) rb_swap_slots(X, Y);
-			if(xNode || yNode) finished = rb_phase_node<false, ORDERED>(X.T, bvh, X.ray, s_stack + X.stackOff, stride, nullptr);
-		}
-		if(finished) {
-			if(ANY) rb_store_any(static_cast<uint8_t *>(out), X.rayIdx, bvh, X.T.best);
-			else rb_store_hit(static_cast<rb_hit *>(out), X.rayIdx, bvh, X.T.best);
-			X.live = false;
+			if(aNode && rb_phase_node<false, ORDERED>(A.T, bvh, A.ray, stackA, stride, nullptr)) rb_slot_finish<ANY>(A, bvh, out);
+			if(bNode && rb_phase_node<false, ORDERED>(B.T, bvh, B.ray, stackB, stride, nullptr)) rb_slot_finish<ANY>(B, bvh, out);
 		}
 	}
 }
@@ -644,7 +644,7 @@ static rb_status rb_launch_trace(const rb_raycaster * rc, const float * d_origin
 			const unsigned grid = unsigned(blocksNeeded < size_t(perSm) * sms ? blocksNeeded : size_t(perSm) * sms);
 			RB_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned int), s));
 			void * outp = ANY ? static_cast<void *>(static_cast<uint8_t *>(d_out) + done) : static_cast<void *>(static_cast<rb_hit *>(d_out) + done);
-			kernel<<<grid, RB_TRACE_BLOCK, smem2, s>>>(rc->dev, d_origins + 3 * done, d_directions + 3 * done, mini, maxi, (unsigned int)n, outp, d_cursor, rc->dualRefill, rc->leafVotes > 0 ? rc->leafVotes : 20);
+			kernel<<<grid, RB_TRACE_BLOCK, smem2, s>>>(rc->dev, d_origins + 3 * done, d_directions + 3 * done, mini, maxi, (unsigned int)n, outp, d_cursor, rc->dualRefill, rc->leafVotes > 0 ? rc->leafVotes : 24);
 			RB_CUDA(cudaGetLastError());
 			rc->launches++;
 		}
