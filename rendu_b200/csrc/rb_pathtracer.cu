@@ -119,8 +119,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_raygen(RbFrame f, RbBatch
 template<bool ORDERED>
 __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_trace(RbDeviceBvh bvh, RbPathBuffers pb, const uint32_t * __restrict__ queue, uint32_t did, int threshold, unsigned long long * __restrict__ stats) {
 	extern __shared__ int s_stack[];
-	int * stack				= s_stack + threadIdx.x;
-	const int stride		= blockDim.x;
+	const RbStack st		= rb_make_stack(s_stack + threadIdx.x, blockDim.x);
 	const unsigned int lane = threadIdx.x & 31u;
 	const unsigned int n	= pb.counters[rb_cnt_queue(did)];
 	unsigned int * cursor	= pb.counters + rb_cnt_cursor_t(did);
@@ -144,7 +143,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_trace(RbDeviceBvh bvh, Rb
 						slot = queue[idx];
 						const float4 o = pb.rayO[slot], d = pb.rayD[slot];
 						ray = rb_make_ray(V3{o.x, o.y, o.z}, V3{d.x, d.y, d.z});
-						rb_traversal_init(T, bvh, 0.0001f, 1e8f);
+						rb_traversal_init(T, bvh, 0.0001f, 1e8f, st);
 						active = true;
 					}
 				}
@@ -155,7 +154,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_trace(RbDeviceBvh bvh, Rb
 		bool more;
 		do {
 			if(active) {
-				if(rb_step<false, false, ORDERED>(T, bvh, ray, stack, stride, nullptr)) {
+				if(rb_step<false, false, ORDERED>(T, bvh, ray, st, nullptr)) {
 					pb.hit[slot] = make_float4(T.best.t, T.best.u, T.best.v, __int_as_float(T.best.tri));
 					active = false;
 				}
@@ -309,8 +308,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shade(RbFrame f, RbBatch 
 template<bool MASKED, bool ORDERED>
 __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shadow(RbDeviceBvh bvh, RbPathBuffers pb, RbSceneDev sc, uint32_t did, int threshold, unsigned long long * __restrict__ stats) {
 	extern __shared__ int s_stack[];
-	int * stack				= s_stack + threadIdx.x;
-	const int stride		= blockDim.x;
+	const RbStack st		= rb_make_stack(s_stack + threadIdx.x, blockDim.x);
 	const unsigned int lane = threadIdx.x & 31u;
 	const unsigned int n	= pb.counters[rb_cnt_shadow(did)];
 	unsigned int * cursor	= pb.counters + rb_cnt_cursor_s(did);
@@ -341,7 +339,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shadow(RbDeviceBvh bvh, R
 						contrib = V3{c.x, c.y, c.z};
 						if(maxDist > 0.0f) {
 							ray = rb_make_ray(lpos, dir);
-							rb_traversal_init(T, bvh, 0.001f, maxDist);
+							rb_traversal_init(T, bvh, 0.001f, maxDist, st);
 							active = true;
 							++queries;
 						} else {
@@ -359,7 +357,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shadow(RbDeviceBvh bvh, R
 		bool more;
 		do {
 			if(active) {
-				if(rb_step<!MASKED, false, ORDERED>(T, bvh, ray, stack, stride, nullptr)) {
+				if(rb_step<!MASKED, false, ORDERED>(T, bvh, ray, st, nullptr)) {
 					bool visible = false, finished = true;
 					if(T.best.tri < 0) {
 						visible = true;
@@ -376,7 +374,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shadow(RbDeviceBvh bvh, R
 								lpos	= lpos + T.best.t * dir;
 								if(maxDist > 0.0f) {
 									ray = rb_make_ray(lpos, dir);
-									rb_traversal_init(T, bvh, 0.001f, maxDist);
+									rb_traversal_init(T, bvh, 0.001f, maxDist, st);
 									finished = false;
 									++queries;
 								} else {

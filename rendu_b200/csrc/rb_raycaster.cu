@@ -106,8 +106,8 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_closest(RbDeviceBvh bvh, 
 	rb_load_ray(org, dir, i, o, d);
 	const RbRay ray = rb_make_ray(o, d);
 	RbHitRec best;
-	if(ORDERED) rb_trace_ordered<false, false>(bvh, ray, mini, maxi, s_stack + threadIdx.x, blockDim.x, best, nullptr);
-	else rb_trace_exact<false, false>(bvh, ray, mini, maxi, s_stack + threadIdx.x, blockDim.x, best, nullptr);
+	if(ORDERED) rb_trace_ordered<false, false>(bvh, ray, mini, maxi, rb_make_stack(s_stack + threadIdx.x, blockDim.x), best, nullptr);
+	else rb_trace_exact<false, false>(bvh, ray, mini, maxi, rb_make_stack(s_stack + threadIdx.x, blockDim.x), best, nullptr);
 	rb_store_hit(out, i, bvh, best);
 }
 
@@ -121,8 +121,8 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_any(RbDeviceBvh bvh, cons
 	const RbRay ray = rb_make_ray(o, d);
 	RbHitRec best;
 	bool any;
-	if(ORDERED) any = rb_trace_ordered<true, false>(bvh, ray, mini, maxi, s_stack + threadIdx.x, blockDim.x, best, nullptr);
-	else any = rb_trace_exact<true, false>(bvh, ray, mini, maxi, s_stack + threadIdx.x, blockDim.x, best, nullptr);
+	if(ORDERED) any = rb_trace_ordered<true, false>(bvh, ray, mini, maxi, rb_make_stack(s_stack + threadIdx.x, blockDim.x), best, nullptr);
+	else any = rb_trace_exact<true, false>(bvh, ray, mini, maxi, rb_make_stack(s_stack + threadIdx.x, blockDim.x), best, nullptr);
 	out[i] = any ? 1 : 0;
 }
 
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_visible(RbDeviceBvh bvh, 
 	const float maxi   = length3(direction);
 	const RbRay ray	   = rb_make_ray(a, direction);
 	RbHitRec best;
-	const bool any = rb_trace_exact<true, false>(bvh, ray, 0.0001f, maxi, s_stack + threadIdx.x, blockDim.x, best, nullptr);
+	const bool any = rb_trace_exact<true, false>(bvh, ray, 0.0001f, maxi, rb_make_stack(s_stack + threadIdx.x, blockDim.x), best, nullptr);
 	out[i] = any ? 0 : 1;
 }
 
@@ -152,8 +152,7 @@ RB_D void rb_store_any(uint8_t * out, size_t i, const RbDeviceBvh &, const RbHit
 template<bool ANY, bool ORDERED>
 __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_persistent(RbDeviceBvh bvh, const float * __restrict__ org, const float * __restrict__ dir, float mini, float maxi, unsigned int n, void * __restrict__ out, unsigned int * __restrict__ cursor, int threshold) {
 	extern __shared__ int s_stack[];
-	int * stack			   = s_stack + threadIdx.x;
-	const int stride	   = blockDim.x;
+	const RbStack st = rb_make_stack(s_stack + threadIdx.x, blockDim.x);
 	const unsigned int lane = threadIdx.x & 31u;
 	bool active	   = false;
 	bool exhausted = false; // warp-uniform: the queue has no more rays
@@ -175,7 +174,7 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_persistent(RbDevice
 						V3 o, d;
 						rb_load_ray(org, dir, idx, o, d);
 						ray = rb_make_ray(o, d);
-						rb_traversal_init(T, bvh, mini, maxi);
+						rb_traversal_init(T, bvh, mini, maxi, st);
 						rayIdx = idx;
 						active = true;
 					}
@@ -187,7 +186,7 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_persistent(RbDevice
 		bool more;
 		do {
 			if(active) {
-				if(rb_step<ANY, false, ORDERED>(T, bvh, ray, stack, stride, nullptr)) {
+				if(rb_step<ANY, false, ORDERED>(T, bvh, ray, st, nullptr)) {
 					if(ANY) rb_store_any(static_cast<uint8_t *>(out), rayIdx, bvh, T.best);
 					else rb_store_hit(static_cast<rb_hit *>(out), rayIdx, bvh, T.best);
 					active = false;
@@ -205,8 +204,7 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_persistent(RbDevice
 template<bool ANY, bool ORDERED>
 __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_phased(RbDeviceBvh bvh, const float * __restrict__ org, const float * __restrict__ dir, float mini, float maxi, unsigned int n, void * __restrict__ out, unsigned int * __restrict__ cursor, int threshold, int leafVotes) {
 	extern __shared__ int s_stack[];
-	int * stack				= s_stack + threadIdx.x;
-	const int stride		= blockDim.x;
+	const RbStack st		= rb_make_stack(s_stack + threadIdx.x, blockDim.x);
 	const unsigned int lane = threadIdx.x & 31u;
 	bool active = false, exhausted = false;
 	unsigned int rayIdx = 0;
@@ -227,7 +225,7 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_phased(RbDeviceBvh 
 						V3 o, d;
 						rb_load_ray(org, dir, idx, o, d);
 						ray = rb_make_ray(o, d);
-						rb_traversal_init(T, bvh, mini, maxi);
+						rb_traversal_init(T, bvh, mini, maxi, st);
 						rayIdx = idx;
 						active = true;
 					}
@@ -245,7 +243,7 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_phased(RbDeviceBvh 
 			if(__popc(leafM) >= leafVotes || nodeM == 0u) {
 				if(wantsLeaf) finished = rb_phase_leaf<ANY, false>(T, bvh, ray, nullptr);
 			} else {
-				if(active && !wantsLeaf) finished = rb_phase_node<false, ORDERED>(T, bvh, ray, stack, stride, nullptr);
+				if(active && !wantsLeaf) finished = rb_phase_node<false, ORDERED>(T, bvh, ray, st, nullptr);
 			}
 			if(finished) {
 				if(ANY) rb_store_any(static_cast<uint8_t *>(out), rayIdx, bvh, T.best);
@@ -279,11 +277,11 @@ RB_D void rb_slot_finish(RbSlot & S, const RbDeviceBvh & bvh, void * out) {
 	S.live = false;
 }
 
-RB_D void rb_slot_start(RbSlot & S, const RbDeviceBvh & bvh, const float * org, const float * dir, unsigned int idx, float mini, float maxi) {
+RB_D void rb_slot_start(RbSlot & S, const RbDeviceBvh & bvh, const float * org, const float * dir, unsigned int idx, float mini, float maxi, const RbStack & st) {
 	V3 o, d;
 	rb_load_ray(org, dir, idx, o, d);
 	S.ray = rb_make_ray(o, d);
-	rb_traversal_init(S.T, bvh, mini, maxi);
+	rb_traversal_init(S.T, bvh, mini, maxi, st);
 	S.rayIdx = idx;
 	S.live	 = true;
 }
@@ -291,9 +289,8 @@ RB_D void rb_slot_start(RbSlot & S, const RbDeviceBvh & bvh, const float * org, 
 template<bool ANY, bool ORDERED>
 __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_dual(RbDeviceBvh bvh, const float * __restrict__ org, const float * __restrict__ dir, float mini, float maxi, unsigned int n, void * __restrict__ out, unsigned int * __restrict__ cursor, int refillSlots, int leafVotes) {
 	extern __shared__ int s_stack[];
-	const int stride		= 2 * blockDim.x;
-	int * stackA			= s_stack + threadIdx.x;
-	int * stackB			= s_stack + threadIdx.x + blockDim.x;
+	const RbStack stackA	= rb_make_stack(s_stack + threadIdx.x, 2 * blockDim.x);
+	const RbStack stackB	= rb_make_stack(s_stack + threadIdx.x + blockDim.x, 2 * blockDim.x);
 	const unsigned int lane = threadIdx.x & 31u;
 	const unsigned int below = (1u << lane) - 1u;
 	RbSlot A, B;
@@ -312,11 +309,11 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_dual(RbDeviceBvh bv
 				base = __shfl_sync(0xffffffffu, base, 0);
 				if(!A.live) {
 					const unsigned int idx = base + __popc(freeA & below);
-					if(idx < n) rb_slot_start(A, bvh, org, dir, idx, mini, maxi);
+					if(idx < n) rb_slot_start(A, bvh, org, dir, idx, mini, maxi, stackA);
 				}
 				if(!B.live) {
 					const unsigned int idx = base + (unsigned int)nA + __popc(freeB & below);
-					if(idx < n) rb_slot_start(B, bvh, org, dir, idx, mini, maxi);
+					if(idx < n) rb_slot_start(B, bvh, org, dir, idx, mini, maxi, stackB);
 				}
 				exhausted = (base + (unsigned int)(nA + nB)) >= n;
 			}
@@ -333,8 +330,8 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_dual(RbDeviceBvh bv
 			if(aLeaf && rb_phase_leaf<ANY, false>(A.T, bvh, A.ray, nullptr)) rb_slot_finish<ANY>(A, bvh, out);
 			if(bLeaf && rb_phase_leaf<ANY, false>(B.T, bvh, B.ray, nullptr)) rb_slot_finish<ANY>(B, bvh, out);
 		} else {
-			if(aNode && rb_phase_node<false, ORDERED>(A.T, bvh, A.ray, stackA, stride, nullptr)) rb_slot_finish<ANY>(A, bvh, out);
-			if(bNode && rb_phase_node<false, ORDERED>(B.T, bvh, B.ray, stackB, stride, nullptr)) rb_slot_finish<ANY>(B, bvh, out);
+			if(aNode && rb_phase_node<false, ORDERED>(A.T, bvh, A.ray, stackA, nullptr)) rb_slot_finish<ANY>(A, bvh, out);
+			if(bNode && rb_phase_node<false, ORDERED>(B.T, bvh, B.ray, stackB, nullptr)) rb_slot_finish<ANY>(B, bvh, out);
 		}
 	}
 }
@@ -350,8 +347,8 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_count(RbDeviceBvh bvh, co
 		rb_load_ray(org, dir, i, o, d);
 		const RbRay ray = rb_make_ray(o, d);
 		RbHitRec best;
-		if(ORDERED) rb_trace_ordered<ANY, true>(bvh, ray, mini, maxi, s_stack + threadIdx.x, blockDim.x, best, &w);
-		else rb_trace_exact<ANY, true>(bvh, ray, mini, maxi, s_stack + threadIdx.x, blockDim.x, best, &w);
+		if(ORDERED) rb_trace_ordered<ANY, true>(bvh, ray, mini, maxi, rb_make_stack(s_stack + threadIdx.x, blockDim.x), best, &w);
+		else rb_trace_exact<ANY, true>(bvh, ray, mini, maxi, rb_make_stack(s_stack + threadIdx.x, blockDim.x), best, &w);
 	}
 	// Warp-level reduction, one atomic per warp and counter.
 	unsigned int a = w.interior, b = w.tris, c = w.roots, m = w.maxStack;

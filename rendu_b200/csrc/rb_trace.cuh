@@ -111,10 +111,36 @@ RB_D float4 rb_ldg4(const float4 * p) {
 struct RbTraversal {
 	RbHitRec best;
 	float mini, maxi, maxi0;
-	int cur, sp, root;
+	int cur, root;
+	unsigned int top; // shared-memory address of the next free stack entry (== base when the stack is empty)
 };
 
-RB_D void rb_traversal_init(RbTraversal & T, const RbDeviceBvh & bvh, float mini, float maxi) {
+// The stack is addressed in the shared window directly (st.shared / ld.shared on a 32-bit address kept in a register):
+// going through a generic int* costs a generic-to-shared conversion (S2UR/ULEA/LEA) at every push and pop.
+struct RbStack {
+	unsigned int base; // address of this thread's entry 0
+	int strideBytes;   // distance between consecutive entries of one thread
+};
+RB_D RbStack rb_make_stack(int * sharedColumn, int strideEntries) {
+	RbStack s;
+	s.base		  = (unsigned int)__cvta_generic_to_shared(sharedColumn);
+	s.strideBytes = strideEntries * (int)sizeof(int);
+	return s;
+}
+RB_D void rb_push(RbTraversal & T, const RbStack & st, int v) {
+	asm volatile("st.shared.b32 [%0], %1;" ::"r"(T.top), "r"(v) : "memory");
+	T.top += st.strideBytes;
+}
+RB_D int rb_pop(RbTraversal & T, const RbStack & st) {
+	int v;
+	T.top -= st.strideBytes;
+	asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(T.top) : "memory");
+	return v;
+}
+RB_D bool rb_stack_empty(const RbTraversal & T, const RbStack & st) { return T.top == st.base; }
+RB_D unsigned int rb_stack_size(const RbTraversal & T, const RbStack & st) { return (T.top - st.base) / (unsigned int)st.strideBytes; }
+
+RB_D void rb_traversal_init(RbTraversal & T, const RbDeviceBvh & bvh, float mini, float maxi, const RbStack & st) {
 	T.best.t   = FLT_MAX;
 	T.best.u   = 0.0f;
 	T.best.v   = 0.0f;
@@ -123,18 +149,17 @@ RB_D void rb_traversal_init(RbTraversal & T, const RbDeviceBvh & bvh, float mini
 	T.maxi	   = maxi;
 	T.maxi0	   = maxi;
 	T.cur	   = RB_REF_NONE;
-	T.sp	   = 0;
+	T.top	   = st.base;
 	T.root	   = bvh.nroots;
 }
 
 // Returns true when the traversal is finished (for ANY: also as soon as a triangle is accepted).
 template<bool ANY, bool COUNT, bool REGULAR>
-RB_D bool rb_step_exact(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ray, int * stack, int stride, RbWork * work) {
+RB_D bool rb_step_exact(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ray, const RbStack & st, RbWork * work) {
 	int cur = T.cur;
 	if(cur == RB_REF_NONE) {
-		if(T.sp > 0) {
-			--T.sp;
-			cur = stack[T.sp * stride];
+		if(!rb_stack_empty(T, st)) {
+			cur = rb_pop(T, st);
 		} else {
 			// Next accepted root, last mesh first.
 			while(T.root > 0) {
@@ -162,16 +187,14 @@ RB_D bool rb_step_exact(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & 
 		const int refL = __float_as_int(n3.x), refR = __float_as_int(n3.y);
 		if(hitR) {
 			if(hitL) {
-				stack[T.sp * stride] = refL;
-				++T.sp;
-				if(COUNT) work->maxStack = max(work->maxStack, (unsigned int)T.sp);
+				rb_push(T, st, refL);
+				if(COUNT) work->maxStack = max(work->maxStack, rb_stack_size(T, st));
 			}
 			cur = refR;
 		} else if(hitL) {
 			cur = refL;
-		} else if(T.sp > 0) {
-			--T.sp;
-			cur = stack[T.sp * stride];
+		} else if(!rb_stack_empty(T, st)) {
+			cur = rb_pop(T, st);
 		} else {
 			cur = RB_REF_NONE;
 		}
@@ -232,12 +255,11 @@ RB_D bool rb_box_test_dist(const RbRay & ray, float bminx, float bminy, float bm
 }
 
 template<bool ANY, bool COUNT, bool REGULAR>
-RB_D bool rb_step_ordered(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ray, int * stack, int stride, RbWork * work) {
+RB_D bool rb_step_ordered(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ray, const RbStack & st, RbWork * work) {
 	int cur = T.cur;
 	if(cur == RB_REF_NONE) {
-		if(T.sp > 0) {
-			--T.sp;
-			cur = stack[T.sp * stride];
+		if(!rb_stack_empty(T, st)) {
+			cur = rb_pop(T, st);
 		} else {
 			while(T.root > 0) {
 				--T.root;
@@ -265,17 +287,15 @@ RB_D bool rb_step_ordered(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay 
 		if(hitL && hitR) {
 			// Visit the nearer child first; on equal entry distance keep the reference's order (right first).
 			const bool leftFirst = dL < dR;
-			stack[T.sp * stride] = leftFirst ? refR : refL;
-			++T.sp;
-			if(COUNT) work->maxStack = max(work->maxStack, (unsigned int)T.sp);
+			rb_push(T, st, leftFirst ? refR : refL);
+			if(COUNT) work->maxStack = max(work->maxStack, rb_stack_size(T, st));
 			cur = leftFirst ? refL : refR;
 		} else if(hitR) {
 			cur = refR;
 		} else if(hitL) {
 			cur = refL;
-		} else if(T.sp > 0) {
-			--T.sp;
-			cur = stack[T.sp * stride];
+		} else if(!rb_stack_empty(T, st)) {
+			cur = rb_pop(T, st);
 		} else {
 			cur = RB_REF_NONE;
 		}
@@ -319,12 +339,11 @@ RB_D bool rb_wants_leaf(const RbTraversal & T) { return T.cur < 0; }
 
 // Returns true when the traversal has finished (no node left).
 template<bool COUNT, bool ORDERED, bool REGULAR>
-RB_D bool rb_phase_node_t(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ray, int * stack, int stride, RbWork * work) {
+RB_D bool rb_phase_node_t(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ray, const RbStack & st, RbWork * work) {
 	int cur = T.cur;
 	if(cur == RB_REF_NONE) {
-		if(T.sp > 0) {
-			--T.sp;
-			cur = stack[T.sp * stride];
+		if(!rb_stack_empty(T, st)) {
+			cur = rb_pop(T, st);
 		} else {
 			while(T.root > 0) {
 				--T.root;
@@ -350,8 +369,7 @@ RB_D bool rb_phase_node_t(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay 
 			const bool hitR = rb_box_test_dist<REGULAR>(ray, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, T.mini, T.maxi, dR);
 			if(hitL && hitR) {
 				const bool leftFirst = dL < dR;
-				stack[T.sp * stride] = leftFirst ? refR : refL;
-				++T.sp;
+				rb_push(T, st, leftFirst ? refR : refL);
 				cur = leftFirst ? refL : refR;
 			} else {
 				cur = hitR ? refR : (hitL ? refL : RB_REF_NONE);
@@ -360,16 +378,13 @@ RB_D bool rb_phase_node_t(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay 
 			const bool hitL = rb_box_test_t<REGULAR>(ray, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, T.mini, T.maxi);
 			const bool hitR = rb_box_test_t<REGULAR>(ray, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, T.mini, T.maxi);
 			if(hitR) {
-				if(hitL) {
-					stack[T.sp * stride] = refL;
-					++T.sp;
-				}
+				if(hitL) rb_push(T, st, refL);
 				cur = refR;
 			} else {
 				cur = hitL ? refL : RB_REF_NONE;
 			}
 		}
-		if(COUNT) work->maxStack = max(work->maxStack, (unsigned int)T.sp);
+		if(COUNT) work->maxStack = max(work->maxStack, rb_stack_size(T, st));
 	}
 	T.cur = cur;
 	return false;
@@ -402,38 +417,38 @@ RB_D bool rb_phase_leaf(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & 
 }
 
 template<bool COUNT, bool ORDERED>
-RB_D bool rb_phase_node(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ray, int * stack, int stride, RbWork * work) {
-	if(ray.regular) return rb_phase_node_t<COUNT, ORDERED, true>(T, bvh, ray, stack, stride, work);
-	return rb_phase_node_t<COUNT, ORDERED, false>(T, bvh, ray, stack, stride, work);
+RB_D bool rb_phase_node(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ray, const RbStack & st, RbWork * work) {
+	if(ray.regular) return rb_phase_node_t<COUNT, ORDERED, true>(T, bvh, ray, st, work);
+	return rb_phase_node_t<COUNT, ORDERED, false>(T, bvh, ray, st, work);
 }
 
 // One traversal step. The NaN-faithful box test is only compiled into the copy taken by irregular rays (a direction
 // component that is zero or denormal, or a non-finite origin); every other ray runs the FMNMX form.
 template<bool ANY, bool COUNT, bool ORDERED>
-RB_D bool rb_step(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ray, int * stack, int stride, RbWork * work) {
+RB_D bool rb_step(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ray, const RbStack & st, RbWork * work) {
 	if(ray.regular) {
-		if(ORDERED) return rb_step_ordered<ANY, COUNT, true>(T, bvh, ray, stack, stride, work);
-		return rb_step_exact<ANY, COUNT, true>(T, bvh, ray, stack, stride, work);
+		if(ORDERED) return rb_step_ordered<ANY, COUNT, true>(T, bvh, ray, st, work);
+		return rb_step_exact<ANY, COUNT, true>(T, bvh, ray, st, work);
 	}
-	if(ORDERED) return rb_step_ordered<ANY, COUNT, false>(T, bvh, ray, stack, stride, work);
-	return rb_step_exact<ANY, COUNT, false>(T, bvh, ray, stack, stride, work);
+	if(ORDERED) return rb_step_ordered<ANY, COUNT, false>(T, bvh, ray, st, work);
+	return rb_step_exact<ANY, COUNT, false>(T, bvh, ray, st, work);
 }
 
 template<bool ANY, bool COUNT>
-RB_D bool rb_trace_exact(const RbDeviceBvh & bvh, const RbRay & ray, float mini, float maxi, int * stack, int stride, RbHitRec & best, RbWork * work) {
+RB_D bool rb_trace_exact(const RbDeviceBvh & bvh, const RbRay & ray, float mini, float maxi, const RbStack & st, RbHitRec & best, RbWork * work) {
 	RbTraversal T;
-	rb_traversal_init(T, bvh, mini, maxi);
-	while(!rb_step<ANY, COUNT, false>(T, bvh, ray, stack, stride, work)) {
+	rb_traversal_init(T, bvh, mini, maxi, st);
+	while(!rb_step<ANY, COUNT, false>(T, bvh, ray, st, work)) {
 	}
 	best = T.best;
 	return best.tri >= 0;
 }
 
 template<bool ANY, bool COUNT>
-RB_D bool rb_trace_ordered(const RbDeviceBvh & bvh, const RbRay & ray, float mini, float maxi, int * stack, int stride, RbHitRec & best, RbWork * work) {
+RB_D bool rb_trace_ordered(const RbDeviceBvh & bvh, const RbRay & ray, float mini, float maxi, const RbStack & st, RbHitRec & best, RbWork * work) {
 	RbTraversal T;
-	rb_traversal_init(T, bvh, mini, maxi);
-	while(!rb_step<ANY, COUNT, true>(T, bvh, ray, stack, stride, work)) {
+	rb_traversal_init(T, bvh, mini, maxi, st);
+	while(!rb_step<ANY, COUNT, true>(T, bvh, ray, st, work)) {
 	}
 	best = T.best;
 	return best.tri >= 0;
