@@ -535,17 +535,21 @@ def run_explore(args):
                 ("ci", lambda: rc.intersects_device(d_io.data_ptr(), d_id.data_ptr(), n, bufs["ci"].data_ptr(), MINI, MAXI, sh)),
                 ("ai", lambda: rc.intersectsAny_device(d_io.data_ptr(), d_id.data_ptr(), n, anys["ai"].data_ptr(), MINI, MAXI, sh))]
         res = {}
+        for _ in range(6):  # bring the clocks up before timing anything of this variant
+            for _, f in runs:
+                f()
         for key, f in runs:
-            for _ in range(2):
-                f()
+            f()
             torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(5):
+            times = []
+            for _ in range(9):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
                 f()
-            e1.record()
-            torch.cuda.synchronize()
-            res[key + "_ms"] = e0.elapsed_time(e1) / 5
+                e1.record()
+                torch.cuda.synchronize()
+                times.append(e0.elapsed_time(e1))
+            res[key + "_ms"] = float(np.median(times))
         res["total_ms"] = sum(res[k] for k in ("cc_ms", "ac_ms", "ci_ms", "ai_ms"))
         res["mrays_s"] = 4 * n / res["total_ms"] / 1e3
         snap = {k: v.clone() for k, v in list(bufs.items()) + list(anys.items())}

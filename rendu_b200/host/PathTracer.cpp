@@ -119,8 +119,18 @@ PathTracer::PathTracer(const std::shared_ptr<Scene> & scene) {
 		}
 		if(!ok(rb_scene_set_background(_deviceScene, mode, color, ids, nids, sun, lut), "background")) return;
 	}
+	// Same log lines as Raycaster::addMesh / updateHierarchy (Raycaster.cpp:48-49,56,141): scripts parse them.
+	size_t totalTriangles = 0, meshId = 0;
+	for(const auto & obj : scene->objects) {
+		Log::Info() << "[Raycaster] Mesh " << meshId++ << " added, " << obj.mesh()->indices.size() / 3 << " triangles, " << obj.mesh()->positions.size() << " vertices." << std::endl;
+		totalTriangles += obj.mesh()->indices.size() / 3;
+	}
+	Log::Info() << "[Raycaster] Building hierarchy for " << totalTriangles << " triangles... " << std::flush;
 	if(!ok(rb_scene_commit(_deviceScene, rb_build_mode(Raycaster::defaultBuildMode())), "scene commit")) return;
 	_raycaster.adopt(rb_scene_raycaster(_deviceScene));
+	uint64_t sz[5] = {0, 0, 0, 0, 0};
+	rb_raycaster_sizes(rb_scene_raycaster(_deviceScene), sz);
+	Log::Info() << "Done: " << sz[0] << " nodes created." << std::endl;
 	ok(rb_pathtracer_create(_deviceScene, &_device), "create");
 }
 
