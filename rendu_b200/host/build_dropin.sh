@@ -13,10 +13,8 @@ if [ ! -d "$REF/src/engine" ] || [ ! -d "$OBJ" ]; then
 fi
 mkdir -p "$ROOT/build/dropin"
 CXX=/usr/bin/g++
-# This directory goes FIRST so that "raycaster/Raycaster.hpp" and "PathTracer.hpp" resolve to the drop-in headers.
-mkdir -p "$ROOT/build/dropin/inc/raycaster"
-echo "#include \"$HERE/Raycaster.hpp\"" > "$ROOT/build/dropin/inc/raycaster/Raycaster.hpp"
-INC="-I $ROOT/build/dropin/inc -I $HERE -I $ROOT/include -I $ROOT/oracle/ref_harness/stub -I $REF/src/engine -I $REF/src/libs -I $REF/src/libs/glfw/include"
+# These directories go FIRST so that "raycaster/Raycaster.hpp" and "PathTracer.hpp" resolve to the drop-in headers.
+INC="-I $HERE/shadow -I $HERE -I $ROOT/include -I $ROOT/oracle/ref_harness/stub -I $REF/src/engine -I $REF/src/libs -I $REF/src/libs/glfw/include"
 for f in Raycaster PathTracer dropin_main; do
 	$CXX -std=c++11 -O2 -w $INC -c "$HERE/$f.cpp" -o "$ROOT/build/dropin/$f.o"
 done
