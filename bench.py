@@ -286,6 +286,15 @@ def run_gpu(args):
             check(L.rb_raycaster_intersect(rc._h, o_.data_ptr(), d_.data_ptr(), MINI, MAXI, n, h_hits.data_ptr()))
             check(L.rb_raycaster_intersect_any(rc._h, o_.data_ptr(), d_.data_ptr(), MINI, MAXI, n, h_any.data_ptr()))
 
+    def copy_gbs(dst, src):
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        t0_ = time.perf_counter()
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        return src.numel() * src.element_size() / (time.perf_counter() - t0_) / 1e9
+
+    link = {"h2d_gbs": copy_gbs(d_hit_c, h_hits), "d2h_gbs": copy_gbs(h_hits, d_hit_c)}
     e2e_steps = max(2, min(args.steps, 5))
     e2e_step()
     barrier()
@@ -343,7 +352,7 @@ def run_gpu(args):
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": config_dict(world), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                        "api": "rb_raycaster_intersect / rb_raycaster_intersect_any with pinned host buffers"},
+                        "api": "rb_raycaster_intersect / rb_raycaster_intersect_any with pinned host buffers", "host_link": link},
                 "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu, "per_launch": per_launch}
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -355,10 +364,10 @@ def run_gpu(args):
 PT_W, PT_H, PT_DEPTH = 1920, 1080, 8
 
 
-def pt_config(world, spp, split):
+def pt_config(world, spp, split, trace_mode="exact"):
     return {"workload": "C3/C4 path trace: 1920x1080, %d spp, depth 8, synthetic textured GGX+Lambert Cornell room (cubemap environment, emissive panel, "
                         "shadowed point light, NEE on) with the 1,002,528-triangle displaced grid as floor" % spp,
-            "width": PT_W, "height": PT_H, "spp": spp, "depth": PT_DEPTH, "split": split if world > 1 else "none",
+            "width": PT_W, "height": PT_H, "spp": spp, "depth": PT_DEPTH, "split": split if world > 1 else "none", "trace_mode": trace_mode,
             "parallelism": "replicated scene, %d rank(s), %s" % (world, "tile split, bands gathered on rank 0" if split == "tile" else "sample split, one NCCL reduce of the fp32 sums"),
             "l2": "wavefront state (4M paths x 176 B) streams through HBM every bounce; no explicit flush"}
 
@@ -395,12 +404,14 @@ def run_pathtrace(args):
     d_img = torch.zeros((PT_H, PT_W, 3), dtype=torch.float32, device=dev)
     h_img = torch.zeros((PT_H, PT_W, 3), dtype=torch.float32).pin_memory()
 
+    tmode = 1 if args.trace_mode == "ordered" else 0
+
     def opts_for(n_spp):
         if world > 1 and args.split == "tile":
-            return rpt.make_opts(seed=1, tile=rd.tile_spec(rank, world))
+            return rpt.make_opts(seed=1, tile=rd.tile_spec(rank, world), trace_mode=tmode)
         if world > 1:
-            return rpt.make_opts(seed=1, samples=rd.sample_spec(rank, world))
-        return rpt.make_opts(seed=1)
+            return rpt.make_opts(seed=1, samples=rd.sample_spec(rank, world), trace_mode=tmode)
+        return rpt.make_opts(seed=1, trace_mode=tmode)
 
     def frame(n_spp, to_host=False):
         o = opts_for(n_spp)
@@ -463,7 +474,7 @@ def run_pathtrace(args):
         img = h_img.numpy()
         line = {"metric": "1080p spp/s", "value": spp * args.steps / (ms * 1e-3), "unit": "spp/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": pt_config(world, spp, args.split), "clocks": clocks,
+                "config": pt_config(world, spp, args.split, args.trace_mode), "clocks": clocks,
                 "e2e": {"value": spp * args.steps / (e2e_ms * 1e-3), "unit": "spp/s", "h2d_bytes_per_step": 48, "d2h_bytes_per_step": PT_W * PT_H * 3 * 4},
                 "gpu_launches": int(float(t[3]) * args.steps), "mrays_s": rays_per_frame / (ms / args.steps * 1e-3) / 1e6,
                 "msamples_s": PT_W * PT_H * spp / (ms / args.steps * 1e-3) / 1e6, "rays_per_sample": rays_per_frame / (PT_W * PT_H * spp),
@@ -575,6 +586,7 @@ def main():
     ap.add_argument("--spp", type=int, default=256)
     ap.add_argument("--split", default="tile", choices=["tile", "sample"])
     ap.add_argument("--small", action="store_true", help="pathtrace: 8k-triangle floor instead of 1M (quick checks)")
+    ap.add_argument("--trace-mode", default="exact", choices=["exact", "ordered"], help="pathtrace: traversal order of the wavefront kernels")
     args = ap.parse_args()
     if args.explore:
         run_explore(args)

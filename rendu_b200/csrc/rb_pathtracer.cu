@@ -17,6 +17,9 @@
 #include <cstring>
 
 #define RB_PT_BLOCK 128
+#ifndef RB_PT_SHADE_MIN_BLOCKS
+#define RB_PT_SHADE_MIN_BLOCKS 6 // caps the shade kernel at 80 registers: it is latency bound, occupancy matters more than spills
+#endif
 
 struct RbFrame {
 	float eye[3], corner[3], dx[3], dy[3];
@@ -179,7 +182,7 @@ RB_D void rb_queue_push(uint32_t * queue, uint32_t * counter, bool want, uint32_
 	if(want) queue[base + __popc(mask & ((1u << lane) - 1u))] = value;
 }
 
-__global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shade(RbFrame f, RbBatch b, RbPathBuffers pb, RbSceneDev sc, uint32_t did, unsigned long long * __restrict__ stats) {
+__global__ void __launch_bounds__(RB_PT_BLOCK, RB_PT_SHADE_MIN_BLOCKS) rb_k_pt_shade(RbFrame f, RbBatch b, RbPathBuffers pb, RbSceneDev sc, uint32_t did, unsigned long long * __restrict__ stats) {
 	const uint32_t n		 = pb.counters[rb_cnt_queue(did)];
 	const uint32_t * queue	 = pb.queue[did & 1u];
 	uint32_t * nextQueue	 = pb.queue[(did + 1u) & 1u];
