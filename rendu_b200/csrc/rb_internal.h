@@ -40,7 +40,7 @@ struct rb_raycaster {
 	bool hostMirrorStale = false; // device tree newer than the host mirror (after LBVH build / refit)
 
 	// Device tree.
-	int device		  = 0;
+	int device		  = -1; // CUDA device holding the tree (-1: nothing uploaded yet)
 	float4 * d_nodes  = nullptr;
 	float4 * d_tris	  = nullptr;
 	float4 * d_roots  = nullptr;

@@ -374,7 +374,9 @@ size_t rb_trace_smem_bytes(const rb_raycaster * rc, int blockThreads) {
 }
 
 void rb_raycaster_free_device(rb_raycaster * rc) {
-	if(!rb_have_device()) return;
+	if(!rb_have_device() || rc->device < 0) return; // nothing was ever allocated: leave the caller's current device alone
+	int previous = 0;
+	cudaGetDevice(&previous);
 	cudaSetDevice(rc->device);
 	cudaFree(rc->d_nodes);
 	cudaFree(rc->d_tris);
@@ -395,6 +397,8 @@ void rb_raycaster_free_device(rb_raycaster * rc) {
 	rc->d_triVerts	 = nullptr;
 	rc->d_triIds	 = nullptr;
 	rc->dev		   = RbDeviceBvh{};
+	rc->device	   = -1;
+	cudaSetDevice(previous);
 }
 
 rb_status rb_raycaster_upload_flat(rb_raycaster * rc, const RbFlatBvh & flat) {
@@ -623,6 +627,7 @@ static rb_status rb_launch_trace(const rb_raycaster * rc, const float * d_origin
 	const size_t smem	= rb_trace_smem_bytes(rc, RB_TRACE_BLOCK);
 	const bool ordered	= rc->traceMode == RB_TRACE_ORDERED;
 	rb_status st;
+	RB_CUDA(cudaSetDevice(rc->device)); // the stream and the pointers must belong to the device that holds the tree
 	if(rc->persistent && rc->dual) {
 		auto kernel = ordered ? rb_k_trace_dual<ANY, true> : rb_k_trace_dual<ANY, false>;
 		const size_t smem2 = 2 * smem;
