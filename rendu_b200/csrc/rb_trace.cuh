@@ -20,8 +20,27 @@
 
 struct RbRay {
 	V3 pos, dir, inv;
+	// Packed copies for the two-wide fp32 instructions of sm_100 (FADD2 / FMUL2): pairs (x,y), (z,x), (y,z) line up with
+	// the pairs a node's float4 loads deliver (see rb_node_test).
+	unsigned long long pxy, pzx, pyz, ixy, izx, iyz;
 	bool regular; // every component of pos and inv is finite: min/max can never see a NaN
 };
+
+RB_D unsigned long long rb_pack2(float a, float b) {
+	unsigned long long r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+	return r;
+}
+RB_D void rb_unpack2(unsigned long long v, float & a, float & b) {
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+// (a - b) * c on two fp32 lanes at once; each lane rounds exactly like the scalar sub.rn / mul.rn pair (no fusion).
+RB_D unsigned long long rb_submul2(unsigned long long a, unsigned long long b, unsigned long long c) {
+	unsigned long long d, r;
+	asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+	asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(d), "l"(c));
+	return r;
+}
 
 // Ray::Ray (Intersection.cpp:3-5): dir = normalize(d), invdir = 1.0f / normalize(d).
 RB_D RbRay rb_make_ray(V3 origin, V3 direction) {
@@ -30,6 +49,8 @@ RB_D RbRay rb_make_ray(V3 origin, V3 direction) {
 	r.dir = normalize3(direction);
 	r.inv = V3{1.0f / r.dir.x, 1.0f / r.dir.y, 1.0f / r.dir.z};
 	r.regular = isfinite(r.inv.x) && isfinite(r.inv.y) && isfinite(r.inv.z) && isfinite(origin.x) && isfinite(origin.y) && isfinite(origin.z);
+	r.pxy = rb_pack2(r.pos.x, r.pos.y); r.pzx = rb_pack2(r.pos.z, r.pos.x); r.pyz = rb_pack2(r.pos.y, r.pos.z);
+	r.ixy = rb_pack2(r.inv.x, r.inv.y); r.izx = rb_pack2(r.inv.z, r.inv.x); r.iyz = rb_pack2(r.inv.y, r.inv.z);
 	return r;
 }
 
@@ -92,6 +113,9 @@ struct RbHitRec {
 struct RbWork {
 	unsigned int interior, tris, roots, maxStack;
 };
+
+template<bool REGULAR>
+RB_D void rb_node_test(const RbRay & ray, const float4 & n0, const float4 & n1, const float4 & n2, float mini, float maxi, bool & hitL, bool & hitR, float & dL, float & dR);
 
 RB_D float4 rb_ldg4(const float4 * p) {
 	return __ldg(p);
@@ -182,8 +206,9 @@ RB_D bool rb_step_exact(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & 
 		const float4 * n = bvh.nodes + 4 * (size_t)cur;
 		const float4 n0 = rb_ldg4(n), n1 = rb_ldg4(n + 1), n2 = rb_ldg4(n + 2), n3 = rb_ldg4(n + 3);
 		if(COUNT) work->interior++;
-		const bool hitL = rb_box_test_t<REGULAR>(ray, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, T.mini, T.maxi);
-		const bool hitR = rb_box_test_t<REGULAR>(ray, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, T.mini, T.maxi);
+		bool hitL, hitR;
+		float dL, dR;
+		rb_node_test<REGULAR>(ray, n0, n1, n2, T.mini, T.maxi, hitL, hitR, dL, dR);
 		const int refL = __float_as_int(n3.x), refR = __float_as_int(n3.y);
 		if(hitR) {
 			if(hitL) {
@@ -281,8 +306,8 @@ RB_D bool rb_step_ordered(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay 
 		const float4 n0 = rb_ldg4(n), n1 = rb_ldg4(n + 1), n2 = rb_ldg4(n + 2), n3 = rb_ldg4(n + 3);
 		if(COUNT) work->interior++;
 		float dL, dR;
-		const bool hitL = rb_box_test_dist<REGULAR>(ray, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, T.mini, T.maxi, dL);
-		const bool hitR = rb_box_test_dist<REGULAR>(ray, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, T.mini, T.maxi, dR);
+		bool hitL, hitR;
+		rb_node_test<REGULAR>(ray, n0, n1, n2, T.mini, T.maxi, hitL, hitR, dL, dR);
 		const int refL = __float_as_int(n3.x), refR = __float_as_int(n3.y);
 		if(hitL && hitR) {
 			// Visit the nearer child first; on equal entry distance keep the reference's order (right first).
@@ -328,6 +353,32 @@ RB_D bool rb_step_ordered(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay 
 }
 
 
+// Both children of an interior node at once (two Intersection::box tests). For regular rays the twelve subtractions and
+// twelve multiplications run as six FADD2 + six FMUL2: the node layout delivers exactly the pairs
+// (L.min.x,L.min.y) (L.min.z,L.max.x) (L.max.y,L.max.z) (R.min.x,R.min.y) (R.min.z,R.max.x) (R.max.y,R.max.z).
+// dL/dR receive max(closest, mini), the slab entry distance used by the ordered traversal.
+template<bool REGULAR>
+RB_D void rb_node_test(const RbRay & ray, const float4 & n0, const float4 & n1, const float4 & n2, float mini, float maxi, bool & hitL, bool & hitR, float & dL, float & dR) {
+	if(REGULAR) {
+		float lminx, lminy, lminz, lmaxx, lmaxy, lmaxz, rminx, rminy, rminz, rmaxx, rmaxy, rmaxz;
+		rb_unpack2(rb_submul2(rb_pack2(n0.x, n0.y), ray.pxy, ray.ixy), lminx, lminy);
+		rb_unpack2(rb_submul2(rb_pack2(n0.z, n0.w), ray.pzx, ray.izx), lminz, lmaxx);
+		rb_unpack2(rb_submul2(rb_pack2(n1.x, n1.y), ray.pyz, ray.iyz), lmaxy, lmaxz);
+		rb_unpack2(rb_submul2(rb_pack2(n1.z, n1.w), ray.pxy, ray.ixy), rminx, rminy);
+		rb_unpack2(rb_submul2(rb_pack2(n2.x, n2.y), ray.pzx, ray.izx), rminz, rmaxx);
+		rb_unpack2(rb_submul2(rb_pack2(n2.z, n2.w), ray.pyz, ray.iyz), rmaxy, rmaxz);
+		dL = fmaxf(fmaxf(fminf(lminx, lmaxx), fminf(lminy, lmaxy)), fmaxf(fminf(lminz, lmaxz), mini));
+		const float fL = fminf(fminf(fmaxf(lminx, lmaxx), fmaxf(lminy, lmaxy)), fminf(fmaxf(lminz, lmaxz), maxi));
+		dR = fmaxf(fmaxf(fminf(rminx, rmaxx), fminf(rminy, rmaxy)), fmaxf(fminf(rminz, rmaxz), mini));
+		const float fR = fminf(fminf(fmaxf(rminx, rmaxx), fmaxf(rminy, rmaxy)), fminf(fmaxf(rminz, rmaxz), maxi));
+		hitL = dL <= fL;
+		hitR = dR <= fR;
+	} else {
+		hitL = rb_box_test_dist<false>(ray, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, mini, maxi, dL);
+		hitR = rb_box_test_dist<false>(ray, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, mini, maxi, dR);
+	}
+}
+
 // ---------------------------------------------------------------------------------------------- phase-split steps
 // The same traversal cut into its two kinds of work so that a warp can decide, by vote, which kind to execute next:
 //   node phase : take the pending node if none is current (stack, else next accepted root), then — if it is an interior
@@ -365,8 +416,8 @@ RB_D bool rb_phase_node_t(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay 
 		const int refL = __float_as_int(n3.x), refR = __float_as_int(n3.y);
 		if(ORDERED) {
 			float dL, dR;
-			const bool hitL = rb_box_test_dist<REGULAR>(ray, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, T.mini, T.maxi, dL);
-			const bool hitR = rb_box_test_dist<REGULAR>(ray, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, T.mini, T.maxi, dR);
+			bool hitL, hitR;
+			rb_node_test<REGULAR>(ray, n0, n1, n2, T.mini, T.maxi, hitL, hitR, dL, dR);
 			if(hitL && hitR) {
 				const bool leftFirst = dL < dR;
 				rb_push(T, st, leftFirst ? refR : refL);
@@ -375,8 +426,9 @@ RB_D bool rb_phase_node_t(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay 
 				cur = hitR ? refR : (hitL ? refL : RB_REF_NONE);
 			}
 		} else {
-			const bool hitL = rb_box_test_t<REGULAR>(ray, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, T.mini, T.maxi);
-			const bool hitR = rb_box_test_t<REGULAR>(ray, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, T.mini, T.maxi);
+			bool hitL, hitR;
+			float dL, dR;
+			rb_node_test<REGULAR>(ray, n0, n1, n2, T.mini, T.maxi, hitL, hitR, dL, dR);
 			if(hitR) {
 				if(hitL) rb_push(T, st, refL);
 				cur = refR;
