@@ -70,9 +70,11 @@ extern "C" rb_status rb_set_device(int device) {
 #define RB_TRACE_BLOCK RB_TRACE_BLOCK_THREADS
 
 // Reads ray i from tightly packed float3 arrays.
+// Rays and hit records stream through once: they are loaded / stored with the evict-first hint (ld.global.cs /
+// st.global.cs) so that they do not push the tree, which every ray re-reads, out of the 126 MB L2.
 RB_D void rb_load_ray(const float * org, const float * dir, size_t i, V3 & o, V3 & d) {
-	o = V3{__ldg(org + 3 * i), __ldg(org + 3 * i + 1), __ldg(org + 3 * i + 2)};
-	d = V3{__ldg(dir + 3 * i), __ldg(dir + 3 * i + 1), __ldg(dir + 3 * i + 2)};
+	o = V3{__ldcs(org + 3 * i), __ldcs(org + 3 * i + 1), __ldcs(org + 3 * i + 2)};
+	d = V3{__ldcs(dir + 3 * i), __ldcs(dir + 3 * i + 1), __ldcs(dir + 3 * i + 2)};
 }
 
 // Raycaster::Hit constructors (Raycaster.cpp:6-12) written as three 16-byte stores.
@@ -91,9 +93,9 @@ RB_D void rb_store_hit(rb_hit * out, size_t i, const RbDeviceBvh & bvh, const Rb
 		c = make_uint4(0u, 0u, 0u, 0u);
 	}
 	uint4 * o = reinterpret_cast<uint4 *>(out + i);
-	o[0] = a;
-	o[1] = b;
-	o[2] = c;
+	__stcs(o, a);
+	__stcs(o + 1, b);
+	__stcs(o + 2, c);
 }
 
 // One ray per thread. The traversal stack lives in shared memory, one column per thread (bank-conflict free).
