@@ -39,18 +39,23 @@ def log(*a):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs. The process is started well before the
+    timed region (its NVML initialisation stalls kernel launches for ~100 ms) and only the samples between begin() and
+    end() are reported."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.lines, self.proc = index, [], None
+        self.index, self.lines, self.proc, self.i0, self.i1 = index, [], None, 0, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 5.0:  # wait for the first sample: initialisation is over
+                time.sleep(0.05)
         except Exception:
             self.proc = None
 
@@ -58,17 +63,26 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def begin(self):
+        self.i0 = len(self.lines)
+
+    def end(self):
+        time.sleep(0.06)
+        self.i1 = len(self.lines)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        if self.i1 is None:
+            self.end()
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        window = self.lines[self.i0:self.i1] or self.lines[-2:]
+        for ln in window:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -248,19 +262,20 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         for _, f in launches:
             f()
     barrier()
 
     # ---- timed region 1: device-resident (value)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in launches] for _ in range(args.steps)]
     l0 = rc.launch_count()
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.begin()
     e_start.record(stream)
     for s in range(args.steps):
         for k, (_, f) in enumerate(launches):
@@ -269,6 +284,7 @@ def run_gpu(args):
             ev[s][k][1].record(stream)
     e_stop.record(stream)
     barrier()
+    sampler.end()
     total_ms = e_start.elapsed_time(e_stop)
     gpu_launches = rc.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
@@ -440,19 +456,21 @@ def run_pathtrace(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        frame(16)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        frame(16)
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.begin()
     e0.record(stream)
     for _ in range(args.steps):
         frame(spp)
     e1.record(stream)
     barrier()
+    sampler.end()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     st = pt.stats()

@@ -59,6 +59,11 @@ struct rb_raycaster {
 	size_t nLeaves	   = 0;
 	int buildMode	   = RB_BUILD_REFERENCE;
 
+	// Work-queue cursors of the persistent kernels: a ring of counters, one taken per launch (no allocation on the
+	// launch path; a slot is reused only after RB_CURSOR_RING further launches).
+	unsigned int * d_cursors = nullptr;
+	mutable std::atomic<uint32_t> cursorNext{0};
+
 	int traceMode = RB_TRACE_EXACT;
 	bool persistent	   = true; // persistent threads + warp work queue (false: one ray per thread)
 	int leafVotes	   = 4;	   // > 0: phase-voting scheduler, leaf phase runs once this many lanes wait for it (0: off)
@@ -96,5 +101,6 @@ rb_status rb_lbvh_refit(rb_raycaster * rc, const float * worldPositions, size_t 
 rb_status rb_lbvh_download(const rb_raycaster * rc, rb_node * nodes, rb_tri * tris, float * verts);
 
 #define RB_TRACE_BLOCK_THREADS 128
+#define RB_CURSOR_RING 1024
 // Launch helpers used by the path tracer (rb_raycaster.cu).
 size_t rb_trace_smem_bytes(const rb_raycaster * rc, int blockThreads);

@@ -411,6 +411,7 @@ rb_status rb_lbvh_build(rb_raycaster * rc) {
 	RB_CUDA(cudaMalloc(&rc->d_triVerts, ntris * 3 * sizeof(uint32_t)));
 	RB_CUDA(cudaMalloc(&rc->d_triIds, ntris * 2 * sizeof(uint32_t)));
 	RB_CUDA(cudaMalloc(&rc->d_flags, (rc->nInterior + 1) * sizeof(unsigned int)));
+	RB_CUDA(cudaMalloc(&rc->d_cursors, RB_CURSOR_RING * sizeof(unsigned int)));
 	RB_CUDA(cudaMemsetAsync(rc->d_nodes, 0, (rc->nInterior + 1) * 64, s));
 	const unsigned int initBounds[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
 	RB_CUDA(cudaMemcpyAsync(d_bounds, initBounds, sizeof(initBounds), cudaMemcpyHostToDevice, s));

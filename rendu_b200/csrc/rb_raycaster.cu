@@ -390,6 +390,8 @@ void rb_raycaster_free_device(rb_raycaster * rc) {
 	cudaFree(rc->d_verts);
 	cudaFree(rc->d_triVerts);
 	cudaFree(rc->d_triIds);
+	cudaFree(rc->d_cursors);
+	rc->d_cursors = nullptr;
 	rc->d_nodes = rc->d_tris = rc->d_roots = nullptr;
 	rc->d_parent	 = nullptr;
 	rc->d_leafParent = nullptr;
@@ -422,6 +424,7 @@ rb_status rb_raycaster_upload_flat(rb_raycaster * rc, const RbFlatBvh & flat) {
 	RB_CUDA(cudaMalloc(&rc->d_leafCode, flat.leafCode.size() * sizeof(int) + 64));
 	RB_CUDA(cudaMalloc(&rc->d_flags, (flat.parent.size() + 1) * sizeof(unsigned int)));
 	rc->nLeaves = flat.leafCode.size();
+	RB_CUDA(cudaMalloc(&rc->d_cursors, RB_CURSOR_RING * sizeof(unsigned int)));
 	RB_CUDA(cudaMemcpy(rc->d_nodes, flat.nodes.data(), flat.nodes.size() * sizeof(float), cudaMemcpyHostToDevice));
 	RB_CUDA(cudaMemcpy(rc->d_tris, flat.tris.data(), flat.tris.size() * sizeof(float), cudaMemcpyHostToDevice));
 	RB_CUDA(cudaMemcpy(rc->d_roots, flat.roots.data(), flat.roots.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -639,20 +642,18 @@ static rb_status rb_launch_trace(const rb_raycaster * rc, const float * d_origin
 		RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, RB_TRACE_BLOCK, smem2));
 		RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, rc->device));
 		if(perSm < 1) return rb_fail(RB_ERR_CUDA, "traversal kernel does not fit on an SM (stack depth %d)", rc->dev.stackDepth);
-		unsigned int * d_cursor = nullptr;
-		RB_CUDA(cudaMallocAsync(&d_cursor, sizeof(unsigned int), s));
 		const size_t chunkMax = 0xC0000000ull;
 		for(size_t done = 0; done < nrays; done += chunkMax) {
 			const size_t n = (nrays - done < chunkMax) ? (nrays - done) : chunkMax;
 			const size_t blocksNeeded = (n + 2 * RB_TRACE_BLOCK - 1) / (2 * RB_TRACE_BLOCK);
 			const unsigned grid = unsigned(blocksNeeded < size_t(perSm) * sms ? blocksNeeded : size_t(perSm) * sms);
+			unsigned int * d_cursor = rc->d_cursors + (rc->cursorNext.fetch_add(1) % RB_CURSOR_RING);
 			RB_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned int), s));
 			void * outp = ANY ? static_cast<void *>(static_cast<uint8_t *>(d_out) + done) : static_cast<void *>(static_cast<rb_hit *>(d_out) + done);
 			kernel<<<grid, RB_TRACE_BLOCK, smem2, s>>>(rc->dev, d_origins + 3 * done, d_directions + 3 * done, mini, maxi, (unsigned int)n, outp, d_cursor, rc->dualRefill, rc->leafVotes > 0 ? rc->leafVotes : 24);
 			RB_CUDA(cudaGetLastError());
 			rc->launches++;
 		}
-		RB_CUDA(cudaFreeAsync(d_cursor, s));
 		return RB_OK;
 	}
 	if(rc->persistent && rc->leafVotes > 0) {
@@ -663,20 +664,18 @@ static rb_status rb_launch_trace(const rb_raycaster * rc, const float * d_origin
 		RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, RB_TRACE_BLOCK, smem));
 		RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, rc->device));
 		if(perSm < 1) return rb_fail(RB_ERR_CUDA, "traversal kernel does not fit on an SM (stack depth %d)", rc->dev.stackDepth);
-		unsigned int * d_cursor = nullptr;
-		RB_CUDA(cudaMallocAsync(&d_cursor, sizeof(unsigned int), s));
 		const size_t chunkMax = 0xC0000000ull;
 		for(size_t done = 0; done < nrays; done += chunkMax) {
 			const size_t n = (nrays - done < chunkMax) ? (nrays - done) : chunkMax;
 			const size_t blocksNeeded = (n + RB_TRACE_BLOCK - 1) / RB_TRACE_BLOCK;
 			const unsigned grid = unsigned(blocksNeeded < size_t(perSm) * sms ? blocksNeeded : size_t(perSm) * sms);
+			unsigned int * d_cursor = rc->d_cursors + (rc->cursorNext.fetch_add(1) % RB_CURSOR_RING);
 			RB_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned int), s));
 			void * outp = ANY ? static_cast<void *>(static_cast<uint8_t *>(d_out) + done) : static_cast<void *>(static_cast<rb_hit *>(d_out) + done);
 			kernel<<<grid, RB_TRACE_BLOCK, smem, s>>>(rc->dev, d_origins + 3 * done, d_directions + 3 * done, mini, maxi, (unsigned int)n, outp, d_cursor, rc->fetchThreshold, rc->leafVotes);
 			RB_CUDA(cudaGetLastError());
 			rc->launches++;
 		}
-		RB_CUDA(cudaFreeAsync(d_cursor, s));
 		return RB_OK;
 	}
 	if(rc->persistent) {
@@ -687,20 +686,18 @@ static rb_status rb_launch_trace(const rb_raycaster * rc, const float * d_origin
 		RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, RB_TRACE_BLOCK, smem));
 		RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, rc->device));
 		if(perSm < 1) return rb_fail(RB_ERR_CUDA, "traversal kernel does not fit on an SM (stack depth %d)", rc->dev.stackDepth);
-		unsigned int * d_cursor = nullptr;
-		RB_CUDA(cudaMallocAsync(&d_cursor, sizeof(unsigned int), s));
 		const size_t chunkMax = 0xC0000000ull; // cursor is 32 bit
 		for(size_t done = 0; done < nrays; done += chunkMax) {
 			const size_t n = (nrays - done < chunkMax) ? (nrays - done) : chunkMax;
 			const size_t blocksNeeded = (n + RB_TRACE_BLOCK - 1) / RB_TRACE_BLOCK;
 			const unsigned grid = unsigned(blocksNeeded < size_t(perSm) * sms ? blocksNeeded : size_t(perSm) * sms);
+			unsigned int * d_cursor = rc->d_cursors + (rc->cursorNext.fetch_add(1) % RB_CURSOR_RING);
 			RB_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned int), s));
 			void * outp = ANY ? static_cast<void *>(static_cast<uint8_t *>(d_out) + done) : static_cast<void *>(static_cast<rb_hit *>(d_out) + done);
 			kernel<<<grid, RB_TRACE_BLOCK, smem, s>>>(rc->dev, d_origins + 3 * done, d_directions + 3 * done, mini, maxi, (unsigned int)n, outp, d_cursor, rc->fetchThreshold);
 			RB_CUDA(cudaGetLastError());
 			rc->launches++;
 		}
-		RB_CUDA(cudaFreeAsync(d_cursor, s));
 		return RB_OK;
 	}
 	const unsigned grid = unsigned((nrays + RB_TRACE_BLOCK - 1) / RB_TRACE_BLOCK);
