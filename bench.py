@@ -521,6 +521,67 @@ def cpu_pathtrace_baseline(desc):
             "sample": "%dx%d at %d spp, depth %d (%.1f s), scaled to 1920x1080" % (w, h, s, PT_DEPTH, dt)}
 
 
+# ------------------------------------------------------------------------------------------ LBVH workload (C5)
+def run_lbvh(args):
+    """BASELINE configs[4]: 10M-triangle displaced grid (N=2236 -> 9,999,392 triangles): GPU LBVH build, refit after
+    re-displacing the vertices, then the C2-style coherent ray set; the reference's CPU updateHierarchy beside it."""
+    import torch
+    import rendu_b200 as rb
+    from rendu_b200 import workloads as wl
+    n_grid = 2236 if not args.small else 500
+    pos, idx = wl.displaced_grid(n_grid)
+    dev = torch.device("cuda", 0)
+    out = {"triangles": int(idx.size // 3)}
+    rc = rb.Raycaster()
+    rc.addMesh(pos, idx)
+    rc.updateHierarchy(rb.BUILD_LBVH)  # warm-up build (module load, allocator)
+    times = []
+    for _ in range(3):
+        rc2 = rb.Raycaster()
+        rc2.addMesh(pos, idx)
+        t0 = time.perf_counter()
+        rc2.updateHierarchy(rb.BUILD_LBVH)
+        times.append(time.perf_counter() - t0)
+        del rc2
+    out["lbvh_build_ms_incl_upload"] = 1e3 * min(times)
+    moved = pos.copy()
+    moved[:, 1] = (moved[:, 1] * np.float32(1.7)).astype(np.float32)
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        rc.refit(moved)
+        times.append(time.perf_counter() - t0)
+    out["refit_ms_incl_upload"] = 1e3 * min(times)
+    out["depth"] = rc.sizes()["depth"]
+    co, cd = wl.coherent_rays(RES)
+    n = co.shape[0]
+    d_o, d_d = torch.from_numpy(co).to(dev), torch.from_numpy(cd).to(dev)
+    d_h = torch.empty(n * 48, dtype=torch.uint8, device=dev)
+    sh = torch.cuda.current_stream().cuda_stream
+    for mode, name in ((rb.TRACE_EXACT, "exact"), (rb.TRACE_ORDERED, "ordered")):
+        rc.set_trace_mode(mode)
+        for _ in range(3):
+            rc.intersects_device(d_o.data_ptr(), d_d.data_ptr(), n, d_h.data_ptr(), MINI, MAXI, sh)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            rc.intersects_device(d_o.data_ptr(), d_d.data_ptr(), n, d_h.data_ptr(), MINI, MAXI, sh)
+        e1.record()
+        torch.cuda.synchronize()
+        out["closest_coherent_mrays_s_" + name] = n / (e0.elapsed_time(e1) / 5 * 1e-3) / 1e6
+    hits = d_h.cpu().numpy().view(rb.HIT_DTYPE)
+    out["hit_rate"] = float((hits["hit"] == 1).mean())
+    if not args.no_cpu:
+        from oracle import ref
+        if ref.available():
+            r = ref.RefRaycaster()
+            r.add_mesh(pos, idx)
+            out["reference_updateHierarchy_s"] = r.build()
+            out["reference_nodes"] = r.sizes()["nodes"]
+    print(json.dumps({"workload": "C5 LBVH build + refit + trace", **out}), flush=True)
+
+
 def run_explore(args):
     """Developer aid (not a bench line): times scheduler / mode variants of the traversal kernels on the C2 sets and
     checks on the device that every variant returns the same hit records as the first one."""
@@ -600,7 +661,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--explore", action="store_true", help="developer aid: time kernel variants, no bench line")
-    ap.add_argument("--workload", default="raycast", choices=["raycast", "pathtrace"], help="raycast = BASELINE configs[1] (default); pathtrace = configs[2]/[3]")
+    ap.add_argument("--workload", default="raycast", choices=["raycast", "pathtrace", "lbvh"], help="raycast = BASELINE configs[1] (default); pathtrace = configs[2]/[3]")
     ap.add_argument("--spp", type=int, default=256)
     ap.add_argument("--split", default="tile", choices=["tile", "sample"])
     ap.add_argument("--small", action="store_true", help="pathtrace: 8k-triangle floor instead of 1M (quick checks)")
@@ -610,6 +671,8 @@ def main():
         run_explore(args)
     elif args.workload == "pathtrace" and args.impl != "reference":
         run_pathtrace(args)
+    elif args.workload == "lbvh" and args.impl != "reference":
+        run_lbvh(args)
     elif args.impl == "reference":
         run_reference(args)
     else:
