@@ -343,8 +343,15 @@ def run_gpu(args):
         dom = int(np.argmax(per_kernel_ms))
         peak, peak_src = measured_hbm_peak()
         achieved = work[dom]["bytes"] / (per_kernel_ms[dom] * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        try:  # DRAM bytes of the same launch from the committed ncu --set full capture (not measured in this run)
+            rec = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))
+            traffic = rec[work[dom]["name"]]["dram_bytes_read"] + rec[work[dom]["name"]]["dram_bytes_write"]
+            traffic_src = rec["source"]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": "rb_k_closest<exact>" if "closest" in work[dom]["name"] else "rb_k_any<exact>", "launch": work[dom]["name"],
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": work[dom]["bytes"], "avg_launch_ms": per_kernel_ms[dom],
                     "per_ray": {"interior_nodes": work[dom]["interior"] / n, "triangle_tests": work[dom]["tris"] / n,
                                 "bytes": work[dom]["bytes"] / n},
@@ -552,6 +559,7 @@ def run_lbvh(args):
         rc.refit(moved)
         times.append(time.perf_counter() - t0)
     out["refit_ms_incl_upload"] = 1e3 * min(times)
+    out.update(rc.build_times())
     out["depth"] = rc.sizes()["depth"]
     co, cd = wl.coherent_rays(RES)
     n = co.shape[0]

@@ -137,6 +137,10 @@ RB_API rb_status rb_raycaster_download_bvh(const rb_raycaster * rc, rb_node * no
  * array (nverts must match). Device-side bottom-up refit; the tree order is kept. */
 RB_API rb_status rb_raycaster_refit(rb_raycaster * rc, const float * world_positions, size_t nverts);
 
+/* Device time (CUDA events, milliseconds) of the last hierarchy build (out[0]; 0 for RB_BUILD_REFERENCE, which builds on
+ * the host) and of the last refit (out[1]), excluding host packing and host-device copies. */
+RB_API rb_status rb_raycaster_build_times(const rb_raycaster * rc, double out[2]);
+
 RB_API rb_status rb_raycaster_set_trace_mode(rb_raycaster * rc, rb_trace_mode mode);
 
 /* Raycaster::intersects (Raycaster.cpp:144-185), batched: origins/directions are nrays*3 floats (directions need

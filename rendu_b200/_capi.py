@@ -83,6 +83,7 @@ def lib():
         "rb_raycaster_download_bvh": (C.c_int, [vp, vp, vp, vp]),
         "rb_raycaster_refit": (C.c_int, [vp, vp, sz]),
         "rb_raycaster_set_trace_mode": (C.c_int, [vp, C.c_int]),
+        "rb_raycaster_build_times": (C.c_int, [vp, vp]),
         "rb_raycaster_intersect": (C.c_int, [vp, vp, vp, f32, f32, sz, vp]),
         "rb_raycaster_intersect_any": (C.c_int, [vp, vp, vp, f32, f32, sz, vp]),
         "rb_raycaster_visible": (C.c_int, [vp, vp, vp, sz, vp]),

@@ -64,6 +64,8 @@ struct rb_raycaster {
 	unsigned int * d_cursors = nullptr;
 	mutable std::atomic<uint32_t> cursorNext{0};
 
+	double buildDeviceMs = 0.0, refitDeviceMs = 0.0;
+
 	int traceMode = RB_TRACE_EXACT;
 	bool persistent	   = true; // persistent threads + warp work queue (false: one ray per thread)
 	int leafVotes	   = 4;	   // > 0: phase-voting scheduler, leaf phase runs once this many lanes wait for it (0: off)

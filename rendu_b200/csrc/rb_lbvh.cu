@@ -416,6 +416,10 @@ rb_status rb_lbvh_build(rb_raycaster * rc) {
 	const unsigned int initBounds[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
 	RB_CUDA(cudaMemcpyAsync(d_bounds, initBounds, sizeof(initBounds), cudaMemcpyHostToDevice, s));
 	uint64_t launches = 0;
+	cudaEvent_t ev0, ev1;
+	cudaEventCreate(&ev0);
+	cudaEventCreate(&ev1);
+	cudaEventRecord(ev0, s);
 	rb_k_lbvh_bounds<<<rb_blocks(n, 256), 256, 0, s>>>(rc->d_verts, d_tvIn, n, d_bounds);
 	rb_k_lbvh_morton<<<rb_blocks(n, 256), 256, 0, s>>>(rc->d_verts, d_tvIn, n, d_bounds, d_keys, d_vals);
 	launches += 2;
@@ -448,6 +452,13 @@ rb_status rb_lbvh_build(rb_raycaster * rc) {
 		st = rb_run_fit(rc, s);
 		++launches;
 	}
+	cudaEventRecord(ev1, s);
+	cudaEventSynchronize(ev1);
+	float buildMs = 0.0f;
+	cudaEventElapsedTime(&buildMs, ev0, ev1);
+	rc->buildDeviceMs = buildMs;
+	cudaEventDestroy(ev0);
+	cudaEventDestroy(ev1);
 	cudaFree(d_tvIn);
 	cudaFree(d_idIn);
 	cudaFree(d_keys);
@@ -471,7 +482,18 @@ rb_status rb_lbvh_refit(rb_raycaster * rc, const float * worldPositions, size_t 
 	cudaStream_t s = cudaStreamPerThread;
 	RB_CUDA(cudaMemcpyAsync(rc->d_verts, worldPositions, nverts * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
 	rc->verts.assign(worldPositions, worldPositions + nverts * 3);
+	cudaEvent_t ev0, ev1;
+	cudaEventCreate(&ev0);
+	cudaEventCreate(&ev1);
+	cudaEventRecord(ev0, s);
 	rb_status st = rb_run_fit(rc, s);
+	cudaEventRecord(ev1, s);
+	cudaEventSynchronize(ev1);
+	float ms = 0.0f;
+	cudaEventElapsedTime(&ms, ev0, ev1);
+	rc->refitDeviceMs = ms;
+	cudaEventDestroy(ev0);
+	cudaEventDestroy(ev1);
 	if(st) return st;
 	rc->hostMirrorStale = true;
 	return RB_OK;

@@ -597,6 +597,13 @@ extern "C" rb_status rb_raycaster_refit(rb_raycaster * rc, const float * world_p
 	return rb_lbvh_refit(rc, world_positions, nverts);
 }
 
+extern "C" rb_status rb_raycaster_build_times(const rb_raycaster * rc, double out[2]) {
+	if(!rc || !out) return rb_fail(RB_ERR_INVALID, "rb_raycaster_build_times: null argument");
+	out[0] = rc->buildDeviceMs;
+	out[1] = rc->refitDeviceMs;
+	return RB_OK;
+}
+
 extern "C" rb_status rb_raycaster_set_trace_mode(rb_raycaster * rc, rb_trace_mode mode) {
 	if(!rc) return rb_fail(RB_ERR_INVALID, "rb_raycaster_set_trace_mode: null handle");
 	if(mode != RB_TRACE_EXACT && mode != RB_TRACE_ORDERED) return rb_fail(RB_ERR_INVALID, "unknown trace mode %d", int(mode));

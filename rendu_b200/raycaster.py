@@ -81,6 +81,11 @@ class Raycaster:
         pos = np.ascontiguousarray(world_positions, np.float32).reshape(-1, 3)
         check(lib().rb_raycaster_refit(self._h, ptr(pos), pos.shape[0]))
 
+    def build_times(self):
+        out = np.zeros(2, np.float64)
+        check(lib().rb_raycaster_build_times(self._h, ptr(out)))
+        return dict(build_device_ms=float(out[0]), refit_device_ms=float(out[1]))
+
     def set_trace_mode(self, mode):
         check(lib().rb_raycaster_set_trace_mode(self._h, int(mode)))
 
