@@ -270,6 +270,14 @@ RB_API rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_camera
 RB_API rb_status rb_pathtracer_resolve_device(rb_pathtracer * pt, const float * d_sum, uint32_t width, uint32_t height, uint32_t samples, uint32_t components, float * d_pixels, const rb_render_opts * opts, void * stream);
 RB_API rb_status rb_pathtracer_stats(const rb_pathtracer * pt, rb_render_stats * out);
 
+/* ------------------------------------------------------------------------------------------------ output stage
+ * The headless `--render` tail: tonemap `1 - exp(-c)` (src/apps/pathtracer/main.cpp:109-116, only when
+ * the target is not EXR), then Image::saveAsLDR's conversion (src/engine/resources/Image.cpp:138-152): `pow(v, 1/2.2)` on
+ * every channel but alpha, `min(255, max(0, 255*v))`, truncation to a byte, alpha forced to 255 (IGNORE_ALPHA). Fused in
+ * one kernel; the PNG encoder stays on the host. `components` is 3 or 4; `out` holds width*height*components bytes. */
+RB_API rb_status rb_output_ldr(const float * pixels, uint32_t width, uint32_t height, uint32_t components, int tonemap, int srgb, uint8_t * out);
+RB_API rb_status rb_output_ldr_device(const float * d_pixels, uint32_t width, uint32_t height, uint32_t components, int tonemap, int srgb, uint8_t * d_out, void * stream);
+
 /* ------------------------------------------------------------------------------------------------ device KATs
  * Known-answer hooks: evaluate the device versions of the reference's scalar building blocks on arrays (host
  * pointers). Used only by the parity tests; they launch real kernels and have no CPU path. */

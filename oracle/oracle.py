@@ -298,3 +298,11 @@ def mt_floats(seed, n):
     out = np.zeros(n, np.float32)
     lib().orc_mt_floats(C.c_uint(seed), C.c_size_t(n), _p(out))
     return out
+
+
+def output_ldr(image, tonemap=True, srgb=True):
+    image = np.ascontiguousarray(image, np.float32)
+    h, w, c = image.shape
+    out = np.zeros((h, w, c), np.uint8)
+    lib().orc_output_ldr(_p(image), w, h, c, 1 if tonemap else 0, 1 if srgb else 0, _p(out))
+    return out

@@ -340,3 +340,17 @@ def sky_eval(org, dirs, sun):
     out = np.zeros_like(org)
     lib().ref_sky_eval(_p(org), _p(dirs), _p(sun), C.c_size_t(org.shape[0]), _p(out))
     return out
+
+
+def output_ldr(image, tonemap=True):
+    """renderOneShot's output tail run by the reference itself: tonemap, Image::save (its PNG writer), reload."""
+    import tempfile
+    image = np.ascontiguousarray(image, np.float32)
+    h, w, c = image.shape
+    out = np.zeros((h, w, c), np.uint8)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "out.png")
+        rc = lib().ref_output_ldr(_p(image), w, h, c, 1 if tonemap else 0, path.encode(), _p(out))
+    if rc != 0:
+        raise RuntimeError("reference Image::save/load failed (%d)" % rc)
+    return out

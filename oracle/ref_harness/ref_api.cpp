@@ -575,6 +575,26 @@ double ref_scene_render(void * h, uint32_t w, uint32_t hgt, uint32_t samples, ui
 	return dt;
 }
 
+/* The tail of renderOneShot (main.cpp:106-119): optional tonemap, then Image::save(path, SRGB_LDR | IGNORE_ALPHA) — the
+ * reference's own PNG writer — and the file read back with the reference's own loader. out: width*height*components bytes. */
+int ref_output_ldr(const float * pixels, uint32_t w, uint32_t h, uint32_t components, int tonemap, const char * tmpPath, uint8_t * out) {
+	Image render(w, h, components);
+	std::memcpy(render.pixels.data(), pixels, render.pixels.size() * sizeof(float));
+	if(tonemap) {
+		System::forParallel(0, render.height, [&render](size_t y) {
+			for(uint x = 0; x < render.width; ++x) {
+				const glm::vec3 & color	   = render.rgb(int(x), int(y));
+				render.rgb(int(x), int(y)) = glm::vec3(1.0f) - glm::exp(-color * 1.f);
+			}
+		});
+	}
+	if(render.save(tmpPath, Image::Save::SRGB_LDR | Image::Save::IGNORE_ALPHA) != 0) return 1;
+	Image back;
+	if(back.load(tmpPath, components, false, true) != 0) return 2;
+	for(size_t i = 0; i < back.pixels.size(); ++i) out[i] = uint8_t(back.pixels[i] * 255.0f + 0.5f);
+	return 0;
+}
+
 uint64_t ref_ray_counter() {
 	return g_rayCount.load();
 }

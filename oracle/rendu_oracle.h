@@ -97,6 +97,9 @@ void orc_ggx_eval(const float * wo, const float * base, const float * rough, con
 void orc_ggx_sample(const float * wo, const float * base, const float * rough, const float * metal, const float * u3, size_t n, float * outWi, float * outEval); /* :54-92 */
 void orc_sky_eval(const orc_image * lut, const float * org, const float * dirs, const float * sun, size_t n, float * out3); /* MaterialSky.cpp:6-98 */
 
+/* renderOneShot's tonemap + Image::saveAsLDR's byte conversion (main.cpp:109-119, Image.cpp:138-152). */
+void orc_output_ldr(const float * pixels, uint32_t width, uint32_t height, uint32_t components, int tonemap, int srgb, uint8_t * out);
+
 /* The reference's random stream (rendu_oracle_std.cpp, libstdc++ <random>): state after Random::seed(seed) as seen by the
  * single worker thread System::forParallel spawns when one CPU is available. */
 void * orc_mt_create(unsigned int seed);

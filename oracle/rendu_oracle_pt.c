@@ -557,3 +557,20 @@ uint64_t orc_render(const orc_scene * scene, const orc_render_args * a, const or
 	free(tid);
 	return rays;
 }
+
+/* Output stage of the headless render: tonemap of renderOneShot (src/apps/pathtracer/main.cpp:109-116) followed by
+ * Image::saveAsLDR's conversion (src/engine/resources/Image.cpp:138-152) with SRGB_LDR | IGNORE_ALPHA (main.cpp:119). */
+void orc_output_ldr(const float * pixels, uint32_t width, uint32_t height, uint32_t components, int tonemap, int srgb, uint8_t * out) {
+	const size_t npx = (size_t)width * height;
+	for(size_t pid = 0; pid < npx; ++pid) {
+		for(uint32_t cid = 0; cid < components; ++cid) {
+			const size_t cur = components * pid + cid;
+			float value = pixels[cur];
+			if(tonemap && cid < 3) value = 1.0f - expf(-value * 1.f);
+			if(srgb && cid != 3) value = powf(value, 1.0f / 2.2f);
+			const float newValue = smin(255.0f, smax(0.0f, 255.0f * value));
+			out[cur] = (unsigned char)newValue;
+			if(cid == 3) out[cur] = 255;
+		}
+	}
+}

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_raygen(RbFrame f, RbBatch
 // ------------------------------------------------------------------------------------------------ closest-hit wavefront
 // `_raycaster.intersects(rayPos, rayDir)` with the reference's default bounds (PathTracer.cpp:204, Raycaster.hpp:65).
 template<bool ORDERED>
-__global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_trace(RbDeviceBvh bvh, RbPathBuffers pb, const uint32_t * __restrict__ queue, uint32_t did, int threshold, unsigned long long * __restrict__ stats) {
+__global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_trace(RbDeviceBvh bvh, RbPathBuffers pb, const uint32_t * __restrict__ queue, uint32_t did, int threshold, int leafVotes, unsigned long long * __restrict__ stats) {
 	extern __shared__ int s_stack[];
 	const RbStack st		= rb_make_stack(s_stack + threadIdx.x, blockDim.x);
 	const unsigned int lane = threadIdx.x & 31u;
@@ -156,11 +156,19 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_trace(RbDeviceBvh bvh, Rb
 		if(!__any_sync(0xffffffffu, active)) break;
 		bool more;
 		do {
-			if(active) {
-				if(rb_step<false, false, ORDERED>(T, bvh, ray, st, nullptr)) {
-					pb.hit[slot] = make_float4(T.best.t, T.best.u, T.best.v, __int_as_float(T.best.tri));
-					active = false;
-				}
+			// Phase vote (see rb_k_trace_phased): leaf phase once `leafVotes` lanes wait for it, node phase otherwise.
+			const bool wantsLeaf	 = active && rb_wants_leaf(T);
+			const unsigned int leafM = __ballot_sync(0xffffffffu, wantsLeaf);
+			const unsigned int nodeM = __ballot_sync(0xffffffffu, active && !wantsLeaf);
+			bool finished = false;
+			if(__popc(leafM) >= leafVotes || nodeM == 0u) {
+				if(wantsLeaf) finished = rb_phase_leaf<false, false>(T, bvh, ray, nullptr);
+			} else {
+				if(active && !wantsLeaf) finished = rb_phase_node<false, ORDERED>(T, bvh, ray, st, nullptr);
+			}
+			if(finished) {
+				pb.hit[slot] = make_float4(T.best.t, T.best.u, T.best.v, __int_as_float(T.best.tri));
+				active = false;
 			}
 			const int nActive = __popc(__ballot_sync(0xffffffffu, active));
 			more = exhausted ? (nActive > 0) : (nActive >= threshold);
@@ -623,7 +631,7 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 				rb_k_pt_raygen<<<gridFlat, RB_PT_BLOCK, 0, s>>>(f, b, pt->pb);
 				++launches;
 				for(uint32_t did = 0; did < depth; ++did) {
-					kTrace<<<gridTrace, RB_PT_BLOCK, smem, s>>>(rc->dev, pt->pb, pt->pb.queue[did & 1u], did, threshold, pt->d_stats);
+					kTrace<<<gridTrace, RB_PT_BLOCK, smem, s>>>(rc->dev, pt->pb, pt->pb.queue[did & 1u], did, threshold, rc->leafVotes > 0 ? rc->leafVotes : 33, pt->d_stats);
 					rb_k_pt_shade<<<gridFlat, RB_PT_BLOCK, 0, s>>>(f, b, pt->pb, sc->dev, did, pt->d_stats);
 					launches += 2;
 					if(sc->dev.nLights > 0) {

@@ -151,6 +151,16 @@ class PathTracer:
                     kernel_launches=int(s.kernel_launches), device_seconds=float(s.device_seconds))
 
 
+def output_ldr(image, tonemap=True, srgb=True):
+    """The tail of the reference's headless render (main.cpp:109-119 + Image::saveAsLDR): float image -> bytes for the PNG
+    encoder, computed on the GPU."""
+    image = np.ascontiguousarray(image, np.float32)
+    h, w, c = image.shape
+    out = np.zeros((h, w, c), np.uint8)
+    check(lib().rb_output_ldr(ptr(image), w, h, c, 1 if tonemap else 0, 1 if srgb else 0, ptr(out)))
+    return out
+
+
 def save_scene(path, description):
     """Flattened scene -> one compressed .npz (used for golden fixtures)."""
     out = {"n_objects": len(description["objects"]), "n_lights": len(description["lights"]), "n_textures": len(description["textures"])}

@@ -170,6 +170,19 @@ def pathtracer_goldens():
     print("shading_kat", ev.shape, len(lights) // 3, "lights")
 
 
+def output_goldens():
+    """renderOneShot's output tail run by the reference itself (its tonemap lines, its PNG writer, its PNG loader)."""
+    rng = np.random.RandomState(31)
+    img = (rng.uniform(0, 2.5, (40, 56, 3)) ** 2).astype(F)
+    img[0, 0] = [0.0, 1e-9, 50.0]
+    img[0, 1] = [1.0, 0.5, 0.25]
+    rgba = np.concatenate([np.clip(img, 0, 1), rng.uniform(0, 1, (40, 56, 1)).astype(F)], -1)
+    np.savez_compressed(os.path.join(OUT, "output_kat.npz"), img=img, tonemapped=ref.output_ldr(img, True), clipped=ref.output_ldr(np.clip(img, 0, 1), False),
+                        rgba=rgba, rgba_out=ref.output_ldr(rgba, True))
+    print("output_kat ok")
+
+
 if __name__ == "__main__":
     main()
     pathtracer_goldens()
+    output_goldens()

@@ -126,3 +126,17 @@ def test_synthetic_scene_builders():
     sc = orc.OracleScene(d)
     img, rays = sc.render(wl.cornell_camera(16 / 9), 32, 18, 4, 4, seed=1, threads=4)
     assert np.isfinite(img).all() and img.mean() > 0.05 and rays > 32 * 18 * 4
+
+
+def test_output_stage_bytes_match_reference_png():
+    """Tonemap + sRGB + quantisation (main.cpp:109-119, Image.cpp:138-152): the oracle's bytes equal what the reference's
+    own Image::save wrote into a PNG (golden; re-checked live when oracle/_ref is present)."""
+    g = dict(np.load(os.path.join(GOLDEN, "output_kat.npz")))
+    assert np.array_equal(orc.output_ldr(g["img"], True, True), g["tonemapped"])
+    assert np.array_equal(orc.output_ldr(np.clip(g["img"], 0, 1), False, True), g["clipped"])
+    assert np.array_equal(orc.output_ldr(g["rgba"], True, True), g["rgba_out"])
+    assert (g["rgba_out"][..., 3] == 255).all()
+    if ref.available():
+        rng = np.random.RandomState(2)
+        img = rng.uniform(0, 4, (17, 23, 3)).astype(np.float32)
+        assert np.array_equal(orc.output_ldr(img, True, True), ref.output_ldr(img, True))
