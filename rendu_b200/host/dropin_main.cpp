@@ -3,6 +3,7 @@
 //   pathtracer_b200 <resources-root> <scene> <width> <height> <samples> <depth> <out.f32>
 #include "PathTracer.hpp"
 #include "resources/ResourcesManager.hpp"
+#include "raycaster/RaycasterVisualisation.hpp"
 #include <cstdio>
 #include <cstdlib>
 
@@ -26,6 +27,14 @@ int main(int argc, char ** argv) {
 	// A few single-ray queries through the unchanged Raycaster API.
 	const Raycaster::Hit hit = tracer.raycaster().intersects(camera.position(), scene->boundingBox().getCentroid() - camera.position());
 	std::printf("center ray: hit=%d dist=%f mesh=%lu\n", int(hit.hit), hit.dist, hit.meshId);
+	// The reference's own debug view on top of the GPU raycaster: BVH levels and the nodes one ray visits.
+	{
+		RaycasterVisualisation visu(tracer.raycaster());
+		std::vector<Mesh> levels, rayLevels;
+		visu.getAllLevels(levels);
+		const Raycaster::Hit vh = visu.getRayLevels(camera.position(), scene->boundingBox().getCentroid() - camera.position(), rayLevels);
+		std::printf("bvh levels: %zu, ray levels: %zu, visualisation hit=%d dist=%f\n", levels.size(), rayLevels.size(), int(vh.hit), vh.dist);
+	}
 	FILE * f = std::fopen(argv[7], "wb");
 	if(!f) return 1;
 	std::fwrite(render.pixels.data(), sizeof(float), render.pixels.size(), f);

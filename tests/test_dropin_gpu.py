@@ -25,6 +25,12 @@ def test_reference_engine_with_gpu_classes_swapped_in(tmp_path):
     assert log.returncode == 0, log.stdout + log.stderr
     assert "[PathTracer] Rendering took" in log.stdout and "Done:" in log.stdout  # the reference's log lines survive
     assert "center ray: hit=1" in log.stdout
+    # The reference's RaycasterVisualisation (unmodified, a friend of Raycaster) runs on the mirrored hierarchy and
+    # finds the same hit as the GPU query.
+    import re
+    m = re.search(r"bvh levels: (\d+), ray levels: (\d+), visualisation hit=1 dist=([0-9.]+)", log.stdout)
+    c = re.search(r"center ray: hit=1 dist=([0-9.]+)", log.stdout)
+    assert m and int(m.group(1)) >= 3 and int(m.group(2)) >= 1 and m.group(3) == c.group(1), log.stdout[-600:]
     img = np.fromfile(out, np.float32).reshape(h, w, 3)
     # Same C ABI, same seed, same scene (flattened by the C++ wrapper instead of the test harness): identical image.
     desc = rpt.load_scene(os.path.join(GOLDEN, "scene_cornellbox.npz"))

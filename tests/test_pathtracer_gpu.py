@@ -142,10 +142,11 @@ def test_synthetic_c3_scene_small(monkeypatch):
 
 
 @pytest.mark.skipif(not ref.available(), reason="bundled scenes need oracle/_ref/resources")
-@pytest.mark.parametrize("name", ["cornellbox-textured", "cornellbox-cutout", "cornellbox-reflections", "boxes"])
+@pytest.mark.parametrize("name", ["cornellbox-textured", "cornellbox-cutout", "cornellbox-reflections", "boxes", "parameter-spheres", "gallery-materials"])
 def test_bundled_scenes_match_oracle(name):
     """Cubemap + normal maps; masked leaves (alpha pass-through in render and in the shadow walk) + spot lights;
-    atmosphere sky; 443 roots + 25 lights."""
+    atmosphere sky; 443 roots + 25 lights; roughness/metalness sweep under a cubemap with no light; 483,584 triangles
+    in 52 meshes (51 transformed instances) with a directional light (FLT_MAX shadow distance) and all material types."""
     sc = ref.RefScene(name)
     desc, cam = sc.flatten(), sc.camera(1.0)
     osc = orc.OracleScene(desc)
