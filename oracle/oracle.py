@@ -156,7 +156,7 @@ class SceneStruct(C.Structure):
 class RenderArgs(C.Structure):
     _fields_ = [("eye", C.c_float * 3), ("corner", C.c_float * 3), ("dx", C.c_float * 3), ("dy", C.c_float * 3), ("width", C.c_uint32),
                 ("height", C.c_uint32), ("samples", C.c_uint32), ("depth", C.c_uint32), ("components", C.c_uint32), ("seed", C.c_uint64),
-                ("sampleIndex", C.c_uint32), ("sampleCount", C.c_uint32)]
+                ("sampleIndex", C.c_uint32), ("sampleCount", C.c_uint32), ("window", C.c_uint32 * 4)]
 
 
 def make_light(l):
@@ -218,7 +218,7 @@ class OracleScene:
         self._keep += [objs, lights, imgs]
         self.struct = s
 
-    def render(self, camera, width, height, samples, depth, seed=0, rng="counter", threads=1, components=3, sample_split=None, image=None):
+    def render(self, camera, width, height, samples, depth, seed=0, rng="counter", threads=1, components=3, sample_split=None, image=None, window=None):
         """PathTracer::render. rng='counter': the CUDA path's generator; rng='mt': the reference's mt19937 stream as seen
         by the single forParallel worker after Random::seed(seed) (single thread). Returns (image, ray count)."""
         L = lib()
@@ -230,6 +230,7 @@ class OracleScene:
             setattr(a, k, (C.c_float * 3)(*[float(x) for x in camera[k]]))
         a.width, a.height, a.samples, a.depth, a.components, a.seed = width, height, samples, depth, components, seed
         a.sampleIndex, a.sampleCount = sample_split if sample_split else (0, 1)
+        a.window = (C.c_uint32 * 4)(*(window if window else (0, 0, 0, 0)))
         px = np.zeros((height, width, components), np.float32) if image is None else image
         if rng == "mt":
             st = C.c_void_p(L.orc_mt_create(C.c_uint(seed)))

@@ -76,6 +76,7 @@ typedef struct {
 	uint32_t width, height, samples, depth, components;
 	uint64_t seed;
 	uint32_t sampleIndex, sampleCount; /* sampleCount <= 1: all stratification cells */
+	uint32_t window[4];                /* x0, y0, x1, y1 of the pixels to render (all zero: the whole image) */
 } orc_render_args;
 /* Sequential random source (the reference's per-thread mt19937, Random.cpp:21-27,72-80). */
 typedef struct { float (*next_float)(void *); int (*next_int)(void *, int lo, int hi); } orc_rng_stream;

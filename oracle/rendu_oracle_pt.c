@@ -512,8 +512,11 @@ static v3 trace_sample(render_job * j, uint32_t x, uint32_t y, uint32_t sid) {
 static void * render_rows(void * arg) {
 	render_job * j = (render_job *)arg;
 	const orc_render_args * a = j->a;
+	const int windowed = a->window[2] > a->window[0] && a->window[3] > a->window[1];
 	for(uint32_t y = j->y0; y < j->y1; ++y) {
+		if(windowed && (y < a->window[1] || y >= a->window[3])) continue;
 		for(uint32_t x = 0; x < a->width; ++x) {
+			if(windowed && (x < a->window[0] || x >= a->window[2])) continue;
 			float * px = j->pixels + ((size_t)y * a->width + x) * a->components;
 			for(uint32_t sid = 0; sid < a->samples; ++sid) {
 				if(a->sampleCount > 1 && sid % a->sampleCount != a->sampleIndex) continue;
