@@ -243,7 +243,11 @@ typedef struct rb_render_opts {
 	uint32_t sample_index, sample_count;
 	uint32_t trace_mode; /* rb_trace_mode used for primary, bounce and shadow rays */
 	uint32_t max_paths_in_flight; /* 0 = default; bounds the wavefront buffers */
-	uint32_t _reserved[5];
+	/* Progressive rendering: with accumulate != 0 rb_pathtracer_render_device ADDS this call's samples
+	 * to d_sum instead of overwriting it, so a viewer can trace one slice of the stratification grid per frame
+	 * (sample_index = frame % sample_count) and resolve what it has so far with samples = cells traced so far. */
+	uint32_t accumulate;
+	uint32_t _reserved[4];
 } rb_render_opts;
 
 typedef struct rb_render_stats {

@@ -44,7 +44,7 @@ class Camera(C.Structure):
 class RenderOpts(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("tile_rows", C.c_uint32), ("tile_index", C.c_uint32), ("tile_count", C.c_uint32),
                 ("sample_index", C.c_uint32), ("sample_count", C.c_uint32), ("trace_mode", C.c_uint32),
-                ("max_paths_in_flight", C.c_uint32), ("_reserved", C.c_uint32 * 5)]
+                ("max_paths_in_flight", C.c_uint32), ("accumulate", C.c_uint32), ("_reserved", C.c_uint32 * 4)]
 
 
 class RenderStats(C.Structure):

@@ -593,7 +593,7 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 	const bool ordered	 = opts ? (opts->trace_mode == RB_TRACE_ORDERED) : false;
 	const int threshold = rc->fetchThreshold;
 	RB_CUDA(cudaSetDevice(rc->device));
-	RB_CUDA(cudaMemsetAsync(d_sum, 0, size_t(width) * height * 3 * sizeof(float), s));
+	if(!(opts && opts->accumulate)) RB_CUDA(cudaMemsetAsync(d_sum, 0, size_t(width) * height * 3 * sizeof(float), s));
 	RB_CUDA(cudaMemsetAsync(pt->d_stats, 0, 4 * sizeof(unsigned long long), s));
 
 	const uint32_t localSamples = (f.samples > f.sampleIndex) ? (f.samples - f.sampleIndex + f.sampleCount - 1) / f.sampleCount : 0;

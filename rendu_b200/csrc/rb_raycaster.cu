@@ -632,81 +632,51 @@ static rb_status rb_prepare_kernel(K kernel, size_t smem) {
 	return RB_OK;
 }
 
-// Launch of the traversal kernels. Two schedulers exist and are selected per handle (rb_internal.h: `persistent`):
-// one ray per thread, or persistent threads with the warp-level work queue above.
+// Launch of the traversal kernels. The scheduler is selected per handle (rb_internal.h): one ray per thread, or one of the
+// persistent work-queue kernels (plain, phase-voting [default], two rays per lane).
+// Persistent launch shared by the three work-queue kernels: grid = SMs x resident CTAs (never more CTAs than there are
+// rays for), a fresh cursor from the handle's ring, batches of < 2^32 rays per launch (the cursor is 32 bit).
+template<bool ANY, typename Kernel, typename... Tuning>
+static rb_status rb_launch_persistent(const rb_raycaster * rc, Kernel kernel, size_t smem, int raysPerThread, const float * d_origins, const float * d_directions, float mini, float maxi, size_t nrays, void * d_out, cudaStream_t s, Tuning... tuning) {
+	if(smem > 48 * 1024) RB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+	int perSm = 0, sms = 0;
+	RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, RB_TRACE_BLOCK, smem));
+	RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, rc->device));
+	if(perSm < 1) return rb_fail(RB_ERR_CUDA, "traversal kernel does not fit on an SM (stack depth %d)", rc->dev.stackDepth);
+	const size_t chunkMax = 0xC0000000ull;
+	const size_t perBlock = size_t(RB_TRACE_BLOCK) * raysPerThread;
+	for(size_t done = 0; done < nrays; done += chunkMax) {
+		const size_t n			  = (nrays - done < chunkMax) ? (nrays - done) : chunkMax;
+		const size_t blocksNeeded = (n + perBlock - 1) / perBlock;
+		const unsigned grid		  = unsigned(blocksNeeded < size_t(perSm) * sms ? blocksNeeded : size_t(perSm) * sms);
+		unsigned int * d_cursor	  = rc->d_cursors + (rc->cursorNext.fetch_add(1) % RB_CURSOR_RING);
+		RB_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned int), s));
+		void * outp = ANY ? static_cast<void *>(static_cast<uint8_t *>(d_out) + done) : static_cast<void *>(static_cast<rb_hit *>(d_out) + done);
+		kernel<<<grid, RB_TRACE_BLOCK, smem, s>>>(rc->dev, d_origins + 3 * done, d_directions + 3 * done, mini, maxi, (unsigned int)n, outp, d_cursor, tuning...);
+		RB_CUDA(cudaGetLastError());
+		rc->launches++;
+	}
+	return RB_OK;
+}
+
 template<bool ANY>
 static rb_status rb_launch_trace(const rb_raycaster * rc, const float * d_origins, const float * d_directions, float mini, float maxi, size_t nrays, void * d_out, cudaStream_t s) {
-	const size_t smem	= rb_trace_smem_bytes(rc, RB_TRACE_BLOCK);
-	const bool ordered	= rc->traceMode == RB_TRACE_ORDERED;
-	rb_status st;
+	const size_t smem  = rb_trace_smem_bytes(rc, RB_TRACE_BLOCK);
+	const bool ordered = rc->traceMode == RB_TRACE_ORDERED;
 	RB_CUDA(cudaSetDevice(rc->device)); // the stream and the pointers must belong to the device that holds the tree
 	if(rc->persistent && rc->dual) {
 		auto kernel = ordered ? rb_k_trace_dual<ANY, true> : rb_k_trace_dual<ANY, false>;
-		const size_t smem2 = 2 * smem;
-		st = rb_prepare_kernel(kernel, smem2);
-		if(st) return st;
-		int perSm = 0, sms = 0;
-		RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, RB_TRACE_BLOCK, smem2));
-		RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, rc->device));
-		if(perSm < 1) return rb_fail(RB_ERR_CUDA, "traversal kernel does not fit on an SM (stack depth %d)", rc->dev.stackDepth);
-		const size_t chunkMax = 0xC0000000ull;
-		for(size_t done = 0; done < nrays; done += chunkMax) {
-			const size_t n = (nrays - done < chunkMax) ? (nrays - done) : chunkMax;
-			const size_t blocksNeeded = (n + 2 * RB_TRACE_BLOCK - 1) / (2 * RB_TRACE_BLOCK);
-			const unsigned grid = unsigned(blocksNeeded < size_t(perSm) * sms ? blocksNeeded : size_t(perSm) * sms);
-			unsigned int * d_cursor = rc->d_cursors + (rc->cursorNext.fetch_add(1) % RB_CURSOR_RING);
-			RB_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned int), s));
-			void * outp = ANY ? static_cast<void *>(static_cast<uint8_t *>(d_out) + done) : static_cast<void *>(static_cast<rb_hit *>(d_out) + done);
-			kernel<<<grid, RB_TRACE_BLOCK, smem2, s>>>(rc->dev, d_origins + 3 * done, d_directions + 3 * done, mini, maxi, (unsigned int)n, outp, d_cursor, rc->dualRefill, rc->leafVotes > 0 ? rc->leafVotes : 24);
-			RB_CUDA(cudaGetLastError());
-			rc->launches++;
-		}
-		return RB_OK;
+		return rb_launch_persistent<ANY>(rc, kernel, 2 * smem, 2, d_origins, d_directions, mini, maxi, nrays, d_out, s, rc->dualRefill, rc->leafVotes > 0 ? rc->leafVotes : 24);
 	}
 	if(rc->persistent && rc->leafVotes > 0) {
 		auto kernel = ordered ? rb_k_trace_phased<ANY, true> : rb_k_trace_phased<ANY, false>;
-		st = rb_prepare_kernel(kernel, smem);
-		if(st) return st;
-		int perSm = 0, sms = 0;
-		RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, RB_TRACE_BLOCK, smem));
-		RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, rc->device));
-		if(perSm < 1) return rb_fail(RB_ERR_CUDA, "traversal kernel does not fit on an SM (stack depth %d)", rc->dev.stackDepth);
-		const size_t chunkMax = 0xC0000000ull;
-		for(size_t done = 0; done < nrays; done += chunkMax) {
-			const size_t n = (nrays - done < chunkMax) ? (nrays - done) : chunkMax;
-			const size_t blocksNeeded = (n + RB_TRACE_BLOCK - 1) / RB_TRACE_BLOCK;
-			const unsigned grid = unsigned(blocksNeeded < size_t(perSm) * sms ? blocksNeeded : size_t(perSm) * sms);
-			unsigned int * d_cursor = rc->d_cursors + (rc->cursorNext.fetch_add(1) % RB_CURSOR_RING);
-			RB_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned int), s));
-			void * outp = ANY ? static_cast<void *>(static_cast<uint8_t *>(d_out) + done) : static_cast<void *>(static_cast<rb_hit *>(d_out) + done);
-			kernel<<<grid, RB_TRACE_BLOCK, smem, s>>>(rc->dev, d_origins + 3 * done, d_directions + 3 * done, mini, maxi, (unsigned int)n, outp, d_cursor, rc->fetchThreshold, rc->leafVotes);
-			RB_CUDA(cudaGetLastError());
-			rc->launches++;
-		}
-		return RB_OK;
+		return rb_launch_persistent<ANY>(rc, kernel, smem, 1, d_origins, d_directions, mini, maxi, nrays, d_out, s, rc->fetchThreshold, rc->leafVotes);
 	}
 	if(rc->persistent) {
 		auto kernel = ordered ? rb_k_trace_persistent<ANY, true> : rb_k_trace_persistent<ANY, false>;
-		st = rb_prepare_kernel(kernel, smem);
-		if(st) return st;
-		int perSm = 0, sms = 0;
-		RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, RB_TRACE_BLOCK, smem));
-		RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, rc->device));
-		if(perSm < 1) return rb_fail(RB_ERR_CUDA, "traversal kernel does not fit on an SM (stack depth %d)", rc->dev.stackDepth);
-		const size_t chunkMax = 0xC0000000ull; // cursor is 32 bit
-		for(size_t done = 0; done < nrays; done += chunkMax) {
-			const size_t n = (nrays - done < chunkMax) ? (nrays - done) : chunkMax;
-			const size_t blocksNeeded = (n + RB_TRACE_BLOCK - 1) / RB_TRACE_BLOCK;
-			const unsigned grid = unsigned(blocksNeeded < size_t(perSm) * sms ? blocksNeeded : size_t(perSm) * sms);
-			unsigned int * d_cursor = rc->d_cursors + (rc->cursorNext.fetch_add(1) % RB_CURSOR_RING);
-			RB_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned int), s));
-			void * outp = ANY ? static_cast<void *>(static_cast<uint8_t *>(d_out) + done) : static_cast<void *>(static_cast<rb_hit *>(d_out) + done);
-			kernel<<<grid, RB_TRACE_BLOCK, smem, s>>>(rc->dev, d_origins + 3 * done, d_directions + 3 * done, mini, maxi, (unsigned int)n, outp, d_cursor, rc->fetchThreshold);
-			RB_CUDA(cudaGetLastError());
-			rc->launches++;
-		}
-		return RB_OK;
+		return rb_launch_persistent<ANY>(rc, kernel, smem, 1, d_origins, d_directions, mini, maxi, nrays, d_out, s, rc->fetchThreshold);
 	}
+	rb_status st;
 	const unsigned grid = unsigned((nrays + RB_TRACE_BLOCK - 1) / RB_TRACE_BLOCK);
 	if(ANY) {
 		auto kernel = ordered ? rb_k_any<true> : rb_k_any<false>;

@@ -94,7 +94,7 @@ def make_camera(eye, corner, dx, dy):
     return c
 
 
-def make_opts(seed=0, tile=None, samples=None, trace_mode=0, max_paths=0):
+def make_opts(seed=0, tile=None, samples=None, trace_mode=0, max_paths=0, accumulate=False):
     o = RenderOpts()
     o.seed = int(seed)
     if tile is not None:
@@ -103,6 +103,7 @@ def make_opts(seed=0, tile=None, samples=None, trace_mode=0, max_paths=0):
         o.sample_index, o.sample_count = [int(x) for x in samples]
     o.trace_mode = int(trace_mode)
     o.max_paths_in_flight = int(max_paths)
+    o.accumulate = 1 if accumulate else 0
     return o
 
 

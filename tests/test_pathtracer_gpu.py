@@ -214,3 +214,21 @@ def test_output_stage_on_device():
     ldr = rpt.output_ldr(img)
     want = orc.output_ldr(img, True, True)
     assert np.abs(ldr.astype(np.int32) - want.astype(np.int32)).max() <= 1 and ldr.max() > 100
+
+
+def test_progressive_accumulation_on_device():
+    """sums stay on the device; four progressive passes over disjoint slices of the stratification grid
+    add up to the one-shot render (fp32 summation order aside)."""
+    import torch
+    desc, cam, _ = golden_scene("cornellbox")
+    pt = rpt.PathTracer(rpt.Scene(desc))
+    w, h, spp = 64, 48, 16
+    d_sum = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda")
+    d_img = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda")
+    sh = torch.cuda.current_stream().cuda_stream
+    for k in range(4):
+        pt.render_device(cam, w, h, spp, 5, d_sum.data_ptr(), rpt.make_opts(seed=5, samples=(k, 4), accumulate=(k > 0)), sh)
+    pt.resolve_device(d_sum.data_ptr(), w, h, spp, 3, d_img.data_ptr(), None, sh)
+    torch.cuda.synchronize()
+    full, _ = gpu_render(desc, cam, w, h, spp, 5, seed=5)
+    np.testing.assert_allclose(d_img.cpu().numpy(), full, rtol=0, atol=2e-6)
