@@ -603,15 +603,13 @@ def run_explore(args):
     sh = torch.cuda.current_stream().cuda_stream
     to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
     d_co, d_cd = to(co), to(cd)
-    variants = [("simple", {"RB_PERSISTENT": "0", "RB_LEAF_VOTES": "0", "RB_DUAL": "0"}, rb.TRACE_EXACT)]
-    for thr in (8, 20, 28):
-        variants.append(("persistent_t%d" % thr, {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": str(thr), "RB_LEAF_VOTES": "0"}, rb.TRACE_EXACT))
-    variants.append(("phased_v4_t20", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "20", "RB_LEAF_VOTES": "4", "RB_DUAL": "0"}, rb.TRACE_EXACT))
-    for votes, refill in ((8, 16), (16, 16), (24, 16), (32, 16), (40, 16), (24, 8), (24, 24), (32, 32), (16, 4)):
-        variants.append(("dual_v%d_r%d" % (votes, refill), {"RB_PERSISTENT": "1", "RB_DUAL": "1", "RB_LEAF_VOTES": str(votes), "RB_DUAL_REFILL": str(refill)}, rb.TRACE_EXACT))
-    variants.append(("ordered_dual_v24_r16", {"RB_PERSISTENT": "1", "RB_DUAL": "1", "RB_LEAF_VOTES": "24", "RB_DUAL_REFILL": "16"}, rb.TRACE_ORDERED))
-    variants.append(("ordered_simple", {"RB_PERSISTENT": "0", "RB_LEAF_VOTES": "0", "RB_DUAL": "0"}, rb.TRACE_ORDERED))
-    variants.append(("ordered_persistent_t20", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "20", "RB_LEAF_VOTES": "0"}, rb.TRACE_ORDERED))
+    variants = [("simple", {"RB_PERSISTENT": "0", "RB_LEAF_VOTES": "0", "RB_DUAL": "0"}, rb.TRACE_EXACT),
+                ("persistent_t20", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "20", "RB_LEAF_VOTES": "0", "RB_DUAL": "0"}, rb.TRACE_EXACT)]
+    for votes, thr in ((2, 20), (4, 20), (6, 20), (8, 20), (12, 20), (16, 20), (4, 12), (4, 16), (4, 24), (4, 28), (8, 16), (8, 24), (12, 24), (12, 28)):
+        variants.append(("phased_v%d_t%d" % (votes, thr), {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": str(thr), "RB_LEAF_VOTES": str(votes), "RB_DUAL": "0"}, rb.TRACE_EXACT))
+    variants.append(("dual_v24_r16", {"RB_PERSISTENT": "1", "RB_DUAL": "1", "RB_LEAF_VOTES": "24", "RB_DUAL_REFILL": "16"}, rb.TRACE_EXACT))
+    variants.append(("ordered_phased_v4_t20", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "20", "RB_LEAF_VOTES": "4", "RB_DUAL": "0"}, rb.TRACE_ORDERED))
+    variants.append(("ordered_persistent_t20", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "20", "RB_LEAF_VOTES": "0", "RB_DUAL": "0"}, rb.TRACE_ORDERED))
     base, d_io, d_id, results = None, None, None, {}
     for name, env, mode in variants:
         os.environ.update(env)

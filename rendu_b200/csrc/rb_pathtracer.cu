@@ -615,7 +615,8 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 		st = rb_pt_grid(kTrace, smem, pt->sms, gridTrace);
 		if(st) return st;
 		const bool masked = sc->dev.anyMasked != 0;
-		auto kShadow = masked ? (ordered ? rb_k_pt_shadow<true, true> : rb_k_pt_shadow<true, false>) : (ordered ? rb_k_pt_shadow<false, true> : rb_k_pt_shadow<false, false>);
+		// Unmasked scenes use any-hit shadow rays, whose result is order independent: always near-child-first.
+		auto kShadow = masked ? (ordered ? rb_k_pt_shadow<true, true> : rb_k_pt_shadow<true, false>) : rb_k_pt_shadow<false, true>;
 		st = rb_pt_grid(kShadow, smem, pt->sms, gridShadow);
 		if(st) return st;
 

@@ -662,7 +662,10 @@ static rb_status rb_launch_persistent(const rb_raycaster * rc, Kernel kernel, si
 template<bool ANY>
 static rb_status rb_launch_trace(const rb_raycaster * rc, const float * d_origins, const float * d_directions, float mini, float maxi, size_t nrays, void * d_out, cudaStream_t s) {
 	const size_t smem  = rb_trace_smem_bytes(rc, RB_TRACE_BLOCK);
-	const bool ordered = rc->traceMode == RB_TRACE_ORDERED;
+	// An any-hit query never shrinks `maxi`, so which nodes are reachable — and therefore whether some triangle is
+	// accepted — does not depend on the visiting order: the near-child-first order is used for it unconditionally
+	// (it finds an occluder sooner), also in RB_TRACE_EXACT mode. Closest-hit queries follow the handle's mode.
+	const bool ordered = ANY || rc->traceMode == RB_TRACE_ORDERED;
 	RB_CUDA(cudaSetDevice(rc->device)); // the stream and the pointers must belong to the device that holds the tree
 	if(rc->persistent && rc->dual) {
 		auto kernel = ordered ? rb_k_trace_dual<ANY, true> : rb_k_trace_dual<ANY, false>;

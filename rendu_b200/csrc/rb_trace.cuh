@@ -442,27 +442,27 @@ RB_D bool rb_phase_node_t(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay 
 	return false;
 }
 
-// Returns true when an ANY query has found its hit.
+// One triangle of the current leaf per call: a leaf with several triangles stays "current" (with its first triangle
+// consumed) and is continued by the next leaf phase, so lanes with one triangle never wait for lanes with two, and the
+// second triangles are batched with other lanes' first ones. Returns true when an ANY query has found its hit.
 template<bool ANY, bool COUNT>
 RB_D bool rb_phase_leaf(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ray, RbWork * work) {
 	const int code	= ~T.cur;
 	const int first = code >> RB_LEAF_BITS;
-	const int count = (code & (RB_LEAF_MAX_TRIS - 1)) + 1;
-	T.cur = RB_REF_NONE;
-	for(int k = 0; k < count; ++k) {
-		const float4 * tp = bvh.tris + 3 * (size_t)(first + k);
-		const float4 t0 = rb_ldg4(tp), t1 = rb_ldg4(tp + 1), t2 = rb_ldg4(tp + 2);
-		if(COUNT) work->tris++;
-		float t, u, v;
-		if(rb_tri_test(ray, V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, T.mini, T.maxi, t, u, v)) {
-			if(ANY) {
-				T.best.t = t; T.best.u = u; T.best.v = v; T.best.tri = first + k;
-				return true;
-			}
-			if(t < T.best.t) {
-				T.best.t = t; T.best.u = u; T.best.v = v; T.best.tri = first + k;
-				T.maxi = t;
-			}
+	const int rest	= code & (RB_LEAF_MAX_TRIS - 1); // triangles left after this one
+	T.cur = rest > 0 ? ~(((first + 1) << RB_LEAF_BITS) | (rest - 1)) : RB_REF_NONE;
+	const float4 * tp = bvh.tris + 3 * (size_t)first;
+	const float4 t0 = rb_ldg4(tp), t1 = rb_ldg4(tp + 1), t2 = rb_ldg4(tp + 2);
+	if(COUNT) work->tris++;
+	float t, u, v;
+	if(rb_tri_test(ray, V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, T.mini, T.maxi, t, u, v)) {
+		if(ANY) {
+			T.best.t = t; T.best.u = u; T.best.v = v; T.best.tri = first;
+			return true;
+		}
+		if(t < T.best.t) {
+			T.best.t = t; T.best.u = u; T.best.v = v; T.best.tri = first;
+			T.maxi = t;
 		}
 	}
 	return false;
