@@ -431,10 +431,10 @@ def run_pathtrace(args):
 
     def opts_for(n_spp):
         if world > 1 and args.split == "tile":
-            return rpt.make_opts(seed=1, tile=rd.tile_spec(rank, world), trace_mode=tmode)
+            return rpt.make_opts(seed=1, tile=rd.tile_spec(rank, world), trace_mode=tmode, max_paths=args.max_paths)
         if world > 1:
-            return rpt.make_opts(seed=1, samples=rd.sample_spec(rank, world), trace_mode=tmode)
-        return rpt.make_opts(seed=1, trace_mode=tmode)
+            return rpt.make_opts(seed=1, samples=rd.sample_spec(rank, world), trace_mode=tmode, max_paths=args.max_paths)
+        return rpt.make_opts(seed=1, trace_mode=tmode, max_paths=args.max_paths)
 
     def frame(n_spp, to_host=False):
         o = opts_for(n_spp)
@@ -669,6 +669,7 @@ def main():
     ap.add_argument("--explore", action="store_true", help="developer aid: time kernel variants, no bench line")
     ap.add_argument("--workload", default="raycast", choices=["raycast", "pathtrace", "lbvh"], help="raycast = BASELINE configs[1] (default); pathtrace = configs[2]/[3]")
     ap.add_argument("--spp", type=int, default=256)
+    ap.add_argument("--max-paths", type=int, default=0, help="pathtrace: paths in flight per wavefront batch (0 = library default)")
     ap.add_argument("--split", default="tile", choices=["tile", "sample"])
     ap.add_argument("--small", action="store_true", help="pathtrace: 8k-triangle floor instead of 1M (quick checks)")
     ap.add_argument("--trace-mode", default="exact", choices=["exact", "ordered"], help="pathtrace: traversal order of the wavefront kernels")

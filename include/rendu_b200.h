@@ -242,7 +242,7 @@ typedef struct rb_render_opts {
 	 * still normalised by the full `samples`, so per-GPU images add up to the full estimate. */
 	uint32_t sample_index, sample_count;
 	uint32_t trace_mode; /* rb_trace_mode used for primary, bounce and shadow rays */
-	uint32_t max_paths_in_flight; /* 0 = default; bounds the wavefront buffers */
+	uint32_t max_paths_in_flight; /* paths per wavefront batch; 0 = default (16 Mi; two batches are in flight: 176 B x 2 x 16 Mi = 5.9 GB) */
 	/* Progressive rendering: with accumulate != 0 rb_pathtracer_render_device ADDS this call's samples
 	 * to d_sum instead of overwriting it, so a viewer can trace one slice of the stratification grid per frame
 	 * (sample_index = frame % sample_count) and resolve what it has so far with samples = cells traced so far. */

@@ -459,48 +459,64 @@ __global__ void rb_k_pt_resolve(RbFrame f, const float * __restrict__ sum, uint3
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+// Wavefront lanes: consecutive batches alternate between buffer sets on their own streams, so that the drain of one
+// batch's persistent kernels (a few long rays keep a handful of warps busy) is filled by the other batch's kernels.
+#define RB_PT_LANES 4
+#define RB_PT_MAX_DEPTH 64
+
 struct rb_pathtracer {
 	rb_scene * scene = nullptr;
-	RbPathBuffers pb = {};
-	size_t capacity	 = 0;
+	RbPathBuffers pb[RB_PT_LANES] = {};
+	size_t capacity[RB_PT_LANES]  = {};
+	cudaStream_t lane[RB_PT_LANES] = {};
+	cudaEvent_t fork = nullptr, join[RB_PT_LANES] = {};
+	int lanes = 2;
 	unsigned long long * d_stats = nullptr;
 	rb_render_stats stats = {};
 	int sms = 0;
 };
 
 static void rb_pt_free(rb_pathtracer * pt) {
-	cudaFree(pt->pb.rayO);
-	cudaFree(pt->pb.rayD);
-	cudaFree(pt->pb.atten);
-	cudaFree(pt->pb.color);
-	cudaFree(pt->pb.hit);
-	cudaFree(pt->pb.queue[0]);
-	cudaFree(pt->pb.queue[1]);
-	cudaFree(pt->pb.shO);
-	cudaFree(pt->pb.shD);
-	cudaFree(pt->pb.shC);
-	cudaFree(pt->pb.counters);
-	pt->pb		 = RbPathBuffers{};
-	pt->capacity = 0;
+	for(int l = 0; l < RB_PT_LANES; ++l) {
+		RbPathBuffers & pb = pt->pb[l];
+		cudaFree(pb.rayO);
+		cudaFree(pb.rayD);
+		cudaFree(pb.atten);
+		cudaFree(pb.color);
+		cudaFree(pb.hit);
+		cudaFree(pb.queue[0]);
+		cudaFree(pb.queue[1]);
+		cudaFree(pb.shO);
+		cudaFree(pb.shD);
+		cudaFree(pb.shC);
+		cudaFree(pb.counters);
+		pb				= RbPathBuffers{};
+		pt->capacity[l] = 0;
+	}
 }
 
-#define RB_PT_MAX_DEPTH 64
-
-static rb_status rb_pt_reserve(rb_pathtracer * pt, size_t paths) {
-	if(paths <= pt->capacity) return RB_OK;
-	rb_pt_free(pt);
-	RB_CUDA(cudaMalloc(&pt->pb.rayO, paths * sizeof(float4)));
-	RB_CUDA(cudaMalloc(&pt->pb.rayD, paths * sizeof(float4)));
-	RB_CUDA(cudaMalloc(&pt->pb.atten, paths * sizeof(float4)));
-	RB_CUDA(cudaMalloc(&pt->pb.color, paths * sizeof(float4)));
-	RB_CUDA(cudaMalloc(&pt->pb.hit, paths * sizeof(float4)));
-	RB_CUDA(cudaMalloc(&pt->pb.queue[0], paths * sizeof(uint32_t)));
-	RB_CUDA(cudaMalloc(&pt->pb.queue[1], paths * sizeof(uint32_t)));
-	RB_CUDA(cudaMalloc(&pt->pb.shO, paths * sizeof(float4)));
-	RB_CUDA(cudaMalloc(&pt->pb.shD, paths * sizeof(float4)));
-	RB_CUDA(cudaMalloc(&pt->pb.shC, paths * sizeof(float4)));
-	RB_CUDA(cudaMalloc(&pt->pb.counters, 4 * (RB_PT_MAX_DEPTH + 1) * sizeof(uint32_t)));
-	pt->capacity = paths;
+static rb_status rb_pt_reserve(rb_pathtracer * pt, int l, size_t paths) {
+	if(paths <= pt->capacity[l]) return RB_OK;
+	RbPathBuffers & pb = pt->pb[l];
+	if(pt->capacity[l]) {
+		RB_CUDA(cudaDeviceSynchronize());
+		cudaFree(pb.rayO); cudaFree(pb.rayD); cudaFree(pb.atten); cudaFree(pb.color); cudaFree(pb.hit);
+		cudaFree(pb.queue[0]); cudaFree(pb.queue[1]); cudaFree(pb.shO); cudaFree(pb.shD); cudaFree(pb.shC); cudaFree(pb.counters);
+		pb = RbPathBuffers{};
+		pt->capacity[l] = 0;
+	}
+	RB_CUDA(cudaMalloc(&pb.rayO, paths * sizeof(float4)));
+	RB_CUDA(cudaMalloc(&pb.rayD, paths * sizeof(float4)));
+	RB_CUDA(cudaMalloc(&pb.atten, paths * sizeof(float4)));
+	RB_CUDA(cudaMalloc(&pb.color, paths * sizeof(float4)));
+	RB_CUDA(cudaMalloc(&pb.hit, paths * sizeof(float4)));
+	RB_CUDA(cudaMalloc(&pb.queue[0], paths * sizeof(uint32_t)));
+	RB_CUDA(cudaMalloc(&pb.queue[1], paths * sizeof(uint32_t)));
+	RB_CUDA(cudaMalloc(&pb.shO, paths * sizeof(float4)));
+	RB_CUDA(cudaMalloc(&pb.shD, paths * sizeof(float4)));
+	RB_CUDA(cudaMalloc(&pb.shC, paths * sizeof(float4)));
+	RB_CUDA(cudaMalloc(&pb.counters, 4 * (RB_PT_MAX_DEPTH + 1) * sizeof(uint32_t)));
+	pt->capacity[l] = paths;
 	return RB_OK;
 }
 
@@ -515,6 +531,16 @@ extern "C" rb_status rb_pathtracer_create(rb_scene * scene, rb_pathtracer ** out
 		delete pt;
 		return rb_fail(RB_ERR_CUDA, "rb_pathtracer_create: cudaMalloc failed");
 	}
+	bool ok = cudaEventCreateWithFlags(&pt->fork, cudaEventDisableTiming) == cudaSuccess;
+	for(int l = 0; l < RB_PT_LANES; ++l) {
+		ok = ok && cudaStreamCreateWithFlags(&pt->lane[l], cudaStreamNonBlocking) == cudaSuccess;
+		ok = ok && cudaEventCreateWithFlags(&pt->join[l], cudaEventDisableTiming) == cudaSuccess;
+	}
+	if(!ok) {
+		rb_pathtracer_destroy(pt);
+		return rb_fail(RB_ERR_CUDA, "rb_pathtracer_create: stream setup failed");
+	}
+	if(const char * e = std::getenv("RB_PT_LANES")) pt->lanes = std::min(std::max(std::atoi(e), 1), RB_PT_LANES);
 	*out = pt;
 	return RB_OK;
 }
@@ -524,6 +550,11 @@ extern "C" void rb_pathtracer_destroy(rb_pathtracer * pt) {
 	if(rb_have_device()) {
 		rb_pt_free(pt);
 		cudaFree(pt->d_stats);
+		if(pt->fork) cudaEventDestroy(pt->fork);
+		for(int l = 0; l < RB_PT_LANES; ++l) {
+			if(pt->join[l]) cudaEventDestroy(pt->join[l]);
+			if(pt->lane[l]) cudaStreamDestroy(pt->lane[l]);
+		}
 	}
 	delete pt;
 }
@@ -600,14 +631,29 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 	const uint64_t localPixels	= uint64_t(f.localRows) * width;
 	uint64_t launches = 0;
 	if(localSamples && localPixels && depth) {
-		size_t maxPaths = (opts && opts->max_paths_in_flight) ? opts->max_paths_in_flight : (size_t(1) << 22);
+		size_t maxPaths = (opts && opts->max_paths_in_flight) ? opts->max_paths_in_flight : (size_t(1) << 24);
 		if(maxPaths < 1024) maxPaths = 1024;
 		const uint32_t schunk	  = uint32_t(localSamples < maxPaths ? localSamples : maxPaths);
 		uint64_t pixelsPerBatch = maxPaths / schunk;
 		if(pixelsPerBatch < 1) pixelsPerBatch = 1;
 		if(pixelsPerBatch > localPixels) pixelsPerBatch = localPixels;
-		st = rb_pt_reserve(pt, size_t(pixelsPerBatch) * schunk);
-		if(st) return st;
+		// One sample chunk per pixel (the usual case): batches touch disjoint pixels and may run on the two lanes. Frames
+		// worth splitting are cut into at least two batches.
+		const bool oneChunk = schunk == localSamples;
+		int lanes = oneChunk ? pt->lanes : 1;
+		if(lanes > 1 && pixelsPerBatch * lanes > localPixels) {
+			// fewer batches than lanes: cut the frame into one batch per lane when it is worth it
+			if(localPixels * schunk >= (uint64_t(1) << 20)) pixelsPerBatch = (localPixels + lanes - 1) / lanes;
+			else lanes = 1;
+		}
+		// Frames that fill the lanes reserve the full batch size, so that a later frame at another sample count does not
+		// have to reallocate.
+		const size_t needed	 = size_t(pixelsPerBatch) * schunk;
+		const size_t reserve = (localPixels * uint64_t(schunk) >= uint64_t(maxPaths)) ? std::max(needed, maxPaths) : needed;
+		for(int l = 0; l < lanes; ++l) {
+			st = rb_pt_reserve(pt, l, reserve);
+			if(st) return st;
+		}
 
 		const size_t smem = rb_trace_smem_bytes(rc, RB_PT_BLOCK);
 		unsigned gridTrace = 0, gridShadow = 0, gridFlat = unsigned(pt->sms * 8);
@@ -619,30 +665,45 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 		auto kShadow = masked ? (ordered ? rb_k_pt_shadow<true, true> : rb_k_pt_shadow<true, false>) : rb_k_pt_shadow<false, true>;
 		st = rb_pt_grid(kShadow, smem, pt->sms, gridShadow);
 		if(st) return st;
+		const int votes = rc->leafVotes > 0 ? rc->leafVotes : 33;
 
+		if(lanes > 1) {
+			RB_CUDA(cudaEventRecord(pt->fork, s));
+			for(int l = 0; l < lanes; ++l) RB_CUDA(cudaStreamWaitEvent(pt->lane[l], pt->fork, 0));
+		}
+		uint64_t batch = 0;
 		for(uint32_t sample0 = 0; sample0 < localSamples; sample0 += schunk) {
 			const uint32_t sc_n = (localSamples - sample0 < schunk) ? (localSamples - sample0) : schunk;
-			for(uint64_t pixel0 = 0; pixel0 < localPixels; pixel0 += pixelsPerBatch) {
+			for(uint64_t pixel0 = 0; pixel0 < localPixels; pixel0 += pixelsPerBatch, ++batch) {
 				RbBatch b;
 				b.pixel0  = uint32_t(pixel0);
 				b.npixels = uint32_t((localPixels - pixel0 < pixelsPerBatch) ? (localPixels - pixel0) : pixelsPerBatch);
 				b.sample0 = sample0;
 				b.schunk  = sc_n;
-				RB_CUDA(cudaMemsetAsync(pt->pb.counters, 0, 4 * (RB_PT_MAX_DEPTH + 1) * sizeof(uint32_t), s));
-				rb_k_pt_raygen<<<gridFlat, RB_PT_BLOCK, 0, s>>>(f, b, pt->pb);
+				const int l				 = lanes > 1 ? int(batch % lanes) : 0;
+				const cudaStream_t ls	 = lanes > 1 ? pt->lane[l] : s;
+				const RbPathBuffers & pb = pt->pb[l];
+				RB_CUDA(cudaMemsetAsync(pb.counters, 0, 4 * (RB_PT_MAX_DEPTH + 1) * sizeof(uint32_t), ls));
+				rb_k_pt_raygen<<<gridFlat, RB_PT_BLOCK, 0, ls>>>(f, b, pb);
 				++launches;
 				for(uint32_t did = 0; did < depth; ++did) {
-					kTrace<<<gridTrace, RB_PT_BLOCK, smem, s>>>(rc->dev, pt->pb, pt->pb.queue[did & 1u], did, threshold, rc->leafVotes > 0 ? rc->leafVotes : 33, pt->d_stats);
-					rb_k_pt_shade<<<gridFlat, RB_PT_BLOCK, 0, s>>>(f, b, pt->pb, sc->dev, did, pt->d_stats);
+					kTrace<<<gridTrace, RB_PT_BLOCK, smem, ls>>>(rc->dev, pb, pb.queue[did & 1u], did, threshold, votes, pt->d_stats);
+					rb_k_pt_shade<<<gridFlat, RB_PT_BLOCK, 0, ls>>>(f, b, pb, sc->dev, did, pt->d_stats);
 					launches += 2;
 					if(sc->dev.nLights > 0) {
-						kShadow<<<gridShadow, RB_PT_BLOCK, smem, s>>>(rc->dev, pt->pb, sc->dev, did, threshold, pt->d_stats);
+						kShadow<<<gridShadow, RB_PT_BLOCK, smem, ls>>>(rc->dev, pb, sc->dev, did, threshold, pt->d_stats);
 						++launches;
 					}
 				}
-				rb_k_pt_accumulate<<<gridFlat, RB_PT_BLOCK, 0, s>>>(f, b, pt->pb, d_sum);
+				rb_k_pt_accumulate<<<gridFlat, RB_PT_BLOCK, 0, ls>>>(f, b, pb, d_sum);
 				++launches;
 				RB_CUDA(cudaGetLastError());
+			}
+		}
+		if(lanes > 1) {
+			for(int l = 0; l < lanes; ++l) {
+				RB_CUDA(cudaEventRecord(pt->join[l], pt->lane[l]));
+				RB_CUDA(cudaStreamWaitEvent(s, pt->join[l], 0));
 			}
 		}
 	}
