@@ -281,6 +281,13 @@ RB_API rb_status rb_pathtracer_stats(const rb_pathtracer * pt, rb_render_stats *
  * one kernel; the PNG encoder stays on the host. `components` is 3 or 4; `out` holds width*height*components bytes. */
 RB_API rb_status rb_output_ldr(const float * pixels, uint32_t width, uint32_t height, uint32_t components, int tonemap, int srgb, uint8_t * out);
 RB_API rb_status rb_output_ldr_device(const float * d_pixels, uint32_t width, uint32_t height, uint32_t components, int tonemap, int srgb, uint8_t * d_out, void * stream);
+/* The .exr branch (main.cpp:108,119 -> Image::saveAsHDR, src/engine/resources/Image.cpp:160-289): the layer split
+ * and the writer's float -> half conversion (src/libs/tinyexr/tinyexr.h:971-1008) in one pass. planes receives
+ * `components` layers of width*height halves in the file's channel order: B,G,R for 3 components, A,B,G,R for 4
+ * (A = 1.0 when ignore_alpha, as main.cpp:119 asks); flip reverses the rows (Image::Save::FLIP). The encoder is then
+ * given HALF input layers. components must be 3 or 4. */
+RB_API rb_status rb_output_hdr(const float * pixels, uint32_t width, uint32_t height, uint32_t components, int ignore_alpha, int flip, uint16_t * planes);
+RB_API rb_status rb_output_hdr_device(const float * d_pixels, uint32_t width, uint32_t height, uint32_t components, int ignore_alpha, int flip, uint16_t * d_planes, void * stream);
 
 /* ------------------------------------------------------------------------------------------------ device KATs
  * Known-answer hooks: evaluate the device versions of the reference's scalar building blocks on arrays (host

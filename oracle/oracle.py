@@ -307,3 +307,28 @@ def output_ldr(image, tonemap=True, srgb=True):
     out = np.zeros((h, w, c), np.uint8)
     lib().orc_output_ldr(_p(image), w, h, c, 1 if tonemap else 0, 1 if srgb else 0, _p(out))
     return out
+
+
+def output_hdr(image, ignore_alpha=True, flip=False):
+    """Planar half layers in EXR channel order ((A)BGR), as uint16 of shape (channels, H, W)."""
+    image = np.ascontiguousarray(image, np.float32)
+    h, w, c = image.shape
+    ch = 3 if c == 2 else c
+    out = np.zeros((ch, h, w), np.uint16)
+    lib().orc_output_hdr(_p(image), w, h, c, 1 if ignore_alpha else 0, 1 if flip else 0, _p(out))
+    return out
+
+
+def half_planes_to_image(planes, components):
+    """Inverse view of output_hdr for the tests: planes (channels, H, W) -> float32 (H, W, components), decoded with the
+    writer's own half -> float rule."""
+    L = lib()
+    L.orc_half_to_float.restype = C.c_float
+    L.orc_half_to_float.argtypes = [C.c_uint16]
+    lut = np.array([L.orc_half_to_float(i) for i in range(65536)], np.float32)
+    ch, h, w = planes.shape
+    out = np.zeros((h, w, components), np.float32)
+    for j in range(components):
+        plane = 0 if ch == 1 else ch - 1 - j
+        out[..., j] = lut[planes[plane]]
+    return out

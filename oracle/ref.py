@@ -354,3 +354,18 @@ def output_ldr(image, tonemap=True):
     if rc != 0:
         raise RuntimeError("reference Image::save/load failed (%d)" % rc)
     return out
+
+
+def output_hdr(image):
+    """The .exr branch of renderOneShot run by the reference itself: Image::save -> saveAsHDR (half channels), reload
+    with its own EXR loader. Returns the stored half values as float32, interleaved like the input."""
+    import tempfile
+    image = np.ascontiguousarray(image, np.float32)
+    h, w, c = image.shape
+    out = np.zeros((h, w, c), np.float32)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "out.exr")
+        rc = lib().ref_output_hdr(_p(image), w, h, c, path.encode(), _p(out))
+    if rc != 0:
+        raise RuntimeError("reference Image::save/load (EXR) failed (%d)" % rc)
+    return out

@@ -595,6 +595,20 @@ int ref_output_ldr(const float * pixels, uint32_t w, uint32_t h, uint32_t compon
 	return 0;
 }
 
+/* The .exr branch of renderOneShot (main.cpp:108,119: no tonemap, Image::save -> saveAsHDR, Image.cpp:160-289): the
+ * reference's own EXR writer (half channels) and the file read back with its own loader (half -> float, Image.cpp:335+).
+ * out: width*height*components floats holding the stored half values. */
+int ref_output_hdr(const float * pixels, uint32_t w, uint32_t h, uint32_t components, const char * tmpPath, float * out) {
+	Image render(w, h, components);
+	std::memcpy(render.pixels.data(), pixels, render.pixels.size() * sizeof(float));
+	if(render.save(tmpPath, Image::Save::SRGB_LDR | Image::Save::IGNORE_ALPHA) != 0) return 1;
+	Image back;
+	if(back.load(tmpPath, components, false, true) != 0) return 2;
+	if(back.pixels.size() != render.pixels.size()) return 3;
+	std::memcpy(out, back.pixels.data(), back.pixels.size() * sizeof(float));
+	return 0;
+}
+
 uint64_t ref_ray_counter() {
 	return g_rayCount.load();
 }

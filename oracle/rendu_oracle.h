@@ -99,6 +99,9 @@ void orc_ggx_sample(const float * wo, const float * base, const float * rough, c
 void orc_sky_eval(const orc_image * lut, const float * org, const float * dirs, const float * sun, size_t n, float * out3); /* MaterialSky.cpp:6-98 */
 
 /* renderOneShot's tonemap + Image::saveAsLDR's byte conversion (main.cpp:109-119, Image.cpp:138-152). */
+uint16_t orc_float_to_half(float value);
+float orc_half_to_float(uint16_t h);
+void orc_output_hdr(const float * pixels, uint32_t width, uint32_t height, uint32_t components, int ignore_alpha, int flip, uint16_t * planes);
 void orc_output_ldr(const float * pixels, uint32_t width, uint32_t height, uint32_t components, int tonemap, int srgb, uint8_t * out);
 
 /* The reference's random stream (rendu_oracle_std.cpp, libstdc++ <random>): state after Random::seed(seed) as seen by the

@@ -577,3 +577,73 @@ void orc_output_ldr(const float * pixels, uint32_t width, uint32_t height, uint3
 		}
 	}
 }
+
+/* float -> half exactly as the EXR writer the reference links does it (src/libs/tinyexr/tinyexr.h:971-1008,
+ * float_to_half_full): zero/denormal floats flush to signed zero, Inf/NaN keep their class (NaN -> 0x200 payload),
+ * overflow saturates to infinity, and rounding adds one when the first dropped mantissa bit is set (round half up, not
+ * round-to-nearest-even); the increment may carry into the exponent. */
+uint16_t orc_float_to_half(float value) {
+	uint32_t bits;
+	memcpy(&bits, &value, sizeof(bits));
+	const uint32_t sign = bits >> 31, exponent = (bits >> 23) & 0xffu, mantissa = bits & 0x7fffffu;
+	uint32_t h = 0;
+	if(exponent == 0) {
+		h = 0;
+	} else if(exponent == 255) {
+		h = 0x7c00u | (mantissa ? 0x200u : 0u);
+	} else {
+		const int newexp = (int)exponent - 127 + 15;
+		if(newexp >= 31) {
+			h = 0x7c00u;
+		} else if(newexp <= 0) {
+			if((14 - newexp) <= 24) {
+				const uint32_t mant = mantissa | 0x800000u;
+				h = (mant >> (14 - newexp)) & 0x3ffu;
+				if((mant >> (13 - newexp)) & 1u) h++;
+			}
+		} else {
+			h = ((uint32_t)newexp << 10) | (mantissa >> 13);
+			if(mantissa & 0x1000u) h++;
+		}
+	}
+	return (uint16_t)((h & 0x7fffu) | (sign << 15));
+}
+
+/* half -> float (tinyexr.h:946-969), used by the tests to compare with what the reference's loader reads back. */
+float orc_half_to_float(uint16_t h) {
+	const uint32_t sign = (uint32_t)(h >> 15) << 31, exponent = (h >> 10) & 0x1fu, mantissa = h & 0x3ffu;
+	uint32_t bits;
+	float out;
+	if(exponent == 31) {
+		bits = sign | 0x7f800000u | (mantissa << 13);
+	} else if(exponent == 0) {
+		/* zero / denormal: mantissa * 2^-24 is exact in fp32 */
+		out = (float)mantissa * (1.0f / 16777216.0f);
+		memcpy(&bits, &out, sizeof(bits));
+		bits |= sign;
+	} else {
+		bits = sign | ((exponent + 112u) << 23) | (mantissa << 13);
+	}
+	memcpy(&out, &bits, sizeof(out));
+	return out;
+}
+
+/* Image::saveAsHDR's layer split (src/engine/resources/Image.cpp:178-232) and the half conversion of the writer:
+ * channels = components, except 2 -> 3 (third layer zero); planes are written in the file's channel order — (A)BGR for
+ * 4/3 channels, the single layer for 1 — each width*height halves; IGNORE_ALPHA stores 1.0 in A; flip reverses rows. */
+void orc_output_hdr(const float * pixels, uint32_t width, uint32_t height, uint32_t components, int ignore_alpha, int flip, uint16_t * planes) {
+	const uint32_t channels = components == 2 ? 3 : components;
+	const size_t npx = (size_t)width * height;
+	for(uint32_t y = 0; y < height; ++y) {
+		for(uint32_t x = 0; x < width; ++x) {
+			const size_t dst = (size_t)y * width + x;
+			const size_t src = flip ? ((size_t)(height - 1 - y) * width + x) : dst;
+			for(uint32_t j = 0; j < channels; ++j) {
+				float value = j < components ? pixels[(size_t)components * src + j] : 0.0f;
+				if(j == 3 && ignore_alpha) value = 1.0f;
+				const uint32_t plane = channels == 1 ? 0 : channels - 1 - j; /* R is the last plane */
+				planes[plane * npx + dst] = orc_float_to_half(value);
+			}
+		}
+	}
+}

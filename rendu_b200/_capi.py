@@ -107,6 +107,8 @@ def lib():
         "rb_pathtracer_stats": (C.c_int, [vp, C.POINTER(RenderStats)]),
         "rb_output_ldr": (C.c_int, [vp, u32, u32, u32, C.c_int, C.c_int, vp]),
         "rb_output_ldr_device": (C.c_int, [vp, u32, u32, u32, C.c_int, C.c_int, vp, vp]),
+        "rb_output_hdr": (C.c_int, [vp, u32, u32, u32, C.c_int, C.c_int, vp]),
+        "rb_output_hdr_device": (C.c_int, [vp, u32, u32, u32, C.c_int, C.c_int, vp, vp]),
         "rb_kat_ggx_eval": (C.c_int, [vp, vp, vp, vp, vp, sz, vp]),
         "rb_kat_ggx_sample": (C.c_int, [vp, vp, vp, vp, vp, sz, vp, vp]),
         "rb_kat_image_sample": (C.c_int, [vp, u32, u32, vp, sz, vp]),

@@ -162,6 +162,16 @@ def output_ldr(image, tonemap=True, srgb=True):
     return out
 
 
+def output_hdr(image, ignore_alpha=True, flip=False):
+    """The .exr branch of the headless render (Image::saveAsHDR + the EXR writer's half conversion): float image ->
+    planar half layers (uint16, shape (components, H, W)) in the file's channel order (A)BGR, computed on the GPU."""
+    image = np.ascontiguousarray(image, np.float32)
+    h, w, c = image.shape
+    out = np.zeros((c, h, w), np.uint16)
+    check(lib().rb_output_hdr(ptr(image), w, h, c, 1 if ignore_alpha else 0, 1 if flip else 0, ptr(out)))
+    return out
+
+
 def save_scene(path, description):
     """Flattened scene -> one compressed .npz (used for golden fixtures)."""
     out = {"n_objects": len(description["objects"]), "n_lights": len(description["lights"]), "n_textures": len(description["textures"])}

@@ -180,6 +180,15 @@ def output_goldens():
     np.savez_compressed(os.path.join(OUT, "output_kat.npz"), img=img, tonemapped=ref.output_ldr(img, True), clipped=ref.output_ldr(np.clip(img, 0, 1), False),
                         rgba=rgba, rgba_out=ref.output_ldr(rgba, True))
     print("output_kat ok")
+    # .exr branch: the reference's EXR writer (half channels) read back by its own loader
+    hdr = np.exp(rng.uniform(-22, 12.5, (32, 40, 3))).astype(F)
+    hdr[0, :8, 0] = [0.0, -0.0, 1e-8, 5.9604645e-8, 2.9802322e-8, 2.98e-8, 6.1e-5, 6.0975552e-05]
+    hdr[0, :8, 1] = [65504.0, 65519.9, 65520.0, 70000.0, np.inf, -np.inf, -1.5, 1.0009766]
+    hdr[0, :8, 2] = [1.00048828125, 1.0004883, 1.0014648, 0.99975586, 0.33333334, 2047.5, 2048.5, 1e-5]
+    hdr[1] *= -1.0
+    hdr4 = np.concatenate([hdr, rng.uniform(0, 1, (32, 40, 1)).astype(F)], -1)
+    np.savez_compressed(os.path.join(OUT, "output_hdr_kat.npz"), img=hdr, stored=ref.output_hdr(hdr), rgba=hdr4, rgba_stored=ref.output_hdr(hdr4))
+    print("output_hdr_kat ok")
 
 
 if __name__ == "__main__":

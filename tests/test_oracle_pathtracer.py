@@ -140,3 +140,27 @@ def test_output_stage_bytes_match_reference_png():
         rng = np.random.RandomState(2)
         img = rng.uniform(0, 4, (17, 23, 3)).astype(np.float32)
         assert np.array_equal(orc.output_ldr(img, True, True), ref.output_ldr(img, True))
+
+
+def test_output_stage_hdr_matches_reference_exr():
+    """.exr branch (Image.cpp:160-289 + tinyexr float_to_half_full): the oracle's half layers decode to exactly the floats
+    the reference's own loader reads back from the EXR its own writer produced (golden; live when oracle/_ref is there).
+    The vectors hold the corner cases of that conversion: subnormal floats, the half subnormal range, ties (round half up),
+    overflow to infinity, infinities, negative values."""
+    g = dict(np.load(os.path.join(GOLDEN, "output_hdr_kat.npz")))
+    for img, stored in ((g["img"], g["stored"]), (g["rgba"], g["rgba_stored"])):
+        planes = orc.output_hdr(img, ignore_alpha=True)
+        assert planes.shape == (img.shape[2],) + img.shape[:2]
+        back = orc.half_planes_to_image(planes, img.shape[2])
+        assert np.array_equal(back.view(np.uint32), stored.view(np.uint32))
+    assert (g["rgba_stored"][..., 3] == 1.0).all()  # IGNORE_ALPHA
+    # round half UP, unlike IEEE round-to-nearest-even: 1 + 2^-11 (a tie) goes up to 1 + 2^-10
+    tie = np.full((16, 16, 3), 1.00048828125, np.float32)
+    assert (orc.half_planes_to_image(orc.output_hdr(tie), 3) == np.float32(1.0009765625)).all()
+    assert (tie.astype(np.float16).astype(np.float32) == 1.0).all()
+    # flip reverses rows
+    assert np.array_equal(orc.output_hdr(g["img"], flip=True), orc.output_hdr(g["img"][::-1]))
+    if ref.available():
+        rng = np.random.RandomState(8)
+        img = np.exp(rng.uniform(-20, 12, (19, 33, 3))).astype(np.float32)
+        assert np.array_equal(orc.half_planes_to_image(orc.output_hdr(img), 3).view(np.uint32), ref.output_hdr(img).view(np.uint32))

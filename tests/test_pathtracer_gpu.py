@@ -216,6 +216,25 @@ def test_output_stage_on_device():
     assert np.abs(ldr.astype(np.int32) - want.astype(np.int32)).max() <= 1 and ldr.max() > 100
 
 
+def test_output_stage_hdr_on_device():
+    """Layer split + the EXR writer's float -> half rule on the GPU: integer work, so bit-exact against the oracle and
+    against what the reference stored (golden)."""
+    g = dict(np.load(os.path.join(GOLDEN, "output_hdr_kat.npz")))
+    for img, stored in ((g["img"], g["stored"]), (g["rgba"], g["rgba_stored"])):
+        planes = rpt.output_hdr(img)
+        assert np.array_equal(planes, orc.output_hdr(img))
+        assert np.array_equal(orc.half_planes_to_image(planes, img.shape[2]).view(np.uint32), stored.view(np.uint32))
+        assert np.array_equal(rpt.output_hdr(img, flip=True), orc.output_hdr(img, flip=True))
+        assert np.array_equal(rpt.output_hdr(img, ignore_alpha=False), orc.output_hdr(img, ignore_alpha=False))
+    # every finite float exponent/rounding class: sweep 1M random bit patterns
+    rng = np.random.RandomState(4)
+    bits = rng.randint(0, 2 ** 32, size=(512, 683, 3), dtype=np.uint64).astype(np.uint32)
+    img = bits.view(np.float32)
+    assert np.array_equal(rpt.output_hdr(img), orc.output_hdr(img))
+    with pytest.raises(rb.RenduError):
+        rpt.output_hdr(np.zeros((8, 8, 2), np.float32))
+
+
 def test_progressive_accumulation_on_device():
     """sums stay on the device; four progressive passes over disjoint slices of the stratification grid
     add up to the one-shot render (fp32 summation order aside)."""
