@@ -153,6 +153,14 @@ RB_API rb_status rb_raycaster_intersect_any(const rb_raycaster * rc, const float
 /* Raycaster::visible (Raycaster.cpp:226-230), batched: out[i] = 1 if the segment p0[i]..p1[i] is free. */
 RB_API rb_status rb_raycaster_visible(const rb_raycaster * rc, const float * p0, const float * p1, size_t n, uint8_t * out);
 
+/* RaycasterVisualisation::getRayLevels (src/engine/raycaster/RaycasterVisualisation.cpp:41-77) on the device tree: one
+ * closest-hit query in the reference's order that also reports every node it visited, in visiting order — its box
+ * (6 floats: min, max) and its depth (roots are depth 0) — for BVH-level displays and click-to-cast ray debugging
+ * (BVHRenderer::castRay). At most `capacity` records are written; *count receives the number of visited nodes. Works
+ * on both tree kinds (for an LBVH tree the levels are those of that tree). hit = what rb_raycaster_intersect returns. */
+RB_API rb_status rb_raycaster_ray_levels(const rb_raycaster * h, const float * origin, const float * direction, float mini, float maxi, uint32_t capacity,
+										 float * boxes6, uint32_t * depths, uint32_t * count, rb_hit * hit);
+
 /* Device-pointer variants: enqueue on `stream` (a cudaStream_t), no host synchronisation. */
 RB_API rb_status rb_raycaster_intersect_device(const rb_raycaster * rc, const float * d_origins, const float * d_directions, float mini, float maxi, size_t nrays, rb_hit * d_out, void * stream);
 RB_API rb_status rb_raycaster_intersect_any_device(const rb_raycaster * rc, const float * d_origins, const float * d_directions, float mini, float maxi, size_t nrays, uint8_t * d_out, void * stream);

@@ -66,6 +66,16 @@ for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
 WRAP="_ZNK9Raycaster10intersectsERKN3glm3vecILi3EfLNS0_9qualifierE0EEES5_ff"
 $CXX -shared -o "$OUT/librendu_ref.so" "$OUT"/obj/*.o -Wl,--wrap=$WRAP -Wl,--wrap=_ZNSt6thread20hardware_concurrencyEv -Wl,--no-undefined -Wl,-Bsymbolic -lpthread
 
+# Second checker library: the reference's own RaycasterVisualisation (unmodified) + its harness. Separate because ref_api.cpp
+# defines a stand-in class of that name (the friend hook); it shares every other reference object.
+mkdir -p "$OUT/objvis"
+pids=()
+compile "$SRC/engine/raycaster/RaycasterVisualisation.cpp" "$OUT/objvis/RaycasterVisualisation.o" "$CXX" "$CXXFLAGS"
+compile "$HERE/ref_harness/refvis_api.cpp" "$OUT/objvis/refvis_api.o" "$CXX" "$CXXFLAGS"
+for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
+VISOBJS=$(ls "$OUT"/obj/*.o | grep -v "/ref_api.o$")
+$CXX -shared -o "$OUT/librendu_refvis.so" $VISOBJS "$OUT"/objvis/*.o -Wl,--no-undefined -Wl,-Bsymbolic -lpthread
+
 # Run-time data of the reference (not source code): scenes, meshes, textures.
 mkdir -p "$OUT/resources"
 for d in common pbrdemo; do

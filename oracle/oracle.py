@@ -109,6 +109,20 @@ class OracleRaycaster:
         lib().orc_intersect_any_batch(C.byref(b), _p(org), _p(dirs), C.c_float(mini), C.c_float(maxi), C.c_size_t(org.shape[0]), int(threads), _p(out))
         return out
 
+    def ray_levels(self, origin, direction, mini=1e-4, maxi=1e8, cap=4096):
+        """RaycasterVisualisation::getRayLevels: (node ids, depths, boxes (n, 6), total visited, hit record)."""
+        o = np.ascontiguousarray(origin, np.float32).reshape(3)
+        d = np.ascontiguousarray(direction, np.float32).reshape(3)
+        ids, depths = np.zeros(cap, np.uint64), np.zeros(cap, np.uint32)
+        count = C.c_size_t(0)
+        hit = np.zeros(1, HIT)
+        b = self._bvh()
+        lib().orc_ray_levels(C.byref(b), _p(o), _p(d), C.c_float(mini), C.c_float(maxi), C.c_size_t(cap), _p(ids), _p(depths), C.byref(count), _p(hit))
+        n = min(count.value, cap)
+        nodes = self.nodes[ids[:n].astype(np.int64)]
+        boxes = np.concatenate([nodes["bmin"], nodes["bmax"]], axis=1).astype(np.float32)
+        return ids[:n], depths[:n], boxes, count.value, hit[0]
+
     def visible(self, p0, p1):
         p0 = np.ascontiguousarray(p0, np.float32).reshape(-1, 3)
         p1 = np.ascontiguousarray(p1, np.float32).reshape(-1, 3)

@@ -45,6 +45,23 @@ def lib():
     return _lib
 
 
+_vislib = None
+
+
+def vislib():
+    """Second checker library: the reference's unmodified RaycasterVisualisation (oracle/ref_harness/refvis_api.cpp)."""
+    global _vislib
+    if _vislib is None:
+        path = os.path.join(os.path.dirname(LIB_PATH), "librendu_refvis.so")
+        if not os.path.exists(path):
+            raise RuntimeError("reference visualisation library missing: run oracle/build_ref.sh")
+        lib()  # the raycaster handles come from the main checker library
+        _vislib = C.CDLL(path)
+        _vislib.refvis_ray_levels.restype = C.c_long
+        _vislib.refvis_all_levels.restype = C.c_long
+    return _vislib
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -127,6 +144,31 @@ class RefRaycaster:
         out = np.zeros(p0.shape[0], np.uint8)
         lib().ref_raycaster_visible(self._h, _p(p0), _p(p1), C.c_size_t(p0.shape[0]), _p(out))
         return out
+
+    def _levels(self, fn, *head):
+        cap_levels, cap_nodes = 256, 1 << 22
+        counts, boxes, nlev = np.zeros(cap_levels, np.uint32), np.zeros((cap_nodes, 6), np.float32), C.c_uint32(0)
+        total = fn(self._h, *head, C.c_uint32(cap_levels), C.c_uint64(cap_nodes), _p(counts), _p(boxes), C.byref(nlev))
+        if total < 0:
+            raise RuntimeError("reference visualisation exceeds the harness capacities")
+        return counts[:nlev.value].copy(), boxes[:total].copy()
+
+    def ray_levels(self, origin, direction, mini=1e-4, maxi=1e8):
+        """The reference's own RaycasterVisualisation::getRayLevels (librendu_refvis.so): per depth level the boxes it draws
+        (levels concatenated), and the hit it returns."""
+        o = np.ascontiguousarray(origin, np.float32).reshape(3)
+        d = np.ascontiguousarray(direction, np.float32).reshape(3)
+        hf, hi = np.zeros(4, np.float32), np.zeros(3, np.uint64)
+        L = vislib()
+
+        def fn(h, *rest):
+            return L.refvis_ray_levels(h, _p(o), _p(d), C.c_float(mini), C.c_float(maxi), *rest, _p(hf), _p(hi))
+        counts, boxes = self._levels(fn)
+        return counts, boxes, dict(hit=int(hi[0]), dist=hf[0], u=hf[1], v=hf[2], w=hf[3], localId=int(hi[1]), meshId=int(hi[2]))
+
+    def all_levels(self):
+        """RaycasterVisualisation::getAllLevels: every node box, breadth first, grouped by depth."""
+        return self._levels(vislib().refvis_all_levels)
 
     def counters(self, org, dirs, mini=1e-4, maxi=1e8, any_hit=False):
         org = np.ascontiguousarray(org, np.float32).reshape(-1, 3)

@@ -124,6 +124,52 @@ static int traverse(const orc_bvh * b, const float * origin, const float * direc
 	return (int)best->hit;
 }
 
+/* RaycasterVisualisation::getRayLevels (src/engine/raycaster/RaycasterVisualisation.cpp:41-77): the closest-hit loop
+ * again, recording every node it pops with its depth (roots are depth 0), in pop order. At most `cap` records are
+ * written; *count receives the number of nodes visited. The boxes the viewer draws are b->nodes[id].bmin/bmax. */
+void orc_ray_levels(const orc_bvh * b, const float * origin, const float * direction, float mini, float maxi, size_t cap, uint64_t * nodeIds, uint32_t * depths, size_t * count, orc_hit * hit) {
+	float r[9];
+	orc_ray(origin, direction, r);
+	stack_t_ st = {0, 0, 0}, dp = {0, 0, 0};
+	for(size_t nid = 0; nid < b->meshCount; ++nid) {
+		if(!orc_box(r, b->nodes[nid].bmin, b->nodes[nid].bmax, mini, maxi)) continue;
+		push(&st, nid);
+		push(&dp, 0);
+	}
+	orc_hit best = miss();
+	size_t visited = 0;
+	while(st.size) {
+		const size_t id		  = st.data[--st.size];
+		const size_t depth	  = dp.data[--dp.size];
+		const orc_node * node = &b->nodes[id];
+		if(visited < cap) {
+			nodeIds[visited] = (uint64_t)id;
+			depths[visited]	 = (uint32_t)depth;
+		}
+		++visited;
+		if(node->leaf) {
+			for(size_t tid = 0; tid < node->right; ++tid) {
+				const orc_tri * tri = &b->tris[node->left + tid];
+				float t, u, v;
+				if(orc_tri_test(b, r, tri, mini, maxi, &t, &u, &v) && t < best.dist) {
+					best.hit = 1; best.dist = t; best.u = u; best.v = v;
+					best.w = 1.0f - u - v;
+					best.localId = tri->localId; best.meshId = tri->meshId;
+					best.internalId = (uint64_t)(node->left + tid);
+					maxi = t;
+				}
+			}
+			continue;
+		}
+		if(orc_box(r, b->nodes[node->left].bmin, b->nodes[node->left].bmax, mini, maxi)) { push(&st, node->left); push(&dp, depth + 1); }
+		if(orc_box(r, b->nodes[node->right].bmin, b->nodes[node->right].bmax, mini, maxi)) { push(&st, node->right); push(&dp, depth + 1); }
+	}
+	free(st.data);
+	free(dp.data);
+	*count = visited;
+	*hit   = best;
+}
+
 orc_hit orc_intersect(const orc_bvh * b, const float * origin, const float * direction, float mini, float maxi) {
 	orc_hit h;
 	traverse(b, origin, direction, mini, maxi, 0, &h);

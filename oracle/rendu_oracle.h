@@ -36,6 +36,8 @@ void orc_ray(const float * origin, const float * direction, float * out9);
 int orc_box(const float * ray9, const float * bmin, const float * bmax, float mini, float maxi);
 /* Raycaster::intersects(ray, tri, mini, maxi) (Raycaster.cpp:232-262). Returns 1 on hit and fills t,u,v. */
 int orc_tri_test(const orc_bvh * b, const float * ray9, const orc_tri * tri, float mini, float maxi, float * t, float * u, float * v);
+/* RaycasterVisualisation::getRayLevels (RaycasterVisualisation.cpp:41-77): visited nodes (id, depth) in pop order. */
+void orc_ray_levels(const orc_bvh * b, const float * origin, const float * direction, float mini, float maxi, size_t cap, uint64_t * nodeIds, uint32_t * depths, size_t * count, orc_hit * hit);
 /* Raycaster::intersects (Raycaster.cpp:144-185). */
 orc_hit orc_intersect(const orc_bvh * b, const float * origin, const float * direction, float mini, float maxi);
 /* Raycaster::intersectsAny (Raycaster.cpp:187-224). */

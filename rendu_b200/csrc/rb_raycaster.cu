@@ -881,6 +881,103 @@ extern "C" rb_status rb_raycaster_visible(const rb_raycaster * rc, const float *
 	return RB_OK;
 }
 
+// ---------------------------------------------------------------- ray debugging: visited nodes of one ray
+// RaycasterVisualisation::getRayLevels (src/engine/raycaster/RaycasterVisualisation.cpp:41-77) on the device tree: the
+// closest-hit loop in the reference's order, recording every node it pops — its box and depth (roots are depth 0) — so
+// that a viewer can draw the levels a ray went through without reading the hierarchy back. On the device a node's box
+// is stored with its parent (or in the root table), so the stack carries where to find it. One thread: this is a
+// click-to-inspect query, not a throughput path.
+struct RbLevelEntry {
+	int ref, depth, src; // src: (parent interior << 1) | side, or ~root slot
+};
+
+__global__ void rb_k_ray_levels(RbDeviceBvh bvh, const float * __restrict__ org, const float * __restrict__ dir, float mini, float maxi, RbLevelEntry * __restrict__ stack, unsigned int capacity,
+								float * __restrict__ boxes, unsigned int * __restrict__ depths, unsigned int * __restrict__ count, rb_hit * __restrict__ hit) {
+	if(blockIdx.x != 0 || threadIdx.x != 0) return;
+	const RbRay ray = rb_make_ray(V3{org[0], org[1], org[2]}, V3{dir[0], dir[1], dir[2]});
+	int top = 0;
+	for(int m = 0; m < bvh.nroots; ++m) {
+		const float4 lo = bvh.roots[2 * m], hi = bvh.roots[2 * m + 1];
+		if(!rb_box_test(ray, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, mini, maxi)) continue;
+		stack[top++] = RbLevelEntry{__float_as_int(lo.w), 0, ~m};
+	}
+	RbHitRec best{FLT_MAX, 0.0f, 0.0f, -1};
+	unsigned int visited = 0;
+	while(top > 0) {
+		const RbLevelEntry e = stack[--top];
+		if(visited < capacity) {
+			float * b = boxes + 6 * (size_t)visited;
+			if(e.src < 0) {
+				const float4 lo = bvh.roots[2 * (~e.src)], hi = bvh.roots[2 * (~e.src) + 1];
+				b[0] = lo.x; b[1] = lo.y; b[2] = lo.z; b[3] = hi.x; b[4] = hi.y; b[5] = hi.z;
+			} else {
+				const float * n = reinterpret_cast<const float *>(bvh.nodes + 4 * (size_t)(e.src >> 1)) + 6 * (e.src & 1);
+				for(int k = 0; k < 6; ++k) b[k] = n[k];
+			}
+			depths[visited] = (unsigned int)e.depth;
+		}
+		++visited;
+		if(e.ref == RB_REF_NONE) continue; // empty leaf
+		if(e.ref < 0) {
+			const int code = ~e.ref, first = code >> RB_LEAF_BITS, n = (code & (RB_LEAF_MAX_TRIS - 1)) + 1;
+			for(int k = 0; k < n; ++k) {
+				const float4 * tp = bvh.tris + 3 * (size_t)(first + k);
+				const float4 t0 = tp[0], t1 = tp[1], t2 = tp[2];
+				float t, u, v;
+				if(rb_tri_test(ray, V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, mini, maxi, t, u, v) && t < best.t) {
+					best = RbHitRec{t, u, v, first + k};
+					maxi = t;
+				}
+			}
+			continue;
+		}
+		const float4 * np = bvh.nodes + 4 * (size_t)e.ref;
+		const float4 a = np[0], b4 = np[1], c = np[2], d4 = np[3];
+		if(rb_box_test(ray, a.x, a.y, a.z, a.w, b4.x, b4.y, mini, maxi)) stack[top++] = RbLevelEntry{__float_as_int(d4.x), e.depth + 1, (e.ref << 1) | 0};
+		if(rb_box_test(ray, b4.z, b4.w, c.x, c.y, c.z, c.w, mini, maxi)) stack[top++] = RbLevelEntry{__float_as_int(d4.y), e.depth + 1, (e.ref << 1) | 1};
+	}
+	*count = visited;
+	rb_store_hit(hit, 0, bvh, best);
+}
+
+extern "C" rb_status rb_raycaster_ray_levels(const rb_raycaster * rc, const float * origin, const float * direction, float mini, float maxi, uint32_t capacity, float * boxes6, uint32_t * depths,
+											 uint32_t * count, rb_hit * hit) {
+	rb_status st = rb_check_query(rc, "rb_raycaster_ray_levels");
+	if(st) return st;
+	if(!origin || !direction || !count || !hit || (capacity && (!boxes6 || !depths))) return rb_fail(RB_ERR_INVALID, "rb_raycaster_ray_levels: null argument");
+	RB_CUDA(cudaSetDevice(rc->device));
+	cudaStream_t s = cudaStreamPerThread;
+	Scratch scratch(s);
+	float *d_ray = nullptr, *d_boxes = nullptr;
+	unsigned int *d_depths = nullptr, *d_count = nullptr;
+	RbLevelEntry * d_stack = nullptr;
+	rb_hit * d_hit = nullptr;
+	const size_t stackEntries = size_t(rc->dev.nroots) + size_t(rc->dev.stackDepth) + 2;
+	RB_CUDA(scratch.alloc(&d_ray, 6 * sizeof(float)));
+	RB_CUDA(scratch.alloc(&d_boxes, size_t(capacity) * 6 * sizeof(float)));
+	RB_CUDA(scratch.alloc(&d_depths, size_t(capacity) * sizeof(unsigned int)));
+	RB_CUDA(scratch.alloc(&d_count, sizeof(unsigned int)));
+	RB_CUDA(scratch.alloc(&d_stack, stackEntries * sizeof(RbLevelEntry)));
+	RB_CUDA(scratch.alloc(&d_hit, sizeof(rb_hit)));
+	const float ray[6] = {origin[0], origin[1], origin[2], direction[0], direction[1], direction[2]};
+	RB_CUDA(cudaMemcpyAsync(d_ray, ray, sizeof(ray), cudaMemcpyHostToDevice, s));
+	rb_k_ray_levels<<<1, 32, 0, s>>>(rc->dev, d_ray, d_ray + 3, mini, maxi, d_stack, capacity, d_boxes, d_depths, d_count, d_hit);
+	RB_CUDA(cudaGetLastError());
+	rc->launches++;
+	unsigned int visited = 0;
+	RB_CUDA(cudaMemcpyAsync(&visited, d_count, sizeof(visited), cudaMemcpyDeviceToHost, s));
+	RB_CUDA(cudaMemcpyAsync(hit, d_hit, sizeof(rb_hit), cudaMemcpyDeviceToHost, s));
+	RB_CUDA(cudaStreamSynchronize(s));
+	const size_t n = visited < capacity ? visited : capacity;
+	if(n) {
+		RB_CUDA(cudaMemcpyAsync(boxes6, d_boxes, n * 6 * sizeof(float), cudaMemcpyDeviceToHost, s));
+		RB_CUDA(cudaMemcpyAsync(depths, d_depths, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+		RB_CUDA(cudaStreamSynchronize(s));
+	}
+	*count = visited;
+	return RB_OK;
+}
+
 // ---------------------------------------------------------------- KAT: Ray::Ray + Intersection::box on arrays
 __global__ void rb_k_kat_box(const float * __restrict__ org, const float * __restrict__ dir, const float * __restrict__ boxes, float mini, float maxi, size_t n, uint8_t * __restrict__ out) {
 	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

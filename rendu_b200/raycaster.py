@@ -112,6 +112,17 @@ class Raycaster:
         check(lib().rb_raycaster_visible(self._h, ptr(a), ptr(b), a.shape[0], ptr(out)))
         return bool(out[0]) if single else out.astype(bool)
 
+    def rayLevels(self, origin, direction, mini=1e-4, maxi=1e8, capacity=4096):
+        """RaycasterVisualisation::getRayLevels (RaycasterVisualisation.cpp:41-77) from the device tree: boxes (n, 6) and
+        depths (n,) of the nodes the ray visited, in visiting order, the total number visited and the Hit."""
+        o = np.ascontiguousarray(origin, np.float32).reshape(3)
+        d = np.ascontiguousarray(direction, np.float32).reshape(3)
+        boxes, depths = np.zeros((capacity, 6), np.float32), np.zeros(capacity, np.uint32)
+        count, hit = C.c_uint32(0), np.zeros(1, HIT_DTYPE)
+        check(lib().rb_raycaster_ray_levels(self._h, ptr(o), ptr(d), mini, maxi, capacity, ptr(boxes), ptr(depths), C.byref(count), ptr(hit)))
+        n = min(count.value, capacity)
+        return boxes[:n], depths[:n], count.value, hit[0]
+
     @staticmethod
     def interpolateAttribute(hit, indices, attribute):
         """Raycaster::interpolateAttribute (Raycaster.hpp:90-97): w*a[i0] + u*a[i1] + v*a[i2]."""

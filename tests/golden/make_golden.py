@@ -84,15 +84,50 @@ def raycast_case(name, meshes, nrand, seed, mini=1e-4, maxi=1e8):
     print(name, "rays", org.shape[0], "hits", int(h["hit"].sum()), "nodes", dump["node_left"].size)
 
 
-def main():
+def case_meshes():
     pos, idx = wl.displaced_grid(37)
-    raycast_case("raycast_grid37", [(pos, idx, None)], 3000, 7)
     # Several meshes: transformed copies, a 2-triangle quad (its root is a leaf), a single triangle, overlapping geometry.
     p8, i8 = wl.displaced_grid(8)
     quad = (np.array([[-1, 0.6, -1], [1, 0.6, -1], [1, 0.6, 1], [-1, 0.6, 1]], F), np.array([0, 1, 2, 0, 2, 3], np.uint32))
     tri = (np.array([[0, 0.9, 0], [0.5, 0.9, 0], [0, 0.9, 0.5]], F), np.array([0, 1, 2], np.uint32))
-    raycast_case("raycast_multimesh", [(p8, i8, None), (p8, i8, rot_scale(0.7, 0.5, (0.2, 0.4, -0.1))), (quad[0], quad[1], None),
-                                       (tri[0], tri[1], translate((0.1, 0.0, 0.1))), (p8, i8, translate((0.0, 0.0, 0.0)))], 3000, 11)
+    return {"raycast_grid37": [(pos, idx, None)],
+            "raycast_multimesh": [(p8, i8, None), (p8, i8, rot_scale(0.7, 0.5, (0.2, 0.4, -0.1))), (quad[0], quad[1], None),
+                                  (tri[0], tri[1], translate((0.1, 0.0, 0.1))), (p8, i8, translate((0.0, 0.0, 0.0)))]}
+
+
+def levels_goldens():
+    """The reference's own RaycasterVisualisation::getRayLevels (unmodified, oracle/_ref/librendu_refvis.so) on rays of
+    the two raycast cases: boxes drawn per depth level + the hit it returns; and getAllLevels' per-level node counts."""
+    save = {}
+    for name, meshes in case_meshes().items():
+        r = ref.RefRaycaster()
+        for pos, idx, model in meshes:
+            r.add_mesh(pos, idx, model)
+        r.build()
+        case = np.load(os.path.join(OUT, name + ".npz"))
+        pick = np.concatenate([np.arange(0, 3000, 250), np.arange(3000, 3000 + 48 * 48, 192), np.arange(3000 + 48 * 48, case["org"].shape[0], 7)])
+        counts_all, boxes_all, hits = [], [], []
+        for i in pick:
+            counts, boxes, hit = r.ray_levels(case["org"][i], case["dirs"][i], float(case["mini"]), float(case["maxi"]))
+            row = np.zeros(64, np.uint32)
+            row[:counts.size] = counts
+            counts_all.append(row)
+            boxes_all.append(boxes)
+            hits.append([hit["hit"], hit["localId"], hit["meshId"], int(np.float32(hit["dist"]).view(np.uint32))])
+        save[name + "_rays"] = pick.astype(np.int64)
+        save[name + "_counts"] = np.array(counts_all)
+        save[name + "_boxes"] = np.concatenate(boxes_all).astype(F)
+        save[name + "_hits"] = np.array(hits, np.int64)
+        ac, ab = r.all_levels()
+        save[name + "_all_counts"] = ac
+        print(name, "rays", pick.size, "boxes", save[name + "_boxes"].shape[0], "levels", ac.size)
+    np.savez_compressed(os.path.join(OUT, "ray_levels.npz"), **save)
+
+
+def main():
+    cases = case_meshes()
+    raycast_case("raycast_grid37", cases["raycast_grid37"], 3000, 7)
+    raycast_case("raycast_multimesh", cases["raycast_multimesh"], 3000, 11)
     # Box test KAT on the edge rays against assorted boxes.
     eo, ed = edge_rays()
     rng = np.random.RandomState(5)
@@ -195,3 +230,4 @@ if __name__ == "__main__":
     main()
     pathtracer_goldens()
     output_goldens()
+    levels_goldens()

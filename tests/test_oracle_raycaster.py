@@ -1,5 +1,7 @@
 """CPU tests (no GPU): the C oracle against (a) golden vectors generated from the real reference and (b) the real
 reference itself when oracle/_ref is present; plus the product's host-side BVH builder against both."""
+import os
+
 import numpy as np
 import pytest
 
@@ -8,6 +10,7 @@ from oracle import ref
 from rendu_b200 import workloads as wl
 from util import case_meshes, load_case
 
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["raycast_grid37", "raycast_multimesh"]
 
 
@@ -50,6 +53,56 @@ def test_oracle_hits_match_golden(name):
     assert np.array_equal(o.intersect_any(c["org"], c["dirs"], 0.05, 1.7), c["any_b"])
     p1 = (c["org"] + c["dirs"]).astype(np.float32)
     assert np.array_equal(o.visible(c["org"][:512], p1[:512]), c["visible"])
+
+
+def levels_grouped(boxes, depths, nlevels=64):
+    """Visiting-order records -> what the viewer draws: boxes grouped by depth (order kept inside a level)."""
+    order = np.argsort(depths, kind="stable")
+    return np.bincount(depths, minlength=nlevels).astype(np.uint32), boxes[order]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_ray_levels_match_reference_visualisation(name):
+    """RaycasterVisualisation::getRayLevels (RaycasterVisualisation.cpp:41-77): the oracle's visited nodes, grouped by
+    depth, are the boxes the reference's own (unmodified) visualisation draws, level by level, and the hit it returns;
+    the breadth-first getAllLevels counts follow from the hierarchy."""
+    g = np.load(os.path.join(GOLDEN, "ray_levels.npz"))
+    c = load_case(name)
+    o = build_oracle(c)
+    at = 0
+    for k, i in enumerate(g[name + "_rays"]):
+        ids, depths, boxes, total, hit = o.ray_levels(c["org"][i], c["dirs"][i], float(c["mini"]), float(c["maxi"]))
+        counts, grouped = levels_grouped(boxes, depths)
+        assert total == ids.size and np.array_equal(counts, g[name + "_counts"][k])
+        want = g[name + "_boxes"][at:at + total]
+        at += total
+        assert np.array_equal(grouped.view(np.uint32), want.view(np.uint32))
+        hw = g[name + "_hits"][k]
+        assert int(hit["hit"]) == hw[0] and int(hit["localId"]) == hw[1] and int(hit["meshId"]) == hw[2]
+        assert int(np.float32(hit["dist"]).view(np.uint32)) == hw[3]
+        single = o.intersect(c["org"][i:i + 1], c["dirs"][i:i + 1], float(c["mini"]), float(c["maxi"]))[0]
+        assert single["internalId"] == hit["internalId"] and single["dist"] == hit["dist"]
+    assert at == g[name + "_boxes"].shape[0]
+    # getAllLevels: node count per depth from a breadth-first walk of the oracle's hierarchy
+    depth = np.zeros(o.nodes.size, np.int64)
+    frontier, level_counts = list(range(o.mesh_count)), []
+    while frontier:
+        level_counts.append(len(frontier))
+        nxt = []
+        for n in frontier:
+            if not o.nodes["leaf"][n]:
+                nxt += [int(o.nodes["left"][n]), int(o.nodes["right"][n])]
+        frontier = nxt
+    assert np.array_equal(np.array(level_counts, np.uint32), g[name + "_all_counts"])
+    if ref.available():
+        r = ref.RefRaycaster()
+        for pos, idx, model in case_meshes(c):
+            r.add_mesh(pos, idx, model)
+        r.build()
+        counts, boxes, _ = r.ray_levels(c["org"][5], c["dirs"][5])
+        ids, depths, ob, total, _ = o.ray_levels(c["org"][5], c["dirs"][5])
+        oc, og = levels_grouped(ob, depths, counts.size)
+        assert np.array_equal(oc[:counts.size], counts) and np.array_equal(og.view(np.uint32), boxes.view(np.uint32))
 
 
 def test_oracle_box_kat():

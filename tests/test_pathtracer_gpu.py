@@ -200,6 +200,22 @@ def test_image_contract_components_accumulation_and_rounding():
         gpu_render(desc, cam, 32, 32, 16, 4, components=2, image=np.zeros((32, 32, 2), np.float32))
 
 
+def test_batches_and_lanes_do_not_change_the_image(monkeypatch):
+    """The wavefront is cut into batches that alternate between stream lanes; every variate is keyed by (seed, pixel,
+    cell, bounce, dimension) and batches own disjoint pixels, so lane count and batch size must not change one bit."""
+    desc, cam, _ = golden_scene("cornellbox")
+    w, h, spp, depth = 320, 256, 16, 5  # 1.3 M paths: enough for the lanes to engage
+    imgs = []
+    for lanes, max_paths in ((1, 0), (2, 0), (4, 0), (2, 200000), (1, 65536), (3, 300000)):
+        monkeypatch.setenv("RB_PT_LANES", str(lanes))
+        img, pt = gpu_render(desc, cam, w, h, spp, depth, seed=11, max_paths=max_paths)
+        assert pt.stats()["samples"] == w * h * spp
+        imgs.append(img)
+    for img in imgs[1:]:
+        assert np.array_equal(img.view(np.uint32), imgs[0].view(np.uint32))
+    assert np.isfinite(imgs[0]).all() and imgs[0].mean() > 0.01
+
+
 def test_output_stage_on_device():
     """Fused tonemap + sRGB + 8-bit conversion kernel vs the reference's bytes. expf/powf may differ from glibc in the last
     ulp, which can move a value across a truncation boundary: at most one code value, in a vanishing fraction of bytes."""

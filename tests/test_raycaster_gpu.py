@@ -45,6 +45,42 @@ def test_golden_closest_any_visible(name):
     assert np.array_equal(r.visible(c["org"][:512], p1[:512]).astype(np.uint8), c["visible"])
 
 
+@pytest.mark.parametrize("name", ["raycast_grid37", "raycast_multimesh"])
+def test_ray_levels_on_device(name):
+    """rb_raycaster_ray_levels: visited boxes / depths / hit of single rays from the device tree equal the oracle's
+    getRayLevels record for record (and the reference's own visualisation through the golden file), on the reference
+    tree; on an LBVH tree the hit equals that tree's intersects() and the visit starts at the roots."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ray_levels.npz"))
+    c = load_case(name)
+    r = product_from_case(c)
+    o = oracle_from_meshes(case_meshes(c))
+    at = 0
+    for k, i in enumerate(g[name + "_rays"]):
+        boxes, depths, total, hit = r.rayLevels(c["org"][i], c["dirs"][i], float(c["mini"]), float(c["maxi"]))
+        ids, od, ob, ototal, ohit = o.ray_levels(c["org"][i], c["dirs"][i], float(c["mini"]), float(c["maxi"]))
+        assert total == ototal and np.array_equal(depths, od) and np.array_equal(boxes.view(np.uint32), ob.view(np.uint32))
+        order = np.argsort(depths, kind="stable")
+        want = g[name + "_boxes"][at:at + total]
+        at += total
+        assert np.array_equal(boxes[order].view(np.uint32), want.view(np.uint32))
+        assert np.array_equal(np.bincount(depths, minlength=64), g[name + "_counts"][k])
+        oh = np.array([ohit])
+        assert_hits_equal(np.array([hit]), oh["hit"], oh["dist"], oh["u"], oh["v"], oh["w"], oh["localId"], oh["meshId"], "ray %d" % i)
+        assert int(hit["internalId"]) == int(ohit["internalId"]) or not ohit["hit"]
+    # truncated capture still reports the full count
+    i = int(g[name + "_rays"][1])
+    boxes, depths, total, _ = r.rayLevels(c["org"][i], c["dirs"][i], capacity=2)
+    assert boxes.shape[0] == min(2, total) and total == o.ray_levels(c["org"][i], c["dirs"][i])[3]
+    # LBVH tree of the same geometry
+    l = product_from_case(c, rb.BUILD_LBVH)
+    for i in g[name + "_rays"][:8]:
+        boxes, depths, total, hit = l.rayLevels(c["org"][i], c["dirs"][i])
+        single = l.intersects(c["org"][i], c["dirs"][i])
+        assert bool(hit["hit"]) == bool(single["hit"]) and hit["dist"] == single["dist"] and hit["internalId"] == single["internalId"]
+        assert total == 0 or depths[0] == 0
+
+
 def test_box_kat_on_device():
     c = load_case("box_kat")
     out = np.zeros(c["org"].shape[0], np.uint8)
