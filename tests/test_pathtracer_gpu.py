@@ -214,6 +214,13 @@ def test_batches_and_lanes_do_not_change_the_image(monkeypatch):
     for img in imgs[1:]:
         assert np.array_equal(img.view(np.uint32), imgs[0].view(np.uint32))
     assert np.isfinite(imgs[0]).all() and imgs[0].mean() > 0.01
+    # More samples per pixel than paths per batch: a pixel's samples are split over several batches, which then run on one
+    # lane in sample order (same per-pixel summation order is not guaranteed across chunkings: compare to fp32 rounding).
+    monkeypatch.setenv("RB_PT_LANES", "2")
+    whole, _ = gpu_render(desc, cam, 12, 10, 2048, 4, seed=5)
+    chunked, pt = gpu_render(desc, cam, 12, 10, 2048, 4, seed=5, max_paths=1024)
+    assert pt.stats()["samples"] == 12 * 10 * 2048
+    np.testing.assert_allclose(chunked, whole, rtol=2e-5, atol=1e-6)
 
 
 def test_output_stage_on_device():
