@@ -524,6 +524,7 @@ extern "C" rb_status rb_pathtracer_create(rb_scene * scene, rb_pathtracer ** out
 	if(!scene || !out) return rb_fail(RB_ERR_INVALID, "rb_pathtracer_create: null argument");
 	RB_REQUIRE_DEVICE();
 	if(!scene->committed) return rb_fail(RB_ERR_INVALID, "rb_pathtracer_create: call rb_scene_commit first");
+	if(cudaSetDevice(scene->raycaster->device) != cudaSuccess) return rb_fail(RB_ERR_CUDA, "rb_pathtracer_create: cannot select device %d", scene->raycaster->device);
 	rb_pathtracer * pt = new rb_pathtracer();
 	pt->scene		   = scene;
 	cudaDeviceGetAttribute(&pt->sms, cudaDevAttrMultiProcessorCount, scene->raycaster->device);

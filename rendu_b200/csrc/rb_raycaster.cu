@@ -722,7 +722,7 @@ extern "C" rb_status rb_raycaster_count_work_device(const rb_raycaster * rc, con
 	if(nrays) {
 		const size_t smem	= rb_trace_smem_bytes(rc, RB_TRACE_BLOCK);
 		const unsigned grid = unsigned((nrays + RB_TRACE_BLOCK - 1) / RB_TRACE_BLOCK);
-		const bool ordered	= rc->traceMode == RB_TRACE_ORDERED;
+		const bool ordered	= any_hit || rc->traceMode == RB_TRACE_ORDERED; // the order rb_launch_trace uses
 #define RB_LAUNCH_COUNT(A, O)                                                                                   \
 	do {                                                                                                        \
 		st = rb_prepare_kernel(rb_k_count<A, O>, smem);                                                         \
