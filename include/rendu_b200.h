@@ -81,7 +81,10 @@ RB_API const char * rb_last_error(void);
 RB_API const char * rb_version(void);
 /* Number of visible CUDA devices (0 when none, never an error). */
 RB_API int rb_device_count(void);
-/* Select the CUDA device used by handles created afterwards on this host thread (default: current device). */
+/* Select the CUDA device used by handles created afterwards on this host thread (default: current device).
+ * A handle stays bound to the device its hierarchy / scene was uploaded to; every later call on it makes that device
+ * current for the calling thread (as cudaSetDevice would) — device pointers and streams passed to the *_device
+ * entry points must belong to it. One process per GPU (the multi-GPU model of this library) never notices. */
 RB_API rb_status rb_set_device(int device);
 
 /* ------------------------------------------------------------------------------------------------ raycaster
