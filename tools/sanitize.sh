@@ -1,0 +1,10 @@
+#!/bin/bash
+# compute-sanitizer passes over small product runs (GPU box). Output: gpurun_out/sanitize_*.log
+mkdir -p gpurun_out
+run() { name=$1; shift; timeout 600 compute-sanitizer --tool "$TOOL" --error-exitcode 9 --print-limit 20 "$@" > gpurun_out/sanitize_${TOOL}_${name}.log 2>&1; echo "$TOOL $name rc=$? $(grep -c 'ERROR SUMMARY' gpurun_out/sanitize_${TOOL}_${name}.log) $(grep 'ERROR SUMMARY' gpurun_out/sanitize_${TOOL}_${name}.log | tail -1)"; }
+for TOOL in memcheck racecheck; do
+run smoke python -c "import __graft_entry__ as g; g.smoke()"
+run golden python -m pytest tests/test_raycaster_gpu.py -q -x -k "golden or ray_levels or many_roots or single_ray"
+run lbvh python -m pytest tests/test_lbvh_gpu.py -q -x -k "multi_mesh or refit"
+run pt python -m pytest tests/test_pathtracer_gpu.py -q -x -k "path_for_path or output_stage or seed_determinism"
+done
