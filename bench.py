@@ -623,10 +623,12 @@ def run_explore(args):
     d_co, d_cd = to(co), to(cd)
     variants = [("simple", {"RB_PERSISTENT": "0", "RB_LEAF_VOTES": "0", "RB_DUAL": "0"}, rb.TRACE_EXACT),
                 ("persistent_t20", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "20", "RB_LEAF_VOTES": "0", "RB_DUAL": "0"}, rb.TRACE_EXACT)]
-    for votes, thr in ((2, 20), (4, 20), (6, 20), (8, 20), (12, 20), (16, 20), (4, 12), (4, 16), (4, 24), (4, 28), (8, 16), (8, 24), (12, 24), (12, 28)):
-        variants.append(("phased_v%d_t%d" % (votes, thr), {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": str(thr), "RB_LEAF_VOTES": str(votes), "RB_DUAL": "0"}, rb.TRACE_EXACT))
+    for votes, thr, steps in ((6, 12, 6), (6, 8, 6), (6, 10, 6), (6, 14, 6), (4, 8, 4), (4, 10, 6), (5, 12, 5), (8, 12, 6), (6, 12, 5), (6, 12, 8), (3, 12, 6), (6, 4, 6)):
+        variants.append(("phased_v%d_t%d_s%d" % (votes, thr, steps), {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": str(thr), "RB_LEAF_VOTES": str(votes), "RB_NODE_STEPS": str(steps), "RB_DUAL": "0"}, rb.TRACE_EXACT))
     variants.append(("dual_v24_r16", {"RB_PERSISTENT": "1", "RB_DUAL": "1", "RB_LEAF_VOTES": "24", "RB_DUAL_REFILL": "16"}, rb.TRACE_EXACT))
-    variants.append(("ordered_phased_v4_t20", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "20", "RB_LEAF_VOTES": "4", "RB_DUAL": "0"}, rb.TRACE_ORDERED))
+    variants.append(("ordered_phased_v8_t20_s2", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "20", "RB_LEAF_VOTES": "8", "RB_NODE_STEPS": "2", "RB_DUAL": "0"}, rb.TRACE_ORDERED))
+    variants.append(("ordered_phased_v6_t12_s6", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "12", "RB_LEAF_VOTES": "6", "RB_NODE_STEPS": "6", "RB_DUAL": "0"}, rb.TRACE_ORDERED))
+    variants.append(("ordered_phased_v6_t12_s3", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "12", "RB_LEAF_VOTES": "6", "RB_NODE_STEPS": "3", "RB_DUAL": "0"}, rb.TRACE_ORDERED))
     variants.append(("ordered_persistent_t20", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "20", "RB_LEAF_VOTES": "0", "RB_DUAL": "0"}, rb.TRACE_ORDERED))
     base, d_io, d_id, results = None, None, None, {}
     for name, env, mode in variants:

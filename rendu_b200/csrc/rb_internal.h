@@ -68,10 +68,11 @@ struct rb_raycaster {
 
 	int traceMode = RB_TRACE_EXACT;
 	bool persistent	   = true; // persistent threads + warp work queue (false: one ray per thread)
-	int leafVotes	   = 8;	   // > 0: phase-voting scheduler, leaf phase runs once this many lanes wait for it (0: off)
+	int leafVotes	   = 6;	   // > 0: phase-voting scheduler, leaf phase runs once this many lanes wait for it (0: off)
+	int nodeSteps	   = 6;	   // phase-voting scheduler: node steps per vote
 	bool dual		   = false; // two rays per lane (rb_k_trace_dual)
 	int dualRefill	   = 16;   // dual: refill once this many of a warp's 64 slots are free
-	int fetchThreshold = 20;   // refill a warp from the queue when fewer lanes than this are still traversing
+	int fetchThreshold = 12;   // refill a warp from the queue when fewer lanes than this are still traversing
 	mutable std::atomic<uint64_t> launches{0};
 };
 

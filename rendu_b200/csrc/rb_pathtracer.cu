@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_raygen(RbFrame f, RbBatch
 // ------------------------------------------------------------------------------------------------ closest-hit wavefront
 // `_raycaster.intersects(rayPos, rayDir)` with the reference's default bounds (PathTracer.cpp:204, Raycaster.hpp:65).
 template<bool ORDERED>
-__global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_trace(RbDeviceBvh bvh, RbPathBuffers pb, const uint32_t * __restrict__ queue, uint32_t did, int threshold, int leafVotes, unsigned long long * __restrict__ stats) {
+__global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_trace(RbDeviceBvh bvh, RbPathBuffers pb, const uint32_t * __restrict__ queue, uint32_t did, int threshold, int leafVotes, int nodeSteps, unsigned long long * __restrict__ stats) {
 	extern __shared__ int s_stack[];
 	const RbStack st		= rb_make_stack(s_stack + threadIdx.x, blockDim.x);
 	const unsigned int lane = threadIdx.x & 31u;
@@ -153,25 +153,30 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_trace(RbDeviceBvh bvh, Rb
 				exhausted = (base + (unsigned int)nIdle) >= n;
 			}
 		}
-		if(!__any_sync(0xffffffffu, active)) break;
+		unsigned int activeM = __ballot_sync(0xffffffffu, active);
+		if(activeM == 0u) break;
 		bool more;
 		do {
-			// Phase vote (see rb_k_trace_phased): leaf phase once `leafVotes` lanes wait for it, node phase otherwise.
+			// Phase vote (see rb_k_trace_phased): leaf phase once `leafVotes` lanes wait for it, otherwise up to
+			// `nodeSteps` node steps.
 			const bool wantsLeaf	 = active && rb_wants_leaf(T);
 			const unsigned int leafM = __ballot_sync(0xffffffffu, wantsLeaf);
-			const unsigned int nodeM = __ballot_sync(0xffffffffu, active && !wantsLeaf);
+			const unsigned int nodeM = activeM & ~leafM;
 			bool finished = false;
 			if(__popc(leafM) >= leafVotes || nodeM == 0u) {
 				if(wantsLeaf) finished = rb_phase_leaf<false, false>(T, bvh, ray, nullptr);
-			} else {
-				if(active && !wantsLeaf) finished = rb_phase_node<false, ORDERED>(T, bvh, ray, st, nullptr);
+			} else if(active && !wantsLeaf) {
+				for(int k = 0; k < nodeSteps; ++k) {
+					finished = rb_phase_node<false, ORDERED>(T, bvh, ray, st, nullptr);
+					if(finished || rb_wants_leaf(T)) break;
+				}
 			}
 			if(finished) {
 				pb.hit[slot] = make_float4(T.best.t, T.best.u, T.best.v, __int_as_float(T.best.tri));
 				active = false;
 			}
-			const int nActive = __popc(__ballot_sync(0xffffffffu, active));
-			more = exhausted ? (nActive > 0) : (nActive >= threshold);
+			activeM = __ballot_sync(0xffffffffu, active);
+			more	= exhausted ? (activeM != 0u) : (__popc(activeM) >= threshold);
 		} while(more);
 	}
 }
@@ -317,7 +322,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK, RB_PT_SHADE_MIN_BLOCKS) rb_k_pt_s
 // alpha < 0.01. When no object of the scene is masked the walk degenerates to "is there any hit", so the any-hit
 // traversal (identical accept/reject decisions, early exit) is used instead (MASKED = false).
 template<bool MASKED, bool ORDERED>
-__global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shadow(RbDeviceBvh bvh, RbPathBuffers pb, RbSceneDev sc, uint32_t did, int threshold, unsigned long long * __restrict__ stats) {
+__global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shadow(RbDeviceBvh bvh, RbPathBuffers pb, RbSceneDev sc, uint32_t did, int threshold, int leafVotes, int nodeSteps, unsigned long long * __restrict__ stats) {
 	extern __shared__ int s_stack[];
 	const RbStack st		= rb_make_stack(s_stack + threadIdx.x, blockDim.x);
 	const unsigned int lane = threadIdx.x & 31u;
@@ -364,48 +369,60 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shadow(RbDeviceBvh bvh, R
 				exhausted = (base + (unsigned int)nIdle) >= n;
 			}
 		}
-		if(!__any_sync(0xffffffffu, active)) break;
+		unsigned int activeM = __ballot_sync(0xffffffffu, active);
+		if(activeM == 0u) break;
 		bool more;
 		do {
-			if(active) {
-				if(rb_step<!MASKED, false, ORDERED>(T, bvh, ray, st, nullptr)) {
-					bool visible = false, finished = true;
-					if(T.best.tri < 0) {
-						visible = true;
-					} else if(MASKED) {
-						const uint4 ta	   = sc.triAttr[T.best.tri];
-						const RbObject obj = sc.objects[ta.w];
-						if((obj.flags & RB_OBJ_MASKED) && (obj.flags & RB_OBJ_USE_UV)) {
-							float lu, lv;
-							rb_fetch_uv(sc, ta, T.best.u, T.best.v, lu, lv);
-							const float alpha = rb_image_rgbal(sc, obj.texAlbedo, lu, lv).w;
-							if(alpha < 0.01f) {
-								// Transparent texel: shift to the hit, shorten the segment, cast again (:149-151).
-								maxDist = maxDist - T.best.t;
-								lpos	= lpos + T.best.t * dir;
-								if(maxDist > 0.0f) {
-									ray = rb_make_ray(lpos, dir);
-									rb_traversal_init(T, bvh, 0.001f, maxDist, st);
-									finished = false;
-									++queries;
-								} else {
-									visible = true;
-								}
+			// Same phase vote as the closest-hit wavefront.
+			const bool wantsLeaf	 = active && rb_wants_leaf(T);
+			const unsigned int leafM = __ballot_sync(0xffffffffu, wantsLeaf);
+			const unsigned int nodeM = activeM & ~leafM;
+			bool done = false;
+			if(__popc(leafM) >= leafVotes || nodeM == 0u) {
+				if(wantsLeaf) done = rb_phase_leaf<!MASKED, false>(T, bvh, ray, nullptr);
+			} else if(active && !wantsLeaf) {
+				for(int k = 0; k < nodeSteps; ++k) {
+					done = rb_phase_node<false, ORDERED>(T, bvh, ray, st, nullptr);
+					if(done || rb_wants_leaf(T)) break;
+				}
+			}
+			if(done) {
+				bool visible = false, finished = true;
+				if(T.best.tri < 0) {
+					visible = true;
+				} else if(MASKED) {
+					const uint4 ta	   = sc.triAttr[T.best.tri];
+					const RbObject obj = sc.objects[ta.w];
+					if((obj.flags & RB_OBJ_MASKED) && (obj.flags & RB_OBJ_USE_UV)) {
+						float lu, lv;
+						rb_fetch_uv(sc, ta, T.best.u, T.best.v, lu, lv);
+						const float alpha = rb_image_rgbal(sc, obj.texAlbedo, lu, lv).w;
+						if(alpha < 0.01f) {
+							// Transparent texel: shift to the hit, shorten the segment, cast again (:149-151).
+							maxDist = maxDist - T.best.t;
+							lpos	= lpos + T.best.t * dir;
+							if(maxDist > 0.0f) {
+								ray = rb_make_ray(lpos, dir);
+								rb_traversal_init(T, bvh, 0.001f, maxDist, st);
+								finished = false;
+								++queries;
+							} else {
+								visible = true;
 							}
 						}
 					}
-					if(finished) {
-						if(visible) {
-							float4 cl = pb.color[slot];
-							cl.x += contrib.x; cl.y += contrib.y; cl.z += contrib.z;
-							pb.color[slot] = cl;
-						}
-						active = false;
+				}
+				if(finished) {
+					if(visible) {
+						float4 cl = pb.color[slot];
+						cl.x += contrib.x; cl.y += contrib.y; cl.z += contrib.z;
+						pb.color[slot] = cl;
 					}
+					active = false;
 				}
 			}
-			const int nActive = __popc(__ballot_sync(0xffffffffu, active));
-			more = exhausted ? (nActive > 0) : (nActive >= threshold);
+			activeM = __ballot_sync(0xffffffffu, active);
+			more	= exhausted ? (activeM != 0u) : (__popc(activeM) >= threshold);
 		} while(more);
 	}
 	if(stats) {
@@ -623,7 +640,9 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 	rb_scene * sc		 = pt->scene;
 	rb_raycaster * rc	 = sc->raycaster;
 	const bool ordered	 = opts ? (opts->trace_mode == RB_TRACE_ORDERED) : false;
-	const int threshold = rc->fetchThreshold;
+	// Wavefront queues are shorter and more varied than the raycaster's batches: a slightly earlier refill and fewer
+	// node steps per vote measured best (tools/pt_sweep.sh); RB_FETCH_THRESHOLD / RB_NODE_STEPS override both.
+	const int threshold = std::getenv("RB_FETCH_THRESHOLD") ? rc->fetchThreshold : 16;
 	RB_CUDA(cudaSetDevice(rc->device));
 	if(!(opts && opts->accumulate)) RB_CUDA(cudaMemsetAsync(d_sum, 0, size_t(width) * height * 3 * sizeof(float), s));
 	RB_CUDA(cudaMemsetAsync(pt->d_stats, 0, 4 * sizeof(unsigned long long), s));
@@ -667,6 +686,7 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 		st = rb_pt_grid(kShadow, smem, pt->sms, gridShadow);
 		if(st) return st;
 		const int votes = rc->leafVotes > 0 ? rc->leafVotes : 33;
+		const int steps = std::getenv("RB_NODE_STEPS") ? (rc->nodeSteps > 0 ? rc->nodeSteps : 1) : 4;
 
 		if(lanes > 1) {
 			RB_CUDA(cudaEventRecord(pt->fork, s));
@@ -688,11 +708,11 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 				rb_k_pt_raygen<<<gridFlat, RB_PT_BLOCK, 0, ls>>>(f, b, pb);
 				++launches;
 				for(uint32_t did = 0; did < depth; ++did) {
-					kTrace<<<gridTrace, RB_PT_BLOCK, smem, ls>>>(rc->dev, pb, pb.queue[did & 1u], did, threshold, votes, pt->d_stats);
+					kTrace<<<gridTrace, RB_PT_BLOCK, smem, ls>>>(rc->dev, pb, pb.queue[did & 1u], did, threshold, votes, steps, pt->d_stats);
 					rb_k_pt_shade<<<gridFlat, RB_PT_BLOCK, 0, ls>>>(f, b, pb, sc->dev, did, pt->d_stats);
 					launches += 2;
 					if(sc->dev.nLights > 0) {
-						kShadow<<<gridShadow, RB_PT_BLOCK, smem, ls>>>(rc->dev, pb, sc->dev, did, threshold, pt->d_stats);
+						kShadow<<<gridShadow, RB_PT_BLOCK, smem, ls>>>(rc->dev, pb, sc->dev, did, threshold, votes, steps, pt->d_stats);
 						++launches;
 					}
 				}

@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_persistent(RbDevice
 // the leaf phase once at least `leafVotes` lanes wait for it (or nobody wants a node), otherwise the node phase. Lanes
 // of the other kind idle for that iteration instead of the whole warp running at the pace of one lane's descent.
 template<bool ANY, bool ORDERED>
-__global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_phased(RbDeviceBvh bvh, const float * __restrict__ org, const float * __restrict__ dir, float mini, float maxi, unsigned int n, void * __restrict__ out, unsigned int * __restrict__ cursor, int threshold, int leafVotes) {
+__global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_phased(RbDeviceBvh bvh, const float * __restrict__ org, const float * __restrict__ dir, float mini, float maxi, unsigned int n, void * __restrict__ out, unsigned int * __restrict__ cursor, int threshold, int leafVotes, int nodeSteps) {
 	extern __shared__ int s_stack[];
 	const RbStack st		= rb_make_stack(s_stack + threadIdx.x, blockDim.x);
 	const unsigned int lane = threadIdx.x & 31u;
@@ -235,25 +235,32 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_phased(RbDeviceBvh 
 				exhausted = (base + (unsigned int)nIdle) >= n;
 			}
 		}
-		if(!__any_sync(0xffffffffu, active)) break;
+		unsigned int activeM = __ballot_sync(0xffffffffu, active);
+		if(activeM == 0u) break;
 		bool more;
 		do {
-			const bool wantsLeaf	  = active && rb_wants_leaf(T);
-			const unsigned int leafM  = __ballot_sync(0xffffffffu, wantsLeaf);
-			const unsigned int nodeM  = __ballot_sync(0xffffffffu, active && !wantsLeaf);
+			// One ballot per iteration: a live lane waits either for a leaf step or for a node step.
+			const bool wantsLeaf	 = active && rb_wants_leaf(T);
+			const unsigned int leafM = __ballot_sync(0xffffffffu, wantsLeaf);
+			const unsigned int nodeM = activeM & ~leafM;
 			bool finished = false;
 			if(__popc(leafM) >= leafVotes || nodeM == 0u) {
 				if(wantsLeaf) finished = rb_phase_leaf<ANY, false>(T, bvh, ray, nullptr);
-			} else {
-				if(active && !wantsLeaf) finished = rb_phase_node<false, ORDERED>(T, bvh, ray, st, nullptr);
+			} else if(active && !wantsLeaf) {
+				// Up to `nodeSteps` descents per vote: the vote, executed by all 32 lanes, costs about as much as a
+				// node step; a lane that reaches a leaf (or finishes) early sits out the remaining steps.
+				for(int k = 0; k < nodeSteps; ++k) {
+					finished = rb_phase_node<false, ORDERED>(T, bvh, ray, st, nullptr);
+					if(finished || rb_wants_leaf(T)) break;
+				}
 			}
 			if(finished) {
 				if(ANY) rb_store_any(static_cast<uint8_t *>(out), rayIdx, bvh, T.best);
 				else rb_store_hit(static_cast<rb_hit *>(out), rayIdx, bvh, T.best);
 				active = false;
 			}
-			const int nActive = __popc(__ballot_sync(0xffffffffu, active));
-			more = exhausted ? (nActive > 0) : (nActive >= threshold);
+			activeM = __ballot_sync(0xffffffffu, active);
+			more	= exhausted ? (activeM != 0u) : (__popc(activeM) >= threshold);
 		} while(more);
 	}
 }
@@ -452,6 +459,7 @@ extern "C" rb_status rb_raycaster_create(rb_raycaster ** out) {
 	if(const char * e = getenv("RB_PERSISTENT")) (*out)->persistent = atoi(e) != 0;
 	if(const char * e = getenv("RB_FETCH_THRESHOLD")) (*out)->fetchThreshold = atoi(e);
 	if(const char * e = getenv("RB_LEAF_VOTES")) (*out)->leafVotes = atoi(e);
+	if(const char * e = getenv("RB_NODE_STEPS")) (*out)->nodeSteps = atoi(e);
 	if(const char * e = getenv("RB_DUAL")) (*out)->dual = atoi(e) != 0;
 	if(const char * e = getenv("RB_DUAL_REFILL")) (*out)->dualRefill = atoi(e);
 	return RB_OK;
@@ -673,7 +681,7 @@ static rb_status rb_launch_trace(const rb_raycaster * rc, const float * d_origin
 	}
 	if(rc->persistent && rc->leafVotes > 0) {
 		auto kernel = ordered ? rb_k_trace_phased<ANY, true> : rb_k_trace_phased<ANY, false>;
-		return rb_launch_persistent<ANY>(rc, kernel, smem, 1, d_origins, d_directions, mini, maxi, nrays, d_out, s, rc->fetchThreshold, rc->leafVotes);
+		return rb_launch_persistent<ANY>(rc, kernel, smem, 1, d_origins, d_directions, mini, maxi, nrays, d_out, s, rc->fetchThreshold, rc->leafVotes, rc->nodeSteps > 0 ? rc->nodeSteps : 1);
 	}
 	if(rc->persistent) {
 		auto kernel = ordered ? rb_k_trace_persistent<ANY, true> : rb_k_trace_persistent<ANY, false>;
