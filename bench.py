@@ -623,7 +623,7 @@ def run_explore(args):
     d_co, d_cd = to(co), to(cd)
     variants = [("simple", {"RB_PERSISTENT": "0", "RB_LEAF_VOTES": "0", "RB_DUAL": "0"}, rb.TRACE_EXACT),
                 ("persistent_t20", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "20", "RB_LEAF_VOTES": "0", "RB_DUAL": "0"}, rb.TRACE_EXACT)]
-    for votes, thr, steps in ((6, 12, 6), (6, 8, 6), (6, 10, 6), (6, 14, 6), (4, 8, 4), (4, 10, 6), (5, 12, 5), (8, 12, 6), (6, 12, 5), (6, 12, 8), (3, 12, 6), (6, 4, 6)):
+    for votes, thr, steps in ((8, 20, 1), (8, 20, 2), (8, 20, 4), (6, 12, 6), (6, 16, 6), (4, 12, 4), (6, 8, 6), (6, 12, 12)):
         variants.append(("phased_v%d_t%d_s%d" % (votes, thr, steps), {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": str(thr), "RB_LEAF_VOTES": str(votes), "RB_NODE_STEPS": str(steps), "RB_DUAL": "0"}, rb.TRACE_EXACT))
     variants.append(("dual_v24_r16", {"RB_PERSISTENT": "1", "RB_DUAL": "1", "RB_LEAF_VOTES": "24", "RB_DUAL_REFILL": "16"}, rb.TRACE_EXACT))
     variants.append(("ordered_phased_v8_t20_s2", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "20", "RB_LEAF_VOTES": "8", "RB_NODE_STEPS": "2", "RB_DUAL": "0"}, rb.TRACE_ORDERED))

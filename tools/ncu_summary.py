@@ -50,7 +50,7 @@ def main(rep):
             cur["hdr"] = r
         elif cur is not None and r and r[0].startswith("0x"):
             cur["rows"].append(r)
-    for b in blocks[:2]:
+    for b in blocks[:1]:
         h = b["hdr"]
         iI, iT, iS, iSrc = h.index("Instructions Executed"), h.index("Thread Instructions Executed"), h.index("# Samples"), h.index("Source")
         tot_i = sum(int(r[iI]) for r in b["rows"]) or 1
