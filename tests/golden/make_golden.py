@@ -54,7 +54,7 @@ def edge_rays():
     return np.array(o, F), np.array(d, F)
 
 
-def raycast_case(name, meshes, nrand, seed, mini=1e-4, maxi=1e8):
+def raycast_case(name, meshes, nrand, seed, mini=1e-4, maxi=1e8, extra=None):
     r = ref.RefRaycaster()
     for pos, idx, model in meshes:
         r.add_mesh(pos, idx, model)
@@ -63,8 +63,8 @@ def raycast_case(name, meshes, nrand, seed, mini=1e-4, maxi=1e8):
     ro, rd = wl.random_rays(nrand, seed)
     co, cd = wl.coherent_rays(48)
     eo, ed = edge_rays()
-    org = np.concatenate([ro, co, eo]).astype(F)
-    dirs = np.concatenate([rd, cd, ed]).astype(F)
+    org = np.concatenate([ro, co, eo] + ([extra[0]] if extra else [])).astype(F)
+    dirs = np.concatenate([rd, cd, ed] + ([extra[1]] if extra else [])).astype(F)
     h = r.intersect(org, dirs, mini, maxi)
     any_hit, _ = r.intersect_any(org, dirs, mini, maxi)
     h2 = r.intersect(org, dirs, 0.05, 1.7)
@@ -84,13 +84,43 @@ def raycast_case(name, meshes, nrand, seed, mini=1e-4, maxi=1e8):
     print(name, "rays", org.shape[0], "hits", int(h["hit"].sum()), "nodes", dump["node_left"].size)
 
 
+def degenerate_meshes():
+    """Geometry that stresses ties and rejects: 40 copies of one triangle (equal centroids -> the nth_element fallback of
+    updateHierarchy, Raycaster.cpp:116-123, and exact distance ties), a grid with every triangle listed twice, zero-area /
+    collinear / sub-epsilon triangles between good ones, two coplanar overlapping quads."""
+    one = np.array([[-0.3, 0.8, -0.3], [0.4, 0.8, -0.2], [-0.1, 0.8, 0.5]], F)
+    m1 = (one, np.tile(np.array([0, 1, 2], np.uint32), 40), None)
+    p6, i6 = wl.displaced_grid(6)
+    m2 = (p6, np.concatenate([i6, i6]).astype(np.uint32), None)
+    v = np.array([[0, 0.5, 0], [0.5, 0.5, 0], [0, 0.5, 0.5], [0.25, 0.5, 0.25], [1e-7, 0.5, 0], [0, 0.5, 1e-7], [0.5, 0.5, 0.5], [-0.5, 0.5, -0.5], [0.5, 0.5, -0.5]], F)
+    i3 = np.array([0, 0, 1,  0, 3, 6,  0, 4, 5,  0, 1, 2,  1, 1, 1,  7, 8, 6,  0, 6, 3,  2, 1, 6,  7, 6, 2], np.uint32)
+    m3 = (v, i3, translate((0.0, -0.1, 0.0)))
+    q = np.array([[-0.8, 0.3, -0.8], [0.8, 0.3, -0.8], [0.8, 0.3, 0.8], [-0.8, 0.3, 0.8], [-0.4, 0.3, -0.4], [0.4, 0.3, -0.4], [0.4, 0.3, 0.4], [-0.4, 0.3, 0.4]], F)
+    m4 = (q, np.array([0, 1, 2, 0, 2, 3, 4, 5, 6, 4, 6, 7], np.uint32), None)
+    return [m1, m2, m3, m4]
+
+
+def degenerate_rays():
+    """Straight down onto the vertices and edge midpoints of the 6x6 grid and of the coplanar quads (shared edges: two or
+    more triangles at exactly the same distance), plus grazing rays inside the quads' plane."""
+    p6, _ = wl.displaced_grid(6)
+    o = [np.array([x, 2.0, z], F) for x, _, z in p6]
+    o += [np.array([(a[0] + b[0]) / 2, 2.0, (a[2] + b[2]) / 2], F) for a, b in zip(p6[:-1], p6[1:])]
+    o += [np.array([x, 2.0, z], F) for x in (-0.8, -0.4, 0.0, 0.4, 0.8) for z in (-0.8, -0.4, 0.0, 0.4, 0.8)]
+    d = [np.array([0, -1, 0], F)] * len(o)
+    o += [np.array([-2.0, 0.3, z], F) for z in (-0.8, -0.4, 0.0, 0.1)]
+    d += [np.array([1, 0, 0], F)] * 4
+    return np.array(o, F), np.array(d, F)
+
+
 def case_meshes():
     pos, idx = wl.displaced_grid(37)
     # Several meshes: transformed copies, a 2-triangle quad (its root is a leaf), a single triangle, overlapping geometry.
     p8, i8 = wl.displaced_grid(8)
     quad = (np.array([[-1, 0.6, -1], [1, 0.6, -1], [1, 0.6, 1], [-1, 0.6, 1]], F), np.array([0, 1, 2, 0, 2, 3], np.uint32))
     tri = (np.array([[0, 0.9, 0], [0.5, 0.9, 0], [0, 0.9, 0.5]], F), np.array([0, 1, 2], np.uint32))
-    return {"raycast_grid37": [(pos, idx, None)],
+    return {"raycast_degenerate": degenerate_meshes(),
+            "raycast_grid37": [(pos, idx, None)],
             "raycast_multimesh": [(p8, i8, None), (p8, i8, rot_scale(0.7, 0.5, (0.2, 0.4, -0.1))), (quad[0], quad[1], None),
                                   (tri[0], tri[1], translate((0.1, 0.0, 0.1))), (p8, i8, translate((0.0, 0.0, 0.0)))]}
 
@@ -106,6 +136,8 @@ def levels_goldens():
         r.build()
         case = np.load(os.path.join(OUT, name + ".npz"))
         pick = np.concatenate([np.arange(0, 3000, 250), np.arange(3000, 3000 + 48 * 48, 192), np.arange(3000 + 48 * 48, case["org"].shape[0], 7)])
+        if name == "raycast_degenerate":
+            pick = np.concatenate([pick, np.arange(case["org"].shape[0] - 60, case["org"].shape[0], 3)])
         counts_all, boxes_all, hits = [], [], []
         for i in pick:
             counts, boxes, hit = r.ray_levels(case["org"][i], case["dirs"][i], float(case["mini"]), float(case["maxi"]))
@@ -128,6 +160,7 @@ def main():
     cases = case_meshes()
     raycast_case("raycast_grid37", cases["raycast_grid37"], 3000, 7)
     raycast_case("raycast_multimesh", cases["raycast_multimesh"], 3000, 11)
+    raycast_case("raycast_degenerate", cases["raycast_degenerate"], 3000, 19, extra=degenerate_rays())
     # Box test KAT on the edge rays against assorted boxes.
     eo, ed = edge_rays()
     rng = np.random.RandomState(5)

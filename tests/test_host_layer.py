@@ -29,7 +29,7 @@ def test_record_layouts_match_reference_structs():
     assert rb.HIT_DTYPE.fields["localId"][1] == 24 and rb.NODE_DTYPE.fields["leaf"][1] == 40 and rb.TRI_DTYPE.fields["meshId"][1] == 56
 
 
-@pytest.mark.parametrize("name", ["raycast_grid37", "raycast_multimesh"])
+@pytest.mark.parametrize("name", ["raycast_grid37", "raycast_multimesh", "raycast_degenerate"])
 def test_host_builder_reproduces_reference_hierarchy(name):
     c = load_case(name)
     r = rb.Raycaster()

@@ -11,7 +11,7 @@ from rendu_b200 import workloads as wl
 from util import case_meshes, load_case
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = ["raycast_grid37", "raycast_multimesh"]
+CASES = ["raycast_grid37", "raycast_multimesh", "raycast_degenerate"]
 
 
 def build_oracle(case):

@@ -30,7 +30,7 @@ def oracle_from_meshes(meshes):
     return o
 
 
-@pytest.mark.parametrize("name", ["raycast_grid37", "raycast_multimesh"])
+@pytest.mark.parametrize("name", ["raycast_grid37", "raycast_multimesh", "raycast_degenerate"])
 def test_golden_closest_any_visible(name):
     c = load_case(name)
     r = product_from_case(c)
@@ -45,7 +45,7 @@ def test_golden_closest_any_visible(name):
     assert np.array_equal(r.visible(c["org"][:512], p1[:512]).astype(np.uint8), c["visible"])
 
 
-@pytest.mark.parametrize("name", ["raycast_grid37", "raycast_multimesh"])
+@pytest.mark.parametrize("name", ["raycast_grid37", "raycast_multimesh", "raycast_degenerate"])
 def test_ray_levels_on_device(name):
     """rb_raycaster_ray_levels: visited boxes / depths / hit of single rays from the device tree equal the oracle's
     getRayLevels record for record (and the reference's own visualisation through the golden file), on the reference
