@@ -50,6 +50,29 @@ def test_lbvh_hits_match_reference_tree(n):
     assert s["nodes"] == 2 * s["tris"] - 1 and s["meshes"] == 1 and s["depth"] >= 1
 
 
+def test_lbvh_degenerate_geometry():
+    """Equal Morton codes (40 copies of one triangle, every grid triangle listed twice), zero-area triangles, coplanar
+    overlaps: the build must terminate with a proper tree, hit/miss must equal the reference's for every ray, and wherever
+    the winning triangle differs (duplicates: any copy may win) the distance must be the same."""
+    from util import case_meshes, load_case
+    c = load_case("raycast_degenerate")
+    r = rb.Raycaster()
+    for pos, idx, model in case_meshes(c):
+        r.addMesh(pos, idx, model)
+    r.updateHierarchy(rb.BUILD_LBVH)
+    s = r.sizes()
+    assert s["tris"] == c["tri_local"].size and s["depth"] >= 1
+    h = r.intersects(c["org"], c["dirs"], float(c["mini"]), float(c["maxi"]))
+    assert np.array_equal(h["hit"], c["hit"])
+    hit = c["hit"] == 1
+    assert np.allclose(h["dist"][hit], c["dist"][hit], rtol=1e-5, atol=0)
+    same = hit & (h["localId"] == c["local_id"]) & (h["meshId"] == c["mesh_id"])
+    assert np.array_equal(h["dist"][same].view(np.uint32), c["dist"][same].view(np.uint32))
+    assert np.array_equal(r.intersectsAny(c["org"], c["dirs"], float(c["mini"]), float(c["maxi"])).astype(np.uint8), c["any"])
+    nodes, tris, verts = r.download_bvh()
+    assert nodes.size == s["nodes"] and tris.size == s["tris"]
+
+
 def test_lbvh_multi_mesh_single_triangle_and_download_roundtrip():
     rng = np.random.RandomState(3)
     meshes = []
