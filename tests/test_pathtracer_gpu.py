@@ -181,6 +181,32 @@ def test_seed_determinism_tiles_and_sample_split():
     np.testing.assert_allclose(sum(parts), a, rtol=0, atol=2e-6)
 
 
+@pytest.mark.parametrize("w,h,spp,depth", [(1, 1, 1, 1), (3, 2, 2, 1), (5, 7, 1, 3), (2, 9, 8, 2), (33, 1, 4, 5)])
+def test_tiny_frames_match_oracle(w, h, spp, depth):
+    """Ragged / minimal inputs: single pixel, single sample (1x1 stratification grid), depth 1 (direct light only), odd
+    sizes that do not fill a warp or a tile band."""
+    desc, cam, _ = golden_scene("cornellbox")
+    gpu, pt = gpu_render(desc, cam, w, h, spp, depth, seed=4)
+    cpu, _ = orc.OracleScene(desc).render(cam, w, h, spp, depth, seed=4, rng="counter", threads=1)
+    assert np.isfinite(gpu).all() and pt.stats()["samples"] == w * h * spp
+    np.testing.assert_allclose(gpu, cpu, rtol=2e-3, atol=2e-3)
+
+
+def test_empty_shares_and_zero_depth():
+    """A rank whose tile share is empty (more ranks than 8-row bands) or whose sample share is empty (more ranks than
+    samples) renders nothing and leaves the image as it was; depth 0 traces nothing, as the reference's bounce loop
+    `for(did = 0; did < depth; ...)` (PathTracer.cpp:202) does."""
+    desc, cam, _ = golden_scene("cornellbox")
+    img = np.full((6, 16, 3), 0.25, np.float32)
+    out, pt = gpu_render(desc, cam, 16, 6, 4, 3, seed=2, image=img.copy(), tile=(8, 1, 4))  # 6 rows: only band 0 exists
+    assert np.array_equal(out, img) and pt.stats()["samples"] == 0
+    out, pt = gpu_render(desc, cam, 16, 6, 2, 3, seed=2, image=img.copy(), samples=(3, 4))  # 2 samples, rank 3 of 4
+    np.testing.assert_allclose(out, img / 2, rtol=0, atol=1e-7)  # (pixels + 0) / samples
+    assert pt.stats()["rays_closest"] == 0
+    out, pt = gpu_render(desc, cam, 16, 6, 4, 0, seed=2)
+    assert (out == 0).all() and pt.stats()["rays_closest"] == 0
+
+
 def test_image_contract_components_accumulation_and_rounding():
     desc, cam, _ = golden_scene("cornellbox-emissive")
     base, _ = gpu_render(desc, cam, 32, 32, 16, 4, seed=1)
