@@ -608,6 +608,45 @@ def run_lbvh(args):
     print(json.dumps({"workload": "C5 LBVH build + refit + trace", **out}), flush=True)
 
 
+def run_c1(args):
+    """BASELINE configs[0]: the reference's own CPU-runnable case — bundled scenes at 256x256, 8 spp, depth 5, scene
+    camera — rendered through rb_pathtracer_render (host image in, host image out) next to the reference's own
+    PathTracer::render on the box's host cores. The scenes come from the committed fixtures (tests/golden/scene_*.npz,
+    flattened from the reference's loader by tests/golden/make_golden.py); the reference loads its own .scene files."""
+    import rendu_b200 as rb  # noqa: F401
+    from rendu_b200 import pathtracer as rpt
+    out = {"workload": "C1 bundled scenes 256x256, 8 spp, depth 5", "scenes": {}}
+    for name in ("cornellbox", "cornellbox-emissive"):
+        desc = rpt.load_scene(os.path.join(ROOT, "tests", "golden", "scene_%s.npz" % name))
+        g = np.load(os.path.join(ROOT, "tests", "golden", "render_%s.npz" % name))
+        cam = dict(eye=g["cam_eye"], corner=g["cam_corner"], dx=g["cam_dx"], dy=g["cam_dy"])
+        t0 = time.perf_counter()
+        pt = rpt.PathTracer(rpt.Scene(desc))
+        setup_s = time.perf_counter() - t0
+        img = np.zeros((256, 256, 3), np.float32)
+        times = []
+        for k in range(13):
+            img[:] = 0
+            t0 = time.perf_counter()
+            pt.render(cam, 8, 5, img, rpt.make_opts(seed=1))
+            times.append(time.perf_counter() - t0)
+        st = pt.stats()
+        rec = {"gpu_render_ms": 1e3 * float(np.median(times[3:])), "gpu_scene_setup_ms": 1e3 * setup_s, "rays": st["rays_closest"] + st["rays_shadow"],
+               "kernel_launches": st["kernel_launches"], "image_mean": float(img.mean())}
+        if not args.no_cpu:
+            from oracle import ref
+            if ref.available():
+                ref.add_default_resources()
+                rs = ref.RefScene(name)
+                ref.seed(1)
+                _, dt, rays = rs.render(256, 256, 8, 5)
+                _, dt2, _ = rs.render(256, 256, 8, 5)
+                rec.update(reference_render_ms=1e3 * min(dt, dt2), reference_rays=rays, reference_threads=ref.threads_default())
+                rec["speedup"] = rec["reference_render_ms"] / rec["gpu_render_ms"]
+        out["scenes"][name] = rec
+    print(json.dumps(out), flush=True)
+
+
 def run_explore(args):
     """Developer aid (not a bench line): times scheduler / mode variants of the traversal kernels on the C2 sets and
     checks on the device that every variant returns the same hit records as the first one."""
@@ -687,7 +726,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--explore", action="store_true", help="developer aid: time kernel variants, no bench line")
-    ap.add_argument("--workload", default="raycast", choices=["raycast", "pathtrace", "lbvh"], help="raycast = BASELINE configs[1] (default); pathtrace = configs[2]/[3]")
+    ap.add_argument("--workload", default="raycast", choices=["raycast", "pathtrace", "lbvh", "c1"], help="raycast = BASELINE configs[1] (default); pathtrace = configs[2]/[3]")
     ap.add_argument("--spp", type=int, default=256)
     ap.add_argument("--max-paths", type=int, default=0, help="pathtrace: paths in flight per wavefront batch (0 = library default)")
     ap.add_argument("--split", default="tile", choices=["tile", "sample"])
@@ -700,6 +739,8 @@ def main():
         run_pathtrace(args)
     elif args.workload == "lbvh" and args.impl != "reference":
         run_lbvh(args)
+    elif args.workload == "c1" and args.impl != "reference":
+        run_c1(args)
     elif args.impl == "reference":
         run_reference(args)
     else:
