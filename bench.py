@@ -329,6 +329,20 @@ def run_gpu(args):
         return src.numel() * src.element_size() / (time.perf_counter() - t0_) / 1e9
 
     link = {"h2d_gbs": copy_gbs(d_hit_c, h_hits), "d2h_gbs": copy_gbs(h_hits, d_hit_c)}
+    # Both directions at once (what the pipelined e2e step asks of the link): a second pinned buffer goes up on one
+    # stream while the hit records come down on another.
+    h_up = torch.empty(n * 48, dtype=torch.uint8).pin_memory()
+    d_up = torch.empty(n * 48, dtype=torch.uint8, device=dev)
+    s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    t0_ = time.perf_counter()
+    with torch.cuda.stream(s_up):
+        d_up.copy_(h_up, non_blocking=True)
+    with torch.cuda.stream(s_dn):
+        h_hits.copy_(d_hit_c, non_blocking=True)
+    torch.cuda.synchronize()
+    link["duplex_gbs_each_way"] = n * 48 / (time.perf_counter() - t0_) / 1e9
+    del h_up, d_up
     e2e_steps = max(2, min(args.steps, 5))
     e2e_step()
     barrier()
