@@ -56,7 +56,8 @@ _lib = None
 
 
 def lib_path():
-    return os.path.join(_HERE, _LIB_NAME)
+    """In-tree library; RENDU_B200_LIB names another build of the same ABI (kernel experiments)."""
+    return os.environ.get("RENDU_B200_LIB") or os.path.join(_HERE, _LIB_NAME)
 
 
 def lib():
