@@ -546,12 +546,12 @@ def run_pathtrace(args):
 
 def cpu_pathtrace_baseline(desc):
     """The C oracle (a port: the reference needs its own Scene object, which cannot hold this synthetic scene) on a
-    bounded sample of the frame: 480x270 at 8 spp, all host threads, scaled linearly (the loop is linear in pixels x spp)."""
+    bounded sample of the frame: 960x540 at 64 spp (about 10 s), all host threads, scaled linearly (the loop is linear in pixels x spp)."""
     from oracle import oracle as orc
     from rendu_b200 import workloads as wl
     threads = max((os.cpu_count() or 2) - 1, 1)
     sc = orc.OracleScene(desc)
-    w, h, s = 480, 270, 8
+    w, h, s = 960, 540, 64
     t0 = time.perf_counter()
     _, rays = sc.render(wl.cornell_camera(PT_W / PT_H), w, h, s, PT_DEPTH, seed=1, rng="counter", threads=threads)
     dt = time.perf_counter() - t0
