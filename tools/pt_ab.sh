@@ -7,5 +7,5 @@ for l in sys.stdin:
         d=json.loads(l); print(d['value'], d['ms_per_step'])"; }
 for i in 1 2; do
 run A=1
-run RENDU_B200_LIB=$PWD/rendu_b200/librendu_b200_mb8.so
+run RENDU_B200_LIB=$PWD/rendu_b200/librendu_b200_variant.so
 done
