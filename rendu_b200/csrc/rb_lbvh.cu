@@ -147,10 +147,11 @@ static rb_status rb_radix_sort(uint64_t * keys, uint32_t * vals, uint32_t n, int
 	const uint32_t tableN  = 256u * nblocks;
 	const uint32_t ntiles  = (tableN + RB_SCAN_TILE - 1) / RB_SCAN_TILE;
 	RbSortScratch sc;
-	RB_CUDA(cudaMalloc(&sc.keysAlt, size_t(n) * sizeof(uint64_t)));
-	RB_CUDA(cudaMalloc(&sc.valsAlt, size_t(n) * sizeof(uint32_t)));
-	RB_CUDA(cudaMalloc(&sc.table, size_t(tableN) * sizeof(uint32_t)));
-	RB_CUDA(cudaMalloc(&sc.sums, size_t(ntiles) * sizeof(uint32_t)));
+	// Stream-ordered scratch: no device-wide synchronisation, and the pool hands the memory back to the next build.
+	RB_CUDA(cudaMallocAsync(&sc.keysAlt, size_t(n) * sizeof(uint64_t), s));
+	RB_CUDA(cudaMallocAsync(&sc.valsAlt, size_t(n) * sizeof(uint32_t), s));
+	RB_CUDA(cudaMallocAsync(&sc.table, size_t(tableN) * sizeof(uint32_t), s));
+	RB_CUDA(cudaMallocAsync(&sc.sums, size_t(ntiles) * sizeof(uint32_t), s));
 	uint64_t *kin = keys, *kout = sc.keysAlt;
 	uint32_t *vin = vals, *vout = sc.valsAlt;
 	int passes = (bits + 7) / 8;
@@ -166,11 +167,11 @@ static rb_status rb_radix_sort(uint64_t * keys, uint32_t * vals, uint32_t n, int
 		std::swap(vin, vout);
 		*launches += 5;
 	}
-	cudaError_t e = cudaStreamSynchronize(s);
-	cudaFree(sc.keysAlt);
-	cudaFree(sc.valsAlt);
-	cudaFree(sc.table);
-	cudaFree(sc.sums);
+	cudaError_t e = cudaGetLastError();
+	cudaFreeAsync(sc.keysAlt, s);
+	cudaFreeAsync(sc.valsAlt, s);
+	cudaFreeAsync(sc.table, s);
+	cudaFreeAsync(sc.sums, s);
 	if(e != cudaSuccess) return rb_fail(RB_ERR_CUDA, "radix sort failed: %s", cudaGetErrorString(e));
 	return RB_OK;
 }
@@ -193,13 +194,30 @@ RB_D void rb_tri_box(const float * __restrict__ verts, uint32_t a, uint32_t b, u
 }
 
 __global__ void rb_k_lbvh_bounds(const float * __restrict__ verts, const uint32_t * __restrict__ triVerts, uint32_t ntris, unsigned int * __restrict__ bounds6) {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if(i >= ntris) return;
-	V3 lo, hi;
-	rb_tri_box(verts, triVerts[3 * i], triVerts[3 * i + 1], triVerts[3 * i + 2], lo, hi);
-	const V3 c = 0.5f * (lo + hi);
-	atomicMin(bounds6 + 0, rb_float_ordered(c.x)); atomicMin(bounds6 + 1, rb_float_ordered(c.y)); atomicMin(bounds6 + 2, rb_float_ordered(c.z));
-	atomicMax(bounds6 + 3, rb_float_ordered(c.x)); atomicMax(bounds6 + 4, rb_float_ordered(c.y)); atomicMax(bounds6 + 5, rb_float_ordered(c.z));
+	// Grid-stride partial min/max per thread, shuffle reduction per warp, one atomic per warp and component.
+	unsigned int lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
+	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ntris; i += gridDim.x * blockDim.x) {
+		V3 a, b;
+		rb_tri_box(verts, triVerts[3 * i], triVerts[3 * i + 1], triVerts[3 * i + 2], a, b);
+		const V3 c = 0.5f * (a + b);
+		const unsigned int k[3] = {rb_float_ordered(c.x), rb_float_ordered(c.y), rb_float_ordered(c.z)};
+		for(int d = 0; d < 3; ++d) {
+			lo[d] = min(lo[d], k[d]);
+			hi[d] = max(hi[d], k[d]);
+		}
+	}
+	for(int off = 16; off > 0; off >>= 1) {
+		for(int d = 0; d < 3; ++d) {
+			lo[d] = min(lo[d], __shfl_down_sync(0xffffffffu, lo[d], off));
+			hi[d] = max(hi[d], __shfl_down_sync(0xffffffffu, hi[d], off));
+		}
+	}
+	if((threadIdx.x & 31u) == 0u) {
+		for(int d = 0; d < 3; ++d) {
+			atomicMin(bounds6 + d, lo[d]);
+			atomicMax(bounds6 + 3 + d, hi[d]);
+		}
+	}
 }
 
 RB_D uint64_t rb_expand21(uint64_t v) { // spread 21 bits so that two zero bits separate consecutive bits
@@ -268,9 +286,10 @@ __global__ void rb_k_lbvh_hierarchy(const uint64_t * __restrict__ keys, int n, i
 }
 
 // Re-gather the triangles in hierarchy order: records for the traversal (v0, v1-v0, v2-v0 + ids) and vertex ids for refits.
-__global__ void rb_k_lbvh_gather(const uint32_t * __restrict__ order, const uint32_t * __restrict__ triVertsIn, const uint32_t * __restrict__ triIdsIn, uint32_t ntris, uint32_t * __restrict__ triVertsOut, uint32_t * __restrict__ triIdsOut) {
+__global__ void rb_k_lbvh_gather(const uint32_t * __restrict__ order, const uint32_t * __restrict__ triVertsIn, const uint32_t * __restrict__ triIdsIn, uint32_t ntris, uint32_t * __restrict__ triVertsOut, uint32_t * __restrict__ triIdsOut, int * __restrict__ leafCode) {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= ntris) return;
+	if(leafCode) leafCode[i] = int(i << RB_LEAF_BITS); // leaf j holds triangle j
 	const uint32_t src = order ? order[i] : i;
 	for(int k = 0; k < 3; ++k) triVertsOut[3 * i + k] = triVertsIn[3 * src + k];
 	triIdsOut[2 * i + 0] = triIdsIn[2 * src + 0];
@@ -420,22 +439,20 @@ rb_status rb_lbvh_build(rb_raycaster * rc) {
 	cudaEventCreate(&ev0);
 	cudaEventCreate(&ev1);
 	cudaEventRecord(ev0, s);
-	rb_k_lbvh_bounds<<<rb_blocks(n, 256), 256, 0, s>>>(rc->d_verts, d_tvIn, n, d_bounds);
+	rb_k_lbvh_bounds<<<std::min<unsigned>(rb_blocks(n, 256), 148u * 8u), 256, 0, s>>>(rc->d_verts, d_tvIn, n, d_bounds);
 	rb_k_lbvh_morton<<<rb_blocks(n, 256), 256, 0, s>>>(rc->d_verts, d_tvIn, n, d_bounds, d_keys, d_vals);
 	launches += 2;
 	rb_status st = rb_radix_sort(d_keys, d_vals, n, 63, s, &launches);
 	if(st == RB_OK) {
-		rb_k_lbvh_gather<<<rb_blocks(n, 256), 256, 0, s>>>(d_vals, d_tvIn, d_idIn, n, rc->d_triVerts, rc->d_triIds);
+		rb_k_lbvh_gather<<<rb_blocks(n, 256), 256, 0, s>>>(d_vals, d_tvIn, d_idIn, n, rc->d_triVerts, rc->d_triIds, rc->d_leafCode);
 		++launches;
 		if(n > 1) {
 			rb_k_lbvh_hierarchy<<<rb_blocks(n - 1, 128), 128, 0, s>>>(d_keys, int(n), d_childRefs, rc->d_parent, rc->d_leafParent);
 			rb_k_lbvh_write_refs<<<rb_blocks(n - 1, 256), 256, 0, s>>>(d_childRefs, int(n - 1), rc->d_nodes);
 			launches += 2;
 		}
-		// Leaf table: leaf j holds triangle j. A single triangle is a root that is itself a leaf.
-		std::vector<int> leafCode(ntris);
-		for(size_t j = 0; j < ntris; ++j) leafCode[j] = int(j << RB_LEAF_BITS);
-		RB_CUDA(cudaMemcpyAsync(rc->d_leafCode, leafCode.data(), ntris * sizeof(int), cudaMemcpyHostToDevice, s));
+		// Leaf table (leaf j holds triangle j) was written by the gather kernel. A single triangle is a root that is
+		// itself a leaf.
 		float rootRec[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 		int rootRef = (n > 1) ? 0 : ~0;
 		std::memcpy(&rootRec[3], &rootRef, 4);
@@ -444,7 +461,6 @@ rb_status rb_lbvh_build(rb_raycaster * rc) {
 			const int rootLink = ~0;
 			RB_CUDA(cudaMemcpyAsync(rc->d_leafParent, &rootLink, sizeof(int), cudaMemcpyHostToDevice, s));
 		}
-		RB_CUDA(cudaStreamSynchronize(s));
 		rc->dev.nodes  = rc->d_nodes;
 		rc->dev.tris   = rc->d_tris;
 		rc->dev.roots  = rc->d_roots;
