@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <string>
+#include <thread>
 #include <vector>
 
 // ---------------------------------------------------------------- errors
@@ -26,6 +27,28 @@ bool rb_have_device();
 	do {                                                                                                        \
 		if(!rb_have_device()) return rb_fail(RB_ERR_NO_DEVICE, "no CUDA device available (no CPU fallback)");     \
 	} while(0)
+
+// ---------------------------------------------------------------- host helpers
+// Splits [0, n) into contiguous ranges over a few host threads (large meshes: packing and per-triangle set-up are
+// memory-bound loops over hundreds of MB). fn(begin, end) must only touch its own range.
+template<typename F>
+void rb_parallel_for(size_t n, size_t grain, F && fn) {
+	const size_t hw = std::thread::hardware_concurrency();
+	size_t nt		= hw > 8 ? 8 : (hw ? hw : 1);
+	if(grain && n / grain < nt) nt = n / grain;
+	if(nt <= 1) {
+		fn(size_t(0), n);
+		return;
+	}
+	std::vector<std::thread> pool;
+	const size_t span = (n + nt - 1) / nt;
+	for(size_t t = 0; t < nt; ++t) {
+		const size_t b = t * span, e = (b + span < n) ? (b + span) : n;
+		if(b >= e) break;
+		pool.emplace_back([&fn, b, e] { fn(b, e); });
+	}
+	for(auto & th : pool) th.join();
+}
 
 // ---------------------------------------------------------------- raycaster handle
 struct rb_raycaster {

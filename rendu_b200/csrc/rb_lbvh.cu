@@ -13,6 +13,9 @@
 #include "rb_math.cuh"
 
 #include <algorithm>
+#include <memory>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -393,16 +396,33 @@ rb_status rb_lbvh_build(rb_raycaster * rc) {
 	const size_t ntris = rc->tris.size();
 	if(ntris == 0) return rb_fail(RB_ERR_INVALID, "rb_raycaster_build: no triangle to build a hierarchy on");
 	if(ntris >= (size_t(1) << (31 - RB_LEAF_BITS))) return rb_fail(RB_ERR_UNSUPPORTED, "too many triangles for 32-bit leaf references");
+	const bool timing = std::getenv("RB_BUILD_TIMING") != nullptr;
+	auto now = [] { return std::chrono::steady_clock::now(); };
+	auto lap = [&](const char * what, std::chrono::steady_clock::time_point & t0) {
+		if(timing) {
+			cudaDeviceSynchronize();
+			const auto t1 = now();
+			std::fprintf(stderr, "[rb_lbvh_build] %-22s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+			t0 = now();
+		}
+	};
+	auto t0 = now();
 	rb_raycaster_free_device(rc);
+	lap("free previous", t0);
 	RB_CUDA(cudaGetDevice(&rc->device));
 	cudaStream_t s = cudaStreamPerThread;
 	const uint32_t n = uint32_t(ntris);
 	// Input triangles in addMesh order: vertex ids and (localId, meshId).
-	std::vector<uint32_t> triVerts(ntris * 3), triIds(ntris * 2);
-	for(size_t i = 0; i < ntris; ++i) {
-		triVerts[3 * i] = uint32_t(rc->tris[i].v0); triVerts[3 * i + 1] = uint32_t(rc->tris[i].v1); triVerts[3 * i + 2] = uint32_t(rc->tris[i].v2);
-		triIds[2 * i] = uint32_t(rc->tris[i].localId); triIds[2 * i + 1] = rc->tris[i].meshId;
-	}
+	// Uninitialised staging (a value-initialised vector would first zero 200 MB on one thread).
+	std::unique_ptr<uint32_t[]> triVerts(new uint32_t[ntris * 3]), triIds(new uint32_t[ntris * 2]);
+	rb_parallel_for(ntris, size_t(1) << 16, [&](size_t begin, size_t end) {
+		for(size_t i = begin; i < end; ++i) {
+			const rb_tri & t = rc->tris[i];
+			triVerts[3 * i] = uint32_t(t.v0); triVerts[3 * i + 1] = uint32_t(t.v1); triVerts[3 * i + 2] = uint32_t(t.v2);
+			triIds[2 * i] = uint32_t(t.localId); triIds[2 * i + 1] = t.meshId;
+		}
+	});
+	lap("pack triangles", t0);
 	uint32_t *d_tvIn = nullptr, *d_idIn = nullptr, *d_vals = nullptr;
 	uint64_t * d_keys = nullptr;
 	unsigned int * d_bounds = nullptr;
@@ -413,10 +433,10 @@ rb_status rb_lbvh_build(rb_raycaster * rc) {
 	rc->nVerts	  = rc->verts.size() / 3;
 	RB_CUDA(cudaMalloc(&rc->d_verts, rc->verts.size() * sizeof(float) + 64));
 	RB_CUDA(cudaMemcpyAsync(rc->d_verts, rc->verts.data(), rc->verts.size() * sizeof(float), cudaMemcpyHostToDevice, s));
-	RB_CUDA(cudaMalloc(&d_tvIn, triVerts.size() * sizeof(uint32_t)));
-	RB_CUDA(cudaMalloc(&d_idIn, triIds.size() * sizeof(uint32_t)));
-	RB_CUDA(cudaMemcpyAsync(d_tvIn, triVerts.data(), triVerts.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-	RB_CUDA(cudaMemcpyAsync(d_idIn, triIds.data(), triIds.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+	RB_CUDA(cudaMalloc(&d_tvIn, ntris * 3 * sizeof(uint32_t)));
+	RB_CUDA(cudaMalloc(&d_idIn, ntris * 2 * sizeof(uint32_t)));
+	RB_CUDA(cudaMemcpyAsync(d_tvIn, triVerts.get(), ntris * 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+	RB_CUDA(cudaMemcpyAsync(d_idIn, triIds.get(), ntris * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
 	RB_CUDA(cudaMalloc(&d_keys, ntris * sizeof(uint64_t)));
 	RB_CUDA(cudaMalloc(&d_vals, ntris * sizeof(uint32_t)));
 	RB_CUDA(cudaMalloc(&d_bounds, 6 * sizeof(unsigned int)));
@@ -434,6 +454,7 @@ rb_status rb_lbvh_build(rb_raycaster * rc) {
 	RB_CUDA(cudaMemsetAsync(rc->d_nodes, 0, (rc->nInterior + 1) * 64, s));
 	const unsigned int initBounds[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
 	RB_CUDA(cudaMemcpyAsync(d_bounds, initBounds, sizeof(initBounds), cudaMemcpyHostToDevice, s));
+	lap("allocate + upload", t0);
 	uint64_t launches = 0;
 	cudaEvent_t ev0, ev1;
 	cudaEventCreate(&ev0);
@@ -475,12 +496,14 @@ rb_status rb_lbvh_build(rb_raycaster * rc) {
 	rc->buildDeviceMs = buildMs;
 	cudaEventDestroy(ev0);
 	cudaEventDestroy(ev1);
+	lap("build kernels", t0);
 	cudaFree(d_tvIn);
 	cudaFree(d_idIn);
 	cudaFree(d_keys);
 	cudaFree(d_vals);
 	cudaFree(d_bounds);
 	cudaFree(d_childRefs);
+	lap("free scratch", t0);
 	if(st) return st;
 	if(size_t(rc->dev.stackDepth) * RB_TRACE_BLOCK_THREADS * sizeof(int) > 160 * 1024) {
 		return rb_fail(RB_ERR_UNSUPPORTED, "LBVH depth %d needs a traversal stack larger than shared memory", rc->maxDepth);

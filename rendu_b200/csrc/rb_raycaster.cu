@@ -500,29 +500,38 @@ extern "C" rb_status rb_raycaster_add_mesh(rb_raycaster * rc, const float * posi
 	const size_t startTriangle = rc->tris.size();
 	rc->tris.resize(startTriangle + ntri);
 	const size_t nvTotal = rc->verts.size() / 3;
-	for(size_t t = 0; t < ntri; ++t) {
-		rb_tri & ti = rc->tris[startTriangle + t];
-		std::memset(&ti, 0, sizeof(ti));
-		ti.v0	   = indexOffset + indices[3 * t + 0];
-		ti.v1	   = indexOffset + indices[3 * t + 1];
-		ti.v2	   = indexOffset + indices[3 * t + 2];
-		ti.localId = 3 * t;
-		ti.meshId  = rc->meshCount;
-		if(ti.v0 >= nvTotal || ti.v1 >= nvTotal || ti.v2 >= nvTotal) {
-			rc->tris.resize(startTriangle);
-			rc->verts.resize(indexOffset * 3);
-			return rb_fail(RB_ERR_INVALID, "rb_raycaster_add_mesh: index out of range in triangle %zu", t);
+	std::atomic<size_t> badTriangle{SIZE_MAX};
+	const uint32_t meshId = rc->meshCount;
+	rb_parallel_for(ntri, size_t(1) << 16, [&](size_t begin, size_t end) {
+		for(size_t t = begin; t < end; ++t) {
+			rb_tri & ti = rc->tris[startTriangle + t];
+			std::memset(&ti, 0, sizeof(ti));
+			ti.v0	   = indexOffset + indices[3 * t + 0];
+			ti.v1	   = indexOffset + indices[3 * t + 1];
+			ti.v2	   = indexOffset + indices[3 * t + 2];
+			ti.localId = 3 * t;
+			ti.meshId  = meshId;
+			if(ti.v0 >= nvTotal || ti.v1 >= nvTotal || ti.v2 >= nvTotal) {
+				size_t seen = badTriangle.load();
+				while(t < seen && !badTriangle.compare_exchange_weak(seen, t)) {}
+				return;
+			}
+			const float * a = rc->verts.data() + 3 * ti.v0;
+			const float * b = rc->verts.data() + 3 * ti.v1;
+			const float * c = rc->verts.data() + 3 * ti.v2;
+			// BoundingBox(v0,v1,v2) (Bounds.cpp:12-15): min(min(v0,v1),v2), glm::min(x,y) = (y<x)?y:x.
+			for(int k = 0; k < 3; ++k) {
+				const float mn01 = (b[k] < a[k]) ? b[k] : a[k];
+				const float mx01 = (a[k] < b[k]) ? b[k] : a[k];
+				ti.bmin[k]		 = (c[k] < mn01) ? c[k] : mn01;
+				ti.bmax[k]		 = (mx01 < c[k]) ? c[k] : mx01;
+			}
 		}
-		const float * a = rc->verts.data() + 3 * ti.v0;
-		const float * b = rc->verts.data() + 3 * ti.v1;
-		const float * c = rc->verts.data() + 3 * ti.v2;
-		// BoundingBox(v0,v1,v2) (Bounds.cpp:12-15): min(min(v0,v1),v2), glm::min(x,y) = (y<x)?y:x.
-		for(int k = 0; k < 3; ++k) {
-			const float mn01 = (b[k] < a[k]) ? b[k] : a[k];
-			const float mx01 = (a[k] < b[k]) ? b[k] : a[k];
-			ti.bmin[k]		 = (c[k] < mn01) ? c[k] : mn01;
-			ti.bmax[k]		 = (mx01 < c[k]) ? c[k] : mx01;
-		}
+	});
+	if(badTriangle.load() != SIZE_MAX) {
+		rc->tris.resize(startTriangle);
+		rc->verts.resize(indexOffset * 3);
+		return rb_fail(RB_ERR_INVALID, "rb_raycaster_add_mesh: index out of range in triangle %zu", badTriangle.load());
 	}
 	// One root per mesh, appended after the existing roots: a rebuild restarts from these (Raycaster.cpp:43-46).
 	rc->meshFirst.push_back(startTriangle);
