@@ -150,7 +150,19 @@ static rb_status rb_radix_sort(uint64_t * keys, uint32_t * vals, uint32_t n, int
 	const uint32_t tableN  = 256u * nblocks;
 	const uint32_t ntiles  = (tableN + RB_SCAN_TILE - 1) / RB_SCAN_TILE;
 	RbSortScratch sc;
-	// Stream-ordered scratch: no device-wide synchronisation, and the pool hands the memory back to the next build.
+	// Stream-ordered scratch: no device-wide synchronisation. The pool keeps up to 256 MB cached across
+	// synchronisation points (default: everything is returned to the driver), so the next build or refit reuses it.
+	{
+		int dev = 0;
+		cudaMemPool_t pool = nullptr;
+		if(cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+			uint64_t keep = 0;
+			if(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess && keep < (uint64_t(256) << 20)) {
+				keep = uint64_t(256) << 20;
+				cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+			}
+		}
+	}
 	RB_CUDA(cudaMallocAsync(&sc.keysAlt, size_t(n) * sizeof(uint64_t), s));
 	RB_CUDA(cudaMallocAsync(&sc.valsAlt, size_t(n) * sizeof(uint32_t), s));
 	RB_CUDA(cudaMallocAsync(&sc.table, size_t(tableN) * sizeof(uint32_t), s));
