@@ -23,109 +23,215 @@ struct Pending {
 inline float minf(float x, float y) { return (y < x) ? y : x; } // glm::min
 inline float maxf(float x, float y) { return (x < y) ? y : x; } // glm::max
 
+// What the builder reads and permutes.
+struct BuildInput {
+	const std::vector<rb_tri> * tris;
+	const float * centroid[3];
+	uint32_t * order;
+};
+
+// Processes ONE set as Raycaster.cpp:73-139 does: box, leaf test, axis, mean partition / median fallback. Fills `node`
+// (children left unset) and returns the split position, or SIZE_MAX for a leaf.
+size_t split_set(const BuildInput & in, size_t begin, size_t count, rb_node & node) {
+	const std::vector<rb_tri> & tris = *in.tris;
+	uint32_t * first = in.order + begin;
+	uint32_t * last	 = first + count;
+	// Union of the triangle boxes (BoundingBox::merge, Bounds.cpp:17-20).
+	float lo[3], hi[3];
+	if(count > 0) {
+		const rb_tri & t0 = tris[first[0]];
+		for(int a = 0; a < 3; ++a) {
+			lo[a] = t0.bmin[a];
+			hi[a] = t0.bmax[a];
+		}
+		for(size_t k = 1; k < count; ++k) {
+			const rb_tri & t = tris[first[k]];
+			for(int a = 0; a < 3; ++a) {
+				lo[a] = minf(lo[a], t.bmin[a]);
+				hi[a] = maxf(hi[a], t.bmax[a]);
+			}
+		}
+	} else {
+		// Empty mesh: the reference would read past its triangle array here; give the root an inverted box that no
+		// ray can enter.
+		for(int a = 0; a < 3; ++a) {
+			lo[a] = 1.0f;
+			hi[a] = -1.0f;
+		}
+	}
+	std::memcpy(node.bmin, lo, sizeof(lo));
+	std::memcpy(node.bmax, hi, sizeof(hi));
+	if(count < 3) {
+		node.leaf  = 1;
+		node.left  = begin;
+		node.right = count;
+		return SIZE_MAX;
+	}
+	node.leaf = 0;
+	// Longest axis of the box (ties resolved as in Raycaster.cpp:97-98).
+	const float sx = hi[0] - lo[0], sy = hi[1] - lo[1], sz = hi[2] - lo[2];
+	const int axis = (sx >= sy && sx >= sz) ? 0 : (sy >= sz ? 1 : 2);
+	const float * c = in.centroid[axis];
+	size_t split = 0;
+	if(count >= 5) {
+		float mean = 0.0f;
+		for(size_t k = 0; k < count; ++k) mean += c[first[k]];
+		mean /= float(count);
+		uint32_t * mid = std::partition(first, last, [c, mean](uint32_t t) { return c[t] < mean; });
+		split		   = size_t(mid - first);
+	}
+	if(split == 0 || split == count || count < 5) {
+		split = count / 2;
+		std::nth_element(first, first + split, last, [c](uint32_t a, uint32_t b) { return c[a] < c[b]; });
+	}
+	return split;
+}
+
+// The reference's LIFO loop on one sub-tree, with local numbering: nodes[0] is the set itself, its descendants follow
+// in the order the reference would emplace them (left child, right child, then the whole right sub-tree before the
+// left one). Because the loop is LIFO, that is also the order in which the global build creates them — contiguously.
+struct SubTree {
+	std::vector<rb_node> nodes;
+	int maxDepth = 0;
+};
+
+void build_subtree(const BuildInput & in, size_t begin, size_t count, int depth, SubTree & out) {
+	out.nodes.assign(1, rb_node{});
+	std::vector<Pending> todo;
+	todo.reserve(64);
+	todo.push_back({0, begin, count, depth});
+	while(!todo.empty()) {
+		const Pending cur = todo.back();
+		todo.pop_back();
+		rb_node node{};
+		const size_t split = split_set(in, cur.begin, cur.count, node);
+		if(split != SIZE_MAX) {
+			out.maxDepth = std::max(out.maxDepth, cur.depth + 1);
+			node.left	 = out.nodes.size();
+			node.right	 = out.nodes.size() + 1;
+			out.nodes.emplace_back();
+			out.nodes.emplace_back();
+			todo.push_back({size_t(node.left), cur.begin, split, cur.depth + 1});
+			todo.push_back({size_t(node.right), cur.begin + split, cur.count - split, cur.depth + 1});
+		}
+		out.nodes[cur.id] = node;
+	}
+}
+
 } // namespace
 
 void rb_host_build_reference(rb_raycaster * rc) {
 	const size_t ntris = rc->tris.size();
-	// One root per mesh (Raycaster.cpp:43-46); a rebuild starts again from the per-mesh triangle ranges, which stay
-	// valid because the build only permutes triangles inside their mesh's range.
-	rc->nodes.assign(rc->meshCount, rb_node{});
-
 	// BoundingBox::getCentroid (Bounds.cpp:61-63): 0.5f * (minis + maxis), per axis.
 	std::vector<float> centroid[3];
-	for(int a = 0; a < 3; ++a) {
-		centroid[a].resize(ntris);
-		for(size_t i = 0; i < ntris; ++i) {
-			centroid[a][i] = 0.5f * (rc->tris[i].bmin[a] + rc->tris[i].bmax[a]);
-		}
-	}
+	for(int a = 0; a < 3; ++a) centroid[a].resize(ntris);
 	std::vector<uint32_t> order(ntris);
-	for(size_t i = 0; i < ntris; ++i) order[i] = uint32_t(i);
+	rb_parallel_for(ntris, size_t(1) << 16, [&](size_t b, size_t e) {
+		for(size_t i = b; i < e; ++i) {
+			for(int a = 0; a < 3; ++a) centroid[a][i] = 0.5f * (rc->tris[i].bmin[a] + rc->tris[i].bmax[a]);
+			order[i] = uint32_t(i);
+		}
+	});
+	BuildInput in{&rc->tris, {centroid[0].data(), centroid[1].data(), centroid[2].data()}, order.data()};
 
+	// The upper part of the tree is built here, in the reference's order; a set of at most `taskSize` triangles is not
+	// expanded but handed to a worker thread (disjoint triangle ranges, nothing shared). Since the reference's loop is
+	// LIFO, all descendants of such a set are created contiguously, right when the set is popped: `sequence` records
+	// the creation order of the upper nodes and of the deferred sub-trees, and the final numbering — one root per mesh
+	// first (Raycaster.cpp:43-46), then emplace_back order — is assigned once the sub-tree sizes are known.
+	const size_t taskSize = ntris >= (size_t(1) << 16) ? std::max<size_t>(ntris / 64, 4096) : 0;
+	struct Upper {
+		rb_node node;
+		long left = -1, right = -1; // upper-node indices of the children
+		long task = -1;				// deferred sub-tree rooted here
+	};
+	struct Task {
+		size_t upper, begin, count;
+		int depth;
+		SubTree tree;
+		size_t base = 0; // final id of local node 1
+	};
+	std::vector<Upper> upper(rc->meshCount);
+	std::vector<Task> tasks;
+	std::vector<long> sequence; // >= 0: upper node created; < 0: ~task index (its descendants are created here)
 	std::vector<Pending> todo;
 	todo.reserve(64);
-	for(size_t m = 0; m < rc->meshCount; ++m) {
-		todo.push_back({m, size_t(rc->meshFirst[m]), size_t(rc->meshTris[m]), 0});
-	}
+	// A rebuild starts again from the per-mesh triangle ranges, which stay valid because the build only permutes
+	// triangles inside their mesh's range.
+	for(size_t m = 0; m < rc->meshCount; ++m) todo.push_back({m, size_t(rc->meshFirst[m]), size_t(rc->meshTris[m]), 0});
 	int maxDepth = 0;
-	const std::vector<rb_tri> & tris = rc->tris;
-
 	while(!todo.empty()) {
 		const Pending cur = todo.back();
 		todo.pop_back();
-		uint32_t * first = order.data() + cur.begin;
-		uint32_t * last	 = first + cur.count;
-
-		// Union of the triangle boxes (BoundingBox::merge, Bounds.cpp:17-20).
-		float lo[3], hi[3];
-		if(cur.count > 0) {
-			const rb_tri & t0 = tris[first[0]];
-			for(int a = 0; a < 3; ++a) {
-				lo[a] = t0.bmin[a];
-				hi[a] = t0.bmax[a];
-			}
-			for(size_t k = 1; k < cur.count; ++k) {
-				const rb_tri & t = tris[first[k]];
-				for(int a = 0; a < 3; ++a) {
-					lo[a] = minf(lo[a], t.bmin[a]);
-					hi[a] = maxf(hi[a], t.bmax[a]);
-				}
-			}
-		} else {
-			// Empty mesh: the reference would read past its triangle array here; give the root an inverted box
-			// that no ray can enter.
-			for(int a = 0; a < 3; ++a) {
-				lo[a] = 1.0f;
-				hi[a] = -1.0f;
-			}
-		}
-		{
-			rb_node & node = rc->nodes[cur.id];
-			std::memcpy(node.bmin, lo, sizeof(lo));
-			std::memcpy(node.bmax, hi, sizeof(hi));
-		}
-		if(cur.count < 3) {
-			rb_node & node = rc->nodes[cur.id];
-			node.leaf	   = 1;
-			node.left	   = cur.begin;
-			node.right	   = cur.count;
+		if(taskSize && cur.count <= taskSize && cur.count >= 3) {
+			upper[cur.id].task = long(tasks.size());
+			sequence.push_back(~long(tasks.size()));
+			tasks.push_back(Task{cur.id, cur.begin, cur.count, cur.depth, SubTree{}, 0});
 			continue;
 		}
-		maxDepth = std::max(maxDepth, cur.depth + 1);
-
-		// Longest axis of the box (ties resolved as in Raycaster.cpp:97-98).
-		const float sx = hi[0] - lo[0], sy = hi[1] - lo[1], sz = hi[2] - lo[2];
-		const int axis = (sx >= sy && sx >= sz) ? 0 : (sy >= sz ? 1 : 2);
-		const float * c = centroid[axis].data();
-
-		size_t split = 0;
-		if(cur.count >= 5) {
-			float mean = 0.0f;
-			for(size_t k = 0; k < cur.count; ++k) mean += c[first[k]];
-			mean /= float(cur.count);
-			uint32_t * mid = std::partition(first, last, [c, mean](uint32_t t) { return c[t] < mean; });
-			split		   = size_t(mid - first);
+		rb_node node{};
+		const size_t split = split_set(in, cur.begin, cur.count, node);
+		if(split != SIZE_MAX) {
+			maxDepth = std::max(maxDepth, cur.depth + 1);
+			const long l = long(upper.size()), r = l + 1;
+			upper.emplace_back();
+			upper.emplace_back();
+			sequence.push_back(l);
+			sequence.push_back(r);
+			upper[cur.id].left	= l;
+			upper[cur.id].right = r;
+			todo.push_back({size_t(l), cur.begin, split, cur.depth + 1});
+			todo.push_back({size_t(r), cur.begin + split, cur.count - split, cur.depth + 1});
 		}
-		if(split == 0 || split == cur.count || cur.count < 5) {
-			split = cur.count / 2;
-			std::nth_element(first, first + split, last, [c](uint32_t a, uint32_t b) { return c[a] < c[b]; });
-		}
-
-		const size_t leftId = rc->nodes.size();
-		rc->nodes.emplace_back();
-		const size_t rightId = rc->nodes.size();
-		rc->nodes.emplace_back();
-		rb_node & node = rc->nodes[cur.id];
-		node.leaf	   = 0;
-		node.left	   = leftId;
-		node.right	   = rightId;
-		todo.push_back({leftId, cur.begin, split, cur.depth + 1});
-		todo.push_back({rightId, cur.begin + split, cur.count - split, cur.depth + 1});
+		upper[cur.id].node = node;
 	}
+	rb_parallel_for(tasks.size(), 1, [&](size_t b, size_t e) {
+		for(size_t k = b; k < e; ++k) build_subtree(in, tasks[k].begin, tasks[k].count, tasks[k].depth, tasks[k].tree);
+	});
+
+	// Final numbering.
+	std::vector<size_t> finalId(upper.size());
+	for(size_t m = 0; m < rc->meshCount; ++m) finalId[m] = m;
+	size_t next = rc->meshCount;
+	for(const long ev : sequence) {
+		if(ev >= 0) {
+			finalId[size_t(ev)] = next++;
+		} else {
+			Task & t = tasks[size_t(~ev)];
+			t.base	 = next;
+			next += t.tree.nodes.size() - 1;
+		}
+	}
+	rc->nodes.assign(next, rb_node{});
+	for(size_t u = 0; u < upper.size(); ++u) {
+		if(upper[u].task >= 0) continue; // written with its sub-tree below
+		rb_node node = upper[u].node;
+		if(!node.leaf) {
+			node.left  = finalId[size_t(upper[u].left)];
+			node.right = finalId[size_t(upper[u].right)];
+		}
+		rc->nodes[finalId[u]] = node;
+	}
+	rb_parallel_for(tasks.size(), 1, [&](size_t b, size_t e) {
+		for(size_t k = b; k < e; ++k) {
+			const Task & t = tasks[k];
+			for(size_t j = 0; j < t.tree.nodes.size(); ++j) {
+				rb_node node = t.tree.nodes[j];
+				if(!node.leaf) {
+					node.left  = t.base + size_t(node.left) - 1;
+					node.right = t.base + size_t(node.right) - 1;
+				}
+				rc->nodes[j == 0 ? finalId[t.upper] : t.base + j - 1] = node;
+			}
+		}
+	});
+	for(const Task & t : tasks) maxDepth = std::max(maxDepth, t.tree.maxDepth);
 
 	// Apply the permutation to the triangle records.
 	std::vector<rb_tri> sorted(ntris);
-	for(size_t i = 0; i < ntris; ++i) sorted[i] = tris[order[i]];
+	rb_parallel_for(ntris, size_t(1) << 16, [&](size_t b, size_t e) {
+		for(size_t i = b; i < e; ++i) sorted[i] = rc->tris[order[i]];
+	});
 	rc->tris.swap(sorted);
 	rc->maxDepth = maxDepth;
 }

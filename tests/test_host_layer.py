@@ -67,6 +67,23 @@ def test_host_builder_matches_oracle_on_100k_triangles():
     assert sorted(tris2["localId"].tolist()) == sorted(tris["localId"].tolist())
 
 
+def test_host_builder_parallel_subtrees_keep_the_reference_numbering():
+    """Above 64 K triangles the builder hands sub-trees to worker threads and renumbers them afterwards; the result must
+    still be the reference's arrays node for node — several meshes of different sizes, including ones too small to split."""
+    r, o = rb.Raycaster(), orc.OracleRaycaster()
+    for n, shift in ((150, 0.0), (3, 0.5), (200, 1.0), (40, 1.5), (1, 2.0)):
+        p, i = wl.displaced_grid(n)
+        m = np.eye(4, dtype=np.float32)
+        m[3, 1] = shift
+        r.addMesh(p, i, m.reshape(16))
+        o.add_mesh(p, i, m.reshape(16))
+    r.build_host_only()
+    o.build()
+    nodes, tris, _ = r.download_bvh()
+    assert tris.size > 65536 and nodes.tobytes() == o.nodes.tobytes()
+    assert np.array_equal(tris["localId"], o.tris["localId"]) and np.array_equal(tris["meshId"], o.tris["meshId"])
+
+
 def test_add_mesh_rejects_bad_indices():
     r = rb.Raycaster()
     pos = np.zeros((3, 3), np.float32)
