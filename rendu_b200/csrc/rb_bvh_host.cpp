@@ -342,27 +342,34 @@ bool rb_host_flatten(const rb_raycaster * rc, RbFlatBvh & out, std::string * why
 	out.triIds.resize(nt * 2);
 	const float * V = rc->verts.data();
 	const size_t nv = rc->verts.size() / 3;
-	for(size_t i = 0; i < nt; ++i) {
-		const rb_tri & t = rc->tris[i];
-		if(t.v0 >= nv || t.v1 >= nv || t.v2 >= nv) {
-			if(why) *why = "triangle vertex index out of range";
-			return false;
+	std::atomic<bool> bad{false};
+	rb_parallel_for(nt, size_t(1) << 16, [&](size_t begin, size_t end) {
+		for(size_t i = begin; i < end; ++i) {
+			const rb_tri & t = rc->tris[i];
+			if(t.v0 >= nv || t.v1 >= nv || t.v2 >= nv) {
+				bad = true;
+				return;
+			}
+			const float * a = V + 3 * t.v0;
+			const float * b = V + 3 * t.v1;
+			const float * c = V + 3 * t.v2;
+			float * d		= out.tris.data() + i * 12;
+			d[0] = a[0]; d[1] = a[1]; d[2] = a[2];
+			d[3] = asFloat(int(uint32_t(t.localId)));
+			d[4] = b[0] - a[0]; d[5] = b[1] - a[1]; d[6] = b[2] - a[2];
+			d[7] = asFloat(int(t.meshId));
+			d[8] = c[0] - a[0]; d[9] = c[1] - a[1]; d[10] = c[2] - a[2];
+			d[11] = 0.0f;
+			out.triVerts[3 * i + 0] = uint32_t(t.v0);
+			out.triVerts[3 * i + 1] = uint32_t(t.v1);
+			out.triVerts[3 * i + 2] = uint32_t(t.v2);
+			out.triIds[2 * i + 0]	= uint32_t(t.localId);
+			out.triIds[2 * i + 1]	= t.meshId;
 		}
-		const float * a = V + 3 * t.v0;
-		const float * b = V + 3 * t.v1;
-		const float * c = V + 3 * t.v2;
-		float * d		= out.tris.data() + i * 12;
-		d[0] = a[0]; d[1] = a[1]; d[2] = a[2];
-		d[3] = asFloat(int(uint32_t(t.localId)));
-		d[4] = b[0] - a[0]; d[5] = b[1] - a[1]; d[6] = b[2] - a[2];
-		d[7] = asFloat(int(t.meshId));
-		d[8] = c[0] - a[0]; d[9] = c[1] - a[1]; d[10] = c[2] - a[2];
-		d[11] = 0.0f;
-		out.triVerts[3 * i + 0] = uint32_t(t.v0);
-		out.triVerts[3 * i + 1] = uint32_t(t.v1);
-		out.triVerts[3 * i + 2] = uint32_t(t.v2);
-		out.triIds[2 * i + 0]	= uint32_t(t.localId);
-		out.triIds[2 * i + 1]	= t.meshId;
+	});
+	if(bad) {
+		if(why) *why = "triangle vertex index out of range";
+		return false;
 	}
 	return true;
 }
