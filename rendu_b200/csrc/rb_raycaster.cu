@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_visible(RbDeviceBvh bvh, 
 	const float maxi   = length3(direction);
 	const RbRay ray	   = rb_make_ray(a, direction);
 	RbHitRec best;
-	const bool any = rb_trace_exact<true, false>(bvh, ray, 0.0001f, maxi, rb_make_stack(s_stack + threadIdx.x, blockDim.x), best, nullptr);
+	// Any-hit: order independent (see rb_launch_trace), so the near-child-first walk is used.
+	const bool any = rb_trace_ordered<true, false>(bvh, ray, 0.0001f, maxi, rb_make_stack(s_stack + threadIdx.x, blockDim.x), best, nullptr);
 	out[i] = any ? 0 : 1;
 }
 
