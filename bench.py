@@ -520,7 +520,7 @@ def run_pathtrace(args):
         frame(spp, to_host=True)
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
-    t = torch.tensor([ms, e2e_ms, float(st["rays_closest"] + st["rays_shadow"]), float(st["kernel_launches"])], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_ms, float(st["rays_closest"] + st["rays_shadow"]), float(st["kernel_launches"]), float(st["rays_closest"]), float(st["shaded"])], dtype=torch.float64, device=dev)
     tmax = t.clone()
     if dist is not None:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -535,6 +535,7 @@ def run_pathtrace(args):
                 "e2e": {"value": spp * args.steps / (e2e_ms * 1e-3), "unit": "spp/s", "h2d_bytes_per_step": 48, "d2h_bytes_per_step": PT_W * PT_H * 3 * 4},
                 "gpu_launches": int(float(t[3]) * args.steps), "mrays_s": rays_per_frame / (ms / args.steps * 1e-3) / 1e6,
                 "msamples_s": PT_W * PT_H * spp / (ms / args.steps * 1e-3) / 1e6, "rays_per_sample": rays_per_frame / (PT_W * PT_H * spp),
+                "closest_rays_per_sample": float(t[4]) / (PT_W * PT_H * spp), "shaded_hits_per_sample": float(t[5]) / (PT_W * PT_H * spp),
                 "image_mean": float(img.mean()), "image_finite": bool(np.isfinite(img).all()), "roofline": None, "cpu_baseline": None}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_pathtrace_baseline(desc)
