@@ -225,11 +225,11 @@ __global__ void __launch_bounds__(RB_PT_BLOCK, RB_PT_SHADE_MIN_BLOCKS) rb_k_pt_s
 				sampleColor += attenuation * rb_eval_background(sc, rayDir, rayPos, ndcx, ndcy, did == 0);
 				pb.color[slot] = make_float4(sampleColor.x, sampleColor.y, sampleColor.z, 0.0f);
 			} else {
-				const uint4 ta	   = sc.triAttr[tri];
-				const RbObject obj = sc.objects[ta.w];
-				const V3 p		   = rayPos + h.x * rayDir; // :214
 				RbSurface surf;
-				rb_fetch_surface(sc, ta, h.y, h.z, surf);
+				uint32_t meshId;
+				rb_fetch_surface(sc, tri, h.y, h.z, surf, meshId);
+				const RbObject obj = sc.objects[meshId];
+				const V3 p		   = rayPos + h.x * rayDir; // :214
 				const bool noUVs = !(obj.flags & RB_OBJ_USE_UV);
 				if(noUVs) {
 					surf.u = 0.5f;
@@ -391,11 +391,11 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shadow(RbDeviceBvh bvh, R
 				if(T.best.tri < 0) {
 					visible = true;
 				} else if(MASKED) {
-					const uint4 ta	   = sc.triAttr[T.best.tri];
-					const RbObject obj = sc.objects[ta.w];
+					uint32_t meshId	   = __float_as_uint(rb_ldg4(bvh.tris + 3 * size_t(T.best.tri) + 1).w); // just read by the traversal
+					const RbObject obj = sc.objects[meshId];
 					if((obj.flags & RB_OBJ_MASKED) && (obj.flags & RB_OBJ_USE_UV)) {
 						float lu, lv;
-						rb_fetch_uv(sc, ta, T.best.u, T.best.v, lu, lv);
+						rb_fetch_uv(sc, T.best.tri, T.best.u, T.best.v, lu, lv, meshId);
 						const float alpha = rb_image_rgbal(sc, obj.texAlbedo, lu, lv).w;
 						if(alpha < 0.01f) {
 							// Transparent texel: shift to the hit, shorten the segment, cast again (:149-151).

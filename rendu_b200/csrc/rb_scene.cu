@@ -19,7 +19,7 @@ static void rb_scene_free_device(rb_scene * sc) {
 	cudaFree(sc->d_objects);
 	cudaFree(sc->d_lights);
 	cudaFree(sc->d_vertexAttr);
-	cudaFree(sc->d_triAttr);
+	cudaFree(sc->d_triShade);
 	cudaFree(sc->d_indices);
 	cudaFree(sc->d_objVertOffset);
 	cudaFree(sc->d_objIndexOffset);
@@ -28,7 +28,7 @@ static void rb_scene_free_device(rb_scene * sc) {
 	sc->d_objects = nullptr;
 	sc->d_lights = nullptr;
 	sc->d_vertexAttr = nullptr;
-	sc->d_triAttr = nullptr;
+	sc->d_triShade = nullptr;
 	sc->d_indices = nullptr;
 	sc->d_objVertOffset = nullptr;
 	sc->d_objIndexOffset = nullptr;
@@ -166,16 +166,25 @@ extern "C" rb_status rb_scene_set_background(rb_scene * sc, uint32_t mode, const
 	return RB_OK;
 }
 
-// Per triangle, in hierarchy order: the three GLOBAL vertex ids (into vertexAttr) and the mesh id, so that shading
-// needs one 16-byte load instead of hit.localId -> indices[] -> attribute arrays (Raycaster.hpp:91-95).
-__global__ void rb_k_build_tri_attr(const float4 * __restrict__ tris, size_t ntris, const uint32_t * __restrict__ indices, const uint32_t * __restrict__ objVertOffset, const uint32_t * __restrict__ objIndexOffset, uint4 * __restrict__ out) {
+// Per triangle, in hierarchy order: the packed attributes of its three vertices, gathered once here so that shading
+// reads one contiguous 144-byte record per hit instead of hit.localId -> indices[] -> three vertices
+// (Raycaster.hpp:91-95). The mesh id rides in the spare component of the first vertex.
+__global__ void rb_k_build_tri_shade(const float4 * __restrict__ tris, size_t ntris, const uint32_t * __restrict__ indices, const uint32_t * __restrict__ objVertOffset, const uint32_t * __restrict__ objIndexOffset,
+									 const float4 * __restrict__ vertexAttr, float4 * __restrict__ out) {
 	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= ntris) return;
 	const uint32_t localId = __float_as_uint(tris[3 * i].w);
 	const uint32_t meshId  = __float_as_uint(tris[3 * i + 1].w);
 	const uint32_t * idx   = indices + objIndexOffset[meshId] + localId;
 	const uint32_t vo	   = objVertOffset[meshId];
-	out[i] = make_uint4(vo + idx[0], vo + idx[1], vo + idx[2], meshId);
+	for(int k = 0; k < 3; ++k) {
+		const float4 * v = vertexAttr + 3 * size_t(vo + idx[k]);
+		float4 v2		 = v[2];
+		if(k == 0) v2.w = __uint_as_float(meshId);
+		out[9 * i + 3 * k + 0] = v[0];
+		out[9 * i + 3 * k + 1] = v[1];
+		out[9 * i + 3 * k + 2] = v2;
+	}
 }
 
 template<typename T>
@@ -221,9 +230,10 @@ extern "C" rb_status rb_scene_commit(rb_scene * sc, rb_build_mode mode) {
 	if((st = rb_upload(&sc->d_objVertOffset, vertOff.data(), vertOff.size() * sizeof(uint32_t)))) return st;
 	if((st = rb_upload(&sc->d_objIndexOffset, idxOff.data(), idxOff.size() * sizeof(uint32_t)))) return st;
 	const size_t ntris = sc->raycaster->nTris;
-	RB_CUDA(cudaMalloc(&sc->d_triAttr, ntris * sizeof(uint4) + 64));
+	RB_CUDA(cudaMalloc(&sc->d_triShade, ntris * 9 * sizeof(float4) + 64));
 	if(ntris) {
-		rb_k_build_tri_attr<<<unsigned((ntris + 255) / 256), 256>>>(sc->raycaster->d_tris, ntris, sc->d_indices, sc->d_objVertOffset, sc->d_objIndexOffset, sc->d_triAttr);
+		rb_k_build_tri_shade<<<unsigned((ntris + 255) / 256), 256>>>(sc->raycaster->d_tris, ntris, sc->d_indices, sc->d_objVertOffset, sc->d_objIndexOffset,
+																	 reinterpret_cast<const float4 *>(sc->d_vertexAttr), sc->d_triShade);
 		RB_CUDA(cudaGetLastError());
 		RB_CUDA(cudaDeviceSynchronize());
 	}
@@ -232,8 +242,7 @@ extern "C" rb_status rb_scene_commit(rb_scene * sc, rb_build_mode mode) {
 	dv.textures	  = sc->d_textures;
 	dv.objects	  = sc->d_objects;
 	dv.lights	  = sc->d_lights;
-	dv.vertexAttr = reinterpret_cast<const float4 *>(sc->d_vertexAttr);
-	dv.triAttr	  = sc->d_triAttr;
+	dv.triShade	  = sc->d_triShade;
 	dv.nLights	  = int(sc->lights.size());
 	dv.bgMode	  = sc->bgMode;
 	for(int k = 0; k < 3; ++k) {

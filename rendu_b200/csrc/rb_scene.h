@@ -31,7 +31,7 @@ struct rb_scene {
 	RbObject * d_objects	 = nullptr;
 	RbLight * d_lights		 = nullptr;
 	float * d_vertexAttr	 = nullptr;
-	uint4 * d_triAttr		 = nullptr;
+	float4 * d_triShade		 = nullptr; // 9 float4 per triangle, hierarchy order
 	uint32_t * d_indices	 = nullptr;
 	uint32_t * d_objVertOffset	= nullptr;
 	uint32_t * d_objIndexOffset = nullptr;

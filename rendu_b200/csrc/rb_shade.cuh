@@ -36,8 +36,8 @@ struct RbSceneDev {
 	const RbTexInfo * textures;
 	const RbObject * objects;
 	const RbLight * lights;
-	const float4 * vertexAttr; // 3 float4 per vertex: (n.xyz, t.x) (t.yz, b.xy) (b.z, uv.xy, 0)
-	const uint4 * triAttr;	   // per triangle in hierarchy order: global vertex ids (x,y,z), mesh id (w)
+	const float4 * triShade; // per triangle in hierarchy order, 9 float4: for each of its three vertices
+							 // (n.xyz, t.x) (t.yz, b.xy) (b.z, uv.xy, mesh id bits) — see rb_k_build_tri_shade
 	int nLights;
 	uint32_t bgMode;
 	float bgColor[3];
@@ -364,15 +364,15 @@ struct RbSurface {
 };
 
 // Raycaster::interpolateAttribute (Raycaster.hpp:90-97): w*a[i0] + u*a[i1] + v*a[i2], for normals, tangents,
-// bitangents and texcoords at once. Vertex attributes are packed as three float4 per vertex.
-RB_D void rb_fetch_surface(const RbSceneDev & sc, uint4 ta, float hu, float hv, RbSurface & s) {
+// bitangents and texcoords at once, from the triangle's pre-gathered record (one dependent load level: hit -> record,
+// instead of hit -> vertex ids -> three vertices).
+RB_D void rb_fetch_surface(const RbSceneDev & sc, int tri, float hu, float hv, RbSurface & s, uint32_t & meshId) {
 	const float hw = 1.0f - hu - hv;
-	const float4 * a = sc.vertexAttr + 3 * size_t(ta.x);
-	const float4 * b = sc.vertexAttr + 3 * size_t(ta.y);
-	const float4 * c = sc.vertexAttr + 3 * size_t(ta.z);
-	const float4 a0 = __ldg(a), a1 = __ldg(a + 1), a2 = __ldg(a + 2);
-	const float4 b0 = __ldg(b), b1 = __ldg(b + 1), b2 = __ldg(b + 2);
-	const float4 c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2);
+	const float4 * p = sc.triShade + 9 * size_t(tri);
+	const float4 a0 = __ldg(p), a1 = __ldg(p + 1), a2 = __ldg(p + 2);
+	const float4 b0 = __ldg(p + 3), b1 = __ldg(p + 4), b2 = __ldg(p + 5);
+	const float4 c0 = __ldg(p + 6), c1 = __ldg(p + 7), c2 = __ldg(p + 8);
+	meshId = __float_as_uint(a2.w);
 #define RB_INTERP(fa, fb, fc) (hw * (fa) + hu * (fb) + hv * (fc))
 	s.n = V3{RB_INTERP(a0.x, b0.x, c0.x), RB_INTERP(a0.y, b0.y, c0.y), RB_INTERP(a0.z, b0.z, c0.z)};
 	s.t = V3{RB_INTERP(a0.w, b0.w, c0.w), RB_INTERP(a1.x, b1.x, c1.x), RB_INTERP(a1.y, b1.y, c1.y)};
@@ -381,11 +381,11 @@ RB_D void rb_fetch_surface(const RbSceneDev & sc, uint4 ta, float hu, float hv, 
 	s.v = RB_INTERP(a2.z, b2.z, c2.z);
 #undef RB_INTERP
 }
-RB_D void rb_fetch_uv(const RbSceneDev & sc, uint4 ta, float hu, float hv, float & u, float & v) {
-	const float hw	= 1.0f - hu - hv;
-	const float4 a2 = __ldg(sc.vertexAttr + 3 * size_t(ta.x) + 2);
-	const float4 b2 = __ldg(sc.vertexAttr + 3 * size_t(ta.y) + 2);
-	const float4 c2 = __ldg(sc.vertexAttr + 3 * size_t(ta.z) + 2);
+RB_D void rb_fetch_uv(const RbSceneDev & sc, int tri, float hu, float hv, float & u, float & v, uint32_t & meshId) {
+	const float hw	 = 1.0f - hu - hv;
+	const float4 * p = sc.triShade + 9 * size_t(tri);
+	const float4 a2 = __ldg(p + 2), b2 = __ldg(p + 5), c2 = __ldg(p + 8);
+	meshId = __float_as_uint(a2.w);
 	u = hw * a2.y + hu * b2.y + hv * c2.y;
 	v = hw * a2.z + hu * b2.z + hv * c2.z;
 }
