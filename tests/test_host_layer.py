@@ -102,6 +102,18 @@ def test_no_cpu_fallback_without_gpu():
     assert e.value.status == _capi.RB_ERR_NO_DEVICE
     with pytest.raises(rb.RenduError):
         r.intersects(np.zeros(3, np.float32), np.array([0, -1, 0], np.float32))
+    # every compute entry point refuses to run, none computes on the host
+    from rendu_b200 import pathtracer as rpt
+    for call in (lambda: r.intersectsAny(np.zeros(3, np.float32), np.array([0, -1, 0], np.float32)),
+                 lambda: r.visible(np.zeros(3, np.float32), np.ones(3, np.float32)),
+                 lambda: r.rayLevels(np.zeros(3, np.float32), np.array([0, -1, 0], np.float32)),
+                 lambda: r.updateHierarchy(rb.BUILD_LBVH),
+                 lambda: rpt.output_ldr(np.zeros((4, 4, 3), np.float32)),
+                 lambda: rpt.output_hdr(np.zeros((4, 4, 3), np.float32)),
+                 lambda: rpt.Scene(wl.tiny_scene())):
+        with pytest.raises(rb.RenduError) as e:
+            call()
+        assert e.value.status in (_capi.RB_ERR_NO_DEVICE, _capi.RB_ERR_INVALID)
 
 
 def test_product_never_touches_the_oracle():
