@@ -74,8 +74,18 @@ extern "C" rb_status rb_scene_add_object(rb_scene * sc, const rb_object_desc * d
 	if(d->tex_albedo < 0 || d->tex_albedo >= ntex) return rb_fail(RB_ERR_INVALID, "rb_scene_add_object: albedo texture id %d out of range", d->tex_albedo);
 	if(!d->emissive && (d->tex_rmao < 0 || d->tex_rmao >= ntex)) return rb_fail(RB_ERR_INVALID, "rb_scene_add_object: rmao texture id %d out of range", d->tex_rmao);
 	if(!d->emissive && d->use_texcoords && (d->tex_normal < 0 || d->tex_normal >= ntex)) return rb_fail(RB_ERR_INVALID, "rb_scene_add_object: normal texture id %d out of range", d->tex_normal);
-	for(size_t i = 0; i < d->nindices; ++i) {
-		if(d->indices[i] >= d->nverts) return rb_fail(RB_ERR_INVALID, "rb_scene_add_object: index %zu out of range", i);
+	{
+		std::atomic<size_t> bad{SIZE_MAX};
+		rb_parallel_for(d->nindices, size_t(1) << 18, [&](size_t begin, size_t end) {
+			for(size_t i = begin; i < end; ++i) {
+				if(d->indices[i] >= d->nverts) {
+					size_t seen = bad.load();
+					while(i < seen && !bad.compare_exchange_weak(seen, i)) {}
+					return;
+				}
+			}
+		});
+		if(bad.load() != SIZE_MAX) return rb_fail(RB_ERR_INVALID, "rb_scene_add_object: index %zu out of range", bad.load());
 	}
 	RbHostObject o;
 	o.vertOffset  = uint32_t(sc->vertexAttr.size() / 12);
@@ -87,15 +97,17 @@ extern "C" rb_status rb_scene_add_object(rb_scene * sc, const rb_object_desc * d
 	sc->indices.insert(sc->indices.end(), d->indices, d->indices + d->nindices);
 	sc->vertexAttr.resize(sc->vertexAttr.size() + d->nverts * 12);
 	float * va = sc->vertexAttr.data() + size_t(o.vertOffset) * 12;
-	for(size_t v = 0; v < d->nverts; ++v) {
-		float * p = va + v * 12;
-		p[0] = d->normals[3 * v]; p[1] = d->normals[3 * v + 1]; p[2] = d->normals[3 * v + 2];
-		p[3] = d->tangents[3 * v]; p[4] = d->tangents[3 * v + 1]; p[5] = d->tangents[3 * v + 2];
-		p[6] = d->bitangents[3 * v]; p[7] = d->bitangents[3 * v + 1]; p[8] = d->bitangents[3 * v + 2];
-		p[9]  = d->texcoords ? d->texcoords[2 * v] : 0.0f;
-		p[10] = d->texcoords ? d->texcoords[2 * v + 1] : 0.0f;
-		p[11] = 0.0f;
-	}
+	rb_parallel_for(d->nverts, size_t(1) << 16, [&](size_t begin, size_t end) {
+		for(size_t v = begin; v < end; ++v) {
+			float * p = va + v * 12;
+			p[0] = d->normals[3 * v]; p[1] = d->normals[3 * v + 1]; p[2] = d->normals[3 * v + 2];
+			p[3] = d->tangents[3 * v]; p[4] = d->tangents[3 * v + 1]; p[5] = d->tangents[3 * v + 2];
+			p[6] = d->bitangents[3 * v]; p[7] = d->bitangents[3 * v + 1]; p[8] = d->bitangents[3 * v + 2];
+			p[9]  = d->texcoords ? d->texcoords[2 * v] : 0.0f;
+			p[10] = d->texcoords ? d->texcoords[2 * v + 1] : 0.0f;
+			p[11] = 0.0f;
+		}
+	});
 	// invtp = glm::inverse(glm::transpose(glm::mat3(model))) (PathTracer.cpp:94), evaluated once with glm's formulas
 	// (func_matrix.inl:87-105 transpose, :269-291 inverse) so the values equal what the reference recomputes per hit.
 	float m[3][3]; // m[col][row] of the TRANSPOSED upper-left 3x3
