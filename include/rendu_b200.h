@@ -107,7 +107,8 @@ typedef enum rb_trace_mode {
 	 * operation for operation, no FMA contraction: results are bit-identical to Raycaster::intersects. */
 	RB_TRACE_EXACT = 0,
 	/* Near-child-first ordered traversal on the same tree, same triangle test. Same hit except where the
-	 * reference's non-watertight box test makes the result depend on visiting order. */
+	 * reference's non-watertight box test makes the result depend on visiting order. Any-hit queries
+	 * (intersect_any, visible) always use this order: they never shrink maxi, so their boolean cannot depend on it. */
 	RB_TRACE_ORDERED = 1
 } rb_trace_mode;
 
