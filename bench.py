@@ -38,6 +38,26 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries the JSON line and nothing else: the reference library logs with std::cout ("[Raycaster] Mesh 0
+# added ..."), so file descriptor 1 is pointed at stderr for the whole run and the line is written to a private
+# duplicate of the original stdout.
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    _claim_stdout()
+    _JSON_OUT.write(json.dumps(obj) + "\n")
+    _JSON_OUT.flush()
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs. The process is started well before the
     timed region (its NVML initialisation stalls kernel launches for ~100 ms) and only the samples between begin() and
@@ -199,7 +219,7 @@ def run_reference(args):
             "data": "synthetic", "config": config_dict(args.gpus),
             "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -409,7 +429,7 @@ def run_gpu(args):
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                         "api": "rb_raycaster_intersect / rb_raycaster_intersect_any with pinned host buffers, closest and any calls issued from two host threads", "host_link": link},
                 "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu, "per_launch": per_launch}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -539,7 +559,7 @@ def run_pathtrace(args):
                 "image_mean": float(img.mean()), "image_finite": bool(np.isfinite(img).all()), "roofline": None, "cpu_baseline": None}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_pathtrace_baseline(desc)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -645,7 +665,7 @@ def run_lbvh(args):
             r.add_mesh(pos, idx)
             out["reference_updateHierarchy_s"] = r.build()
             out["reference_nodes"] = r.sizes()["nodes"]
-    print(json.dumps({"workload": "C5 LBVH build + refit + trace", **out}), flush=True)
+    emit({"workload": "C5 LBVH build + refit + trace", **out})
 
 
 def run_c1(args):
@@ -684,7 +704,7 @@ def run_c1(args):
                 rec.update(reference_render_ms=1e3 * min(dt, dt2), reference_rays=rays, reference_threads=ref.threads_default())
                 rec["speedup"] = rec["reference_render_ms"] / rec["gpu_render_ms"]
         out["scenes"][name] = rec
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def run_explore(args):
@@ -773,6 +793,7 @@ def main():
     ap.add_argument("--small", action="store_true", help="pathtrace: 8k-triangle floor instead of 1M (quick checks)")
     ap.add_argument("--trace-mode", default="exact", choices=["exact", "ordered"], help="pathtrace: traversal order of the wavefront kernels")
     args = ap.parse_args()
+    _claim_stdout()
     if args.explore:
         run_explore(args)
     elif args.workload == "pathtrace" and args.impl != "reference":
