@@ -9,7 +9,7 @@ stand-in in the gloo tests).
 import torch
 import torch.distributed as dist
 
-DEFAULT_TILE_ROWS = 8
+DEFAULT_TILE_ROWS = 2  # band height of the tile split: 2 rows balance the C3 frame to 1 % over 8 ranks (8 rows: 6 %; tools/tile_balance.py)
 
 
 def tile_spec(rank, world, tile_rows=DEFAULT_TILE_ROWS):
