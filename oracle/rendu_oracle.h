@@ -5,7 +5,7 @@
  *
  * Pinning: the reference ships no tests, golden vectors or fixtures for this path, so the
  * oracle is pinned against the reference ITSELF: oracle/_ref/librendu_ref.so is the reference's own translation
- * units compiled unmodified (oracle/build_ref.sh); tests/test_oracle_vs_reference.py checks every function here
+ * units compiled unmodified (oracle/build_ref.sh); tests/test_oracle_raycaster.py and tests/test_oracle_pathtracer.py check every function here
  * against it bit for bit (rays, hierarchy, scalar kernels, and whole renders with the same mt19937 stream), and
  * tests/golden/ holds vectors generated from it (tests/golden/make_golden.py) for machines without /root/reference.
  */
