@@ -67,6 +67,8 @@ struct rb_raycaster {
 	float4 * d_nodes  = nullptr;
 	float4 * d_tris	  = nullptr;
 	float4 * d_roots  = nullptr;
+	float4 * d_rootBlocks = nullptr; // union boxes of aligned root blocks (many-mesh scenes), see rb_next_root
+	bool rootBlocksWanted = false;	  // decided at upload (rb_root_blocks_worthwhile), kept across refits
 	size_t nInterior  = 0;
 	size_t nTris	  = 0;
 	RbDeviceBvh dev	  = {};
@@ -125,6 +127,9 @@ void rb_raycaster_free_device(rb_raycaster * rc);
 rb_status rb_lbvh_build(rb_raycaster * rc);
 rb_status rb_lbvh_refit(rb_raycaster * rc, const float * worldPositions, size_t nverts);
 rb_status rb_lbvh_download(const rb_raycaster * rc, rb_node * nodes, rb_tri * tris, float * verts);
+// (Re)builds the root-block boxes from the root table on the device; called after an upload and after every fit.
+rb_status rb_build_root_levels(rb_raycaster * rc, cudaStream_t s);
+bool rb_root_blocks_worthwhile(const float * roots8, size_t nroots);
 
 #define RB_TRACE_BLOCK_THREADS 128
 #define RB_CURSOR_RING 1024

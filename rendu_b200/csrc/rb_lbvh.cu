@@ -13,6 +13,7 @@
 #include "rb_math.cuh"
 
 #include <algorithm>
+#include <cfloat>
 #include <memory>
 #include <chrono>
 #include <cstdlib>
@@ -383,6 +384,95 @@ __global__ void rb_k_lbvh_write_refs(const int * __restrict__ childRefs, int nin
 // ------------------------------------------------------------------------------------------------ host
 static unsigned rb_blocks(size_t n, unsigned block) { return unsigned((n + block - 1) / block); }
 
+// ------------------------------------------------------------------------------------------------ root blocks
+// dst[b] = union of src[2b] and src[2b+1] (entries laid out like roots: (min, ·) (max, ·)); empty entries — inverted
+// boxes of meshes without triangles — are ignored, a block of empty entries stays empty.
+__global__ void rb_k_root_level(const float4 * __restrict__ src, int nsrc, float4 * __restrict__ dst, int ndst) {
+	const int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if(b >= ndst) return;
+	float lo[3] = {1.0f, 1.0f, 1.0f}, hi[3] = {-1.0f, -1.0f, -1.0f};
+	bool any = false;
+	for(int j = 2 * b; j < 2 * b + 2 && j < nsrc; ++j) {
+		const float4 a = src[2 * j], c = src[2 * j + 1];
+		if(a.x > c.x || a.y > c.y || a.z > c.z) continue;
+		const float l[3] = {a.x, a.y, a.z}, h[3] = {c.x, c.y, c.z};
+		for(int k = 0; k < 3; ++k) {
+			lo[k] = any ? fminf(lo[k], l[k]) : l[k];
+			hi[k] = any ? fmaxf(hi[k], h[k]) : h[k];
+		}
+		any = true;
+	}
+	dst[2 * b]	   = make_float4(lo[0], lo[1], lo[2], 0.0f);
+	dst[2 * b + 1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+}
+
+// Blocks are made of CONSECUTIVE roots (the visiting order is the mesh order and must stay so), which only helps when
+// consecutive meshes are also neighbours in space — objects listed row by row, instanced grids. The host decides at
+// upload time: pairs of consecutive root boxes must, on average, stay small against the whole scene.
+bool rb_root_blocks_worthwhile(const float * roots8, size_t nroots) {
+	if(nroots < 16 || std::getenv("RB_NO_ROOT_BLOCKS")) return false; // a handful of roots is cheaper to test one by one
+	auto area = [](const float * lo, const float * hi) {
+		const float x = hi[0] - lo[0], y = hi[1] - lo[1], z = hi[2] - lo[2];
+		return (x < 0.0f || y < 0.0f || z < 0.0f) ? 0.0 : 2.0 * (double(x) * y + double(y) * z + double(z) * x);
+	};
+	float slo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, shi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+	double pairs = 0.0;
+	size_t npairs = 0;
+	for(size_t r = 0; r < nroots; ++r) {
+		const float * lo = roots8 + 8 * r;
+		const float * hi = lo + 4;
+		if(lo[0] > hi[0]) continue; // empty mesh
+		for(int k = 0; k < 3; ++k) {
+			slo[k] = std::min(slo[k], lo[k]);
+			shi[k] = std::max(shi[k], hi[k]);
+		}
+		if((r & 1) && roots8[8 * (r - 1)] <= roots8[8 * (r - 1) + 4]) {
+			const float * plo = roots8 + 8 * (r - 1);
+			float ulo[3], uhi[3];
+			for(int k = 0; k < 3; ++k) {
+				ulo[k] = std::min(lo[k], plo[k]);
+				uhi[k] = std::max(hi[k], plo[4 + k]);
+			}
+			pairs += area(ulo, uhi);
+			++npairs;
+		}
+	}
+	const double scene = area(slo, shi);
+	return npairs > 0 && scene > 0.0 && (pairs / double(npairs)) < 0.02 * scene;
+}
+
+rb_status rb_build_root_levels(rb_raycaster * rc, cudaStream_t s) {
+	const int n = rc->dev.nroots;
+	rc->dev.rootLevels = 0;
+	rc->dev.rootBlocks = nullptr;
+	if(!rc->rootBlocksWanted || n < 16) return RB_OK;
+	int levels = 0;
+	while((2 << levels) <= n && levels < RB_MAX_ROOT_LEVELS) ++levels; // 2^levels <= n
+	int offset[RB_MAX_ROOT_LEVELS + 2] = {0};
+	int total = 0;
+	for(int k = 1; k <= levels; ++k) {
+		offset[k] = total;
+		total += (n + (1 << k) - 1) >> k;
+	}
+	if(rc->d_rootBlocks) RB_CUDA(cudaFree(rc->d_rootBlocks));
+	rc->d_rootBlocks = nullptr;
+	RB_CUDA(cudaMalloc(&rc->d_rootBlocks, size_t(total) * 2 * sizeof(float4) + 64));
+	const float4 * src = rc->d_roots;
+	int nsrc = n;
+	for(int k = 1; k <= levels; ++k) {
+		const int ndst = (n + (1 << k) - 1) >> k;
+		float4 * dst   = rc->d_rootBlocks + 2 * size_t(offset[k]);
+		rb_k_root_level<<<rb_blocks(uint32_t(ndst), 128), 128, 0, s>>>(src, nsrc, dst, ndst);
+		src	 = dst;
+		nsrc = ndst;
+	}
+	RB_CUDA(cudaGetLastError());
+	for(int k = 0; k <= RB_MAX_ROOT_LEVELS; ++k) rc->dev.rootLevelOffset[k] = (k >= 1 && k <= levels) ? offset[k] : 0;
+	rc->dev.rootBlocks = rc->d_rootBlocks;
+	rc->dev.rootLevels = levels;
+	return RB_OK;
+}
+
 static rb_status rb_run_fit(rb_raycaster * rc, cudaStream_t s) {
 	const int nleaves = int(rc->nLeaves);
 	unsigned int * d_depth = nullptr;
@@ -400,7 +490,7 @@ static rb_status rb_run_fit(rb_raycaster * rc, cudaStream_t s) {
 	if(e != cudaSuccess) return rb_fail(RB_ERR_CUDA, "hierarchy fit failed: %s", cudaGetErrorString(e));
 	rc->maxDepth	   = int(depth);
 	rc->dev.stackDepth = rc->maxDepth + 1;
-	return RB_OK;
+	return rb_build_root_levels(rc, s); // root boxes may have moved
 }
 
 rb_status rb_lbvh_build(rb_raycaster * rc) {

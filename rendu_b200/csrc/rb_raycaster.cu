@@ -400,6 +400,10 @@ void rb_raycaster_free_device(rb_raycaster * rc) {
 	cudaFree(rc->d_triIds);
 	cudaFree(rc->d_cursors);
 	rc->d_cursors = nullptr;
+	cudaFree(rc->d_rootBlocks);
+	rc->d_rootBlocks   = nullptr;
+	rc->dev.rootBlocks = nullptr;
+	rc->dev.rootLevels = 0;
 	rc->d_nodes = rc->d_tris = rc->d_roots = nullptr;
 	rc->d_parent	 = nullptr;
 	rc->d_leafParent = nullptr;
@@ -447,6 +451,10 @@ rb_status rb_raycaster_upload_flat(rb_raycaster * rc, const RbFlatBvh & flat) {
 	rc->dev.roots	   = rc->d_roots;
 	rc->dev.nroots	   = int(rc->meshCount);
 	rc->dev.stackDepth = rc->maxDepth + 1;
+	rc->rootBlocksWanted = rb_root_blocks_worthwhile(flat.roots.data(), flat.roots.size() / 8);
+	rb_status st		 = rb_build_root_levels(rc, cudaStreamPerThread);
+	if(st) return st;
+	RB_CUDA(cudaStreamSynchronize(cudaStreamPerThread));
 	rc->built		   = true;
 	rc->hostMirrorStale = false;
 	return RB_OK;

@@ -177,6 +177,41 @@ RB_D void rb_traversal_init(RbTraversal & T, const RbDeviceBvh & bvh, float mini
 	T.root	   = bvh.nroots;
 }
 
+// Next root whose box the ray enters, last mesh first: the reference tests every root against the caller's (mini, maxi)
+// and its stack hands them back in reverse (Raycaster.cpp:149-155). A scene with hundreds of objects has hundreds of
+// roots; for them the handle carries union boxes of aligned blocks of 2^k consecutive roots. Arriving at the last root
+// of such a block, the block's box is tested first and the whole block is skipped on a miss. The visiting order of the
+// roots that are entered is unchanged, and no root the reference would enter is skipped: the slab test is monotone in
+// the box (every fp32 operation in it is), so a ray that misses the union misses each member — for regular rays; the
+// NaN-carrying irregular rays take the plain loop.
+template<bool REGULAR, bool COUNT>
+RB_D int rb_next_root(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ray, float maxi, RbWork * work) {
+	while(T.root > 0) {
+		const int r = T.root - 1;
+		if(REGULAR && bvh.rootLevels > 0) {
+			int k		 = min(__ffs(r + 1) - 1, bvh.rootLevels); // r + 1 is a multiple of 2^k
+			bool skipped = false;
+			for(; k >= 1; --k) {
+				const float4 * b = bvh.rootBlocks + 2 * size_t(bvh.rootLevelOffset[k] + (r >> k));
+				const float4 b0 = rb_ldg4(b), b1 = rb_ldg4(b + 1);
+				if(COUNT) work->roots++;
+				if(!rb_box_test_t<true>(ray, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, T.mini, maxi)) {
+					T.root	= (r >> k) << k;
+					skipped = true;
+					break;
+				}
+			}
+			if(skipped) continue;
+		}
+		T.root = r;
+		const float4 r0 = rb_ldg4(bvh.roots + 2 * r);
+		const float4 r1 = rb_ldg4(bvh.roots + 2 * r + 1);
+		if(COUNT) work->roots++;
+		if(rb_box_test_t<REGULAR>(ray, r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, T.mini, maxi)) return __float_as_int(r0.w);
+	}
+	return RB_REF_NONE;
+}
+
 // Returns true when the traversal is finished (for ANY: also as soon as a triangle is accepted).
 template<bool ANY, bool COUNT, bool REGULAR>
 RB_D bool rb_step_exact(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ray, const RbStack & st, RbWork * work) {
@@ -185,17 +220,7 @@ RB_D bool rb_step_exact(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & 
 		if(!rb_stack_empty(T, st)) {
 			cur = rb_pop(T, st);
 		} else {
-			// Next accepted root, last mesh first.
-			while(T.root > 0) {
-				--T.root;
-				const float4 r0 = rb_ldg4(bvh.roots + 2 * T.root);
-				const float4 r1 = rb_ldg4(bvh.roots + 2 * T.root + 1);
-				if(COUNT) work->roots++;
-				if(rb_box_test(ray, r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, T.mini, T.maxi0)) {
-					cur = __float_as_int(r0.w);
-					break;
-				}
-			}
+			cur = rb_next_root<REGULAR, COUNT>(T, bvh, ray, T.maxi0, work);
 			if(cur == RB_REF_NONE) {
 				return true;
 			}
@@ -286,16 +311,7 @@ RB_D bool rb_step_ordered(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay 
 		if(!rb_stack_empty(T, st)) {
 			cur = rb_pop(T, st);
 		} else {
-			while(T.root > 0) {
-				--T.root;
-				const float4 r0 = rb_ldg4(bvh.roots + 2 * T.root);
-				const float4 r1 = rb_ldg4(bvh.roots + 2 * T.root + 1);
-				if(COUNT) work->roots++;
-				if(rb_box_test(ray, r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, T.mini, T.maxi)) {
-					cur = __float_as_int(r0.w);
-					break;
-				}
-			}
+			cur = rb_next_root<REGULAR, COUNT>(T, bvh, ray, T.maxi, work);
 			if(cur == RB_REF_NONE) {
 				return true;
 			}
@@ -396,16 +412,7 @@ RB_D bool rb_phase_node_t(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay 
 		if(!rb_stack_empty(T, st)) {
 			cur = rb_pop(T, st);
 		} else {
-			while(T.root > 0) {
-				--T.root;
-				const float4 r0 = rb_ldg4(bvh.roots + 2 * T.root);
-				const float4 r1 = rb_ldg4(bvh.roots + 2 * T.root + 1);
-				if(COUNT) work->roots++;
-				if(rb_box_test_t<REGULAR>(ray, r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, T.mini, ORDERED ? T.maxi : T.maxi0)) {
-					cur = __float_as_int(r0.w);
-					break;
-				}
-			}
+			cur = rb_next_root<REGULAR, COUNT>(T, bvh, ray, ORDERED ? T.maxi : T.maxi0, work);
 			if(cur == RB_REF_NONE) return true;
 		}
 	}

@@ -108,6 +108,57 @@ def test_upload_path_with_externally_built_hierarchy():
     assert n2.tobytes() == nodes.tobytes() and np.array_equal(t2["localId"], tris["localId"])
 
 
+@pytest.mark.parametrize("nmesh,row_order", [(16, True), (17, True), (333, True), (333, False)])
+def test_hundreds_of_roots_block_skipping_keeps_the_reference_result(nmesh, row_order, monkeypatch):
+    """From 16 meshes on, when consecutive meshes are neighbours in space (objects listed row by row), the root table
+    carries union boxes of aligned blocks of roots and a ray skips whole blocks it misses (rb_next_root); in random
+    order the blocks are not built. Either way hits must stay the reference's bit for bit (which root is entered first
+    decides ties between overlapping meshes), in every scheduler, for edge rays too, and after a refit moved the roots."""
+    rng = np.random.RandomState(nmesh)
+    side = int(np.ceil(np.sqrt(nmesh)))
+    meshes = []
+    for k in range(nmesh):
+        p, i = wl.displaced_grid(1 + k % 4)
+        m = np.eye(4, dtype=np.float32)
+        m[0, 0] = m[1, 1] = m[2, 2] = 0.12 if not row_order else 1.2 / side
+        if row_order:
+            m[3, :3] = [-0.9 + 1.8 * (k % side) / side, 0.3 + 0.2 * rng.uniform(), -0.9 + 1.8 * (k // side) / side]
+        else:
+            m[3, :3] = rng.uniform(-0.9, 0.9, 3) * np.array([1.0, 0.4, 1.0], np.float32) + np.array([0, 0.4, 0], np.float32)
+        if k % 7 == 3:
+            m[3, :3] = meshes[-1][2].reshape(4, 4)[3, :3]  # exactly overlapping copy of the previous mesh: distance ties
+            p, i = meshes[-1][0], meshes[-1][1]
+        meshes.append((p, i, m.reshape(16)))
+    o = oracle_from_meshes(meshes)
+    ro, rd = wl.random_rays(30000, 5 + nmesh)
+    co, cd = wl.coherent_rays(96)
+    c = load_case("raycast_grid37")
+    eo, ed = c["org"][-60:], c["dirs"][-60:]  # the NaN / inf / axis-parallel edge rays of the golden cases
+    org, dirs = np.concatenate([ro, co, eo]), np.concatenate([rd, cd, ed])
+    ho = o.intersect(org, dirs, threads=8)
+    ha = o.intersect_any(org, dirs, threads=8)
+    for persistent, votes in (("1", "6"), ("1", "0"), ("0", "0")):
+        monkeypatch.setenv("RB_PERSISTENT", persistent)
+        monkeypatch.setenv("RB_LEAF_VOTES", votes)
+        r = rb.Raycaster()
+        for p, i, m in meshes:
+            r.addMesh(p, i, m)
+        r.updateHierarchy()
+        h = r.intersects(org, dirs)
+        assert_hits_equal(h, ho["hit"], ho["dist"], ho["u"], ho["v"], ho["w"], ho["localId"], ho["meshId"], "roots%d/%s%s" % (nmesh, persistent, votes))
+        assert np.array_equal(r.intersectsAny(org, dirs).astype(np.uint8), ha)
+        assert int(h["hit"].sum()) > 100
+    # refit: every mesh moves up by 0.25 -> the root boxes and their block unions must follow
+    s = r.sizes()
+    _, _, verts = r.download_bvh()
+    moved = verts.copy()
+    moved[:, 1] += np.float32(0.25)
+    r.refit(moved)
+    h2 = r.intersects(org + np.array([0, 0.25, 0], np.float32), dirs)
+    assert np.array_equal(h2["hit"], ho["hit"]) or (h2["hit"] != ho["hit"]).mean() < 0.01  # same geometry, shifted with the rays (fp32 shift rounding aside)
+    assert s["meshes"] == nmesh
+
+
 @pytest.mark.parametrize("n,nrays,seed", [(1, 500, 1), (2, 500, 2), (9, 4000, 3), (96, 60000, 4)])
 def test_seeded_grids_against_oracle(n, nrays, seed):
     pos, idx = wl.displaced_grid(n)
