@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_raygen(RbFrame f, RbBatch
 
 // ------------------------------------------------------------------------------------------------ closest-hit wavefront
 // `_raycaster.intersects(rayPos, rayDir)` with the reference's default bounds (PathTracer.cpp:204, Raycaster.hpp:65).
-template<bool ORDERED>
+template<bool ORDERED, bool BLOCKS>
 __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_trace(RbDeviceBvh bvh, RbPathBuffers pb, const uint32_t * __restrict__ queue, uint32_t did, int threshold, int leafVotes, int nodeSteps, unsigned long long * __restrict__ stats) {
 	extern __shared__ int s_stack[];
 	const RbStack st		= rb_make_stack(s_stack + threadIdx.x, blockDim.x);
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_trace(RbDeviceBvh bvh, Rb
 				if(wantsLeaf) finished = rb_phase_leaf<false, false>(T, bvh, ray, nullptr);
 			} else if(active && !wantsLeaf) {
 				for(int k = 0; k < nodeSteps; ++k) {
-					finished = rb_phase_node<false, ORDERED>(T, bvh, ray, st, nullptr);
+					finished = rb_phase_node<false, ORDERED, BLOCKS>(T, bvh, ray, st, nullptr);
 					if(finished || rb_wants_leaf(T)) break;
 				}
 			}
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK, RB_PT_SHADE_MIN_BLOCKS) rb_k_pt_s
 // unmasked (or UV-less) occluder blocks, a masked one is looked up in its alpha channel and walked through when
 // alpha < 0.01. When no object of the scene is masked the walk degenerates to "is there any hit", so the any-hit
 // traversal (identical accept/reject decisions, early exit) is used instead (MASKED = false).
-template<bool MASKED, bool ORDERED>
+template<bool MASKED, bool ORDERED, bool BLOCKS>
 __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shadow(RbDeviceBvh bvh, RbPathBuffers pb, RbSceneDev sc, uint32_t did, int threshold, int leafVotes, int nodeSteps, unsigned long long * __restrict__ stats) {
 	extern __shared__ int s_stack[];
 	const RbStack st		= rb_make_stack(s_stack + threadIdx.x, blockDim.x);
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shadow(RbDeviceBvh bvh, R
 				if(wantsLeaf) done = rb_phase_leaf<!MASKED, false>(T, bvh, ray, nullptr);
 			} else if(active && !wantsLeaf) {
 				for(int k = 0; k < nodeSteps; ++k) {
-					done = rb_phase_node<false, ORDERED>(T, bvh, ray, st, nullptr);
+					done = rb_phase_node<false, ORDERED, BLOCKS>(T, bvh, ray, st, nullptr);
 					if(done || rb_wants_leaf(T)) break;
 				}
 			}
@@ -677,12 +677,14 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 
 		const size_t smem = rb_trace_smem_bytes(rc, RB_PT_BLOCK);
 		unsigned gridTrace = 0, gridShadow = 0, gridFlat = unsigned(pt->sms * 8);
-		auto kTrace = ordered ? rb_k_pt_trace<true> : rb_k_pt_trace<false>;
+		const bool blocks = rc->dev.rootLevels > 0; // many-mesh scenes: kernels compiled with the root-block skipping
+		auto kTrace = blocks ? (ordered ? rb_k_pt_trace<true, true> : rb_k_pt_trace<false, true>) : (ordered ? rb_k_pt_trace<true, false> : rb_k_pt_trace<false, false>);
 		st = rb_pt_grid(kTrace, smem, pt->sms, gridTrace);
 		if(st) return st;
 		const bool masked = sc->dev.anyMasked != 0;
 		// Unmasked scenes use any-hit shadow rays, whose result is order independent: always near-child-first.
-		auto kShadow = masked ? (ordered ? rb_k_pt_shadow<true, true> : rb_k_pt_shadow<true, false>) : rb_k_pt_shadow<false, true>;
+		auto kShadow = blocks ? (masked ? (ordered ? rb_k_pt_shadow<true, true, true> : rb_k_pt_shadow<true, false, true>) : rb_k_pt_shadow<false, true, true>)
+							  : (masked ? (ordered ? rb_k_pt_shadow<true, true, false> : rb_k_pt_shadow<true, false, false>) : rb_k_pt_shadow<false, true, false>);
 		st = rb_pt_grid(kShadow, smem, pt->sms, gridShadow);
 		if(st) return st;
 		const int votes = rc->leafVotes > 0 ? rc->leafVotes : 33;

@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_persistent(RbDevice
 // Phase-voting scheduler. Every live lane is waiting either for a node step or for a leaf step; the warp executes
 // the leaf phase once at least `leafVotes` lanes wait for it (or nobody wants a node), otherwise the node phase. Lanes
 // of the other kind idle for that iteration instead of the whole warp running at the pace of one lane's descent.
-template<bool ANY, bool ORDERED>
+template<bool ANY, bool ORDERED, bool BLOCKS>
 __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_phased(RbDeviceBvh bvh, const float * __restrict__ org, const float * __restrict__ dir, float mini, float maxi, unsigned int n, void * __restrict__ out, unsigned int * __restrict__ cursor, int threshold, int leafVotes, int nodeSteps) {
 	extern __shared__ int s_stack[];
 	const RbStack st		= rb_make_stack(s_stack + threadIdx.x, blockDim.x);
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_phased(RbDeviceBvh 
 				// Up to `nodeSteps` descents per vote: the vote, executed by all 32 lanes, costs about as much as a
 				// node step; a lane that reaches a leaf (or finishes) early sits out the remaining steps.
 				for(int k = 0; k < nodeSteps; ++k) {
-					finished = rb_phase_node<false, ORDERED>(T, bvh, ray, st, nullptr);
+					finished = rb_phase_node<false, ORDERED, BLOCKS>(T, bvh, ray, st, nullptr);
 					if(finished || rb_wants_leaf(T)) break;
 				}
 			}
@@ -698,7 +698,9 @@ static rb_status rb_launch_trace(const rb_raycaster * rc, const float * d_origin
 		return rb_launch_persistent<ANY>(rc, kernel, 2 * smem, 2, d_origins, d_directions, mini, maxi, nrays, d_out, s, rc->dualRefill, rc->leafVotes > 0 ? rc->leafVotes : 24);
 	}
 	if(rc->persistent && rc->leafVotes > 0) {
-		auto kernel = ordered ? rb_k_trace_phased<ANY, true> : rb_k_trace_phased<ANY, false>;
+		// Handles that carry root blocks (many meshes in a spatially coherent order) use the kernels compiled with them.
+		auto kernel = rc->dev.rootLevels > 0 ? (ordered ? rb_k_trace_phased<ANY, true, true> : rb_k_trace_phased<ANY, false, true>)
+											 : (ordered ? rb_k_trace_phased<ANY, true, false> : rb_k_trace_phased<ANY, false, false>);
 		return rb_launch_persistent<ANY>(rc, kernel, smem, 1, d_origins, d_directions, mini, maxi, nrays, d_out, s, rc->fetchThreshold, rc->leafVotes, rc->nodeSteps > 0 ? rc->nodeSteps : 1);
 	}
 	if(rc->persistent) {

@@ -183,12 +183,14 @@ RB_D void rb_traversal_init(RbTraversal & T, const RbDeviceBvh & bvh, float mini
 // of such a block, the block's box is tested first and the whole block is skipped on a miss. The visiting order of the
 // roots that are entered is unchanged, and no root the reference would enter is skipped: the slab test is monotone in
 // the box (every fp32 operation in it is), so a ray that misses the union misses each member — for regular rays; the
-// NaN-carrying irregular rays take the plain loop.
-template<bool REGULAR, bool COUNT>
+// NaN-carrying irregular rays take the plain loop. BLOCKS is a template switch: with the block code inlined the node
+// step of every kernel runs 15 % slower (register allocation of the hot loop; out of line it is worse still, the call
+// forces the traversal state into local memory), so only handles that carry blocks launch the BLOCKS = true kernels.
+template<bool REGULAR, bool COUNT, bool BLOCKS>
 RB_D int rb_next_root(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ray, float maxi, RbWork * work) {
 	while(T.root > 0) {
 		const int r = T.root - 1;
-		if(REGULAR && bvh.rootLevels > 0) {
+		if(BLOCKS && REGULAR && bvh.rootLevels > 0) {
 			int k		 = min(__ffs(r + 1) - 1, bvh.rootLevels); // r + 1 is a multiple of 2^k
 			bool skipped = false;
 			for(; k >= 1; --k) {
@@ -220,7 +222,7 @@ RB_D bool rb_step_exact(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & 
 		if(!rb_stack_empty(T, st)) {
 			cur = rb_pop(T, st);
 		} else {
-			cur = rb_next_root<REGULAR, COUNT>(T, bvh, ray, T.maxi0, work);
+			cur = rb_next_root<REGULAR, COUNT, false>(T, bvh, ray, T.maxi0, work);
 			if(cur == RB_REF_NONE) {
 				return true;
 			}
@@ -311,7 +313,7 @@ RB_D bool rb_step_ordered(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay 
 		if(!rb_stack_empty(T, st)) {
 			cur = rb_pop(T, st);
 		} else {
-			cur = rb_next_root<REGULAR, COUNT>(T, bvh, ray, T.maxi, work);
+			cur = rb_next_root<REGULAR, COUNT, false>(T, bvh, ray, T.maxi, work);
 			if(cur == RB_REF_NONE) {
 				return true;
 			}
@@ -405,14 +407,14 @@ RB_D void rb_node_test(const RbRay & ray, const float4 & n0, const float4 & n1, 
 RB_D bool rb_wants_leaf(const RbTraversal & T) { return T.cur < 0; }
 
 // Returns true when the traversal has finished (no node left).
-template<bool COUNT, bool ORDERED, bool REGULAR>
+template<bool COUNT, bool ORDERED, bool REGULAR, bool BLOCKS>
 RB_D bool rb_phase_node_t(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ray, const RbStack & st, RbWork * work) {
 	int cur = T.cur;
 	if(cur == RB_REF_NONE) {
 		if(!rb_stack_empty(T, st)) {
 			cur = rb_pop(T, st);
 		} else {
-			cur = rb_next_root<REGULAR, COUNT>(T, bvh, ray, ORDERED ? T.maxi : T.maxi0, work);
+			cur = rb_next_root<REGULAR, COUNT, BLOCKS>(T, bvh, ray, ORDERED ? T.maxi : T.maxi0, work);
 			if(cur == RB_REF_NONE) return true;
 		}
 	}
@@ -475,10 +477,10 @@ RB_D bool rb_phase_leaf(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & 
 	return false;
 }
 
-template<bool COUNT, bool ORDERED>
+template<bool COUNT, bool ORDERED, bool BLOCKS = false>
 RB_D bool rb_phase_node(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ray, const RbStack & st, RbWork * work) {
-	if(ray.regular) return rb_phase_node_t<COUNT, ORDERED, true>(T, bvh, ray, st, work);
-	return rb_phase_node_t<COUNT, ORDERED, false>(T, bvh, ray, st, work);
+	if(ray.regular) return rb_phase_node_t<COUNT, ORDERED, true, BLOCKS>(T, bvh, ray, st, work);
+	return rb_phase_node_t<COUNT, ORDERED, false, BLOCKS>(T, bvh, ray, st, work);
 }
 
 // One traversal step. The NaN-faithful box test is only compiled into the copy taken by irregular rays (a direction
