@@ -25,7 +25,7 @@ inline float maxf(float x, float y) { return (x < y) ? y : x; } // glm::max
 
 // What the builder reads and permutes.
 struct BuildInput {
-	const std::vector<rb_tri> * tris;
+	const RbTriVec * tris;
 	const float * centroid[3];
 	uint32_t * order;
 };
@@ -33,7 +33,7 @@ struct BuildInput {
 // Processes ONE set as Raycaster.cpp:73-139 does: box, leaf test, axis, mean partition / median fallback. Fills `node`
 // (children left unset) and returns the split position, or SIZE_MAX for a leaf.
 size_t split_set(const BuildInput & in, size_t begin, size_t count, rb_node & node) {
-	const std::vector<rb_tri> & tris = *in.tris;
+	const RbTriVec & tris = *in.tris;
 	uint32_t * first = in.order + begin;
 	uint32_t * last	 = first + count;
 	// Union of the triangle boxes (BoundingBox::merge, Bounds.cpp:17-20).
@@ -228,7 +228,7 @@ void rb_host_build_reference(rb_raycaster * rc) {
 	for(const Task & t : tasks) maxDepth = std::max(maxDepth, t.tree.maxDepth);
 
 	// Apply the permutation to the triangle records.
-	std::vector<rb_tri> sorted(ntris);
+	RbTriVec sorted(ntris);
 	rb_parallel_for(ntris, size_t(1) << 16, [&](size_t b, size_t e) {
 		for(size_t i = b; i < e; ++i) sorted[i] = rc->tris[order[i]];
 	});

@@ -6,8 +6,10 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <memory>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 // ---------------------------------------------------------------- errors
@@ -50,11 +52,28 @@ void rb_parallel_for(size_t n, size_t grain, F && fn) {
 	for(auto & th : pool) th.join();
 }
 
+// std::vector whose resize() leaves new elements uninitialised: a 10M-triangle mesh is 640 MB of records that the
+// next (multi-threaded) loop overwrites anyway; value-initialising them first costs a single-threaded pass and all
+// the page faults on one core.
+template<typename T>
+struct RbNoInitAlloc : std::allocator<T> {
+	template<typename U>
+	struct rebind {
+		using other = RbNoInitAlloc<U>;
+	};
+	template<typename U, typename... Args>
+	void construct(U * p, Args &&... args) {
+		if(sizeof...(Args) == 0) ::new(static_cast<void *>(p)) U;
+		else ::new(static_cast<void *>(p)) U(std::forward<Args>(args)...);
+	}
+};
+using RbTriVec = std::vector<rb_tri, RbNoInitAlloc<rb_tri>>;
+
 // ---------------------------------------------------------------- raycaster handle
 struct rb_raycaster {
 	// Host mirror in the reference's own format (kept so RaycasterVisualisation-style consumers can read it back).
 	std::vector<float> verts; // merged world-space vertices, xyz
-	std::vector<rb_tri> tris;
+	RbTriVec tris;
 	std::vector<rb_node> nodes;
 	uint32_t meshCount = 0;
 	std::vector<uint64_t> meshFirst, meshTris; // per mesh: first triangle and triangle count (stable across rebuilds)
