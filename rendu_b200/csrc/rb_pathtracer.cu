@@ -676,7 +676,11 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 		}
 
 		const size_t smem = rb_trace_smem_bytes(rc, RB_PT_BLOCK);
-		unsigned gridTrace = 0, gridShadow = 0, gridFlat = unsigned(pt->sms * 8);
+		// Grid-stride kernels are launched as exactly one wave of resident CTAs: with 8 CTAs per SM requested and 6
+		// resident (shade: 80 registers) a third of the CTAs would run alone in a second round.
+		unsigned gridTrace = 0, gridShadow = 0, gridShade = 0, gridFlat = unsigned(pt->sms * 8);
+		st = rb_pt_grid(rb_k_pt_shade, 0, pt->sms, gridShade);
+		if(st) return st;
 		const bool blocks = rc->dev.rootLevels > 0; // many-mesh scenes: kernels compiled with the root-block skipping
 		auto kTrace = blocks ? (ordered ? rb_k_pt_trace<true, true> : rb_k_pt_trace<false, true>) : (ordered ? rb_k_pt_trace<true, false> : rb_k_pt_trace<false, false>);
 		st = rb_pt_grid(kTrace, smem, pt->sms, gridTrace);
@@ -711,7 +715,7 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 				++launches;
 				for(uint32_t did = 0; did < depth; ++did) {
 					kTrace<<<gridTrace, RB_PT_BLOCK, smem, ls>>>(rc->dev, pb, pb.queue[did & 1u], did, threshold, votes, steps, pt->d_stats);
-					rb_k_pt_shade<<<gridFlat, RB_PT_BLOCK, 0, ls>>>(f, b, pb, sc->dev, did, pt->d_stats);
+					rb_k_pt_shade<<<gridShade, RB_PT_BLOCK, 0, ls>>>(f, b, pb, sc->dev, did, pt->d_stats);
 					launches += 2;
 					if(sc->dev.nLights > 0) {
 						kShadow<<<gridShadow, RB_PT_BLOCK, smem, ls>>>(rc->dev, pb, sc->dev, did, threshold, votes, steps, pt->d_stats);
