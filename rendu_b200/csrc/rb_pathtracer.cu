@@ -486,7 +486,8 @@ struct rb_pathtracer {
 	RbPathBuffers pb[RB_PT_LANES] = {};
 	size_t capacity[RB_PT_LANES]  = {};
 	cudaStream_t lane[RB_PT_LANES] = {};
-	cudaEvent_t fork = nullptr, join[RB_PT_LANES] = {};
+	cudaStream_t side[RB_PT_LANES] = {}; // shadow wavefront of a lane: runs beside the next level's closest-hit wavefront
+	cudaEvent_t fork = nullptr, join[RB_PT_LANES] = {}, shaded[RB_PT_LANES] = {}, shadowed[RB_PT_LANES] = {};
 	int lanes = 2;
 	unsigned long long * d_stats = nullptr;
 	rb_render_stats stats = {};
@@ -552,7 +553,10 @@ extern "C" rb_status rb_pathtracer_create(rb_scene * scene, rb_pathtracer ** out
 	bool ok = cudaEventCreateWithFlags(&pt->fork, cudaEventDisableTiming) == cudaSuccess;
 	for(int l = 0; l < RB_PT_LANES; ++l) {
 		ok = ok && cudaStreamCreateWithFlags(&pt->lane[l], cudaStreamNonBlocking) == cudaSuccess;
+		ok = ok && cudaStreamCreateWithFlags(&pt->side[l], cudaStreamNonBlocking) == cudaSuccess;
 		ok = ok && cudaEventCreateWithFlags(&pt->join[l], cudaEventDisableTiming) == cudaSuccess;
+		ok = ok && cudaEventCreateWithFlags(&pt->shaded[l], cudaEventDisableTiming) == cudaSuccess;
+		ok = ok && cudaEventCreateWithFlags(&pt->shadowed[l], cudaEventDisableTiming) == cudaSuccess;
 	}
 	if(!ok) {
 		rb_pathtracer_destroy(pt);
@@ -571,7 +575,10 @@ extern "C" void rb_pathtracer_destroy(rb_pathtracer * pt) {
 		if(pt->fork) cudaEventDestroy(pt->fork);
 		for(int l = 0; l < RB_PT_LANES; ++l) {
 			if(pt->join[l]) cudaEventDestroy(pt->join[l]);
+			if(pt->shaded[l]) cudaEventDestroy(pt->shaded[l]);
+			if(pt->shadowed[l]) cudaEventDestroy(pt->shadowed[l]);
 			if(pt->lane[l]) cudaStreamDestroy(pt->lane[l]);
+			if(pt->side[l]) cudaStreamDestroy(pt->side[l]);
 		}
 	}
 	delete pt;
@@ -713,15 +720,30 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 				RB_CUDA(cudaMemsetAsync(pb.counters, 0, 4 * (RB_PT_MAX_DEPTH + 1) * sizeof(uint32_t), ls));
 				rb_k_pt_raygen<<<gridFlat, RB_PT_BLOCK, 0, ls>>>(f, b, pb);
 				++launches;
+				// The shadow wavefront of level d only feeds the colour that shade(d+1) reads, so it runs on a side stream
+				// next to trace(d+1): trace -> shade -> [shadow || next trace] -> shade ...
+				// (small batches stay on one stream: the event traffic would cost more than the overlap gives)
+				const cudaStream_t ss = (uint64_t(b.npixels) * b.schunk >= (uint64_t(1) << 20)) ? pt->side[l] : ls;
+				bool shadowPending	  = false;
 				for(uint32_t did = 0; did < depth; ++did) {
 					kTrace<<<gridTrace, RB_PT_BLOCK, smem, ls>>>(rc->dev, pb, pb.queue[did & 1u], did, threshold, votes, steps, pt->d_stats);
+					if(shadowPending) RB_CUDA(cudaStreamWaitEvent(ls, pt->shadowed[l], 0)); // shade overwrites the shadow entries
 					rb_k_pt_shade<<<gridShade, RB_PT_BLOCK, 0, ls>>>(f, b, pb, sc->dev, did, pt->d_stats);
 					launches += 2;
 					if(sc->dev.nLights > 0) {
-						kShadow<<<gridShadow, RB_PT_BLOCK, smem, ls>>>(rc->dev, pb, sc->dev, did, threshold, votes, steps, pt->d_stats);
+						if(ss != ls) {
+							RB_CUDA(cudaEventRecord(pt->shaded[l], ls));
+							RB_CUDA(cudaStreamWaitEvent(ss, pt->shaded[l], 0));
+						}
+						kShadow<<<gridShadow, RB_PT_BLOCK, smem, ss>>>(rc->dev, pb, sc->dev, did, threshold, votes, steps, pt->d_stats);
+						if(ss != ls) {
+							RB_CUDA(cudaEventRecord(pt->shadowed[l], ss));
+							shadowPending = true;
+						}
 						++launches;
 					}
 				}
+				if(shadowPending) RB_CUDA(cudaStreamWaitEvent(ls, pt->shadowed[l], 0));
 				rb_k_pt_accumulate<<<gridFlat, RB_PT_BLOCK, 0, ls>>>(f, b, pb, d_sum);
 				++launches;
 				RB_CUDA(cudaGetLastError());
