@@ -229,6 +229,12 @@ RB_API rb_status rb_scene_add_light(rb_scene * sc, const rb_light_desc * desc);
 RB_API rb_status rb_scene_set_background(rb_scene * sc, uint32_t mode, const float color[3], const int32_t * textures, uint32_t ntextures, const float sun_direction[3], int32_t sky_lut);
 /* Upload everything and build the raycaster (addMesh per object + updateHierarchy, PathTracer.cpp:11-21). */
 RB_API rb_status rb_scene_commit(rb_scene * sc, rb_build_mode mode);
+/* Lights and background may be edited after the commit — the reference reads them through the Scene at render time
+ * (PathTracer.cpp:23-55, :232-255), so whatever its caller changed between two render() calls shows in the next frame:
+ * rb_scene_clear_lights + rb_scene_add_light and / or rb_scene_set_background, then rb_scene_sync (the next render
+ * also does it). Only the two small tables are re-uploaded; geometry, textures and the hierarchy stay. */
+RB_API rb_status rb_scene_clear_lights(rb_scene * sc);
+RB_API rb_status rb_scene_sync(rb_scene * sc);
 /* The scene's raycaster (owned by the scene) — PathTracer::raycaster(). */
 RB_API rb_raycaster * rb_scene_raycaster(rb_scene * sc);
 

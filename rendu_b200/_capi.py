@@ -100,6 +100,8 @@ def lib():
         "rb_scene_add_light": (C.c_int, [vp, C.POINTER(LightDesc)]),
         "rb_scene_set_background": (C.c_int, [vp, u32, vp, vp, u32, vp, i32]),
         "rb_scene_commit": (C.c_int, [vp, C.c_int]),
+        "rb_scene_clear_lights": (C.c_int, [vp]),
+        "rb_scene_sync": (C.c_int, [vp]),
         "rb_scene_raycaster": (vp, [vp]),
         "rb_pathtracer_create": (C.c_int, [vp, C.POINTER(vp)]),
         "rb_pathtracer_destroy": (None, [vp]),

@@ -645,6 +645,10 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 	if(st) return st;
 	cudaStream_t s		 = static_cast<cudaStream_t>(stream);
 	rb_scene * sc		 = pt->scene;
+	if(sc->tablesDirty) { // lights / background edited since the last render
+		st = rb_scene_sync(sc);
+		if(st) return st;
+	}
 	rb_raycaster * rc	 = sc->raycaster;
 	const bool ordered	 = opts ? (opts->trace_mode == RB_TRACE_ORDERED) : false;
 	// Wavefront queues are shorter and more varied than the raycaster's batches: a slightly earlier refill and fewer

@@ -133,7 +133,8 @@ extern "C" rb_status rb_scene_add_object(rb_scene * sc, const rb_object_desc * d
 	o.dev.texRmao	= d->tex_rmao;
 	o.dev.flags		= (d->emissive ? RB_OBJ_EMISSIVE : 0u) | (d->masked ? RB_OBJ_MASKED : 0u) | (d->use_texcoords ? RB_OBJ_USE_UV : 0u);
 	sc->objects.push_back(std::move(o));
-	sc->committed = false;
+	sc->committed		  = false;
+	sc->geometryCommitted = false;
 	return RB_OK;
 }
 
@@ -154,7 +155,8 @@ extern "C" rb_status rb_scene_add_light(rb_scene * sc, const rb_light_desc * d) 
 	l.cosOuterCos = std::cos(l.outerCos);
 	l.innerCos	  = std::cos(d->inner_angle);
 	sc->lights.push_back(l);
-	sc->committed = false;
+	sc->tablesDirty = true;
+	if(!sc->geometryCommitted) sc->committed = false;
 	return RB_OK;
 }
 
@@ -173,8 +175,9 @@ extern "C" rb_status rb_scene_set_background(rb_scene * sc, uint32_t mode, const
 		sc->sunDir[k]  = sun_direction ? sun_direction[k] : 0.0f;
 	}
 	for(uint32_t k = 0; k < 6; ++k) sc->bgTex[k] = (k < need) ? textures[k] : -1;
-	sc->skyLut	  = sky_lut;
-	sc->committed = false;
+	sc->skyLut		= sky_lut;
+	sc->tablesDirty = true;
+	if(!sc->geometryCommitted) sc->committed = false;
 	return RB_OK;
 }
 
@@ -264,7 +267,51 @@ extern "C" rb_status rb_scene_commit(rb_scene * sc, rb_build_mode mode) {
 	for(int k = 0; k < 6; ++k) dv.bgTex[k] = sc->bgTex[k];
 	dv.skyLut	 = sc->skyLut;
 	dv.anyMasked = anyMasked ? 1u : 0u;
-	sc->committed = true;
+	sc->committed		  = true;
+	sc->geometryCommitted = true;
+	sc->tablesDirty		  = false;
+	return RB_OK;
+}
+
+extern "C" rb_status rb_scene_clear_lights(rb_scene * sc) {
+	if(!sc) return rb_fail(RB_ERR_INVALID, "rb_scene_clear_lights: null handle");
+	sc->lights.clear();
+	sc->tablesDirty = true;
+	return RB_OK;
+}
+
+// Lights and background of a committed scene: the reference reads them through the Scene at render time
+// (PathTracer.cpp:23-55, :232-255), so a caller may edit them between two renders. Re-uploads the two small tables;
+// geometry, textures and the hierarchy are untouched.
+extern "C" rb_status rb_scene_sync(rb_scene * sc) {
+	if(!sc) return rb_fail(RB_ERR_INVALID, "rb_scene_sync: null handle");
+	RB_REQUIRE_DEVICE();
+	if(!sc->geometryCommitted) return rb_fail(RB_ERR_INVALID, "rb_scene_sync: call rb_scene_commit first");
+	if(!sc->tablesDirty) return RB_OK;
+	if(sc->bgMode == RB_BG_IMAGE || sc->bgMode == RB_BG_SKYBOX) {
+		const int need = sc->bgMode == RB_BG_IMAGE ? 1 : 6;
+		for(int k = 0; k < need; ++k) {
+			if(sc->bgTex[k] < 0 || sc->bgTex[k] >= int32_t(sc->textures.size())) return rb_fail(RB_ERR_INVALID, "rb_scene_sync: background texture id %d out of range", sc->bgTex[k]);
+		}
+	}
+	RB_CUDA(cudaSetDevice(sc->raycaster->device));
+	RB_CUDA(cudaDeviceSynchronize()); // a render may still be reading the old light table
+	cudaFree(sc->d_lights);
+	sc->d_lights = nullptr;
+	rb_status st = rb_upload(&sc->d_lights, sc->lights.data(), sc->lights.size() * sizeof(RbLight));
+	if(st) return st;
+	RbSceneDev & dv = sc->dev;
+	dv.lights  = sc->d_lights;
+	dv.nLights = int(sc->lights.size());
+	dv.bgMode  = sc->bgMode;
+	for(int k = 0; k < 3; ++k) {
+		dv.bgColor[k] = sc->bgColor[k];
+		dv.sunDir[k]  = sc->sunDir[k];
+	}
+	for(int k = 0; k < 6; ++k) dv.bgTex[k] = sc->bgTex[k];
+	dv.skyLut		= sc->skyLut;
+	sc->tablesDirty = false;
+	sc->committed	= true;
 	return RB_OK;
 }
 

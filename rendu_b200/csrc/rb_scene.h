@@ -24,6 +24,8 @@ struct rb_scene {
 	int32_t bgTex[6] = {-1, -1, -1, -1, -1, -1};
 	int32_t skyLut	 = -1;
 	bool committed	 = false;
+	bool geometryCommitted = false; // objects/textures are on the device; lights / background may still be stale
+	bool tablesDirty = false;		// lights or background changed since the last upload (rb_scene_sync)
 
 	rb_raycaster * raycaster = nullptr;
 	float * d_texels		 = nullptr;

@@ -70,30 +70,7 @@ PathTracer::PathTracer(const std::shared_ptr<Scene> & scene) {
 		d.use_texcoords	 = (obj.useTexCoords() && d.texcoords) ? 1u : 0u;
 		if(!ok(rb_scene_add_object(_deviceScene, &d), "object upload")) return;
 	}
-	for(const auto & light : scene->lights) {
-		rb_light_desc d;
-		std::memset(&d, 0, sizeof(d));
-		d.casts_shadow = light->castsShadow() ? 1u : 0u;
-		for(int k = 0; k < 3; ++k) d.intensity[k] = light->intensity()[k];
-		if(const PointLight * p = dynamic_cast<const PointLight *>(light.get())) {
-			d.kind = RB_LIGHT_POINT;
-			for(int k = 0; k < 3; ++k) d.position[k] = p->position()[k];
-			d.radius = p->radius();
-		} else if(const SpotLight * s = dynamic_cast<const SpotLight *>(light.get())) {
-			d.kind = RB_LIGHT_SPOT;
-			for(int k = 0; k < 3; ++k) {
-				d.position[k]  = s->position()[k];
-				d.direction[k] = s->direction()[k];
-			}
-			d.radius	  = s->radius();
-			d.inner_angle = s->angles()[0];
-			d.outer_angle = s->angles()[1];
-		} else if(const DirectionalLight * dl = dynamic_cast<const DirectionalLight *>(light.get())) {
-			d.kind = RB_LIGHT_DIRECTIONAL;
-			for(int k = 0; k < 3; ++k) d.direction[k] = dl->direction()[k];
-		}
-		if(!ok(rb_scene_add_light(_deviceScene, &d), "light upload")) return;
-	}
+	if(!uploadLights()) return;
 	{
 		const Material & bg = scene->background->material();
 		float color[3]		= {0.0f, 0.0f, 0.0f}, sun[3] = {0.0f, 1.0f, 0.0f};
@@ -139,6 +116,37 @@ PathTracer::~PathTracer() {
 	if(_deviceScene) rb_scene_destroy(_deviceScene); // also frees the raycaster _raycaster merely adopted
 }
 
+// scene->lights flattened for the device. Called at construction and again before every render: the reference reads
+// the lights through the shared Scene inside render() (PathTracer.cpp:232-255), so edits made between two frames count.
+bool PathTracer::uploadLights() {
+	if(!ok(rb_scene_clear_lights(_deviceScene), "light upload")) return false;
+	for(const auto & light : _scene->lights) {
+		rb_light_desc d;
+		std::memset(&d, 0, sizeof(d));
+		d.casts_shadow = light->castsShadow() ? 1u : 0u;
+		for(int k = 0; k < 3; ++k) d.intensity[k] = light->intensity()[k];
+		if(const PointLight * p = dynamic_cast<const PointLight *>(light.get())) {
+			d.kind = RB_LIGHT_POINT;
+			for(int k = 0; k < 3; ++k) d.position[k] = p->position()[k];
+			d.radius = p->radius();
+		} else if(const SpotLight * s = dynamic_cast<const SpotLight *>(light.get())) {
+			d.kind = RB_LIGHT_SPOT;
+			for(int k = 0; k < 3; ++k) {
+				d.position[k]  = s->position()[k];
+				d.direction[k] = s->direction()[k];
+			}
+			d.radius	  = s->radius();
+			d.inner_angle = s->angles()[0];
+			d.outer_angle = s->angles()[1];
+		} else if(const DirectionalLight * dl = dynamic_cast<const DirectionalLight *>(light.get())) {
+			d.kind = RB_LIGHT_DIRECTIONAL;
+			for(int k = 0; k < 3; ++k) d.direction[k] = dl->direction()[k];
+		}
+		if(!ok(rb_scene_add_light(_deviceScene, &d), "light upload")) return false;
+	}
+	return true;
+}
+
 void PathTracer::render(const Camera & camera, size_t samples, size_t depth, Image & render) {
 	if(!_scene || !_device) {
 		Log::Error() << "[PathTracer] No scene available." << std::endl;
@@ -169,6 +177,7 @@ void PathTracer::render(const Camera & camera, size_t samples, size_t depth, Ima
 	opts.tile_count	  = _tile[2];
 	opts.sample_index = _split[0];
 	opts.sample_count = _split[1];
+	if(!uploadLights()) return;
 	Query timer;
 	timer.begin();
 	ok(rb_pathtracer_render(_device, &cam, render.width, render.height, uint32_t(samples), uint32_t(depth), render.components, render.pixels.data(), &opts), "render");

@@ -27,6 +27,8 @@ public:
 	void setSampleSplit(unsigned int index, unsigned int count) { _split[0] = index; _split[1] = count; }
 
 private:
+	bool uploadLights();
+
 	Raycaster _raycaster;
 	std::shared_ptr<Scene> _scene;
 	rb_scene * _deviceScene = nullptr;

@@ -61,18 +61,9 @@ class Scene:
             d.use_texcoords = 1 if o["use_uv"] else 0
             self._keep.append((arrs, idx))
             check(L.rb_scene_add_object(self._h, C.byref(d)))
-        for l in description["lights"]:
-            d = LightDesc()
-            d.kind, d.casts_shadow = int(l["kind"]), 1 if l["casts_shadow"] else 0
-            d.intensity, d.position, d.direction = _f3(l["intensity"]), _f3(l["position"]), _f3(l["direction"])
-            d.radius, d.inner_angle, d.outer_angle = float(l["radius"]), float(l["inner"]), float(l["outer"])
-            check(L.rb_scene_add_light(self._h, C.byref(d)))
-        bg = description["background"]
-        texs = np.array([tid(i) for i in bg.get("textures", [])], np.int32)
-        color = np.asarray(bg.get("color", (0, 0, 0)), np.float32)
-        sun = np.asarray(bg.get("sun", (0, 1, 0)), np.float32)
-        lut = tid(bg.get("sky_lut", -1))
-        check(L.rb_scene_set_background(self._h, int(bg["mode"]), ptr(color), ptr(texs) if texs.size else None, texs.size, ptr(sun), lut))
+        self._tex_ids = tex_ids
+        self._add_lights(description["lights"])
+        self._set_background(description["background"])
         check(L.rb_scene_commit(self._h, int(build_mode)))
         self._keep = []
 
@@ -83,6 +74,35 @@ class Scene:
             except Exception:
                 pass
             self._h = None
+
+    def _tid(self, i):
+        return self._tex_ids[i] if i is not None and i >= 0 else -1
+
+    def _add_lights(self, lights):
+        for l in lights:
+            d = LightDesc()
+            d.kind, d.casts_shadow = int(l["kind"]), 1 if l["casts_shadow"] else 0
+            d.intensity, d.position, d.direction = _f3(l["intensity"]), _f3(l["position"]), _f3(l["direction"])
+            d.radius, d.inner_angle, d.outer_angle = float(l["radius"]), float(l["inner"]), float(l["outer"])
+            check(lib().rb_scene_add_light(self._h, C.byref(d)))
+
+    def _set_background(self, bg):
+        texs = np.array([self._tid(i) for i in bg.get("textures", [])], np.int32)
+        color = np.asarray(bg.get("color", (0, 0, 0)), np.float32)
+        sun = np.asarray(bg.get("sun", (0, 1, 0)), np.float32)
+        lut = self._tid(bg.get("sky_lut", -1))
+        check(lib().rb_scene_set_background(self._h, int(bg["mode"]), ptr(color), ptr(texs) if texs.size else None, texs.size, ptr(sun), lut))
+
+    def set_lights(self, lights):
+        """Replace the lights of a committed scene (the reference reads scene->lights at render time, PathTracer.cpp:232)."""
+        check(lib().rb_scene_clear_lights(self._h))
+        self._add_lights(lights)
+        check(lib().rb_scene_sync(self._h))
+
+    def set_background(self, bg):
+        """Replace the background of a committed scene (texture ids refer to the textures uploaded at construction)."""
+        self._set_background(bg)
+        check(lib().rb_scene_sync(self._h))
 
     def raycaster(self):
         return Raycaster(_handle=lib().rb_scene_raycaster(self._h), _owner=self)

@@ -249,6 +249,41 @@ def test_batches_and_lanes_do_not_change_the_image(monkeypatch):
     np.testing.assert_allclose(chunked, whole, rtol=2e-5, atol=1e-6)
 
 
+def test_lights_and_background_follow_edits_between_renders():
+    """The reference reads scene->lights and the background through the shared Scene inside render(), so an edit between
+    two frames shows in the next one. Here: rb_scene_clear_lights / add_light / set_background + rb_scene_sync on a
+    committed scene give exactly the image of a scene built with the new values; geometry is not rebuilt."""
+    import copy
+    desc, cam, _ = golden_scene("cornellbox")
+    sc = rpt.Scene(desc)
+    pt = rpt.PathTracer(sc)
+    img0 = np.zeros((40, 48, 3), np.float32)
+    pt.render(cam, 16, 4, img0, rpt.make_opts(seed=6))
+    # brighter, moved light; another background colour
+    d2 = copy.deepcopy(desc)
+    for l in d2["lights"]:
+        l["intensity"] = (np.asarray(l["intensity"], np.float32) * np.float32(2.5)).astype(np.float32)
+        l["position"] = (np.asarray(l["position"], np.float32) + np.array([0.1, -0.05, 0.0], np.float32)).astype(np.float32)
+    d2["background"]["color"] = np.array([0.2, 0.4, 0.9], np.float32)
+    sc.set_lights(d2["lights"])
+    sc.set_background(d2["background"])
+    img1 = np.zeros_like(img0)
+    pt.render(cam, 16, 4, img1, rpt.make_opts(seed=6))
+    fresh, _ = gpu_render(d2, cam, 48, 40, 16, 4, seed=6)
+    assert np.array_equal(img1.view(np.uint32), fresh.view(np.uint32)) and not np.array_equal(img1, img0)
+    # no lights at all: next-event estimation and the shadow wavefront switch off
+    sc.set_lights([])
+    img2 = np.zeros_like(img0)
+    pt.render(cam, 16, 4, img2, rpt.make_opts(seed=6))
+    assert pt.stats()["rays_shadow"] == 0 and img2.mean() < img1.mean()
+    # and back
+    sc.set_lights(desc["lights"])
+    sc.set_background(desc["background"])
+    img3 = np.zeros_like(img0)
+    pt.render(cam, 16, 4, img3, rpt.make_opts(seed=6))
+    assert np.array_equal(img3.view(np.uint32), img0.view(np.uint32))
+
+
 def test_output_stage_on_device():
     """Fused tonemap + sRGB + 8-bit conversion kernel vs the reference's bytes. expf/powf may differ from glibc in the last
     ulp, which can move a value across a truncation boundary: at most one code value, in a vanishing fraction of bytes."""
