@@ -17,7 +17,8 @@ def pytest_configure(config):
         subprocess.check_call(["make", "-s", "-j8", "-C", os.path.join(ROOT, "rendu_b200", "csrc")])
     if not os.path.exists(os.path.join(ROOT, "oracle", "librendu_oracle.so")):
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
-    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "librendu_ref.so")) and os.path.isdir("/root/reference/src"):
+    ref_libs = [os.path.join(ROOT, "oracle", "_ref", n) for n in ("librendu_ref.so", "librendu_refvis.so")]
+    if not all(os.path.exists(p) for p in ref_libs) and os.path.isdir("/root/reference/src"):
         subprocess.check_call(["bash", os.path.join(ROOT, "oracle", "build_ref.sh")])
 
 
