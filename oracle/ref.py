@@ -48,6 +48,10 @@ def lib():
 _vislib = None
 
 
+def vis_available():
+    return available() and os.path.exists(os.path.join(os.path.dirname(LIB_PATH), "librendu_refvis.so"))
+
+
 def vislib():
     """Second checker library: the reference's unmodified RaycasterVisualisation (oracle/ref_harness/refvis_api.cpp)."""
     global _vislib

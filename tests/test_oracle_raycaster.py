@@ -94,7 +94,7 @@ def test_oracle_ray_levels_match_reference_visualisation(name):
                 nxt += [int(o.nodes["left"][n]), int(o.nodes["right"][n])]
         frontier = nxt
     assert np.array_equal(np.array(level_counts, np.uint32), g[name + "_all_counts"])
-    if ref.available():
+    if ref.vis_available():
         r = ref.RefRaycaster()
         for pos, idx, model in case_meshes(c):
             r.add_mesh(pos, idx, model)
