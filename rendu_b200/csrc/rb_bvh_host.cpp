@@ -87,6 +87,124 @@ size_t split_set(const BuildInput & in, size_t begin, size_t count, rb_node & no
 	return split;
 }
 
+// The same step for the few very large sets at the top of the tree, on several threads, with the same result bit for
+// bit: min/max unions are associative; the centroid mean stays a sequential fp32 sum (its rounding depends on the order);
+// and libstdc++'s std::partition for bidirectional iterators (bits/stl_algo.h, __partition) is a two-pointer sweep whose
+// outcome has a closed form — with m elements satisfying the predicate, the k-th element of [0, m) that fails it (from
+// the left) is swapped with the k-th element of [m, n) that satisfies it (from the right), everything else stays — so
+// the two index lists are built with per-chunk counts and the swaps are applied in parallel.
+size_t split_set_parallel(const BuildInput & in, size_t begin, size_t count, rb_node & node) {
+	const RbTriVec & tris = *in.tris;
+	uint32_t * first = in.order + begin;
+	const size_t chunks = 64;
+	const size_t span	= (count + chunks - 1) / chunks;
+	// Union of the triangle boxes.
+	std::vector<float> plo(chunks * 3, 0.0f), phi(chunks * 3, 0.0f);
+	std::vector<uint8_t> used(chunks, 0);
+	rb_parallel_for(chunks, 1, [&](size_t cb, size_t ce) {
+		for(size_t c = cb; c < ce; ++c) {
+			const size_t b = c * span, e = std::min(count, b + span);
+			if(b >= e) continue;
+			float lo[3], hi[3];
+			const rb_tri & t0 = tris[first[b]];
+			for(int a = 0; a < 3; ++a) {
+				lo[a] = t0.bmin[a];
+				hi[a] = t0.bmax[a];
+			}
+			for(size_t k = b + 1; k < e; ++k) {
+				const rb_tri & t = tris[first[k]];
+				for(int a = 0; a < 3; ++a) {
+					lo[a] = minf(lo[a], t.bmin[a]);
+					hi[a] = maxf(hi[a], t.bmax[a]);
+				}
+			}
+			for(int a = 0; a < 3; ++a) {
+				plo[3 * c + a] = lo[a];
+				phi[3 * c + a] = hi[a];
+			}
+			used[c] = 1;
+		}
+	});
+	float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+	bool any = false;
+	for(size_t c = 0; c < chunks; ++c) { // chunk order = element order: minf/maxf pick the same values as the plain loop
+		if(!used[c]) continue;
+		for(int a = 0; a < 3; ++a) {
+			lo[a] = any ? minf(lo[a], plo[3 * c + a]) : plo[3 * c + a];
+			hi[a] = any ? maxf(hi[a], phi[3 * c + a]) : phi[3 * c + a];
+		}
+		any = true;
+	}
+	std::memcpy(node.bmin, lo, sizeof(lo));
+	std::memcpy(node.bmax, hi, sizeof(hi));
+	node.leaf = 0;
+	const float sx = hi[0] - lo[0], sy = hi[1] - lo[1], sz = hi[2] - lo[2];
+	const int axis = (sx >= sy && sx >= sz) ? 0 : (sy >= sz ? 1 : 2);
+	const float * c = in.centroid[axis];
+	float mean = 0.0f;
+	for(size_t k = 0; k < count; ++k) mean += c[first[k]];
+	mean /= float(count);
+	// Predicate counts per chunk -> m.
+	std::vector<size_t> trues(chunks + 1, 0);
+	rb_parallel_for(chunks, 1, [&](size_t cb, size_t ce) {
+		for(size_t ch = cb; ch < ce; ++ch) {
+			const size_t b = ch * span, e = std::min(count, b + span);
+			size_t n = 0;
+			for(size_t k = b; k < e; ++k) n += (c[first[k]] < mean) ? 1 : 0;
+			trues[ch + 1] = n;
+		}
+	});
+	for(size_t ch = 0; ch < chunks; ++ch) trues[ch + 1] += trues[ch];
+	const size_t m = trues[chunks];
+	size_t split  = m;
+	if(m != 0 && m != count) {
+		// leftFalse: positions < m failing the predicate, ascending; rightTrue: positions >= m satisfying it, ascending
+		// here and consumed from the back. Both have the same length.
+		std::vector<size_t> nFalse(chunks + 1, 0), nTrue(chunks + 1, 0);
+		rb_parallel_for(chunks, 1, [&](size_t cb, size_t ce) {
+			for(size_t ch = cb; ch < ce; ++ch) {
+				const size_t b = ch * span, e = std::min(count, b + span);
+				size_t f = 0, t = 0;
+				for(size_t k = b; k < e; ++k) {
+					const bool p = c[first[k]] < mean;
+					if(k < m) f += p ? 0 : 1;
+					else t += p ? 1 : 0;
+				}
+				nFalse[ch + 1] = f;
+				nTrue[ch + 1]  = t;
+			}
+		});
+		for(size_t ch = 0; ch < chunks; ++ch) {
+			nFalse[ch + 1] += nFalse[ch];
+			nTrue[ch + 1] += nTrue[ch];
+		}
+		const size_t swaps = nFalse[chunks];
+		std::vector<uint32_t> leftFalse(swaps), rightTrue(swaps);
+		rb_parallel_for(chunks, 1, [&](size_t cb, size_t ce) {
+			for(size_t ch = cb; ch < ce; ++ch) {
+				const size_t b = ch * span, e = std::min(count, b + span);
+				size_t f = nFalse[ch], t = nTrue[ch];
+				for(size_t k = b; k < e; ++k) {
+					const bool p = c[first[k]] < mean;
+					if(k < m) {
+						if(!p) leftFalse[f++] = uint32_t(k);
+					} else if(p) {
+						rightTrue[t++] = uint32_t(k);
+					}
+				}
+			}
+		});
+		rb_parallel_for(swaps, size_t(1) << 14, [&](size_t b, size_t e) {
+			for(size_t k = b; k < e; ++k) std::swap(first[leftFalse[k]], first[rightTrue[swaps - 1 - k]]);
+		});
+	} else {
+		// Everything on one side: the reference falls back to the median (Raycaster.cpp:116-123).
+		split = count / 2;
+		std::nth_element(first, first + split, first + count, [c](uint32_t a, uint32_t b) { return c[a] < c[b]; });
+	}
+	return split;
+}
+
 // The reference's LIFO loop on one sub-tree, with local numbering: nodes[0] is the set itself, its descendants follow
 // in the order the reference would emplace them (left child, right child, then the whole right sub-tree before the
 // left one). Because the loop is LIFO, that is also the order in which the global build creates them — contiguously.
@@ -170,7 +288,7 @@ void rb_host_build_reference(rb_raycaster * rc) {
 			continue;
 		}
 		rb_node node{};
-		const size_t split = split_set(in, cur.begin, cur.count, node);
+		const size_t split = (cur.count >= (size_t(1) << 17)) ? split_set_parallel(in, cur.begin, cur.count, node) : split_set(in, cur.begin, cur.count, node);
 		if(split != SIZE_MAX) {
 			maxDepth = std::max(maxDepth, cur.depth + 1);
 			const long l = long(upper.size()), r = l + 1;

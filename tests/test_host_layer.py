@@ -84,6 +84,25 @@ def test_host_builder_parallel_subtrees_keep_the_reference_numbering():
     assert np.array_equal(tris["localId"], o.tris["localId"]) and np.array_equal(tris["meshId"], o.tris["meshId"])
 
 
+def test_host_builder_parallel_partition_matches_std_partition_on_large_and_degenerate_sets():
+    """Sets of 128 K triangles and more are split with a multi-threaded restatement of libstdc++'s std::partition (closed
+    form of its two-pointer sweep); the oracle runs the real std::partition. 150 K copies of one triangle take the
+    median fallback at the top level, a planar grid has thousands of equal centroid coordinates."""
+    one = np.array([[-0.3, 0.8, -0.3], [0.4, 0.8, -0.2], [-0.1, 0.8, 0.5]], np.float32)
+    p2, i2 = wl.displaced_grid(300)
+    flat = p2.copy()
+    flat[:, 1] = 0.0
+    r, o = rb.Raycaster(), orc.OracleRaycaster()
+    for p, i in ((one, np.tile(np.array([0, 1, 2], np.uint32), 150000)), (p2, i2), (flat, i2)):
+        r.addMesh(p, i)
+        o.add_mesh(p, i)
+    r.build_host_only()
+    o.build()
+    nodes, tris, _ = r.download_bvh()
+    assert tris.size == 510000 and nodes.tobytes() == o.nodes.tobytes()
+    assert np.array_equal(tris["localId"], o.tris["localId"]) and np.array_equal(tris["meshId"], o.tris["meshId"])
+
+
 def test_add_mesh_rejects_bad_indices():
     r = rb.Raycaster()
     pos = np.zeros((3, 3), np.float32)
