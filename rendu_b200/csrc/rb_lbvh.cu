@@ -641,76 +641,74 @@ rb_status rb_lbvh_refit(rb_raycaster * rc, const float * worldPositions, size_t 
 }
 
 // Device tree -> the reference's Node / TriangleInfos arrays (what RaycasterVisualisation reads). Roots come first
-// (slots 0..nroots-1), then every other node in a depth-first order; a leaf keeps (first triangle, count).
+// (slots 0..nroots-1), then the children of every device interior node; a leaf keeps (first triangle, count).
 rb_status rb_lbvh_download(const rb_raycaster * rc, rb_node * nodesOut, rb_tri * trisOut, float * vertsOut) {
 	RB_REQUIRE_DEVICE();
 	RB_CUDA(cudaSetDevice(rc->device));
 	RB_CUDA(cudaDeviceSynchronize());
 	const size_t ni = rc->nInterior, nt = rc->nTris, nr = size_t(rc->dev.nroots);
-	std::vector<float> nodes(ni * 16 + 16), roots(nr * 8 + 8), verts(rc->nVerts * 3);
-	std::vector<uint32_t> triVerts(nt * 3), triIds(nt * 2);
-	if(ni) RB_CUDA(cudaMemcpy(nodes.data(), rc->d_nodes, ni * 64, cudaMemcpyDeviceToHost));
-	if(nr) RB_CUDA(cudaMemcpy(roots.data(), rc->d_roots, nr * 32, cudaMemcpyDeviceToHost));
-	if(nt) RB_CUDA(cudaMemcpy(triVerts.data(), rc->d_triVerts, nt * 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-	if(nt) RB_CUDA(cudaMemcpy(triIds.data(), rc->d_triIds, nt * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-	if(rc->nVerts) RB_CUDA(cudaMemcpy(verts.data(), rc->d_verts, rc->nVerts * 3 * sizeof(float), cudaMemcpyDeviceToHost));
-	if(vertsOut && rc->nVerts) std::memcpy(vertsOut, verts.data(), rc->nVerts * 3 * sizeof(float));
+	// Uninitialised staging: value-initialised vectors would zero more than a gigabyte at 10 M triangles first.
+	std::unique_ptr<float[]> nodes(new float[ni * 16 + 16]), roots(new float[nr * 8 + 8]), verts(new float[rc->nVerts * 3 + 3]);
+	std::unique_ptr<uint32_t[]> triVerts(new uint32_t[nt * 3 + 3]), triIds(new uint32_t[nt * 2 + 2]);
+	if(ni) RB_CUDA(cudaMemcpy(nodes.get(), rc->d_nodes, ni * 64, cudaMemcpyDeviceToHost));
+	if(nr) RB_CUDA(cudaMemcpy(roots.get(), rc->d_roots, nr * 32, cudaMemcpyDeviceToHost));
+	if(nt) RB_CUDA(cudaMemcpy(triVerts.get(), rc->d_triVerts, nt * 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	if(nt) RB_CUDA(cudaMemcpy(triIds.get(), rc->d_triIds, nt * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	if(rc->nVerts) RB_CUDA(cudaMemcpy(verts.get(), rc->d_verts, rc->nVerts * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+	if(vertsOut && rc->nVerts) std::memcpy(vertsOut, verts.get(), rc->nVerts * 3 * sizeof(float));
 	if(trisOut) {
-		for(size_t i = 0; i < nt; ++i) {
-			rb_tri & t = trisOut[i];
-			std::memset(&t, 0, sizeof(t));
-			t.v0 = triVerts[3 * i]; t.v1 = triVerts[3 * i + 1]; t.v2 = triVerts[3 * i + 2];
-			t.localId = triIds[2 * i];
-			t.meshId  = triIds[2 * i + 1];
-			const float *a = &verts[3 * t.v0], *b = &verts[3 * t.v1], *c = &verts[3 * t.v2];
-			for(int k = 0; k < 3; ++k) {
-				const float mn = (b[k] < a[k]) ? b[k] : a[k], mx = (a[k] < b[k]) ? b[k] : a[k];
-				t.bmin[k] = (c[k] < mn) ? c[k] : mn;
-				t.bmax[k] = (mx < c[k]) ? c[k] : mx;
+		rb_parallel_for(nt, size_t(1) << 16, [&](size_t begin, size_t end) {
+			for(size_t i = begin; i < end; ++i) {
+				rb_tri & t = trisOut[i];
+				std::memset(&t, 0, sizeof(t));
+				t.v0 = triVerts[3 * i]; t.v1 = triVerts[3 * i + 1]; t.v2 = triVerts[3 * i + 2];
+				t.localId = triIds[2 * i];
+				t.meshId  = triIds[2 * i + 1];
+				const float *a = &verts[3 * t.v0], *b = &verts[3 * t.v1], *c = &verts[3 * t.v2];
+				for(int k = 0; k < 3; ++k) {
+					const float mn = (b[k] < a[k]) ? b[k] : a[k], mx = (a[k] < b[k]) ? b[k] : a[k];
+					t.bmin[k] = (c[k] < mn) ? c[k] : mn;
+					t.bmax[k] = (mx < c[k]) ? c[k] : mx;
+				}
 			}
-		}
+		});
 	}
 	if(nodesOut) {
-		struct Item { int ref; size_t slot; float box[6]; };
-		std::vector<Item> todo;
-		size_t next = nr;
-		for(size_t r = 0; r < nr; ++r) {
-			Item it;
-			std::memcpy(&it.ref, &roots[8 * r + 3], 4);
-			it.slot = r;
-			for(int k = 0; k < 3; ++k) { it.box[k] = roots[8 * r + k]; it.box[3 + k] = roots[8 * r + 4 + k]; }
-			todo.push_back(it);
-		}
-		while(!todo.empty()) {
-			const Item it = todo.back();
-			todo.pop_back();
-			rb_node & nd = nodesOut[it.slot];
+		// Numbering: roots in slots [0, nr); the two children of device interior node i in slots nr + 2i and nr + 2i + 1.
+		// Every record then depends on one device node only, so the conversion runs on all host threads (the reference's
+		// consumers follow left/right indices and never assume an order).
+		auto fill = [&](rb_node & nd, int ref, const float * lo, const float * hi) {
 			std::memset(&nd, 0, sizeof(nd));
-			std::memcpy(nd.bmin, it.box, 12);
-			std::memcpy(nd.bmax, it.box + 3, 12);
-			if(it.ref < 0 || it.ref == RB_REF_NONE) {
+			std::memcpy(nd.bmin, lo, 12);
+			std::memcpy(nd.bmax, hi, 12);
+			if(ref < 0 || ref == RB_REF_NONE) {
 				nd.leaf = 1;
-				if(it.ref != RB_REF_NONE) {
-					const int code = ~it.ref;
+				if(ref != RB_REF_NONE) {
+					const int code = ~ref;
 					nd.left	 = uint64_t(code >> RB_LEAF_BITS);
 					nd.right = uint64_t((code & (RB_LEAF_MAX_TRIS - 1)) + 1);
 				}
-				continue;
+			} else {
+				nd.leaf	 = 0;
+				nd.left	 = nr + 2 * size_t(ref);
+				nd.right = nr + 2 * size_t(ref) + 1;
 			}
-			const float * f = &nodes[size_t(it.ref) * 16];
-			Item l, r;
-			std::memcpy(&l.ref, &f[12], 4);
-			std::memcpy(&r.ref, &f[13], 4);
-			std::memcpy(l.box, f, 24);
-			std::memcpy(r.box, f + 6, 24);
-			l.slot = next++;
-			r.slot = next++;
-			nd.leaf	 = 0;
-			nd.left	 = l.slot;
-			nd.right = r.slot;
-			todo.push_back(l);
-			todo.push_back(r);
+		};
+		for(size_t r = 0; r < nr; ++r) {
+			int ref;
+			std::memcpy(&ref, &roots[8 * r + 3], 4);
+			fill(nodesOut[r], ref, &roots[8 * r], &roots[8 * r + 4]);
 		}
+		rb_parallel_for(ni, size_t(1) << 15, [&](size_t begin, size_t end) {
+			for(size_t i = begin; i < end; ++i) {
+				const float * f = &nodes[i * 16];
+				int refL, refR;
+				std::memcpy(&refL, &f[12], 4);
+				std::memcpy(&refR, &f[13], 4);
+				fill(nodesOut[nr + 2 * i], refL, f, f + 3);
+				fill(nodesOut[nr + 2 * i + 1], refR, f + 6, f + 9);
+			}
+		});
 	}
 	return RB_OK;
 }
