@@ -798,16 +798,18 @@ struct Scratch {
 // stream, so that the upload of chunk c+1, the traversal of chunk c and the download of chunk c-1 overlap (two copy
 // engines + SMs). The ring belongs to the calling host thread: concurrent callers never share buffers or streams.
 namespace {
-constexpr size_t kPipeChunk = size_t(1) << 19; // rays per chunk
-constexpr int kPipeSlots	= 3;
+constexpr int kPipeSlotsMax = 8;
+// Rays per chunk and slots in the ring (RB_PIPE_CHUNK / RB_PIPE_SLOTS override them, for tuning).
+static const size_t kPipeChunk = [] { const char * e = getenv("RB_PIPE_CHUNK"); const long v = e ? atol(e) : 0; return v >= 1024 ? size_t(v) : (size_t(1) << 19); }();
+static const int kPipeSlots	   = [] { const char * e = getenv("RB_PIPE_SLOTS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= kPipeSlotsMax) ? v : 3; }();
 
 struct HostPipe {
 	int device = -1;
-	cudaStream_t stream[kPipeSlots] = {};
-	cudaEvent_t done[kPipeSlots]	= {};
-	float * d_org[kPipeSlots]		= {};
-	float * d_dir[kPipeSlots]		= {};
-	void * d_out[kPipeSlots]		= {};
+	cudaStream_t stream[kPipeSlotsMax] = {};
+	cudaEvent_t done[kPipeSlotsMax]	= {};
+	float * d_org[kPipeSlotsMax]		= {};
+	float * d_dir[kPipeSlotsMax]		= {};
+	void * d_out[kPipeSlotsMax]		= {};
 	bool ready = false;
 
 	rb_status ensure(int dev) {
