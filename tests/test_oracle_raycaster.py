@@ -148,3 +148,63 @@ def test_oracle_matches_live_reference_large():
     any_r, _ = r.intersect_any(org, dirs, threads=4)
     assert np.array_equal(o.intersect_any(org, dirs, threads=4), any_r)
     assert hr["hit"].sum() > 5000
+
+
+def test_root_block_skipping_visits_the_same_roots_in_the_same_order():
+    """Model of rb_next_root (rendu_b200/csrc/rb_trace.cuh) on the oracle's bit-exact box test: with union boxes over
+    aligned blocks of 2^k consecutive roots, walking the roots from the last to the first and skipping a block whose
+    union the ray misses enters exactly the roots — in exactly the order — of the reference's plain loop
+    (Raycaster.cpp:149-155 pushes every root whose box passes, the stack pops them in reverse). Holds because the slab
+    test is monotone in the box for rays without NaNs; rays with zero / denormal direction components take the plain
+    loop in the product and are left out here."""
+    rng = np.random.RandomState(12)
+    n = 333
+    side = int(np.ceil(np.sqrt(n)))
+    lo = np.zeros((n, 3), np.float32)
+    for k in range(n):
+        lo[k] = [-0.9 + 1.8 * (k % side) / side, 0.2 * rng.uniform(), -0.9 + 1.8 * (k // side) / side]
+    hi = (lo + rng.uniform(0.02, 0.12, (n, 3))).astype(np.float32)
+    levels = int(np.floor(np.log2(n)))
+    blocks = {0: (lo, hi)}
+    for k in range(1, levels + 1):
+        plo, phi = blocks[k - 1]
+        nb = (plo.shape[0] + 1) // 2
+        blo, bhi = np.zeros((nb, 3), np.float32), np.zeros((nb, 3), np.float32)
+        for b in range(nb):
+            sl = slice(2 * b, min(2 * b + 2, plo.shape[0]))
+            blo[b], bhi[b] = plo[sl].min(0), phi[sl].max(0)
+        blocks[k] = (blo, bhi)
+    org, dirs = wl.random_rays(120, 31)
+    co, cd = wl.coherent_rays(8)
+    org, dirs = np.concatenate([org, co]), np.concatenate([dirs, cd])
+    mini, maxi = 1e-4, 1e8
+
+    def passes(k, idx, i):
+        b = np.concatenate([blocks[k][0][idx], blocks[k][1][idx]])[None]
+        return bool(orc.box_test(org[i:i + 1], dirs[i:i + 1], b, mini, maxi)[0][0])
+
+    skipped_total = 0
+    for i in range(org.shape[0]):
+        plain = [r for r in range(n - 1, -1, -1) if passes(0, r, i)]
+        entered, root, tests = [], n, 0
+        while root > 0:
+            r = root - 1
+            k = min(((r + 1) & -(r + 1)).bit_length() - 1, levels)
+            skipped = False
+            while k >= 1:
+                tests += 1
+                if not passes(k, r >> k, i):
+                    root = (r >> k) << k
+                    skipped = True
+                    break
+                k -= 1
+            if skipped:
+                continue
+            root = r
+            tests += 1
+            if passes(0, r, i):
+                entered.append(r)
+        assert entered == plain, "ray %d" % i
+        skipped_total += n - tests
+    assert skipped_total > 0.5 * n * org.shape[0]  # most root tests are saved on a row-ordered scene
+
