@@ -138,8 +138,16 @@ RB_API rb_status rb_raycaster_sizes(const rb_raycaster * rc, uint64_t out[5]);
 RB_API rb_status rb_raycaster_download_bvh(const rb_raycaster * rc, rb_node * nodes, rb_tri * tris, float * vertices);
 
 /* Re-fit all boxes after the vertices moved (same topology): positions replace the merged world-space vertex
- * array (nverts must match). Device-side bottom-up refit; the tree order is kept. */
+ * array (nverts must match). Device-side bottom-up refit; the tree order is kept. world_positions == NULL (nverts 0)
+ * fits the vertices the handle already holds, i.e. after one or more rb_raycaster_update_mesh calls. */
 RB_API rb_status rb_raycaster_refit(rb_raycaster * rc, const float * world_positions, size_t nverts);
+
+/* Incremental geometry (no reference counterpart: Raycaster bakes `model` at addMesh, Raycaster.cpp:22-28, and an
+ * animated Object never reaches it). Mesh `mesh` (addMesh order) gets new model-space positions and / or a new model
+ * matrix with the same topology; its world-space vertices are recomputed with addMesh's own arithmetic and only that
+ * range is uploaded. Boxes are stale until the next rb_raycaster_refit(rc, NULL, 0). Needs a hierarchy built from
+ * rb_raycaster_add_mesh calls (not rb_raycaster_upload_bvh, which carries no per-mesh vertex ranges). */
+RB_API rb_status rb_raycaster_update_mesh(rb_raycaster * rc, uint32_t mesh, const float * positions, size_t nverts, const float * model);
 
 /* Device time (CUDA events, milliseconds) of the last hierarchy build (out[0]; 0 for RB_BUILD_REFERENCE, which builds on
  * the host) and of the last refit (out[1]), excluding host packing and host-device copies. */
@@ -235,6 +243,12 @@ RB_API rb_status rb_scene_commit(rb_scene * sc, rb_build_mode mode);
  * also does it). Only the two small tables are re-uploaded; geometry, textures and the hierarchy stay. */
 RB_API rb_status rb_scene_clear_lights(rb_scene * sc);
 RB_API rb_status rb_scene_sync(rb_scene * sc);
+/* New model matrix (16 floats, column-major) for object `object` (rb_scene_add_object order) — what Object::update
+ * leaves in Object::model() for an animated object (Object.cpp, Animation.cpp). Before the commit it simply replaces
+ * the matrix; on a committed scene the next rb_scene_sync (or render) re-transforms that object's vertices, refits
+ * the hierarchy on the device (same topology, rb_raycaster_update_mesh + rb_raycaster_refit) and rewrites the object's
+ * normal matrix; textures, attributes and the other objects are untouched. */
+RB_API rb_status rb_scene_set_object_transform(rb_scene * sc, uint32_t object, const float model[16]);
 /* The scene's raycaster (owned by the scene) — PathTracer::raycaster(). */
 RB_API rb_raycaster * rb_scene_raycaster(rb_scene * sc);
 

@@ -83,6 +83,7 @@ def lib():
         "rb_raycaster_sizes": (C.c_int, [vp, vp]),
         "rb_raycaster_download_bvh": (C.c_int, [vp, vp, vp, vp]),
         "rb_raycaster_refit": (C.c_int, [vp, vp, sz]),
+        "rb_raycaster_update_mesh": (C.c_int, [vp, u32, vp, sz, vp]),
         "rb_raycaster_set_trace_mode": (C.c_int, [vp, C.c_int]),
         "rb_raycaster_build_times": (C.c_int, [vp, vp]),
         "rb_raycaster_intersect": (C.c_int, [vp, vp, vp, f32, f32, sz, vp]),
@@ -102,6 +103,7 @@ def lib():
         "rb_scene_commit": (C.c_int, [vp, C.c_int]),
         "rb_scene_clear_lights": (C.c_int, [vp]),
         "rb_scene_sync": (C.c_int, [vp]),
+        "rb_scene_set_object_transform": (C.c_int, [vp, u32, vp]),
         "rb_scene_raycaster": (vp, [vp]),
         "rb_pathtracer_create": (C.c_int, [vp, C.POINTER(vp)]),
         "rb_pathtracer_destroy": (None, [vp]),

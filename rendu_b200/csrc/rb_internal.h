@@ -77,9 +77,11 @@ struct rb_raycaster {
 	std::vector<rb_node> nodes;
 	uint32_t meshCount = 0;
 	std::vector<uint64_t> meshFirst, meshTris; // per mesh: first triangle and triangle count (stable across rebuilds)
+	std::vector<uint64_t> meshVertFirst, meshVerts; // per mesh: first vertex and vertex count in `verts` (addMesh order)
 	int maxDepth	   = 0; // max number of interior nodes on a root-to-leaf path
 	bool built		   = false;
 	bool hostMirrorStale = false; // device tree newer than the host mirror (after LBVH build / refit)
+	bool triBoxesStale	 = false; // `verts` changed since the boxes in `tris` were computed (refit): redone before a rebuild
 
 	// Device tree.
 	int device		  = -1; // CUDA device holding the tree (-1: nothing uploaded yet)

@@ -476,7 +476,7 @@ rb_status rb_build_root_levels(rb_raycaster * rc, cudaStream_t s) {
 static rb_status rb_run_fit(rb_raycaster * rc, cudaStream_t s) {
 	const int nleaves = int(rc->nLeaves);
 	unsigned int * d_depth = nullptr;
-	RB_CUDA(cudaMalloc(&d_depth, sizeof(unsigned int)));
+	RB_CUDA(cudaMallocAsync(&d_depth, sizeof(unsigned int), s)); // stream-ordered: a per-frame refit must not synchronise the device
 	RB_CUDA(cudaMemsetAsync(d_depth, 0, sizeof(unsigned int), s));
 	RB_CUDA(cudaMemsetAsync(rc->d_flags, 0, (rc->nInterior + 1) * sizeof(unsigned int), s));
 	if(nleaves) {
@@ -485,8 +485,8 @@ static rb_status rb_run_fit(rb_raycaster * rc, cudaStream_t s) {
 	}
 	unsigned int depth = 0;
 	cudaError_t e = cudaMemcpyAsync(&depth, d_depth, sizeof(depth), cudaMemcpyDeviceToHost, s);
+	cudaFreeAsync(d_depth, s);
 	if(e == cudaSuccess) e = cudaStreamSynchronize(s);
-	cudaFree(d_depth);
 	if(e != cudaSuccess) return rb_fail(RB_ERR_CUDA, "hierarchy fit failed: %s", cudaGetErrorString(e));
 	rc->maxDepth	   = int(depth);
 	rc->dev.stackDepth = rc->maxDepth + 1;
@@ -618,11 +618,15 @@ rb_status rb_lbvh_build(rb_raycaster * rc) {
 
 rb_status rb_lbvh_refit(rb_raycaster * rc, const float * worldPositions, size_t nverts) {
 	RB_REQUIRE_DEVICE();
-	if(nverts != rc->nVerts) return rb_fail(RB_ERR_INVALID, "rb_raycaster_refit: %zu vertices given, hierarchy has %zu", nverts, rc->nVerts);
+	// worldPositions == NULL: fit the vertices the handle already holds (after rb_raycaster_update_mesh).
+	if(worldPositions && nverts != rc->nVerts) return rb_fail(RB_ERR_INVALID, "rb_raycaster_refit: %zu vertices given, hierarchy has %zu", nverts, rc->nVerts);
 	RB_CUDA(cudaSetDevice(rc->device));
 	cudaStream_t s = cudaStreamPerThread;
-	RB_CUDA(cudaMemcpyAsync(rc->d_verts, worldPositions, nverts * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
-	rc->verts.assign(worldPositions, worldPositions + nverts * 3);
+	if(worldPositions) {
+		RB_CUDA(cudaMemcpyAsync(rc->d_verts, worldPositions, nverts * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+		rc->verts.assign(worldPositions, worldPositions + nverts * 3);
+		rc->triBoxesStale = true;
+	}
 	cudaEvent_t ev0, ev1;
 	cudaEventCreate(&ev0);
 	cudaEventCreate(&ev1);

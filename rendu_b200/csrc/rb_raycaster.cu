@@ -480,23 +480,22 @@ extern "C" void rb_raycaster_destroy(rb_raycaster * rc) {
 	delete rc;
 }
 
-extern "C" rb_status rb_raycaster_add_mesh(rb_raycaster * rc, const float * positions, size_t nverts, const uint32_t * indices, size_t nindices, const float * model) {
-	if(!rc || (!positions && nverts) || (!indices && nindices)) return rb_fail(RB_ERR_INVALID, "rb_raycaster_add_mesh: null argument");
+// vec3(model * vec4(v, 1)) as Raycaster::addMesh applies it (Raycaster.cpp:22-28); an exact identity copies.
+// `model != glm::mat4(1.0f)` (Raycaster.cpp:22) is an element-wise float comparison.
+static void rb_transform_positions(float * dst, const float * positions, size_t nverts, const float * model) {
 	static const float identity[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-	// `model != glm::mat4(1.0f)` (Raycaster.cpp:22): element-wise float comparison.
 	bool isIdentity = true;
 	if(model) {
 		for(int k = 0; k < 16; ++k) isIdentity = isIdentity && (model[k] == identity[k]);
 	}
-	const size_t indexOffset = rc->verts.size() / 3;
-	rc->verts.resize((indexOffset + nverts) * 3);
-	float * dst = rc->verts.data() + indexOffset * 3;
 	if(isIdentity) {
 		if(nverts) std::memcpy(dst, positions, nverts * 3 * sizeof(float));
-	} else {
-		// vec3(model * vec4(v, 1)): glm evaluates (m0*x + m1*y) + (m2*z + m3*w) per component (type_mat4x4.inl:561-571).
-		const float * m = model;
-		for(size_t v = 0; v < nverts; ++v) {
+		return;
+	}
+	// glm evaluates (m0*x + m1*y) + (m2*z + m3*w) per component (type_mat4x4.inl:561-571).
+	const float * m = model;
+	rb_parallel_for(nverts, size_t(1) << 16, [&](size_t begin, size_t end) {
+		for(size_t v = begin; v < end; ++v) {
 			const float x = positions[3 * v], y = positions[3 * v + 1], z = positions[3 * v + 2];
 			for(int r = 0; r < 3; ++r) {
 				const float a0 = m[0 + r] * x + m[4 + r] * y;
@@ -504,7 +503,27 @@ extern "C" rb_status rb_raycaster_add_mesh(rb_raycaster * rc, const float * posi
 				dst[3 * v + r] = a0 + a1;
 			}
 		}
+	});
+}
+
+// BoundingBox(v0,v1,v2) (Bounds.cpp:12-15): min(min(v0,v1),v2), glm::min(x,y) = (y<x)?y:x.
+static void rb_triangle_box(rb_tri & ti, const float * verts) {
+	const float * a = verts + 3 * ti.v0;
+	const float * b = verts + 3 * ti.v1;
+	const float * c = verts + 3 * ti.v2;
+	for(int k = 0; k < 3; ++k) {
+		const float mn01 = (b[k] < a[k]) ? b[k] : a[k];
+		const float mx01 = (a[k] < b[k]) ? b[k] : a[k];
+		ti.bmin[k]		 = (c[k] < mn01) ? c[k] : mn01;
+		ti.bmax[k]		 = (mx01 < c[k]) ? c[k] : mx01;
 	}
+}
+
+extern "C" rb_status rb_raycaster_add_mesh(rb_raycaster * rc, const float * positions, size_t nverts, const uint32_t * indices, size_t nindices, const float * model) {
+	if(!rc || (!positions && nverts) || (!indices && nindices)) return rb_fail(RB_ERR_INVALID, "rb_raycaster_add_mesh: null argument");
+	const size_t indexOffset = rc->verts.size() / 3;
+	rc->verts.resize((indexOffset + nverts) * 3);
+	rb_transform_positions(rc->verts.data() + indexOffset * 3, positions, nverts, model);
 	const size_t ntri		  = nindices / 3;
 	const size_t startTriangle = rc->tris.size();
 	rc->tris.resize(startTriangle + ntri);
@@ -525,16 +544,7 @@ extern "C" rb_status rb_raycaster_add_mesh(rb_raycaster * rc, const float * posi
 				while(t < seen && !badTriangle.compare_exchange_weak(seen, t)) {}
 				return;
 			}
-			const float * a = rc->verts.data() + 3 * ti.v0;
-			const float * b = rc->verts.data() + 3 * ti.v1;
-			const float * c = rc->verts.data() + 3 * ti.v2;
-			// BoundingBox(v0,v1,v2) (Bounds.cpp:12-15): min(min(v0,v1),v2), glm::min(x,y) = (y<x)?y:x.
-			for(int k = 0; k < 3; ++k) {
-				const float mn01 = (b[k] < a[k]) ? b[k] : a[k];
-				const float mx01 = (a[k] < b[k]) ? b[k] : a[k];
-				ti.bmin[k]		 = (c[k] < mn01) ? c[k] : mn01;
-				ti.bmax[k]		 = (mx01 < c[k]) ? c[k] : mx01;
-			}
+			rb_triangle_box(ti, rc->verts.data());
 		}
 	});
 	if(badTriangle.load() != SIZE_MAX) {
@@ -545,14 +555,42 @@ extern "C" rb_status rb_raycaster_add_mesh(rb_raycaster * rc, const float * posi
 	// One root per mesh, appended after the existing roots: a rebuild restarts from these (Raycaster.cpp:43-46).
 	rc->meshFirst.push_back(startTriangle);
 	rc->meshTris.push_back(ntri);
+	rc->meshVertFirst.push_back(indexOffset);
+	rc->meshVerts.push_back(nverts);
 	rc->meshCount++;
 	rc->built = false;
+	return RB_OK;
+}
+
+// Incremental geometry: mesh `mesh` (addMesh order) gets new model-space positions and / or a new model matrix, same
+// topology. The world-space vertices are recomputed exactly as addMesh computes them and only this mesh's range goes
+// to the device; the boxes follow at the next rb_raycaster_refit (pass NULL positions there: "fit what the handle holds").
+extern "C" rb_status rb_raycaster_update_mesh(rb_raycaster * rc, uint32_t mesh, const float * positions, size_t nverts, const float * model) {
+	if(!rc || !positions) return rb_fail(RB_ERR_INVALID, "rb_raycaster_update_mesh: null argument");
+	if(mesh >= rc->meshVertFirst.size()) return rb_fail(RB_ERR_INVALID, "rb_raycaster_update_mesh: mesh %u unknown (%zu meshes were added through rb_raycaster_add_mesh)", mesh, rc->meshVertFirst.size());
+	if(nverts != rc->meshVerts[mesh]) return rb_fail(RB_ERR_INVALID, "rb_raycaster_update_mesh: mesh %u has %zu vertices, %zu given", mesh, size_t(rc->meshVerts[mesh]), nverts);
+	RB_REQUIRE_DEVICE();
+	if(!rc->built || !rc->d_verts) return rb_fail(RB_ERR_INVALID, "rb_raycaster_update_mesh: hierarchy not built");
+	const size_t first = size_t(rc->meshVertFirst[mesh]);
+	float * dst		   = rc->verts.data() + first * 3;
+	rb_transform_positions(dst, positions, nverts, model);
+	rc->triBoxesStale = true;
+	RB_CUDA(cudaSetDevice(rc->device));
+	if(nverts) RB_CUDA(cudaMemcpyAsync(rc->d_verts + first * 3, dst, nverts * 3 * sizeof(float), cudaMemcpyHostToDevice, cudaStreamPerThread));
+	RB_CUDA(cudaStreamSynchronize(cudaStreamPerThread)); // `verts` is pageable memory the caller may update again
 	return RB_OK;
 }
 
 extern "C" rb_status rb_raycaster_build(rb_raycaster * rc, rb_build_mode mode) {
 	if(!rc) return rb_fail(RB_ERR_INVALID, "rb_raycaster_build: null handle");
 	rc->buildMode = mode;
+	if(rc->triBoxesStale) {
+		// Vertices moved since addMesh (refit / update_mesh): the triangle boxes the builders start from are redone.
+		rb_parallel_for(rc->tris.size(), size_t(1) << 16, [&](size_t begin, size_t end) {
+			for(size_t t = begin; t < end; ++t) rb_triangle_box(rc->tris[t], rc->verts.data());
+		});
+		rc->triBoxesStale = false;
+	}
 	if(mode == RB_BUILD_REFERENCE) {
 		// The host mirror is built first so that it can be read back (rb_raycaster_download_bvh) even on a machine
 		// without a GPU; tracing still needs the device copy.
@@ -576,6 +614,9 @@ extern "C" rb_status rb_raycaster_upload_bvh(rb_raycaster * rc, const rb_node * 
 	rc->nodes.assign(nodes, nodes + nnodes);
 	rc->meshFirst.clear();
 	rc->meshTris.clear();
+	rc->meshVertFirst.clear();
+	rc->meshVerts.clear();
+	rc->triBoxesStale = false;
 	rc->tris.assign(tris, tris + ntris);
 	rc->verts.assign(vertices, vertices + nverts * 3);
 	rc->meshCount = mesh_count;
@@ -617,7 +658,8 @@ extern "C" rb_status rb_raycaster_download_bvh(const rb_raycaster * rc, rb_node 
 }
 
 extern "C" rb_status rb_raycaster_refit(rb_raycaster * rc, const float * world_positions, size_t nverts) {
-	if(!rc || !world_positions) return rb_fail(RB_ERR_INVALID, "rb_raycaster_refit: null argument");
+	if(!rc) return rb_fail(RB_ERR_INVALID, "rb_raycaster_refit: null handle");
+	if(!world_positions && nverts) return rb_fail(RB_ERR_INVALID, "rb_raycaster_refit: null positions with a vertex count");
 	RB_REQUIRE_DEVICE();
 	if(!rc->built) return rb_fail(RB_ERR_INVALID, "rb_raycaster_refit: hierarchy not built");
 	return rb_lbvh_refit(rc, world_positions, nverts);

@@ -63,6 +63,29 @@ extern "C" rb_status rb_scene_add_texture(rb_scene * sc, const float * pixels, u
 	return RB_OK;
 }
 
+// invtp = glm::inverse(glm::transpose(glm::mat3(model))) (PathTracer.cpp:94), evaluated once with glm's formulas
+// (func_matrix.inl:87-105 transpose, :269-291 inverse) so the values equal what the reference recomputes per hit.
+static void rb_normal_matrix(const float * model, float * invtp) {
+	float m[3][3]; // m[col][row] of the TRANSPOSED upper-left 3x3
+	for(int c = 0; c < 3; ++c) {
+		for(int r = 0; r < 3; ++r) m[c][r] = model[r * 4 + c]; // transpose: result[c][r] = model[r][c]
+	}
+	const float oneOverDet = 1.0f / (+m[0][0] * (m[1][1] * m[2][2] - m[2][1] * m[1][2]) - m[1][0] * (m[0][1] * m[2][2] - m[2][1] * m[0][2]) + m[2][0] * (m[0][1] * m[1][2] - m[1][1] * m[0][2]));
+	float inv[3][3];
+	inv[0][0] = +(m[1][1] * m[2][2] - m[2][1] * m[1][2]) * oneOverDet;
+	inv[1][0] = -(m[1][0] * m[2][2] - m[2][0] * m[1][2]) * oneOverDet;
+	inv[2][0] = +(m[1][0] * m[2][1] - m[2][0] * m[1][1]) * oneOverDet;
+	inv[0][1] = -(m[0][1] * m[2][2] - m[2][1] * m[0][2]) * oneOverDet;
+	inv[1][1] = +(m[0][0] * m[2][2] - m[2][0] * m[0][2]) * oneOverDet;
+	inv[2][1] = -(m[0][0] * m[2][1] - m[2][0] * m[0][1]) * oneOverDet;
+	inv[0][2] = +(m[0][1] * m[1][2] - m[1][1] * m[0][2]) * oneOverDet;
+	inv[1][2] = -(m[0][0] * m[1][2] - m[1][0] * m[0][2]) * oneOverDet;
+	inv[2][2] = +(m[0][0] * m[1][1] - m[1][0] * m[0][1]) * oneOverDet;
+	for(int c = 0; c < 3; ++c) {
+		for(int r = 0; r < 3; ++r) invtp[c * 3 + r] = inv[c][r];
+	}
+}
+
 extern "C" rb_status rb_scene_add_object(rb_scene * sc, const rb_object_desc * d) {
 	if(!sc || !d) return rb_fail(RB_ERR_INVALID, "rb_scene_add_object: null argument");
 	if(!d->positions || !d->indices || !d->normals || !d->tangents || !d->bitangents) {
@@ -108,26 +131,7 @@ extern "C" rb_status rb_scene_add_object(rb_scene * sc, const rb_object_desc * d
 			p[11] = 0.0f;
 		}
 	});
-	// invtp = glm::inverse(glm::transpose(glm::mat3(model))) (PathTracer.cpp:94), evaluated once with glm's formulas
-	// (func_matrix.inl:87-105 transpose, :269-291 inverse) so the values equal what the reference recomputes per hit.
-	float m[3][3]; // m[col][row] of the TRANSPOSED upper-left 3x3
-	for(int c = 0; c < 3; ++c) {
-		for(int r = 0; r < 3; ++r) m[c][r] = d->model[r * 4 + c]; // transpose: result[c][r] = model[r][c]
-	}
-	const float oneOverDet = 1.0f / (+m[0][0] * (m[1][1] * m[2][2] - m[2][1] * m[1][2]) - m[1][0] * (m[0][1] * m[2][2] - m[2][1] * m[0][2]) + m[2][0] * (m[0][1] * m[1][2] - m[1][1] * m[0][2]));
-	float inv[3][3];
-	inv[0][0] = +(m[1][1] * m[2][2] - m[2][1] * m[1][2]) * oneOverDet;
-	inv[1][0] = -(m[1][0] * m[2][2] - m[2][0] * m[1][2]) * oneOverDet;
-	inv[2][0] = +(m[1][0] * m[2][1] - m[2][0] * m[1][1]) * oneOverDet;
-	inv[0][1] = -(m[0][1] * m[2][2] - m[2][1] * m[0][2]) * oneOverDet;
-	inv[1][1] = +(m[0][0] * m[2][2] - m[2][0] * m[0][2]) * oneOverDet;
-	inv[2][1] = -(m[0][0] * m[2][1] - m[2][0] * m[0][1]) * oneOverDet;
-	inv[0][2] = +(m[0][1] * m[1][2] - m[1][1] * m[0][2]) * oneOverDet;
-	inv[1][2] = -(m[0][0] * m[1][2] - m[1][0] * m[0][2]) * oneOverDet;
-	inv[2][2] = +(m[0][0] * m[1][1] - m[1][0] * m[0][1]) * oneOverDet;
-	for(int c = 0; c < 3; ++c) {
-		for(int r = 0; r < 3; ++r) o.dev.invtp[c * 3 + r] = inv[c][r];
-	}
+	rb_normal_matrix(d->model, o.dev.invtp);
 	o.dev.texAlbedo = d->tex_albedo;
 	o.dev.texNormal = d->tex_normal;
 	o.dev.texRmao	= d->tex_rmao;
@@ -280,6 +284,19 @@ extern "C" rb_status rb_scene_clear_lights(rb_scene * sc) {
 	return RB_OK;
 }
 
+extern "C" rb_status rb_scene_set_object_transform(rb_scene * sc, uint32_t object, const float model[16]) {
+	if(!sc || !model) return rb_fail(RB_ERR_INVALID, "rb_scene_set_object_transform: null argument");
+	if(object >= sc->objects.size()) return rb_fail(RB_ERR_INVALID, "rb_scene_set_object_transform: object %u out of range (%zu objects)", object, sc->objects.size());
+	RbHostObject & o = sc->objects[object];
+	std::memcpy(o.model, model, sizeof(o.model));
+	rb_normal_matrix(o.model, o.dev.invtp);
+	if(sc->geometryCommitted) {
+		o.transformDirty = true;
+		sc->tablesDirty	 = true;
+	}
+	return RB_OK;
+}
+
 // Lights and background of a committed scene: the reference reads them through the Scene at render time
 // (PathTracer.cpp:23-55, :232-255), so a caller may edit them between two renders. Re-uploads the two small tables;
 // geometry, textures and the hierarchy are untouched.
@@ -295,7 +312,22 @@ extern "C" rb_status rb_scene_sync(rb_scene * sc) {
 		}
 	}
 	RB_CUDA(cudaSetDevice(sc->raycaster->device));
-	RB_CUDA(cudaDeviceSynchronize()); // a render may still be reading the old light table
+	RB_CUDA(cudaDeviceSynchronize()); // a render may still be reading the old tables
+	// Objects whose model matrix changed: vertices re-transformed, one refit for all of them, normal matrices rewritten.
+	bool moved = false;
+	for(size_t k = 0; k < sc->objects.size(); ++k) {
+		RbHostObject & o = sc->objects[k];
+		if(!o.transformDirty) continue;
+		rb_status us = rb_raycaster_update_mesh(sc->raycaster, uint32_t(k), o.positions.data(), o.nverts, o.model);
+		if(us) return us;
+		RB_CUDA(cudaMemcpy(sc->d_objects + k, &o.dev, sizeof(RbObject), cudaMemcpyHostToDevice));
+		o.transformDirty = false;
+		moved			 = true;
+	}
+	if(moved) {
+		rb_status fs = rb_raycaster_refit(sc->raycaster, nullptr, 0);
+		if(fs) return fs;
+	}
 	cudaFree(sc->d_lights);
 	sc->d_lights = nullptr;
 	rb_status st = rb_upload(&sc->d_lights, sc->lights.data(), sc->lights.size() * sizeof(RbLight));

@@ -9,6 +9,7 @@ struct RbHostObject {
 	size_t nverts = 0, nindices = 0;
 	uint32_t vertOffset = 0, indexOffset = 0;
 	RbObject dev;
+	bool transformDirty = false; // model changed after the commit: vertices and normal matrix follow at the next sync
 };
 
 struct rb_scene {

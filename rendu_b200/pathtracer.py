@@ -104,6 +104,14 @@ class Scene:
         self._set_background(bg)
         check(lib().rb_scene_sync(self._h))
 
+    def set_object_transform(self, index, model, sync=True):
+        """New model matrix (column-major, as description["objects"][i]["model"]) for one object of a committed scene:
+        its vertices are re-transformed and the hierarchy refitted on the device at the next sync / render."""
+        m = np.ascontiguousarray(np.asarray(model, np.float32).reshape(16))
+        check(lib().rb_scene_set_object_transform(self._h, int(index), ptr(m)))
+        if sync:
+            check(lib().rb_scene_sync(self._h))
+
     def raycaster(self):
         return Raycaster(_handle=lib().rb_scene_raycaster(self._h), _owner=self)
 

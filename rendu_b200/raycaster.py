@@ -77,9 +77,19 @@ class Raycaster:
         check(lib().rb_raycaster_download_bvh(self._h, ptr(nodes), ptr(tris), ptr(verts)))
         return nodes, tris, verts
 
-    def refit(self, world_positions):
+    def refit(self, world_positions=None):
+        """Bottom-up refit on the device. None: fit the vertices the handle holds (after update_mesh)."""
+        if world_positions is None:
+            check(lib().rb_raycaster_refit(self._h, None, 0))
+            return
         pos = np.ascontiguousarray(world_positions, np.float32).reshape(-1, 3)
         check(lib().rb_raycaster_refit(self._h, ptr(pos), pos.shape[0]))
+
+    def update_mesh(self, mesh, positions, model=None):
+        """New model-space positions / model matrix for one mesh (same topology); call refit() afterwards."""
+        pos = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+        m = None if model is None else np.ascontiguousarray(np.asarray(model, np.float32).reshape(16))
+        check(lib().rb_raycaster_update_mesh(self._h, int(mesh), ptr(pos), pos.shape[0], ptr(m) if m is not None else None))
 
     def build_times(self):
         out = np.zeros(2, np.float64)

@@ -111,6 +111,21 @@ def test_add_mesh_rejects_bad_indices():
     assert r.sizes()["tris"] == 0
 
 
+def test_update_mesh_validates_before_touching_the_device():
+    """rb_raycaster_update_mesh: unknown mesh and a vertex count that differs from addMesh's are argument errors on any
+    machine; the copy itself needs the device (no CPU fallback)."""
+    pos, idx = wl.displaced_grid(4)
+    r = rb.Raycaster()
+    r.addMesh(pos, idx)
+    for call in (lambda: r.update_mesh(1, pos), lambda: r.update_mesh(0, pos[:-1])):
+        with pytest.raises(rb.RenduError) as e:
+            call()
+        assert e.value.status == _capi.RB_ERR_INVALID
+    with pytest.raises(rb.RenduError) as e:
+        r.update_mesh(0, pos)  # not built yet / no device
+    assert e.value.status in (_capi.RB_ERR_INVALID, _capi.RB_ERR_NO_DEVICE)
+
+
 @pytest.mark.skipif(rb.device_count() > 0, reason="checks the behaviour of a machine without a GPU")
 def test_no_cpu_fallback_without_gpu():
     pos, idx = wl.displaced_grid(4)

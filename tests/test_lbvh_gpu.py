@@ -179,3 +179,82 @@ def test_path_tracer_on_lbvh_tree():
         imgs.append(img)
     off = (np.abs(imgs[0] - imgs[1]).max(axis=2) > 2e-3).mean()
     assert off < 0.01, off
+
+
+def _model(tx=0.0, ty=0.0, tz=0.0, s=1.0, rot=0.0):
+    """Column-major (glm) model matrix flattened: rotation about y, uniform scale, translation."""
+    c, sn = np.float32(np.cos(rot)), np.float32(np.sin(rot))
+    m = np.zeros((4, 4), np.float32)  # m[col][row]
+    m[0] = [s * c, 0, -s * sn, 0]
+    m[1] = [0, s, 0, 0]
+    m[2] = [s * sn, 0, s * c, 0]
+    m[3] = [tx, ty, tz, 1]
+    return m.reshape(16)
+
+
+@pytest.mark.parametrize("mode", [rb.BUILD_REFERENCE, rb.BUILD_LBVH])
+def test_update_mesh_then_refit_equals_fresh_add_mesh(mode):
+    """Incremental geometry: one mesh of two gets a new model matrix; after update_mesh + refit(None) the vertices are
+    the ones addMesh would have produced (bit-exact) and the hits equal a fresh build on the moved scene (different
+    tree topology, so the lbvh-style comparison applies)."""
+    gpos, gidx = wl.displaced_grid(48)
+    bpos, bidx = wl.displaced_grid(12)
+    m0, m1 = _model(0.1, 0.6, -0.2, 0.35, 0.3), _model(-0.3, 0.9, 0.25, 0.5, -1.1)
+    r = rb.Raycaster()
+    r.addMesh(gpos, gidx)
+    r.addMesh(bpos, bidx, m0)
+    r.updateHierarchy(mode)
+    org, dirs = rays_for_tests(20000, 21)
+    r.intersects(org, dirs)
+    r.update_mesh(1, bpos, m1)
+    r.refit()
+    h = r.intersects(org, dirs)
+    o = orc.OracleRaycaster()
+    o.add_mesh(gpos, gidx)
+    o.add_mesh(bpos, bidx, m1)
+    o.build()
+    compare_with_oracle(h, o.intersect(org, dirs, threads=8), max_ties=20)
+    assert np.array_equal(r.intersectsAny(org, dirs).astype(np.uint8), o.intersect_any(org, dirs, threads=8))
+    fresh = rb.Raycaster()
+    fresh.addMesh(gpos, gidx)
+    fresh.addMesh(bpos, bidx, m1)
+    fresh.updateHierarchy(rb.BUILD_REFERENCE)
+    assert np.array_equal(r.download_bvh()[2], fresh.download_bvh()[2])
+    # Error behaviour: unknown mesh, wrong vertex count, uploaded hierarchies carry no per-mesh ranges.
+    with pytest.raises(rb.RenduError):
+        r.update_mesh(2, bpos, m1)
+    with pytest.raises(rb.RenduError):
+        r.update_mesh(1, bpos[:-1], m1)
+    up = rb.Raycaster()
+    nodes, tris, verts = fresh.download_bvh()
+    up.upload_bvh(nodes, tris, verts, fresh.sizes()["meshes"])
+    with pytest.raises(rb.RenduError):
+        up.update_mesh(0, gpos)
+
+
+def test_rebuild_after_refit_uses_the_moved_vertices():
+    """A rebuild after a refit starts from triangle boxes recomputed on the moved vertices. (Like the reference's, a
+    second updateHierarchy starts from the triangle order the first one left, so the tree is not the one of a fresh
+    handle; the bar is the lbvh one: same hits up to exact-distance ties, and boxes that contain their children.)"""
+    pos, idx = wl.displaced_grid(40)
+    moved = pos.copy()
+    moved[:, 1] = (moved[:, 1] * np.float32(-3.0) + np.float32(0.2) * np.cos(np.float32(5) * moved[:, 2])).astype(np.float32)
+    o = orc.OracleRaycaster()
+    o.add_mesh(moved, idx)
+    o.build()
+    org, dirs = rays_for_tests(20000, 22)
+    ho = o.intersect(org, dirs, threads=8)
+    for mode in (rb.BUILD_REFERENCE, rb.BUILD_LBVH):
+        r = rb.Raycaster()
+        r.addMesh(pos, idx)
+        r.updateHierarchy(rb.BUILD_REFERENCE)
+        r.refit(moved)
+        r.updateHierarchy(mode)
+        compare_with_oracle(r.intersects(org, dirs), ho, max_ties=20)
+        nodes, tris, verts = r.download_bvh()
+        assert np.array_equal(verts, moved)
+        tv = verts[np.stack([tris["v0"], tris["v1"], tris["v2"]], 1).astype(np.int64)]
+        assert np.array_equal(tris["bmin"], tv.min(axis=1)) and np.array_equal(tris["bmax"], tv.max(axis=1))
+        inner = nodes[nodes["leaf"] == 0]
+        ch = nodes[inner["right"].astype(np.int64)]
+        assert (ch["bmin"] >= inner["bmin"]).all() and (ch["bmax"] <= inner["bmax"]).all()
