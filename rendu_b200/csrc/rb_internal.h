@@ -90,6 +90,7 @@ struct rb_raycaster {
 	float4 * d_roots  = nullptr;
 	float4 * d_rootBlocks = nullptr; // union boxes of aligned root blocks (many-mesh scenes), see rb_next_root
 	bool rootBlocksWanted = false;	  // decided at upload (rb_root_blocks_worthwhile), kept across refits
+	size_t rootBlocksCapacity = 0;	  // entries d_rootBlocks was allocated for
 	size_t nInterior  = 0;
 	size_t nTris	  = 0;
 	RbDeviceBvh dev	  = {};

@@ -454,9 +454,13 @@ rb_status rb_build_root_levels(rb_raycaster * rc, cudaStream_t s) {
 		offset[k] = total;
 		total += (n + (1 << k) - 1) >> k;
 	}
-	if(rc->d_rootBlocks) RB_CUDA(cudaFree(rc->d_rootBlocks));
-	rc->d_rootBlocks = nullptr;
-	RB_CUDA(cudaMalloc(&rc->d_rootBlocks, size_t(total) * 2 * sizeof(float4) + 64));
+	if(!rc->d_rootBlocks || rc->rootBlocksCapacity < size_t(total)) { // a refit of the same roots reuses the table
+		if(rc->d_rootBlocks) RB_CUDA(cudaFree(rc->d_rootBlocks));
+		rc->d_rootBlocks	   = nullptr;
+		rc->rootBlocksCapacity = 0;
+		RB_CUDA(cudaMalloc(&rc->d_rootBlocks, size_t(total) * 2 * sizeof(float4) + 64));
+		rc->rootBlocksCapacity = size_t(total);
+	}
 	const float4 * src = rc->d_roots;
 	int nsrc = n;
 	for(int k = 1; k <= levels; ++k) {
@@ -475,9 +479,9 @@ rb_status rb_build_root_levels(rb_raycaster * rc, cudaStream_t s) {
 
 static rb_status rb_run_fit(rb_raycaster * rc, cudaStream_t s) {
 	const int nleaves = int(rc->nLeaves);
-	unsigned int * d_depth = nullptr;
-	RB_CUDA(cudaMallocAsync(&d_depth, sizeof(unsigned int), s)); // stream-ordered: a per-frame refit must not synchronise the device
-	RB_CUDA(cudaMemsetAsync(d_depth, 0, sizeof(unsigned int), s));
+	// The spare entry behind the arrival counters receives the depth: a per-frame refit allocates nothing (a 4-byte
+	// cudaMallocAsync per call made the driver map and unmap pool memory at every synchronisation: 8-14 ms per refit).
+	unsigned int * d_depth = rc->d_flags + rc->nInterior;
 	RB_CUDA(cudaMemsetAsync(rc->d_flags, 0, (rc->nInterior + 1) * sizeof(unsigned int), s));
 	if(nleaves) {
 		rb_k_fit<<<rb_blocks(nleaves, 128), 128, 0, s>>>(rc->d_verts, rc->d_triVerts, rc->d_triIds, rc->d_leafCode, rc->d_leafParent, rc->d_parent, nleaves, rc->d_nodes, rc->d_tris, rc->d_roots, rc->d_flags, d_depth);
@@ -485,7 +489,6 @@ static rb_status rb_run_fit(rb_raycaster * rc, cudaStream_t s) {
 	}
 	unsigned int depth = 0;
 	cudaError_t e = cudaMemcpyAsync(&depth, d_depth, sizeof(depth), cudaMemcpyDeviceToHost, s);
-	cudaFreeAsync(d_depth, s);
 	if(e == cudaSuccess) e = cudaStreamSynchronize(s);
 	if(e != cudaSuccess) return rb_fail(RB_ERR_CUDA, "hierarchy fit failed: %s", cudaGetErrorString(e));
 	rc->maxDepth	   = int(depth);

@@ -523,17 +523,17 @@ static rb_status rb_pt_reserve(rb_pathtracer * pt, int l, size_t paths) {
 		pb = RbPathBuffers{};
 		pt->capacity[l] = 0;
 	}
-	RB_CUDA(cudaMalloc(&pb.rayO, paths * sizeof(float4)));
-	RB_CUDA(cudaMalloc(&pb.rayD, paths * sizeof(float4)));
-	RB_CUDA(cudaMalloc(&pb.atten, paths * sizeof(float4)));
-	RB_CUDA(cudaMalloc(&pb.color, paths * sizeof(float4)));
-	RB_CUDA(cudaMalloc(&pb.hit, paths * sizeof(float4)));
-	RB_CUDA(cudaMalloc(&pb.queue[0], paths * sizeof(uint32_t)));
-	RB_CUDA(cudaMalloc(&pb.queue[1], paths * sizeof(uint32_t)));
-	RB_CUDA(cudaMalloc(&pb.shO, paths * sizeof(float4)));
-	RB_CUDA(cudaMalloc(&pb.shD, paths * sizeof(float4)));
-	RB_CUDA(cudaMalloc(&pb.shC, paths * sizeof(float4)));
-	RB_CUDA(cudaMalloc(&pb.counters, 4 * (RB_PT_MAX_DEPTH + 1) * sizeof(uint32_t)));
+	// All or nothing: a partial allocation (out of memory half way) is released again, capacity stays 0.
+	void ** slots[]		 = {(void **)&pb.rayO, (void **)&pb.rayD, (void **)&pb.atten, (void **)&pb.color, (void **)&pb.hit, (void **)&pb.queue[0], (void **)&pb.queue[1], (void **)&pb.shO, (void **)&pb.shD, (void **)&pb.shC, (void **)&pb.counters};
+	const size_t bytes[] = {paths * sizeof(float4), paths * sizeof(float4), paths * sizeof(float4), paths * sizeof(float4), paths * sizeof(float4), paths * sizeof(uint32_t), paths * sizeof(uint32_t), paths * sizeof(float4), paths * sizeof(float4), paths * sizeof(float4), 4 * (RB_PT_MAX_DEPTH + 1) * sizeof(uint32_t)};
+	for(size_t k = 0; k < sizeof(slots) / sizeof(slots[0]); ++k) {
+		const cudaError_t e = cudaMalloc(slots[k], bytes[k]);
+		if(e != cudaSuccess) {
+			for(size_t j = 0; j < k; ++j) cudaFree(*slots[j]);
+			pb = RbPathBuffers{};
+			return rb_fail(RB_ERR_CUDA, "path buffers for %zu paths: cudaMalloc failed: %s", paths, cudaGetErrorString(e));
+		}
+	}
 	pt->capacity[l] = paths;
 	return RB_OK;
 }

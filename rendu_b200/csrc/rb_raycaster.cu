@@ -402,6 +402,7 @@ void rb_raycaster_free_device(rb_raycaster * rc) {
 	rc->d_cursors = nullptr;
 	cudaFree(rc->d_rootBlocks);
 	rc->d_rootBlocks   = nullptr;
+	rc->rootBlocksCapacity = 0;
 	rc->dev.rootBlocks = nullptr;
 	rc->dev.rootLevels = 0;
 	rc->d_nodes = rc->d_tris = rc->d_roots = nullptr;
