@@ -724,11 +724,16 @@ def run_explore(args):
                 ("persistent_t20", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "20", "RB_LEAF_VOTES": "0", "RB_DUAL": "0"}, rb.TRACE_EXACT)]
     for votes, thr, steps in ((8, 20, 1), (8, 20, 2), (8, 20, 4), (6, 12, 6), (6, 16, 6), (4, 12, 4), (6, 8, 6), (6, 12, 12)):
         variants.append(("phased_v%d_t%d_s%d" % (votes, thr, steps), {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": str(thr), "RB_LEAF_VOTES": str(votes), "RB_NODE_STEPS": str(steps), "RB_DUAL": "0"}, rb.TRACE_EXACT))
+    for votes, thr, steps in ((6, 20, 6), (6, 24, 6), (6, 28, 6), (6, 32, 6), (4, 24, 4), (8, 24, 6), (6, 24, 4)):
+        variants.append(("phased_v%d_t%d_s%d" % (votes, thr, steps), {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": str(thr), "RB_LEAF_VOTES": str(votes), "RB_NODE_STEPS": str(steps), "RB_DUAL": "0"}, rb.TRACE_EXACT))
     variants.append(("dual_v24_r16", {"RB_PERSISTENT": "1", "RB_DUAL": "1", "RB_LEAF_VOTES": "24", "RB_DUAL_REFILL": "16"}, rb.TRACE_EXACT))
     variants.append(("ordered_phased_v8_t20_s2", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "20", "RB_LEAF_VOTES": "8", "RB_NODE_STEPS": "2", "RB_DUAL": "0"}, rb.TRACE_ORDERED))
     variants.append(("ordered_phased_v6_t12_s6", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "12", "RB_LEAF_VOTES": "6", "RB_NODE_STEPS": "6", "RB_DUAL": "0"}, rb.TRACE_ORDERED))
     variants.append(("ordered_phased_v6_t12_s3", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "12", "RB_LEAF_VOTES": "6", "RB_NODE_STEPS": "3", "RB_DUAL": "0"}, rb.TRACE_ORDERED))
     variants.append(("ordered_persistent_t20", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "20", "RB_LEAF_VOTES": "0", "RB_DUAL": "0"}, rb.TRACE_ORDERED))
+    only = os.environ.get("RB_EXPLORE_ONLY")  # comma-separated name prefixes: time a subset (the first one is the reference)
+    if only:
+        variants = [v for v in variants if any(v[0].startswith(p) for p in only.split(","))]
     base, d_io, d_id, results = None, None, None, {}
     for name, env, mode in variants:
         os.environ.update(env)
