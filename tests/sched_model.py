@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Developer aid (CPU only): a warp-instruction model of the phase-voting traversal scheduler (rb_k_trace_phased).
+"""Analysis aid on the test side (CPU only; it drives the oracle, which only tests/ may do): a warp-instruction model of the phase-voting traversal scheduler (rb_k_trace_phased).
 
 The oracle replays the reference traversal of a block of C2 rays and hands back, per ray, the sequence of steps the
 kernel executes for it (N = node step on an interior node, P = node step that only pops a leaf, L = one triangle test).
@@ -7,7 +7,7 @@ A 32-lane warp is then simulated under a scheduling policy and every warp-level 
 execution, whatever the number of lanes that take part — the quantity the kernel is bound by (issue /
 divergence bound). The model ignores latency, so it ranks policies; it does not predict milliseconds.
 
-    python tools/sched_model.py [--rows 8] [--set incoherent|coherent]
+    python tests/sched_model.py [--rows 8] [--set incoherent|coherent]
 """
 import argparse, os, sys
 import numpy as np
