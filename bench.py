@@ -726,6 +726,9 @@ def run_explore(args):
         variants.append(("phased_v%d_t%d_s%d" % (votes, thr, steps), {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": str(thr), "RB_LEAF_VOTES": str(votes), "RB_NODE_STEPS": str(steps), "RB_DUAL": "0"}, rb.TRACE_EXACT))
     for votes, thr, steps in ((6, 20, 6), (6, 24, 6), (6, 28, 6), (6, 32, 6), (4, 24, 4), (8, 24, 6), (6, 24, 4)):
         variants.append(("phased_v%d_t%d_s%d" % (votes, thr, steps), {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": str(thr), "RB_LEAF_VOTES": str(votes), "RB_NODE_STEPS": str(steps), "RB_DUAL": "0"}, rb.TRACE_EXACT))
+    for thr in (12, 20, 24, 28, 32):  # prepared-ray ring (experiment): the refill costs no latency, so the threshold can go up
+        variants.append(("ring_v6_t%d_s6" % thr, {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": str(thr), "RB_LEAF_VOTES": "6", "RB_NODE_STEPS": "6", "RB_DUAL": "0", "RB_RING": "1"}, rb.TRACE_EXACT))
+    variants.append(("ring_v4_t28_s3", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "28", "RB_LEAF_VOTES": "4", "RB_NODE_STEPS": "3", "RB_DUAL": "0", "RB_RING": "1"}, rb.TRACE_EXACT))
     variants.append(("dual_v24_r16", {"RB_PERSISTENT": "1", "RB_DUAL": "1", "RB_LEAF_VOTES": "24", "RB_DUAL_REFILL": "16"}, rb.TRACE_EXACT))
     variants.append(("ordered_phased_v8_t20_s2", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "20", "RB_LEAF_VOTES": "8", "RB_NODE_STEPS": "2", "RB_DUAL": "0"}, rb.TRACE_ORDERED))
     variants.append(("ordered_phased_v6_t12_s6", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "12", "RB_LEAF_VOTES": "6", "RB_NODE_STEPS": "6", "RB_DUAL": "0"}, rb.TRACE_ORDERED))
@@ -737,6 +740,7 @@ def run_explore(args):
     base, d_io, d_id, results = None, None, None, {}
     for name, env, mode in variants:
         os.environ.update(env)
+        os.environ["RB_RING"] = env.get("RB_RING", "0")
         rc = rb.Raycaster()
         rc.addMesh(pos, idx)
         rc.updateHierarchy()

@@ -118,6 +118,7 @@ struct rb_raycaster {
 	int leafVotes	   = 6;	   // > 0: phase-voting scheduler, leaf phase runs once this many lanes wait for it (0: off)
 	int nodeSteps	   = 6;	   // phase-voting scheduler: node steps per vote
 	bool dual		   = false; // two rays per lane (rb_k_trace_dual)
+	bool ring		   = false; // prepared-ray ring per warp (rb_k_trace_ring, experiment)
 	int dualRefill	   = 16;   // dual: refill once this many of a warp's 64 slots are free
 	int fetchThreshold = 12;   // refill a warp from the queue when fewer lanes than this are still traversing
 	mutable std::atomic<uint64_t> launches{0};

@@ -266,6 +266,140 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_phased(RbDeviceBvh 
 	}
 }
 
+// Phase-voting scheduler with a per-warp shared-memory ring of PREPARED rays (experiment, RB_RING=1).
+// In the kernel above a refill puts a dependent global load and the ≈60 instructions of Ray::Ray (sqrt, IEEE
+// divisions) on the critical path of the whole warp, executed by the few lanes that are idle; that is why refilling
+// early does not pay there. Here the warp fetches 32 rays at a time with one atomicAdd, every lane prepares one of them
+// (full SIMD width, one coalesced load) and parks it in the warp's ring; a lane whose ray has finished takes the next
+// prepared ray with a ballot-ranked shared-memory read. Closest-hit records go the other way: (t, u, v, triangle, ray)
+// is parked in a second ring and expanded into the 48-byte Hit by the full warp, 32 records at a time.
+// Per ray the order of operations is untouched: identical results.
+#define RB_RING_RAY_WORDS 11 // pos, dir, inv (9), ray index, regular flag
+#define RB_RING_DONE_WORDS 5 // t, u, v, triangle, ray index
+#define RB_RING_DONE_SLOTS 64
+#define RB_RING_WARP_WORDS (RB_RING_RAY_WORDS * 32 + RB_RING_DONE_WORDS * RB_RING_DONE_SLOTS)
+
+template<bool ANY, bool ORDERED>
+__global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_ring(RbDeviceBvh bvh, const float * __restrict__ org, const float * __restrict__ dir, float mini, float maxi, unsigned int n, void * __restrict__ out, unsigned int * __restrict__ cursor, int threshold, int leafVotes, int nodeSteps) {
+	extern __shared__ int s_stack[];
+	const RbStack st		 = rb_make_stack(s_stack + threadIdx.x, blockDim.x);
+	const unsigned int lane	 = threadIdx.x & 31u;
+	const unsigned int below = (1u << lane) - 1u;
+	float * ring = reinterpret_cast<float *>(s_stack + (bvh.stackDepth > 0 ? bvh.stackDepth : 1) * blockDim.x) + (threadIdx.x >> 5) * RB_RING_WARP_WORDS;
+	float * done = ring + RB_RING_RAY_WORDS * 32;
+	unsigned int ringHead = 0, ringCount = 0, doneHead = 0, doneCount = 0; // warp-uniform
+	bool active = false, exhausted = false; // exhausted: the global queue is empty (the ring may still hold rays)
+	unsigned int rayIdx = 0;
+	RbRay ray;
+	RbTraversal T;
+	// The guard bounds the loop whatever happens: an experiment must not be able to hang the device.
+	for(unsigned int guard = 0; guard < 0x20000000u; ++guard) {
+		unsigned int idle = __ballot_sync(0xffffffffu, !active);
+		while(idle != 0u) {
+			if(ringCount == 0u) {
+				if(exhausted) break;
+				unsigned int base = 0;
+				if(lane == 0) base = atomicAdd(cursor, 32u);
+				base = __shfl_sync(0xffffffffu, base, 0);
+				const unsigned int idx = base + lane;
+				if(idx < n) {
+					V3 o, d;
+					rb_load_ray(org, dir, idx, o, d);
+					const RbRay r = rb_make_ray(o, d);
+					ring[0 * 32 + lane] = r.pos.x; ring[1 * 32 + lane] = r.pos.y; ring[2 * 32 + lane] = r.pos.z;
+					ring[3 * 32 + lane] = r.dir.x; ring[4 * 32 + lane] = r.dir.y; ring[5 * 32 + lane] = r.dir.z;
+					ring[6 * 32 + lane] = r.inv.x; ring[7 * 32 + lane] = r.inv.y; ring[8 * 32 + lane] = r.inv.z;
+					ring[9 * 32 + lane]	 = __uint_as_float(idx);
+					ring[10 * 32 + lane] = __uint_as_float(r.regular ? 1u : 0u);
+				}
+				__syncwarp();
+				ringHead  = 0;
+				ringCount = base < n ? min(32u, n - base) : 0u;
+				exhausted = (base >= n) || (n - base <= 32u);
+				if(ringCount == 0u) break;
+			}
+			const unsigned int take = min((unsigned int)__popc(idle), ringCount);
+			const unsigned int rank = __popc(idle & below);
+			if(!active && rank < take) {
+				const unsigned int slot = ringHead + rank; // < 32: ringHead + ringCount never exceeds the batch
+				ray.pos		= V3{ring[0 * 32 + slot], ring[1 * 32 + slot], ring[2 * 32 + slot]};
+				ray.dir		= V3{ring[3 * 32 + slot], ring[4 * 32 + slot], ring[5 * 32 + slot]};
+				ray.inv		= V3{ring[6 * 32 + slot], ring[7 * 32 + slot], ring[8 * 32 + slot]};
+				rayIdx		= __float_as_uint(ring[9 * 32 + slot]);
+				ray.regular = __float_as_uint(ring[10 * 32 + slot]) != 0u;
+				ray.pxy = rb_pack2(ray.pos.x, ray.pos.y); ray.pzx = rb_pack2(ray.pos.z, ray.pos.x); ray.pyz = rb_pack2(ray.pos.y, ray.pos.z);
+				ray.ixy = rb_pack2(ray.inv.x, ray.inv.y); ray.izx = rb_pack2(ray.inv.z, ray.inv.x); ray.iyz = rb_pack2(ray.inv.y, ray.inv.z);
+				rb_traversal_init(T, bvh, mini, maxi, st);
+				active = true;
+			}
+			__syncwarp(); // the slots are read before a later batch may overwrite them
+			ringHead += take;
+			ringCount -= take;
+			idle = __ballot_sync(0xffffffffu, !active);
+		}
+		unsigned int activeM = __ballot_sync(0xffffffffu, active);
+		if(activeM == 0u) break;
+		const bool noMore = exhausted && ringCount == 0u;
+		bool more;
+		do {
+			const bool wantsLeaf	 = active && rb_wants_leaf(T);
+			const unsigned int leafM = __ballot_sync(0xffffffffu, wantsLeaf);
+			const unsigned int nodeM = activeM & ~leafM;
+			bool finished = false;
+			if(__popc(leafM) >= leafVotes || nodeM == 0u) {
+				if(wantsLeaf) finished = rb_phase_leaf<ANY, false>(T, bvh, ray, nullptr);
+			} else if(active && !wantsLeaf) {
+				for(int k = 0; k < nodeSteps; ++k) {
+					finished = rb_phase_node<false, ORDERED, false>(T, bvh, ray, st, nullptr);
+					if(finished || rb_wants_leaf(T)) break;
+				}
+			}
+			if(finished) {
+				if(ANY) rb_store_any(static_cast<uint8_t *>(out), rayIdx, bvh, T.best);
+				active = false;
+			}
+			if(!ANY) {
+				const unsigned int fin = __ballot_sync(0xffffffffu, finished);
+				if(fin != 0u) {
+					if(finished) {
+						const unsigned int slot = (doneHead + doneCount + __popc(fin & below)) & (RB_RING_DONE_SLOTS - 1);
+						done[0 * RB_RING_DONE_SLOTS + slot] = T.best.t;
+						done[1 * RB_RING_DONE_SLOTS + slot] = T.best.u;
+						done[2 * RB_RING_DONE_SLOTS + slot] = T.best.v;
+						done[3 * RB_RING_DONE_SLOTS + slot] = __int_as_float(T.best.tri);
+						done[4 * RB_RING_DONE_SLOTS + slot] = __uint_as_float(rayIdx);
+					}
+					doneCount += __popc(fin); // <= 31 + 32 < RB_RING_DONE_SLOTS
+					__syncwarp();
+					if(doneCount >= 32u) {
+						const unsigned int slot = (doneHead + lane) & (RB_RING_DONE_SLOTS - 1);
+						RbHitRec h;
+						h.t	  = done[0 * RB_RING_DONE_SLOTS + slot];
+						h.u	  = done[1 * RB_RING_DONE_SLOTS + slot];
+						h.v	  = done[2 * RB_RING_DONE_SLOTS + slot];
+						h.tri = __float_as_int(done[3 * RB_RING_DONE_SLOTS + slot]);
+						rb_store_hit(static_cast<rb_hit *>(out), __float_as_uint(done[4 * RB_RING_DONE_SLOTS + slot]), bvh, h);
+						__syncwarp();
+						doneHead = (doneHead + 32u) & (RB_RING_DONE_SLOTS - 1);
+						doneCount -= 32u;
+					}
+				}
+			}
+			activeM = __ballot_sync(0xffffffffu, active);
+			more	= activeM != 0u && (noMore || __popc(activeM) >= threshold);
+		} while(more);
+	}
+	if(!ANY && lane < doneCount) {
+		const unsigned int slot = (doneHead + lane) & (RB_RING_DONE_SLOTS - 1);
+		RbHitRec h;
+		h.t	  = done[0 * RB_RING_DONE_SLOTS + slot];
+		h.u	  = done[1 * RB_RING_DONE_SLOTS + slot];
+		h.v	  = done[2 * RB_RING_DONE_SLOTS + slot];
+		h.tri = __float_as_int(done[3 * RB_RING_DONE_SLOTS + slot]);
+		rb_store_hit(static_cast<rb_hit *>(out), __float_as_uint(done[4 * RB_RING_DONE_SLOTS + slot]), bvh, h);
+	}
+}
+
 // Two rays per lane. The profile of the kernels above (profiles/) shows why a warp is slow: in the node loop only ~11
 // of 32 lanes are busy — the others have reached a leaf and wait for the slowest descent. Here every lane owns two
 // independent rays, A and B, each with its own registers and stack column; one iteration runs the node phase for the A
@@ -471,6 +605,7 @@ extern "C" rb_status rb_raycaster_create(rb_raycaster ** out) {
 	if(const char * e = getenv("RB_LEAF_VOTES")) (*out)->leafVotes = atoi(e);
 	if(const char * e = getenv("RB_NODE_STEPS")) (*out)->nodeSteps = atoi(e);
 	if(const char * e = getenv("RB_DUAL")) (*out)->dual = atoi(e) != 0;
+	if(const char * e = getenv("RB_RING")) (*out)->ring = atoi(e) != 0;
 	if(const char * e = getenv("RB_DUAL_REFILL")) (*out)->dualRefill = atoi(e);
 	return RB_OK;
 }
@@ -739,6 +874,11 @@ static rb_status rb_launch_trace(const rb_raycaster * rc, const float * d_origin
 	if(rc->persistent && rc->dual) {
 		auto kernel = ordered ? rb_k_trace_dual<ANY, true> : rb_k_trace_dual<ANY, false>;
 		return rb_launch_persistent<ANY>(rc, kernel, 2 * smem, 2, d_origins, d_directions, mini, maxi, nrays, d_out, s, rc->dualRefill, rc->leafVotes > 0 ? rc->leafVotes : 24);
+	}
+	if(rc->persistent && rc->leafVotes > 0 && rc->ring && rc->dev.rootLevels == 0) {
+		auto kernel = ordered ? rb_k_trace_ring<ANY, true> : rb_k_trace_ring<ANY, false>;
+		const size_t ringBytes = size_t(RB_TRACE_BLOCK / 32) * RB_RING_WARP_WORDS * sizeof(float);
+		return rb_launch_persistent<ANY>(rc, kernel, smem + ringBytes, 1, d_origins, d_directions, mini, maxi, nrays, d_out, s, rc->fetchThreshold, rc->leafVotes, rc->nodeSteps > 0 ? rc->nodeSteps : 1);
 	}
 	if(rc->persistent && rc->leafVotes > 0) {
 		// Handles that carry root blocks (many meshes in a spatially coherent order) use the kernels compiled with them.

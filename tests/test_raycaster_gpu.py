@@ -240,15 +240,18 @@ def test_ordered_mode_same_hits_and_less_work():
     assert (~same).sum() <= 2, (~same).sum()
 
 
-@pytest.mark.parametrize("persistent,threshold,votes,dual", [("0", "20", "0", "0"), ("1", "1", "0", "0"), ("1", "32", "0", "0"), ("1", "20", "1", "0"), ("1", "20", "8", "0"),
-                                                             ("1", "4", "32", "0"), ("1", "20", "20", "1"), ("1", "20", "1", "1"), ("1", "20", "32", "1")])
-def test_scheduler_variants_are_bit_identical(persistent, threshold, votes, dual, monkeypatch):
-    """One ray per thread, the persistent work-queue kernels (any refill threshold) and the phase-voting scheduler (any
-    vote count) must return the same records: they only change how the rays of a warp are interleaved."""
+@pytest.mark.parametrize("persistent,threshold,votes,dual,ring", [("0", "20", "0", "0", "0"), ("1", "1", "0", "0", "0"), ("1", "32", "0", "0", "0"), ("1", "20", "1", "0", "0"), ("1", "20", "8", "0", "0"),
+                                                                  ("1", "4", "32", "0", "0"), ("1", "20", "20", "1", "0"), ("1", "20", "1", "1", "0"), ("1", "20", "32", "1", "0"),
+                                                                  ("1", "12", "6", "0", "1"), ("1", "32", "1", "0", "1"), ("1", "1", "32", "0", "1")])
+def test_scheduler_variants_are_bit_identical(persistent, threshold, votes, dual, ring, monkeypatch):
+    """One ray per thread, the persistent work-queue kernels (any refill threshold), the phase-voting scheduler (any
+    vote count), its two-rays-per-lane and prepared-ray-ring experiments must return the same records: they only change
+    how the rays of a warp are interleaved."""
     monkeypatch.setenv("RB_PERSISTENT", persistent)
     monkeypatch.setenv("RB_FETCH_THRESHOLD", threshold)
     monkeypatch.setenv("RB_LEAF_VOTES", votes)
     monkeypatch.setenv("RB_DUAL", dual)
+    monkeypatch.setenv("RB_RING", ring)
     c = load_case("raycast_multimesh")
     r = product_from_case(c)
     h = r.intersects(c["org"], c["dirs"], float(c["mini"]), float(c["maxi"]))
