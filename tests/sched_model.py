@@ -46,6 +46,86 @@ def ray_tokens(o, org, dirs):
     return out
 
 
+def simulate_postponed(rays, threshold, votes, steps, c_refill, c_finish, c_park=4):
+    """The same warp when a lane may PARK one leaf and keep descending (rb_k_trace_phased with POSTPONE):
+    a lane waits for the leaf phase only when it reaches a second leaf while one is parked, or when it has run out of
+    nodes with a leaf still parked; a leaf phase serves every lane that has a parked triangle, waiting or not. The step
+    sequences are the reference's (the few extra nodes a later-shrinking `maxi` lets through are not modelled).
+    Returns (warp-instructions per ray, mean lanes busy in node steps, mean lanes busy in leaf steps)."""
+    nxt, n = 0, len(rays)
+    seq = [None] * 32
+    pos = np.zeros(32, np.int64)
+    parked = np.zeros(32, np.int64)  # triangles left in the parked leaf
+    live = np.zeros(32, bool)
+    cost = 0.0
+    node_steps = node_lanes = leaf_steps = leaf_lanes = 0
+
+    def at_leaf(l):
+        return pos[l] < seq[l].size and seq[l][pos[l]] == 2
+
+    def park(l):  # the leaf the lane stands on becomes its parked leaf (all its triangles)
+        k = 0
+        while at_leaf(l):
+            pos[l] += 1
+            k += 1
+        parked[l] = k
+
+    while True:
+        exhausted = nxt >= n
+        if not exhausted and (~live).any():
+            for l in np.flatnonzero(~live):
+                if nxt < n:
+                    seq[l], pos[l], live[l], parked[l] = rays[nxt], 0, True, 0
+                    nxt += 1
+            cost += c_refill
+            exhausted = nxt >= n
+        if not live.any():
+            break
+        while True:
+            for l in np.flatnonzero(live):
+                if parked[l] == 0 and at_leaf(l):
+                    park(l)
+            blocked = np.array([live[l] and parked[l] > 0 and (at_leaf(l) or pos[l] >= seq[l].size) for l in range(32)])
+            wants_node = live & ~blocked
+            cost += C_VOTE
+            finished = np.zeros(32, bool)
+            if blocked.sum() >= votes or not wants_node.any():
+                cost += C_LEAF
+                leaf_steps += 1
+                for l in np.flatnonzero(live & (parked > 0)):
+                    parked[l] -= 1
+                    leaf_lanes += 1
+            else:
+                act = wants_node.copy()
+                for _ in range(steps):
+                    if not act.any():
+                        break
+                    cost += C_NODE + c_park
+                    node_steps += 1
+                    node_lanes += int(act.sum())
+                    for l in np.flatnonzero(act):
+                        if pos[l] >= seq[l].size:
+                            if parked[l] > 0:  # out of nodes, but a parked leaf is left: wait for the leaf phase
+                                act[l] = False
+                            else:
+                                finished[l] = True
+                                act[l] = False
+                            continue
+                        pos[l] += 1
+                        if at_leaf(l):
+                            if parked[l] == 0:
+                                park(l)
+                            else:
+                                act[l] = False
+            if finished.any():
+                cost += c_finish
+                live &= ~finished
+            nlive = int(live.sum())
+            if not (nlive > 0 if exhausted else nlive >= threshold):
+                break
+    return cost / n, node_lanes / max(node_steps, 1), leaf_lanes / max(leaf_steps, 1)
+
+
 def simulate(rays, threshold, votes, steps, c_refill, c_finish, per_ray_extra=0.0):
     """One persistent warp consuming `rays` in order. Returns (warp-instructions per ray, mean lanes busy in node steps)."""
     nxt = 0
@@ -138,6 +218,14 @@ def main():
             row.append("%4.0f" % c)
             occ.append("%4.1f" % a)
         print("%-34s %s   | lanes/node step: %s" % (name, "  ".join(row), " ".join(occ)))
+    for name, votes, steps in (("parked leaf   v6 s6 (R150 F45)", 6, 6), ("parked leaf   v12 s6", 12, 6), ("parked leaf   v16 s8", 16, 8), ("parked leaf   v24 s8", 24, 8)):
+        row, occ, locc = [], [], []
+        for t in (4, 8, 12, 16, 20, 24, 28, 32):
+            c, a, b = simulate_postponed(rays, t, votes, steps, 150, 45)
+            row.append("%4.0f" % c)
+            occ.append("%4.1f" % a)
+            locc.append("%4.1f" % b)
+        print("%-34s %s   | lanes/node step: %s | lanes/leaf step: %s" % (name, "  ".join(row), " ".join(occ), " ".join(locc)))
 
 
 if __name__ == "__main__":
