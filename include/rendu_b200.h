@@ -109,7 +109,12 @@ typedef enum rb_trace_mode {
 	/* Near-child-first ordered traversal on the same tree, same triangle test. Same hit except where the
 	 * reference's non-watertight box test makes the result depend on visiting order. Any-hit queries
 	 * (intersect_any, visible) always use this order: they never shrink maxi, so their boolean cannot depend on it. */
-	RB_TRACE_ORDERED = 1
+	RB_TRACE_ORDERED = 1,
+	/* Experiment: the reference-order tree collapsed into eight-wide nodes with 8-bit child boxes rounded outwards
+	 * (rb_raycaster_wide_build), children visited in the reference's order. Enters a superset of the reference's
+	 * leaves in the same relative order: same closest hit (also on exact ties) except where a triangle is accepted
+	 * whose own boxes the reference's rounded slab test rejects. Raycaster queries only (not the path tracer). */
+	RB_TRACE_WIDE = 2
 } rb_trace_mode;
 
 RB_API rb_status rb_raycaster_create(rb_raycaster ** out);
@@ -154,6 +159,15 @@ RB_API rb_status rb_raycaster_update_mesh(rb_raycaster * rc, uint32_t mesh, cons
 RB_API rb_status rb_raycaster_build_times(const rb_raycaster * rc, double out[2]);
 
 RB_API rb_status rb_raycaster_set_trace_mode(rb_raycaster * rc, rb_trace_mode mode);
+
+/* Collapse the host-built reference-order hierarchy (Raycaster.cpp:58-142) into the eight-wide quantised layout of
+ * RB_TRACE_WIDE and, when the hierarchy is on a device, upload it. The collapse itself needs no GPU. out (may be NULL):
+ * out[0]=wide nodes, out[1]=triangles, out[2]=roots, out[3]=depth. Fails for LBVH-built or re-fitted hierarchies and for
+ * leaves of more than three triangles. A later rebuild or refit discards the wide copy. */
+RB_API rb_status rb_raycaster_wide_build(rb_raycaster * rc, uint64_t out[4]);
+/* Host copy of the wide hierarchy: nodes = out[0]*20 words, tris = out[1]*12 floats (word 11 = triangle index in hierarchy
+ * order), root_nodes = out[2] ints (wide node of each mesh, -1 for an empty mesh). Any pointer may be NULL. */
+RB_API rb_status rb_raycaster_wide_download(const rb_raycaster * rc, uint32_t * nodes, float * tris, int32_t * root_nodes);
 
 /* Raycaster::intersects (Raycaster.cpp:144-185), batched: origins/directions are nrays*3 floats (directions need
  * not be normalised, Intersection.cpp:3-5). Reference defaults: mini = 1e-4f, maxi = 1e8f (Raycaster.hpp:65). */

@@ -85,6 +85,8 @@ def lib():
         "rb_raycaster_refit": (C.c_int, [vp, vp, sz]),
         "rb_raycaster_update_mesh": (C.c_int, [vp, u32, vp, sz, vp]),
         "rb_raycaster_set_trace_mode": (C.c_int, [vp, C.c_int]),
+        "rb_raycaster_wide_build": (C.c_int, [vp, vp]),
+        "rb_raycaster_wide_download": (C.c_int, [vp, vp, vp, vp]),
         "rb_raycaster_build_times": (C.c_int, [vp, vp]),
         "rb_raycaster_intersect": (C.c_int, [vp, vp, vp, f32, f32, sz, vp]),
         "rb_raycaster_intersect_any": (C.c_int, [vp, vp, vp, f32, f32, sz, vp]),

@@ -2,6 +2,7 @@
 #pragma once
 #include "../../include/rendu_b200.h"
 #include "rb_types.h"
+#include "rb_wide.h"
 
 #include <atomic>
 #include <cstdarg>
@@ -105,6 +106,14 @@ struct rb_raycaster {
 	size_t nVerts	   = 0;
 	size_t nLeaves	   = 0;
 	int buildMode	   = RB_BUILD_REFERENCE;
+
+	// Eight-wide quantised copy of the host-built tree (rb_wide.h; RB_TRACE_WIDE): host arrays and device copy.
+	std::unique_ptr<RbWideBvh> wide;
+	uint4 * d_wideNodes	 = nullptr;
+	float4 * d_wideTris	 = nullptr;
+	int * d_wideRoots	 = nullptr;
+	RbDeviceWide devWide = {};
+	bool wideOnDevice	 = false;
 
 	// Work-queue cursors of the persistent kernels: a ring of counters, one taken per launch (no allocation on the
 	// launch path; a slot is reused only after RB_CURSOR_RING further launches).

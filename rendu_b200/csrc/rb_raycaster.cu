@@ -3,6 +3,7 @@
 // intersects :144-185, intersectsAny :187-224, visible :226-230).
 #include "rb_internal.h"
 #include "rb_trace.cuh"
+#include "rb_wide.cuh"
 
 #include <cstdlib>
 #include <cstring>
@@ -400,6 +401,80 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_ring(RbDeviceBvh bv
 	}
 }
 
+// Eight-wide quantised tree (RB_TRACE_WIDE; rb_wide.h, rb_wide.cuh): persistent threads + warp work queue as in
+// rb_k_trace_persistent, one rb_wide_step per iteration. Rays whose slab arithmetic can produce NaNs or overflow
+// (a zero / denormal direction component, |1/d| >= 2^60, a non-finite origin) are rare: they are walked through the
+// binary tree on the spot, by the exact NaN-faithful traversal.
+RB_D bool rb_wide_ray_ok(const RbRay & ray) {
+	const float big = 1152921504606846976.0f; // 2^60
+	return ray.regular && fabsf(ray.inv.x) < big && fabsf(ray.inv.y) < big && fabsf(ray.inv.z) < big;
+}
+
+template<bool ANY>
+__global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_wide(RbDeviceBvh bvh, const float * __restrict__ org, const float * __restrict__ dir, float mini, float maxi, unsigned int n, void * __restrict__ out, unsigned int * __restrict__ cursor, int threshold, RbDeviceWide wide) {
+	extern __shared__ int s_stack[];
+	const RbStack st = rb_make_stack(s_stack + threadIdx.x, blockDim.x);
+	const unsigned int lane = threadIdx.x & 31u;
+	bool active = false, exhausted = false;
+	unsigned int rayIdx = 0;
+	RbRay ray;
+	RbWideTraversal T;
+	for(;;) {
+		if(!exhausted) {
+			const unsigned int idle = __ballot_sync(0xffffffffu, !active);
+			if(idle) {
+				const int nIdle	 = __popc(idle);
+				const int leader = __ffs(idle) - 1;
+				unsigned int base = 0;
+				if((int)lane == leader) base = atomicAdd(cursor, (unsigned int)nIdle);
+				base = __shfl_sync(0xffffffffu, base, leader);
+				if(!active) {
+					const unsigned int idx = base + __popc(idle & ((1u << lane) - 1u));
+					if(idx < n) {
+						V3 o, d;
+						rb_load_ray(org, dir, idx, o, d);
+						ray = rb_make_ray(o, d);
+						if(rb_wide_ray_ok(ray)) {
+							rb_wide_init(T, bvh, mini, maxi, st);
+							rayIdx = idx;
+							active = true;
+						} else {
+							RbTraversal B;
+							rb_traversal_init(B, bvh, mini, maxi, st);
+							if(ANY) {
+								while(!rb_step_ordered<true, false, false>(B, bvh, ray, st, nullptr)) {
+								}
+							} else {
+								while(!rb_step_exact<false, false, false>(B, bvh, ray, st, nullptr)) {
+								}
+							}
+							if(ANY) rb_store_any(static_cast<uint8_t *>(out), idx, bvh, B.best);
+							else rb_store_hit(static_cast<rb_hit *>(out), idx, bvh, B.best);
+						}
+					}
+				}
+				exhausted = (base + (unsigned int)nIdle) >= n;
+			}
+		}
+		if(!__any_sync(0xffffffffu, active)) {
+			if(exhausted) break;
+			continue; // every fetched ray took the binary path: fetch again
+		}
+		bool more;
+		do {
+			if(active) {
+				if(rb_wide_step<ANY>(T, bvh, wide, ray, st)) {
+					if(ANY) rb_store_any(static_cast<uint8_t *>(out), rayIdx, bvh, T.best);
+					else rb_store_hit(static_cast<rb_hit *>(out), rayIdx, bvh, T.best);
+					active = false;
+				}
+			}
+			const int nActive = __popc(__ballot_sync(0xffffffffu, active));
+			more = exhausted ? (nActive > 0) : (nActive >= threshold);
+		} while(more);
+	}
+}
+
 // Two rays per lane. The profile of the kernels above (profiles/) shows why a warp is slow: in the node loop only ~11
 // of 32 lanes are busy — the others have reached a leaf and wait for the slowest descent. Here every lane owns two
 // independent rays, A and B, each with its own registers and stack column; one iteration runs the node phase for the A
@@ -517,6 +592,18 @@ size_t rb_trace_smem_bytes(const rb_raycaster * rc, int blockThreads) {
 	return size_t(depth) * size_t(blockThreads) * sizeof(int);
 }
 
+// The wide tree is a derived copy: it goes whenever the binary tree it was collapsed from is replaced or re-fitted.
+static void rb_wide_free_device(rb_raycaster * rc) {
+	cudaFree(rc->d_wideNodes);
+	cudaFree(rc->d_wideTris);
+	cudaFree(rc->d_wideRoots);
+	rc->d_wideNodes = nullptr;
+	rc->d_wideTris	= nullptr;
+	rc->d_wideRoots = nullptr;
+	rc->devWide		= RbDeviceWide{};
+	rc->wideOnDevice = false;
+}
+
 void rb_raycaster_free_device(rb_raycaster * rc) {
 	if(!rb_have_device() || rc->device < 0) return; // nothing was ever allocated: leave the caller's current device alone
 	int previous = 0;
@@ -534,6 +621,7 @@ void rb_raycaster_free_device(rb_raycaster * rc) {
 	cudaFree(rc->d_triIds);
 	cudaFree(rc->d_cursors);
 	rc->d_cursors = nullptr;
+	rb_wide_free_device(rc);
 	cudaFree(rc->d_rootBlocks);
 	rc->d_rootBlocks   = nullptr;
 	rc->rootBlocksCapacity = 0;
@@ -798,6 +886,11 @@ extern "C" rb_status rb_raycaster_refit(rb_raycaster * rc, const float * world_p
 	if(!world_positions && nverts) return rb_fail(RB_ERR_INVALID, "rb_raycaster_refit: null positions with a vertex count");
 	RB_REQUIRE_DEVICE();
 	if(!rc->built) return rb_fail(RB_ERR_INVALID, "rb_raycaster_refit: hierarchy not built");
+	if(rc->wideOnDevice) { // its quantised boxes describe the old positions
+		RB_CUDA(cudaSetDevice(rc->device));
+		rb_wide_free_device(rc);
+	}
+	rc->wide.reset();
 	return rb_lbvh_refit(rc, world_positions, nverts);
 }
 
@@ -810,8 +903,51 @@ extern "C" rb_status rb_raycaster_build_times(const rb_raycaster * rc, double ou
 
 extern "C" rb_status rb_raycaster_set_trace_mode(rb_raycaster * rc, rb_trace_mode mode) {
 	if(!rc) return rb_fail(RB_ERR_INVALID, "rb_raycaster_set_trace_mode: null handle");
-	if(mode != RB_TRACE_EXACT && mode != RB_TRACE_ORDERED) return rb_fail(RB_ERR_INVALID, "unknown trace mode %d", int(mode));
+	if(mode != RB_TRACE_EXACT && mode != RB_TRACE_ORDERED && mode != RB_TRACE_WIDE) return rb_fail(RB_ERR_INVALID, "unknown trace mode %d", int(mode));
+	if(mode == RB_TRACE_WIDE && !rc->wideOnDevice) return rb_fail(RB_ERR_INVALID, "RB_TRACE_WIDE: no wide tree on the device (call rb_raycaster_wide_build after rb_raycaster_build)");
 	rc->traceMode = mode;
+	return RB_OK;
+}
+
+extern "C" rb_status rb_raycaster_wide_build(rb_raycaster * rc, uint64_t out[4]) {
+	if(!rc) return rb_fail(RB_ERR_INVALID, "rb_raycaster_wide_build: null handle");
+	if(rc->buildMode != RB_BUILD_REFERENCE || rc->hostMirrorStale || rc->nodes.empty()) return rb_fail(RB_ERR_INVALID, "rb_raycaster_wide_build: needs the host-built (reference-order) hierarchy, not re-fitted since");
+	RbFlatBvh flat;
+	std::string why;
+	if(!rb_host_flatten(rc, flat, &why)) return rb_fail(RB_ERR_INVALID, "rb_raycaster_wide_build: %s", why.c_str());
+	auto wide = std::make_unique<RbWideBvh>();
+	if(!rb_wide_collapse(flat, rc->meshCount, *wide, &why)) return rb_fail(RB_ERR_INVALID, "rb_raycaster_wide_build: %s", why.c_str());
+	rc->wide = std::move(wide);
+	if(out) {
+		out[0] = rc->wide->nodes.size() / RB_WIDE_NODE_WORDS;
+		out[1] = rc->wide->tris.size() / 12;
+		out[2] = rc->wide->rootNode.size();
+		out[3] = uint64_t(rc->wide->depth);
+	}
+	if(!rc->built || rc->device < 0) return RB_OK; // host only (no device tree yet): sizes and download still work
+	RB_CUDA(cudaSetDevice(rc->device));
+	rb_wide_free_device(rc);
+	const RbWideBvh & w = *rc->wide;
+	RB_CUDA(cudaMalloc(&rc->d_wideNodes, w.nodes.size() * sizeof(uint32_t) + 64));
+	RB_CUDA(cudaMalloc(&rc->d_wideTris, w.tris.size() * sizeof(float) + 64));
+	RB_CUDA(cudaMalloc(&rc->d_wideRoots, w.rootNode.size() * sizeof(int32_t) + 64));
+	RB_CUDA(cudaMemcpy(rc->d_wideNodes, w.nodes.data(), w.nodes.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+	RB_CUDA(cudaMemcpy(rc->d_wideTris, w.tris.data(), w.tris.size() * sizeof(float), cudaMemcpyHostToDevice));
+	RB_CUDA(cudaMemcpy(rc->d_wideRoots, w.rootNode.data(), w.rootNode.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+	rc->devWide.nodes	   = rc->d_wideNodes;
+	rc->devWide.tris	   = rc->d_wideTris;
+	rc->devWide.rootNode   = rc->d_wideRoots;
+	rc->devWide.stackDepth = w.depth + 1;
+	rc->wideOnDevice	   = true;
+	return RB_OK;
+}
+
+extern "C" rb_status rb_raycaster_wide_download(const rb_raycaster * rc, uint32_t * nodes, float * tris, int32_t * root_nodes) {
+	if(!rc) return rb_fail(RB_ERR_INVALID, "rb_raycaster_wide_download: null handle");
+	if(!rc->wide) return rb_fail(RB_ERR_INVALID, "rb_raycaster_wide_download: no wide tree (call rb_raycaster_wide_build)");
+	if(nodes) std::memcpy(nodes, rc->wide->nodes.data(), rc->wide->nodes.size() * sizeof(uint32_t));
+	if(tris) std::memcpy(tris, rc->wide->tris.data(), rc->wide->tris.size() * sizeof(float));
+	if(root_nodes) std::memcpy(root_nodes, rc->wide->rootNode.data(), rc->wide->rootNode.size() * sizeof(int32_t));
 	return RB_OK;
 }
 
@@ -871,6 +1007,12 @@ static rb_status rb_launch_trace(const rb_raycaster * rc, const float * d_origin
 	// (it finds an occluder sooner), also in RB_TRACE_EXACT mode. Closest-hit queries follow the handle's mode.
 	const bool ordered = ANY || rc->traceMode == RB_TRACE_ORDERED;
 	RB_CUDA(cudaSetDevice(rc->device)); // the stream and the pointers must belong to the device that holds the tree
+	if(rc->traceMode == RB_TRACE_WIDE) {
+		if(!rc->wideOnDevice) return rb_fail(RB_ERR_INVALID, "RB_TRACE_WIDE: the wide tree is gone (the hierarchy was rebuilt or re-fitted): call rb_raycaster_wide_build again");
+		const int entries	  = 5 * rc->devWide.stackDepth > rc->dev.stackDepth ? 5 * rc->devWide.stackDepth : (rc->dev.stackDepth > 0 ? rc->dev.stackDepth : 1);
+		const size_t wideSmem = size_t(entries) * RB_TRACE_BLOCK * sizeof(int);
+		return rb_launch_persistent<ANY>(rc, rb_k_trace_wide<ANY>, wideSmem, 1, d_origins, d_directions, mini, maxi, nrays, d_out, s, rc->fetchThreshold, rc->devWide);
+	}
 	if(rc->persistent && rc->dual) {
 		auto kernel = ordered ? rb_k_trace_dual<ANY, true> : rb_k_trace_dual<ANY, false>;
 		return rb_launch_persistent<ANY>(rc, kernel, 2 * smem, 2, d_origins, d_directions, mini, maxi, nrays, d_out, s, rc->dualRefill, rc->leafVotes > 0 ? rc->leafVotes : 24);

@@ -12,7 +12,7 @@ from . import _capi
 from ._capi import HIT_DTYPE, NODE_DTYPE, TRI_DTYPE, check, lib, ptr
 
 BUILD_REFERENCE, BUILD_LBVH = 0, 1
-TRACE_EXACT, TRACE_ORDERED = 0, 1
+TRACE_EXACT, TRACE_ORDERED, TRACE_WIDE = 0, 1, 2
 
 
 def _rays(a):
@@ -98,6 +98,23 @@ class Raycaster:
 
     def set_trace_mode(self, mode):
         check(lib().rb_raycaster_set_trace_mode(self._h, int(mode)))
+
+    def build_wide(self):
+        """Collapse the host-built hierarchy into the eight-wide quantised layout (RB_TRACE_WIDE) and upload it when the
+        hierarchy is on a device; returns its sizes. The collapse itself runs without a GPU."""
+        out = np.zeros(4, np.uint64)
+        check(lib().rb_raycaster_wide_build(self._h, ptr(out)))
+        self._wide_sizes = dict(nodes=int(out[0]), tris=int(out[1]), roots=int(out[2]), depth=int(out[3]))
+        return dict(self._wide_sizes)
+
+    def download_wide(self):
+        """(nodes (n, 20) uint32, tris (m, 12) float32 with word 11 = hierarchy index, root_nodes (r,) int32)."""
+        s = self._wide_sizes
+        nodes = np.zeros((s["nodes"], 20), np.uint32)
+        tris = np.zeros((s["tris"], 12), np.float32)
+        roots = np.zeros(s["roots"], np.int32)
+        check(lib().rb_raycaster_wide_download(self._h, ptr(nodes), ptr(tris), ptr(roots)))
+        return nodes, tris, roots
 
     # ------------------------------------------------------------------ queries (Raycaster.cpp:144-230)
     def intersects(self, origin, direction, mini=0.0001, maxi=1e8):
