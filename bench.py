@@ -729,6 +729,8 @@ def run_explore(args):
     for thr in (12, 20, 24, 28, 32):  # prepared-ray ring (experiment): the refill costs no latency, so the threshold can go up
         variants.append(("ring_v6_t%d_s6" % thr, {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": str(thr), "RB_LEAF_VOTES": "6", "RB_NODE_STEPS": "6", "RB_DUAL": "0", "RB_RING": "1"}, rb.TRACE_EXACT))
     variants.append(("ring_v4_t28_s3", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "28", "RB_LEAF_VOTES": "4", "RB_NODE_STEPS": "3", "RB_DUAL": "0", "RB_RING": "1"}, rb.TRACE_EXACT))
+    for thr in (12, 20, 28):  # eight-wide quantised tree (rb_wide.h): plain persistent scheduler, refill threshold as named
+        variants.append(("wide_t%d" % thr, {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": str(thr), "RB_DUAL": "0"}, rb.TRACE_WIDE))
     variants.append(("dual_v24_r16", {"RB_PERSISTENT": "1", "RB_DUAL": "1", "RB_LEAF_VOTES": "24", "RB_DUAL_REFILL": "16"}, rb.TRACE_EXACT))
     variants.append(("ordered_phased_v8_t20_s2", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "20", "RB_LEAF_VOTES": "8", "RB_NODE_STEPS": "2", "RB_DUAL": "0"}, rb.TRACE_ORDERED))
     variants.append(("ordered_phased_v6_t12_s6", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "12", "RB_LEAF_VOTES": "6", "RB_NODE_STEPS": "6", "RB_DUAL": "0"}, rb.TRACE_ORDERED))
@@ -744,6 +746,8 @@ def run_explore(args):
         rc = rb.Raycaster()
         rc.addMesh(pos, idx)
         rc.updateHierarchy()
+        if mode == rb.TRACE_WIDE:
+            rc.build_wide()
         rc.set_trace_mode(mode)
         bufs = {k: torch.empty(n * 48, dtype=torch.uint8, device=dev) for k in ("cc", "ci")}
         anys = {k: torch.empty(n, dtype=torch.uint8, device=dev) for k in ("ac", "ai")}

@@ -1,15 +1,30 @@
 // rb_wide.cpp — host collapse of the reference-order binary tree into the eight-wide quantised tree of rb_wide.h.
+//
+// Which descendants a wide node adopts is decided by the surface-area dynamic programme of Ylitie, Karras and Laine,
+// "Efficient Incoherent Ray Traversal on GPUs Through Compressed Wide BVHs" (HPG 2017), section 3: for every binary
+// node n and every i in 1..7, C(n, i) is the cheapest way to cover the subtree of n with at most i children of a wide
+// node, where one child is either a leaf of up to three triangles or a wide node of its own. Whatever is chosen, the
+// children are listed — and later visited — in the order the reference's stack loop reaches them (right before left,
+// Raycaster.cpp:160-173), and a leaf child lists its triangles in that order too.
 #include "rb_wide.h"
 #include "rb_internal.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 
 namespace {
 
+// Entering a wide node against testing one triangle, in the kernel's own currency (about 200 against 80 instructions,
+// five against three L1 wavefronts).
+const double kCostNode = 1.0, kCostTri = 0.5;
+
 struct WChild {
-	int ref; // binary child reference: >= 0 interior node, < 0 leaf code
+	int node;  // >= 0: binary interior node that becomes a wide node; -1: leaf child
+	int ntris; // leaf child: its triangles (hierarchy indices) in visiting order
+	int tri[RB_WIDE_MAX_LEAF_TRIS];
 	float lo[3], hi[3];
 };
 
@@ -18,27 +33,13 @@ inline int refOf(float f) {
 	std::memcpy(&v, &f, 4);
 	return v;
 }
+inline bool isNone(int ref) { return ref == RB_REF_NONE; }
+inline bool isLeaf(int ref) { return ref < 0; }
+inline int leafFirst(int ref) { return (~ref) >> RB_LEAF_BITS; }
+inline int leafCount(int ref) { return ((~ref) & (RB_LEAF_MAX_TRIS - 1)) + 1; }
 
-// The two children of binary interior node b in VISITING order (right first, Raycaster.cpp:160-173); empty ones dropped.
-inline int childrenOf(const float * nodes, int b, WChild out[2]) {
-	const float * d = nodes + size_t(b) * 16;
-	int n = 0;
-	const int refR = refOf(d[13]), refL = refOf(d[12]);
-	if(refR != RB_REF_NONE) {
-		out[n].ref = refR;
-		for(int a = 0; a < 3; ++a) { out[n].lo[a] = d[6 + a]; out[n].hi[a] = d[9 + a]; }
-		++n;
-	}
-	if(refL != RB_REF_NONE) {
-		out[n].ref = refL;
-		for(int a = 0; a < 3; ++a) { out[n].lo[a] = d[a]; out[n].hi[a] = d[3 + a]; }
-		++n;
-	}
-	return n;
-}
-
-inline double halfArea(const WChild & c) {
-	const double x = double(c.hi[0]) - c.lo[0], y = double(c.hi[1]) - c.lo[1], z = double(c.hi[2]) - c.lo[2];
+inline double halfArea(const float * lo, const float * hi) {
+	const double x = double(hi[0]) - lo[0], y = double(hi[1]) - lo[1], z = double(hi[2]) - lo[2];
 	return x * y + y * z + z * x;
 }
 
@@ -48,18 +49,176 @@ inline float roundDown(double x) {
 	return f;
 }
 
+struct Plan {
+	const float * nodes = nullptr; // flattened binary nodes, 16 floats each
+	std::vector<uint32_t> prims;   // triangles below each interior node
+	std::vector<double> cost;	   // 8 per node: [i] = C(n, i), i = 1..7
+	std::vector<uint8_t> split;	   // 8 per node: [i] = slots given to the LEFT child when covering with i (0: cover with i-1);
+								   // [0] = the same for the eight slots of the node's own wide node
+	std::vector<uint8_t> asLeaf;   // covering with one child: 1 = a leaf of all its triangles, 0 = a wide node
+
+	const float * loL(int b) const { return nodes + size_t(b) * 16; }
+	const float * hiL(int b) const { return nodes + size_t(b) * 16 + 3; }
+	const float * loR(int b) const { return nodes + size_t(b) * 16 + 6; }
+	const float * hiR(int b) const { return nodes + size_t(b) * 16 + 9; }
+	int refL(int b) const { return refOf(nodes[size_t(b) * 16 + 12]); }
+	int refR(int b) const { return refOf(nodes[size_t(b) * 16 + 13]); }
+
+	uint32_t primsOf(int ref) const { return isNone(ref) ? 0u : (isLeaf(ref) ? uint32_t(leafCount(ref)) : prims[ref]); }
+	void table(int ref, const float * lo, const float * hi, double out[8]) const {
+		for(int i = 1; i <= 7; ++i) {
+			if(isNone(ref)) out[i] = 0.0;
+			else if(isLeaf(ref)) out[i] = halfArea(lo, hi) * leafCount(ref) * kCostTri;
+			else out[i] = cost[size_t(ref) * 8 + i];
+		}
+	}
+};
+
+// Fills the plan bottom-up. `box` of an interior node is the one its parent (or the root table) stores for it.
+bool makePlan(const RbFlatBvh & flat, size_t nroots, Plan & P, std::string * why) {
+	const size_t nI = flat.nodes.size() / 16;
+	P.nodes = flat.nodes.data();
+	P.prims.assign(nI, 0u);
+	P.cost.assign(nI * 8, 0.0);
+	P.split.assign(nI * 8, 0);
+	P.asLeaf.assign(nI, 0);
+	std::vector<float> box(nI * 6, 0.0f);
+	std::vector<int> order;
+	order.reserve(nI);
+	std::vector<int> stack;
+	std::vector<uint8_t> seen(nI, 0);
+	for(size_t r = 0; r < nroots; ++r) {
+		const float * d = flat.roots.data() + r * 8;
+		const int ref	= refOf(d[3]);
+		if(isNone(ref) || isLeaf(ref)) continue;
+		if(size_t(ref) >= nI || seen[ref]) {
+			if(why) *why = "malformed hierarchy (root reference)";
+			return false;
+		}
+		seen[ref] = 1;
+		for(int a = 0; a < 3; ++a) { box[size_t(ref) * 6 + a] = d[a]; box[size_t(ref) * 6 + 3 + a] = d[4 + a]; }
+		stack.push_back(ref);
+	}
+	while(!stack.empty()) {
+		const int b = stack.back();
+		stack.pop_back();
+		order.push_back(b);
+		const int refs[2]	   = {P.refL(b), P.refR(b)};
+		const float * los[2] = {P.loL(b), P.loR(b)};
+		const float * his[2] = {P.hiL(b), P.hiR(b)};
+		for(int c = 0; c < 2; ++c) {
+			if(isNone(refs[c]) || isLeaf(refs[c])) continue;
+			if(size_t(refs[c]) >= nI || seen[refs[c]]) {
+				if(why) *why = "malformed hierarchy (a node is referenced twice)";
+				return false;
+			}
+			seen[refs[c]] = 1;
+			std::memcpy(&box[size_t(refs[c]) * 6], los[c], 12);
+			std::memcpy(&box[size_t(refs[c]) * 6 + 3], his[c], 12);
+			stack.push_back(refs[c]);
+		}
+	}
+	const double inf = std::numeric_limits<double>::infinity();
+	for(size_t q = order.size(); q-- > 0;) {
+		const int b = order[q];
+		const int rl = P.refL(b), rr = P.refR(b);
+		P.prims[b] = P.primsOf(rl) + P.primsOf(rr);
+		double cl[8], cr[8];
+		P.table(rl, P.loL(b), P.hiL(b), cl);
+		P.table(rr, P.loR(b), P.hiR(b), cr);
+		double dist[9];
+		uint8_t dk[9];
+		for(int j = 2; j <= 8; ++j) {
+			dist[j] = inf;
+			dk[j]	= 1;
+			for(int k = 1; k < j && k <= 7; ++k) {
+				if(j - k > 7) continue;
+				const double c = cl[k] + cr[j - k];
+				if(c < dist[j]) {
+					dist[j] = c;
+					dk[j]	= uint8_t(k);
+				}
+			}
+		}
+		const double area	   = halfArea(&box[size_t(b) * 6], &box[size_t(b) * 6 + 3]);
+		const double cInternal = area * kCostNode + dist[8];
+		const double cLeaf	   = P.prims[b] <= RB_WIDE_MAX_LEAF_TRIS ? area * P.prims[b] * kCostTri : inf;
+		double * C			   = &P.cost[size_t(b) * 8];
+		uint8_t * S			   = &P.split[size_t(b) * 8];
+		S[0]				   = dk[8];
+		P.asLeaf[b]			   = !(cInternal < cLeaf); // NaN areas (rejected later) fall on the leaf side harmlessly
+		C[1]				   = P.asLeaf[b] ? cLeaf : cInternal;
+		if(!(C[1] < inf)) {	   // more than three triangles and a NaN area: keep it a node
+			P.asLeaf[b] = 0;
+			C[1]		= cInternal;
+		}
+		for(int i = 2; i <= 7; ++i) {
+			if(dist[i] < C[i - 1]) {
+				C[i] = dist[i];
+				S[i] = dk[i];
+			} else {
+				C[i] = C[i - 1];
+				S[i] = 0;
+			}
+		}
+	}
+	return true;
+}
+
+void gatherTris(const Plan & P, int ref, WChild & c) {
+	if(isNone(ref)) return;
+	if(isLeaf(ref)) {
+		for(int k = 0; k < leafCount(ref) && c.ntris < RB_WIDE_MAX_LEAF_TRIS; ++k) c.tri[c.ntris++] = leafFirst(ref) + k;
+		return;
+	}
+	gatherTris(P, P.refR(ref), c); // right first: the reference's visiting order
+	gatherTris(P, P.refL(ref), c);
+}
+
+// Appends to `list` the children that cover `ref` with at most i slots, in visiting order.
+void collect(const Plan & P, int ref, const float * lo, const float * hi, int i, std::vector<WChild> & list) {
+	if(isNone(ref)) return;
+	WChild c;
+	c.node	= -1;
+	c.ntris = 0;
+	std::memcpy(c.lo, lo, 12);
+	std::memcpy(c.hi, hi, 12);
+	if(isLeaf(ref)) {
+		gatherTris(P, ref, c);
+		list.push_back(c);
+		return;
+	}
+	while(i > 1 && P.split[size_t(ref) * 8 + i] == 0) --i;
+	if(i == 1) {
+		if(P.asLeaf[ref]) gatherTris(P, ref, c);
+		else c.node = ref;
+		list.push_back(c);
+		return;
+	}
+	const int k = P.split[size_t(ref) * 8 + i];
+	collect(P, P.refR(ref), P.loR(ref), P.hiR(ref), i - k, list);
+	collect(P, P.refL(ref), P.loL(ref), P.hiL(ref), k, list);
+}
+
 struct WorkItem {
-	int wide;	// index of the wide node to fill
-	int ref;	// binary reference it stands for (interior node, or a leaf code for a mesh that is a single leaf)
+	int wide;  // index of the wide node to fill
+	int ref;   // binary reference it stands for (an interior node, or a leaf for a mesh that is a single leaf)
 	int depth;
-	float lo[3], hi[3]; // box of that reference (only used for the single-leaf case)
+	float lo[3], hi[3];
 };
 
 } // namespace
 
 bool rb_wide_collapse(const RbFlatBvh & flat, size_t nroots, RbWideBvh & out, std::string * why) {
-	const float * bn = flat.nodes.data();
 	const size_t nTris = flat.tris.size() / 12;
+	for(int code : flat.leafCode) {
+		if((code & (RB_LEAF_MAX_TRIS - 1)) + 1 > RB_WIDE_MAX_LEAF_TRIS) {
+			if(why) *why = "leaves of more than three triangles are not supported by the wide layout";
+			return false;
+		}
+	}
+	Plan P;
+	if(!makePlan(flat, nroots, P, why)) return false;
 	out.nodes.clear();
 	out.tris.clear();
 	out.tris.reserve(flat.tris.size());
@@ -69,7 +228,7 @@ bool rb_wide_collapse(const RbFlatBvh & flat, size_t nroots, RbWideBvh & out, st
 	for(size_t r = 0; r < nroots; ++r) {
 		const float * d = flat.roots.data() + r * 8;
 		const int ref	= refOf(d[3]);
-		if(ref == RB_REF_NONE) continue;
+		if(isNone(ref)) continue;
 		WorkItem w;
 		w.wide	= int(out.nodes.size() / RB_WIDE_NODE_WORDS);
 		w.ref	= ref;
@@ -84,36 +243,17 @@ bool rb_wide_collapse(const RbFlatBvh & flat, size_t nroots, RbWideBvh & out, st
 		const WorkItem item = work.back();
 		work.pop_back();
 		if(item.depth > out.depth) out.depth = item.depth;
-		// The up-to-eight descendants this node adopts, in visiting order.
 		list.clear();
-		if(item.ref < 0) {
-			WChild c;
-			c.ref = item.ref;
-			std::memcpy(c.lo, item.lo, sizeof(c.lo));
-			std::memcpy(c.hi, item.hi, sizeof(c.hi));
-			list.push_back(c);
+		if(isLeaf(item.ref)) {
+			collect(P, item.ref, item.lo, item.hi, 1, list);
 		} else {
-			WChild two[2];
-			const int n = childrenOf(bn, item.ref, two);
-			list.assign(two, two + n);
-			for(;;) {
-				if(list.size() >= 8) break;
-				int pick = -1;
-				double best = -1.0;
-				for(size_t i = 0; i < list.size(); ++i) {
-					if(list[i].ref < 0) continue;
-					const double area = halfArea(list[i]);
-					if(!(area <= best)) { // NaN areas are picked too: they are rejected below
-						best = area;
-						pick = int(i);
-					}
-				}
-				if(pick < 0) break;
-				WChild two2[2];
-				const int m = childrenOf(bn, list[pick].ref, two2);
-				list.erase(list.begin() + pick);
-				list.insert(list.begin() + pick, two2, two2 + m);
-			}
+			const int b = item.ref, k = P.split[size_t(b) * 8];
+			collect(P, P.refR(b), P.loR(b), P.hiR(b), 8 - k, list);
+			collect(P, P.refL(b), P.loL(b), P.hiL(b), k, list);
+		}
+		if(list.size() > 8) {
+			if(why) *why = "internal error: a wide node with more than eight children";
+			return false;
 		}
 		uint32_t * node = out.nodes.data() + size_t(item.wide) * RB_WIDE_NODE_WORDS;
 		uint8_t q[6][8];
@@ -151,8 +291,7 @@ bool rb_wide_collapse(const RbFlatBvh & flat, size_t nroots, RbWideBvh & out, st
 				// the origin: the quantum has to grow until it does).
 				if(std::isfinite(p) && (lo - double(p)) / s >= 2.0 * RB_WIDE_MARGIN && (hi - double(p)) / s + RB_WIDE_MARGIN <= 255.0) break;
 			}
-			float pf = p;
-			std::memcpy(&node[a], &pf, 4);
+			std::memcpy(&node[a], &p, 4);
 			expo |= uint32_t(e + 127) << (8 * a);
 			for(size_t i = 0; i < list.size(); ++i) {
 				const double l = std::floor((double(list[i].lo[a]) - double(p)) / s - RB_WIDE_MARGIN);
@@ -171,36 +310,34 @@ bool rb_wide_collapse(const RbFlatBvh & flat, size_t nroots, RbWideBvh & out, st
 		}
 		node[3] = expo | (uint32_t(list.size()) << 24);
 		// Children: interior ones get consecutive nodes, leaves consecutive triangles, both in slot order.
-		const int childBase = int(out.nodes.size() / RB_WIDE_NODE_WORDS);
+		const int childBase	 = int(out.nodes.size() / RB_WIDE_NODE_WORDS);
 		const size_t triBase = out.tris.size() / 12;
-		uint8_t meta[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+		uint8_t meta[8]		 = {0, 0, 0, 0, 0, 0, 0, 0};
 		int nInterior = 0, triOffset = 0;
 		for(size_t i = 0; i < list.size(); ++i) {
-			if(list[i].ref >= 0) {
+			if(list[i].node >= 0) {
 				meta[i] = uint8_t(0x20 | (24 + nInterior));
 				++nInterior;
-			} else {
-				const int code	= ~list[i].ref;
-				const int first = code >> RB_LEAF_BITS;
-				const int count = (code & (RB_LEAF_MAX_TRIS - 1)) + 1;
-				if(count > RB_WIDE_MAX_LEAF_TRIS) {
-					if(why) *why = "leaves of more than three triangles are not supported by the wide layout";
-					return false;
-				}
-				if(size_t(first) + size_t(count) > nTris) {
+				continue;
+			}
+			const int count = list[i].ntris;
+			if(count < 1 || count > RB_WIDE_MAX_LEAF_TRIS) {
+				if(why) *why = "internal error: leaf child without triangles";
+				return false;
+			}
+			meta[i] = uint8_t((((1u << count) - 1u) << 5) | uint32_t(triOffset));
+			for(int k = 0; k < count; ++k) {
+				if(size_t(list[i].tri[k]) >= nTris) {
 					if(why) *why = "leaf triangle range out of bounds";
 					return false;
 				}
-				meta[i] = uint8_t((((1u << count) - 1u) << 5) | uint32_t(triOffset));
-				for(int k = 0; k < count; ++k) {
-					const float * src = flat.tris.data() + size_t(first + k) * 12;
-					const size_t at	  = out.tris.size();
-					out.tris.insert(out.tris.end(), src, src + 12);
-					const int32_t hier = int32_t(first + k);
-					std::memcpy(&out.tris[at + 11], &hier, 4);
-				}
-				triOffset += count;
+				const float * src = flat.tris.data() + size_t(list[i].tri[k]) * 12;
+				const size_t at	  = out.tris.size();
+				out.tris.insert(out.tris.end(), src, src + 12);
+				const int32_t hier = int32_t(list[i].tri[k]);
+				std::memcpy(&out.tris[at + 11], &hier, 4);
 			}
+			triOffset += count;
 		}
 		if(triBase + size_t(triOffset) >= (size_t(1) << 31)) {
 			if(why) *why = "too many triangles for 32-bit references";
@@ -214,10 +351,10 @@ bool rb_wide_collapse(const RbFlatBvh & flat, size_t nroots, RbWideBvh & out, st
 		for(int plane = 0; plane < 6; ++plane) std::memcpy(&node[8 + 2 * plane], q[plane], 8);
 		int k = 0;
 		for(size_t i = 0; i < list.size(); ++i) {
-			if(list[i].ref < 0) continue;
+			if(list[i].node < 0) continue;
 			WorkItem w;
 			w.wide	= childBase + k++;
-			w.ref	= list[i].ref;
+			w.ref	= list[i].node;
 			w.depth = item.depth + 1;
 			std::memcpy(w.lo, list[i].lo, sizeof(w.lo));
 			std::memcpy(w.hi, list[i].hi, sizeof(w.hi));

@@ -1,8 +1,6 @@
 """Eight-wide quantised hierarchy (RB_TRACE_WIDE, rendu_b200/csrc/rb_wide.*): the host collapse is checked on the CPU —
 structure, outward rounding of every stored box, and the numpy restatement of the kernel's traversal (tests/wide_model.py)
 against the oracle; on the GPU the kernel is compared with the exact mode record for record."""
-import os
-
 import numpy as np
 import pytest
 
@@ -102,7 +100,6 @@ def test_wide_needs_the_host_built_tree():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("RB_TEST_WIDE") != "1", reason="the wide kernel was written after this round's GPU budget was spent: first device run is RB_TEST_WIDE=1 next round")
 def test_wide_kernel_equals_exact_mode():
     """The kernel against the exact mode on the device: random, coherent and the golden edge rays (NaN / inf / axis-parallel
     directions take the binary tree inside the wide kernel), closest and any hit; then a rebuild discards the wide copy."""
@@ -128,4 +125,6 @@ def test_wide_kernel_equals_exact_mode():
     with pytest.raises(rb.RenduError):
         r.intersects(org[:4], dirs[:4])  # the wide copy went with the rebuild
     r.set_trace_mode(rb.TRACE_EXACT)
-    assert r.intersects(org[:64], dirs[:64]).tobytes() == exact[:64].tobytes()
+    again = r.intersects(org[:64], dirs[:64])  # the rebuilt tree numbers its triangles differently (internalId): compare the hit itself
+    for f in ("hit", "dist", "u", "v", "localId", "meshId"):
+        assert np.array_equal(again[f], exact[:64][f]), f
