@@ -66,8 +66,11 @@ def test_collapse_structure_and_outward_rounding(case):
         assert (dlo[:, used] <= lo[node, used].T - 0.03 * q).all() and (dhi[:, used] >= hi[node, used].T + 0.03 * q).all()
 
 
-def test_model_traversal_returns_the_oracle_hits():
-    c = load_case("raycast_multimesh")
+@pytest.mark.parametrize("case", ["raycast_multimesh", "raycast_degenerate"])
+def test_model_traversal_returns_the_reference_hits(case):
+    """The numpy restatement of the kernel against the hits the reference itself returned (tests/golden): overlapping
+    meshes with exact-distance ties, and degenerate / flat / empty geometry."""
+    c = load_case(case)
     meshes = list(case_meshes(c))
     _, T = wm.build(meshes)
     regular = np.isfinite(c["org"]).all(1) & np.isfinite(c["dirs"]).all(1) & (np.abs(c["dirs"]) > 1e-12).all(1)
