@@ -938,6 +938,7 @@ extern "C" rb_status rb_raycaster_wide_build(rb_raycaster * rc, uint64_t out[4])
 	rc->devWide.tris	   = rc->d_wideTris;
 	rc->devWide.rootNode   = rc->d_wideRoots;
 	rc->devWide.stackDepth = w.depth + 1;
+	rc->devWide.oneBits	   = 0x3f800000u;
 	rc->wideOnDevice	   = true;
 	return RB_OK;
 }

@@ -34,6 +34,12 @@ RB_D unsigned long long rb_pack2(float a, float b) {
 RB_D void rb_unpack2(unsigned long long v, float & a, float & b) {
 	asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
 }
+// a * b + c on two fp32 lanes at once, each lane one fused multiply-add (round to nearest even) like the scalar FFMA.
+RB_D unsigned long long rb_fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+	unsigned long long d;
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+	return d;
+}
 // (a - b) * c on two fp32 lanes at once; each lane rounds exactly like the scalar sub.rn / mul.rn pair (no fusion).
 RB_D unsigned long long rb_submul2(unsigned long long a, unsigned long long b, unsigned long long c) {
 	unsigned long long d, r;

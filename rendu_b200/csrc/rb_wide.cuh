@@ -65,8 +65,10 @@ RB_D void rb_wide_pop(RbWideTraversal & T, const RbStack & st) {
 	T.top = a;
 }
 
-// 1 + q * 2^-15 for byte `k` of word `w` (k is a compile-time constant: one PRMT).
-#define RB_WIDE_F(w, k) __uint_as_float(__byte_perm((w), 0x3f800000u, 0x7604u | ((k) << 4)))
+// 1 + q * 2^-15 for byte `k` of word `w` (k is a compile-time constant: one PRMT). `one` is 0x3f800000 read from the
+// kernel arguments: PRMT takes one immediate, and if the compiler knows the constant it makes THAT the immediate and
+// spends a MOV on every selector (48 per node).
+#define RB_WIDE_F(w, k) __uint_as_float(__byte_perm((w), one, 0x7604u | ((k) << 4)))
 
 // Four 3-bit fields sitting in the low bits of the four bytes of c, packed into 12 contiguous bits.
 RB_D unsigned int rb_wide_pack3(unsigned int c) {
@@ -95,25 +97,30 @@ RB_D void rb_wide_enter(RbWideTraversal & T, const RbDeviceWide & wide, const Rb
 	const unsigned int nearY0 = ny ? n4.x : n2.z, nearY1 = ny ? n4.y : n2.w, farY0 = ny ? n2.z : n4.x, farY1 = ny ? n2.w : n4.y;
 	const unsigned int nearZ0 = nz ? n4.z : n3.x, nearZ1 = nz ? n4.w : n3.y, farZ0 = nz ? n3.x : n4.z, farZ1 = nz ? n3.y : n4.w;
 	unsigned int hit = 0u;
-#define RB_WIDE_CHILD(W, k, s)                                                                                              \
+	const unsigned int one = wide.oneBits;
+	// Two children at a time: the six plane distances of each are three two-wide FMAs (fma.rn.f32x2, sm_100) per pair
+	// of planes — each half rounds exactly like the scalar FFMA.
+	const unsigned long long Ax2 = rb_pack2(Ax, Ax), Ay2 = rb_pack2(Ay, Ay), Az2 = rb_pack2(Az, Az);
+	const unsigned long long Bx2 = rb_pack2(Bx, Bx), By2 = rb_pack2(By, By), Bz2 = rb_pack2(Bz, Bz);
+#define RB_WIDE_PAIR(W, k, s)                                                                                               \
 	{                                                                                                                       \
-		const float tnx = __fmaf_rn(RB_WIDE_F(nearX##W, k), Ax, Bx), tny = __fmaf_rn(RB_WIDE_F(nearY##W, k), Ay, By);       \
-		const float tnz = __fmaf_rn(RB_WIDE_F(nearZ##W, k), Az, Bz);                                                        \
-		const float tfx = __fmaf_rn(RB_WIDE_F(farX##W, k), Ax, Bx), tfy = __fmaf_rn(RB_WIDE_F(farY##W, k), Ay, By);         \
-		const float tfz = __fmaf_rn(RB_WIDE_F(farZ##W, k), Az, Bz);                                                         \
-		const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, T.mini));                                                        \
-		const float tf = fminf(fminf(tfx, tfy), fminf(tfz, T.maxi));                                                        \
-		if(tn <= tf) hit |= 7u << (3 * (s));                                                                                \
+		float tnx0, tnx1, tny0, tny1, tnz0, tnz1, tfx0, tfx1, tfy0, tfy1, tfz0, tfz1;                                       \
+		rb_unpack2(rb_fma2(rb_pack2(RB_WIDE_F(nearX##W, k), RB_WIDE_F(nearX##W, k + 1)), Ax2, Bx2), tnx0, tnx1);            \
+		rb_unpack2(rb_fma2(rb_pack2(RB_WIDE_F(nearY##W, k), RB_WIDE_F(nearY##W, k + 1)), Ay2, By2), tny0, tny1);            \
+		rb_unpack2(rb_fma2(rb_pack2(RB_WIDE_F(nearZ##W, k), RB_WIDE_F(nearZ##W, k + 1)), Az2, Bz2), tnz0, tnz1);            \
+		rb_unpack2(rb_fma2(rb_pack2(RB_WIDE_F(farX##W, k), RB_WIDE_F(farX##W, k + 1)), Ax2, Bx2), tfx0, tfx1);              \
+		rb_unpack2(rb_fma2(rb_pack2(RB_WIDE_F(farY##W, k), RB_WIDE_F(farY##W, k + 1)), Ay2, By2), tfy0, tfy1);              \
+		rb_unpack2(rb_fma2(rb_pack2(RB_WIDE_F(farZ##W, k), RB_WIDE_F(farZ##W, k + 1)), Az2, Bz2), tfz0, tfz1);              \
+		const float tn0 = fmaxf(fmaxf(tnx0, tny0), fmaxf(tnz0, T.mini)), tf0 = fminf(fminf(tfx0, tfy0), fminf(tfz0, T.maxi)); \
+		const float tn1 = fmaxf(fmaxf(tnx1, tny1), fmaxf(tnz1, T.mini)), tf1 = fminf(fminf(tfx1, tfy1), fminf(tfz1, T.maxi)); \
+		if(tn0 <= tf0) hit |= 7u << (3 * (s));                                                                              \
+		if(tn1 <= tf1) hit |= 7u << (3 * (s) + 3);                                                                          \
 	}
-	RB_WIDE_CHILD(0, 0, 0)
-	RB_WIDE_CHILD(0, 1, 1)
-	RB_WIDE_CHILD(0, 2, 2)
-	RB_WIDE_CHILD(0, 3, 3)
-	RB_WIDE_CHILD(1, 0, 4)
-	RB_WIDE_CHILD(1, 1, 5)
-	RB_WIDE_CHILD(1, 2, 6)
-	RB_WIDE_CHILD(1, 3, 7)
-#undef RB_WIDE_CHILD
+	RB_WIDE_PAIR(0, 0, 0)
+	RB_WIDE_PAIR(0, 2, 2)
+	RB_WIDE_PAIR(1, 0, 4)
+	RB_WIDE_PAIR(1, 2, 6)
+#undef RB_WIDE_PAIR
 	// The items each slot really has: the unary counts (top three bits of every meta byte) packed three bits per slot.
 	const unsigned int cLo = (n1.z >> 5) & 0x07070707u, cHi = (n1.w >> 5) & 0x07070707u;
 	T.pending = hit & (rb_wide_pack3(cLo) | (rb_wide_pack3(cHi) << 12));
@@ -124,7 +131,7 @@ RB_D void rb_wide_enter(RbWideTraversal & T, const RbDeviceWide & wide, const Rb
 // rays that can produce NaNs in the slab test through the binary tree, whose box test reproduces them).
 template<bool ANY>
 RB_D bool rb_wide_step(RbWideTraversal & T, const RbDeviceBvh & bvh, const RbDeviceWide & wide, const RbRay & ray, const RbStack & st) {
-	int enter = -1; // node to enter in this step (one call site of rb_wide_enter: it is 200 instructions)
+	int enter = -1; // node to enter in this step (one call site of rb_wide_enter: it is 180 instructions)
 	if(T.pending == 0u) {
 		if(T.top != st.base) {
 			rb_wide_pop(T, st);

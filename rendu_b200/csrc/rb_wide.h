@@ -48,4 +48,5 @@ struct RbDeviceWide {
 	const float4 * tris; // 3 per triangle
 	const int * rootNode;
 	int stackDepth; // stack entries a traversal needs
+	unsigned int oneBits; // 0x3f800000, handed in as DATA so that it sits in a register (see RB_WIDE_F in rb_wide.cuh)
 };
