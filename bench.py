@@ -731,6 +731,8 @@ def run_explore(args):
     variants.append(("ring_v4_t28_s3", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "28", "RB_LEAF_VOTES": "4", "RB_NODE_STEPS": "3", "RB_DUAL": "0", "RB_RING": "1"}, rb.TRACE_EXACT))
     for thr in (12, 20, 28):  # eight-wide quantised tree (rb_wide.h): plain persistent scheduler, refill threshold as named
         variants.append(("wide_t%d" % thr, {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": str(thr), "RB_DUAL": "0"}, rb.TRACE_WIDE))
+    for votes, thr in ((6, 12), (12, 12), (6, 20), (16, 20)):  # the same tree under the phase-voting scheduler (node entries against triangle tests)
+        variants.append(("wide_phased_v%d_t%d" % (votes, thr), {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": str(thr), "RB_LEAF_VOTES": str(votes), "RB_DUAL": "0", "RB_WIDE_PHASED": "1"}, rb.TRACE_WIDE))
     variants.append(("dual_v24_r16", {"RB_PERSISTENT": "1", "RB_DUAL": "1", "RB_LEAF_VOTES": "24", "RB_DUAL_REFILL": "16"}, rb.TRACE_EXACT))
     variants.append(("ordered_phased_v8_t20_s2", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "20", "RB_LEAF_VOTES": "8", "RB_NODE_STEPS": "2", "RB_DUAL": "0"}, rb.TRACE_ORDERED))
     variants.append(("ordered_phased_v6_t12_s6", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "12", "RB_LEAF_VOTES": "6", "RB_NODE_STEPS": "6", "RB_DUAL": "0"}, rb.TRACE_ORDERED))
@@ -743,6 +745,7 @@ def run_explore(args):
     for name, env, mode in variants:
         os.environ.update(env)
         os.environ["RB_RING"] = env.get("RB_RING", "0")
+        os.environ["RB_WIDE_PHASED"] = env.get("RB_WIDE_PHASED", "0")
         rc = rb.Raycaster()
         rc.addMesh(pos, idx)
         rc.updateHierarchy()

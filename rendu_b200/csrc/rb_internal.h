@@ -128,6 +128,7 @@ struct rb_raycaster {
 	int nodeSteps	   = 6;	   // phase-voting scheduler: node steps per vote
 	bool dual		   = false; // two rays per lane (rb_k_trace_dual)
 	bool ring		   = false; // prepared-ray ring per warp (rb_k_trace_ring, experiment)
+	bool widePhased	   = false; // RB_TRACE_WIDE under the phase-voting scheduler (rb_k_trace_wide_phased, experiment)
 	int dualRefill	   = 16;   // dual: refill once this many of a warp's 64 slots are free
 	int fetchThreshold = 12;   // refill a warp from the queue when fewer lanes than this are still traversing
 	mutable std::atomic<uint64_t> launches{0};

@@ -475,6 +475,81 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_wide(RbDeviceBvh bv
 	}
 }
 
+// The wide traversal under the phase-voting scheduler of rb_k_trace_phased (RB_WIDE_PHASED=1; not yet run on a device):
+// a triangle phase runs once `leafVotes` lanes wait for one (or no lane has a node to enter), otherwise one node phase.
+template<bool ANY>
+__global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_wide_phased(RbDeviceBvh bvh, const float * __restrict__ org, const float * __restrict__ dir, float mini, float maxi, unsigned int n, void * __restrict__ out, unsigned int * __restrict__ cursor, int threshold, int leafVotes, RbDeviceWide wide) {
+	extern __shared__ int s_stack[];
+	const RbStack st = rb_make_stack(s_stack + threadIdx.x, blockDim.x);
+	const unsigned int lane = threadIdx.x & 31u;
+	bool active = false, exhausted = false;
+	unsigned int rayIdx = 0;
+	RbRay ray;
+	RbWideTraversal T;
+	for(;;) {
+		if(!exhausted) {
+			const unsigned int idle = __ballot_sync(0xffffffffu, !active);
+			if(idle) {
+				const int nIdle	 = __popc(idle);
+				const int leader = __ffs(idle) - 1;
+				unsigned int base = 0;
+				if((int)lane == leader) base = atomicAdd(cursor, (unsigned int)nIdle);
+				base = __shfl_sync(0xffffffffu, base, leader);
+				if(!active) {
+					const unsigned int idx = base + __popc(idle & ((1u << lane) - 1u));
+					if(idx < n) {
+						V3 o, d;
+						rb_load_ray(org, dir, idx, o, d);
+						ray = rb_make_ray(o, d);
+						if(rb_wide_ray_ok(ray)) {
+							rb_wide_init(T, bvh, mini, maxi, st);
+							rayIdx = idx;
+							active = true;
+						} else {
+							RbTraversal B;
+							rb_traversal_init(B, bvh, mini, maxi, st);
+							if(ANY) {
+								while(!rb_step_ordered<true, false, false>(B, bvh, ray, st, nullptr)) {
+								}
+							} else {
+								while(!rb_step_exact<false, false, false>(B, bvh, ray, st, nullptr)) {
+								}
+							}
+							if(ANY) rb_store_any(static_cast<uint8_t *>(out), idx, bvh, B.best);
+							else rb_store_hit(static_cast<rb_hit *>(out), idx, bvh, B.best);
+						}
+					}
+				}
+				exhausted = (base + (unsigned int)nIdle) >= n;
+			}
+		}
+		unsigned int activeM = __ballot_sync(0xffffffffu, active);
+		if(activeM == 0u) {
+			if(exhausted) break;
+			continue;
+		}
+		bool more;
+		do {
+			const bool wantsTri		 = active && rb_wide_wants_triangle(T);
+			const unsigned int triM	 = __ballot_sync(0xffffffffu, wantsTri);
+			const unsigned int nodeM = activeM & ~triM;
+			bool finished = false;
+			if(__popc(triM) >= leafVotes || nodeM == 0u) {
+				if(wantsTri) finished = rb_wide_phase_triangle<ANY>(T, wide, ray, st);
+			} else if(active && !wantsTri) {
+				finished = rb_wide_phase_node(T, bvh, wide, ray, st);
+			}
+			if(finished) {
+				if(ANY) rb_store_any(static_cast<uint8_t *>(out), rayIdx, bvh, T.best);
+				else rb_store_hit(static_cast<rb_hit *>(out), rayIdx, bvh, T.best);
+				active = false;
+			}
+			activeM = __ballot_sync(0xffffffffu, active);
+			more	= exhausted ? (activeM != 0u) : (__popc(activeM) >= threshold);
+		} while(more);
+	}
+}
+
 // Two rays per lane. The profile of the kernels above (profiles/) shows why a warp is slow: in the node loop only ~11
 // of 32 lanes are busy — the others have reached a leaf and wait for the slowest descent. Here every lane owns two
 // independent rays, A and B, each with its own registers and stack column; one iteration runs the node phase for the A
@@ -694,6 +769,7 @@ extern "C" rb_status rb_raycaster_create(rb_raycaster ** out) {
 	if(const char * e = getenv("RB_NODE_STEPS")) (*out)->nodeSteps = atoi(e);
 	if(const char * e = getenv("RB_DUAL")) (*out)->dual = atoi(e) != 0;
 	if(const char * e = getenv("RB_RING")) (*out)->ring = atoi(e) != 0;
+	if(const char * e = getenv("RB_WIDE_PHASED")) (*out)->widePhased = atoi(e) != 0;
 	if(const char * e = getenv("RB_DUAL_REFILL")) (*out)->dualRefill = atoi(e);
 	return RB_OK;
 }
@@ -1012,6 +1088,7 @@ static rb_status rb_launch_trace(const rb_raycaster * rc, const float * d_origin
 		if(!rc->wideOnDevice) return rb_fail(RB_ERR_INVALID, "RB_TRACE_WIDE: the wide tree is gone (the hierarchy was rebuilt or re-fitted): call rb_raycaster_wide_build again");
 		const int entries	  = 5 * rc->devWide.stackDepth > rc->dev.stackDepth ? 5 * rc->devWide.stackDepth : (rc->dev.stackDepth > 0 ? rc->dev.stackDepth : 1);
 		const size_t wideSmem = size_t(entries) * RB_TRACE_BLOCK * sizeof(int);
+		if(rc->widePhased) return rb_launch_persistent<ANY>(rc, rb_k_trace_wide_phased<ANY>, wideSmem, 1, d_origins, d_directions, mini, maxi, nrays, d_out, s, rc->fetchThreshold, rc->leafVotes > 0 ? rc->leafVotes : 6, rc->devWide);
 		return rb_launch_persistent<ANY>(rc, rb_k_trace_wide<ANY>, wideSmem, 1, d_origins, d_directions, mini, maxi, nrays, d_out, s, rc->fetchThreshold, rc->devWide);
 	}
 	if(rc->persistent && rc->dual) {

@@ -175,3 +175,69 @@ RB_D bool rb_wide_step(RbWideTraversal & T, const RbDeviceBvh & bvh, const RbDev
 	rb_wide_enter(T, wide, ray, enter);
 	return false;
 }
+
+// ---------------------------------------------------------------------------------------------- phase-split steps
+// The same traversal cut into its two kinds of work (as rb_phase_node / rb_phase_leaf do for the binary tree), so that a
+// warp can vote which kind to run: entering a node is ≈180 instructions, a triangle test ≈80, and a warp that mixes them
+// pays for both in every iteration. Between steps a ray's pending list is kept non-empty whenever its stack is not
+// (the pop is taken eagerly), so "what does this lane want next" is a look at the lowest pending bit.
+RB_D void rb_wide_settle(RbWideTraversal & T, const RbStack & st) {
+	if(T.pending == 0u && T.top != st.base) rb_wide_pop(T, st);
+}
+
+// True when the next item of the ray is a triangle (false: an interior child, or the next root).
+RB_D bool rb_wide_wants_triangle(const RbWideTraversal & T) {
+	if(T.pending == 0u) return false;
+	const unsigned int bit	= __ffs(T.pending) - 1;
+	const unsigned int slot = (bit * 11u) >> 5;
+	return (__byte_perm(T.metaLo, T.metaHi, slot) & 31u) < 24u;
+}
+
+// Node phase: enter the next interior child, or — with nothing pending — the next root. Returns true when the ray has
+// finished (no root left).
+RB_D bool rb_wide_phase_node(RbWideTraversal & T, const RbDeviceBvh & bvh, const RbDeviceWide & wide, const RbRay & ray, const RbStack & st) {
+	int enter;
+	if(T.pending == 0u) {
+		RbTraversal R;
+		R.mini = T.mini;
+		R.root = T.root;
+		const int ref = rb_next_root<true, false, false>(R, bvh, ray, T.maxi0, nullptr);
+		T.root		  = R.root;
+		if(ref == RB_REF_NONE) return true;
+		enter = __ldg(wide.rootNode + T.root);
+	} else {
+		const unsigned int bit = __ffs(T.pending) - 1;
+		T.pending &= T.pending - 1u;
+		const unsigned int slot = (bit * 11u) >> 5;
+		enter = int(T.childBase + (__byte_perm(T.metaLo, T.metaHi, slot) & 31u) - 24u);
+		if(T.pending != 0u) rb_wide_push(T, st);
+	}
+	rb_wide_enter(T, wide, ray, enter);
+	rb_wide_settle(T, st);
+	return false;
+}
+
+// Leaf phase: one triangle. Returns true when an ANY query has found its hit.
+template<bool ANY>
+RB_D bool rb_wide_phase_triangle(RbWideTraversal & T, const RbDeviceWide & wide, const RbRay & ray, const RbStack & st) {
+	const unsigned int bit = __ffs(T.pending) - 1;
+	T.pending &= T.pending - 1u;
+	const unsigned int slot = (bit * 11u) >> 5;
+	const unsigned int low	= __byte_perm(T.metaLo, T.metaHi, slot) & 31u;
+	const int tri			= int(T.triBase + low + (bit - 3u * slot));
+	const float4 * tp		= wide.tris + 3 * (size_t)tri;
+	const float4 t0 = rb_ldg4(tp), t1 = rb_ldg4(tp + 1), t2 = rb_ldg4(tp + 2);
+	float t, u, v;
+	if(rb_tri_test(ray, V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, T.mini, T.maxi, t, u, v)) {
+		if(ANY) {
+			T.best.t = t; T.best.u = u; T.best.v = v; T.best.tri = __float_as_int(t2.w);
+			return true;
+		}
+		if(t < T.best.t) {
+			T.best.t = t; T.best.u = u; T.best.v = v; T.best.tri = __float_as_int(t2.w);
+			T.maxi = t;
+		}
+	}
+	rb_wide_settle(T, st);
+	return false;
+}
