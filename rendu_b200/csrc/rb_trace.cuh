@@ -26,6 +26,7 @@ struct RbRay {
 	bool regular; // every component of pos and inv is finite: min/max can never see a NaN
 };
 
+#ifndef RB_HOST_CHECK
 RB_D unsigned long long rb_pack2(float a, float b) {
 	unsigned long long r;
 	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
@@ -47,8 +48,17 @@ RB_D unsigned long long rb_submul2(unsigned long long a, unsigned long long b, u
 	asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(d), "l"(c));
 	return r;
 }
+// Shared-memory word at a 32-bit shared-window address (the traversal stacks).
+RB_D void rb_sts(unsigned int address, unsigned int value) {
+	asm volatile("st.shared.b32 [%0], %1;" ::"r"(address), "r"(value) : "memory");
+}
+RB_D unsigned int rb_lds(unsigned int address) {
+	unsigned int value;
+	asm volatile("ld.shared.b32 %0, [%1];" : "=r"(value) : "r"(address) : "memory");
+	return value;
+}
+#endif // RB_HOST_CHECK: tests/host_check/ compiles this header with g++ and supplies these six primitives itself
 
-// Ray::Ray (Intersection.cpp:3-5): dir = normalize(d), invdir = 1.0f / normalize(d).
 RB_D RbRay rb_make_ray(V3 origin, V3 direction) {
 	RbRay r;
 	r.pos = origin;
@@ -158,14 +168,12 @@ RB_D RbStack rb_make_stack(int * sharedColumn, int strideEntries) {
 	return s;
 }
 RB_D void rb_push(RbTraversal & T, const RbStack & st, int v) {
-	asm volatile("st.shared.b32 [%0], %1;" ::"r"(T.top), "r"(v) : "memory");
+	rb_sts(T.top, (unsigned int)v);
 	T.top += st.strideBytes;
 }
 RB_D int rb_pop(RbTraversal & T, const RbStack & st) {
-	int v;
 	T.top -= st.strideBytes;
-	asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(T.top) : "memory");
-	return v;
+	return (int)rb_lds(T.top);
 }
 RB_D bool rb_stack_empty(const RbTraversal & T, const RbStack & st) { return T.top == st.base; }
 RB_D unsigned int rb_stack_size(const RbTraversal & T, const RbStack & st) { return (T.top - st.base) / (unsigned int)st.strideBytes; }

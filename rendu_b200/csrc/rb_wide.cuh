@@ -40,28 +40,28 @@ RB_D void rb_wide_init(RbWideTraversal & T, const RbDeviceBvh & bvh, float mini,
 // Stack entries are five words; word w of entry e of a thread lives at base + (5 e + w) * strideBytes.
 RB_D void rb_wide_push(RbWideTraversal & T, const RbStack & st) {
 	unsigned int a = T.top;
-	asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(T.childBase) : "memory");
+	rb_sts(a, T.childBase);
 	a += st.strideBytes;
-	asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(T.triBase) : "memory");
+	rb_sts(a, T.triBase);
 	a += st.strideBytes;
-	asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(T.metaLo) : "memory");
+	rb_sts(a, T.metaLo);
 	a += st.strideBytes;
-	asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(T.metaHi) : "memory");
+	rb_sts(a, T.metaHi);
 	a += st.strideBytes;
-	asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(T.pending) : "memory");
+	rb_sts(a, T.pending);
 	T.top = a + st.strideBytes;
 }
 RB_D void rb_wide_pop(RbWideTraversal & T, const RbStack & st) {
 	unsigned int a = T.top - st.strideBytes;
-	asm volatile("ld.shared.b32 %0, [%1];" : "=r"(T.pending) : "r"(a) : "memory");
+	T.pending = rb_lds(a);
 	a -= st.strideBytes;
-	asm volatile("ld.shared.b32 %0, [%1];" : "=r"(T.metaHi) : "r"(a) : "memory");
+	T.metaHi = rb_lds(a);
 	a -= st.strideBytes;
-	asm volatile("ld.shared.b32 %0, [%1];" : "=r"(T.metaLo) : "r"(a) : "memory");
+	T.metaLo = rb_lds(a);
 	a -= st.strideBytes;
-	asm volatile("ld.shared.b32 %0, [%1];" : "=r"(T.triBase) : "r"(a) : "memory");
+	T.triBase = rb_lds(a);
 	a -= st.strideBytes;
-	asm volatile("ld.shared.b32 %0, [%1];" : "=r"(T.childBase) : "r"(a) : "memory");
+	T.childBase = rb_lds(a);
 	T.top = a;
 }
 

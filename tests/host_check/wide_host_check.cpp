@@ -1,0 +1,52 @@
+// wide_host_check.cpp — TEST INFRASTRUCTURE: rb_wide.cuh (the eight-wide traversal the GPU kernels inline) compiled by g++
+// and stepped one ray at a time on the CPU. tests/test_wide.py compares what it returns with the reference's golden hits.
+// Build: g++ -O1 -std=c++17 -ffp-contract=off -shared -fPIC -I/usr/local/cuda/include wide_host_check.cpp
+#include "cuda_shim.h"
+
+#include "../../rendu_b200/csrc/rb_wide.cuh"
+
+// roots: 8 floats per root as the library lays them out (min xyz, reference, max xyz, 0). mode 0: rb_wide_step (what
+// rb_k_trace_wide runs); mode 1: rb_wide_phase_node / rb_wide_phase_triangle in the order one lane of
+// rb_k_trace_wide_phased would run them. Outputs per ray: triangle in hierarchy order (-1: miss), t, u, v.
+// Returns the number of rays that could not take the wide tree (irregular rays: the kernels walk the binary tree for them).
+extern "C" int rb_hc_wide_trace(const float * roots, int nroots, const uint32_t * wideNodes, const float * wideTris, const int * wideRoots, int wideDepth, const float * org, const float * dir, int nrays, float mini, float maxi, int anyHit, int mode, int * outTri, float * outTuv) {
+	RbDeviceBvh bvh = {};
+	bvh.roots		= reinterpret_cast<const float4 *>(roots);
+	bvh.nroots		= nroots;
+	RbDeviceWide wide = {};
+	wide.nodes		  = reinterpret_cast<const uint4 *>(wideNodes);
+	wide.tris		  = reinterpret_cast<const float4 *>(wideTris);
+	wide.rootNode	  = wideRoots;
+	wide.stackDepth	  = wideDepth + 1;
+	wide.oneBits	  = 0x3f800000u;
+	if(size_t(5 * wide.stackDepth) * 4 > sizeof(rb_hc_shared)) return -1;
+	const RbStack st = rb_make_stack(reinterpret_cast<int *>(rb_hc_shared), 1);
+	int skipped = 0;
+	for(int i = 0; i < nrays; ++i) {
+		const RbRay ray = rb_make_ray(V3{org[3 * i], org[3 * i + 1], org[3 * i + 2]}, V3{dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]});
+		outTri[i] = -2;
+		outTuv[3 * i] = outTuv[3 * i + 1] = outTuv[3 * i + 2] = 0.0f;
+		const float big = 1152921504606846976.0f; // rb_wide_ray_ok of rb_raycaster.cu
+		if(!(ray.regular && std::fabs(ray.inv.x) < big && std::fabs(ray.inv.y) < big && std::fabs(ray.inv.z) < big)) {
+			++skipped;
+			continue;
+		}
+		RbWideTraversal T;
+		rb_wide_init(T, bvh, mini, maxi, st);
+		bool done = false;
+		for(long guard = 0; !done && guard < 100000000; ++guard) {
+			if(mode == 0) {
+				done = anyHit ? rb_wide_step<true>(T, bvh, wide, ray, st) : rb_wide_step<false>(T, bvh, wide, ray, st);
+			} else if(rb_wide_wants_triangle(T)) {
+				done = anyHit ? rb_wide_phase_triangle<true>(T, wide, ray, st) : rb_wide_phase_triangle<false>(T, wide, ray, st);
+			} else {
+				done = rb_wide_phase_node(T, bvh, wide, ray, st);
+			}
+		}
+		outTri[i]		  = T.best.tri;
+		outTuv[3 * i]	  = T.best.t;
+		outTuv[3 * i + 1] = T.best.u;
+		outTuv[3 * i + 2] = T.best.v;
+	}
+	return skipped;
+}

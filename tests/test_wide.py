@@ -7,7 +7,7 @@ import pytest
 import rendu_b200 as rb
 import wide_model as wm
 from rendu_b200 import workloads as wl
-from util import case_meshes, load_case
+from util import ROOT, case_meshes, load_case
 
 
 def _true_boxes(T):
@@ -87,6 +87,58 @@ def test_model_traversal_returns_the_reference_hits(case):
         a = wm.trace(T, c["org"][k], c["dirs"][k], mini, maxi, any_hit=True)[0] >= 0
         assert a == bool(c["any"][k]), k
     assert hits > 100
+
+
+def _host_check():
+    """tests/host_check: rb_wide.cuh itself, compiled by g++ (the PTX primitives and intrinsics shimmed), as a ctypes library."""
+    import ctypes as C
+    import os
+    import subprocess
+    here = os.path.join(ROOT, "tests", "host_check")
+    out = os.path.join(here, "libwide_host_check.so")
+    deps = [os.path.join(here, f) for f in ("wide_host_check.cpp", "cuda_shim.h")] + [os.path.join(ROOT, "rendu_b200", "csrc", f) for f in ("rb_wide.cuh", "rb_wide.h", "rb_trace.cuh", "rb_math.cuh", "rb_types.h")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-I/usr/local/cuda/include", deps[0], "-o", out])
+    L = C.CDLL(out)
+    L.rb_hc_wide_trace.restype = C.c_int
+    L.rb_hc_wide_trace.argtypes = [C.c_void_p] + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int, C.c_float, C.c_float, C.c_int, C.c_int] + [C.c_void_p] * 2
+    return L
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("case", ["raycast_multimesh", "raycast_degenerate", "raycast_grid37"])
+def test_device_source_stepped_on_the_host_returns_the_reference_hits(case, mode):
+    """The kernels' own traversal source (rb_wide_step; rb_wide_phase_node / _triangle as the phase-voting kernel orders them)
+    on every regular ray of the golden cases, closest and any hit, against what the reference returned."""
+    from rendu_b200._capi import ptr
+    L = _host_check()
+    c = load_case(case)
+    r, T = wm.build(list(case_meshes(c)))
+    nm = len(T.roots)
+    roots = np.zeros((nm, 8), np.float32)
+    for m in range(nm):
+        if T.roots[m] < 0:
+            roots[m] = [1, 1, 1, 0, -1, -1, -1, 0]  # empty mesh: the inverted box the library stores
+        else:
+            roots[m, 0:3], roots[m, 4:7] = T.root_boxes[m]
+    org, dirs = np.ascontiguousarray(c["org"], np.float32), np.ascontiguousarray(c["dirs"], np.float32)
+    n = org.shape[0]
+    nodes, tris, wroots = np.ascontiguousarray(T.nodes), np.ascontiguousarray(T.tris), np.ascontiguousarray(T.roots)
+    local = np.ascontiguousarray(tris[:, 3]).view(np.int32)[np.argsort(T.hier)]  # localId by hierarchy index
+    for any_hit in (0, 1):
+        tri, tuv = np.zeros(n, np.int32), np.zeros((n, 3), np.float32)
+        skipped = L.rb_hc_wide_trace(ptr(roots), nm, ptr(nodes), ptr(tris), ptr(wroots), r._wide_sizes["depth"], ptr(org), ptr(dirs), n, float(c["mini"]), float(c["maxi"]), any_hit, mode, ptr(tri), ptr(tuv))
+        took = tri != -2
+        assert skipped == int((~took).sum()) and took.sum() > 0.9 * n
+        if any_hit:
+            assert np.array_equal(tri[took] >= 0, c["any"][took].astype(bool))
+            continue
+        assert np.array_equal(tri[took] >= 0, c["hit"][took].astype(bool))
+        h = took & (tri >= 0)
+        assert h.sum() > 100
+        for k, name in enumerate(("dist", "u", "v")):
+            assert np.array_equal(tuv[h, k].view(np.uint32), c[name][h].view(np.uint32)), name
+        assert np.array_equal(local[tri[h]], c["local_id"][h].astype(np.int32))
 
 
 def test_wide_needs_the_host_built_tree():
