@@ -479,7 +479,9 @@ def run_pathtrace(args):
     d_img = torch.zeros((PT_H, PT_W, 3), dtype=torch.float32, device=dev)
     h_img = torch.zeros((PT_H, PT_W, 3), dtype=torch.float32).pin_memory()
 
-    tmode = 1 if args.trace_mode == "ordered" else 0
+    tmode = {"exact": 0, "ordered": 1, "wide": 2}[args.trace_mode]
+    if tmode == 2:  # experiment: closest-hit wavefront on the eight-wide quantised tree (shadow rays keep the binary one)
+        scene.raycaster().build_wide()
 
     def opts_for(n_spp):
         if world > 1 and args.split == "tile":
@@ -807,7 +809,7 @@ def main():
     ap.add_argument("--max-paths", type=int, default=0, help="pathtrace: paths in flight per wavefront batch (0 = library default)")
     ap.add_argument("--split", default="tile", choices=["tile", "sample"])
     ap.add_argument("--small", action="store_true", help="pathtrace: 8k-triangle floor instead of 1M (quick checks)")
-    ap.add_argument("--trace-mode", default="exact", choices=["exact", "ordered"], help="pathtrace: traversal order of the wavefront kernels")
+    ap.add_argument("--trace-mode", default="exact", choices=["exact", "ordered", "wide"], help="pathtrace: traversal order of the wavefront kernels")
     args = ap.parse_args()
     _claim_stdout()
     if args.explore:

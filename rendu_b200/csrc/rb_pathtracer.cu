@@ -12,6 +12,7 @@
 // become exactly zero is dropped instead of being traced further (everything it could still add is multiplied by 0).
 #include "rb_scene.h"
 #include "rb_trace.cuh"
+#include "rb_wide.cuh"
 
 #include <cmath>
 #include <cstring>
@@ -170,6 +171,77 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_trace(RbDeviceBvh bvh, Rb
 					finished = rb_phase_node<false, ORDERED, BLOCKS>(T, bvh, ray, st, nullptr);
 					if(finished || rb_wants_leaf(T)) break;
 				}
+			}
+			if(finished) {
+				pb.hit[slot] = make_float4(T.best.t, T.best.u, T.best.v, __int_as_float(T.best.tri));
+				active = false;
+			}
+			activeM = __ballot_sync(0xffffffffu, active);
+			more	= exhausted ? (activeM != 0u) : (__popc(activeM) >= threshold);
+		} while(more);
+	}
+}
+
+// The closest-hit wavefront on the eight-wide quantised tree (rb_render_opts.trace_mode = RB_TRACE_WIDE; experiment, see
+// rb_wide.h): the queue handling of rb_k_pt_trace around the phase-split wide steps. Path rays are regular except for
+// exact axis-parallel directions; those walk the binary tree on the spot, as in rb_k_trace_wide.
+__global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_trace_wide(RbDeviceBvh bvh, RbDeviceWide wide, RbPathBuffers pb, const uint32_t * __restrict__ queue, uint32_t did, int threshold, int leafVotes, unsigned long long * __restrict__ stats) {
+	extern __shared__ int s_stack[];
+	const RbStack st		= rb_make_stack(s_stack + threadIdx.x, blockDim.x);
+	const unsigned int lane = threadIdx.x & 31u;
+	const unsigned int n	= pb.counters[rb_cnt_queue(did)];
+	unsigned int * cursor	= pb.counters + rb_cnt_cursor_t(did);
+	if(blockIdx.x == 0 && threadIdx.x == 0 && stats) atomicAdd(stats + 0, (unsigned long long)n);
+	bool active = false, exhausted = false;
+	unsigned int slot = 0;
+	RbRay ray;
+	RbWideTraversal T;
+	for(;;) {
+		if(!exhausted) {
+			const unsigned int idle = __ballot_sync(0xffffffffu, !active);
+			if(idle) {
+				const int nIdle	 = __popc(idle);
+				const int leader = __ffs(idle) - 1;
+				unsigned int base = 0;
+				if((int)lane == leader) base = atomicAdd(cursor, (unsigned int)nIdle);
+				base = __shfl_sync(0xffffffffu, base, leader);
+				if(!active) {
+					const unsigned int idx = base + __popc(idle & ((1u << lane) - 1u));
+					if(idx < n) {
+						slot = queue[idx];
+						const float4 o = pb.rayO[slot], d = pb.rayD[slot];
+						ray = rb_make_ray(V3{o.x, o.y, o.z}, V3{d.x, d.y, d.z});
+						const float big = 1152921504606846976.0f; // 2^60, as rb_wide_ray_ok
+						if(ray.regular && fabsf(ray.inv.x) < big && fabsf(ray.inv.y) < big && fabsf(ray.inv.z) < big) {
+							rb_wide_init(T, bvh, 0.0001f, 1e8f, st);
+							active = true;
+						} else {
+							RbTraversal B;
+							rb_traversal_init(B, bvh, 0.0001f, 1e8f, st);
+							while(!rb_step_exact<false, false, false>(B, bvh, ray, st, nullptr)) {
+							}
+							pb.hit[slot] = make_float4(B.best.t, B.best.u, B.best.v, __int_as_float(B.best.tri));
+						}
+					}
+				}
+				exhausted = (base + (unsigned int)nIdle) >= n;
+			}
+		}
+		unsigned int activeM = __ballot_sync(0xffffffffu, active);
+		if(activeM == 0u) {
+			if(exhausted) break;
+			continue;
+		}
+		bool more;
+		do {
+			const bool wantsTri		 = active && rb_wide_wants_triangle(T);
+			const unsigned int triM	 = __ballot_sync(0xffffffffu, wantsTri);
+			const unsigned int nodeM = activeM & ~triM;
+			bool finished = false;
+			if(__popc(triM) >= leafVotes || nodeM == 0u) {
+				if(wantsTri) finished = rb_wide_phase_triangle<false>(T, wide, ray, st);
+			} else if(active && !wantsTri) {
+				finished = rb_wide_phase_node(T, bvh, wide, ray, st);
 			}
 			if(finished) {
 				pb.hit[slot] = make_float4(T.best.t, T.best.u, T.best.v, __int_as_float(T.best.tri));
@@ -651,6 +723,8 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 	}
 	rb_raycaster * rc	 = sc->raycaster;
 	const bool ordered	 = opts ? (opts->trace_mode == RB_TRACE_ORDERED) : false;
+	const bool wideTrace = opts && opts->trace_mode == RB_TRACE_WIDE; // closest-hit wavefront on the eight-wide tree (shadow rays keep the binary one)
+	if(wideTrace && !rc->wideOnDevice) return rb_fail(RB_ERR_INVALID, "rb_pathtracer_render: trace_mode RB_TRACE_WIDE needs rb_raycaster_wide_build on the scene's raycaster first");
 	// Wavefront queues are shorter and more varied than the raycaster's batches: a slightly earlier refill and fewer
 	// node steps per vote measured best (tools/pt_sweep.sh); RB_FETCH_THRESHOLD / RB_NODE_STEPS override both.
 	const int threshold = std::getenv("RB_FETCH_THRESHOLD") ? rc->fetchThreshold : 16;
@@ -687,6 +761,13 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 		}
 
 		const size_t smem = rb_trace_smem_bytes(rc, RB_PT_BLOCK);
+		const int wideEntries = wideTrace ? std::max(5 * rc->devWide.stackDepth, rc->dev.stackDepth > 0 ? rc->dev.stackDepth : 1) : 0;
+		const size_t smemWide = size_t(wideEntries) * RB_PT_BLOCK * sizeof(int);
+		unsigned gridTraceWide = 0;
+		if(wideTrace) {
+			st = rb_pt_grid(rb_k_pt_trace_wide, smemWide, pt->sms, gridTraceWide);
+			if(st) return st;
+		}
 		// Grid-stride kernels are launched as exactly one wave of resident CTAs: with 8 CTAs per SM requested and 6
 		// resident (shade: 80 registers) a third of the CTAs would run alone in a second round.
 		unsigned gridTrace = 0, gridShadow = 0, gridShade = 0, gridFlat = unsigned(pt->sms * 8);
@@ -730,7 +811,8 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 				const cudaStream_t ss = (uint64_t(b.npixels) * b.schunk >= (uint64_t(1) << 20)) ? pt->side[l] : ls;
 				bool shadowPending	  = false;
 				for(uint32_t did = 0; did < depth; ++did) {
-					kTrace<<<gridTrace, RB_PT_BLOCK, smem, ls>>>(rc->dev, pb, pb.queue[did & 1u], did, threshold, votes, steps, pt->d_stats);
+					if(wideTrace) rb_k_pt_trace_wide<<<gridTraceWide, RB_PT_BLOCK, smemWide, ls>>>(rc->dev, rc->devWide, pb, pb.queue[did & 1u], did, threshold, votes > 32 ? 6 : votes, pt->d_stats);
+					else kTrace<<<gridTrace, RB_PT_BLOCK, smem, ls>>>(rc->dev, pb, pb.queue[did & 1u], did, threshold, votes, steps, pt->d_stats);
 					if(shadowPending) RB_CUDA(cudaStreamWaitEvent(ls, pt->shadowed[l], 0)); // shade overwrites the shadow entries
 					rb_k_pt_shade<<<gridShade, RB_PT_BLOCK, 0, ls>>>(f, b, pb, sc->dev, did, pt->d_stats);
 					launches += 2;
