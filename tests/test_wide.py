@@ -91,6 +91,38 @@ def test_model_traversal_returns_the_reference_hits(case):
     assert hits > 100
 
 
+def test_soup_far_from_the_origin_keeps_margins_and_hits():
+    """Tiny and huge triangles around (4000, 4000, 4000): fp32 spacing there is 2.4e-4, coarser than the quanta of small
+    nodes — the builder has to grow their scale until the outward margin survives; hits must stay the oracle's."""
+    from oracle import oracle as orc
+    rng = np.random.default_rng(7)
+    n = 3000
+    c = rng.uniform(-1, 1, (n, 3)).astype(np.float32) * np.float32(5.0) + np.float32(4000.0)
+    e1, e2 = rng.normal(0, 0.05, (n, 3)).astype(np.float32), rng.normal(0, 0.05, (n, 3)).astype(np.float32)
+    e1[:20] *= 40
+    e2[:20] *= 40
+    pos = np.stack([c, c + e1, c + e2], 1).reshape(-1, 3).astype(np.float32)
+    idx = np.arange(3 * n, dtype=np.uint32)
+    o = orc.OracleRaycaster()
+    o.add_mesh(pos, idx)
+    o.build()
+    _, T = wm.build([(pos, idx)])
+    lo, hi = _true_boxes(T)
+    for node in range(T.nodes.shape[0]):
+        dlo, dhi = T.child_boxes(node)
+        q = np.ldexp(1.0, T.e[node])[:, None]
+        used = T.meta[node] != 0
+        assert (dlo[:, used] <= lo[node, used].T - 0.03 * q).all() and (dhi[:, used] >= hi[node, used].T + 0.03 * q).all()
+    org = (rng.uniform(-1, 1, (600, 3)) * 12 + 4000).astype(np.float32)
+    dirs = ((rng.uniform(-1, 1, (600, 3)) * 5 + 4000).astype(np.float32) - org).astype(np.float32)
+    h = o.intersect(org, dirs, threads=4)
+    assert int(h["hit"].sum()) > 100
+    for k in range(org.shape[0]):
+        tri, t, _, _, _, _, _ = wm.trace(T, org[k], dirs[k])
+        assert (tri >= 0) == bool(h["hit"][k]), k
+        assert tri < 0 or (tri == int(h["internalId"][k]) and np.float32(t).view(np.uint32) == h["dist"][k].view(np.uint32)), k
+
+
 def _host_check():
     """tests/host_check: rb_wide.cuh itself, compiled by g++ (the PTX primitives and intrinsics shimmed), as a ctypes library."""
     import ctypes as C
