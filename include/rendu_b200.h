@@ -336,6 +336,29 @@ RB_API rb_status rb_output_ldr_device(const float * d_pixels, uint32_t width, ui
 RB_API rb_status rb_output_hdr(const float * pixels, uint32_t width, uint32_t height, uint32_t components, int ignore_alpha, int flip, uint16_t * planes);
 RB_API rb_status rb_output_hdr_device(const float * d_pixels, uint32_t width, uint32_t height, uint32_t components, int ignore_alpha, int flip, uint16_t * d_planes, void * stream);
 
+/* ------------------------------------------------------------------------------------------------ OBJ ingestion
+ * Host side of SURVEY §8f rank 2: what Mesh(std::istream &, Mesh::Load, name) (src/engine/resources/Mesh.cpp:100-266, the
+ * loader behind Resources::getMesh, ResourcesManager.cpp:306-340) makes of a Wavefront OBJ text — the same vertices in the
+ * same order, the same indices, the same floats — parsed on all host threads from memory. Only `v`, `vn`, `vt` and the
+ * first three corners of `f` lines count, `vt` is stored as (u, 1 - v), Indexed mode creates one vertex per distinct
+ * corner text in first-use order. Where the reference would throw or read out of bounds (a number that does not parse,
+ * an index outside the file's arrays, relative indices) this returns RB_ERR_INVALID. Tangent frames are not computed
+ * (the reference delegates them to MikkTSpace). No GPU involved; the result feeds rb_raycaster_add_mesh. */
+typedef struct rb_mesh rb_mesh;
+typedef enum rb_obj_mode { /* Mesh::Load (Mesh.hpp:19-23) */
+	RB_OBJ_EXPANDED = 0, /* one vertex per face corner */
+	RB_OBJ_POINTS	= 1, /* vertices as listed, no faces */
+	RB_OBJ_INDEXED	= 2	 /* vertices shared between corners with identical attribute indices (what getMesh uses) */
+} rb_obj_mode;
+RB_API rb_status rb_obj_parse(const char * text, size_t nbytes, rb_obj_mode mode, rb_mesh ** out);
+RB_API void rb_mesh_destroy(rb_mesh * mesh);
+/* out[0]=positions, out[1]=normals, out[2]=texcoords (each a count of vertices, 0 when the file has none), out[3]=indices. */
+RB_API rb_status rb_mesh_sizes(const rb_mesh * mesh, uint64_t out[4]);
+/* Copies the arrays out (any pointer may be NULL); bbox receives Mesh::computeBoundingBox (Mesh.cpp:306-324): min xyz, max xyz. */
+RB_API rb_status rb_mesh_read(const rb_mesh * mesh, float * positions, float * normals, float * texcoords, uint32_t * indices, float bbox[6]);
+/* Mesh::computeNormals (Mesh.cpp:326-352): replaces the normals by area-independent face-normal averages. */
+RB_API rb_status rb_mesh_compute_normals(rb_mesh * mesh);
+
 /* ------------------------------------------------------------------------------------------------ device KATs
  * Known-answer hooks: evaluate the device versions of the reference's scalar building blocks on arrays (host
  * pointers). Used only by the parity tests; they launch real kernels and have no CPU path. */

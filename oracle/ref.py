@@ -415,3 +415,26 @@ def output_hdr(image):
     if rc != 0:
         raise RuntimeError("reference Image::save/load (EXR) failed (%d)" % rc)
     return out
+
+
+class RefMesh:
+    """The reference's own OBJ loader (Mesh.cpp:100-266) on a text in memory, optionally followed by computeNormals."""
+
+    def __init__(self, text, mode=2, compute_normals=False):
+        data = text if isinstance(text, (bytes, bytearray)) else text.encode("utf-8")
+        L = lib()
+        L.ref_mesh_load.restype = C.c_void_p
+        L.ref_mesh_load.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int]
+        h = C.c_void_p(L.ref_mesh_load(bytes(data), len(data), int(mode), 1 if compute_normals else 0))
+        n = np.zeros(4, np.uint64)
+        L.ref_mesh_sizes.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_mesh_sizes(h, _p(n))
+        self.positions = np.zeros((int(n[0]), 3), np.float32)
+        self.normals = np.zeros((int(n[1]), 3), np.float32)
+        self.texcoords = np.zeros((int(n[2]), 2), np.float32)
+        self.indices = np.zeros(int(n[3]), np.uint32)
+        self.bbox = np.zeros(6, np.float32)
+        L.ref_mesh_read.argtypes = [C.c_void_p] * 6
+        L.ref_mesh_read(h, _p(self.positions), _p(self.normals), _p(self.texcoords), _p(self.indices), _p(self.bbox))
+        L.ref_mesh_free.argtypes = [C.c_void_p]
+        L.ref_mesh_free(h)

@@ -16,6 +16,7 @@
 #include "resources/ResourcesManager.hpp"
 #include "resources/Texture.hpp"
 #include "resources/Image.hpp"
+#include "resources/Mesh.hpp"
 #include "scene/Scene.hpp"
 #include "scene/Sky.hpp"
 #include "scene/lights/PointLight.hpp"
@@ -32,6 +33,7 @@
 #include <chrono>
 #include <cstring>
 #include <sched.h>
+#include <sstream>
 #include <thread>
 
 /* The reference declares this class a friend of Raycaster and Raycaster::Hit; the harness supplies its own
@@ -607,6 +609,38 @@ int ref_output_hdr(const float * pixels, uint32_t w, uint32_t h, uint32_t compon
 	if(back.pixels.size() != render.pixels.size()) return 3;
 	std::memcpy(out, back.pixels.data(), back.pixels.size() * sizeof(float));
 	return 0;
+}
+
+/* The reference's OBJ loader as Resources::getMesh drives it (ResourcesManager.cpp:316-328), on a text in memory:
+ * Mesh(std::istream &, Mesh::Load, name), optionally computeNormals(), then computeBoundingBox(). mode follows
+ * Mesh::Load's order (Expanded, Points, Indexed). */
+void * ref_mesh_load(const char * text, size_t nbytes, int mode, int computeNormals) {
+	std::stringstream in(std::string(text, nbytes));
+	Mesh * m = new Mesh(in, static_cast<Mesh::Load>(mode), "harness");
+	if(computeNormals) m->computeNormals();
+	m->computeBoundingBox();
+	return m;
+}
+void ref_mesh_sizes(void * h, uint64_t out[4]) {
+	const Mesh * m = static_cast<const Mesh *>(h);
+	out[0] = m->positions.size();
+	out[1] = m->normals.size();
+	out[2] = m->texcoords.size();
+	out[3] = m->indices.size();
+}
+void ref_mesh_read(void * h, float * positions, float * normals, float * texcoords, uint32_t * indices, float * bbox) {
+	const Mesh * m = static_cast<const Mesh *>(h);
+	if(!m->positions.empty()) std::memcpy(positions, m->positions.data(), m->positions.size() * sizeof(glm::vec3));
+	if(!m->normals.empty()) std::memcpy(normals, m->normals.data(), m->normals.size() * sizeof(glm::vec3));
+	if(!m->texcoords.empty()) std::memcpy(texcoords, m->texcoords.data(), m->texcoords.size() * sizeof(glm::vec2));
+	for(size_t i = 0; i < m->indices.size(); ++i) indices[i] = m->indices[i];
+	for(int k = 0; k < 3; ++k) {
+		bbox[k]		= m->bbox.minis[k];
+		bbox[3 + k] = m->bbox.maxis[k];
+	}
+}
+void ref_mesh_free(void * h) {
+	delete static_cast<Mesh *>(h);
 }
 
 uint64_t ref_ray_counter() {

@@ -86,6 +86,11 @@ def lib():
         "rb_raycaster_update_mesh": (C.c_int, [vp, u32, vp, sz, vp]),
         "rb_raycaster_set_trace_mode": (C.c_int, [vp, C.c_int]),
         "rb_raycaster_wide_build": (C.c_int, [vp, vp]),
+        "rb_obj_parse": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, vp]),
+        "rb_mesh_destroy": (None, [vp]),
+        "rb_mesh_sizes": (C.c_int, [vp, vp]),
+        "rb_mesh_read": (C.c_int, [vp, vp, vp, vp, vp, vp]),
+        "rb_mesh_compute_normals": (C.c_int, [vp]),
         "rb_raycaster_wide_download": (C.c_int, [vp, vp, vp, vp]),
         "rb_raycaster_build_times": (C.c_int, [vp, vp]),
         "rb_raycaster_intersect": (C.c_int, [vp, vp, vp, f32, f32, sz, vp]),
