@@ -407,7 +407,7 @@ def run_gpu(args):
                     "algorithmic_bytes_per_launch": work[dom]["bytes"], "avg_launch_ms": per_kernel_ms[dom],
                     "per_ray": {"interior_nodes": work[dom]["interior"] / n, "triangle_tests": work[dom]["tris"] / n,
                                 "bytes": work[dom]["bytes"] / n},
-                    "note": "the 82 MB tree is L2-resident, so bytes/s above is served mostly by L2, not HBM; see profiles/"}
+                    "note": "the 82 MB tree is L2-resident, so bytes/s above is served mostly by L2, not HBM; the kernel's limiter is the L1 data pipe (l1tex__data_pipe_lsu_wavefronts at 85-90 % of one per cycle, profiles/r01_l1_data_pipe.txt), then issue slots (54 %)"}
         per_launch = {w["name"]: {"ms": per_kernel_ms[k], "mrays_s": n / (per_kernel_ms[k] * 1e-3) / 1e6,
                                   "interior_per_ray": w["interior"] / n, "tri_tests_per_ray": w["tris"] / n,
                                   "gbs": w["bytes"] / (per_kernel_ms[k] * 1e-3) / 1e9} for k, w in enumerate(work)}

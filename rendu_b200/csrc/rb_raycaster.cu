@@ -5,6 +5,7 @@
 #include "rb_trace.cuh"
 #include "rb_wide.cuh"
 
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -988,11 +989,15 @@ extern "C" rb_status rb_raycaster_set_trace_mode(rb_raycaster * rc, rb_trace_mod
 extern "C" rb_status rb_raycaster_wide_build(rb_raycaster * rc, uint64_t out[4]) {
 	if(!rc) return rb_fail(RB_ERR_INVALID, "rb_raycaster_wide_build: null handle");
 	if(rc->buildMode != RB_BUILD_REFERENCE || rc->hostMirrorStale || rc->nodes.empty()) return rb_fail(RB_ERR_INVALID, "rb_raycaster_wide_build: needs the host-built (reference-order) hierarchy, not re-fitted since");
+	const bool timing = getenv("RB_BUILD_TIMING") != nullptr;
+	const auto t0	  = std::chrono::steady_clock::now();
 	RbFlatBvh flat;
 	std::string why;
 	if(!rb_host_flatten(rc, flat, &why)) return rb_fail(RB_ERR_INVALID, "rb_raycaster_wide_build: %s", why.c_str());
-	auto wide = std::make_unique<RbWideBvh>();
+	const auto t1 = std::chrono::steady_clock::now();
+	auto wide	  = std::make_unique<RbWideBvh>();
 	if(!rb_wide_collapse(flat, rc->meshCount, *wide, &why)) return rb_fail(RB_ERR_INVALID, "rb_raycaster_wide_build: %s", why.c_str());
+	if(timing) fprintf(stderr, "[rb_raycaster_wide_build] flatten %.1f ms, collapse %.1f ms\n", std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
 	rc->wide = std::move(wide);
 	if(out) {
 		out[0] = rc->wide->nodes.size() / RB_WIDE_NODE_WORDS;

@@ -10,8 +10,10 @@
 #include "rb_internal.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -218,7 +220,9 @@ bool rb_wide_collapse(const RbFlatBvh & flat, size_t nroots, RbWideBvh & out, st
 		}
 	}
 	Plan P;
+	const auto t0 = std::chrono::steady_clock::now();
 	if(!makePlan(flat, nroots, P, why)) return false;
+	if(std::getenv("RB_BUILD_TIMING")) fprintf(stderr, "[rb_wide_collapse] plan %.1f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
 	out.nodes.clear();
 	out.tris.clear();
 	out.tris.reserve(flat.tris.size());
