@@ -123,6 +123,22 @@ def test_soup_far_from_the_origin_keeps_margins_and_hits():
         assert tri < 0 or (tri == int(h["internalId"][k]) and np.float32(t).view(np.uint32) == h["dist"][k].view(np.uint32)), k
 
 
+def test_warp_model_of_the_wide_kernels_stays_above_perfect_packing():
+    pos, idx = wl.displaced_grid(24)
+    _, T = wm.build([(pos, idx)])
+    org, dirs = wl.coherent_rays(12)
+    seqs = []
+    for k in range(org.shape[0]):
+        st = []
+        _, _, _, _, nodes, tris, _ = wm.trace(T, org[k], dirs[k], steps=st)
+        assert st.count(0) == nodes and st.count(2) == tris
+        seqs.append(st)
+    ideal = sum(s.count(0) * wm.C_ENTER + s.count(2) * wm.C_TRI for s in seqs) / 32.0 / len(seqs)
+    for phased in (False, True):
+        cost, lanes = wm.simulate_warp(seqs, 12, phased)
+        assert cost > ideal and 1.0 <= lanes <= 32.0
+
+
 def _host_check():
     """tests/host_check: rb_wide.cuh itself, compiled by g++ (the PTX primitives and intrinsics shimmed), as a ctypes library."""
     import ctypes as C

@@ -110,7 +110,7 @@ def _byte_perm_low(lo, hi, slot):
     return ((lo | (hi << 32)) >> (8 * slot)) & 0xff
 
 
-def trace(T, o, d, mini=1e-4, maxi=1e8, any_hit=False):
+def trace(T, o, d, mini=1e-4, maxi=1e8, any_hit=False, steps=None):
     """rb_wide_step until the ray finishes. Returns (hierarchy triangle or -1, t, u, v, nodes entered, triangle tests,
     pops)."""
     o, d, inv = make_ray(np.asarray(o), np.asarray(d))
@@ -126,6 +126,8 @@ def trace(T, o, d, mini=1e-4, maxi=1e8, any_hit=False):
         cur = int(T.roots[r])
         pending = enter(T, cur, o, inv, mini, maxi)
         n_nodes += 1
+        if steps is not None:
+            steps.append(0)
         while True:
             if pending == 0:
                 if not stack:
@@ -144,9 +146,13 @@ def trace(T, o, d, mini=1e-4, maxi=1e8, any_hit=False):
                 cur = int(T.child_base[cur]) + low - 24
                 pending = enter(T, cur, o, inv, mini, maxi)
                 n_nodes += 1
+                if steps is not None:
+                    steps.append(0)
                 continue
             tri = int(T.tri_base[cur]) + low + (bit - 3 * slot)
             n_tris += 1
+            if steps is not None:
+                steps.append(2)
             h = tri_test(o, d, T.tris[tri], mini, maxi)
             if h is not None:
                 if any_hit:
@@ -155,6 +161,63 @@ def trace(T, o, d, mini=1e-4, maxi=1e8, any_hit=False):
                     best = (int(T.hier[tri]), h[0], h[1], h[2])
                     maxi = h[0]
     return best[0], best[1], best[2], best[3], n_nodes, n_tris, n_pops
+
+
+# warp-instruction costs read off the SASS of rb_k_trace_wide / rb_k_trace_wide_phased (cuobjdump -sass): entering a
+# node (with the pop / push around it), one triangle test, the vote of the phased kernel, loop control of the plain one
+C_ENTER, C_TRI, C_VOTE, C_LOOP = 200, 85, 30, 12
+
+
+def simulate_warp(rays, threshold, phased, votes=6, c_refill=150, c_finish=45):
+    """One persistent warp consuming `rays` (lists of 0 = node entry, 2 = triangle test) in order, as tests/sched_model.py
+    does for the binary kernels: every instruction block is charged once per execution, whatever the number of lanes in it.
+    Plain kernel: one rb_wide_step per lane and iteration, so an iteration costs a node entry if any lane enters a node plus
+    a triangle test if any lane tests one. Phased: one kind per iteration, chosen by vote. Returns warp-instructions per ray
+    and the mean number of lanes busy in node entries."""
+    nxt, n = 0, len(rays)
+    seq, pos = [None] * 32, np.zeros(32, np.int64)
+    live = np.zeros(32, bool)
+    cost, node_steps, node_lanes = 0.0, 0, 0
+    while True:
+        exhausted = nxt >= n
+        if not exhausted and (~live).any():
+            for l in np.flatnonzero(~live):
+                if nxt < n:
+                    seq[l], pos[l], live[l] = rays[nxt], 0, True
+                    nxt += 1
+            cost += c_refill
+            exhausted = nxt >= n
+        if not live.any():
+            break
+        while True:
+            kind = np.array([seq[l][pos[l]] if live[l] and pos[l] < len(seq[l]) else (1 if live[l] else -1) for l in range(32)])  # 1: out of items -> finishes in a node step
+            wants_tri, wants_node = kind == 2, (kind == 0) | (kind == 1)
+            if phased:
+                cost += C_VOTE
+                run_tri = wants_tri.sum() >= votes or not wants_node.any()
+                run_node = not run_tri
+            else:
+                cost += C_LOOP
+                run_tri, run_node = wants_tri.any(), wants_node.any()
+            finished = np.zeros(32, bool)
+            if run_tri:
+                cost += C_TRI
+                pos[wants_tri] += 1
+            if run_node:
+                enters = wants_node & (kind == 0)
+                if enters.any():
+                    cost += C_ENTER
+                    node_steps += 1
+                    node_lanes += int(enters.sum())
+                    pos[enters] += 1
+                finished = wants_node & (kind == 1)
+            if finished.any():
+                cost += c_finish
+                live &= ~finished
+            nlive = int(live.sum())
+            if not (nlive > 0 if exhausted else nlive >= threshold):
+                break
+    return cost / n, node_lanes / max(node_steps, 1)
 
 
 def build(pos_idx_list):
@@ -206,6 +269,20 @@ def main():
     n = org.shape[0]
     print("%d %s rays: %.2f wide nodes, %.2f triangle tests, %.2f pops per ray; %d differ from the oracle" % (n, args.set, nn / n, nt / n, npop / n, bad))
     print("L1 wavefronts per ray if every lane is alone on its lines: wide %.0f (5 per node, 3 per triangle) — binary tree 4 per node, 3 per triangle" % (5 * nn / n + 3 * nt / n))
+    seqs = []
+    for k in range(org.shape[0]):
+        st = []
+        trace(T, org[k], dirs[k], steps=st)
+        seqs.append(st)
+    print("warp-instructions per ray (tests/sched_model.py gives the binary kernels: default scheduler 279 incoherent at threshold 12)")
+    print("%-28s %s" % ("policy", "  ".join("T=%-2d" % t for t in (8, 12, 16, 20, 24, 28))))
+    for name, phased, votes in (("wide, plain persistent", False, 0), ("wide, phased v6", True, 6), ("wide, phased v12", True, 12), ("wide, phased v16", True, 16)):
+        row, occ = [], []
+        for t in (8, 12, 16, 20, 24, 28):
+            c, a = simulate_warp(seqs, t, phased, votes)
+            row.append("%4.0f" % c)
+            occ.append("%4.1f" % a)
+        print("%-28s %s   | lanes per node entry: %s" % (name, "  ".join(row), " ".join(occ)))
 
 
 if __name__ == "__main__":
