@@ -53,6 +53,12 @@ void Raycaster::updateHierarchy() {
 	Log::Info() << "[Raycaster] Building hierarchy for " << sz[1] << " triangles... " << std::flush;
 	if(!rbCheck(rb_raycaster_build(_device, rb_build_mode(defaultBuildMode())), "updateHierarchy")) return;
 	refreshMirror();
+	// Traversal mode (extension): RENDU_B200_TRACE=ordered | wide; default is the reference's own order and bits. The
+	// wide mode (experiment) collapses the tree just built into eight-wide quantised nodes first.
+	if(const char * mode = std::getenv("RENDU_B200_TRACE")) {
+		if(std::strcmp(mode, "ordered") == 0) rbCheck(rb_raycaster_set_trace_mode(_device, RB_TRACE_ORDERED), "trace mode");
+		else if(std::strcmp(mode, "wide") == 0 && rbCheck(rb_raycaster_wide_build(_device, nullptr), "wide hierarchy")) rbCheck(rb_raycaster_set_trace_mode(_device, RB_TRACE_WIDE), "trace mode");
+	}
 	Log::Info() << "Done: " << _hierarchy.size() << " nodes created." << std::endl;
 }
 
