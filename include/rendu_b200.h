@@ -99,7 +99,11 @@ typedef enum rb_build_mode {
 	RB_BUILD_REFERENCE = 0,
 	/* GPU LBVH: Morton codes on triangle-box centroids, radix sort, Karras hierarchy, bottom-up AABB fit.
 	 * One tree over all meshes. Same closest hits except exact-distance ties / box-edge grazing (documented). */
-	RB_BUILD_LBVH = 1
+	RB_BUILD_LBVH = 1,
+	/* Host build in the reference's framework (one root per mesh, same leaf rule, same node records) with the split of
+	 * every set chosen by the binned surface-area heuristic instead of the mean of the longest axis: a better tree for
+	 * traversal, not the reference's. Same closest hits except exact-distance ties / box-edge grazing. */
+	RB_BUILD_SAH = 2
 } rb_build_mode;
 
 typedef enum rb_trace_mode {

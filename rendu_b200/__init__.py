@@ -7,7 +7,7 @@ There is no CPU fallback anywhere in this package: every compute call goes throu
 ``RenduError`` if the library or a GPU is missing.
 """
 from ._capi import RenduError, lib, lib_path, device_count, HIT_DTYPE, NODE_DTYPE, TRI_DTYPE  # noqa: F401
-from .raycaster import Raycaster, BUILD_REFERENCE, BUILD_LBVH, TRACE_EXACT, TRACE_ORDERED, TRACE_WIDE  # noqa: F401
+from .raycaster import Raycaster, BUILD_REFERENCE, BUILD_LBVH, BUILD_SAH, TRACE_EXACT, TRACE_ORDERED, TRACE_WIDE  # noqa: F401
 
 __all__ = ["RenduError", "lib", "lib_path", "device_count", "Raycaster", "HIT_DTYPE", "NODE_DTYPE", "TRI_DTYPE",
-           "BUILD_REFERENCE", "BUILD_LBVH", "TRACE_EXACT", "TRACE_ORDERED", "TRACE_WIDE"]
+           "BUILD_REFERENCE", "BUILD_LBVH", "BUILD_SAH", "TRACE_EXACT", "TRACE_ORDERED", "TRACE_WIDE"]

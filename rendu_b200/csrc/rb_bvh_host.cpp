@@ -11,6 +11,7 @@
 #include "rb_internal.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 namespace {
@@ -28,6 +29,7 @@ struct BuildInput {
 	const RbTriVec * tris;
 	const float * centroid[3];
 	uint32_t * order;
+	bool sah = false; // RB_BUILD_SAH: binned surface-area splits instead of the reference's mean splits
 };
 
 // Processes ONE set as Raycaster.cpp:73-139 does: box, leaf test, axis, mean partition / median fallback. Fills `node`
@@ -81,6 +83,136 @@ size_t split_set(const BuildInput & in, size_t begin, size_t count, rb_node & no
 		split		   = size_t(mid - first);
 	}
 	if(split == 0 || split == count || count < 5) {
+		split = count / 2;
+		std::nth_element(first, first + split, last, [c](uint32_t a, uint32_t b) { return c[a] < c[b]; });
+	}
+	return split;
+}
+
+// RB_BUILD_SAH: the same step with the split chosen by the binned surface-area heuristic (16 bins per axis over the
+// centroid bounds, cost = area(left) * count(left) + area(right) * count(right)) instead of the reference's mean of the
+// longest axis. Same leaf rule (fewer than three triangles), same node format, same framework around it — only the tree
+// is a different one, so hits agree with the reference except on exact-distance ties and box-edge grazing, as for
+// RB_BUILD_LBVH. Falls back to the median of the longest axis where no plane separates the centroids.
+size_t split_set_sah(const BuildInput & in, size_t begin, size_t count, rb_node & node) {
+	const RbTriVec & tris = *in.tris;
+	uint32_t * first = in.order + begin;
+	uint32_t * last	 = first + count;
+	float lo[3] = {1.0f, 1.0f, 1.0f}, hi[3] = {-1.0f, -1.0f, -1.0f};
+	float clo[3] = {0, 0, 0}, chi[3] = {0, 0, 0};
+	for(size_t k = 0; k < count; ++k) {
+		const uint32_t t  = first[k];
+		const rb_tri & tr = tris[t];
+		for(int a = 0; a < 3; ++a) {
+			const float c = in.centroid[a][t];
+			if(k == 0) {
+				lo[a]  = tr.bmin[a];
+				hi[a]  = tr.bmax[a];
+				clo[a] = chi[a] = c;
+			} else {
+				lo[a]  = minf(lo[a], tr.bmin[a]);
+				hi[a]  = maxf(hi[a], tr.bmax[a]);
+				clo[a] = minf(clo[a], c);
+				chi[a] = maxf(chi[a], c);
+			}
+		}
+	}
+	std::memcpy(node.bmin, lo, sizeof(lo));
+	std::memcpy(node.bmax, hi, sizeof(hi));
+	if(count < 3) {
+		node.leaf  = 1;
+		node.left  = begin;
+		node.right = count;
+		return SIZE_MAX;
+	}
+	node.leaf = 0;
+	const int B = 16;
+	struct Bin {
+		float lo[3], hi[3];
+		size_t n;
+	};
+	auto halfArea = [](const float * l, const float * h) {
+		const float x = h[0] - l[0], y = h[1] - l[1], z = h[2] - l[2];
+		return x * y + y * z + z * x;
+	};
+	double bestCost = 0.0;
+	int bestAxis = -1, bestBin = 0;
+	float bestScale = 0.0f;
+	for(int axis = 0; axis < 3; ++axis) {
+		const float extent = chi[axis] - clo[axis];
+		if(!(extent > 0.0f)) continue;
+		const float scale = float(B) / extent;
+		if(!std::isfinite(scale)) continue;
+		Bin bins[B];
+		for(int b = 0; b < B; ++b) bins[b].n = 0;
+		const float * c = in.centroid[axis];
+		for(size_t k = 0; k < count; ++k) {
+			const uint32_t t = first[k];
+			int b			 = int((c[t] - clo[axis]) * scale);
+			b				 = b < 0 ? 0 : (b >= B ? B - 1 : b);
+			Bin & bin		 = bins[b];
+			const rb_tri & tr = tris[t];
+			if(bin.n++ == 0) {
+				std::memcpy(bin.lo, tr.bmin, 12);
+				std::memcpy(bin.hi, tr.bmax, 12);
+			} else {
+				for(int a = 0; a < 3; ++a) {
+					bin.lo[a] = minf(bin.lo[a], tr.bmin[a]);
+					bin.hi[a] = maxf(bin.hi[a], tr.bmax[a]);
+				}
+			}
+		}
+		// Suffix boxes, then a prefix sweep over the 15 planes.
+		float rlo[B][3], rhi[B][3];
+		size_t rn[B];
+		size_t acc = 0;
+		float alo[3] = {0, 0, 0}, ahi[3] = {0, 0, 0};
+		for(int b = B - 1; b >= 0; --b) {
+			if(bins[b].n) {
+				for(int a = 0; a < 3; ++a) {
+					alo[a] = acc ? minf(alo[a], bins[b].lo[a]) : bins[b].lo[a];
+					ahi[a] = acc ? maxf(ahi[a], bins[b].hi[a]) : bins[b].hi[a];
+				}
+				acc += bins[b].n;
+			}
+			std::memcpy(rlo[b], alo, 12);
+			std::memcpy(rhi[b], ahi, 12);
+			rn[b] = acc;
+		}
+		acc = 0;
+		for(int b = 0; b + 1 < B; ++b) {
+			if(bins[b].n) {
+				for(int a = 0; a < 3; ++a) {
+					alo[a] = acc ? minf(alo[a], bins[b].lo[a]) : bins[b].lo[a];
+					ahi[a] = acc ? maxf(ahi[a], bins[b].hi[a]) : bins[b].hi[a];
+				}
+				acc += bins[b].n;
+			}
+			if(acc == 0 || rn[b + 1] == 0) continue;
+			const double cost = double(halfArea(alo, ahi)) * double(acc) + double(halfArea(rlo[b + 1], rhi[b + 1])) * double(rn[b + 1]);
+			if(bestAxis < 0 || cost < bestCost) {
+				bestCost  = cost;
+				bestAxis  = axis;
+				bestBin	  = b;
+				bestScale = scale;
+			}
+		}
+	}
+	size_t split = 0;
+	if(bestAxis >= 0) {
+		const float * c	 = in.centroid[bestAxis];
+		const float base = clo[bestAxis];
+		uint32_t * mid	 = std::partition(first, last, [=](uint32_t t) {
+			  int b = int((c[t] - base) * bestScale);
+			  b		= b < 0 ? 0 : (b >= B ? B - 1 : b);
+			  return b <= bestBin;
+		  });
+		split = size_t(mid - first);
+	}
+	if(split == 0 || split == count) {
+		const float sx = hi[0] - lo[0], sy = hi[1] - lo[1], sz = hi[2] - lo[2];
+		const int axis = (sx >= sy && sx >= sz) ? 0 : (sy >= sz ? 1 : 2);
+		const float * c = in.centroid[axis];
 		split = count / 2;
 		std::nth_element(first, first + split, last, [c](uint32_t a, uint32_t b) { return c[a] < c[b]; });
 	}
@@ -222,7 +354,7 @@ void build_subtree(const BuildInput & in, size_t begin, size_t count, int depth,
 		const Pending cur = todo.back();
 		todo.pop_back();
 		rb_node node{};
-		const size_t split = split_set(in, cur.begin, cur.count, node);
+		const size_t split = in.sah ? split_set_sah(in, cur.begin, cur.count, node) : split_set(in, cur.begin, cur.count, node);
 		if(split != SIZE_MAX) {
 			out.maxDepth = std::max(out.maxDepth, cur.depth + 1);
 			node.left	 = out.nodes.size();
@@ -250,7 +382,7 @@ void rb_host_build_reference(rb_raycaster * rc) {
 			order[i] = uint32_t(i);
 		}
 	});
-	BuildInput in{&rc->tris, {centroid[0].data(), centroid[1].data(), centroid[2].data()}, order.data()};
+	BuildInput in{&rc->tris, {centroid[0].data(), centroid[1].data(), centroid[2].data()}, order.data(), rc->buildMode == RB_BUILD_SAH};
 
 	// The upper part of the tree is built here, in the reference's order; a set of at most `taskSize` triangles is not
 	// expanded but handed to a worker thread (disjoint triangle ranges, nothing shared). Since the reference's loop is
@@ -288,7 +420,7 @@ void rb_host_build_reference(rb_raycaster * rc) {
 			continue;
 		}
 		rb_node node{};
-		const size_t split = (cur.count >= (size_t(1) << 17)) ? split_set_parallel(in, cur.begin, cur.count, node) : split_set(in, cur.begin, cur.count, node);
+		const size_t split = in.sah ? split_set_sah(in, cur.begin, cur.count, node) : (cur.count >= (size_t(1) << 17)) ? split_set_parallel(in, cur.begin, cur.count, node) : split_set(in, cur.begin, cur.count, node);
 		if(split != SIZE_MAX) {
 			maxDepth = std::max(maxDepth, cur.depth + 1);
 			const long l = long(upper.size()), r = l + 1;

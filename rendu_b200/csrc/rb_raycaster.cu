@@ -892,7 +892,7 @@ extern "C" rb_status rb_raycaster_build(rb_raycaster * rc, rb_build_mode mode) {
 		});
 		rc->triBoxesStale = false;
 	}
-	if(mode == RB_BUILD_REFERENCE) {
+	if(mode == RB_BUILD_REFERENCE || mode == RB_BUILD_SAH) {
 		// The host mirror is built first so that it can be read back (rb_raycaster_download_bvh) even on a machine
 		// without a GPU; tracing still needs the device copy.
 		rb_host_build_reference(rc);
@@ -988,7 +988,7 @@ extern "C" rb_status rb_raycaster_set_trace_mode(rb_raycaster * rc, rb_trace_mod
 
 extern "C" rb_status rb_raycaster_wide_build(rb_raycaster * rc, uint64_t out[4]) {
 	if(!rc) return rb_fail(RB_ERR_INVALID, "rb_raycaster_wide_build: null handle");
-	if(rc->buildMode != RB_BUILD_REFERENCE || rc->hostMirrorStale || rc->nodes.empty()) return rb_fail(RB_ERR_INVALID, "rb_raycaster_wide_build: needs the host-built (reference-order) hierarchy, not re-fitted since");
+	if(rc->buildMode == RB_BUILD_LBVH || rc->hostMirrorStale || rc->nodes.empty()) return rb_fail(RB_ERR_INVALID, "rb_raycaster_wide_build: needs a host-built hierarchy (RB_BUILD_REFERENCE or RB_BUILD_SAH), not re-fitted since");
 	const bool timing = getenv("RB_BUILD_TIMING") != nullptr;
 	const auto t0	  = std::chrono::steady_clock::now();
 	RbFlatBvh flat;

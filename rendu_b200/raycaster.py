@@ -11,7 +11,7 @@ import numpy as np
 from . import _capi
 from ._capi import HIT_DTYPE, NODE_DTYPE, TRI_DTYPE, check, lib, ptr
 
-BUILD_REFERENCE, BUILD_LBVH = 0, 1
+BUILD_REFERENCE, BUILD_LBVH, BUILD_SAH = 0, 1, 2
 TRACE_EXACT, TRACE_ORDERED, TRACE_WIDE = 0, 1, 2
 
 
@@ -51,9 +51,9 @@ class Raycaster:
     def updateHierarchy(self, mode=BUILD_REFERENCE):
         check(lib().rb_raycaster_build(self._h, int(mode)))
 
-    def build_host_only(self):
-        """Run the reference-order host build; tolerate the missing GPU (used by CPU-side tests of the builder)."""
-        st = lib().rb_raycaster_build(self._h, BUILD_REFERENCE)
+    def build_host_only(self, mode=BUILD_REFERENCE):
+        """Run a host build (reference order, or BUILD_SAH); tolerate the missing GPU (used by CPU-side tests of the builder)."""
+        st = lib().rb_raycaster_build(self._h, int(mode))
         if st not in (_capi.RB_OK, _capi.RB_ERR_NO_DEVICE):
             check(st)
         return st

@@ -91,6 +91,44 @@ def test_model_traversal_returns_the_reference_hits(case):
     assert hits > 100
 
 
+def test_sah_host_build_is_a_valid_tree_with_the_same_hits():
+    """RB_BUILD_SAH: same framework and records as the reference-order build, other splits — every triangle once, boxes
+    that contain their subtrees, and (through the wide collapse and its model) the oracle's closest hits."""
+    from oracle import oracle as orc
+    rng = np.random.default_rng(3)
+    n = 4000
+    c = np.concatenate([rng.normal(0, 0.2, (n // 2, 3)), rng.uniform(-2, 2, (n // 2, 3))]).astype(np.float32)  # a dense clump in a sparse cloud
+    e1, e2 = rng.normal(0, 0.03, (n, 3)).astype(np.float32), rng.normal(0, 0.03, (n, 3)).astype(np.float32)
+    pos = np.stack([c, c + e1, c + e2], 1).reshape(-1, 3).astype(np.float32)
+    idx = np.arange(3 * n, dtype=np.uint32)
+    o = orc.OracleRaycaster()
+    o.add_mesh(pos, idx)
+    o.build()
+    r = rb.Raycaster()
+    r.addMesh(pos, idx)
+    r.build_host_only(rb.BUILD_SAH)
+    nodes, tris, _ = r.download_bvh()
+    assert sorted(tris["localId"].tolist()) == list(range(0, 3 * n, 3)) and r.sizes()["depth"] < 64
+    leaf = nodes["leaf"].astype(bool)
+    assert nodes["right"][leaf].max() <= 2 and nodes["right"][leaf].sum() == n
+    inner = np.flatnonzero(~leaf)
+    for child in ("left", "right"):
+        ch = nodes[child][inner].astype(np.int64)
+        assert (nodes["bmin"][ch] >= nodes["bmin"][inner]).all() and (nodes["bmax"][ch] <= nodes["bmax"][inner]).all()
+    r.build_wide()
+    wn, wt, wr = r.download_wide()
+    T = wm.WideTree(wn, wt, wr, [(nodes["bmin"][0].astype(np.float32), nodes["bmax"][0].astype(np.float32))])
+    local = tris["localId"].astype(np.int64)
+    org = rng.uniform(-3, 3, (400, 3)).astype(np.float32)
+    dirs = (rng.normal(0, 0.5, (400, 3)).astype(np.float32) - org).astype(np.float32)
+    h = o.intersect(org, dirs, threads=4)
+    assert int(h["hit"].sum()) > 50
+    for k in range(org.shape[0]):
+        tri, t, _, _, _, _, _ = wm.trace(T, org[k], dirs[k])
+        assert (tri >= 0) == bool(h["hit"][k]), k
+        assert tri < 0 or (local[tri] == int(h["localId"][k]) and np.float32(t).view(np.uint32) == h["dist"][k].view(np.uint32)), k
+
+
 def test_soup_far_from_the_origin_keeps_margins_and_hits():
     """Tiny and huge triangles around (4000, 4000, 4000): fp32 spacing there is 2.4e-4, coarser than the quanta of small
     nodes — the builder has to grow their scale until the outward margin survives; hits must stay the oracle's."""
