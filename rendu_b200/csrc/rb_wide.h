@@ -1,10 +1,11 @@
-// rb_wide.h — eight-wide hierarchy with quantised child boxes (RB_TRACE_WIDE, experiment prepared for the next round).
+// rb_wide.h — eight-wide hierarchy with quantised child boxes (RB_TRACE_WIDE; experiment: parity-checked, not yet timed).
 //
 // Why: the traversal of the binary tree is bound by the L1 data pipe — every divergent 16-byte load of a lane is one
 // wavefront, four per node visit, ≈130 per incoherent ray (profiles/r01_l1_data_pipe.txt). An eight-wide node with
 // 8-bit child boxes is 80 bytes (five loads) and replaces three to four binary visits.
 //
-// The wide tree is a COLLAPSE of the reference-order binary tree (Raycaster.cpp:58-142 as mirrored by rb_bvh_host.cpp),
+// The wide tree is a COLLAPSE of the host-built binary tree (the reference-order one, Raycaster.cpp:58-142 as mirrored by
+// rb_bvh_host.cpp, or its RB_BUILD_SAH sibling),
 // made on the host: a wide node adopts up to eight descendants of one binary node, listed in the order the reference's
 // stack loop would reach them (right child before left, Raycaster.cpp:160-173), and the traversal consumes the listed
 // children strictly in that order, leaves and interior children interleaved. Child boxes are stored relative to the
@@ -39,8 +40,9 @@ struct RbWideBvh {
 	int depth = 0;				 // wide nodes on the longest root-to-leaf path
 };
 
-// Collapses the flattened binary tree. Fails (with a reason) on leaves of more than RB_WIDE_MAX_LEAF_TRIS triangles
-// and on trees too large for the 24-bit node index of a stack entry.
+// Collapses the flattened binary tree (which descendants a node adopts: surface-area dynamic programme, rb_wide.cpp; a
+// leaf child may merge binary leaves of up to RB_WIDE_MAX_LEAF_TRIS triangles in total, listed in visiting order).
+// Fails (with a reason) on binary leaves of more than RB_WIDE_MAX_LEAF_TRIS triangles and on non-finite boxes.
 bool rb_wide_collapse(const RbFlatBvh & flat, size_t nroots, RbWideBvh & out, std::string * why);
 
 struct RbDeviceWide {
