@@ -733,6 +733,7 @@ def run_explore(args):
     variants.append(("ring_v4_t28_s3", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "28", "RB_LEAF_VOTES": "4", "RB_NODE_STEPS": "3", "RB_DUAL": "0", "RB_RING": "1"}, rb.TRACE_EXACT))
     for thr in (12, 20, 28):  # eight-wide quantised tree (rb_wide.h): plain persistent scheduler, refill threshold as named
         variants.append(("wide_t%d" % thr, {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": str(thr), "RB_DUAL": "0"}, rb.TRACE_WIDE))
+    variants.append(("wide_octant_t12", {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": "12", "RB_DUAL": "0", "RB_WIDE_OCTANT": "1"}, rb.TRACE_WIDE))  # closest hit front to back
     for votes, thr in ((6, 12), (12, 12), (6, 20), (16, 20)):  # the same tree under the phase-voting scheduler (node entries against triangle tests)
         variants.append(("wide_phased_v%d_t%d" % (votes, thr), {"RB_PERSISTENT": "1", "RB_FETCH_THRESHOLD": str(thr), "RB_LEAF_VOTES": str(votes), "RB_DUAL": "0", "RB_WIDE_PHASED": "1"}, rb.TRACE_WIDE))
     variants.append(("dual_v24_r16", {"RB_PERSISTENT": "1", "RB_DUAL": "1", "RB_LEAF_VOTES": "24", "RB_DUAL_REFILL": "16"}, rb.TRACE_EXACT))
@@ -748,6 +749,7 @@ def run_explore(args):
         os.environ.update(env)
         os.environ["RB_RING"] = env.get("RB_RING", "0")
         os.environ["RB_WIDE_PHASED"] = env.get("RB_WIDE_PHASED", "0")
+        os.environ["RB_WIDE_OCTANT"] = env.get("RB_WIDE_OCTANT", "0")
         rc = rb.Raycaster()
         rc.addMesh(pos, idx)
         rc.updateHierarchy()

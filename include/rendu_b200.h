@@ -172,6 +172,10 @@ RB_API rb_status rb_raycaster_wide_build(rb_raycaster * rc, uint64_t out[4]);
 /* Host copy of the wide hierarchy: nodes = out[0]*20 words, tris = out[1]*12 floats (word 11 = triangle index in hierarchy
  * order), root_nodes = out[2] ints (wide node of each mesh, -1 for an empty mesh). Any pointer may be NULL. */
 RB_API rb_status rb_raycaster_wide_download(const rb_raycaster * rc, uint32_t * nodes, float * tris, int32_t * root_nodes);
+/* The second copy of the wide nodes (out[0]*20 words), children placed in slots by direction for front-to-back visiting
+ * where the reference's order is not promised (environment RB_WIDE_OCTANT=1: closest-hit queries of RB_TRACE_WIDE; same hits
+ * except exact-distance ties). Same indices, offsets and boxes as the first copy. */
+RB_API rb_status rb_raycaster_wide_download_by_octant(const rb_raycaster * rc, uint32_t * nodes);
 
 /* Raycaster::intersects (Raycaster.cpp:144-185), batched: origins/directions are nrays*3 floats (directions need
  * not be normalised, Intersection.cpp:3-5). Reference defaults: mini = 1e-4f, maxi = 1e8f (Raycaster.hpp:65). */

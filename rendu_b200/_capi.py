@@ -92,6 +92,7 @@ def lib():
         "rb_mesh_read": (C.c_int, [vp, vp, vp, vp, vp, vp]),
         "rb_mesh_compute_normals": (C.c_int, [vp]),
         "rb_raycaster_wide_download": (C.c_int, [vp, vp, vp, vp]),
+        "rb_raycaster_wide_download_by_octant": (C.c_int, [vp, vp]),
         "rb_raycaster_build_times": (C.c_int, [vp, vp]),
         "rb_raycaster_intersect": (C.c_int, [vp, vp, vp, f32, f32, sz, vp]),
         "rb_raycaster_intersect_any": (C.c_int, [vp, vp, vp, f32, f32, sz, vp]),

@@ -110,6 +110,7 @@ struct rb_raycaster {
 	// Eight-wide quantised copy of the host-built tree (rb_wide.h; RB_TRACE_WIDE): host arrays and device copy.
 	std::unique_ptr<RbWideBvh> wide;
 	uint4 * d_wideNodes	 = nullptr;
+	uint4 * d_wideNodesOct = nullptr; // the same nodes, slots by direction (RbWideBvh::nodesByOctant)
 	float4 * d_wideTris	 = nullptr;
 	int * d_wideRoots	 = nullptr;
 	RbDeviceWide devWide = {};
@@ -128,6 +129,7 @@ struct rb_raycaster {
 	int nodeSteps	   = 6;	   // phase-voting scheduler: node steps per vote
 	bool dual		   = false; // two rays per lane (rb_k_trace_dual)
 	bool ring		   = false; // prepared-ray ring per warp (rb_k_trace_ring, experiment)
+	int wideOctant	   = 0;	   // RB_TRACE_WIDE: 1 = closest-hit queries visit slots by direction (front to back), 2 = any-hit queries too (experiment)
 	bool widePhased	   = false; // RB_TRACE_WIDE under the phase-voting scheduler (rb_k_trace_wide_phased, experiment)
 	int dualRefill	   = 16;   // dual: refill once this many of a warp's 64 slots are free
 	int fetchThreshold = 12;   // refill a warp from the queue when fewer lanes than this are still traversing

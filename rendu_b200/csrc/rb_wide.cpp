@@ -224,6 +224,7 @@ bool rb_wide_collapse(const RbFlatBvh & flat, size_t nroots, RbWideBvh & out, st
 	if(!makePlan(flat, nroots, P, why)) return false;
 	if(std::getenv("RB_BUILD_TIMING")) fprintf(stderr, "[rb_wide_collapse] plan %.1f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
 	out.nodes.clear();
+	out.nodesByOctant.clear();
 	out.tris.clear();
 	out.tris.reserve(flat.tris.size());
 	out.rootNode.assign(nroots, -1);
@@ -353,6 +354,51 @@ bool rb_wide_collapse(const RbFlatBvh & flat, size_t nroots, RbWideBvh & out, st
 		node[5] = uint32_t(triBase);
 		std::memcpy(&node[6], meta, 8);
 		for(int plane = 0; plane < 6; ++plane) std::memcpy(&node[8 + 2 * plane], q[plane], 8);
+		// The copy with slots by direction: greedy assignment of (child, slot) pairs by decreasing
+		// dot(child centre - node centre, corner direction of the slot).
+		{
+			out.nodesByOctant.resize(out.nodes.size(), 0u);
+			uint32_t * oct = out.nodesByOctant.data() + size_t(item.wide) * RB_WIDE_NODE_WORDS;
+			std::memcpy(oct, node, RB_WIDE_NODE_WORDS * sizeof(uint32_t));
+			double centre[3] = {0, 0, 0};
+			for(int a = 0; a < 3; ++a) {
+				double lo = INFINITY, hi = -INFINITY;
+				for(const WChild & c : list) {
+					lo = std::fmin(lo, double(c.lo[a]));
+					hi = std::fmax(hi, double(c.hi[a]));
+				}
+				centre[a] = list.empty() ? 0.0 : 0.5 * (lo + hi);
+			}
+			int slotOf[8], childAt[8];
+			for(int i = 0; i < 8; ++i) slotOf[i] = childAt[i] = -1;
+			for(size_t round = 0; round < list.size(); ++round) {
+				double best = -INFINITY;
+				int bi = -1, bs = -1;
+				for(size_t i = 0; i < list.size(); ++i) {
+					if(slotOf[i] >= 0) continue;
+					for(int sl = 0; sl < 8; ++sl) {
+						if(childAt[sl] >= 0) continue;
+						double d = 0.0;
+						for(int a = 0; a < 3; ++a) d += (0.5 * (double(list[i].lo[a]) + double(list[i].hi[a])) - centre[a]) * (((sl >> a) & 1) ? 1.0 : -1.0);
+						if(d > best) {
+							best = d;
+							bi	 = int(i);
+							bs	 = sl;
+						}
+					}
+				}
+				slotOf[bi]	= bs;
+				childAt[bs] = bi;
+			}
+			uint8_t metaO[8], qO[6][8];
+			for(int sl = 0; sl < 8; ++sl) {
+				const int i = childAt[sl];
+				metaO[sl]	= i >= 0 ? meta[i] : 0;
+				for(int plane = 0; plane < 6; ++plane) qO[plane][sl] = i >= 0 ? q[plane][i] : (plane < 3 ? 255 : 0);
+			}
+			std::memcpy(&oct[6], metaO, 8);
+			for(int plane = 0; plane < 6; ++plane) std::memcpy(&oct[8 + 2 * plane], qO[plane], 8);
+		}
 		int k = 0;
 		for(size_t i = 0; i < list.size(); ++i) {
 			if(list[i].node < 0) continue;

@@ -19,7 +19,8 @@ struct RbWideTraversal {
 	RbHitRec best; // best.tri: index in hierarchy order (word 11 of the wide triangle record)
 	float mini, maxi, maxi0;
 	unsigned int childBase, triBase, metaLo, metaHi;
-	unsigned int pending; // 24 bits, three per slot
+	unsigned int pending; // 24 bits, three per slot (OCT: per visiting position, see rb_wide_permute)
+	unsigned int flip;	  // OCT: visiting position of a slot = slot ^ flip (bit a set where the ray runs towards -a)
 	int root;
 	unsigned int top; // shared-memory address of the next free stack entry
 };
@@ -33,6 +34,7 @@ RB_D void rb_wide_init(RbWideTraversal & T, const RbDeviceBvh & bvh, float mini,
 	T.maxi	   = maxi;
 	T.maxi0	   = maxi;
 	T.pending  = 0u;
+	T.flip	   = 0u;
 	T.top	   = st.base;
 	T.root	   = bvh.nroots;
 }
@@ -75,9 +77,23 @@ RB_D unsigned int rb_wide_pack3(unsigned int c) {
 	return (c & 0x7u) | ((c >> 5) & 0x38u) | ((c >> 10) & 0x1c0u) | ((c >> 15) & 0xe00u);
 }
 
+// Slots by direction (RbWideBvh::nodesByOctant): a ray visits slot s at position s ^ flip. The pending list is kept per
+// POSITION, so that its lowest bit is still the next item: the three-bit groups are permuted by the XOR, i.e. swapped in
+// neighbours, pairs and halves as the bits of `flip` say.
+RB_D unsigned int rb_wide_permute(unsigned int x, unsigned int flip) {
+	if(flip & 1u) x = ((x & 0x1c71c7u) << 3) | ((x >> 3) & 0x1c71c7u);
+	if(flip & 2u) x = ((x & 0x03f03fu) << 6) | ((x >> 6) & 0x03f03fu);
+	if(flip & 4u) x = ((x & 0x000fffu) << 12) | (x >> 12);
+	return x;
+}
+RB_D unsigned int rb_wide_flip(const RbRay & ray) {
+	return (ray.inv.x < 0.0f ? 1u : 0u) | (ray.inv.y < 0.0f ? 2u : 0u) | (ray.inv.z < 0.0f ? 4u : 0u);
+}
+
 // Loads node `n`, box-tests its eight children against (mini, maxi) and makes it the current node of T.
+template<bool OCT>
 RB_D void rb_wide_enter(RbWideTraversal & T, const RbDeviceWide & wide, const RbRay & ray, int n) {
-	const uint4 * p = wide.nodes + 5 * (size_t)n;
+	const uint4 * p = (OCT ? wide.nodesByOctant : wide.nodes) + 5 * (size_t)n;
 	const uint4 n0 = __ldg(p), n1 = __ldg(p + 1), n2 = __ldg(p + 2), n3 = __ldg(p + 3), n4 = __ldg(p + 4);
 	T.childBase = n1.x;
 	T.triBase	= n1.y;
@@ -124,12 +140,13 @@ RB_D void rb_wide_enter(RbWideTraversal & T, const RbDeviceWide & wide, const Rb
 	// The items each slot really has: the unary counts (top three bits of every meta byte) packed three bits per slot.
 	const unsigned int cLo = (n1.z >> 5) & 0x07070707u, cHi = (n1.w >> 5) & 0x07070707u;
 	T.pending = hit & (rb_wide_pack3(cLo) | (rb_wide_pack3(cHi) << 12));
+	if(OCT) T.pending = rb_wide_permute(T.pending, T.flip);
 }
 
 // One step: consume the next pending item — enter an interior child, or test one triangle of a leaf child. Returns
 // true when the ray has finished (ANY: also as soon as a triangle is accepted). Regular rays only (the caller sends
 // rays that can produce NaNs in the slab test through the binary tree, whose box test reproduces them).
-template<bool ANY>
+template<bool ANY, bool OCT = false>
 RB_D bool rb_wide_step(RbWideTraversal & T, const RbDeviceBvh & bvh, const RbDeviceWide & wide, const RbRay & ray, const RbStack & st) {
 	int enter = -1; // node to enter in this step (one call site of rb_wide_enter: it is 180 instructions)
 	if(T.pending == 0u) {
@@ -149,13 +166,14 @@ RB_D bool rb_wide_step(RbWideTraversal & T, const RbDeviceBvh & bvh, const RbDev
 	if(enter < 0) {
 		const unsigned int bit = __ffs(T.pending) - 1;
 		T.pending &= T.pending - 1u;
-		const unsigned int slot = (bit * 11u) >> 5; // bit / 3 for bit < 24
+		const unsigned int spot = (bit * 11u) >> 5; // bit / 3 for bit < 24: the visiting position
+		const unsigned int slot = OCT ? (spot ^ T.flip) : spot;
 		const unsigned int low	= __byte_perm(T.metaLo, T.metaHi, slot) & 31u;
 		if(low >= 24u) {
 			enter = int(T.childBase + low - 24u);
 			if(T.pending != 0u) rb_wide_push(T, st);
 		} else {
-			const int tri	  = int(T.triBase + low + (bit - 3u * slot));
+			const int tri	  = int(T.triBase + low + (bit - 3u * spot));
 			const float4 * tp = wide.tris + 3 * (size_t)tri;
 			const float4 t0 = rb_ldg4(tp), t1 = rb_ldg4(tp + 1), t2 = rb_ldg4(tp + 2);
 			float t, u, v;
@@ -172,7 +190,7 @@ RB_D bool rb_wide_step(RbWideTraversal & T, const RbDeviceBvh & bvh, const RbDev
 			return false;
 		}
 	}
-	rb_wide_enter(T, wide, ray, enter);
+	rb_wide_enter<OCT>(T, wide, ray, enter);
 	return false;
 }
 
@@ -186,15 +204,17 @@ RB_D void rb_wide_settle(RbWideTraversal & T, const RbStack & st) {
 }
 
 // True when the next item of the ray is a triangle (false: an interior child, or the next root).
+template<bool OCT = false>
 RB_D bool rb_wide_wants_triangle(const RbWideTraversal & T) {
 	if(T.pending == 0u) return false;
 	const unsigned int bit	= __ffs(T.pending) - 1;
-	const unsigned int slot = (bit * 11u) >> 5;
-	return (__byte_perm(T.metaLo, T.metaHi, slot) & 31u) < 24u;
+	const unsigned int spot = (bit * 11u) >> 5;
+	return (__byte_perm(T.metaLo, T.metaHi, OCT ? (spot ^ T.flip) : spot) & 31u) < 24u;
 }
 
 // Node phase: enter the next interior child, or — with nothing pending — the next root. Returns true when the ray has
 // finished (no root left).
+template<bool OCT = false>
 RB_D bool rb_wide_phase_node(RbWideTraversal & T, const RbDeviceBvh & bvh, const RbDeviceWide & wide, const RbRay & ray, const RbStack & st) {
 	int enter;
 	if(T.pending == 0u) {
@@ -208,23 +228,23 @@ RB_D bool rb_wide_phase_node(RbWideTraversal & T, const RbDeviceBvh & bvh, const
 	} else {
 		const unsigned int bit = __ffs(T.pending) - 1;
 		T.pending &= T.pending - 1u;
-		const unsigned int slot = (bit * 11u) >> 5;
-		enter = int(T.childBase + (__byte_perm(T.metaLo, T.metaHi, slot) & 31u) - 24u);
+		const unsigned int spot = (bit * 11u) >> 5;
+		enter = int(T.childBase + (__byte_perm(T.metaLo, T.metaHi, OCT ? (spot ^ T.flip) : spot) & 31u) - 24u);
 		if(T.pending != 0u) rb_wide_push(T, st);
 	}
-	rb_wide_enter(T, wide, ray, enter);
+	rb_wide_enter<OCT>(T, wide, ray, enter);
 	rb_wide_settle(T, st);
 	return false;
 }
 
 // Leaf phase: one triangle. Returns true when an ANY query has found its hit.
-template<bool ANY>
+template<bool ANY, bool OCT = false>
 RB_D bool rb_wide_phase_triangle(RbWideTraversal & T, const RbDeviceWide & wide, const RbRay & ray, const RbStack & st) {
 	const unsigned int bit = __ffs(T.pending) - 1;
 	T.pending &= T.pending - 1u;
-	const unsigned int slot = (bit * 11u) >> 5;
-	const unsigned int low	= __byte_perm(T.metaLo, T.metaHi, slot) & 31u;
-	const int tri			= int(T.triBase + low + (bit - 3u * slot));
+	const unsigned int spot = (bit * 11u) >> 5;
+	const unsigned int low	= __byte_perm(T.metaLo, T.metaHi, OCT ? (spot ^ T.flip) : spot) & 31u;
+	const int tri			= int(T.triBase + low + (bit - 3u * spot));
 	const float4 * tp		= wide.tris + 3 * (size_t)tri;
 	const float4 t0 = rb_ldg4(tp), t1 = rb_ldg4(tp + 1), t2 = rb_ldg4(tp + 2);
 	float t, u, v;

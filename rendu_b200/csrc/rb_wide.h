@@ -35,6 +35,12 @@ struct RbFlatBvh;
 
 struct RbWideBvh {
 	std::vector<uint32_t> nodes; // RB_WIDE_NODE_WORDS per node
+	// The same nodes with their children moved to slots chosen by direction: the child that lies furthest towards the
+	// corner (sx, sy, sz) of the node, sign bit a of s set = positive, sits in (or near) slot s. A ray whose direction has
+	// the sign bits o then meets the children roughly front to back in the order slot ^ (~o & 7) = 0, 1, ... 7 (Ylitie,
+	// Karras, Laine 2017, section 3.2). Indices, triangle offsets and boxes are those of `nodes`; only the slots differ.
+	// For closest-hit queries that do not promise the reference's order (RB_WIDE_OCTANT): same hits except exact-distance ties.
+	std::vector<uint32_t> nodesByOctant;
 	std::vector<float> tris;	 // 12 floats per triangle, wide order
 	std::vector<int32_t> rootNode; // per root (mesh): wide node index, -1 = empty mesh
 	int depth = 0;				 // wide nodes on the longest root-to-leaf path
@@ -46,7 +52,8 @@ struct RbWideBvh {
 bool rb_wide_collapse(const RbFlatBvh & flat, size_t nroots, RbWideBvh & out, std::string * why);
 
 struct RbDeviceWide {
-	const uint4 * nodes; // 5 per node
+	const uint4 * nodes; // 5 per node (slots in the reference's visiting order)
+	const uint4 * nodesByOctant; // the same nodes, slots by direction
 	const float4 * tris; // 3 per triangle
 	const int * rootNode;
 	int stackDepth; // stack entries a traversal needs

@@ -116,6 +116,12 @@ class Raycaster:
         check(lib().rb_raycaster_wide_download(self._h, ptr(nodes), ptr(tris), ptr(roots)))
         return nodes, tris, roots
 
+    def download_wide_by_octant(self):
+        """The second copy of the wide nodes (n, 20) uint32: children in slots by direction."""
+        nodes = np.zeros((self._wide_sizes["nodes"], 20), np.uint32)
+        check(lib().rb_raycaster_wide_download_by_octant(self._h, ptr(nodes)))
+        return nodes
+
     # ------------------------------------------------------------------ queries (Raycaster.cpp:144-230)
     def intersects(self, origin, direction, mini=0.0001, maxi=1e8):
         o, single = _rays(origin)

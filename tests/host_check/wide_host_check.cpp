@@ -7,14 +7,16 @@
 
 // roots: 8 floats per root as the library lays them out (min xyz, reference, max xyz, 0). mode 0: rb_wide_step (what
 // rb_k_trace_wide runs); mode 1: rb_wide_phase_node / rb_wide_phase_triangle in the order one lane of
-// rb_k_trace_wide_phased would run them. Outputs per ray: triangle in hierarchy order (-1: miss), t, u, v.
+// rb_k_trace_wide_phased would run them; byOctant != 0: wideNodes holds the slots-by-direction copy and the steps run
+// with OCT = true. Outputs per ray: triangle in hierarchy order (-1: miss), t, u, v.
 // Returns the number of rays that could not take the wide tree (irregular rays: the kernels walk the binary tree for them).
-extern "C" int rb_hc_wide_trace(const float * roots, int nroots, const uint32_t * wideNodes, const float * wideTris, const int * wideRoots, int wideDepth, const float * org, const float * dir, int nrays, float mini, float maxi, int anyHit, int mode, int * outTri, float * outTuv) {
+extern "C" int rb_hc_wide_trace(const float * roots, int nroots, const uint32_t * wideNodes, const float * wideTris, const int * wideRoots, int wideDepth, const float * org, const float * dir, int nrays, float mini, float maxi, int anyHit, int mode, int byOctant, int * outTri, float * outTuv, int * outEntered) {
 	RbDeviceBvh bvh = {};
 	bvh.roots		= reinterpret_cast<const float4 *>(roots);
 	bvh.nroots		= nroots;
 	RbDeviceWide wide = {};
 	wide.nodes		  = reinterpret_cast<const uint4 *>(wideNodes);
+	wide.nodesByOctant = wide.nodes;
 	wide.tris		  = reinterpret_cast<const float4 *>(wideTris);
 	wide.rootNode	  = wideRoots;
 	wide.stackDepth	  = wideDepth + 1;
@@ -33,9 +35,15 @@ extern "C" int rb_hc_wide_trace(const float * roots, int nroots, const uint32_t 
 		}
 		RbWideTraversal T;
 		rb_wide_init(T, bvh, mini, maxi, st);
+		if(byOctant) T.flip = rb_wide_flip(ray);
 		bool done = false;
-		for(long guard = 0; !done && guard < 100000000; ++guard) {
-			if(mode == 0) {
+		long steps = 0;
+		for(; !done && steps < 100000000; ++steps) {
+			if(byOctant) {
+				if(mode == 0) done = anyHit ? rb_wide_step<true, true>(T, bvh, wide, ray, st) : rb_wide_step<false, true>(T, bvh, wide, ray, st);
+				else if(rb_wide_wants_triangle<true>(T)) done = anyHit ? rb_wide_phase_triangle<true, true>(T, wide, ray, st) : rb_wide_phase_triangle<false, true>(T, wide, ray, st);
+				else done = rb_wide_phase_node<true>(T, bvh, wide, ray, st);
+			} else if(mode == 0) {
 				done = anyHit ? rb_wide_step<true>(T, bvh, wide, ray, st) : rb_wide_step<false>(T, bvh, wide, ray, st);
 			} else if(rb_wide_wants_triangle(T)) {
 				done = anyHit ? rb_wide_phase_triangle<true>(T, wide, ray, st) : rb_wide_phase_triangle<false>(T, wide, ray, st);
@@ -43,6 +51,7 @@ extern "C" int rb_hc_wide_trace(const float * roots, int nroots, const uint32_t 
 				done = rb_wide_phase_node(T, bvh, wide, ray, st);
 			}
 		}
+		if(outEntered) outEntered[i] = int(steps); // node entries + triangle tests (+ pops in the plain stepping)
 		outTri[i]		  = T.best.tri;
 		outTuv[3 * i]	  = T.best.t;
 		outTuv[3 * i + 1] = T.best.u;

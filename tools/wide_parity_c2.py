@@ -46,11 +46,11 @@ def main():
         for mode, label in ((0, "rb_wide_step"), (1, "phase-split")):
             tri, tuv = np.zeros(n, np.int32), np.zeros((n, 3), np.float32)
             t0 = time.time()
-            skipped = L.rb_hc_wide_trace(ptr(roots), 1, ptr(nodes), ptr(tris), ptr(wroots), r._wide_sizes["depth"], ptr(org), ptr(dirs), n, 1e-4, 1e8, 0, mode, ptr(tri), ptr(tuv))
+            skipped = L.rb_hc_wide_trace(ptr(roots), 1, ptr(nodes), ptr(tris), ptr(wroots), r._wide_sizes["depth"], ptr(org), ptr(dirs), n, 1e-4, 1e8, 0, mode, 0, ptr(tri), ptr(tuv), None)
             took, hit = tri != -2, tri >= 0
             differ = took & ((hit != ho["hit"].astype(bool)) | (hit & ((tri != ho["internalId"].astype(np.int64)) | (tuv[:, 0].view(np.uint32) != ho["dist"].view(np.uint32)))))
             ta, tuva = np.zeros(n, np.int32), np.zeros((n, 3), np.float32)
-            L.rb_hc_wide_trace(ptr(roots), 1, ptr(nodes), ptr(tris), ptr(wroots), r._wide_sizes["depth"], ptr(org), ptr(dirs), n, 1e-4, 1e8, 1, mode, ptr(ta), ptr(tuva))
+            L.rb_hc_wide_trace(ptr(roots), 1, ptr(nodes), ptr(tris), ptr(wroots), r._wide_sizes["depth"], ptr(org), ptr(dirs), n, 1e-4, 1e8, 1, mode, 0, ptr(ta), ptr(tuva), None)
             rec[label] = {"rays_on_the_wide_tree": int(took.sum()), "irregular_rays_left_to_the_binary_tree": int(skipped), "closest_hit_records_that_differ": int(differ.sum()),
                           "any_hit_flags_that_differ": int((took & ((ta >= 0) != ha.astype(bool))).sum()), "seconds": round(time.time() - t0, 1)}
         out["sets"][name] = rec
