@@ -85,44 +85,26 @@ bool makePlan(const RbFlatBvh & flat, size_t nroots, Plan & P, std::string * why
 	P.split.assign(nI * 8, 0);
 	P.asLeaf.assign(nI, 0);
 	std::vector<float> box(nI * 6, 0.0f);
-	std::vector<int> order;
-	order.reserve(nI);
-	std::vector<int> stack;
 	std::vector<uint8_t> seen(nI, 0);
-	for(size_t r = 0; r < nroots; ++r) {
-		const float * d = flat.roots.data() + r * 8;
-		const int ref	= refOf(d[3]);
-		if(isNone(ref) || isLeaf(ref)) continue;
-		if(size_t(ref) >= nI || seen[ref]) {
-			if(why) *why = "malformed hierarchy (root reference)";
-			return false;
-		}
-		seen[ref] = 1;
-		for(int a = 0; a < 3; ++a) { box[size_t(ref) * 6 + a] = d[a]; box[size_t(ref) * 6 + 3 + a] = d[4 + a]; }
-		stack.push_back(ref);
-	}
-	while(!stack.empty()) {
-		const int b = stack.back();
-		stack.pop_back();
-		order.push_back(b);
-		const int refs[2]	   = {P.refL(b), P.refR(b)};
+	std::string malformed;
+	// Children's boxes live in their parent's record: expanding a node hands them down.
+	auto expand = [&](int b, std::vector<int> & into) {
+		const int refs[2]	 = {P.refL(b), P.refR(b)};
 		const float * los[2] = {P.loL(b), P.loR(b)};
 		const float * his[2] = {P.hiL(b), P.hiR(b)};
 		for(int c = 0; c < 2; ++c) {
 			if(isNone(refs[c]) || isLeaf(refs[c])) continue;
-			if(size_t(refs[c]) >= nI || seen[refs[c]]) {
-				if(why) *why = "malformed hierarchy (a node is referenced twice)";
-				return false;
-			}
+			if(size_t(refs[c]) >= nI || seen[refs[c]]) return false; // seen[] entries of different sub-trees are different bytes
 			seen[refs[c]] = 1;
 			std::memcpy(&box[size_t(refs[c]) * 6], los[c], 12);
 			std::memcpy(&box[size_t(refs[c]) * 6 + 3], his[c], 12);
-			stack.push_back(refs[c]);
+			into.push_back(refs[c]);
 		}
-	}
+		return true;
+	};
 	const double inf = std::numeric_limits<double>::infinity();
-	for(size_t q = order.size(); q-- > 0;) {
-		const int b = order[q];
+	// One node of the dynamic programme; its children are done.
+	auto solve = [&](int b) {
 		const int rl = P.refL(b), rr = P.refR(b);
 		P.prims[b] = P.primsOf(rl) + P.primsOf(rr);
 		double cl[8], cr[8];
@@ -163,7 +145,58 @@ bool makePlan(const RbFlatBvh & flat, size_t nroots, Plan & P, std::string * why
 				S[i] = 0;
 			}
 		}
+	};
+	// The top of the forest breadth first (parents before children) until there are enough sub-trees to share out;
+	// every sub-tree is then walked and solved bottom-up by one thread; the top is solved last, in reverse.
+	std::vector<int> top, frontier;
+	for(size_t r = 0; r < nroots; ++r) {
+		const float * d = flat.roots.data() + r * 8;
+		const int ref	= refOf(d[3]);
+		if(isNone(ref) || isLeaf(ref)) continue;
+		if(size_t(ref) >= nI || seen[ref]) {
+			if(why) *why = "malformed hierarchy (root reference)";
+			return false;
+		}
+		seen[ref] = 1;
+		for(int a = 0; a < 3; ++a) { box[size_t(ref) * 6 + a] = d[a]; box[size_t(ref) * 6 + 3 + a] = d[4 + a]; }
+		frontier.push_back(ref);
 	}
+	const size_t wanted = nI >= (size_t(1) << 15) ? 256 : 0;
+	for(size_t head = 0; head < frontier.size() && frontier.size() - head < wanted;) {
+		const int b = frontier[head++];
+		top.push_back(b);
+		if(!expand(b, frontier)) {
+			if(why) *why = "malformed hierarchy (a node is referenced twice)";
+			return false;
+		}
+	}
+	frontier.erase(frontier.begin(), frontier.begin() + long(top.size()));
+	std::vector<uint8_t> bad(frontier.size(), 0);
+	rb_parallel_for(frontier.size(), 1, [&](size_t fb, size_t fe) {
+		std::vector<int> order, stack;
+		for(size_t f = fb; f < fe; ++f) {
+			order.clear();
+			stack.assign(1, frontier[f]);
+			while(!stack.empty()) {
+				const int b = stack.back();
+				stack.pop_back();
+				order.push_back(b);
+				if(!expand(b, stack)) {
+					bad[f] = 1;
+					break;
+				}
+			}
+			if(bad[f]) continue;
+			for(size_t q = order.size(); q-- > 0;) solve(order[q]);
+		}
+	});
+	for(uint8_t b : bad) {
+		if(b) {
+			if(why) *why = "malformed hierarchy (a node is referenced twice)";
+			return false;
+		}
+	}
+	for(size_t q = top.size(); q-- > 0;) solve(top[q]);
 	return true;
 }
 
@@ -354,35 +387,59 @@ bool rb_wide_collapse(const RbFlatBvh & flat, size_t nroots, RbWideBvh & out, st
 		node[5] = uint32_t(triBase);
 		std::memcpy(&node[6], meta, 8);
 		for(int plane = 0; plane < 6; ++plane) std::memcpy(&node[8 + 2 * plane], q[plane], 8);
-		// The copy with slots by direction: greedy assignment of (child, slot) pairs by decreasing
-		// dot(child centre - node centre, corner direction of the slot).
-		{
-			out.nodesByOctant.resize(out.nodes.size(), 0u);
-			uint32_t * oct = out.nodesByOctant.data() + size_t(item.wide) * RB_WIDE_NODE_WORDS;
-			std::memcpy(oct, node, RB_WIDE_NODE_WORDS * sizeof(uint32_t));
-			double centre[3] = {0, 0, 0};
-			for(int a = 0; a < 3; ++a) {
-				double lo = INFINITY, hi = -INFINITY;
-				for(const WChild & c : list) {
-					lo = std::fmin(lo, double(c.lo[a]));
-					hi = std::fmax(hi, double(c.hi[a]));
+		int k = 0;
+		for(size_t i = 0; i < list.size(); ++i) {
+			if(list[i].node < 0) continue;
+			WorkItem w;
+			w.wide	= childBase + k++;
+			w.ref	= list[i].node;
+			w.depth = item.depth + 1;
+			std::memcpy(w.lo, list[i].lo, sizeof(w.lo));
+			std::memcpy(w.hi, list[i].hi, sizeof(w.hi));
+			work.push_back(w);
+		}
+	}
+	// The copy with slots by direction, node by node on all threads: greedy assignment of (child, slot) pairs by decreasing
+	// dot(child centre - node centre, corner direction of the slot), centres taken from the stored (quantised) boxes.
+	out.nodesByOctant.assign(out.nodes.size(), 0u);
+	rb_parallel_for(out.nodes.size() / RB_WIDE_NODE_WORDS, 4096, [&](size_t nb, size_t ne) {
+		for(size_t n = nb; n < ne; ++n) {
+			const uint32_t * src = out.nodes.data() + n * RB_WIDE_NODE_WORDS;
+			uint32_t * dst		 = out.nodesByOctant.data() + n * RB_WIDE_NODE_WORDS;
+			std::memcpy(dst, src, RB_WIDE_NODE_WORDS * sizeof(uint32_t));
+			uint8_t meta[8], q[6][8];
+			std::memcpy(meta, &src[6], 8);
+			for(int plane = 0; plane < 6; ++plane) std::memcpy(q[plane], &src[8 + 2 * plane], 8);
+			double scale[3], lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+			for(int a = 0; a < 3; ++a) scale[a] = std::ldexp(1.0, int((src[3] >> (8 * a)) & 0xffu) - 127);
+			int count = 0;
+			for(int i = 0; i < 8; ++i) {
+				if(meta[i] == 0) continue;
+				++count;
+				for(int a = 0; a < 3; ++a) {
+					lo[a] = std::fmin(lo[a], double(q[a][i]) * scale[a]);
+					hi[a] = std::fmax(hi[a], double(q[3 + a][i]) * scale[a]);
 				}
-				centre[a] = list.empty() ? 0.0 : 0.5 * (lo + hi);
+			}
+			double towards[8][8]; // [child][slot]
+			for(int i = 0; i < 8; ++i) {
+				if(meta[i] == 0) continue;
+				double off[3];
+				for(int a = 0; a < 3; ++a) off[a] = 0.5 * (double(q[a][i]) + double(q[3 + a][i])) * scale[a] - 0.5 * (lo[a] + hi[a]);
+				for(int sl = 0; sl < 8; ++sl) towards[i][sl] = ((sl & 1) ? off[0] : -off[0]) + ((sl & 2) ? off[1] : -off[1]) + ((sl & 4) ? off[2] : -off[2]);
 			}
 			int slotOf[8], childAt[8];
 			for(int i = 0; i < 8; ++i) slotOf[i] = childAt[i] = -1;
-			for(size_t round = 0; round < list.size(); ++round) {
+			for(int round = 0; round < count; ++round) {
 				double best = -INFINITY;
 				int bi = -1, bs = -1;
-				for(size_t i = 0; i < list.size(); ++i) {
-					if(slotOf[i] >= 0) continue;
+				for(int i = 0; i < 8; ++i) {
+					if(meta[i] == 0 || slotOf[i] >= 0) continue;
 					for(int sl = 0; sl < 8; ++sl) {
 						if(childAt[sl] >= 0) continue;
-						double d = 0.0;
-						for(int a = 0; a < 3; ++a) d += (0.5 * (double(list[i].lo[a]) + double(list[i].hi[a])) - centre[a]) * (((sl >> a) & 1) ? 1.0 : -1.0);
-						if(d > best) {
-							best = d;
-							bi	 = int(i);
+						if(towards[i][sl] > best) {
+							best = towards[i][sl];
+							bi	 = i;
 							bs	 = sl;
 						}
 					}
@@ -396,20 +453,9 @@ bool rb_wide_collapse(const RbFlatBvh & flat, size_t nroots, RbWideBvh & out, st
 				metaO[sl]	= i >= 0 ? meta[i] : 0;
 				for(int plane = 0; plane < 6; ++plane) qO[plane][sl] = i >= 0 ? q[plane][i] : (plane < 3 ? 255 : 0);
 			}
-			std::memcpy(&oct[6], metaO, 8);
-			for(int plane = 0; plane < 6; ++plane) std::memcpy(&oct[8 + 2 * plane], qO[plane], 8);
+			std::memcpy(&dst[6], metaO, 8);
+			for(int plane = 0; plane < 6; ++plane) std::memcpy(&dst[8 + 2 * plane], qO[plane], 8);
 		}
-		int k = 0;
-		for(size_t i = 0; i < list.size(); ++i) {
-			if(list[i].node < 0) continue;
-			WorkItem w;
-			w.wide	= childBase + k++;
-			w.ref	= list[i].node;
-			w.depth = item.depth + 1;
-			std::memcpy(w.lo, list[i].lo, sizeof(w.lo));
-			std::memcpy(w.hi, list[i].hi, sizeof(w.hi));
-			work.push_back(w);
-		}
-	}
+	});
 	return true;
 }
