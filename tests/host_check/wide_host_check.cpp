@@ -59,3 +59,43 @@ extern "C" int rb_hc_wide_trace(const float * roots, int nroots, const uint32_t 
 	}
 	return skipped;
 }
+
+// The binary traversal the default kernels inline (rb_trace.cuh), one ray at a time: mode 0 = rb_step (what
+// rb_k_closest / rb_k_any / rb_k_trace_persistent run), mode 1 = rb_phase_node / rb_phase_leaf in the order one lane of
+// rb_k_trace_phased runs them (`nodeSteps` node steps per vote). ordered != 0: near child first (RB_TRACE_ORDERED).
+// nodes: 16 floats per interior node, tris: 12 floats per triangle, roots: 8 floats per root — the device layout
+// (rb_bvh_host.cpp, rb_host_flatten). Every ray is traced, irregular ones (NaN / inf / axis-parallel) included.
+extern "C" int rb_hc_binary_trace(const float * nodes, const float * tris, const float * roots, int nroots, int stackDepth, const float * org, const float * dir, int nrays, float mini, float maxi, int anyHit, int ordered, int mode, int nodeSteps, int * outTri, float * outTuv) {
+	RbDeviceBvh bvh = {};
+	bvh.nodes		= reinterpret_cast<const float4 *>(nodes);
+	bvh.tris		= reinterpret_cast<const float4 *>(tris);
+	bvh.roots		= reinterpret_cast<const float4 *>(roots);
+	bvh.nroots		= nroots;
+	bvh.stackDepth	= stackDepth;
+	if(size_t(stackDepth + 1) * 4 > sizeof(rb_hc_shared)) return -1;
+	const RbStack st = rb_make_stack(reinterpret_cast<int *>(rb_hc_shared), 1);
+	for(int i = 0; i < nrays; ++i) {
+		const RbRay ray = rb_make_ray(V3{org[3 * i], org[3 * i + 1], org[3 * i + 2]}, V3{dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]});
+		RbTraversal T;
+		rb_traversal_init(T, bvh, mini, maxi, st);
+		bool done = false;
+		for(long guard = 0; !done && guard < 100000000; ++guard) {
+			if(mode == 0) {
+				if(anyHit) done = ordered ? rb_step<true, false, true>(T, bvh, ray, st, nullptr) : rb_step<true, false, false>(T, bvh, ray, st, nullptr);
+				else done = ordered ? rb_step<false, false, true>(T, bvh, ray, st, nullptr) : rb_step<false, false, false>(T, bvh, ray, st, nullptr);
+			} else if(rb_wants_leaf(T)) {
+				done = anyHit ? rb_phase_leaf<true, false>(T, bvh, ray, nullptr) : rb_phase_leaf<false, false>(T, bvh, ray, nullptr);
+			} else {
+				for(int k = 0; k < nodeSteps && !done; ++k) {
+					done = ordered ? rb_phase_node<false, true>(T, bvh, ray, st, nullptr) : rb_phase_node<false, false>(T, bvh, ray, st, nullptr);
+					if(rb_wants_leaf(T)) break;
+				}
+			}
+		}
+		outTri[i]		  = T.best.tri;
+		outTuv[3 * i]	  = T.best.t;
+		outTuv[3 * i + 1] = T.best.u;
+		outTuv[3 * i + 2] = T.best.v;
+	}
+	return 0;
+}
