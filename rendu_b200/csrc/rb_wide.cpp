@@ -262,7 +262,7 @@ bool rb_wide_collapse(const RbFlatBvh & flat, size_t nroots, RbWideBvh & out, st
 	out.tris.reserve(flat.tris.size());
 	out.rootNode.assign(nroots, -1);
 	out.depth = 0;
-	std::vector<WorkItem> work;
+	std::vector<WorkItem> work; // the nodes of the current level
 	for(size_t r = 0; r < nroots; ++r) {
 		const float * d = flat.roots.data() + r * 8;
 		const int ref	= refOf(d[3]);
@@ -276,12 +276,19 @@ bool rb_wide_collapse(const RbFlatBvh & flat, size_t nroots, RbWideBvh & out, st
 		out.nodes.resize(out.nodes.size() + RB_WIDE_NODE_WORDS, 0u);
 		work.push_back(w);
 	}
-	std::vector<WChild> list;
-	while(!work.empty()) {
-		const WorkItem item = work.back();
-		work.pop_back();
-		if(item.depth > out.depth) out.depth = item.depth;
-		list.clear();
+	// Level by level: the nodes of a level are prepared on all threads (children, quantised planes, counts), a prefix sum
+	// hands out the node and triangle ranges of their children, and a second parallel pass writes them.
+	struct Prepared {
+		uint32_t words[RB_WIDE_NODE_WORDS];
+		int nInterior = 0, nTris = 0;
+		int childRef[8];
+		float childLo[8][3], childHi[8][3];
+		int tri[8 * RB_WIDE_MAX_LEAF_TRIS];
+		std::string error;
+	};
+	auto prepare = [&](const WorkItem & item, Prepared & pr) {
+		std::vector<WChild> list;
+		list.reserve(8);
 		if(isLeaf(item.ref)) {
 			collect(P, item.ref, item.lo, item.hi, 1, list);
 		} else {
@@ -290,10 +297,11 @@ bool rb_wide_collapse(const RbFlatBvh & flat, size_t nroots, RbWideBvh & out, st
 			collect(P, P.refL(b), P.loL(b), P.hiL(b), k, list);
 		}
 		if(list.size() > 8) {
-			if(why) *why = "internal error: a wide node with more than eight children";
-			return false;
+			pr.error = "internal error: a wide node with more than eight children";
+			return;
 		}
-		uint32_t * node = out.nodes.data() + size_t(item.wide) * RB_WIDE_NODE_WORDS;
+		uint32_t * node = pr.words;
+		std::memset(node, 0, sizeof(pr.words));
 		uint8_t q[6][8];
 		for(int s = 0; s < 8; ++s) {
 			q[0][s] = q[1][s] = q[2][s] = 255;
@@ -304,8 +312,8 @@ bool rb_wide_collapse(const RbFlatBvh & flat, size_t nroots, RbWideBvh & out, st
 			double lo = INFINITY, hi = -INFINITY;
 			for(const WChild & c : list) {
 				if(!std::isfinite(c.lo[a]) || !std::isfinite(c.hi[a]) || c.lo[a] > c.hi[a]) {
-					if(why) *why = "a box with non-finite or inverted bounds cannot be quantised";
-					return false;
+					pr.error = "a box with non-finite or inverted bounds cannot be quantised";
+					return;
 				}
 				lo = std::fmin(lo, double(c.lo[a]));
 				hi = std::fmax(hi, double(c.hi[a]));
@@ -320,8 +328,8 @@ bool rb_wide_collapse(const RbFlatBvh & flat, size_t nroots, RbWideBvh & out, st
 			double s = 0.0;
 			for(;; ++e) {
 				if(e > 40) {
-					if(why) *why = "box extent out of the range of the quantisation exponents";
-					return false;
+					pr.error = "box extent out of the range of the quantisation exponents";
+					return;
 				}
 				s = std::ldexp(1.0, e);
 				p = roundDown(lo - 2.0 * RB_WIDE_MARGIN * s);
@@ -335,12 +343,10 @@ bool rb_wide_collapse(const RbFlatBvh & flat, size_t nroots, RbWideBvh & out, st
 				const double l = std::floor((double(list[i].lo[a]) - double(p)) / s - RB_WIDE_MARGIN);
 				const double h = std::ceil((double(list[i].hi[a]) - double(p)) / s + RB_WIDE_MARGIN);
 				if(!(l >= 0.0 && h <= 255.0 && l <= h)) {
-					if(why) {
-						char buf[256];
-						snprintf(buf, sizeof(buf), "internal error: quantised plane out of range (axis %d: child [%g, %g], origin %g, scale 2^%d, q [%g, %g])", a, double(list[i].lo[a]), double(list[i].hi[a]), double(p), e, l, h);
-						*why = buf;
-					}
-					return false;
+					char buf[256];
+					snprintf(buf, sizeof(buf), "internal error: quantised plane out of range (axis %d: child [%g, %g], origin %g, scale 2^%d, q [%g, %g])", a, double(list[i].lo[a]), double(list[i].hi[a]), double(p), e, l, h);
+					pr.error = buf;
+					return;
 				}
 				q[a][i]		= uint8_t(l);
 				q[3 + a][i] = uint8_t(h);
@@ -348,56 +354,85 @@ bool rb_wide_collapse(const RbFlatBvh & flat, size_t nroots, RbWideBvh & out, st
 		}
 		node[3] = expo | (uint32_t(list.size()) << 24);
 		// Children: interior ones get consecutive nodes, leaves consecutive triangles, both in slot order.
-		const int childBase	 = int(out.nodes.size() / RB_WIDE_NODE_WORDS);
-		const size_t triBase = out.tris.size() / 12;
-		uint8_t meta[8]		 = {0, 0, 0, 0, 0, 0, 0, 0};
-		int nInterior = 0, triOffset = 0;
+		uint8_t meta[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+		pr.nInterior = pr.nTris = 0;
 		for(size_t i = 0; i < list.size(); ++i) {
 			if(list[i].node >= 0) {
-				meta[i] = uint8_t(0x20 | (24 + nInterior));
-				++nInterior;
+				meta[i] = uint8_t(0x20 | (24 + pr.nInterior));
+				pr.childRef[pr.nInterior] = list[i].node;
+				std::memcpy(pr.childLo[pr.nInterior], list[i].lo, 12);
+				std::memcpy(pr.childHi[pr.nInterior], list[i].hi, 12);
+				++pr.nInterior;
 				continue;
 			}
 			const int count = list[i].ntris;
 			if(count < 1 || count > RB_WIDE_MAX_LEAF_TRIS) {
-				if(why) *why = "internal error: leaf child without triangles";
-				return false;
+				pr.error = "internal error: leaf child without triangles";
+				return;
 			}
-			meta[i] = uint8_t((((1u << count) - 1u) << 5) | uint32_t(triOffset));
+			meta[i] = uint8_t((((1u << count) - 1u) << 5) | uint32_t(pr.nTris));
 			for(int k = 0; k < count; ++k) {
 				if(size_t(list[i].tri[k]) >= nTris) {
-					if(why) *why = "leaf triangle range out of bounds";
-					return false;
+					pr.error = "leaf triangle range out of bounds";
+					return;
 				}
-				const float * src = flat.tris.data() + size_t(list[i].tri[k]) * 12;
-				const size_t at	  = out.tris.size();
-				out.tris.insert(out.tris.end(), src, src + 12);
-				const int32_t hier = int32_t(list[i].tri[k]);
-				std::memcpy(&out.tris[at + 11], &hier, 4);
+				pr.tri[pr.nTris++] = list[i].tri[k];
 			}
-			triOffset += count;
 		}
-		if(triBase + size_t(triOffset) >= (size_t(1) << 31)) {
-			if(why) *why = "too many triangles for 32-bit references";
-			return false;
-		}
-		out.nodes.resize(out.nodes.size() + size_t(nInterior) * RB_WIDE_NODE_WORDS, 0u);
-		node = out.nodes.data() + size_t(item.wide) * RB_WIDE_NODE_WORDS; // resize may have moved the array
-		node[4] = uint32_t(childBase);
-		node[5] = uint32_t(triBase);
 		std::memcpy(&node[6], meta, 8);
 		for(int plane = 0; plane < 6; ++plane) std::memcpy(&node[8 + 2 * plane], q[plane], 8);
-		int k = 0;
-		for(size_t i = 0; i < list.size(); ++i) {
-			if(list[i].node < 0) continue;
-			WorkItem w;
-			w.wide	= childBase + k++;
-			w.ref	= list[i].node;
-			w.depth = item.depth + 1;
-			std::memcpy(w.lo, list[i].lo, sizeof(w.lo));
-			std::memcpy(w.hi, list[i].hi, sizeof(w.hi));
-			work.push_back(w);
+	};
+	std::vector<WorkItem> next;
+	std::vector<Prepared> prepared;
+	std::vector<size_t> nodeAt, triAt;
+	while(!work.empty()) {
+		++out.depth;
+		const size_t n = work.size();
+		prepared.assign(n, Prepared());
+		rb_parallel_for(n, 256, [&](size_t b, size_t e) {
+			for(size_t i = b; i < e; ++i) prepare(work[i], prepared[i]);
+		});
+		nodeAt.assign(n + 1, out.nodes.size() / RB_WIDE_NODE_WORDS);
+		triAt.assign(n + 1, out.tris.size() / 12);
+		for(size_t i = 0; i < n; ++i) {
+			if(!prepared[i].error.empty()) {
+				if(why) *why = prepared[i].error;
+				return false;
+			}
+			nodeAt[i + 1] = nodeAt[i] + size_t(prepared[i].nInterior);
+			triAt[i + 1]  = triAt[i] + size_t(prepared[i].nTris);
 		}
+		if(triAt[n] >= (size_t(1) << 31) || nodeAt[n] >= (size_t(1) << 31)) {
+			if(why) *why = "too many nodes or triangles for 32-bit references";
+			return false;
+		}
+		const size_t firstChild = nodeAt[0];
+		out.nodes.resize(nodeAt[n] * RB_WIDE_NODE_WORDS, 0u);
+		out.tris.resize(triAt[n] * 12);
+		next.assign(nodeAt[n] - firstChild, WorkItem());
+		rb_parallel_for(n, 256, [&](size_t b, size_t e) {
+			for(size_t i = b; i < e; ++i) {
+				Prepared & pr	= prepared[i];
+				pr.words[4]		= uint32_t(nodeAt[i]);
+				pr.words[5]		= uint32_t(triAt[i]);
+				std::memcpy(out.nodes.data() + size_t(work[i].wide) * RB_WIDE_NODE_WORDS, pr.words, sizeof(pr.words));
+				for(int k = 0; k < pr.nTris; ++k) {
+					float * dst = out.tris.data() + (triAt[i] + size_t(k)) * 12;
+					std::memcpy(dst, flat.tris.data() + size_t(pr.tri[k]) * 12, 48);
+					const int32_t hier = int32_t(pr.tri[k]);
+					std::memcpy(dst + 11, &hier, 4);
+				}
+				for(int k = 0; k < pr.nInterior; ++k) {
+					WorkItem & w = next[nodeAt[i] - firstChild + size_t(k)];
+					w.wide		 = int(nodeAt[i] + size_t(k));
+					w.ref		 = pr.childRef[k];
+					w.depth		 = out.depth + 1;
+					std::memcpy(w.lo, pr.childLo[k], 12);
+					std::memcpy(w.hi, pr.childHi[k], 12);
+				}
+			}
+		});
+		work.swap(next);
 	}
 	// The copy with slots by direction, node by node on all threads: greedy assignment of (child, slot) pairs by decreasing
 	// dot(child centre - node centre, corner direction of the slot), centres taken from the stored (quantised) boxes.
