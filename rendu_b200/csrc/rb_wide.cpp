@@ -238,7 +238,6 @@ void collect(const Plan & P, int ref, const float * lo, const float * hi, int i,
 struct WorkItem {
 	int wide;  // index of the wide node to fill
 	int ref;   // binary reference it stands for (an interior node, or a leaf for a mesh that is a single leaf)
-	int depth;
 	float lo[3], hi[3];
 };
 
@@ -270,7 +269,6 @@ bool rb_wide_collapse(const RbFlatBvh & flat, size_t nroots, RbWideBvh & out, st
 		WorkItem w;
 		w.wide	= int(out.nodes.size() / RB_WIDE_NODE_WORDS);
 		w.ref	= ref;
-		w.depth = 1;
 		for(int a = 0; a < 3; ++a) { w.lo[a] = d[a]; w.hi[a] = d[4 + a]; }
 		out.rootNode[r] = w.wide;
 		out.nodes.resize(out.nodes.size() + RB_WIDE_NODE_WORDS, 0u);
@@ -426,7 +424,6 @@ bool rb_wide_collapse(const RbFlatBvh & flat, size_t nroots, RbWideBvh & out, st
 					WorkItem & w = next[nodeAt[i] - firstChild + size_t(k)];
 					w.wide		 = int(nodeAt[i] + size_t(k));
 					w.ref		 = pr.childRef[k];
-					w.depth		 = out.depth + 1;
 					std::memcpy(w.lo, pr.childLo[k], 12);
 					std::memcpy(w.hi, pr.childHi[k], 12);
 				}
