@@ -296,7 +296,8 @@ typedef struct rb_render_opts {
 	 * still normalised by the full `samples`, so per-GPU images add up to the full estimate. */
 	uint32_t sample_index, sample_count;
 	uint32_t trace_mode; /* rb_trace_mode used for primary, bounce and shadow rays (RB_TRACE_WIDE, experiment: closest-hit
-	                      * wavefront on the wide tree after rb_raycaster_wide_build on rb_scene_raycaster(); shadow rays as RB_TRACE_EXACT) */
+	                      * wavefront — and the shadow wavefront of scenes without masked materials — on the wide tree, after
+	                      * rb_raycaster_wide_build on rb_scene_raycaster()) */
 	uint32_t max_paths_in_flight; /* paths per wavefront batch; 0 = default (16 Mi; two batches are in flight: 176 B x 2 x 16 Mi = 5.9 GB) */
 	/* Progressive rendering: with accumulate != 0 rb_pathtracer_render_device ADDS this call's samples
 	 * to d_sum instead of overwriting it, so a viewer can trace one slice of the stratification grid per frame

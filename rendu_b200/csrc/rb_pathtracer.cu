@@ -503,6 +503,96 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shadow(RbDeviceBvh bvh, R
 	}
 }
 
+// The shadow wavefront of an UNMASKED scene on the eight-wide tree (trace_mode RB_TRACE_WIDE; experiment): any-hit queries,
+// whose answer no visiting order can change. Masked scenes keep rb_k_pt_shadow (their walk needs the closest occluder).
+__global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shadow_wide(RbDeviceBvh bvh, RbDeviceWide wide, RbPathBuffers pb, uint32_t did, int threshold, int leafVotes, unsigned long long * __restrict__ stats) {
+	extern __shared__ int s_stack[];
+	const RbStack st		= rb_make_stack(s_stack + threadIdx.x, blockDim.x);
+	const unsigned int lane = threadIdx.x & 31u;
+	const unsigned int n	= pb.counters[rb_cnt_shadow(did)];
+	unsigned int * cursor	= pb.counters + rb_cnt_cursor_s(did);
+	bool active = false, exhausted = false;
+	unsigned int slot = 0, queries = 0;
+	V3 contrib = v3(0.0f);
+	RbRay ray;
+	RbWideTraversal T;
+	for(;;) {
+		if(!exhausted) {
+			const unsigned int idle = __ballot_sync(0xffffffffu, !active);
+			if(idle) {
+				const int nIdle	 = __popc(idle);
+				const int leader = __ffs(idle) - 1;
+				unsigned int base = 0;
+				if((int)lane == leader) base = atomicAdd(cursor, (unsigned int)nIdle);
+				base = __shfl_sync(0xffffffffu, base, leader);
+				if(!active) {
+					const unsigned int idx = base + __popc(idle & ((1u << lane) - 1u));
+					if(idx < n) {
+						const float4 o = pb.shO[idx], d = pb.shD[idx], c = pb.shC[idx];
+						const float maxDist = o.w;
+						slot	= __float_as_uint(d.w);
+						contrib = V3{c.x, c.y, c.z};
+						bool visible = true, decided = true;
+						if(maxDist > 0.0f) {
+							ray = rb_make_ray(V3{o.x, o.y, o.z}, V3{d.x, d.y, d.z});
+							++queries;
+							const float big = 1152921504606846976.0f; // 2^60, as rb_wide_ray_ok
+							if(ray.regular && fabsf(ray.inv.x) < big && fabsf(ray.inv.y) < big && fabsf(ray.inv.z) < big) {
+								rb_wide_init(T, bvh, 0.001f, maxDist, st);
+								active	= true;
+								decided = false;
+							} else {
+								RbTraversal B;
+								rb_traversal_init(B, bvh, 0.001f, maxDist, st);
+								while(!rb_step_ordered<true, false, false>(B, bvh, ray, st, nullptr)) {
+								}
+								visible = B.best.tri < 0;
+							}
+						}
+						if(decided && visible) {
+							float4 cl = pb.color[slot];
+							cl.x += contrib.x; cl.y += contrib.y; cl.z += contrib.z;
+							pb.color[slot] = cl;
+						}
+					}
+				}
+				exhausted = (base + (unsigned int)nIdle) >= n;
+			}
+		}
+		unsigned int activeM = __ballot_sync(0xffffffffu, active);
+		if(activeM == 0u) {
+			if(exhausted) break;
+			continue;
+		}
+		bool more;
+		do {
+			const bool wantsTri		 = active && rb_wide_wants_triangle(T);
+			const unsigned int triM	 = __ballot_sync(0xffffffffu, wantsTri);
+			const unsigned int nodeM = activeM & ~triM;
+			bool done = false;
+			if(__popc(triM) >= leafVotes || nodeM == 0u) {
+				if(wantsTri) done = rb_wide_phase_triangle<true>(T, wide, ray, st);
+			} else if(active && !wantsTri) {
+				done = rb_wide_phase_node(T, bvh, wide, ray, st);
+			}
+			if(done) {
+				if(T.best.tri < 0) {
+					float4 cl = pb.color[slot];
+					cl.x += contrib.x; cl.y += contrib.y; cl.z += contrib.z;
+					pb.color[slot] = cl;
+				}
+				active = false;
+			}
+			activeM = __ballot_sync(0xffffffffu, active);
+			more	= exhausted ? (activeM != 0u) : (__popc(activeM) >= threshold);
+		} while(more);
+	}
+	if(stats) {
+		for(int off = 16; off > 0; off >>= 1) queries += __shfl_down_sync(0xffffffffu, queries, off);
+		if(lane == 0 && queries) atomicAdd(stats + 1, (unsigned long long)queries);
+	}
+}
+
 // ------------------------------------------------------------------------------------------------ accumulation
 // `render.rgb(x,y) += glm::min(sampleColor, 5.0f)` (PathTracer.cpp:288): one warp per pixel sums the clamped samples of
 // the batch in a fixed order (lane-strided, then a shuffle tree), so the image is reproducible bit for bit.
@@ -723,7 +813,7 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 	}
 	rb_raycaster * rc	 = sc->raycaster;
 	const bool ordered	 = opts ? (opts->trace_mode == RB_TRACE_ORDERED) : false;
-	const bool wideTrace = opts && opts->trace_mode == RB_TRACE_WIDE; // closest-hit wavefront on the eight-wide tree (shadow rays keep the binary one)
+	const bool wideTrace = opts && opts->trace_mode == RB_TRACE_WIDE; // closest-hit wavefront — and, in unmasked scenes, the shadow wavefront — on the eight-wide tree
 	if(wideTrace && !rc->wideOnDevice) return rb_fail(RB_ERR_INVALID, "rb_pathtracer_render: trace_mode RB_TRACE_WIDE needs rb_raycaster_wide_build on the scene's raycaster first");
 	// Wavefront queues are shorter and more varied than the raycaster's batches: a slightly earlier refill and fewer
 	// node steps per vote measured best (tools/pt_sweep.sh); RB_FETCH_THRESHOLD / RB_NODE_STEPS override both.
@@ -783,6 +873,12 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 							  : (masked ? (ordered ? rb_k_pt_shadow<true, true, false> : rb_k_pt_shadow<true, false, false>) : rb_k_pt_shadow<false, true, false>);
 		st = rb_pt_grid(kShadow, smem, pt->sms, gridShadow);
 		if(st) return st;
+		const bool wideShadow  = wideTrace && !masked; // masked scenes need the closest occluder: binary kernel
+		unsigned gridShadowWide = 0;
+		if(wideShadow) {
+			st = rb_pt_grid(rb_k_pt_shadow_wide, smemWide, pt->sms, gridShadowWide);
+			if(st) return st;
+		}
 		const int votes = rc->leafVotes > 0 ? rc->leafVotes : 33;
 		const int steps = std::getenv("RB_NODE_STEPS") ? (rc->nodeSteps > 0 ? rc->nodeSteps : 1) : 4;
 
@@ -821,7 +917,8 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 							RB_CUDA(cudaEventRecord(pt->shaded[l], ls));
 							RB_CUDA(cudaStreamWaitEvent(ss, pt->shaded[l], 0));
 						}
-						kShadow<<<gridShadow, RB_PT_BLOCK, smem, ss>>>(rc->dev, pb, sc->dev, did, threshold, votes, steps, pt->d_stats);
+						if(wideShadow) rb_k_pt_shadow_wide<<<gridShadowWide, RB_PT_BLOCK, smemWide, ss>>>(rc->dev, rc->devWide, pb, did, threshold, votes > 32 ? 6 : votes, pt->d_stats);
+						else kShadow<<<gridShadow, RB_PT_BLOCK, smem, ss>>>(rc->dev, pb, sc->dev, did, threshold, votes, steps, pt->d_stats);
 						if(ss != ls) {
 							RB_CUDA(cudaEventRecord(pt->shadowed[l], ss));
 							shadowPending = true;
