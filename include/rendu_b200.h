@@ -249,7 +249,9 @@ typedef struct rb_light_desc {
 
 RB_API rb_status rb_scene_create(rb_scene ** out);
 RB_API void rb_scene_destroy(rb_scene * sc);
-/* Image as the reference holds it on the CPU: float pixels, row-major, `components` (3 or 4) per texel. */
+/* Image as the reference holds it on the CPU: float pixels, row-major, `components` (3 or 4) per texel. The texel pool
+ * goes to the device at rb_scene_commit: a texture (or object) added to a committed scene un-commits it, and rendering,
+ * rb_scene_sync and rb_pathtracer_create fail with RB_ERR_INVALID until rb_scene_commit runs again. */
 RB_API rb_status rb_scene_add_texture(rb_scene * sc, const float * pixels, uint32_t width, uint32_t height, uint32_t components, int32_t * out_id);
 /* Objects must be added in scene->objects order (PathTracer.cpp:13-18): the call index is the meshId. */
 RB_API rb_status rb_scene_add_object(rb_scene * sc, const rb_object_desc * desc);
@@ -271,7 +273,9 @@ RB_API rb_status rb_scene_sync(rb_scene * sc);
  * the hierarchy on the device (same topology, rb_raycaster_update_mesh + rb_raycaster_refit) and rewrites the object's
  * normal matrix; textures, attributes and the other objects are untouched. */
 RB_API rb_status rb_scene_set_object_transform(rb_scene * sc, uint32_t object, const float model[16]);
-/* The scene's raycaster (owned by the scene) — PathTracer::raycaster(). */
+/* The scene's raycaster (owned by the scene) — PathTracer::raycaster(). Queries, rb_raycaster_wide_build and refits are
+ * fine; a rb_raycaster_build on it reorders the triangles under the per-triangle shading records gathered at commit, and
+ * the next render then fails with RB_ERR_INVALID until the scene is committed again. */
 RB_API rb_raycaster * rb_scene_raycaster(rb_scene * sc);
 
 /* ------------------------------------------------------------------------------------------------ path tracer

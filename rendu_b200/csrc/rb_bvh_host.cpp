@@ -557,6 +557,29 @@ bool rb_host_flatten(const rb_raycaster * rc, RbFlatBvh & out, std::string * why
 		out.leafParent.push_back(link);
 		out.leafCode.push_back(int((uint32_t(n.left) << RB_LEAF_BITS) | uint32_t(n.right - 1)));
 	};
+	// Every interior record is dereferenced below, reachable from a root or not (an uploaded hierarchy is caller data).
+	for(size_t i = 0; i < nn; ++i) {
+		const rb_node & n = rc->nodes[i];
+		if(n.leaf) {
+			if(n.right > RB_LEAF_MAX_TRIS || n.left + n.right > nt) {
+				if(why) *why = "leaf " + std::to_string(i) + " holds a triangle range outside the triangle array (or more than " + std::to_string(RB_LEAF_MAX_TRIS) + " triangles)";
+				return false;
+			}
+			continue;
+		}
+		if(n.left >= nn || n.right >= nn) {
+			if(why) *why = "interior node " + std::to_string(i) + " has a child index outside the node array";
+			return false;
+		}
+		for(const uint64_t c : {n.left, n.right}) {
+			// An empty leaf below an interior node would never report to its parent's arrival counter: a refit would
+			// silently stop fitting that subtree's ancestors. The reference never creates one (Raycaster.cpp:88-91).
+			if(rc->nodes[c].leaf && rc->nodes[c].right == 0) {
+				if(why) *why = "interior node " + std::to_string(i) + " has an empty leaf as a child";
+				return false;
+			}
+		}
+	}
 	for(size_t i = 0; i < nn; ++i) {
 		const rb_node & n = rc->nodes[i];
 		if(n.leaf) continue;

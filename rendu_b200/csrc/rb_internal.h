@@ -81,6 +81,7 @@ struct rb_raycaster {
 	std::vector<uint64_t> meshVertFirst, meshVerts; // per mesh: first vertex and vertex count in `verts` (addMesh order)
 	int maxDepth	   = 0; // max number of interior nodes on a root-to-leaf path
 	bool built		   = false;
+	uint64_t buildSerial = 0; // counts successful builds / uploads: the triangle order changed (rb_scene keys its per-triangle records to it)
 	bool hostMirrorStale = false; // device tree newer than the host mirror (after LBVH build / refit)
 	bool triBoxesStale	 = false; // `verts` changed since the boxes in `tris` were computed (refit): redone before a rebuild
 

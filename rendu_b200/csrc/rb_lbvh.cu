@@ -615,6 +615,7 @@ rb_status rb_lbvh_build(rb_raycaster * rc) {
 	}
 	rc->launches += launches;
 	rc->built			= true;
+	rc->buildSerial++;
 	rc->hostMirrorStale = true;
 	return RB_OK;
 }

@@ -812,6 +812,10 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 		if(st) return st;
 	}
 	rb_raycaster * rc	 = sc->raycaster;
+	if(!sc->committed || !sc->geometryCommitted) return rb_fail(RB_ERR_INVALID, "rb_pathtracer_render: the scene changed since rb_scene_commit (a texture or an object was added): commit it again");
+	// rb_scene_raycaster() hands out the scene's raycaster; a build on it reorders the triangles under the per-triangle
+	// shading records gathered at commit.
+	if(!rc->built || rc->buildSerial != sc->triShadeSerial) return rb_fail(RB_ERR_INVALID, "rb_pathtracer_render: the hierarchy of the scene's raycaster was rebuilt outside rb_scene_commit: commit the scene again");
 	const bool ordered	 = opts ? (opts->trace_mode == RB_TRACE_ORDERED) : false;
 	const bool wideTrace = opts && opts->trace_mode == RB_TRACE_WIDE; // closest-hit wavefront — and, in unmasked scenes, the shadow wavefront — on the eight-wide tree
 	if(wideTrace && !rc->wideOnDevice) return rb_fail(RB_ERR_INVALID, "rb_pathtracer_render: trace_mode RB_TRACE_WIDE needs rb_raycaster_wide_build on the scene's raycaster first");

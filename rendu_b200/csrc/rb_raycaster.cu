@@ -716,6 +716,10 @@ void rb_raycaster_free_device(rb_raycaster * rc) {
 	rc->d_triIds	 = nullptr;
 	rc->dev		   = RbDeviceBvh{};
 	rc->device	   = -1;
+	// No device tree, nothing to query: a rebuild or upload that fails half-way must leave a handle that answers
+	// "hierarchy not built", not one whose kernels run on null pointers. Set again at the end of a successful upload.
+	rc->built = false;
+	if(rc->traceMode == RB_TRACE_WIDE) rc->traceMode = RB_TRACE_EXACT;
 	cudaSetDevice(previous);
 }
 
@@ -758,6 +762,7 @@ rb_status rb_raycaster_upload_flat(rb_raycaster * rc, const RbFlatBvh & flat) {
 	if(st) return st;
 	RB_CUDA(cudaStreamSynchronize(cudaStreamPerThread));
 	rc->built		   = true;
+	rc->buildSerial++;
 	rc->hostMirrorStale = false;
 	return RB_OK;
 }
@@ -826,6 +831,7 @@ static void rb_triangle_box(rb_tri & ti, const float * verts) {
 
 extern "C" rb_status rb_raycaster_add_mesh(rb_raycaster * rc, const float * positions, size_t nverts, const uint32_t * indices, size_t nindices, const float * model) {
 	if(!rc || (!positions && nverts) || (!indices && nindices)) return rb_fail(RB_ERR_INVALID, "rb_raycaster_add_mesh: null argument");
+	if(rc->meshFirst.size() != rc->meshCount) return rb_fail(RB_ERR_INVALID, "rb_raycaster_add_mesh: the uploaded hierarchy on this handle mixes its meshes under %u root(s); meshes cannot be appended to it", rc->meshCount);
 	const size_t indexOffset = rc->verts.size() / 3;
 	rc->verts.resize((indexOffset + nverts) * 3);
 	rb_transform_positions(rc->verts.data() + indexOffset * 3, positions, nverts, model);
@@ -896,6 +902,7 @@ extern "C" rb_status rb_raycaster_build(rb_raycaster * rc, rb_build_mode mode) {
 		});
 		rc->triBoxesStale = false;
 	}
+	if(rc->meshFirst.size() != rc->meshCount || rc->meshTris.size() != rc->meshCount) return rb_fail(RB_ERR_INVALID, "rb_raycaster_build: the uploaded hierarchy on this handle mixes its meshes under %u root(s); there are no per-mesh triangle ranges to rebuild from", rc->meshCount);
 	if(mode == RB_BUILD_REFERENCE || mode == RB_BUILD_SAH) {
 		// The host mirror is built first so that it can be read back (rb_raycaster_download_bvh) even on a machine
 		// without a GPU; tracing still needs the device copy.
@@ -913,6 +920,41 @@ extern "C" rb_status rb_raycaster_build(rb_raycaster * rc, rb_build_mode mode) {
 	return rb_fail(RB_ERR_INVALID, "rb_raycaster_build: unknown mode %d", int(mode));
 }
 
+static bool rb_reconstruct_mesh_ranges(rb_raycaster * rc, std::string * why) {
+	const size_t nt = rc->tris.size(), nv = rc->verts.size() / 3, nm = rc->meshCount;
+	rc->meshFirst.assign(nm, 0);
+	rc->meshTris.assign(nm, 0);
+	rc->meshVertFirst.assign(nm, 0);
+	rc->meshVerts.assign(nm, 0);
+	std::vector<uint64_t> vmin(nm, UINT64_MAX);
+	size_t t = 0;
+	for(size_t m = 0; m < nm; ++m) {
+		rc->meshFirst[m] = t;
+		while(t < nt && rc->tris[t].meshId == m) {
+			const rb_tri & ti = rc->tris[t++];
+			vmin[m] = std::min(vmin[m], std::min(uint64_t(ti.v0), std::min(uint64_t(ti.v1), uint64_t(ti.v2))));
+		}
+		rc->meshTris[m] = t - rc->meshFirst[m];
+	}
+	if(t != nt) {
+		*why = "triangle " + std::to_string(t) + " carries mesh id " + std::to_string(rc->tris[t].meshId) + ": the triangles of a mesh must be contiguous and the meshes in order, with ids below mesh_count";
+		return false;
+	}
+	// Vertex ranges: mesh m starts at the lowest vertex its triangles use (vertices nobody uses stay with the mesh before).
+	uint64_t next = nv;
+	for(size_t m = nm; m-- > 0;) {
+		const uint64_t first = m == 0 ? 0 : std::min(vmin[m], next);
+		if(first > next) {
+			*why = "vertex indices of mesh " + std::to_string(m) + " out of range";
+			return false;
+		}
+		rc->meshVertFirst[m] = first;
+		rc->meshVerts[m]	 = next - first;
+		next				 = first;
+	}
+	return true;
+}
+
 extern "C" rb_status rb_raycaster_upload_bvh(rb_raycaster * rc, const rb_node * nodes, size_t nnodes, const rb_tri * tris, size_t ntris, const float * vertices, size_t nverts, uint32_t mesh_count) {
 	if(!rc || (!nodes && nnodes) || (!tris && ntris) || (!vertices && nverts)) return rb_fail(RB_ERR_INVALID, "rb_raycaster_upload_bvh: null argument");
 	RB_REQUIRE_DEVICE();
@@ -927,6 +969,18 @@ extern "C" rb_status rb_raycaster_upload_bvh(rb_raycaster * rc, const rb_node * 
 	rc->meshCount = mesh_count;
 	rc->buildMode = RB_BUILD_REFERENCE;
 	std::string why;
+	// The per-mesh triangle and vertex ranges that rb_raycaster_add_mesh keeps (a later rb_raycaster_build restarts from
+	// them, a later add_mesh appends to them) are reconstructed from the records: addMesh appends, and the reference's
+	// build permutes triangles inside their mesh's range only (Raycaster.cpp:30-46,100-125), so both are contiguous and in
+	// mesh order in any hierarchy the reference could have produced.
+	// A hierarchy with mixed meshes under one root (a downloaded LBVH tree) has no such ranges: it can be traced, re-fitted
+	// and read back, but rb_raycaster_build(REFERENCE / SAH) and rb_raycaster_add_mesh on this handle fail with a clear error.
+	if(!rb_reconstruct_mesh_ranges(rc, &why)) {
+		rc->meshFirst.clear();
+		rc->meshTris.clear();
+		rc->meshVertFirst.clear();
+		rc->meshVerts.clear();
+	}
 	const int depth = rb_host_tree_depth(rc, &why);
 	if(depth < 0) return rb_fail(RB_ERR_INVALID, "rb_raycaster_upload_bvh: %s", why.c_str());
 	rc->maxDepth = depth;

@@ -60,6 +60,10 @@ extern "C" rb_status rb_scene_add_texture(rb_scene * sc, const float * pixels, u
 	}
 	*out_id = int32_t(sc->textures.size());
 	sc->textures.push_back(ti);
+	// The texel pool on the device is uploaded by rb_scene_commit only: a texture added afterwards exists on the host alone,
+	// so the scene counts as uncommitted until the next commit (rb_scene_sync and rendering refuse it until then).
+	sc->committed		  = false;
+	sc->geometryCommitted = false;
 	return RB_OK;
 }
 
@@ -271,6 +275,7 @@ extern "C" rb_status rb_scene_commit(rb_scene * sc, rb_build_mode mode) {
 	for(int k = 0; k < 6; ++k) dv.bgTex[k] = sc->bgTex[k];
 	dv.skyLut	 = sc->skyLut;
 	dv.anyMasked = anyMasked ? 1u : 0u;
+	sc->triShadeSerial	  = sc->raycaster->buildSerial;
 	sc->committed		  = true;
 	sc->geometryCommitted = true;
 	sc->tablesDirty		  = false;

@@ -26,6 +26,7 @@ struct rb_scene {
 	int32_t skyLut	 = -1;
 	bool committed	 = false;
 	bool geometryCommitted = false; // objects/textures are on the device; lights / background may still be stale
+	uint64_t triShadeSerial = 0;	// rb_raycaster::buildSerial the per-triangle shading records were gathered for
 	bool tablesDirty = false;		// lights or background changed since the last upload (rb_scene_sync)
 
 	rb_raycaster * raycaster = nullptr;

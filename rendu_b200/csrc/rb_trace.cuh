@@ -137,6 +137,22 @@ RB_D float4 rb_ldg4(const float4 * p) {
 	return __ldg(p);
 }
 
+// A 64-byte interior node as two 256-bit loads (LDG.E.256, sm_100 / PTX 8.8) instead of four 128-bit ones: a divergent
+// load costs one L1 data-pipe wavefront per lane and request whatever its width (up to the 32-byte sector), and that pipe
+// is what bounds the incoherent launches. Same bytes, same read-only path: results are unchanged.
+#ifndef RB_HOST_CHECK
+RB_D void rb_ldg_node(const float4 * n, float4 & n0, float4 & n1, float4 & n2, float4 & n3) {
+#if defined(RB_NODE_LDG128)
+	n0 = __ldg(n); n1 = __ldg(n + 1); n2 = __ldg(n + 2); n3 = __ldg(n + 3);
+#else
+	asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		: "=f"(n0.x), "=f"(n0.y), "=f"(n0.z), "=f"(n0.w), "=f"(n1.x), "=f"(n1.y), "=f"(n1.z), "=f"(n1.w) : "l"(n));
+	asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		: "=f"(n2.x), "=f"(n2.y), "=f"(n2.z), "=f"(n2.w), "=f"(n3.x), "=f"(n3.y), "=f"(n3.z), "=f"(n3.w) : "l"(n + 2));
+#endif
+}
+#endif
+
 // Closest hit / any hit in the REFERENCE ORDER: roots pre-tested against the caller's (mini, maxi) and consumed last
 // mesh first, depth-first with the right child popped before the left, `maxi` shrinking on every accepted hit
 // (strict <, so the first triangle found wins exact ties). Equivalent, decision for decision, to the std::stack loop
@@ -223,7 +239,10 @@ RB_D int rb_next_root(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ra
 		const float4 r0 = rb_ldg4(bvh.roots + 2 * r);
 		const float4 r1 = rb_ldg4(bvh.roots + 2 * r + 1);
 		if(COUNT) work->roots++;
-		if(rb_box_test_t<REGULAR>(ray, r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, T.mini, maxi)) return __float_as_int(r0.w);
+		// A mesh without triangles has a root with no reference (and a box the symmetric slab test cannot be trusted to
+		// reject): it is skipped, not taken for "no roots left" — the meshes added before it still have to be tested.
+		const int ref = __float_as_int(r0.w);
+		if(ref != RB_REF_NONE && rb_box_test_t<REGULAR>(ray, r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, T.mini, maxi)) return ref;
 	}
 	return RB_REF_NONE;
 }
@@ -245,7 +264,8 @@ RB_D bool rb_step_exact(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & 
 	// Descend while on interior nodes.
 	while(cur >= 0 && cur != RB_REF_NONE) {
 		const float4 * n = bvh.nodes + 4 * (size_t)cur;
-		const float4 n0 = rb_ldg4(n), n1 = rb_ldg4(n + 1), n2 = rb_ldg4(n + 2), n3 = rb_ldg4(n + 3);
+		float4 n0, n1, n2, n3;
+		rb_ldg_node(n, n0, n1, n2, n3);
 		if(COUNT) work->interior++;
 		bool hitL, hitR;
 		float dL, dR;
@@ -335,7 +355,8 @@ RB_D bool rb_step_ordered(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay 
 	}
 	while(cur >= 0 && cur != RB_REF_NONE) {
 		const float4 * n = bvh.nodes + 4 * (size_t)cur;
-		const float4 n0 = rb_ldg4(n), n1 = rb_ldg4(n + 1), n2 = rb_ldg4(n + 2), n3 = rb_ldg4(n + 3);
+		float4 n0, n1, n2, n3;
+		rb_ldg_node(n, n0, n1, n2, n3);
 		if(COUNT) work->interior++;
 		float dL, dR;
 		bool hitL, hitR;
@@ -434,7 +455,8 @@ RB_D bool rb_phase_node_t(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay 
 	}
 	if(cur >= 0) {
 		const float4 * n = bvh.nodes + 4 * (size_t)cur;
-		const float4 n0 = rb_ldg4(n), n1 = rb_ldg4(n + 1), n2 = rb_ldg4(n + 2), n3 = rb_ldg4(n + 3);
+		float4 n0, n1, n2, n3;
+		rb_ldg_node(n, n0, n1, n2, n3);
 		if(COUNT) work->interior++;
 		const int refL = __float_as_int(n3.x), refR = __float_as_int(n3.y);
 		if(ORDERED) {

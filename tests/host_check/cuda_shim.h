@@ -49,3 +49,5 @@ static inline unsigned long long rb_submul2(unsigned long long a, unsigned long 
 	volatile float d0 = a0 - b0, d1 = a1 - b1; // two roundings per lane, never contracted
 	return rb_pack2(d0 * c0, d1 * c1);
 }
+// The node fetch of rb_trace.cuh (two 256-bit loads on the device): plain reads here.
+static inline void rb_ldg_node(const float4 * n, float4 & n0, float4 & n1, float4 & n2, float4 & n3) { n0 = n[0]; n1 = n[1]; n2 = n[2]; n3 = n[3]; }

@@ -372,3 +372,32 @@ def test_progressive_accumulation_on_device():
     torch.cuda.synchronize()
     full, _ = gpu_render(desc, cam, w, h, spp, 5, seed=5)
     np.testing.assert_allclose(d_img.cpu().numpy(), full, rtol=0, atol=2e-6)
+
+
+def test_scene_changes_after_the_commit_are_refused_until_recommitted():
+    """a texture added after the commit lives on the host only (its id would index past the device pool), and
+    a rebuild of the scene's raycaster reorders the triangles under the per-triangle shading records: both must make the
+    next render fail cleanly; a new commit repairs both."""
+    desc, cam = wl.tiny_scene(), wl.tiny_camera()
+    sc = rpt.Scene(desc)
+    pt = rpt.PathTracer(sc)
+    a = np.zeros((16, 16, 3), np.float32)
+    pt.render(cam, 4, 3, a, rpt.make_opts(seed=1))
+    tex = np.full((4, 4, 4), 0.5, np.float32)
+    out = C.c_int32(-1)
+    check(lib().rb_scene_add_texture(sc._h, ptr(tex), 4, 4, 4, C.byref(out)))
+    with pytest.raises(rb.RenduError):
+        pt.render(cam, 4, 3, np.zeros((16, 16, 3), np.float32), rpt.make_opts(seed=1))
+    with pytest.raises(rb.RenduError):
+        check(lib().rb_scene_sync(sc._h))
+    check(lib().rb_scene_commit(sc._h, rb.BUILD_REFERENCE))
+    b = np.zeros((16, 16, 3), np.float32)
+    pt.render(cam, 4, 3, b, rpt.make_opts(seed=1))
+    assert np.array_equal(a, b)
+    sc.raycaster().updateHierarchy(rb.BUILD_LBVH)  # behind the scene's back
+    with pytest.raises(rb.RenduError):
+        pt.render(cam, 4, 3, np.zeros((16, 16, 3), np.float32), rpt.make_opts(seed=1))
+    check(lib().rb_scene_commit(sc._h, rb.BUILD_REFERENCE))
+    c = np.zeros((16, 16, 3), np.float32)
+    pt.render(cam, 4, 3, c, rpt.make_opts(seed=1))
+    assert np.array_equal(a, c)

@@ -317,3 +317,87 @@ def test_full_size_c2_properties_and_sampled_parity():
     sel = np.arange(0, co.shape[0], 401)
     ho = o.intersect(co[sel], cd[sel], threads=8)
     assert_hits_equal(h[sel], ho["hit"], ho["dist"], ho["u"], ho["v"], ho["w"], ho["localId"], ho["meshId"], "c2 sample")
+
+
+# ---------------------------------------------------------------------------------------------- robustness
+def _reference_arrays(c):
+    nodes = np.zeros(c["node_left"].size, rb.NODE_DTYPE)
+    nodes["bmin"], nodes["bmax"] = c["node_box"][:, :3], c["node_box"][:, 3:]
+    nodes["left"], nodes["right"], nodes["leaf"] = c["node_left"], c["node_right"], c["node_leaf"]
+    tris = np.zeros(c["tri_local"].size, rb.TRI_DTYPE)
+    tris["v0"], tris["v1"], tris["v2"] = c["tri_v"][:, 0], c["tri_v"][:, 1], c["tri_v"][:, 2]
+    tris["localId"], tris["meshId"] = c["tri_local"], c["tri_mesh"]
+    return nodes, tris
+
+
+@pytest.mark.parametrize("mode", [rb.TRACE_EXACT, rb.TRACE_ORDERED, rb.TRACE_WIDE])
+def test_empty_mesh_does_not_hide_the_meshes_before_it(mode):
+    """A mesh without triangles added after real ones: its root must be skipped, not read as 'no roots left' (roots are
+    consumed last mesh first). Rays through the cube [-1,1]^3 around the origin are the ones a symmetric slab test would
+    let into the empty root's box."""
+    pos, idx = wl.displaced_grid(24)
+    org, dirs = wl.random_rays(20000, 5)
+    co, cd = wl.coherent_rays(64)
+    org, dirs = np.concatenate([org, co]), np.concatenate([dirs, cd])
+    plain = rb.Raycaster()
+    plain.addMesh(pos, idx)
+    plain.updateHierarchy()
+    want, want_any = plain.intersects(org, dirs), plain.intersectsAny(org, dirs)
+    assert int(want["hit"].sum()) > 5000
+    r = rb.Raycaster()
+    r.addMesh(pos, idx)
+    r.addMesh(np.zeros((0, 3), np.float32), np.zeros(0, np.uint32))
+    r.addMesh(np.zeros((3, 3), np.float32), np.zeros(0, np.uint32))  # vertices, no triangle
+    r.updateHierarchy()
+    if mode == rb.TRACE_WIDE:
+        r.build_wide()
+    r.set_trace_mode(mode)
+    got, got_any = r.intersects(org, dirs), r.intersectsAny(org, dirs)
+    assert np.array_equal(got_any, want_any)
+    for f in ("hit", "dist", "u", "v", "w", "localId", "meshId"):
+        assert np.array_equal(got[f], want[f]), f
+
+
+def test_rebuild_and_add_mesh_after_an_upload():
+    """rb_raycaster_upload_bvh reconstructs the per-mesh ranges, so a later build or add_mesh on the same handle works on
+    consistent tables (it used to index empty vectors); a hierarchy that mixes its meshes under one root refuses both."""
+    c = load_case("raycast_multimesh")
+    nodes, tris = _reference_arrays(c)
+    r = rb.Raycaster()
+    r.upload_bvh(nodes, tris, c["verts"], int(c["mesh_count"]))
+    r.updateHierarchy()  # rebuild from the uploaded triangles: the reference's tree again
+    h = r.intersects(c["org"], c["dirs"], float(c["mini"]), float(c["maxi"]))
+    assert_hits_equal(h, c["hit"], c["dist"], c["u"], c["v"], c["w"], c["local_id"], c["mesh_id"], "rebuilt after upload")
+    pos, idx = wl.displaced_grid(4)
+    r.addMesh(pos * np.float32(0.01) + np.float32(50.0), idx)  # far away: the golden hits stay
+    r.updateHierarchy()
+    assert r.sizes()["meshes"] == int(c["mesh_count"]) + 1
+    h = r.intersects(c["org"], c["dirs"], float(c["mini"]), float(c["maxi"]))
+    assert_hits_equal(h, c["hit"], c["dist"], c["u"], c["v"], c["w"], c["local_id"], c["mesh_id"], "mesh appended after upload")
+    # one LBVH root over two meshes, read back and uploaded again: traceable, but no ranges to rebuild from
+    l = product_from_case(c, rb.BUILD_LBVH)
+    n2, t2, v2 = l.download_bvh()
+    u = rb.Raycaster()
+    u.upload_bvh(n2, t2, v2, l.sizes()["meshes"])
+    assert np.array_equal(u.intersects(c["org"], c["dirs"])["hit"], l.intersects(c["org"], c["dirs"])["hit"])
+    if len(np.unique(t2["meshId"])) > 1 and l.sizes()["meshes"] == 1:
+        with pytest.raises(rb.RenduError):
+            u.updateHierarchy()
+        with pytest.raises(rb.RenduError):
+            u.addMesh(pos, idx)
+
+
+def test_upload_rejects_garbage_records_outside_the_forest_and_failed_uploads_leave_no_tree():
+    c = load_case("raycast_grid37")
+    nodes, tris = _reference_arrays(c)
+    r = rb.Raycaster()
+    r.upload_bvh(nodes, tris, c["verts"], int(c["mesh_count"]))
+    assert r.intersects(c["org"][:8], c["dirs"][:8]).size == 8
+    bad = np.concatenate([nodes, np.zeros(1, rb.NODE_DTYPE)])  # an interior record no root reaches, children out of range
+    bad[-1]["left"], bad[-1]["right"], bad[-1]["leaf"] = 10 ** 9, 10 ** 9 + 1, 0
+    with pytest.raises(rb.RenduError):
+        r.upload_bvh(bad, tris, c["verts"], int(c["mesh_count"]))
+    with pytest.raises(rb.RenduError):  # the failed upload took the old device tree with it: a clean error, no kernel on null pointers
+        r.intersects(c["org"][:8], c["dirs"][:8])
+    r.upload_bvh(nodes, tris, c["verts"], int(c["mesh_count"]))
+    assert r.intersects(c["org"][:8], c["dirs"][:8]).size == 8
