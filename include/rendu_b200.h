@@ -307,8 +307,26 @@ typedef struct rb_render_opts {
 	 * to d_sum instead of overwriting it, so a viewer can trace one slice of the stratification grid per frame
 	 * (sample_index = frame % sample_count) and resolve what it has so far with samples = cells traced so far. */
 	uint32_t accumulate;
-	uint32_t _reserved[4];
+	/* All GPUs of the box from one call (rb_pathtracer_render only; replaces System::forParallel, System.hpp:72-104,
+	 * PathTracer.cpp:186): gpus > 1 replicates the scene on that many devices at the first such render (one host thread
+	 * per GPU) and splits every frame among them — RB_SPLIT_TILE: bands of tile_rows rows (0 = 2) dealt round-robin,
+	 * gathered on the path tracer's own device with strided peer copies, bit-identical to one GPU; RB_SPLIT_SAMPLE:
+	 * stratification cells dealt round-robin, per-pixel sums combined with one ncclReduce over NVLink (NCCL is loaded at
+	 * run time; RB_SAMPLE_REDUCE=p2p sums over peer memory inside the resolve kernel instead), equal to one GPU up to
+	 * fp32 summation order. tile_count / sample_count must stay 0 then. 0 or 1: this device only. */
+	uint32_t gpus;
+	uint32_t split; /* rb_split */
+	uint32_t _reserved[2];
 } rb_render_opts;
+
+typedef enum rb_split { RB_SPLIT_TILE = 0, RB_SPLIT_SAMPLE = 1 } rb_split;
+
+/* Timing of the last multi-GPU render of a path tracer: the slowest GPU's share (CUDA events on its stream) and the
+ * combine step on the root device (band copies or reduce, plus the resolve). */
+typedef struct rb_multi_stats {
+	uint32_t gpus, split, used_nccl, peer_access;
+	float render_ms, combine_ms;
+} rb_multi_stats;
 
 typedef struct rb_render_stats {
 	uint64_t rays_closest; /* primary + bounce queries (Raycaster::intersects from render) */
@@ -333,6 +351,21 @@ RB_API rb_status rb_pathtracer_render(rb_pathtracer * pt, const rb_camera * came
 RB_API rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_camera * camera, uint32_t width, uint32_t height, uint32_t samples, uint32_t depth, float * d_sum, const rb_render_opts * opts, void * stream);
 RB_API rb_status rb_pathtracer_resolve_device(rb_pathtracer * pt, const float * d_sum, uint32_t width, uint32_t height, uint32_t samples, uint32_t components, float * d_pixels, const rb_render_opts * opts, void * stream);
 RB_API rb_status rb_pathtracer_stats(const rb_pathtracer * pt, rb_render_stats * out);
+RB_API rb_status rb_pathtracer_multi_stats(rb_pathtracer * pt, rb_multi_stats * out);
+
+/* Measurement aid (the reference has no counterpart; bench.py's roofline uses it outside its timed regions): one frame
+ * rendered twice — once on a single stream with a CUDA event before every kernel, giving device milliseconds and launch
+ * counts per kernel class (0 ray generation, 1 closest-hit wavefront, 2 shading, 3 shadow wavefront, 4 accumulation),
+ * and once with counting copies of the two traversal kernels, giving the interior nodes / triangles / roots they test
+ * (the per-ray figures of DESIGN.md section 5). The image is discarded. */
+typedef struct rb_pt_profile {
+	double ms[5];
+	uint64_t launches[5];
+	uint64_t rays_closest, rays_shadow, shaded_hits, samples;
+	uint64_t trace_interior, trace_tris, trace_roots;
+	uint64_t shadow_interior, shadow_tris, shadow_roots;
+} rb_pt_profile;
+RB_API rb_status rb_pathtracer_profile_frame(rb_pathtracer * pt, const rb_camera * camera, uint32_t width, uint32_t height, uint32_t samples, uint32_t depth, const rb_render_opts * opts, rb_pt_profile * out);
 
 /* ------------------------------------------------------------------------------------------------ output stage
  * The headless `--render` tail: tonemap `1 - exp(-c)` (src/apps/pathtracer/main.cpp:109-116, only when

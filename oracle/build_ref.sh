@@ -61,6 +61,7 @@ compile "$SRC/libs/miniz/miniz.c" "$OUT/obj/miniz.o" "$CC" "-O2 -fPIC -w"
 compile "$SRC/libs/mikktspace/mikktspace.c" "$OUT/obj/mikktspace.o" "$CC" "-O2 -fPIC -w"
 compile "$HERE/ref_harness/ref_api.cpp" "$OUT/obj/ref_api.o" "$CXX" "$CXXFLAGS"
 compile "$HERE/ref_harness/ref_shim.cpp" "$OUT/obj/ref_shim.o" "$CXX" "$CXXFLAGS"
+compile "$HERE/ref_harness/ref_build_scene.cpp" "$OUT/obj/ref_build_scene.o" "$CXX" "$CXXFLAGS"
 for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
 
 WRAP="_ZNK9Raycaster10intersectsERKN3glm3vecILi3EfLNS0_9qualifierE0EEES5_ff"

@@ -366,6 +366,63 @@ class RefScene:
         return dict(objects=objects, lights=lights, background=bg, textures=textures)
 
 
+class RefBuiltScene:
+    """The reference's own Scene / PathTracer filled from a plain-array scene description (the dict layout of
+    rendu_b200.workloads / RefScene.flatten) through oracle/ref_harness/ref_build_scene.cpp: lets the UNMODIFIED
+    PathTracer::render be timed on the synthetic C3/C4 scene, which no .scene file describes. Point lights and colour /
+    cubemap backgrounds only (what that scene uses)."""
+
+    def __init__(self, desc):
+        L = lib()
+        L.ref_built_scene_create.restype = C.c_void_p
+        L.ref_built_scene_finish.restype = C.c_double
+        L.ref_built_scene_render.restype = C.c_double
+        self._h = C.c_void_p(L.ref_built_scene_create())
+        bg = desc["background"]
+        cube = [int(i) for i in bg.get("textures", [])] if int(bg["mode"]) == 2 else []
+        tex_id = {}
+        for i, t in enumerate(desc["textures"]):
+            if i in cube:
+                continue
+            t = np.ascontiguousarray(t, np.float32)
+            assert t.ndim == 3 and t.shape[2] == 4, "scene textures are RGBA on the host (Codable.cpp:143-161)"
+            tex_id[i] = L.ref_built_scene_add_texture(self._h, _p(t), t.shape[1], t.shape[0], 1)
+        bg_tex = -1
+        if cube:
+            faces = np.ascontiguousarray(np.stack([desc["textures"][i] for i in cube]), np.float32)
+            bg_tex = L.ref_built_scene_add_texture(self._h, _p(faces), faces.shape[2], faces.shape[1], 6)
+        elif int(bg["mode"]) == 1:
+            bg_tex = tex_id[int(bg["textures"][0])]
+        for o in desc["objects"]:
+            a = {k: np.ascontiguousarray(o[k], np.float32) for k in ("positions", "normals", "tangents", "bitangents", "texcoords")}
+            idx = np.ascontiguousarray(o["indices"], np.uint32).reshape(-1)
+            nv = a["positions"].reshape(-1, 3).shape[0]
+            uv = a["texcoords"] if a["texcoords"].size == 2 * nv else None
+            tex3 = np.array([tex_id.get(int(t), -1) if t is not None and int(t) >= 0 else -1 for t in (list(o["textures"]) + [-1, -1, -1])[:3]], np.int32)
+            model = np.ascontiguousarray(np.asarray(o["model"], np.float32).reshape(16))
+            L.ref_built_scene_add_object(self._h, _p(a["positions"]), _p(a["normals"]), _p(a["tangents"]), _p(a["bitangents"]), _p(uv), C.c_size_t(nv),
+                                         _p(idx), C.c_size_t(idx.size), _p(model), _p(tex3), int(o["material_type"]), int(bool(o["masked"])), int(bool(o["use_uv"])))
+        for l in desc["lights"]:
+            assert int(l["kind"]) == 0, "RefBuiltScene: point lights only"
+            L.ref_built_scene_add_point_light(self._h, _p(np.asarray(l["position"], np.float32)), _p(np.asarray(l["intensity"], np.float32)),
+                                              C.c_float(float(l["radius"])), int(bool(l["casts_shadow"])))
+        L.ref_built_scene_set_background(self._h, int(bg["mode"]), _p(np.asarray(bg.get("color", (0, 0, 0)), np.float32)), int(bg_tex))
+        self.build_seconds = float(L.ref_built_scene_finish(self._h))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().ref_built_scene_destroy(self._h)
+            self._h = None
+
+    def render(self, eye, center, up, fov, w, h, samples, depth, components=3):
+        """PathTracer::render with the reference's own Camera (pose + projection(ratio=w/h, fov)); image, seconds, rays."""
+        cam = np.array(list(eye) + list(center) + list(up) + [fov], np.float32)
+        px = np.zeros((h, w, components), np.float32)
+        lib().ref_ray_counter_reset()
+        dt = lib().ref_built_scene_render(self._h, _p(cam), w, h, samples, depth, components, _p(px))
+        return px, float(dt), int(lib().ref_ray_counter())
+
+
 def sky_lut():
     add_default_resources()
     L = lib()

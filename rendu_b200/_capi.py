@@ -44,12 +44,24 @@ class Camera(C.Structure):
 class RenderOpts(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("tile_rows", C.c_uint32), ("tile_index", C.c_uint32), ("tile_count", C.c_uint32),
                 ("sample_index", C.c_uint32), ("sample_count", C.c_uint32), ("trace_mode", C.c_uint32),
-                ("max_paths_in_flight", C.c_uint32), ("accumulate", C.c_uint32), ("_reserved", C.c_uint32 * 4)]
+                ("max_paths_in_flight", C.c_uint32), ("accumulate", C.c_uint32), ("gpus", C.c_uint32), ("split", C.c_uint32),
+                ("_reserved", C.c_uint32 * 2)]
 
 
 class RenderStats(C.Structure):
     _fields_ = [("rays_closest", C.c_uint64), ("rays_shadow", C.c_uint64), ("samples", C.c_uint64), ("shaded_hits", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("device_seconds", C.c_double)]
+
+
+class MultiStats(C.Structure):
+    _fields_ = [("gpus", C.c_uint32), ("split", C.c_uint32), ("used_nccl", C.c_uint32), ("peer_access", C.c_uint32),
+                ("render_ms", C.c_float), ("combine_ms", C.c_float)]
+
+
+class PtProfile(C.Structure):
+    _fields_ = [("ms", C.c_double * 5), ("launches", C.c_uint64 * 5), ("rays_closest", C.c_uint64), ("rays_shadow", C.c_uint64),
+                ("shaded_hits", C.c_uint64), ("samples", C.c_uint64), ("trace_interior", C.c_uint64), ("trace_tris", C.c_uint64),
+                ("trace_roots", C.c_uint64), ("shadow_interior", C.c_uint64), ("shadow_tris", C.c_uint64), ("shadow_roots", C.c_uint64)]
 
 
 _lib = None
@@ -119,6 +131,8 @@ def lib():
         "rb_pathtracer_render_device": (C.c_int, [vp, C.POINTER(Camera), u32, u32, u32, u32, vp, C.POINTER(RenderOpts), vp]),
         "rb_pathtracer_resolve_device": (C.c_int, [vp, vp, u32, u32, u32, u32, vp, C.POINTER(RenderOpts), vp]),
         "rb_pathtracer_stats": (C.c_int, [vp, C.POINTER(RenderStats)]),
+        "rb_pathtracer_multi_stats": (C.c_int, [vp, C.POINTER(MultiStats)]),
+        "rb_pathtracer_profile_frame": (C.c_int, [vp, C.POINTER(Camera), u32, u32, u32, u32, C.POINTER(RenderOpts), C.POINTER(PtProfile)]),
         "rb_output_ldr": (C.c_int, [vp, u32, u32, u32, C.c_int, C.c_int, vp]),
         "rb_output_ldr_device": (C.c_int, [vp, u32, u32, u32, C.c_int, C.c_int, vp, vp]),
         "rb_output_hdr": (C.c_int, [vp, u32, u32, u32, C.c_int, C.c_int, vp]),

@@ -526,7 +526,8 @@ int rb_host_tree_depth(const rb_raycaster * rc, std::string * why) {
 bool rb_host_flatten(const rb_raycaster * rc, RbFlatBvh & out, std::string * why) {
 	const size_t nn = rc->nodes.size();
 	const size_t nt = rc->tris.size();
-	if(nt >= (size_t(1) << (31 - RB_LEAF_BITS))) {
+	out.dummyTris = 0;
+	if(nt + 1 >= (size_t(1) << (31 - RB_LEAF_BITS))) {
 		if(why) *why = "too many triangles for 32-bit leaf references";
 		return false;
 	}
@@ -605,12 +606,18 @@ bool rb_host_flatten(const rb_raycaster * rc, RbFlatBvh & out, std::string * why
 		if(!n.leaf) out.parent[interiorIndex[m]] = ~int(m); // negative: a root, ~value = root slot
 		else addLeaf(m, ~int(m));
 		if(n.right == 0 && n.leaf) {
-			// Empty mesh: inverted box, never accepted.
-			d[0] = d[1] = d[2] = 1.0f;
-			d[4] = d[5] = d[6] = -1.0f;
+			// Empty mesh. Its root must not carry RB_REF_NONE: the traversal reads that value as "no roots left" and would
+			// never test the meshes added before it (roots are consumed last mesh first), and no box keeps every ray out —
+			// the slab test is symmetric in min / max. The root gets a leaf of ONE degenerate triangle instead (all zeros,
+			// appended after the real ones): det = 0 fails `abs(det) < FLT_EPSILON`, a NaN ray fails the final range test.
+			// The root's box is the point (0, 0, 0): a valid (if empty) box for the refit and wide-tree code.
+			d[0] = d[1] = d[2] = 0.0f;
+			d[4] = d[5] = d[6] = 0.0f;
+			d[3] = asFloat(~int(uint32_t(nt) << RB_LEAF_BITS));
+			out.dummyTris = 1;
 		}
 	}
-	out.tris.assign(nt * 12, 0.0f);
+	out.tris.assign((nt + out.dummyTris) * 12, 0.0f);
 	out.triVerts.resize(nt * 3);
 	out.triIds.resize(nt * 2);
 	const float * V = rc->verts.data();

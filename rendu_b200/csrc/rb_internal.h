@@ -152,6 +152,7 @@ struct RbFlatBvh {
 	std::vector<int> leafParent; // per leaf, same encoding
 	std::vector<int> leafCode;	 // per leaf: (first triangle << 3) | (count - 1)
 	std::vector<uint32_t> triIds; // (localId, meshId) per triangle
+	size_t dummyTris = 0;		  // degenerate records appended to `tris` (the leaf an empty mesh's root points at); not counted as triangles
 };
 bool rb_host_flatten(const rb_raycaster * rc, RbFlatBvh & out, std::string * why);
 

@@ -120,7 +120,23 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_raygen(RbFrame f, RbBatch
 
 // ------------------------------------------------------------------------------------------------ closest-hit wavefront
 // `_raycaster.intersects(rayPos, rayDir)` with the reference's default bounds (PathTracer.cpp:204, Raycaster.hpp:65).
-template<bool ORDERED, bool BLOCKS>
+// COUNT = true (rb_pathtracer_profile_frame only, never the timed path): the same kernel also counts the interior nodes,
+// triangles and roots it tests — the figures the roofline's algorithmic bytes are computed from — into stats[base..base+2].
+RB_D void rb_pt_flush_work(const RbWork & w, unsigned int lane, unsigned long long * stats, int base) {
+	unsigned int a = w.interior, b = w.tris, c = w.roots;
+	for(int off = 16; off > 0; off >>= 1) {
+		a += __shfl_down_sync(0xffffffffu, a, off);
+		b += __shfl_down_sync(0xffffffffu, b, off);
+		c += __shfl_down_sync(0xffffffffu, c, off);
+	}
+	if(lane == 0) {
+		atomicAdd(stats + base, (unsigned long long)a);
+		atomicAdd(stats + base + 1, (unsigned long long)b);
+		atomicAdd(stats + base + 2, (unsigned long long)c);
+	}
+}
+
+template<bool ORDERED, bool BLOCKS, bool COUNT = false>
 __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_trace(RbDeviceBvh bvh, RbPathBuffers pb, const uint32_t * __restrict__ queue, uint32_t did, int threshold, int leafVotes, int nodeSteps, unsigned long long * __restrict__ stats) {
 	extern __shared__ int s_stack[];
 	const RbStack st		= rb_make_stack(s_stack + threadIdx.x, blockDim.x);
@@ -128,6 +144,8 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_trace(RbDeviceBvh bvh, Rb
 	const unsigned int n	= pb.counters[rb_cnt_queue(did)];
 	unsigned int * cursor	= pb.counters + rb_cnt_cursor_t(did);
 	if(blockIdx.x == 0 && threadIdx.x == 0 && stats) atomicAdd(stats + 0, (unsigned long long)n);
+	RbWork work = {0u, 0u, 0u, 0u};
+	RbWork * const wp = COUNT ? &work : nullptr;
 	bool active = false, exhausted = false;
 	unsigned int slot = 0;
 	RbRay ray;
@@ -165,10 +183,10 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_trace(RbDeviceBvh bvh, Rb
 			const unsigned int nodeM = activeM & ~leafM;
 			bool finished = false;
 			if(__popc(leafM) >= leafVotes || nodeM == 0u) {
-				if(wantsLeaf) finished = rb_phase_leaf<false, false>(T, bvh, ray, nullptr);
+				if(wantsLeaf) finished = rb_phase_leaf<false, COUNT>(T, bvh, ray, wp);
 			} else if(active && !wantsLeaf) {
 				for(int k = 0; k < nodeSteps; ++k) {
-					finished = rb_phase_node<false, ORDERED, BLOCKS>(T, bvh, ray, st, nullptr);
+					finished = rb_phase_node<COUNT, ORDERED, BLOCKS>(T, bvh, ray, st, wp);
 					if(finished || rb_wants_leaf(T)) break;
 				}
 			}
@@ -180,6 +198,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_trace(RbDeviceBvh bvh, Rb
 			more	= exhausted ? (activeM != 0u) : (__popc(activeM) >= threshold);
 		} while(more);
 	}
+	if(COUNT && stats) rb_pt_flush_work(work, lane, stats, 4);
 }
 
 // The closest-hit wavefront on the eight-wide quantised tree (rb_render_opts.trace_mode = RB_TRACE_WIDE; experiment, see
@@ -393,7 +412,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK, RB_PT_SHADE_MIN_BLOCKS) rb_k_pt_s
 // unmasked (or UV-less) occluder blocks, a masked one is looked up in its alpha channel and walked through when
 // alpha < 0.01. When no object of the scene is masked the walk degenerates to "is there any hit", so the any-hit
 // traversal (identical accept/reject decisions, early exit) is used instead (MASKED = false).
-template<bool MASKED, bool ORDERED, bool BLOCKS>
+template<bool MASKED, bool ORDERED, bool BLOCKS, bool COUNT = false>
 __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shadow(RbDeviceBvh bvh, RbPathBuffers pb, RbSceneDev sc, uint32_t did, int threshold, int leafVotes, int nodeSteps, unsigned long long * __restrict__ stats) {
 	extern __shared__ int s_stack[];
 	const RbStack st		= rb_make_stack(s_stack + threadIdx.x, blockDim.x);
@@ -403,6 +422,8 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shadow(RbDeviceBvh bvh, R
 	bool active = false, exhausted = false;
 	unsigned int slot = 0;
 	unsigned int queries = 0;
+	RbWork work = {0u, 0u, 0u, 0u};
+	RbWork * const wp = COUNT ? &work : nullptr;
 	V3 lpos = v3(0.0f), dir = v3(0.0f), contrib = v3(0.0f);
 	float maxDist = 0.0f;
 	RbRay ray;
@@ -451,10 +472,10 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shadow(RbDeviceBvh bvh, R
 			const unsigned int nodeM = activeM & ~leafM;
 			bool done = false;
 			if(__popc(leafM) >= leafVotes || nodeM == 0u) {
-				if(wantsLeaf) done = rb_phase_leaf<!MASKED, false>(T, bvh, ray, nullptr);
+				if(wantsLeaf) done = rb_phase_leaf<!MASKED, COUNT>(T, bvh, ray, wp);
 			} else if(active && !wantsLeaf) {
 				for(int k = 0; k < nodeSteps; ++k) {
-					done = rb_phase_node<false, ORDERED, BLOCKS>(T, bvh, ray, st, nullptr);
+					done = rb_phase_node<COUNT, ORDERED, BLOCKS>(T, bvh, ray, st, wp);
 					if(done || rb_wants_leaf(T)) break;
 				}
 			}
@@ -500,6 +521,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shadow(RbDeviceBvh bvh, R
 	if(stats) {
 		for(int off = 16; off > 0; off >>= 1) queries += __shfl_down_sync(0xffffffffu, queries, off);
 		if(lane == 0 && queries) atomicAdd(stats + 1, (unsigned long long)queries);
+		if(COUNT) rb_pt_flush_work(work, lane, stats, 7);
 	}
 }
 
@@ -651,10 +673,23 @@ struct rb_pathtracer {
 	cudaStream_t side[RB_PT_LANES] = {}; // shadow wavefront of a lane: runs beside the next level's closest-hit wavefront
 	cudaEvent_t fork = nullptr, join[RB_PT_LANES] = {}, shaded[RB_PT_LANES] = {}, shadowed[RB_PT_LANES] = {};
 	int lanes = 2;
-	unsigned long long * d_stats = nullptr;
+	unsigned long long * d_stats = nullptr; // RB_PT_NSTATS counters (rays, shaded hits; the COUNT kernels' work counters)
 	rb_render_stats stats = {};
 	int sms = 0;
+	// rb_pathtracer_profile_frame: the frame runs on one stream, an event before every kernel (timing), or with the
+	// counting copies of the traversal kernels (counting). Null during ordinary renders.
+	struct Profile {
+		bool timing = false, counting = false;
+		std::vector<cudaEvent_t> events;
+		std::vector<int> kinds; // kernel class launched after events[k]
+	} * prof = nullptr;
+	void * multi = nullptr; // rb_multi.cu: replicas on the other GPUs of the box (rb_render_opts.gpus > 1)
 };
+
+rb_scene * rb_pt_scene(rb_pathtracer * pt) { return pt->scene; }
+void ** rb_pt_multi_slot(rb_pathtracer * pt) { return &pt->multi; }
+void rb_pt_set_stats(rb_pathtracer * pt, const rb_render_stats & s) { pt->stats = s; }
+#define RB_PT_NSTATS 12
 
 static void rb_pt_free(rb_pathtracer * pt) {
 	for(int l = 0; l < RB_PT_LANES; ++l) {
@@ -708,7 +743,7 @@ extern "C" rb_status rb_pathtracer_create(rb_scene * scene, rb_pathtracer ** out
 	rb_pathtracer * pt = new rb_pathtracer();
 	pt->scene		   = scene;
 	cudaDeviceGetAttribute(&pt->sms, cudaDevAttrMultiProcessorCount, scene->raycaster->device);
-	if(cudaMalloc(&pt->d_stats, 4 * sizeof(unsigned long long)) != cudaSuccess) {
+	if(cudaMalloc(&pt->d_stats, RB_PT_NSTATS * sizeof(unsigned long long)) != cudaSuccess) {
 		delete pt;
 		return rb_fail(RB_ERR_CUDA, "rb_pathtracer_create: cudaMalloc failed");
 	}
@@ -731,6 +766,10 @@ extern "C" rb_status rb_pathtracer_create(rb_scene * scene, rb_pathtracer ** out
 
 extern "C" void rb_pathtracer_destroy(rb_pathtracer * pt) {
 	if(!pt) return;
+	if(pt->multi) {
+		rb_pt_multi_destroy(pt->multi);
+		pt->multi = nullptr;
+	}
 	if(rb_have_device()) {
 		rb_pt_free(pt);
 		cudaFree(pt->d_stats);
@@ -824,7 +863,7 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 	const int threshold = std::getenv("RB_FETCH_THRESHOLD") ? rc->fetchThreshold : 16;
 	RB_CUDA(cudaSetDevice(rc->device));
 	if(!(opts && opts->accumulate)) RB_CUDA(cudaMemsetAsync(d_sum, 0, size_t(width) * height * 3 * sizeof(float), s));
-	RB_CUDA(cudaMemsetAsync(pt->d_stats, 0, 4 * sizeof(unsigned long long), s));
+	RB_CUDA(cudaMemsetAsync(pt->d_stats, 0, RB_PT_NSTATS * sizeof(unsigned long long), s));
 
 	const uint32_t localSamples = (f.samples > f.sampleIndex) ? (f.samples - f.sampleIndex + f.sampleCount - 1) / f.sampleCount : 0;
 	const uint64_t localPixels	= uint64_t(f.localRows) * width;
@@ -839,7 +878,17 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 		// One sample chunk per pixel (the usual case): batches touch disjoint pixels and may run on the two lanes. Frames
 		// worth splitting are cut into at least two batches.
 		const bool oneChunk = schunk == localSamples;
-		int lanes = oneChunk ? pt->lanes : 1;
+		const bool profTiming = pt->prof && pt->prof->timing, profCounting = pt->prof && pt->prof->counting;
+		int lanes = (oneChunk && !pt->prof) ? pt->lanes : 1;
+		auto mark = [&](int kind, cudaStream_t on) -> cudaError_t { // profile: an event before every kernel of the (single-stream) frame
+			if(!profTiming) return cudaSuccess;
+			cudaEvent_t e;
+			cudaError_t ce = cudaEventCreate(&e);
+			if(ce != cudaSuccess) return ce;
+			pt->prof->events.push_back(e);
+			pt->prof->kinds.push_back(kind);
+			return cudaEventRecord(e, on);
+		};
 		if(lanes > 1 && pixelsPerBatch * lanes > localPixels) {
 			// fewer batches than lanes: cut the frame into one batch per lane when it is worth it
 			if(localPixels * schunk >= (uint64_t(1) << 20)) pixelsPerBatch = (localPixels + lanes - 1) / lanes;
@@ -869,12 +918,14 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 		if(st) return st;
 		const bool blocks = rc->dev.rootLevels > 0; // many-mesh scenes: kernels compiled with the root-block skipping
 		auto kTrace = blocks ? (ordered ? rb_k_pt_trace<true, true> : rb_k_pt_trace<false, true>) : (ordered ? rb_k_pt_trace<true, false> : rb_k_pt_trace<false, false>);
+		if(profCounting) kTrace = ordered ? rb_k_pt_trace<true, false, true> : rb_k_pt_trace<false, false, true>; // plain root loop: same tests, counted
 		st = rb_pt_grid(kTrace, smem, pt->sms, gridTrace);
 		if(st) return st;
 		const bool masked = sc->dev.anyMasked != 0;
 		// Unmasked scenes use any-hit shadow rays, whose result is order independent: always near-child-first.
 		auto kShadow = blocks ? (masked ? (ordered ? rb_k_pt_shadow<true, true, true> : rb_k_pt_shadow<true, false, true>) : rb_k_pt_shadow<false, true, true>)
 							  : (masked ? (ordered ? rb_k_pt_shadow<true, true, false> : rb_k_pt_shadow<true, false, false>) : rb_k_pt_shadow<false, true, false>);
+		if(profCounting) kShadow = masked ? (ordered ? rb_k_pt_shadow<true, true, false, true> : rb_k_pt_shadow<true, false, false, true>) : rb_k_pt_shadow<false, true, false, true>;
 		st = rb_pt_grid(kShadow, smem, pt->sms, gridShadow);
 		if(st) return st;
 		const bool wideShadow  = wideTrace && !masked; // masked scenes need the closest occluder: binary kernel
@@ -903,17 +954,20 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 				const cudaStream_t ls	 = lanes > 1 ? pt->lane[l] : s;
 				const RbPathBuffers & pb = pt->pb[l];
 				RB_CUDA(cudaMemsetAsync(pb.counters, 0, 4 * (RB_PT_MAX_DEPTH + 1) * sizeof(uint32_t), ls));
+				RB_CUDA(mark(0, ls));
 				rb_k_pt_raygen<<<gridFlat, RB_PT_BLOCK, 0, ls>>>(f, b, pb);
 				++launches;
 				// The shadow wavefront of level d only feeds the colour that shade(d+1) reads, so it runs on a side stream
 				// next to trace(d+1): trace -> shade -> [shadow || next trace] -> shade ...
 				// (small batches stay on one stream: the event traffic would cost more than the overlap gives)
-				const cudaStream_t ss = (uint64_t(b.npixels) * b.schunk >= (uint64_t(1) << 20)) ? pt->side[l] : ls;
+				const cudaStream_t ss = (!pt->prof && uint64_t(b.npixels) * b.schunk >= (uint64_t(1) << 20)) ? pt->side[l] : ls;
 				bool shadowPending	  = false;
 				for(uint32_t did = 0; did < depth; ++did) {
+					RB_CUDA(mark(1, ls));
 					if(wideTrace) rb_k_pt_trace_wide<<<gridTraceWide, RB_PT_BLOCK, smemWide, ls>>>(rc->dev, rc->devWide, pb, pb.queue[did & 1u], did, threshold, votes > 32 ? 6 : votes, pt->d_stats);
 					else kTrace<<<gridTrace, RB_PT_BLOCK, smem, ls>>>(rc->dev, pb, pb.queue[did & 1u], did, threshold, votes, steps, pt->d_stats);
 					if(shadowPending) RB_CUDA(cudaStreamWaitEvent(ls, pt->shadowed[l], 0)); // shade overwrites the shadow entries
+					RB_CUDA(mark(2, ls));
 					rb_k_pt_shade<<<gridShade, RB_PT_BLOCK, 0, ls>>>(f, b, pb, sc->dev, did, pt->d_stats);
 					launches += 2;
 					if(sc->dev.nLights > 0) {
@@ -921,6 +975,7 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 							RB_CUDA(cudaEventRecord(pt->shaded[l], ls));
 							RB_CUDA(cudaStreamWaitEvent(ss, pt->shaded[l], 0));
 						}
+						RB_CUDA(mark(3, ss));
 						if(wideShadow) rb_k_pt_shadow_wide<<<gridShadowWide, RB_PT_BLOCK, smemWide, ss>>>(rc->dev, rc->devWide, pb, did, threshold, votes > 32 ? 6 : votes, pt->d_stats);
 						else kShadow<<<gridShadow, RB_PT_BLOCK, smem, ss>>>(rc->dev, pb, sc->dev, did, threshold, votes, steps, pt->d_stats);
 						if(ss != ls) {
@@ -931,8 +986,10 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 					}
 				}
 				if(shadowPending) RB_CUDA(cudaStreamWaitEvent(ls, pt->shadowed[l], 0));
+				RB_CUDA(mark(4, ls));
 				rb_k_pt_accumulate<<<gridFlat, RB_PT_BLOCK, 0, ls>>>(f, b, pb, d_sum);
 				++launches;
+				RB_CUDA(mark(5, ls)); // end of the batch
 				RB_CUDA(cudaGetLastError());
 			}
 		}
@@ -968,6 +1025,13 @@ extern "C" rb_status rb_pathtracer_render(rb_pathtracer * pt, const rb_camera * 
 	RB_REQUIRE_DEVICE();
 	if(components < 3) return rb_fail(RB_ERR_INVALID, "rb_pathtracer_render: expected an RGB image (components >= 3)"); // PathTracer.cpp:166-168
 	RB_CUDA(cudaSetDevice(pt->scene->raycaster->device));
+	if(opts && opts->gpus > 1) {
+		if(pt->scene->tablesDirty) { // the replicas are keyed to the edit counter: bring the primary up to date first
+			rb_status ss = rb_scene_sync(pt->scene);
+			if(ss) return ss;
+		}
+		return rb_pt_multi_render(pt, camera, width, height, samples, depth, components, pixels, opts);
+	}
 	cudaStream_t s = cudaStreamPerThread;
 	const size_t npx = size_t(width) * height;
 	float *d_sum = nullptr, *d_pixels = nullptr;
@@ -1004,6 +1068,50 @@ extern "C" rb_status rb_pathtracer_render(rb_pathtracer * pt, const rb_camera * 
 	cudaEventDestroy(e1);
 	cudaFree(d_sum);
 	cudaFree(d_pixels);
+	return st;
+}
+
+// One frame taken apart (bench.py's roofline; never part of a timed region): pass 1 runs the ordinary kernels on ONE
+// stream with an event before each (no second lane, no side stream, so the classes do not overlap and their times add
+// up to the serialised frame); pass 2 runs the counting copies of the two traversal kernels.
+extern "C" rb_status rb_pathtracer_profile_frame(rb_pathtracer * pt, const rb_camera * camera, uint32_t width, uint32_t height, uint32_t samples, uint32_t depth, const rb_render_opts * opts, rb_pt_profile * out) {
+	if(!pt || !camera || !out) return rb_fail(RB_ERR_INVALID, "rb_pathtracer_profile_frame: null argument");
+	RB_REQUIRE_DEVICE();
+	std::memset(out, 0, sizeof(*out));
+	RB_CUDA(cudaSetDevice(pt->scene->raycaster->device));
+	float * d_sum = nullptr;
+	RB_CUDA(cudaMalloc(&d_sum, size_t(width) * height * 3 * sizeof(float)));
+	rb_pathtracer::Profile prof;
+	cudaStream_t s = cudaStreamPerThread;
+	rb_status st   = RB_OK;
+	for(int pass = 0; pass < 2 && !st; ++pass) {
+		prof.timing	  = pass == 0;
+		prof.counting = pass == 1;
+		pt->prof	  = &prof;
+		st			  = rb_pathtracer_render_device(pt, camera, width, height, samples, depth, d_sum, opts, s);
+		pt->prof	  = nullptr;
+		if(st) break;
+		if(cudaStreamSynchronize(s) != cudaSuccess) { st = rb_fail(RB_ERR_CUDA, "rb_pathtracer_profile_frame: %s", cudaGetErrorString(cudaGetLastError())); break; }
+		if(pass == 0) {
+			for(size_t k = 0; k + 1 < prof.events.size(); ++k) {
+				const int kind = prof.kinds[k];
+				if(kind > 4) continue; // batch end marker -> next batch's first event: nothing in between
+				float ms = 0.0f;
+				cudaEventElapsedTime(&ms, prof.events[k], prof.events[k + 1]);
+				out->ms[kind] += ms;
+				out->launches[kind] += 1;
+			}
+		} else {
+			unsigned long long hs[RB_PT_NSTATS];
+			if(cudaMemcpy(hs, pt->d_stats, sizeof(hs), cudaMemcpyDeviceToHost) != cudaSuccess) { st = rb_fail(RB_ERR_CUDA, "rb_pathtracer_profile_frame: counters unreadable"); break; }
+			out->rays_closest = hs[0]; out->rays_shadow = hs[1]; out->shaded_hits = hs[2];
+			out->trace_interior = hs[4]; out->trace_tris = hs[5]; out->trace_roots = hs[6];
+			out->shadow_interior = hs[7]; out->shadow_tris = hs[8]; out->shadow_roots = hs[9];
+			out->samples = pt->stats.samples;
+		}
+	}
+	for(cudaEvent_t e : prof.events) cudaEventDestroy(e);
+	cudaFree(d_sum);
 	return st;
 }
 

@@ -728,7 +728,7 @@ rb_status rb_raycaster_upload_flat(rb_raycaster * rc, const RbFlatBvh & flat) {
 	rb_raycaster_free_device(rc);
 	RB_CUDA(cudaGetDevice(&rc->device));
 	rc->nInterior = flat.nodes.size() / 16;
-	rc->nTris	  = flat.tris.size() / 12;
+	rc->nTris	  = flat.tris.size() / 12 - flat.dummyTris;
 	rc->nVerts	  = rc->verts.size() / 3;
 	// Allocations are padded so that empty arrays still give valid pointers.
 	RB_CUDA(cudaMalloc(&rc->d_nodes, flat.nodes.size() * sizeof(float) + 64));

@@ -42,6 +42,7 @@ extern "C" void rb_scene_destroy(rb_scene * sc) {
 }
 
 extern "C" rb_status rb_scene_add_texture(rb_scene * sc, const float * pixels, uint32_t width, uint32_t height, uint32_t components, int32_t * out_id) {
+	if(sc) sc->editSerial++;
 	if(!sc || !pixels || !out_id) return rb_fail(RB_ERR_INVALID, "rb_scene_add_texture: null argument");
 	if(width == 0 || height == 0 || components < 1 || components > 4) return rb_fail(RB_ERR_INVALID, "rb_scene_add_texture: bad dimensions %ux%ux%u", width, height, components);
 	RbTexInfo ti;
@@ -91,6 +92,7 @@ static void rb_normal_matrix(const float * model, float * invtp) {
 }
 
 extern "C" rb_status rb_scene_add_object(rb_scene * sc, const rb_object_desc * d) {
+	if(sc) sc->editSerial++;
 	if(!sc || !d) return rb_fail(RB_ERR_INVALID, "rb_scene_add_object: null argument");
 	if(!d->positions || !d->indices || !d->normals || !d->tangents || !d->bitangents) {
 		// PathTracer::PathTracer logs "requires local tangent frames for all meshes" (PathTracer.cpp:14-16); here it is an error.
@@ -147,6 +149,7 @@ extern "C" rb_status rb_scene_add_object(rb_scene * sc, const rb_object_desc * d
 }
 
 extern "C" rb_status rb_scene_add_light(rb_scene * sc, const rb_light_desc * d) {
+	if(sc) sc->editSerial++;
 	if(!sc || !d) return rb_fail(RB_ERR_INVALID, "rb_scene_add_light: null argument");
 	if(d->kind > RB_LIGHT_DIRECTIONAL) return rb_fail(RB_ERR_INVALID, "rb_scene_add_light: unknown kind %u", d->kind);
 	RbLight l;
@@ -169,6 +172,7 @@ extern "C" rb_status rb_scene_add_light(rb_scene * sc, const rb_light_desc * d) 
 }
 
 extern "C" rb_status rb_scene_set_background(rb_scene * sc, uint32_t mode, const float color[3], const int32_t * textures, uint32_t ntextures, const float sun_direction[3], int32_t sky_lut) {
+	if(sc) sc->editSerial++;
 	if(!sc) return rb_fail(RB_ERR_INVALID, "rb_scene_set_background: null handle");
 	if(mode > RB_BG_ATMOSPHERE) return rb_fail(RB_ERR_INVALID, "rb_scene_set_background: unknown mode %u", mode);
 	const uint32_t need = mode == RB_BG_IMAGE ? 1u : (mode == RB_BG_SKYBOX ? 6u : 0u);
@@ -218,6 +222,7 @@ static rb_status rb_upload(T ** dst, const void * src, size_t bytes) {
 }
 
 extern "C" rb_status rb_scene_commit(rb_scene * sc, rb_build_mode mode) {
+	if(sc) sc->editSerial++;
 	if(!sc) return rb_fail(RB_ERR_INVALID, "rb_scene_commit: null handle");
 	RB_REQUIRE_DEVICE();
 	if(sc->objects.empty()) return rb_fail(RB_ERR_INVALID, "rb_scene_commit: scene has no object");
@@ -283,6 +288,7 @@ extern "C" rb_status rb_scene_commit(rb_scene * sc, rb_build_mode mode) {
 }
 
 extern "C" rb_status rb_scene_clear_lights(rb_scene * sc) {
+	if(sc) sc->editSerial++;
 	if(!sc) return rb_fail(RB_ERR_INVALID, "rb_scene_clear_lights: null handle");
 	sc->lights.clear();
 	sc->tablesDirty = true;
@@ -290,6 +296,7 @@ extern "C" rb_status rb_scene_clear_lights(rb_scene * sc) {
 }
 
 extern "C" rb_status rb_scene_set_object_transform(rb_scene * sc, uint32_t object, const float model[16]) {
+	if(sc) sc->editSerial++;
 	if(!sc || !model) return rb_fail(RB_ERR_INVALID, "rb_scene_set_object_transform: null argument");
 	if(object >= sc->objects.size()) return rb_fail(RB_ERR_INVALID, "rb_scene_set_object_transform: object %u out of range (%zu objects)", object, sc->objects.size());
 	RbHostObject & o = sc->objects[object];
@@ -349,6 +356,28 @@ extern "C" rb_status rb_scene_sync(rb_scene * sc) {
 	dv.skyLut		= sc->skyLut;
 	sc->tablesDirty = false;
 	sc->committed	= true;
+	return RB_OK;
+}
+
+rb_status rb_scene_clone_host(const rb_scene * sc, rb_scene ** out) {
+	if(!sc || !out) return rb_fail(RB_ERR_INVALID, "rb_scene_clone_host: null argument");
+	rb_scene * r = new rb_scene(*sc); // host vectors are copied; everything that names device memory is reset below
+	r->raycaster		 = nullptr;
+	r->d_texels			 = nullptr;
+	r->d_textures		 = nullptr;
+	r->d_objects		 = nullptr;
+	r->d_lights			 = nullptr;
+	r->d_vertexAttr		 = nullptr;
+	r->d_triShade		 = nullptr;
+	r->d_indices		 = nullptr;
+	r->d_objVertOffset	 = nullptr;
+	r->d_objIndexOffset	 = nullptr;
+	r->dev				 = RbSceneDev{};
+	r->committed		 = false;
+	r->geometryCommitted = false;
+	r->tablesDirty		 = false;
+	for(RbHostObject & o : r->objects) o.transformDirty = false; // the clone is committed from the current matrices
+	*out = r;
 	return RB_OK;
 }
 

@@ -26,6 +26,7 @@ struct rb_scene {
 	int32_t skyLut	 = -1;
 	bool committed	 = false;
 	bool geometryCommitted = false; // objects/textures are on the device; lights / background may still be stale
+	uint64_t editSerial = 0;		// bumped by every call that changes the scene (replicas on other GPUs are keyed to it)
 	uint64_t triShadeSerial = 0;	// rb_raycaster::buildSerial the per-triangle shading records were gathered for
 	bool tablesDirty = false;		// lights or background changed since the last upload (rb_scene_sync)
 
@@ -41,3 +42,10 @@ struct rb_scene {
 	uint32_t * d_objIndexOffset = nullptr;
 	RbSceneDev dev = {};
 };
+
+struct rb_pathtracer;
+// rb_multi.cu
+rb_status rb_pt_multi_render(rb_pathtracer * pt, const rb_camera * camera, uint32_t width, uint32_t height, uint32_t samples, uint32_t depth, uint32_t components, float * pixels, const rb_render_opts * opts);
+void rb_pt_multi_destroy(void * multi);
+// Host side of a scene copied into a new, uncommitted handle (no device state): what a replica on another GPU starts from.
+rb_status rb_scene_clone_host(const rb_scene * sc, rb_scene ** out);

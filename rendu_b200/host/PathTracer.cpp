@@ -12,6 +12,7 @@
 #include "system/Query.hpp"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -42,6 +43,8 @@ struct TextureTable {
 
 PathTracer::PathTracer(const std::shared_ptr<Scene> & scene) {
 	_scene = scene;
+	if(const char * e = std::getenv("RENDU_B200_GPUS")) _gpus = unsigned(std::atoi(e));
+	if(const char * e = std::getenv("RENDU_B200_SPLIT")) _gpuSampleSplit = std::string(e) == "sample";
 	if(!ok(rb_scene_create(&_deviceScene), "scene")) return;
 	TextureTable textures{_deviceScene, {}};
 	for(const auto & obj : scene->objects) {
@@ -119,7 +122,7 @@ PathTracer::~PathTracer() {
 // scene->lights flattened for the device. Called at construction and again before every render: the reference reads
 // the lights through the shared Scene inside render() (PathTracer.cpp:232-255), so edits made between two frames count.
 bool PathTracer::uploadLights() {
-	if(!ok(rb_scene_clear_lights(_deviceScene), "light upload")) return false;
+	std::vector<rb_light_desc> descs;
 	for(const auto & light : _scene->lights) {
 		rb_light_desc d;
 		std::memset(&d, 0, sizeof(d));
@@ -142,8 +145,18 @@ bool PathTracer::uploadLights() {
 			d.kind = RB_LIGHT_DIRECTIONAL;
 			for(int k = 0; k < 3; ++k) d.direction[k] = dl->direction()[k];
 		}
+		descs.push_back(d);
+	}
+	// Unchanged since the last frame (the usual case): nothing to send, and the replicas on the other GPUs stay valid.
+	const unsigned char * bytes = reinterpret_cast<const unsigned char *>(descs.data());
+	std::vector<unsigned char> flat(bytes, bytes + descs.size() * sizeof(rb_light_desc));
+	flat.push_back(1); // an empty light list still differs from "never uploaded"
+	if(flat == _lightsUploaded) return true;
+	if(!ok(rb_scene_clear_lights(_deviceScene), "light upload")) return false;
+	for(const rb_light_desc & d : descs) {
 		if(!ok(rb_scene_add_light(_deviceScene, &d), "light upload")) return false;
 	}
+	_lightsUploaded.swap(flat);
 	return true;
 }
 
@@ -177,6 +190,8 @@ void PathTracer::render(const Camera & camera, size_t samples, size_t depth, Ima
 	opts.tile_count	  = _tile[2];
 	opts.sample_index = _split[0];
 	opts.sample_count = _split[1];
+	opts.gpus		  = _gpus;
+	opts.split		  = _gpuSampleSplit ? RB_SPLIT_SAMPLE : RB_SPLIT_TILE;
 	if(!uploadLights()) return;
 	Query timer;
 	timer.begin();

@@ -25,6 +25,10 @@ public:
 	void setSeed(unsigned long long seed) { _seed = seed; }
 	void setTile(unsigned int rows, unsigned int index, unsigned int count) { _tile[0] = rows; _tile[1] = index; _tile[2] = count; }
 	void setSampleSplit(unsigned int index, unsigned int count) { _split[0] = index; _split[1] = count; }
+	// All GPUs of the box from this one render() call — what replaces System::forParallel (System.hpp:72-104): `count`
+	// devices, frame split by image tile (sampleSplit = false: bit-identical to one GPU) or by stratification cell
+	// (one NCCL reduce of the sums). Defaults come from the environment: RENDU_B200_GPUS, RENDU_B200_SPLIT=tile|sample.
+	void setGpus(unsigned int count, bool sampleSplit = false) { _gpus = count; _gpuSampleSplit = sampleSplit; }
 
 private:
 	bool uploadLights();
@@ -36,4 +40,7 @@ private:
 	unsigned long long _seed = 0;
 	unsigned int _tile[3]	 = {0, 0, 0};
 	unsigned int _split[2]	 = {0, 0};
+	unsigned int _gpus		 = 0;
+	bool _gpuSampleSplit	 = false;
+	std::vector<unsigned char> _lightsUploaded; // flattened scene->lights as last sent to the device
 };

@@ -21,7 +21,7 @@ done
 # The reference's BVH debug view, UNMODIFIED, compiled against the drop-in header: it is a friend of Raycaster and reads
 # _hierarchy / _triangles / _vertices directly (RaycasterVisualisation.cpp:15-30,41-77), which is why the mirror exists.
 $CXX -std=c++11 -O2 -w $INC -c "$REF/src/engine/raycaster/RaycasterVisualisation.cpp" -o "$ROOT/build/dropin/RaycasterVisualisation.o"
-REFOBJS=$(ls "$OBJ"/*.o | grep -v -E "/(Raycaster|PathTracer|ref_api)\.o$")
+REFOBJS=$(ls "$OBJ"/*.o | grep -v -E "/(Raycaster|PathTracer|ref_api|ref_build_scene)\.o$")
 $CXX -o "$ROOT/build/pathtracer_b200" "$ROOT/build/dropin/"{Raycaster,PathTracer,dropin_main,RaycasterVisualisation}.o $REFOBJS \
 	-L"$ROOT/rendu_b200" -lrendu_b200 -Wl,-rpath,'$ORIGIN/../rendu_b200' -lpthread
 echo "build_dropin: $ROOT/build/pathtracer_b200 ready"

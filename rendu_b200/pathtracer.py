@@ -122,7 +122,10 @@ def make_camera(eye, corner, dx, dy):
     return c
 
 
-def make_opts(seed=0, tile=None, samples=None, trace_mode=0, max_paths=0, accumulate=False):
+SPLIT_TILE, SPLIT_SAMPLE = 0, 1
+
+
+def make_opts(seed=0, tile=None, samples=None, trace_mode=0, max_paths=0, accumulate=False, gpus=0, split=SPLIT_TILE, tile_rows=0):
     o = RenderOpts()
     o.seed = int(seed)
     if tile is not None:
@@ -132,6 +135,9 @@ def make_opts(seed=0, tile=None, samples=None, trace_mode=0, max_paths=0, accumu
     o.trace_mode = int(trace_mode)
     o.max_paths_in_flight = int(max_paths)
     o.accumulate = 1 if accumulate else 0
+    o.gpus, o.split = int(gpus), int(split)  # gpus > 1: render() fans the frame out over that many devices of this process
+    if gpus and gpus > 1 and tile_rows:
+        o.tile_rows = int(tile_rows)
     return o
 
 
@@ -172,6 +178,24 @@ class PathTracer:
 
     def resolve_device(self, d_sum, width, height, samples, components, d_pixels, opts=None, stream=0):
         check(lib().rb_pathtracer_resolve_device(self._h, d_sum, width, height, int(samples), components, d_pixels, C.byref(opts) if opts is not None else None, stream))
+
+    def multi_stats(self):
+        """Slowest GPU's render time and the combine step (band copies / reduce + resolve) of the last gpus > 1 render."""
+        m = _capi.MultiStats()
+        check(lib().rb_pathtracer_multi_stats(self._h, C.byref(m)))
+        return dict(gpus=int(m.gpus), split=int(m.split), used_nccl=bool(m.used_nccl), peer_access=bool(m.peer_access), render_ms=float(m.render_ms), combine_ms=float(m.combine_ms))
+
+    def profile_frame(self, camera, width, height, samples, depth, opts=None):
+        """One frame taken apart (bench roofline): device ms and launches per kernel class on a single stream, and the
+        nodes / triangles / roots tested by the two traversal wavefronts (counting copies of the kernels)."""
+        cam = camera if isinstance(camera, Camera) else make_camera(camera["eye"], camera["corner"], camera["dx"], camera["dy"])
+        p = _capi.PtProfile()
+        check(lib().rb_pathtracer_profile_frame(self._h, C.byref(cam), width, height, int(samples), int(depth), C.byref(opts) if opts is not None else None, C.byref(p)))
+        names = ("raygen", "trace", "shade", "shadow", "accumulate")
+        out = {"ms": {n: float(p.ms[i]) for i, n in enumerate(names)}, "launches": {n: int(p.launches[i]) for i, n in enumerate(names)}}
+        for k in ("rays_closest", "rays_shadow", "shaded_hits", "samples", "trace_interior", "trace_tris", "trace_roots", "shadow_interior", "shadow_tris", "shadow_roots"):
+            out[k] = int(getattr(p, k))
+        return out
 
     def stats(self):
         s = RenderStats()

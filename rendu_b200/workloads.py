@@ -247,5 +247,9 @@ def cornell_synthetic(grid_n=708, tex_res=512, cube_res=256):
     return dict(objects=objs, lights=lights, textures=tex, background=bg)
 
 
+CORNELL_CAMERA = dict(eye=(0.0, 1.0, 3.4), center=(0.0, 0.9, 0.0), up=(0.0, 1.0, 0.0), fov=0.75)
+
+
 def cornell_camera(ratio):
-    return camera_shifts((0.0, 1.0, 3.4), (0.0, 0.9, 0.0), (0, 1, 0), 0.75, ratio)
+    c = CORNELL_CAMERA
+    return camera_shifts(c["eye"], c["center"], c["up"], c["fov"], ratio)

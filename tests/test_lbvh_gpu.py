@@ -220,16 +220,23 @@ def test_update_mesh_then_refit_equals_fresh_add_mesh(mode):
     fresh.addMesh(bpos, bidx, m1)
     fresh.updateHierarchy(rb.BUILD_REFERENCE)
     assert np.array_equal(r.download_bvh()[2], fresh.download_bvh()[2])
-    # Error behaviour: unknown mesh, wrong vertex count, uploaded hierarchies carry no per-mesh ranges.
+    # Error behaviour: unknown mesh, wrong vertex count.
     with pytest.raises(rb.RenduError):
         r.update_mesh(2, bpos, m1)
     with pytest.raises(rb.RenduError):
         r.update_mesh(1, bpos[:-1], m1)
+    # An uploaded reference-order hierarchy gets its per-mesh ranges back (rb_raycaster_upload_bvh reconstructs them from
+    # the triangle records), so its meshes can be moved like those of a handle filled through add_mesh.
     up = rb.Raycaster()
     nodes, tris, verts = fresh.download_bvh()
     up.upload_bvh(nodes, tris, verts, fresh.sizes()["meshes"])
+    up.update_mesh(1, bpos, m1)
+    up.refit()
+    assert np.array_equal(up.download_bvh()[2], fresh.download_bvh()[2])
+    for f in ("hit", "dist", "localId", "meshId"):
+        assert np.array_equal(up.intersects(org, dirs)[f], fresh.intersects(org, dirs)[f]), f
     with pytest.raises(rb.RenduError):
-        up.update_mesh(0, gpos)
+        up.update_mesh(1, bpos[:-1], m1)
 
 
 def test_rebuild_after_refit_uses_the_moved_vertices():

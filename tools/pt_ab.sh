@@ -1,6 +1,6 @@
 #!/bin/bash
 # developer aid: A/B two builds of the library on the path-tracing workload (GPU box)
-run() { echo "== $*"; env "$@" python bench.py --workload pathtrace --spp 64 --steps 3 --warmup 3 --no-cpu 2>/dev/null | python -c "
+run() { echo "== $*"; env "$@" python bench.py --spp 64 --steps 3 --warmup 3 --no-cpu 2>/dev/null | python -c "
 import json,sys
 for l in sys.stdin:
     if l.startswith('{'):

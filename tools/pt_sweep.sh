@@ -1,6 +1,6 @@
 #!/bin/bash
 # developer aid: path-tracer throughput for lane / batch-size / scheduler settings (GPU box)
-run() { echo "== $EXTRA $*"; env "$@" python bench.py --workload pathtrace --spp 64 --steps 3 --warmup 3 --no-cpu $EXTRA 2>/dev/null | python -c "
+run() { echo "== $EXTRA $*"; env "$@" python bench.py --spp 64 --steps 3 --warmup 3 --no-cpu $EXTRA 2>/dev/null | python -c "
 import json,sys
 for l in sys.stdin:
     if l.startswith('{'):

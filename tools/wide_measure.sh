@@ -11,5 +11,5 @@ cp gpurun_out/explore.json gpurun_out/wide_explore.json 2>/dev/null
 RB_EXPLORE_ONLY=wide_t12 timeout 600 ncu --set full --clock-control none --import-source on -k regex:rb_k_trace_wide -c 4 -o gpurun_out/wide_t12 -f python bench.py --explore > gpurun_out/wide_ncu.log 2>&1
 RB_EXPLORE_ONLY=wide_phased_v6_t12 timeout 600 ncu --set full --clock-control none --import-source on -k regex:rb_k_trace_wide -c 4 -o gpurun_out/wide_phased_v6_t12 -f python bench.py --explore >> gpurun_out/wide_ncu.log 2>&1
 # the path tracer's closest-hit wavefront on the wide tree against exact mode (16 spp frames, same box)
-for m in exact wide; do timeout -k 5 200 python bench.py --workload pathtrace --spp 16 --steps 3 --warmup 2 --no-cpu --trace-mode $m 2>/dev/null | tail -1 > gpurun_out/wide_pt_$m.json; done
+for m in exact wide; do timeout -k 5 200 python bench.py --spp 16 --steps 3 --warmup 2 --no-cpu --trace-mode $m 2>/dev/null | tail -1 > gpurun_out/wide_pt_$m.json; done
 ls -la gpurun_out | tail -8
