@@ -664,10 +664,14 @@ def run_headline(args):
         o1 = opts_for("none")
         host_image[:] = 0
         pt.render(cam, spp, PT_DEPTH, host_image, o1)
+        e2e_each = []
         t0 = time.perf_counter()
         for _ in range(steps):
+            t1 = time.perf_counter()
             pt.render(cam, spp, PT_DEPTH, host_image, o1)  # accumulates into the caller's image like the reference: values grow, the work does not
+            e2e_each.append((time.perf_counter() - t1) * 1e3)
         e2e_ms = (time.perf_counter() - t0) * 1e3
+        log("[bench] e2e frames (ms): " + " ".join("%.1f" % x for x in e2e_each) + "; device seconds of the last: %.4f" % pt.stats()["device_seconds"])
         host_image[:] = 0
         pt.render(cam, spp, PT_DEPTH, host_image, o1)
         e2e_h2d, e2e_d2h = PT_W * PT_H * 3 * 4 + 48, PT_W * PT_H * 3 * 4

@@ -684,6 +684,10 @@ struct rb_pathtracer {
 		std::vector<int> kinds; // kernel class launched after events[k]
 	} * prof = nullptr;
 	void * multi = nullptr; // rb_multi.cu: replicas on the other GPUs of the box (rb_render_opts.gpus > 1)
+	// Frame buffers of rb_pathtracer_render (host image in / out), kept between calls: a cudaMalloc / cudaFree pair per
+	// frame synchronises the device and showed up as 100-300 ms stalls in the first frames of a sequence.
+	float * d_frameSum = nullptr, * d_framePixels = nullptr;
+	size_t frameSumFloats = 0, framePixelFloats = 0;
 };
 
 rb_scene * rb_pt_scene(rb_pathtracer * pt) { return pt->scene; }
@@ -773,6 +777,8 @@ extern "C" void rb_pathtracer_destroy(rb_pathtracer * pt) {
 	if(rb_have_device()) {
 		rb_pt_free(pt);
 		cudaFree(pt->d_stats);
+		cudaFree(pt->d_frameSum);
+		cudaFree(pt->d_framePixels);
 		if(pt->fork) cudaEventDestroy(pt->fork);
 		for(int l = 0; l < RB_PT_LANES; ++l) {
 			if(pt->join[l]) cudaEventDestroy(pt->join[l]);
@@ -1034,12 +1040,21 @@ extern "C" rb_status rb_pathtracer_render(rb_pathtracer * pt, const rb_camera * 
 	}
 	cudaStream_t s = cudaStreamPerThread;
 	const size_t npx = size_t(width) * height;
-	float *d_sum = nullptr, *d_pixels = nullptr;
-	RB_CUDA(cudaMalloc(&d_sum, npx * 3 * sizeof(float)));
-	if(cudaMalloc(&d_pixels, npx * components * sizeof(float)) != cudaSuccess) {
-		cudaFree(d_sum);
-		return rb_fail(RB_ERR_CUDA, "rb_pathtracer_render: cudaMalloc failed");
+	if(pt->frameSumFloats < npx * 3) {
+		cudaFree(pt->d_frameSum);
+		pt->d_frameSum	   = nullptr;
+		pt->frameSumFloats = 0;
+		RB_CUDA(cudaMalloc(&pt->d_frameSum, npx * 3 * sizeof(float)));
+		pt->frameSumFloats = npx * 3;
 	}
+	if(pt->framePixelFloats < npx * components) {
+		cudaFree(pt->d_framePixels);
+		pt->d_framePixels	 = nullptr;
+		pt->framePixelFloats = 0;
+		RB_CUDA(cudaMalloc(&pt->d_framePixels, npx * components * sizeof(float)));
+		pt->framePixelFloats = npx * components;
+	}
+	float *d_sum = pt->d_frameSum, *d_pixels = pt->d_framePixels;
 	cudaEvent_t e0, e1;
 	cudaEventCreate(&e0);
 	cudaEventCreate(&e1);
@@ -1066,8 +1081,6 @@ extern "C" rb_status rb_pathtracer_render(rb_pathtracer * pt, const rb_camera * 
 	} while(false);
 	cudaEventDestroy(e0);
 	cudaEventDestroy(e1);
-	cudaFree(d_sum);
-	cudaFree(d_pixels);
 	return st;
 }
 

@@ -958,12 +958,13 @@ static bool rb_reconstruct_mesh_ranges(rb_raycaster * rc, std::string * why) {
 extern "C" rb_status rb_raycaster_upload_bvh(rb_raycaster * rc, const rb_node * nodes, size_t nnodes, const rb_tri * tris, size_t ntris, const float * vertices, size_t nverts, uint32_t mesh_count) {
 	if(!rc || (!nodes && nnodes) || (!tris && ntris) || (!vertices && nverts)) return rb_fail(RB_ERR_INVALID, "rb_raycaster_upload_bvh: null argument");
 	RB_REQUIRE_DEVICE();
+	rb_raycaster_free_device(rc); // the host arrays are replaced below: whatever tree is on the device no longer matches them
 	rc->nodes.assign(nodes, nodes + nnodes);
 	rc->meshFirst.clear();
 	rc->meshTris.clear();
 	rc->meshVertFirst.clear();
 	rc->meshVerts.clear();
-	rc->triBoxesStale = false;
+	rc->triBoxesStale = true; // a later rebuild starts from triangle boxes recomputed on `vertices`, not from the caller's records
 	rc->tris.assign(tris, tris + ntris);
 	rc->verts.assign(vertices, vertices + nverts * 3);
 	rc->meshCount = mesh_count;

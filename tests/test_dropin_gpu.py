@@ -42,3 +42,28 @@ def test_reference_engine_with_gpu_classes_swapped_in(tmp_path):
     conv = g["converged"]
     assert abs(img.mean() - conv.mean()) / conv.mean() < 0.01
     assert np.linalg.norm(img - conv) / np.linalg.norm(conv) < 1.5 * 0.43 * np.sqrt(1 / 256 + 1 / 2048)
+
+
+@pytest.mark.skipif(not (os.path.exists(BINARY) and os.path.isdir(RES)), reason="drop-in binary / bundled resources not built (needs /root/reference at build time)")
+def test_headless_render_cli_writes_the_files_the_reference_writer_would(tmp_path):
+    """`pathtracer_b200 --render` (the reference's `PathTracer --render`, src/apps/pathtracer/main.cpp:21-122, same flags): the
+    tail of renderOneShot — tonemap, sRGB, quantisation for .png; layer split and float->half for .exr — runs on the GPU
+    and feeds the reference's own encoders. For the same frame the file equals, byte for byte, what the reference's
+    Image::save writes after its CPU conversions (--reference-writer). With several GPUs the tile split gives the same file."""
+    import rendu_b200 as rb
+
+    def run(out, *extra):
+        cmd = [BINARY, "--render", "--scene", "cornellbox-textured", "--resources-root", RES, "--size", "96", "64", "--samples", "16", "--depth", "4", "--seed", "5", "--output", out, *extra]
+        log = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+        assert log.returncode == 0, log.stdout + log.stderr
+        assert "[PathTracer] Rendering took" in log.stdout and "[PathTracer] Saving to " + out in log.stdout
+        return open(out, "rb").read()
+
+    for ext in ("png", "exr"):
+        gpu = run(str(tmp_path / ("gpu." + ext)))
+        ref = run(str(tmp_path / ("ref." + ext)), "--reference-writer")
+        assert len(gpu) > 1000 and gpu == ref, "%s written from the GPU output stage differs from Image::save's" % ext
+        if rb.device_count() >= 2:
+            assert run(str(tmp_path / ("two." + ext)), "--gpus", "2") == gpu
+    bad = subprocess.run([BINARY, "--scene", "cornellbox"], capture_output=True, text=True, timeout=60)
+    assert bad.returncode == 2  # no interactive viewer in the drop-in

@@ -308,11 +308,11 @@ def test_wide_kernel_equals_exact_mode():
     # Only a triangle accepted although the reference's rounded slab test rejects one of its boxes may differ.
     assert differ.size <= 2, (differ.size, wide[differ[:4]], exact[differ[:4]])
     assert int(exact["hit"].sum()) > 50000
-    r.updateHierarchy()
+    r.updateHierarchy()  # the wide copy goes with the rebuild, and the handle is back in exact mode (rb_raycaster_free_device)
+    again = r.intersects(org[:64], dirs[:64])
     with pytest.raises(rb.RenduError):
-        r.intersects(org[:4], dirs[:4])  # the wide copy went with the rebuild
-    r.set_trace_mode(rb.TRACE_EXACT)
-    again = r.intersects(org[:64], dirs[:64])  # the rebuilt tree numbers its triangles differently (internalId): compare the hit itself
+        r.set_trace_mode(rb.TRACE_WIDE)  # RB_TRACE_WIDE without a new rb_raycaster_wide_build fails loudly
+    # the rebuilt tree numbers its triangles differently (internalId): compare the hit itself
     for f in ("hit", "dist", "u", "v", "localId", "meshId"):
         assert np.array_equal(again[f], exact[:64][f]), f
 
