@@ -415,6 +415,10 @@ RB_API rb_status rb_kat_cubemap_sample(const float * faces, uint32_t width, uint
 RB_API rb_status rb_kat_light_sample(const rb_light_desc * light, const float * positions, size_t n, float * out5);
 RB_API rb_status rb_kat_sky_eval(const float * lut_rgba, uint32_t width, uint32_t height, const float * origins, const float * dirs, const float sun[3], size_t n, float * out3);
 RB_API rb_status rb_kat_box_test(const float * origins, const float * dirs, const float * boxes6, float mini, float maxi, size_t n, uint8_t * out);
+/* Raycaster::intersects(const Ray &, const TriangleInfos &, mini, maxi) (Raycaster.cpp:232-262; private, reached by the friend
+ * RaycasterVisualisation): n (ray, triangle) pairs. positions / dirs are a Ray's `pos` and already-normalised `dir`, used as
+ * given; vertices9 holds v0, v1, v2 per pair; out4 = (hit, dist, u, v) per pair. */
+RB_API rb_status rb_kat_triangle_test(const float * positions, const float * dirs, const float * vertices9, float mini, float maxi, size_t n, float * out4);
 
 #ifdef __cplusplus
 }

@@ -1521,3 +1521,45 @@ extern "C" rb_status rb_kat_box_test(const float * origins, const float * dirs, 
 	RB_CUDA(cudaStreamSynchronize(s));
 	return RB_OK;
 }
+
+// Raycaster::intersects(const Ray &, const TriangleInfos &, mini, maxi) (Raycaster.cpp:232-262) for arrays of (ray, triangle)
+// pairs: the per-triangle Möller-Trumbore test on its own. `dirs` are used AS GIVEN (a Ray's already-normalised `dir`):
+// normalising a second time can move a component by one ulp. out4 = (hit ? 1 : 0, t, u, v) per pair. It is what the
+// drop-in's private per-triangle intersects — called by RaycasterVisualisation::getRayLevels on the leaves one ray visits
+// (RaycasterVisualisation.cpp:61-66) — runs on, and a known-answer test of the triangle test.
+__global__ void rb_k_kat_tri(const float * __restrict__ pos, const float * __restrict__ dir, const float * __restrict__ v9, float mini, float maxi, size_t n, float * __restrict__ out) {
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	RbRay ray;
+	ray.pos = V3{pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
+	ray.dir = V3{dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]};
+	const float * v = v9 + 9 * i;
+	const V3 v0 = V3{v[0], v[1], v[2]}, v1 = V3{v[3], v[4], v[5]}, v2 = V3{v[6], v[7], v[8]};
+	float t = 0.0f, u = 0.0f, w = 0.0f;
+	const bool hit = rb_tri_test(ray, v0, v1 - v0, v2 - v0, mini, maxi, t, u, w);
+	out[4 * i + 0] = hit ? 1.0f : 0.0f;
+	out[4 * i + 1] = hit ? t : 0.0f;
+	out[4 * i + 2] = hit ? u : 0.0f;
+	out[4 * i + 3] = hit ? w : 0.0f;
+}
+
+extern "C" rb_status rb_kat_triangle_test(const float * positions, const float * dirs, const float * vertices9, float mini, float maxi, size_t n, float * out4) {
+	RB_REQUIRE_DEVICE();
+	if(n == 0) return RB_OK;
+	if(!positions || !dirs || !vertices9 || !out4) return rb_fail(RB_ERR_INVALID, "rb_kat_triangle_test: null argument");
+	cudaStream_t s = cudaStreamPerThread;
+	Scratch scratch(s);
+	float *d_o = nullptr, *d_d = nullptr, *d_v = nullptr, *d_r = nullptr;
+	RB_CUDA(scratch.alloc(&d_o, n * 3 * sizeof(float)));
+	RB_CUDA(scratch.alloc(&d_d, n * 3 * sizeof(float)));
+	RB_CUDA(scratch.alloc(&d_v, n * 9 * sizeof(float)));
+	RB_CUDA(scratch.alloc(&d_r, n * 4 * sizeof(float)));
+	RB_CUDA(cudaMemcpyAsync(d_o, positions, n * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+	RB_CUDA(cudaMemcpyAsync(d_d, dirs, n * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+	RB_CUDA(cudaMemcpyAsync(d_v, vertices9, n * 9 * sizeof(float), cudaMemcpyHostToDevice, s));
+	rb_k_kat_tri<<<unsigned((n + 127) / 128), 128, 0, s>>>(d_o, d_d, d_v, mini, maxi, n, d_r);
+	RB_CUDA(cudaGetLastError());
+	RB_CUDA(cudaMemcpyAsync(out4, d_r, n * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
+	RB_CUDA(cudaStreamSynchronize(s));
+	return RB_OK;
+}

@@ -99,11 +99,14 @@ void Raycaster::intersectsAny(const glm::vec3 * origins, const glm::vec3 * direc
 	if(_device && n) rbCheck(rb_raycaster_intersect_any(_device, &origins[0][0], &directions[0][0], mini, maxi, n, out), "intersectsAny(batch)");
 }
 
-// Only RaycasterVisualisation::getRayLevels calls this (per-level replay of ONE ray for the debug view): a single
-// triangle against a single ray, evaluated as a one-triangle GPU query through a scratch raycaster would be absurd, so
-// the debug view asks the device for the full query instead and filters by triangle.
+// The private per-triangle test (Raycaster.cpp:232-262). Only the friend RaycasterVisualisation::getRayLevels calls it — on
+// the triangles of the leaves ONE ray visits (RaycasterVisualisation.cpp:61-66) — so a one-pair launch per call is fine. The
+// semantics are the reference's: this triangle alone against the ray and (mini, maxi), whatever else the ray would hit.
 Raycaster::Hit Raycaster::intersects(const Ray & ray, const TriangleInfos & tri, float mini, float maxi) const {
-	const Hit h = intersects(ray.pos, ray.dir, mini, maxi);
-	if(h.hit && h.localId == tri.localId && h.meshId == tri.meshId) return h;
-	return Hit();
+	if(tri.v0 >= _vertices.size() || tri.v1 >= _vertices.size() || tri.v2 >= _vertices.size()) return Hit();
+	const float verts[9] = {_vertices[tri.v0].x, _vertices[tri.v0].y, _vertices[tri.v0].z, _vertices[tri.v1].x, _vertices[tri.v1].y, _vertices[tri.v1].z,
+							_vertices[tri.v2].x, _vertices[tri.v2].y, _vertices[tri.v2].z};
+	float out[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+	if(!rbCheck(rb_kat_triangle_test(&ray.pos[0], &ray.dir[0], verts, mini, maxi, 1, out), "intersects(ray, triangle)") || out[0] == 0.0f) return Hit();
+	return Hit(out[1], out[2], out[3], tri.localId, tri.meshId);
 }
