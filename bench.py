@@ -26,11 +26,14 @@ import sys
 import threading
 import time
 
+import ctypes
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+C_F3 = ctypes.c_float * 3
 GRID_N = 708          # 2*708^2 = 1,002,528 triangles
 RES = 2048            # 2048^2 = 4,194,304 rays per set
 MINI, MAXI = 1e-4, 1e8
@@ -420,10 +423,41 @@ def raycast_block(args, R, steps, with_cpu):
     h2d = 4 * n * 24
     d2h = 2 * n * 48 + 2 * n
 
-    times = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    # The same step with the opt-in wire format for the coherent set: its rays ARE the primary rays of a pinhole camera
+    # (eye (0,1.5,2.2), image plane y = 0 over [-1,1]^2), so rb_raycaster_intersect_primary generates them on the device
+    # from 48 bytes of camera — bit for bit the rays of wl.coherent_rays, hence the same Hit records (checked below).
+    from rendu_b200 import _capi
+    cam = _capi.Camera()
+    cam.eye, cam.corner = (C_F3)(0.0, 1.5, 2.2), (C_F3)(-1.0, 0.0, -1.0)
+    cam.dx, cam.dy = (C_F3)(2.0, 0.0, 0.0), (C_F3)(0.0, 0.0, 2.0)
+    h_hits2 = torch.empty(n * 48, dtype=torch.uint8).pin_memory()
+
+    def e2e_closest_primary():
+        check(L.rb_raycaster_intersect_primary(rc._h, ctypes.byref(cam), RES, RES, MINI, MAXI, h_hits2.data_ptr()))
+        check(L.rb_raycaster_intersect(rc._h, h_io.data_ptr(), h_id.data_ptr(), MINI, MAXI, n, h_hits.data_ptr()))
+
+    def e2e_any_primary():
+        check(L.rb_raycaster_intersect_any_primary(rc._h, ctypes.byref(cam), RES, RES, MINI, MAXI, h_any.data_ptr()))
+        check(L.rb_raycaster_intersect_any(rc._h, h_io.data_ptr(), h_id.data_ptr(), MINI, MAXI, n, h_any.data_ptr()))
+
+    def e2e_step_primary():
+        fa, fb = pool.submit(e2e_closest_primary), pool.submit(e2e_any_primary)
+        fa.result()
+        fb.result()
+
+    e2e_step_primary()
+    primary_equal = bool(torch.equal(h_hits2, d_hit_c.cpu()))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e2e_step_primary()
+    barrier()
+    e2e_primary_s = time.perf_counter() - t0
+
+    times = torch.tensor([total_ms, e2e_s * 1e3, e2e_primary_s * 1e3], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = float(times[0]), float(times[1])
+    total_ms, e2e_ms, e2e_primary_ms = float(times[0]), float(times[1]), float(times[2])
     queries_step = 4 * n
     value = world * queries_step * steps / (total_ms * 1e-3) / 1e6
     e2e_value = world * queries_step * steps / (e2e_ms * 1e-3) / 1e6
@@ -490,7 +524,10 @@ def raycast_block(args, R, steps, with_cpu):
     return {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "steps": steps, "ms_per_step": total_ms / steps, "scaling": "weak (every rank traces the full sets; no collective)",
             "config": config_dict(world), "gpu_launches": int(gpu_launches),
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps,
-                    "api": "rb_raycaster_intersect / rb_raycaster_intersect_any with pinned host buffers, closest and any calls issued from two host threads", "host_link": link},
+                    "api": "rb_raycaster_intersect / rb_raycaster_intersect_any with pinned host buffers, closest and any calls issued from two host threads", "host_link": link,
+                    "with_device_generated_primary_rays": {"value": world * queries_step * steps / (e2e_primary_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 2 * n * 24 + 96, "d2h_bytes_per_step": d2h,
+                                                           "api": "coherent set through rb_raycaster_intersect_primary / _any_primary (camera in, Raycaster::Hit records out), incoherent set as above",
+                                                           "records_identical_to_host_rays": primary_equal}},
             "roofline": roofline, "per_launch": per_launch, "parity": parity, "cpu_baseline": cpu}
 
 
@@ -519,7 +556,7 @@ def pt_config(world, spp, split, trace_mode="exact"):
                         "shadowed point light, NEE on) with the 1,002,528-triangle displaced grid as floor; PathTracer::render" % spp,
             "width": PT_W, "height": PT_H, "spp": spp, "depth": PT_DEPTH, "triangles": 2 * GRID_N * GRID_N + 12, "split": split if world > 1 else "none", "trace_mode": trace_mode,
             "parallelism": "replicated scene, %d rank(s)%s" % (world, "" if world == 1 else (", tile split (2-row bands dealt round-robin), bands gathered on rank 0" if split == "tile" else ", sample split, one NCCL reduce of the fp32 sums")),
-            "l2": "no explicit flush: every bounce streams the wavefront state of a batch (16 Mi paths x 176 B = 2.9 GB) through HBM, far beyond the 126 MB L2"}
+            "l2": "no explicit flush: every bounce streams the wavefront state of a batch (32 Mi paths x 176 B = 5.9 GB) through HBM, far beyond the 126 MB L2"}
 
 
 def pt_roofline(pt, cam, opts, rays_scale=1.0):
@@ -573,7 +610,7 @@ def run_headline(args):
     spp = args.spp or (256 if world == 1 else 4096)
     steps, warmup = args.steps, max(args.warmup, 3)
     # The C2 block runs first, on its own handle, and is gone before the path tracer allocates its wavefront state.
-    block = raycast_block(args, R, steps if world == 1 else max(3, min(steps, 5)), world == 1 and not args.no_cpu)
+    block = None if args.no_raycast else raycast_block(args, R, steps if world == 1 else max(3, min(steps, 5)), world == 1 and not args.no_cpu)
     torch.cuda.empty_cache()
     t_setup = time.time()
     desc = wl.cornell_synthetic(GRID_N if not args.small else 64, 512, 256)
@@ -981,6 +1018,7 @@ def main():
     ap.add_argument("--spp", type=int, default=0, help="samples per pixel of the frame (0 = 256 on one GPU, 4096 on several)")
     ap.add_argument("--max-paths", type=int, default=0, help="paths in flight per wavefront batch (0 = library default)")
     ap.add_argument("--split", default="tile", choices=["tile", "sample"], help="N>1: the split `value` is measured with (the other one is timed beside it)")
+    ap.add_argument("--no-raycast", action="store_true", help="developer aid: skip the C2 raycast block (kernel sweeps of the path tracer)")
     ap.add_argument("--small", action="store_true", help="8k-triangle floor instead of 1M (quick checks)")
     ap.add_argument("--trace-mode", default="exact", choices=["exact", "ordered", "wide"], help="traversal order of the path tracer's wavefront kernels")
     args = ap.parse_args()

@@ -195,6 +195,23 @@ RB_API rb_status rb_raycaster_visible(const rb_raycaster * rc, const float * p0,
 RB_API rb_status rb_raycaster_ray_levels(const rb_raycaster * h, const float * origin, const float * direction, float mini, float maxi, uint32_t capacity,
 										 float * boxes6, uint32_t * depths, uint32_t * count, rb_hit * hit);
 
+/* What render() derives from the Camera on the host (PathTracer.cpp:177,197; Camera.cpp:42-49). */
+typedef struct rb_camera {
+	float eye[3];	 /* Camera::position() */
+	float corner[3]; /* Camera::pixelShifts */
+	float dx[3];
+	float dy[3];
+} rb_camera;
+
+/* Primary rays of a pinhole camera, generated on the device (an opt-in wire format of the batch API: nothing but the
+ * camera goes up the host link, where rb_raycaster_intersect uploads 24 bytes per ray). Ray of pixel (x, y), row-major,
+ * y * width + x: from `eye` through the centre of the pixel with the reference's arithmetic (PathTracer.cpp:193-198:
+ * ndc = (x + 0.5, y + 0.5) / (width, height); worldPos = corner + ndc.x * dx + ndc.y * dy; direction = worldPos - eye,
+ * normalised by Ray::Ray) — bit for bit the rays a host loop with the same formula would pass to rb_raycaster_intersect,
+ * hence the same Raycaster::Hit records. out holds width * height records / flags. */
+RB_API rb_status rb_raycaster_intersect_primary(const rb_raycaster * rc, const rb_camera * camera, uint32_t width, uint32_t height, float mini, float maxi, rb_hit * out);
+RB_API rb_status rb_raycaster_intersect_any_primary(const rb_raycaster * rc, const rb_camera * camera, uint32_t width, uint32_t height, float mini, float maxi, uint8_t * out);
+
 /* Device-pointer variants: enqueue on `stream` (a cudaStream_t), no host synchronisation. */
 RB_API rb_status rb_raycaster_intersect_device(const rb_raycaster * rc, const float * d_origins, const float * d_directions, float mini, float maxi, size_t nrays, rb_hit * d_out, void * stream);
 RB_API rb_status rb_raycaster_intersect_any_device(const rb_raycaster * rc, const float * d_origins, const float * d_directions, float mini, float maxi, size_t nrays, uint8_t * d_out, void * stream);
@@ -283,14 +300,6 @@ RB_API rb_raycaster * rb_scene_raycaster(rb_scene * sc);
 
 typedef struct rb_pathtracer rb_pathtracer;
 
-/* What render() derives from the Camera on the host (PathTracer.cpp:177,197; Camera.cpp:42-49). */
-typedef struct rb_camera {
-	float eye[3];	 /* Camera::position() */
-	float corner[3]; /* Camera::pixelShifts */
-	float dx[3];
-	float dy[3];
-} rb_camera;
-
 typedef struct rb_render_opts {
 	uint64_t seed;		 /* counter-based RNG key; same seed => same image, whatever the GPU count */
 	/* Tile split: only rows y with (y / tile_rows) % tile_count == tile_index are rendered (others untouched).
@@ -302,7 +311,7 @@ typedef struct rb_render_opts {
 	uint32_t trace_mode; /* rb_trace_mode used for primary, bounce and shadow rays (RB_TRACE_WIDE, experiment: closest-hit
 	                      * wavefront — and the shadow wavefront of scenes without masked materials — on the wide tree, after
 	                      * rb_raycaster_wide_build on rb_scene_raycaster()) */
-	uint32_t max_paths_in_flight; /* paths per wavefront batch; 0 = default (16 Mi; two batches are in flight: 176 B x 2 x 16 Mi = 5.9 GB) */
+	uint32_t max_paths_in_flight; /* paths per wavefront batch; 0 = default (32 Mi; two batches are in flight: 176 B x 2 x 32 Mi = 11.8 GB of the B200's 180 GB) */
 	/* Progressive rendering: with accumulate != 0 rb_pathtracer_render_device ADDS this call's samples
 	 * to d_sum instead of overwriting it, so a viewer can trace one slice of the stratification grid per frame
 	 * (sample_index = frame % sample_count) and resolve what it has so far with samples = cells traced so far. */

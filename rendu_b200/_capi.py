@@ -109,6 +109,8 @@ def lib():
         "rb_raycaster_intersect": (C.c_int, [vp, vp, vp, f32, f32, sz, vp]),
         "rb_raycaster_intersect_any": (C.c_int, [vp, vp, vp, f32, f32, sz, vp]),
         "rb_raycaster_visible": (C.c_int, [vp, vp, vp, sz, vp]),
+        "rb_raycaster_intersect_primary": (C.c_int, [vp, C.POINTER(Camera), u32, u32, f32, f32, vp]),
+        "rb_raycaster_intersect_any_primary": (C.c_int, [vp, C.POINTER(Camera), u32, u32, f32, f32, vp]),
         "rb_raycaster_ray_levels": (C.c_int, [vp, vp, vp, f32, f32, u32, vp, vp, vp, vp]),
         "rb_raycaster_intersect_device": (C.c_int, [vp, vp, vp, f32, f32, sz, vp, vp]),
         "rb_raycaster_intersect_any_device": (C.c_int, [vp, vp, vp, f32, f32, sz, vp, vp]),

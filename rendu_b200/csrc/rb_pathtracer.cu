@@ -875,7 +875,7 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 	const uint64_t localPixels	= uint64_t(f.localRows) * width;
 	uint64_t launches = 0;
 	if(localSamples && localPixels && depth) {
-		size_t maxPaths = (opts && opts->max_paths_in_flight) ? opts->max_paths_in_flight : (size_t(1) << 24);
+		size_t maxPaths = (opts && opts->max_paths_in_flight) ? opts->max_paths_in_flight : (size_t(1) << 25); // 32 Mi paths x 176 B x 2 lanes = 11.8 GB of the 180 GB
 		if(maxPaths < 1024) maxPaths = 1024;
 		const uint32_t schunk	  = uint32_t(localSamples < maxPaths ? localSamples : maxPaths);
 		uint64_t pixelsPerBatch = maxPaths / schunk;

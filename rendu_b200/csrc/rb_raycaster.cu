@@ -1349,6 +1349,63 @@ rb_status rb_host_batch(const rb_raycaster * rc, const float * origins, const fl
 }
 } // namespace
 
+// Primary rays of a pinhole camera, generated on the device: pixel (x, y) -> the ray from `eye` through the centre of the
+// pixel, with the reference's own arithmetic (PathTracer.cpp:193-198: ndc = screenPos / (W, H); worldPos = corner +
+// ndc.x * dx + ndc.y * dy; direction = worldPos - eye, normalised by Ray::Ray). Nothing goes up the host link but the camera.
+__global__ void rb_k_primary_rays(rb_camera cam, uint32_t width, uint32_t height, size_t first, size_t n, float * __restrict__ org, float * __restrict__ dir) {
+	for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		const size_t p	  = first + i;
+		const uint32_t x  = uint32_t(p % width), y = uint32_t(p / width);
+		const float ndcx  = (float(x) + 0.5f) / float(width);
+		const float ndcy  = (float(y) + 0.5f) / float(height);
+		const float wx = (cam.corner[0] + ndcx * cam.dx[0]) + ndcy * cam.dy[0];
+		const float wy = (cam.corner[1] + ndcx * cam.dx[1]) + ndcy * cam.dy[1];
+		const float wz = (cam.corner[2] + ndcx * cam.dx[2]) + ndcy * cam.dy[2];
+		org[3 * i + 0] = cam.eye[0]; org[3 * i + 1] = cam.eye[1]; org[3 * i + 2] = cam.eye[2];
+		dir[3 * i + 0] = wx - cam.eye[0]; dir[3 * i + 1] = wy - cam.eye[1]; dir[3 * i + 2] = wz - cam.eye[2];
+	}
+}
+
+namespace {
+template<bool ANY>
+rb_status rb_host_primary(const rb_raycaster * rc, const rb_camera * cam, uint32_t width, uint32_t height, float mini, float maxi, void * out) {
+	RB_CUDA(cudaSetDevice(rc->device));
+	rb_status st = t_pipe.ensure(rc->device);
+	if(st) return st;
+	const size_t nrays = size_t(width) * height, outStride = ANY ? sizeof(uint8_t) : sizeof(rb_hit);
+	size_t chunkIdx = 0;
+	for(size_t begin = 0; begin < nrays; begin += kPipeChunk, ++chunkIdx) {
+		const int k	   = int(chunkIdx % kPipeSlots);
+		const size_t n = (nrays - begin < kPipeChunk) ? (nrays - begin) : kPipeChunk;
+		cudaStream_t s = t_pipe.stream[k];
+		rb_k_primary_rays<<<unsigned((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184), 256, 0, s>>>(*cam, width, height, begin, n, t_pipe.d_org[k], t_pipe.d_dir[k]);
+		RB_CUDA(cudaGetLastError());
+		rc->launches++;
+		st = rb_launch_trace<ANY>(rc, t_pipe.d_org[k], t_pipe.d_dir[k], mini, maxi, n, t_pipe.d_out[k], s);
+		if(st) return st;
+		RB_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(out) + begin * outStride, t_pipe.d_out[k], n * outStride, cudaMemcpyDeviceToHost, s));
+	}
+	for(int k = 0; k < kPipeSlots; ++k) RB_CUDA(cudaStreamSynchronize(t_pipe.stream[k]));
+	return RB_OK;
+}
+} // namespace
+
+extern "C" rb_status rb_raycaster_intersect_primary(const rb_raycaster * rc, const rb_camera * camera, uint32_t width, uint32_t height, float mini, float maxi, rb_hit * out) {
+	rb_status st = rb_check_query(rc, "rb_raycaster_intersect_primary");
+	if(st) return st;
+	if(!camera || !out) return rb_fail(RB_ERR_INVALID, "rb_raycaster_intersect_primary: null argument");
+	if(width == 0 || height == 0) return RB_OK;
+	return rb_host_primary<false>(rc, camera, width, height, mini, maxi, out);
+}
+
+extern "C" rb_status rb_raycaster_intersect_any_primary(const rb_raycaster * rc, const rb_camera * camera, uint32_t width, uint32_t height, float mini, float maxi, uint8_t * out) {
+	rb_status st = rb_check_query(rc, "rb_raycaster_intersect_any_primary");
+	if(st) return st;
+	if(!camera || !out) return rb_fail(RB_ERR_INVALID, "rb_raycaster_intersect_any_primary: null argument");
+	if(width == 0 || height == 0) return RB_OK;
+	return rb_host_primary<true>(rc, camera, width, height, mini, maxi, out);
+}
+
 extern "C" rb_status rb_raycaster_intersect(const rb_raycaster * rc, const float * origins, const float * directions, float mini, float maxi, size_t nrays, rb_hit * out) {
 	rb_status st = rb_check_query(rc, "rb_raycaster_intersect");
 	if(st) return st;

@@ -15,6 +15,13 @@ BUILD_REFERENCE, BUILD_LBVH, BUILD_SAH = 0, 1, 2
 TRACE_EXACT, TRACE_ORDERED, TRACE_WIDE = 0, 1, 2
 
 
+def _camera(c):
+    cam = _capi.Camera()
+    for k in ("eye", "corner", "dx", "dy"):
+        setattr(cam, k, (C.c_float * 3)(*[float(x) for x in c[k]]))
+    return cam
+
+
 def _rays(a):
     a = np.ascontiguousarray(a, dtype=np.float32)
     single = a.ndim == 1
@@ -144,6 +151,21 @@ class Raycaster:
         out = np.zeros(a.shape[0], np.uint8)
         check(lib().rb_raycaster_visible(self._h, ptr(a), ptr(b), a.shape[0], ptr(out)))
         return bool(out[0]) if single else out.astype(bool)
+
+    def intersects_primary(self, camera, width, height, mini=0.0001, maxi=1e8, out=None):
+        """Closest hits of the primary rays of a pinhole camera (eye, corner, dx, dy as Camera::pixelShifts gives them), generated on
+        the device through pixel centres: (height * width,) Hit records, row-major."""
+        cam = camera if isinstance(camera, _capi.Camera) else _camera(camera)
+        out = np.zeros(width * height, HIT_DTYPE) if out is None else out
+        check(lib().rb_raycaster_intersect_primary(self._h, C.byref(cam), width, height, mini, maxi, ptr(out)))
+        return out
+
+    def intersectsAny_primary(self, camera, width, height, mini=0.0001, maxi=1e8, out=None):
+        cam = camera if isinstance(camera, _capi.Camera) else _camera(camera)
+        mine = out is None
+        out = np.zeros(width * height, np.uint8) if mine else out
+        check(lib().rb_raycaster_intersect_any_primary(self._h, C.byref(cam), width, height, mini, maxi, ptr(out)))
+        return out.astype(bool) if mine else out
 
     def rayLevels(self, origin, direction, mini=1e-4, maxi=1e8, capacity=4096):
         """RaycasterVisualisation::getRayLevels (RaycasterVisualisation.cpp:41-77) from the device tree: boxes (n, 6) and

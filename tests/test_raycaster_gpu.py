@@ -463,3 +463,29 @@ def test_per_triangle_test_reproduces_the_hits_of_the_golden_rays():
     # (mini, maxi) are honoured: a window that ends before the hit rejects it
     check(lib().rb_kat_triangle_test(ptr(o), ptr(np.ascontiguousarray(dn)), ptr(v9), float(c["mini"]), float(c["dist"][sel].min() * 0.5), sel.size, ptr(out)))
     assert (out[:, 0] == 0).all()
+
+
+def test_device_generated_primary_rays_give_the_records_of_the_same_rays_passed_from_the_host():
+    """rb_raycaster_intersect_primary / _any_primary: pinhole-camera rays through pixel centres, generated on the device with
+    the reference's arithmetic (PathTracer.cpp:193-198). The C2 coherent set is such a camera, so the records must equal
+    those of wl.coherent_rays passed through rb_raycaster_intersect, bit for bit; a tilted camera is checked against a numpy
+    restatement of the formula."""
+    pos, idx = wl.displaced_grid(96)
+    r = rb.Raycaster()
+    r.addMesh(pos, idx)
+    r.updateHierarchy()
+    res = 192
+    co, cd = wl.coherent_rays(res)
+    cam = dict(eye=(0.0, 1.5, 2.2), corner=(-1.0, 0.0, -1.0), dx=(2.0, 0.0, 0.0), dy=(0.0, 0.0, 2.0))
+    want, got = r.intersects(co, cd), r.intersects_primary(cam, res, res)
+    assert got.tobytes() == want.tobytes() and int(want["hit"].sum()) > res * res // 2
+    assert np.array_equal(r.intersectsAny_primary(cam, res, res), r.intersectsAny(co, cd))
+    c2 = wl.camera_shifts((0.3, 1.1, 1.9), (0.0, 0.1, 0.0), (0, 1, 0), 0.8, 1.5)
+    w, h = 150, 100
+    F = np.float32
+    xs, ys = (np.arange(w, dtype=F) + F(0.5)) / F(w), (np.arange(h, dtype=F) + F(0.5)) / F(h)
+    NX, NY = np.meshgrid(xs, ys, indexing="xy")
+    wp = [((F(c2["corner"][k]) + NX * F(c2["dx"][k])).astype(F) + NY * F(c2["dy"][k])).astype(F) for k in range(3)]
+    d = np.stack([(wp[k] - F(c2["eye"][k])).astype(F).ravel() for k in range(3)], -1)
+    o = np.tile(np.asarray(c2["eye"], F), (w * h, 1))
+    assert r.intersects_primary(c2, w, h).tobytes() == r.intersects(o, d).tobytes()
