@@ -10,6 +10,6 @@ timeout -k 5 300 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_
 # launch list of a short headline run (never a bench number)
 timeout -k 5 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches.csv python bench.py --spp 16 --steps 1 --warmup 3 --no-cpu > /dev/null 2>&1
 # full captures: the C2 launches, then the three big path-tracer kernels of a 16-spp frame
-timeout -k 5 600 ncu --set full --clock-control none --import-source on -k regex:rb_k_trace_phased -s 12 -c 4 -o gpurun_out/r02_ncu_raycast -f python bench.py --workload raycast --steps 1 --warmup 3 --no-cpu > gpurun_out/r02_ncu.log 2>&1
-timeout -k 5 600 ncu --set full --clock-control none --import-source on -k regex:"rb_k_pt_(trace|shade|shadow)" -s 48 -c 9 -o gpurun_out/r02_ncu_pt -f python bench.py --spp 16 --steps 1 --warmup 3 --no-cpu --workload headline >> gpurun_out/r02_ncu.log 2>&1
+timeout -k 5 600 ncu --set full --clock-control none --import-source on -k regex:rb_k_trace_phased -s 13 -c 4 -o gpurun_out/r02_ncu_raycast -f python bench.py --workload raycast --steps 1 --warmup 3 --no-cpu > gpurun_out/r02_ncu.log 2>&1
+timeout -k 5 600 ncu --set full --clock-control none --import-source on -k regex:"rb_k_pt_(trace|shade|shadow)" -s 72 -c 9 -o gpurun_out/r02_ncu_pt -f python bench.py --spp 16 --steps 1 --warmup 3 --no-cpu --no-raycast >> gpurun_out/r02_ncu.log 2>&1
 ls -la gpurun_out | tail -6
