@@ -69,6 +69,20 @@ RB_HD float rb_rng_float(uint64_t key, uint32_t dim) {
 // ---------------------------------------------------------------------------------------------- images
 RB_HD int rb_mod_pos(int x, int w) { return ((x % w) + w) % w; } // Image.hpp:189-191
 
+// modPos(x, w) and modPos(x + 1, w) — the two columns (rows) of a bilinear tap — without the four integer divisions the
+// literal form costs per pair (a signed 32-bit modulo by a run-time value is ~28 instructions; the three textures of a
+// shaded hit took 24 of them, 40 % of the shade kernel's instructions). Same values: for a power-of-two size the
+// two's-complement AND is the floor modulo; otherwise the second one follows from the first.
+RB_D void rb_wrap_pair(int x, int w, int & a, int & b) {
+	if((w & (w - 1)) == 0) {
+		a = x & (w - 1);
+		b = (x + 1) & (w - 1);
+	} else {
+		a = rb_mod_pos(x, w);
+		b = (a + 1 == w) ? 0 : a + 1;
+	}
+}
+
 // Image::rgbal (Image.cpp:86-106): wrap-around bilinear, texel-corner convention (no half-texel offset).
 RB_D float4 rb_image_rgbal(const RbSceneDev & sc, int tex, float x, float y) {
 	const RbTexInfo ti = sc.textures[tex];
@@ -78,10 +92,9 @@ RB_D float4 rb_image_rgbal(const RbSceneDev & sc, int tex, float x, float y) {
 	const float yb = floorf(yi);
 	const float dx = xi - xb;
 	const float dy = yi - yb;
-	const int x0 = rb_mod_pos(int(xb), int(ti.width));
-	const int y0 = rb_mod_pos(int(yb), int(ti.height));
-	const int x1 = rb_mod_pos(int(xb) + 1, int(ti.width));
-	const int y1 = rb_mod_pos(int(yb) + 1, int(ti.height));
+	int x0, x1, y0, y1;
+	rb_wrap_pair(int(xb), int(ti.width), x0, x1);
+	rb_wrap_pair(int(yb), int(ti.height), y0, y1);
 	const float4 * base = sc.texels + ti.offset;
 	const float4 p00 = __ldg(base + size_t(y0) * ti.width + x0);
 	const float4 p01 = __ldg(base + size_t(y1) * ti.width + x0);
