@@ -362,6 +362,18 @@ RB_API rb_status rb_pathtracer_resolve_device(rb_pathtracer * pt, const float * 
 RB_API rb_status rb_pathtracer_stats(const rb_pathtracer * pt, rb_render_stats * out);
 RB_API rb_status rb_pathtracer_multi_stats(rb_pathtracer * pt, rb_multi_stats * out);
 
+/* Live rendering (PathTracerApp's "Live render", src/apps/pathtracer/PathTracerApp.cpp:57-98,127-136, which
+ * calls render() for the whole frame every UI frame and uploads the float image again). A frame is refined pass by pass:
+ * _live_begin sizes the session, every _live_pass traces the next slice of the stratification grid (cells sid % pass_count
+ * == passes done) and adds it to per-pixel sums that never leave the device — a changed camera, sample count, depth or
+ * pass_count starts over, a finished frame makes the call a no-op — and _live_display returns the mean so far as 8-bit
+ * pixels (tonemap 1 - exp(-c), sRGB, quantisation as in rb_output_ldr, alpha 255 for 4 components): `components` bytes per
+ * pixel come back per displayed frame, nothing goes up but the camera. After pass_count passes the bytes equal
+ * rb_output_ldr of one rb_pathtracer_render with the same samples and seed. */
+RB_API rb_status rb_pathtracer_live_begin(rb_pathtracer * pt, uint32_t width, uint32_t height);
+RB_API rb_status rb_pathtracer_live_pass(rb_pathtracer * pt, const rb_camera * camera, uint32_t samples, uint32_t depth, uint32_t pass_count, const rb_render_opts * opts);
+RB_API rb_status rb_pathtracer_live_display(rb_pathtracer * pt, uint32_t components, int tonemap, int srgb, uint8_t * out, uint32_t * passes_done);
+
 /* Measurement aid (the reference has no counterpart; bench.py's roofline uses it outside its timed regions): one frame
  * rendered twice — once on a single stream with a CUDA event before every kernel, giving device milliseconds and launch
  * counts per kernel class (0 ray generation, 1 closest-hit wavefront, 2 shading, 3 shadow wavefront, 4 accumulation),

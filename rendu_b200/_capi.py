@@ -134,6 +134,9 @@ def lib():
         "rb_pathtracer_resolve_device": (C.c_int, [vp, vp, u32, u32, u32, u32, vp, C.POINTER(RenderOpts), vp]),
         "rb_pathtracer_stats": (C.c_int, [vp, C.POINTER(RenderStats)]),
         "rb_pathtracer_multi_stats": (C.c_int, [vp, C.POINTER(MultiStats)]),
+        "rb_pathtracer_live_begin": (C.c_int, [vp, u32, u32]),
+        "rb_pathtracer_live_pass": (C.c_int, [vp, C.POINTER(Camera), u32, u32, u32, C.POINTER(RenderOpts)]),
+        "rb_pathtracer_live_display": (C.c_int, [vp, u32, C.c_int, C.c_int, vp, C.POINTER(u32)]),
         "rb_pathtracer_profile_frame": (C.c_int, [vp, C.POINTER(Camera), u32, u32, u32, u32, C.POINTER(RenderOpts), C.POINTER(PtProfile)]),
         "rb_output_ldr": (C.c_int, [vp, u32, u32, u32, C.c_int, C.c_int, vp]),
         "rb_output_ldr_device": (C.c_int, [vp, u32, u32, u32, C.c_int, C.c_int, vp, vp]),

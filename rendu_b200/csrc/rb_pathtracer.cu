@@ -688,6 +688,11 @@ struct rb_pathtracer {
 	// frame synchronises the device and showed up as 100-300 ms stalls in the first frames of a sequence.
 	float * d_frameSum = nullptr, * d_framePixels = nullptr;
 	size_t frameSumFloats = 0, framePixelFloats = 0;
+	// Live session (rb_pathtracer_live_*): per-pixel sums and display bytes stay on the device between passes.
+	float * d_liveSum	  = nullptr;
+	uint8_t * d_liveBytes = nullptr;
+	uint32_t liveW = 0, liveH = 0, livePasses = 0, livePassCount = 0, liveSamples = 0, liveDepth = 0;
+	rb_camera liveCamera = {};
 };
 
 rb_scene * rb_pt_scene(rb_pathtracer * pt) { return pt->scene; }
@@ -779,6 +784,8 @@ extern "C" void rb_pathtracer_destroy(rb_pathtracer * pt) {
 		cudaFree(pt->d_stats);
 		cudaFree(pt->d_frameSum);
 		cudaFree(pt->d_framePixels);
+		cudaFree(pt->d_liveSum);
+		cudaFree(pt->d_liveBytes);
 		if(pt->fork) cudaEventDestroy(pt->fork);
 		for(int l = 0; l < RB_PT_LANES; ++l) {
 			if(pt->join[l]) cudaEventDestroy(pt->join[l]);
@@ -1140,5 +1147,92 @@ extern "C" rb_status rb_pathtracer_stats(const rb_pathtracer * pt, rb_render_sta
 		out->rays_shadow  = hs[1];
 		out->shaded_hits  = hs[2];
 	}
+	return RB_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------ live rendering
+// PathTracerApp's "Live render" (src/apps/pathtracer/PathTracerApp.cpp:57-98,127-136) calls render() for a whole small frame
+// every UI frame and uploads the float image again. Here a frame is refined pass by pass: pass p of `pass_count` traces the
+// stratification cells sid % pass_count == p and ADDS them to sums that stay on the device; what comes back per displayed
+// frame is 8-bit pixels (mean so far -> tonemap 1 - exp(-c) -> sRGB -> byte, one fused kernel), 3 or 4 bytes per pixel
+// instead of 12 or 16 up and down. After pass_count passes the sums equal those of one render() call with `samples`.
+__global__ void rb_k_live_display(const float * __restrict__ sum, size_t npixels, float cells, uint32_t components, int tonemap, int srgb, uint8_t * __restrict__ out) {
+	for(size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npixels; p += (size_t)gridDim.x * blockDim.x) {
+		for(uint32_t c = 0; c < 3; ++c) {
+			float value = sum[3 * p + c] / cells; // render.rgb(x, y) / float(samples) (PathTracer.cpp:291-292) over the cells traced so far
+			if(tonemap) value = 1.0f - expf(-value * 1.f);
+			if(srgb) value = powf(value, 1.0f / 2.2f);
+			out[p * components + c] = static_cast<unsigned char>(std_min(255.0f, std_max(0.0f, 255.0f * value)));
+		}
+		if(components == 4) out[p * 4 + 3] = 255;
+	}
+}
+
+extern "C" rb_status rb_pathtracer_live_begin(rb_pathtracer * pt, uint32_t width, uint32_t height) {
+	if(!pt) return rb_fail(RB_ERR_INVALID, "rb_pathtracer_live_begin: null handle");
+	RB_REQUIRE_DEVICE();
+	if(width == 0 || height == 0) return rb_fail(RB_ERR_INVALID, "rb_pathtracer_live_begin: empty frame");
+	RB_CUDA(cudaSetDevice(pt->scene->raycaster->device));
+	if(width != pt->liveW || height != pt->liveH) {
+		cudaFree(pt->d_liveSum);
+		cudaFree(pt->d_liveBytes);
+		pt->d_liveSum = nullptr;
+		pt->d_liveBytes = nullptr;
+		pt->liveW = pt->liveH = 0;
+		RB_CUDA(cudaMalloc(&pt->d_liveSum, size_t(width) * height * 3 * sizeof(float)));
+		RB_CUDA(cudaMalloc(&pt->d_liveBytes, size_t(width) * height * 4));
+		pt->liveW = width;
+		pt->liveH = height;
+	}
+	pt->livePasses = 0; // the first pass overwrites the sums
+	return RB_OK;
+}
+
+extern "C" rb_status rb_pathtracer_live_pass(rb_pathtracer * pt, const rb_camera * camera, uint32_t samples, uint32_t depth, uint32_t pass_count, const rb_render_opts * opts) {
+	if(!pt || !camera) return rb_fail(RB_ERR_INVALID, "rb_pathtracer_live_pass: null argument");
+	RB_REQUIRE_DEVICE();
+	if(!pt->d_liveSum) return rb_fail(RB_ERR_INVALID, "rb_pathtracer_live_pass: call rb_pathtracer_live_begin first");
+	if(pass_count == 0 || pass_count > samples) return rb_fail(RB_ERR_INVALID, "rb_pathtracer_live_pass: pass_count must be in [1, samples]");
+	if(opts && (opts->tile_count > 1 || opts->sample_count > 1 || opts->gpus > 1)) return rb_fail(RB_ERR_INVALID, "rb_pathtracer_live_pass: the passes are the split; leave tile_* / sample_* / gpus at 0");
+	// A moved camera (or other frame parameters) starts the frame over, as a new render() call does in the reference's loop.
+	const bool same = pt->livePasses > 0 && std::memcmp(&pt->liveCamera, camera, sizeof(rb_camera)) == 0 && pt->liveSamples == samples && pt->liveDepth == depth && pt->livePassCount == pass_count;
+	if(!same) pt->livePasses = 0;
+	if(pt->livePasses >= pass_count) return RB_OK; // converged: every cell of the stratification grid has been traced
+	rb_render_opts o;
+	if(opts) o = *opts;
+	else std::memset(&o, 0, sizeof(o));
+	o.sample_index = pt->livePasses;
+	o.sample_count = pass_count;
+	o.accumulate   = pt->livePasses > 0 ? 1u : 0u;
+	rb_status st = rb_pathtracer_render_device(pt, camera, pt->liveW, pt->liveH, samples, depth, pt->d_liveSum, &o, cudaStreamPerThread);
+	if(st) return st;
+	pt->liveCamera	  = *camera;
+	pt->liveSamples	  = samples;
+	pt->liveDepth	  = depth;
+	pt->livePassCount = pass_count;
+	pt->livePasses++;
+	return RB_OK;
+}
+
+extern "C" rb_status rb_pathtracer_live_display(rb_pathtracer * pt, uint32_t components, int tonemap, int srgb, uint8_t * out, uint32_t * passes_done) {
+	if(!pt || !out) return rb_fail(RB_ERR_INVALID, "rb_pathtracer_live_display: null argument");
+	RB_REQUIRE_DEVICE();
+	if(components != 3 && components != 4) return rb_fail(RB_ERR_INVALID, "rb_pathtracer_live_display: components must be 3 or 4");
+	if(!pt->d_liveSum || pt->livePasses == 0) return rb_fail(RB_ERR_INVALID, "rb_pathtracer_live_display: no pass has been traced");
+	RB_CUDA(cudaSetDevice(pt->scene->raycaster->device));
+	cudaStream_t s = cudaStreamPerThread;
+	const size_t npx = size_t(pt->liveW) * pt->liveH;
+	// Cells traced so far: pass p holds the cells sid % pass_count == p of the (power-of-two) sample count render() rounds to.
+	RbFrame f;
+	rb_status st = rb_pt_frame(&pt->liveCamera, pt->liveW, pt->liveH, pt->liveSamples, 1, nullptr, f);
+	if(st) return st;
+	uint64_t cells = 0;
+	for(uint32_t p = 0; p < pt->livePasses; ++p) cells += (f.samples > p) ? (f.samples - p + pt->livePassCount - 1) / pt->livePassCount : 0;
+	rb_k_live_display<<<unsigned(pt->sms * 8), 256, 0, s>>>(pt->d_liveSum, npx, float(cells), components, tonemap, srgb, pt->d_liveBytes);
+	RB_CUDA(cudaGetLastError());
+	RB_CUDA(cudaMemcpyAsync(out, pt->d_liveBytes, npx * components, cudaMemcpyDeviceToHost, s));
+	RB_CUDA(cudaStreamSynchronize(s));
+	if(passes_done) *passes_done = pt->livePasses;
 	return RB_OK;
 }

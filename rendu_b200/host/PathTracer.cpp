@@ -204,3 +204,38 @@ void PathTracer::render(const Camera & camera, size_t samples, size_t depth, Ima
 	Log::Info() << "[PathTracer] Rendering took " << seconds << "s at " << render.width << "x" << render.height << "." << std::endl;
 	Log::Info() << "[PathTracer] " << (st.rays_closest + st.rays_shadow) << " rays, " << double(st.rays_closest + st.rays_shadow) / (st.device_seconds > 0.0 ? st.device_seconds : 1.0) / 1e6 << " Mrays/s on the device." << std::endl;
 }
+
+void PathTracer::cameraFor(const Camera & camera, rb_camera & cam) const {
+	glm::vec3 corner, dx, dy;
+	camera.pixelShifts(corner, dx, dy); // PathTracer.cpp:177
+	for(int k = 0; k < 3; ++k) {
+		cam.eye[k]	  = camera.position()[k];
+		cam.corner[k] = corner[k];
+		cam.dx[k]	  = dx[k];
+		cam.dy[k]	  = dy[k];
+	}
+}
+
+bool PathTracer::liveBegin(unsigned int width, unsigned int height) {
+	return _device && ok(rb_pathtracer_live_begin(_device, width, height), "live begin");
+}
+
+bool PathTracer::livePass(const Camera & camera, size_t samples, size_t depth, size_t passCount) {
+	if(!_device || !uploadLights()) return false;
+	rb_camera cam;
+	cameraFor(camera, cam);
+	rb_render_opts opts;
+	std::memset(&opts, 0, sizeof(opts));
+	opts.seed = _seed;
+	return ok(rb_pathtracer_live_pass(_device, &cam, uint32_t(samples), uint32_t(depth), uint32_t(passCount), &opts), "live pass");
+}
+
+unsigned int PathTracer::liveDisplay(std::vector<unsigned char> & pixels, unsigned int components) {
+	if(!_device) return 0;
+	uint32_t done = 0;
+	// The session knows its own size; the caller's vector is sized by the first successful call through liveBegin's values.
+	if(pixels.empty()) return 0;
+	if(!ok(rb_pathtracer_live_display(_device, components, 1, 1, pixels.data(), &done), "live display")) return 0;
+	return done;
+}
+

@@ -7,6 +7,7 @@
 
 struct rb_scene;
 struct rb_pathtracer;
+struct rb_camera;
 
 class PathTracer {
 public:
@@ -30,8 +31,18 @@ public:
 	// (one NCCL reduce of the sums). Defaults come from the environment: RENDU_B200_GPUS, RENDU_B200_SPLIT=tile|sample.
 	void setGpus(unsigned int count, bool sampleSplit = false) { _gpus = count; _gpuSampleSplit = sampleSplit; }
 
+	// Live rendering — what PathTracerApp's "Live render" loop (PathTracerApp.cpp:57-98,127-136) would call instead of a full
+	// render() + Texture::upload per UI frame: liveBegin sizes the session; every livePass traces the next 1 / passCount of
+	// the stratification cells and adds it to sums that stay on the GPU (a moved camera starts over, a converged frame costs
+	// nothing); liveDisplay fetches the frame as refined so far as 8-bit pixels (tonemapped, sRGB) ready for an RGBA8
+	// texture. Returns the number of passes the image holds (0 on failure).
+	bool liveBegin(unsigned int width, unsigned int height);
+	bool livePass(const Camera & camera, size_t samples, size_t depth, size_t passCount);
+	unsigned int liveDisplay(std::vector<unsigned char> & pixels, unsigned int components = 4);
+
 private:
 	bool uploadLights();
+	void cameraFor(const Camera & camera, struct rb_camera & out) const;
 
 	Raycaster _raycaster;
 	std::shared_ptr<Scene> _scene;

@@ -179,6 +179,23 @@ class PathTracer:
     def resolve_device(self, d_sum, width, height, samples, components, d_pixels, opts=None, stream=0):
         check(lib().rb_pathtracer_resolve_device(self._h, d_sum, width, height, int(samples), components, d_pixels, C.byref(opts) if opts is not None else None, stream))
 
+    # ------------------------------------------------------------------ live rendering (PathTracerApp.cpp:57-98,127-136)
+    def live_begin(self, width, height):
+        check(lib().rb_pathtracer_live_begin(self._h, int(width), int(height)))
+        self._live = (int(width), int(height))
+
+    def live_pass(self, camera, samples, depth, pass_count, opts=None):
+        cam = camera if isinstance(camera, Camera) else make_camera(camera["eye"], camera["corner"], camera["dx"], camera["dy"])
+        check(lib().rb_pathtracer_live_pass(self._h, C.byref(cam), int(samples), int(depth), int(pass_count), C.byref(opts) if opts is not None else None))
+
+    def live_display(self, components=4, tonemap=True, srgb=True):
+        """(H, W, components) uint8 of the frame as refined so far, and the number of passes it holds."""
+        w, h = self._live
+        out = np.zeros((h, w, components), np.uint8)
+        done = C.c_uint32(0)
+        check(lib().rb_pathtracer_live_display(self._h, components, 1 if tonemap else 0, 1 if srgb else 0, ptr(out), C.byref(done)))
+        return out, int(done.value)
+
     def multi_stats(self):
         """Slowest GPU's render time and the combine step (band copies / reduce + resolve) of the last gpus > 1 render."""
         m = _capi.MultiStats()

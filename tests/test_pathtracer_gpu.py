@@ -401,3 +401,37 @@ def test_scene_changes_after_the_commit_are_refused_until_recommitted():
     c = np.zeros((16, 16, 3), np.float32)
     pt.render(cam, 4, 3, c, rpt.make_opts(seed=1))
     assert np.array_equal(a, c)
+
+
+def test_live_session_refines_on_the_device_and_ends_at_the_one_shot_frame():
+    """rb_pathtracer_live_* (PathTracerApp's live render, PathTracerApp.cpp:57-98,127-136): passes add slices of the
+    stratification grid to sums that stay on the device; what comes back is 8-bit pixels. After all passes the bytes equal the
+    output stage applied to one render() of the same samples and seed; earlier displays are valid previews (mean over the
+    cells so far); a moved camera starts the frame over; extra passes on a finished frame change nothing."""
+    desc, cam = wl.cornell_synthetic(32, 64, 32), wl.cornell_camera(96 / 64)
+    pt = rpt.PathTracer(rpt.Scene(desc))
+    one = np.zeros((64, 96, 3), np.float32)
+    pt.render(cam, 64, 4, one, rpt.make_opts(seed=9))
+    want = rpt.output_ldr(np.concatenate([one, np.ones((64, 96, 1), np.float32)], axis=2))
+    pt.live_begin(96, 64)
+    previews = []
+    for p in range(8):
+        pt.live_pass(cam, 64, 4, 8, rpt.make_opts(seed=9))
+        img, done = pt.live_display(4)
+        assert done == p + 1
+        previews.append(img)
+    # the passes add the same clamped samples in another order: fp32 sums may differ in the last bit, a byte by one step
+    d = np.abs(previews[-1].astype(np.int32) - want.astype(np.int32))
+    assert d.max() <= 1 and (d > 0).mean() < 0.005
+    err = [np.abs(x[..., :3].astype(np.int32) - want[..., :3].astype(np.int32)).mean() for x in previews]
+    assert err[0] > err[3] > err[7] and err[7] < 0.01  # the preview converges to the final frame
+    pt.live_pass(cam, 64, 4, 8, rpt.make_opts(seed=9))  # finished: a no-op
+    img, done = pt.live_display(3)
+    assert done == 8 and np.array_equal(img, previews[-1][..., :3])
+    cam2 = wl.cornell_camera(96 / 64)
+    cam2["eye"] = cam2["eye"] + np.float32(0.05)
+    pt.live_pass(cam2, 64, 4, 8, rpt.make_opts(seed=9))
+    img2, done = pt.live_display(4)
+    assert done == 1 and not np.array_equal(img2, previews[0])
+    with pytest.raises(rb.RenduError):
+        pt.live_pass(cam, 64, 4, 128)
