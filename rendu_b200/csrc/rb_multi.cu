@@ -15,7 +15,10 @@
 #include "rb_scene.h"
 #include <nccl.h>
 #include <dlfcn.h>
+#include <algorithm>
+#include <mutex>
 #include <thread>
+#include <utility>
 
 rb_scene * rb_pt_scene(rb_pathtracer * pt);
 void ** rb_pt_multi_slot(rb_pathtracer * pt);
@@ -197,9 +200,16 @@ static rb_status ensureReplicas(rb_pathtracer * pt, uint32_t gpus, Multi ** out)
 			m->peerAccess = false;
 			continue;
 		}
+		// Peer access stays enabled for the life of the process: asked for once per (device, peer) pair.
+		static std::mutex lock;
+		static std::vector<std::pair<int, int>> enabled;
+		std::lock_guard<std::mutex> guard(lock);
+		const std::pair<int, int> key(primary, m->reps[g].device);
+		if(std::find(enabled.begin(), enabled.end(), key) != enabled.end()) continue;
 		const cudaError_t e = cudaDeviceEnablePeerAccess(m->reps[g].device, 0);
-		if(e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) m->peerAccess = false;
-		cudaGetLastError();
+		if(e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) enabled.push_back(key);
+		else m->peerAccess = false;
+		if(e != cudaSuccess) cudaGetLastError(); // clear the (non-sticky) error state
 	}
 	*slot = m;
 	*out  = m;

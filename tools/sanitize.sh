@@ -7,4 +7,5 @@ run smoke python -c "import __graft_entry__ as g; g.smoke()"
 run golden python -m pytest tests/test_raycaster_gpu.py -q -x -k "golden or ray_levels or many_roots or single_ray"
 run lbvh python -m pytest tests/test_lbvh_gpu.py -q -x -k "multi_mesh or refit"
 run pt python -m pytest tests/test_pathtracer_gpu.py -q -x -k "path_for_path or output_stage or seed_determinism"
+run r02 python -m pytest tests/test_pathtracer_gpu.py tests/test_raycaster_gpu.py tests/test_multigpu_gpu.py -q -x -k "live_session or recommitted or profile_frame or multi_gpu_render or primary_rays or per_triangle or empty_mesh or after_an_upload or garbage_records"
 done
