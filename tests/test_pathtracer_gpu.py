@@ -162,6 +162,15 @@ def test_bundled_scenes_match_oracle(name):
         gpu1, _ = gpu_render(desc, cam, 48, 48, 32, 1, seed=2)
         cpu1, _ = osc.render(cam, 48, 48, 32, 1, seed=2, rng="counter", threads=8)
         assert_same_paths(gpu1, cpu1, frac_tol=0.001)  # masked leaves + spot cones + alpha shadow walk, first bounce
+        # ... and the explanation itself, at full depth: with the two spot lights pulled 0.5 % towards the room's centre, off the
+        # wall planes, the same scene (masked leaves, alpha walk, spot cones, five bounces) agrees like every other one.
+        import copy
+        moved = copy.deepcopy(desc)
+        for l in moved["lights"]:
+            l["position"] = (np.asarray(l["position"], np.float32) * np.float32(0.995) + np.float32(0.005) * np.array([0.0, 1.0, 0.0], np.float32)).astype(np.float32)
+        gpu5, _ = gpu_render(moved, cam, 48, 48, 32, 5, seed=2)
+        cpu5, _ = orc.OracleScene(moved).render(cam, 48, 48, 32, 5, seed=2, rng="counter", threads=8)
+        assert_same_paths(gpu5, cpu5, frac_tol=0.02)
 
 
 def test_seed_determinism_tiles_and_sample_split():
