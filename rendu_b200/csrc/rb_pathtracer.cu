@@ -136,7 +136,7 @@ RB_D void rb_pt_flush_work(const RbWork & w, unsigned int lane, unsigned long lo
 	}
 }
 
-template<bool ORDERED, bool BLOCKS, bool COUNT = false>
+template<bool ORDERED, int ROOTS, bool COUNT = false>
 __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_trace(RbDeviceBvh bvh, RbPathBuffers pb, const uint32_t * __restrict__ queue, uint32_t did, int threshold, int leafVotes, int nodeSteps, unsigned long long * __restrict__ stats) {
 	extern __shared__ int s_stack[];
 	const RbStack st		= rb_make_stack(s_stack + threadIdx.x, blockDim.x);
@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_trace(RbDeviceBvh bvh, Rb
 						const float4 o = pb.rayO[slot], d = pb.rayD[slot];
 						ray = rb_make_ray(V3{o.x, o.y, o.z}, V3{d.x, d.y, d.z});
 						rb_traversal_init(T, bvh, 0.0001f, 1e8f, st);
+						if(ROOTS == RB_ROOTS_MASK) T.root = int(rb_roots_pretest<COUNT>(bvh, ray, 0.0001f, 1e8f, wp));
 						active = true;
 					}
 				}
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_trace(RbDeviceBvh bvh, Rb
 				if(wantsLeaf) finished = rb_phase_leaf<false, COUNT>(T, bvh, ray, wp);
 			} else if(active && !wantsLeaf) {
 				for(int k = 0; k < nodeSteps; ++k) {
-					finished = rb_phase_node<COUNT, ORDERED, BLOCKS>(T, bvh, ray, st, wp);
+					finished = rb_phase_node<COUNT, ORDERED, ROOTS>(T, bvh, ray, st, wp);
 					if(finished || rb_wants_leaf(T)) break;
 				}
 			}
@@ -412,7 +413,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK, RB_PT_SHADE_MIN_BLOCKS) rb_k_pt_s
 // unmasked (or UV-less) occluder blocks, a masked one is looked up in its alpha channel and walked through when
 // alpha < 0.01. When no object of the scene is masked the walk degenerates to "is there any hit", so the any-hit
 // traversal (identical accept/reject decisions, early exit) is used instead (MASKED = false).
-template<bool MASKED, bool ORDERED, bool BLOCKS, bool COUNT = false>
+template<bool MASKED, bool ORDERED, int ROOTS, bool COUNT = false>
 __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shadow(RbDeviceBvh bvh, RbPathBuffers pb, RbSceneDev sc, uint32_t did, int threshold, int leafVotes, int nodeSteps, unsigned long long * __restrict__ stats) {
 	extern __shared__ int s_stack[];
 	const RbStack st		= rb_make_stack(s_stack + threadIdx.x, blockDim.x);
@@ -449,6 +450,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shadow(RbDeviceBvh bvh, R
 						if(maxDist > 0.0f) {
 							ray = rb_make_ray(lpos, dir);
 							rb_traversal_init(T, bvh, 0.001f, maxDist, st);
+							if(ROOTS == RB_ROOTS_MASK) T.root = int(rb_roots_pretest<COUNT>(bvh, ray, 0.001f, maxDist, wp));
 							active = true;
 							++queries;
 						} else {
@@ -475,7 +477,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shadow(RbDeviceBvh bvh, R
 				if(wantsLeaf) done = rb_phase_leaf<!MASKED, COUNT>(T, bvh, ray, wp);
 			} else if(active && !wantsLeaf) {
 				for(int k = 0; k < nodeSteps; ++k) {
-					done = rb_phase_node<COUNT, ORDERED, BLOCKS>(T, bvh, ray, st, wp);
+					done = rb_phase_node<COUNT, ORDERED, ROOTS>(T, bvh, ray, st, wp);
 					if(done || rb_wants_leaf(T)) break;
 				}
 			}
@@ -497,6 +499,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shadow(RbDeviceBvh bvh, R
 							if(maxDist > 0.0f) {
 								ray = rb_make_ray(lpos, dir);
 								rb_traversal_init(T, bvh, 0.001f, maxDist, st);
+								if(ROOTS == RB_ROOTS_MASK) T.root = int(rb_roots_pretest<COUNT>(bvh, ray, 0.001f, maxDist, wp));
 								finished = false;
 								++queries;
 							} else {
@@ -930,15 +933,21 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 		st = rb_pt_grid(rb_k_pt_shade, 0, pt->sms, gridShade);
 		if(st) return st;
 		const bool blocks = rc->dev.rootLevels > 0; // many-mesh scenes: kernels compiled with the root-block skipping
-		auto kTrace = blocks ? (ordered ? rb_k_pt_trace<true, true> : rb_k_pt_trace<false, true>) : (ordered ? rb_k_pt_trace<true, false> : rb_k_pt_trace<false, false>);
-		if(profCounting) kTrace = ordered ? rb_k_pt_trace<true, false, true> : rb_k_pt_trace<false, false, true>; // plain root loop: same tests, counted
+		// A handful of roots (<= 32): all box-tested when a ray starts instead of lazily in the middle of its traversal.
+		// Not in the near-child-first order of closest-hit rays, which tests roots against the shrinking maxi.
+		const bool maskRoots = !blocks && rc->dev.nroots >= 2 && rc->dev.nroots <= 32 && !std::getenv("RB_PT_LAZY_ROOTS");
+		auto kTrace = blocks ? (ordered ? rb_k_pt_trace<true, RB_ROOTS_BLOCKS> : rb_k_pt_trace<false, RB_ROOTS_BLOCKS>)
+							 : (ordered ? rb_k_pt_trace<true, RB_ROOTS_LAZY> : (maskRoots ? rb_k_pt_trace<false, RB_ROOTS_MASK> : rb_k_pt_trace<false, RB_ROOTS_LAZY>));
+		if(profCounting) kTrace = ordered ? rb_k_pt_trace<true, RB_ROOTS_LAZY, true> : (maskRoots ? rb_k_pt_trace<false, RB_ROOTS_MASK, true> : rb_k_pt_trace<false, RB_ROOTS_LAZY, true>); // (block skipping: plain root loop, same hits, counted)
 		st = rb_pt_grid(kTrace, smem, pt->sms, gridTrace);
 		if(st) return st;
 		const bool masked = sc->dev.anyMasked != 0;
 		// Unmasked scenes use any-hit shadow rays, whose result is order independent: always near-child-first.
-		auto kShadow = blocks ? (masked ? (ordered ? rb_k_pt_shadow<true, true, true> : rb_k_pt_shadow<true, false, true>) : rb_k_pt_shadow<false, true, true>)
-							  : (masked ? (ordered ? rb_k_pt_shadow<true, true, false> : rb_k_pt_shadow<true, false, false>) : rb_k_pt_shadow<false, true, false>);
-		if(profCounting) kShadow = masked ? (ordered ? rb_k_pt_shadow<true, true, false, true> : rb_k_pt_shadow<true, false, false, true>) : rb_k_pt_shadow<false, true, false, true>;
+		// The shadow wavefront keeps the lazy root loop: most of its walks end at the first occluder, before the other roots
+		// are looked at (measured: +5 % with the pretest, against -3 % for the closest-hit wavefront).
+		auto kShadow = blocks ? (masked ? (ordered ? rb_k_pt_shadow<true, true, RB_ROOTS_BLOCKS> : rb_k_pt_shadow<true, false, RB_ROOTS_BLOCKS>) : rb_k_pt_shadow<false, true, RB_ROOTS_BLOCKS>)
+							  : (masked ? (ordered ? rb_k_pt_shadow<true, true, RB_ROOTS_LAZY> : rb_k_pt_shadow<true, false, RB_ROOTS_LAZY>) : rb_k_pt_shadow<false, true, RB_ROOTS_LAZY>);
+		if(profCounting) kShadow = masked ? (ordered ? rb_k_pt_shadow<true, true, RB_ROOTS_LAZY, true> : rb_k_pt_shadow<true, false, RB_ROOTS_LAZY, true>) : rb_k_pt_shadow<false, true, RB_ROOTS_LAZY, true>;
 		st = rb_pt_grid(kShadow, smem, pt->sms, gridShadow);
 		if(st) return st;
 		const bool wideShadow  = wideTrace && !masked; // masked scenes need the closest occluder: binary kernel

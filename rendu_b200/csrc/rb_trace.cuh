@@ -216,8 +216,41 @@ RB_D void rb_traversal_init(RbTraversal & T, const RbDeviceBvh & bvh, float mini
 // NaN-carrying irregular rays take the plain loop. BLOCKS is a template switch: with the block code inlined the node
 // step of every kernel runs 15 % slower (register allocation of the hot loop; out of line it is worse still, the call
 // forces the traversal state into local memory), so only handles that carry blocks launch the BLOCKS = true kernels.
-template<bool REGULAR, bool COUNT, bool BLOCKS>
+#define RB_ROOTS_LAZY 0	  // every root box-tested when the ray gets to it
+#define RB_ROOTS_BLOCKS 1 // ... with whole blocks of consecutive roots skipped on a miss (many-mesh scenes)
+#define RB_ROOTS_MASK 2	  // at most 32 roots, all box-tested when the ray starts (rb_roots_pretest): T.root is the bit mask of those entered
+
+// The reference box-tests EVERY root against the caller's (mini, maxi) before it pops the first one (Raycaster.cpp:149-155).
+// For a handful of roots the same is done here, up front: the tests are independent (their loads overlap), where the lazy
+// loop pays one dependent load-test-branch round trip per root in the middle of the traversal — in a scene of seven meshes
+// that was 40 % of the closest-hit wavefront's instructions and most of its serial latency. Same tests, same (mini, maxi),
+// same order of the roots entered: same hits. Callers use it for nroots <= 32 in the reference's visiting order.
+template<bool REGULAR, bool COUNT>
+RB_D unsigned int rb_roots_pretest_t(const RbDeviceBvh & bvh, const RbRay & ray, float mini, float maxi, RbWork * work) {
+	unsigned int mask = 0u;
+	for(int r = 0; r < bvh.nroots; ++r) {
+		const float4 r0 = rb_ldg4(bvh.roots + 2 * r);
+		const float4 r1 = rb_ldg4(bvh.roots + 2 * r + 1);
+		if(rb_box_test_t<REGULAR>(ray, r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, mini, maxi)) mask |= 1u << r;
+	}
+	if(COUNT) work->roots += (unsigned int)bvh.nroots;
+	return mask;
+}
+template<bool COUNT>
+RB_D unsigned int rb_roots_pretest(const RbDeviceBvh & bvh, const RbRay & ray, float mini, float maxi, RbWork * work) {
+	return ray.regular ? rb_roots_pretest_t<true, COUNT>(bvh, ray, mini, maxi, work) : rb_roots_pretest_t<false, COUNT>(bvh, ray, mini, maxi, work);
+}
+
+template<bool REGULAR, bool COUNT, int ROOTS>
 RB_D int rb_next_root(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ray, float maxi, RbWork * work) {
+	if(ROOTS == RB_ROOTS_MASK) {
+		const unsigned int mask = (unsigned int)T.root;
+		if(mask == 0u) return RB_REF_NONE;
+		const int r = 31 - __clz(mask); // last mesh first
+		T.root		= int(mask & ~(1u << r));
+		return __float_as_int(rb_ldg4(bvh.roots + 2 * r).w);
+	}
+	const bool BLOCKS = ROOTS == RB_ROOTS_BLOCKS;
 	while(T.root > 0) {
 		const int r = T.root - 1;
 		if(BLOCKS && REGULAR && bvh.rootLevels > 0) {
@@ -442,14 +475,14 @@ RB_D void rb_node_test(const RbRay & ray, const float4 & n0, const float4 & n1, 
 RB_D bool rb_wants_leaf(const RbTraversal & T) { return T.cur < 0; }
 
 // Returns true when the traversal has finished (no node left).
-template<bool COUNT, bool ORDERED, bool REGULAR, bool BLOCKS>
+template<bool COUNT, bool ORDERED, bool REGULAR, int ROOTS>
 RB_D bool rb_phase_node_t(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ray, const RbStack & st, RbWork * work) {
 	int cur = T.cur;
 	if(cur == RB_REF_NONE) {
 		if(!rb_stack_empty(T, st)) {
 			cur = rb_pop(T, st);
 		} else {
-			cur = rb_next_root<REGULAR, COUNT, BLOCKS>(T, bvh, ray, ORDERED ? T.maxi : T.maxi0, work);
+			cur = rb_next_root<REGULAR, COUNT, ROOTS>(T, bvh, ray, ORDERED ? T.maxi : T.maxi0, work);
 			if(cur == RB_REF_NONE) return true;
 		}
 	}
@@ -513,10 +546,10 @@ RB_D bool rb_phase_leaf(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & 
 	return false;
 }
 
-template<bool COUNT, bool ORDERED, bool BLOCKS = false>
+template<bool COUNT, bool ORDERED, int ROOTS = RB_ROOTS_LAZY>
 RB_D bool rb_phase_node(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ray, const RbStack & st, RbWork * work) {
-	if(ray.regular) return rb_phase_node_t<COUNT, ORDERED, true, BLOCKS>(T, bvh, ray, st, work);
-	return rb_phase_node_t<COUNT, ORDERED, false, BLOCKS>(T, bvh, ray, st, work);
+	if(ray.regular) return rb_phase_node_t<COUNT, ORDERED, true, ROOTS>(T, bvh, ray, st, work);
+	return rb_phase_node_t<COUNT, ORDERED, false, ROOTS>(T, bvh, ray, st, work);
 }
 
 // One traversal step. The NaN-faithful box test is only compiled into the copy taken by irregular rays (a direction
