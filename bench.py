@@ -556,7 +556,9 @@ def pt_config(world, spp, split, trace_mode="exact"):
                         "shadowed point light, NEE on) with the 1,002,528-triangle displaced grid as floor; PathTracer::render" % spp,
             "width": PT_W, "height": PT_H, "spp": spp, "depth": PT_DEPTH, "triangles": 2 * GRID_N * GRID_N + 12, "split": split if world > 1 else "none", "trace_mode": trace_mode,
             "parallelism": "replicated scene, %d rank(s)%s" % (world, "" if world == 1 else (", tile split (2-row bands dealt round-robin), bands gathered on rank 0" if split == "tile" else ", sample split, one NCCL reduce of the fp32 sums")),
-            "l2": "no explicit flush: every bounce streams the wavefront state of a batch (32 Mi paths x 176 B = 5.9 GB) through HBM, far beyond the 126 MB L2"}
+            "l2": "no explicit flush: every bounce streams the wavefront state of a batch (32 Mi paths x 176 B = 5.9 GB) through HBM, far beyond the 126 MB L2",
+            "frames": "one GPU renders the 256-spp frame of BASELINE configs[2], N > 1 the 4096-spp frame of configs[3] (override: --spp): same scene, same rate metric; "
+                      "per-frame fixed costs (ray generation, accumulation, batch ramp-up) weigh 16 x less in the longer frame, so v_N / (N v_1) may exceed 1 by a few percent"}
 
 
 def pt_roofline(pt, cam, opts, rays_scale=1.0):
