@@ -158,6 +158,12 @@ RB_API rb_status rb_raycaster_refit(rb_raycaster * rc, const float * world_posit
  * rb_raycaster_add_mesh calls (not rb_raycaster_upload_bvh, which carries no per-mesh vertex ranges). */
 RB_API rb_status rb_raycaster_update_mesh(rb_raycaster * rc, uint32_t mesh, const float * positions, size_t nverts, const float * model);
 
+/* When to stop re-fitting: out[0] = surface-area cost of the hierarchy as built (sum over interior nodes of the areas of
+ * their two child boxes — proportional to the number of child boxes a random line enters), out[1] = the same after the last
+ * refit. A refit keeps the topology, so out[1] / out[0] grows as objects move apart from where the tree put them;
+ * rb_scene_sync rebuilds instead of re-fitting once the ratio passes 2 (RB_REBUILD_RATIO overrides). */
+RB_API rb_status rb_raycaster_tree_cost(rb_raycaster * rc, double out[2]);
+
 /* Device time (CUDA events, milliseconds) of the last hierarchy build (out[0]; 0 for RB_BUILD_REFERENCE, which builds on
  * the host) and of the last refit (out[1]), excluding host packing and host-device copies. */
 RB_API rb_status rb_raycaster_build_times(const rb_raycaster * rc, double out[2]);

@@ -106,6 +106,7 @@ def lib():
         "rb_raycaster_wide_download": (C.c_int, [vp, vp, vp, vp]),
         "rb_raycaster_wide_download_by_octant": (C.c_int, [vp, vp]),
         "rb_raycaster_build_times": (C.c_int, [vp, vp]),
+        "rb_raycaster_tree_cost": (C.c_int, [vp, vp]),
         "rb_raycaster_intersect": (C.c_int, [vp, vp, vp, f32, f32, sz, vp]),
         "rb_raycaster_intersect_any": (C.c_int, [vp, vp, vp, f32, f32, sz, vp]),
         "rb_raycaster_visible": (C.c_int, [vp, vp, vp, sz, vp]),

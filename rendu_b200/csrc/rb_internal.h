@@ -81,6 +81,10 @@ struct rb_raycaster {
 	std::vector<uint64_t> meshVertFirst, meshVerts; // per mesh: first vertex and vertex count in `verts` (addMesh order)
 	int maxDepth	   = 0; // max number of interior nodes on a root-to-leaf path
 	bool built		   = false;
+	// rb_raycaster_tree_cost: surface-area cost of the tree when it was built and after the last refit
+	double areaAtBuild = 0.0, areaNow = 0.0;
+	uint64_t areaSerial = ~uint64_t(0);
+	bool areaStale = false;
 	uint64_t buildSerial = 0; // counts successful builds / uploads: the triangle order changed (rb_scene keys its per-triangle records to it)
 	bool hostMirrorStale = false; // device tree newer than the host mirror (after LBVH build / refit)
 	bool triBoxesStale	 = false; // `verts` changed since the boxes in `tris` were computed (refit): redone before a rebuild

@@ -1027,6 +1027,12 @@ extern "C" rb_status rb_raycaster_refit(rb_raycaster * rc, const float * world_p
 		rb_wide_free_device(rc);
 	}
 	rc->wide.reset();
+	if(rc->areaSerial != rc->buildSerial) { // baseline of rb_raycaster_tree_cost: the tree as built, taken before the first refit touches it
+		double built[2];
+		rb_status as = rb_raycaster_tree_cost(rc, built);
+		if(as) return as;
+	}
+	rc->areaStale = true;
 	return rb_lbvh_refit(rc, world_positions, nverts);
 }
 
@@ -1620,3 +1626,61 @@ extern "C" rb_status rb_kat_triangle_test(const float * positions, const float *
 	RB_CUDA(cudaStreamSynchronize(s));
 	return RB_OK;
 }
+
+// ---------------------------------------------------------------- when to stop re-fitting
+// A refit keeps the topology, so after large motions boxes of unrelated triangles overlap and rays enter more of them.
+// The measure is the surface-area cost of the tree the traversal actually walks: the sum, over interior nodes, of the
+// areas of their two child boxes (the expected number of child boxes a random line enters is proportional to it). It is
+// taken after every build (the baseline) and can be taken again after a refit; the ratio says how much more box-entering
+// work the re-fitted tree asks for than when it was built.
+__global__ void rb_k_tree_area(const float4 * __restrict__ nodes, size_t ninterior, double * __restrict__ out) {
+	double acc = 0.0;
+	for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ninterior; i += (size_t)gridDim.x * blockDim.x) {
+		const float4 n0 = nodes[4 * i], n1 = nodes[4 * i + 1], n2 = nodes[4 * i + 2];
+		const float lx = n0.w - n0.x, ly = n1.x - n0.y, lz = n1.y - n0.z;
+		const float rx = n2.y - n1.z, ry = n2.z - n1.w, rz = n2.w - n2.x;
+		// empty / inverted boxes (never produced by the fit kernel for real children) count as zero
+		if(lx >= 0.0f && ly >= 0.0f && lz >= 0.0f) acc += double(lx) * ly + double(ly) * lz + double(lz) * lx;
+		if(rx >= 0.0f && ry >= 0.0f && rz >= 0.0f) acc += double(rx) * ry + double(ry) * rz + double(rz) * rx;
+	}
+	for(int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+	if((threadIdx.x & 31u) == 0) atomicAdd(out, acc);
+}
+
+rb_status rb_tree_area(const rb_raycaster * rc, double * area) {
+	*area = 0.0;
+	if(rc->nInterior == 0) return RB_OK;
+	RB_CUDA(cudaSetDevice(rc->device));
+	cudaStream_t s = cudaStreamPerThread;
+	Scratch scratch(s);
+	double * d_a = nullptr;
+	RB_CUDA(scratch.alloc(&d_a, sizeof(double)));
+	RB_CUDA(cudaMemsetAsync(d_a, 0, sizeof(double), s));
+	rb_k_tree_area<<<592, 256, 0, s>>>(rc->dev.nodes, rc->nInterior, d_a);
+	RB_CUDA(cudaGetLastError());
+	RB_CUDA(cudaMemcpyAsync(area, d_a, sizeof(double), cudaMemcpyDeviceToHost, s));
+	RB_CUDA(cudaStreamSynchronize(s));
+	return RB_OK;
+}
+
+extern "C" rb_status rb_raycaster_tree_cost(rb_raycaster * rc, double out[2]) {
+	rb_status st = rb_check_query(rc, "rb_raycaster_tree_cost");
+	if(st) return st;
+	if(!out) return rb_fail(RB_ERR_INVALID, "rb_raycaster_tree_cost: null output");
+	if(rc->areaSerial != rc->buildSerial) { // first question since this build: the tree as built IS the baseline, unless it was re-fitted already
+		st = rb_tree_area(rc, &rc->areaAtBuild);
+		if(st) return st;
+		rc->areaSerial = rc->buildSerial;
+		rc->areaNow	   = rc->areaAtBuild;
+		rc->areaStale  = false;
+	}
+	if(rc->areaStale) {
+		st = rb_tree_area(rc, &rc->areaNow);
+		if(st) return st;
+		rc->areaStale = false;
+	}
+	out[0] = rc->areaAtBuild;
+	out[1] = rc->areaNow;
+	return RB_OK;
+}
+

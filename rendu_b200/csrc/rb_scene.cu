@@ -339,6 +339,18 @@ extern "C" rb_status rb_scene_sync(rb_scene * sc) {
 	if(moved) {
 		rb_status fs = rb_raycaster_refit(sc->raycaster, nullptr, 0);
 		if(fs) return fs;
+		// Refit or rebuild? The refit keeps the topology; once the boxes of the re-fitted tree offer twice the surface they
+		// did when the tree was built (rb_raycaster_tree_cost), traversal pays more every frame than one rebuild costs: the
+		// scene is committed again from the current matrices — the tree a fresh scene with these transforms would get.
+		double cost[2] = {0.0, 0.0};
+		fs = rb_raycaster_tree_cost(sc->raycaster, cost);
+		if(fs) return fs;
+		const char * e	   = std::getenv("RB_REBUILD_RATIO");
+		const double limit = e ? std::atof(e) : 2.0;
+		if(limit > 0.0 && cost[0] > 0.0 && cost[1] > limit * cost[0]) {
+			sc->rebuilds++;
+			return rb_scene_commit(sc, rb_build_mode(sc->raycaster->buildMode));
+		}
 	}
 	cudaFree(sc->d_lights);
 	sc->d_lights = nullptr;

@@ -26,6 +26,7 @@ struct rb_scene {
 	int32_t skyLut	 = -1;
 	bool committed	 = false;
 	bool geometryCommitted = false; // objects/textures are on the device; lights / background may still be stale
+	uint64_t rebuilds = 0;			// times rb_scene_sync chose a rebuild over a refit
 	uint64_t editSerial = 0;		// bumped by every call that changes the scene (replicas on other GPUs are keyed to it)
 	uint64_t triShadeSerial = 0;	// rb_raycaster::buildSerial the per-triangle shading records were gathered for
 	bool tablesDirty = false;		// lights or background changed since the last upload (rb_scene_sync)

@@ -98,6 +98,12 @@ class Raycaster:
         m = None if model is None else np.ascontiguousarray(np.asarray(model, np.float32).reshape(16))
         check(lib().rb_raycaster_update_mesh(self._h, int(mesh), ptr(pos), pos.shape[0], ptr(m) if m is not None else None))
 
+    def tree_cost(self):
+        """Surface-area cost of the hierarchy as built and after the last refit (rebuild when the ratio gets large)."""
+        out = np.zeros(2, np.float64)
+        check(lib().rb_raycaster_tree_cost(self._h, ptr(out)))
+        return dict(at_build=float(out[0]), now=float(out[1]), ratio=float(out[1] / out[0]) if out[0] > 0 else 1.0)
+
     def build_times(self):
         out = np.zeros(2, np.float64)
         check(lib().rb_raycaster_build_times(self._h, ptr(out)))

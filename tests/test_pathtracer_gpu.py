@@ -444,3 +444,44 @@ def test_live_session_refines_on_the_device_and_ends_at_the_one_shot_frame():
     assert done == 1 and not np.array_equal(img2, previews[0])
     with pytest.raises(rb.RenduError):
         pt.live_pass(cam, 64, 4, 128)
+
+
+def test_scene_sync_rebuilds_instead_of_refitting_when_the_tree_cost_doubles(monkeypatch):
+    """rb_raycaster_tree_cost + the policy in rb_scene_sync ('nothing decides refit-vs-rebuild'): a small
+    motion re-fits (cost ratio stays near 1, the hierarchy keeps its build), a large one — objects thrown far apart from where
+    the tree put them — makes the re-fitted boxes more than twice as large and the scene is committed again: the cost is back
+    at the baseline of a fresh build and the frame equals that of a scene created with the new transforms."""
+    desc, cam = wl.cornell_synthetic(32, 64, 32), wl.cornell_camera(1.0)
+    sc = rpt.Scene(desc)
+    pt = rpt.PathTracer(sc)
+    c0 = sc.raycaster().tree_cost()
+    assert c0["at_build"] > 0 and c0["ratio"] == 1.0
+
+    def moved_model(dx, dy, dz, s=1.0):
+        m = np.eye(4, dtype=np.float32)
+        m[0, 0] = m[1, 1] = m[2, 2] = s
+        m[3, :3] = [dx, dy, dz]
+        return m.reshape(16)
+
+    sc.set_object_transform(5, moved_model(0.02, 0.0, 0.01))  # the metal panel, nudged: a refit
+    c1 = sc.raycaster().tree_cost()
+    assert c1["at_build"] == c0["at_build"] and 0.9 < c1["ratio"] < 1.5
+    monkeypatch.setenv("RB_REBUILD_RATIO", "0")  # policy off: the refit has to live with the stretched boxes
+    sc.set_object_transform(0, moved_model(0.0, 0.0, 0.0, 6.0))  # the 2k-triangle floor blown up six-fold
+    stretched = sc.raycaster().tree_cost()
+    assert stretched["ratio"] > 2.0
+    a = np.zeros((48, 48, 3), np.float32)
+    pt.render(cam, 16, 4, a, rpt.make_opts(seed=3))
+    monkeypatch.delenv("RB_REBUILD_RATIO")
+    sc.set_object_transform(0, moved_model(0.0, 0.0, 0.0, 6.000001))  # any further edit: the sync now rebuilds
+    rebuilt = sc.raycaster().tree_cost()
+    assert rebuilt["ratio"] == 1.0 and rebuilt["at_build"] != c0["at_build"]
+    b = np.zeros((48, 48, 3), np.float32)
+    pt.render(cam, 16, 4, b, rpt.make_opts(seed=3))
+    fresh_desc = wl.cornell_synthetic(32, 64, 32)
+    fresh_desc["objects"][0]["model"] = moved_model(0.0, 0.0, 0.0, 6.000001)
+    fresh_desc["objects"][5]["model"] = moved_model(0.02, 0.0, 0.01)
+    c = np.zeros((48, 48, 3), np.float32)
+    rpt.PathTracer(rpt.Scene(fresh_desc)).render(cam, 16, 4, c, rpt.make_opts(seed=3))
+    assert np.array_equal(b, c)  # the rebuilt scene IS the fresh scene
+    assert np.isfinite(a).all() and np.abs(a - b).mean() < 0.05  # and the re-fitted tree rendered (almost) the same frame, only slower
