@@ -20,6 +20,7 @@ static inline unsigned int __float_as_uint(float f) { unsigned int v; std::memcp
 static inline int __float_as_int(float f) { int v; std::memcpy(&v, &f, 4); return v; }
 static inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
 static inline int __ffs(unsigned int v) { return __builtin_ffs(int(v)); }
+static inline int __clz(unsigned int v) { return v ? __builtin_clz(v) : 32; }
 static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 template<typename T> static inline T __ldg(const T * p) { return *p; }
 // PRMT: result byte i = byte (selector nibble i) of the eight bytes {a (0-3), b (4-7)} (no sign-replication modes used).

@@ -78,8 +78,22 @@ extern "C" int rb_hc_binary_trace(const float * nodes, const float * tris, const
 		const RbRay ray = rb_make_ray(V3{org[3 * i], org[3 * i + 1], org[3 * i + 2]}, V3{dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]});
 		RbTraversal T;
 		rb_traversal_init(T, bvh, mini, maxi, st);
+		// mode 2: the phase-split steps with the roots box-tested up front (RB_ROOTS_MASK, what the path tracer's closest-hit
+		// wavefront runs on scenes of at most 32 meshes); reference order only.
+		if(mode == 2) T.root = int(rb_roots_pretest<false>(bvh, ray, mini, maxi, nullptr));
 		bool done = false;
 		for(long guard = 0; !done && guard < 100000000; ++guard) {
+			if(mode == 2) {
+				if(rb_wants_leaf(T)) {
+					done = anyHit ? rb_phase_leaf<true, false>(T, bvh, ray, nullptr) : rb_phase_leaf<false, false>(T, bvh, ray, nullptr);
+				} else {
+					for(int k = 0; k < nodeSteps && !done; ++k) {
+						done = rb_phase_node<false, false, RB_ROOTS_MASK>(T, bvh, ray, st, nullptr);
+						if(rb_wants_leaf(T)) break;
+					}
+				}
+				continue;
+			}
 			if(mode == 0) {
 				if(anyHit) done = ordered ? rb_step<true, false, true>(T, bvh, ray, st, nullptr) : rb_step<true, false, false>(T, bvh, ray, st, nullptr);
 				else done = ordered ? rb_step<false, false, true>(T, bvh, ray, st, nullptr) : rb_step<false, false, false>(T, bvh, ray, st, nullptr);

@@ -41,7 +41,7 @@ def flatten(r):
     return np.ascontiguousarray(out), t, roots, r.sizes()["depth"] + 1, tris
 
 
-@pytest.mark.parametrize("mode,steps", [(0, 1), (1, 1), (1, 6)])
+@pytest.mark.parametrize("mode,steps", [(0, 1), (1, 1), (1, 6), (2, 4)])  # 2: roots box-tested up front (RB_ROOTS_MASK, the path tracer's closest-hit wavefront)
 @pytest.mark.parametrize("case", ["raycast_grid37", "raycast_multimesh", "raycast_degenerate"])
 def test_binary_traversal_source_returns_the_reference_hits(case, mode, steps):
     L = _host_check()
@@ -70,6 +70,10 @@ def test_binary_traversal_source_returns_the_reference_hits(case, mode, steps):
         assert np.array_equal(tuv[h, k].view(np.uint32), c[name][h].view(np.uint32)), name
     assert np.array_equal(records["localId"][tri[h]].astype(np.int64), c["local_id"][h].astype(np.int64))
     assert np.array_equal(records["meshId"][tri[h]].astype(np.int64), c["mesh_id"][h].astype(np.int64))
+    if mode == 2:  # the up-front root tests exist in the reference's order only
+        tri_any, _ = run(1, 0)
+        assert np.array_equal(tri_any >= 0, c["any"].astype(bool))
+        return
     # any hit: exact order and near child first give the reference's flags
     for ordered in (0, 1):
         tri_any, _ = run(1, ordered)
