@@ -1,7 +1,7 @@
 """World-size-2 gloo tests (CPU) of the multi-GPU plumbing: tile split gathers disjoint bands into the exact
 single-process image; sample split reduces per-rank sums into the single-process sums (fp32 order aside).
 The local renderer is the ORACLE here (there is no GPU in this container) — the CUDA path is exercised under NCCL by
-bench.py --workload pathtrace on the B200 box and by tests/test_pathtracer_gpu.py for the split options themselves."""
+bench.py --gpus N (torchrun) on the B200 box and by tests/test_pathtracer_gpu.py for the split options themselves."""
 import os
 import socket
 

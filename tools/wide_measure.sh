@@ -1,10 +1,10 @@
 #!/bin/bash
-# First GPU call of the next round (one B200): parity of the eight-wide kernels, their timing against the default
+# The eight-wide kernels on one B200 (first run: round 2): parity of the eight-wide kernels, their timing against the default
 # scheduler on C2, and an ncu capture of the incoherent closest-hit launch of the best one. Outputs land in gpurun_out/.
 #   gpurun --timeout 900 -- 'bash tools/wide_measure.sh'
 set -u
 mkdir -p gpurun_out
-RB_TEST_UNVERIFIED=1 timeout -k 5 300 python -m pytest tests/test_wide.py tests/test_raycaster_gpu.py -q -m gpu > gpurun_out/wide_tests.log 2>&1; echo "tests rc=$?" | tee -a gpurun_out/wide_tests.log
+timeout -k 5 300 python -m pytest tests/test_wide.py tests/test_raycaster_gpu.py -q -m gpu > gpurun_out/wide_tests.log 2>&1; echo "tests rc=$?" | tee -a gpurun_out/wide_tests.log
 RB_EXPLORE_ONLY=phased_v6_t12_s6,wide timeout 300 python bench.py --explore 2>&1 | grep "\[explore\]" | tee gpurun_out/wide_explore.log
 cp gpurun_out/explore.json gpurun_out/wide_explore.json 2>/dev/null
 # Launch list and full capture of the wide kernel alone (first variant = the one profiled): never a bench number.
