@@ -445,6 +445,27 @@ def raycast_block(args, R, steps, with_cpu):
         fa.result()
         fb.result()
 
+    # ... and with the asynchronous forms from ONE host thread: the four calls queue up in call order on the thread's ring —
+    # closest-hit (download-heavy) first, any-hit (upload only) last — and overlap into max(up, down) on the link.
+    h_hits_i = torch.empty(n * 48, dtype=torch.uint8).pin_memory()
+    h_any_i = torch.empty(n, dtype=torch.uint8).pin_memory()
+
+    def e2e_step_async():
+        check(L.rb_raycaster_intersect_async(rc._h, h_co.data_ptr(), h_cd.data_ptr(), MINI, MAXI, n, h_hits2.data_ptr()))
+        check(L.rb_raycaster_intersect_async(rc._h, h_io.data_ptr(), h_id.data_ptr(), MINI, MAXI, n, h_hits_i.data_ptr()))
+        check(L.rb_raycaster_intersect_any_async(rc._h, h_co.data_ptr(), h_cd.data_ptr(), MINI, MAXI, n, h_any.data_ptr()))
+        check(L.rb_raycaster_intersect_any_async(rc._h, h_io.data_ptr(), h_id.data_ptr(), MINI, MAXI, n, h_any_i.data_ptr()))
+        check(L.rb_raycaster_sync(rc._h))
+
+    e2e_step_async()
+    async_equal = bool(torch.equal(h_hits2, d_hit_c.cpu()) and torch.equal(h_hits_i, d_hit_i.cpu()) and torch.equal(h_any, d_any_c.cpu()) and torch.equal(h_any_i, d_any_i.cpu()))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e2e_step_async()
+    barrier()
+    e2e_async_s = time.perf_counter() - t0
+
     e2e_step_primary()
     primary_equal = bool(torch.equal(h_hits2, d_hit_c.cpu()))
     barrier()
@@ -454,10 +475,10 @@ def raycast_block(args, R, steps, with_cpu):
     barrier()
     e2e_primary_s = time.perf_counter() - t0
 
-    times = torch.tensor([total_ms, e2e_s * 1e3, e2e_primary_s * 1e3], dtype=torch.float64, device=dev)
+    times = torch.tensor([total_ms, e2e_s * 1e3, e2e_primary_s * 1e3, e2e_async_s * 1e3], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, e2e_primary_ms = float(times[0]), float(times[1]), float(times[2])
+    total_ms, e2e_ms, e2e_primary_ms, e2e_async_ms = float(times[0]), float(times[1]), float(times[2]), float(times[3])
     queries_step = 4 * n
     value = world * queries_step * steps / (total_ms * 1e-3) / 1e6
     e2e_value = world * queries_step * steps / (e2e_ms * 1e-3) / 1e6
@@ -525,6 +546,9 @@ def raycast_block(args, R, steps, with_cpu):
             "config": config_dict(world), "gpu_launches": int(gpu_launches),
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps,
                     "api": "rb_raycaster_intersect / rb_raycaster_intersect_any with pinned host buffers, closest and any calls issued from two host threads", "host_link": link,
+                    "asynchronous_calls_one_thread": {"value": world * queries_step * steps / (e2e_async_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                                                      "api": "rb_raycaster_intersect_async x2, rb_raycaster_intersect_any_async x2, rb_raycaster_sync: same host rays in, same Raycaster::Hit records out",
+                                                      "records_identical_to_resident_run": async_equal},
                     "with_device_generated_primary_rays": {"value": world * queries_step * steps / (e2e_primary_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 2 * n * 24 + 96, "d2h_bytes_per_step": d2h,
                                                            "api": "coherent set through rb_raycaster_intersect_primary / _any_primary (camera in, Raycaster::Hit records out), incoherent set as above",
                                                            "records_identical_to_host_rays": primary_equal}},

@@ -218,6 +218,15 @@ typedef struct rb_camera {
 RB_API rb_status rb_raycaster_intersect_primary(const rb_raycaster * rc, const rb_camera * camera, uint32_t width, uint32_t height, float mini, float maxi, rb_hit * out);
 RB_API rb_status rb_raycaster_intersect_any_primary(const rb_raycaster * rc, const rb_camera * camera, uint32_t width, uint32_t height, float mini, float maxi, uint8_t * out);
 
+/* Asynchronous batch queries: as rb_raycaster_intersect / _intersect_any, but the call returns as soon as its chunks are
+ * queued on the calling thread's ring; the results are complete after rb_raycaster_sync called from the same thread.
+ * Consecutive asynchronous calls of a thread queue up in call order and overlap their uploads, traversals and downloads;
+ * issue the download-heavy closest-hit queries first. The host buffers must stay valid until the sync, and should be
+ * page-locked (otherwise the copies are synchronous and nothing overlaps). */
+RB_API rb_status rb_raycaster_intersect_async(const rb_raycaster * rc, const float * origins, const float * directions, float mini, float maxi, size_t nrays, rb_hit * out);
+RB_API rb_status rb_raycaster_intersect_any_async(const rb_raycaster * rc, const float * origins, const float * directions, float mini, float maxi, size_t nrays, uint8_t * out);
+RB_API rb_status rb_raycaster_sync(const rb_raycaster * rc);
+
 /* Device-pointer variants: enqueue on `stream` (a cudaStream_t), no host synchronisation. */
 RB_API rb_status rb_raycaster_intersect_device(const rb_raycaster * rc, const float * d_origins, const float * d_directions, float mini, float maxi, size_t nrays, rb_hit * d_out, void * stream);
 RB_API rb_status rb_raycaster_intersect_any_device(const rb_raycaster * rc, const float * d_origins, const float * d_directions, float mini, float maxi, size_t nrays, uint8_t * d_out, void * stream);

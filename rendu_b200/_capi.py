@@ -110,6 +110,9 @@ def lib():
         "rb_raycaster_intersect": (C.c_int, [vp, vp, vp, f32, f32, sz, vp]),
         "rb_raycaster_intersect_any": (C.c_int, [vp, vp, vp, f32, f32, sz, vp]),
         "rb_raycaster_visible": (C.c_int, [vp, vp, vp, sz, vp]),
+        "rb_raycaster_intersect_async": (C.c_int, [vp, vp, vp, f32, f32, sz, vp]),
+        "rb_raycaster_intersect_any_async": (C.c_int, [vp, vp, vp, f32, f32, sz, vp]),
+        "rb_raycaster_sync": (C.c_int, [vp]),
         "rb_raycaster_intersect_primary": (C.c_int, [vp, C.POINTER(Camera), u32, u32, f32, f32, vp]),
         "rb_raycaster_intersect_any_primary": (C.c_int, [vp, C.POINTER(Camera), u32, u32, f32, f32, vp]),
         "rb_raycaster_ray_levels": (C.c_int, [vp, vp, vp, f32, f32, u32, vp, vp, vp, vp]),

@@ -1298,6 +1298,7 @@ struct HostPipe {
 	float * d_dir[kPipeSlotsMax]		= {};
 	void * d_out[kPipeSlotsMax]		= {};
 	bool ready = false;
+	size_t nextChunk = 0; // chunks rotate through the slots across calls, so that asynchronous calls queue up behind each other
 
 	rb_status ensure(int dev) {
 		if(ready && dev == device) return RB_OK;
@@ -1332,14 +1333,13 @@ struct HostPipe {
 thread_local HostPipe t_pipe;
 
 template<bool ANY>
-rb_status rb_host_batch(const rb_raycaster * rc, const float * origins, const float * directions, float mini, float maxi, size_t nrays, void * out) {
+rb_status rb_host_batch(const rb_raycaster * rc, const float * origins, const float * directions, float mini, float maxi, size_t nrays, void * out, bool wait = true) {
 	RB_CUDA(cudaSetDevice(rc->device));
 	rb_status st = t_pipe.ensure(rc->device);
 	if(st) return st;
 	const size_t outStride = ANY ? sizeof(uint8_t) : sizeof(rb_hit);
-	size_t chunkIdx = 0;
-	for(size_t begin = 0; begin < nrays; begin += kPipeChunk, ++chunkIdx) {
-		const int k		= int(chunkIdx % kPipeSlots);
+	for(size_t begin = 0; begin < nrays; begin += kPipeChunk) {
+		const int k = int(t_pipe.nextChunk++ % kPipeSlots);
 		const size_t n	= (nrays - begin < kPipeChunk) ? (nrays - begin) : kPipeChunk;
 		cudaStream_t s	= t_pipe.stream[k];
 		// The slot's previous chunk must have left the device before its buffers are overwritten: same stream, so
@@ -1350,10 +1350,43 @@ rb_status rb_host_batch(const rb_raycaster * rc, const float * origins, const fl
 		if(st) return st;
 		RB_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(out) + begin * outStride, t_pipe.d_out[k], n * outStride, cudaMemcpyDeviceToHost, s));
 	}
-	for(int k = 0; k < kPipeSlots; ++k) RB_CUDA(cudaStreamSynchronize(t_pipe.stream[k]));
+	if(wait) {
+		for(int k = 0; k < kPipeSlots; ++k) RB_CUDA(cudaStreamSynchronize(t_pipe.stream[k]));
+	}
 	return RB_OK;
 }
 } // namespace
+
+// Asynchronous forms: the call returns once its chunks are queued on the calling thread's ring; results are complete after
+// rb_raycaster_sync from the SAME thread. Consecutive asynchronous calls queue up behind each other in call order, so a caller
+// that issues its download-heavy queries first (closest hit: 48 bytes per ray come back) and its upload-only ones last (any
+// hit: 1 byte) keeps both directions of the host link busy from one thread — the four calls of the C2 step overlap into
+// max(up, down) instead of paying for each call's own ramp-up and drain. Host buffers must stay valid (and pinned, for the
+// copies to be asynchronous at all) until the sync.
+extern "C" rb_status rb_raycaster_intersect_async(const rb_raycaster * rc, const float * origins, const float * directions, float mini, float maxi, size_t nrays, rb_hit * out) {
+	rb_status st = rb_check_query(rc, "rb_raycaster_intersect_async");
+	if(st) return st;
+	if(nrays == 0) return RB_OK;
+	if(!origins || !directions || !out) return rb_fail(RB_ERR_INVALID, "rb_raycaster_intersect_async: null argument");
+	return rb_host_batch<false>(rc, origins, directions, mini, maxi, nrays, out, false);
+}
+
+extern "C" rb_status rb_raycaster_intersect_any_async(const rb_raycaster * rc, const float * origins, const float * directions, float mini, float maxi, size_t nrays, uint8_t * out) {
+	rb_status st = rb_check_query(rc, "rb_raycaster_intersect_any_async");
+	if(st) return st;
+	if(nrays == 0) return RB_OK;
+	if(!origins || !directions || !out) return rb_fail(RB_ERR_INVALID, "rb_raycaster_intersect_any_async: null argument");
+	return rb_host_batch<true>(rc, origins, directions, mini, maxi, nrays, out, false);
+}
+
+extern "C" rb_status rb_raycaster_sync(const rb_raycaster * rc) {
+	if(!rc) return rb_fail(RB_ERR_INVALID, "rb_raycaster_sync: null handle");
+	RB_REQUIRE_DEVICE();
+	if(!t_pipe.ready) return RB_OK; // nothing was ever queued from this thread
+	RB_CUDA(cudaSetDevice(t_pipe.device));
+	for(int k = 0; k < kPipeSlots; ++k) RB_CUDA(cudaStreamSynchronize(t_pipe.stream[k]));
+	return RB_OK;
+}
 
 // Primary rays of a pinhole camera, generated on the device: pixel (x, y) -> the ray from `eye` through the centre of the
 // pixel, with the reference's own arithmetic (PathTracer.cpp:193-198: ndc = screenPos / (W, H); worldPos = corner +
@@ -1379,9 +1412,8 @@ rb_status rb_host_primary(const rb_raycaster * rc, const rb_camera * cam, uint32
 	rb_status st = t_pipe.ensure(rc->device);
 	if(st) return st;
 	const size_t nrays = size_t(width) * height, outStride = ANY ? sizeof(uint8_t) : sizeof(rb_hit);
-	size_t chunkIdx = 0;
-	for(size_t begin = 0; begin < nrays; begin += kPipeChunk, ++chunkIdx) {
-		const int k	   = int(chunkIdx % kPipeSlots);
+	for(size_t begin = 0; begin < nrays; begin += kPipeChunk) {
+		const int k = int(t_pipe.nextChunk++ % kPipeSlots);
 		const size_t n = (nrays - begin < kPipeChunk) ? (nrays - begin) : kPipeChunk;
 		cudaStream_t s = t_pipe.stream[k];
 		rb_k_primary_rays<<<unsigned((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184), 256, 0, s>>>(*cam, width, height, begin, n, t_pipe.d_org[k], t_pipe.d_dir[k]);

@@ -489,3 +489,28 @@ def test_device_generated_primary_rays_give_the_records_of_the_same_rays_passed_
     d = np.stack([(wp[k] - F(c2["eye"][k])).astype(F).ravel() for k in range(3)], -1)
     o = np.tile(np.asarray(c2["eye"], F), (w * h, 1))
     assert r.intersects_primary(c2, w, h).tobytes() == r.intersects(o, d).tobytes()
+
+
+def test_asynchronous_batch_calls_queue_up_and_return_the_same_records():
+    """rb_raycaster_intersect_async / _any_async / rb_raycaster_sync: several calls queued from one thread, results complete
+    after the sync and identical to the blocking calls."""
+    import ctypes as C
+    from rendu_b200._capi import check, lib, ptr
+    pos, idx = wl.displaced_grid(64)
+    r = rb.Raycaster()
+    r.addMesh(pos, idx)
+    r.updateHierarchy()
+    sets = [wl.random_rays(70000, 31), wl.coherent_rays(200), wl.random_rays(5, 32)]
+    want = [(r.intersects(o, d), r.intersectsAny(o, d)) for o, d in sets]
+    outs = [(np.zeros(o.shape[0], rb.HIT_DTYPE), np.zeros(o.shape[0], np.uint8)) for o, _ in sets]
+    keep = []
+    for (o, d), (h, a) in zip(sets, outs):
+        o, d = np.ascontiguousarray(o, np.float32), np.ascontiguousarray(d, np.float32)
+        keep.append((o, d))
+        check(lib().rb_raycaster_intersect_async(r._h, ptr(o), ptr(d), 1e-4, 1e8, o.shape[0], ptr(h)))
+    for (o, d), (h, a) in zip(keep, outs):
+        check(lib().rb_raycaster_intersect_any_async(r._h, ptr(o), ptr(d), 1e-4, 1e8, o.shape[0], ptr(a)))
+    check(lib().rb_raycaster_sync(r._h))
+    for (wh, wa), (h, a) in zip(want, outs):
+        assert h.tobytes() == wh.tobytes() and np.array_equal(a.astype(bool), wa)
+    check(lib().rb_raycaster_sync(r._h))  # nothing pending: returns at once
