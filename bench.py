@@ -19,6 +19,7 @@ timed beside it). The same rate metric at every N, so the driver's v_N / (N v_1)
 Launch: python bench.py [--gpus N --steps K --warmup W]; for N > 1 under torchrun.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -783,6 +784,7 @@ def run_headline(args):
                 "rays_per_frame": rays_per_frame, "rays_per_sample": rays_per_frame / (PT_W * PT_H * spp),
                 "closest_rays_per_sample": float(t[4]) / (PT_W * PT_H * spp), "shaded_hits_per_sample": float(t[5]) / (PT_W * PT_H * spp),
                 "image": {"mean": float(img[finite].mean()), "non_finite_pixels": int((~finite).any(axis=2).sum()),
+                          "sha256": hashlib.sha256(np.ascontiguousarray(img).tobytes()).hexdigest(),
                           "note": "a non-finite pixel is reference-faithful (0 * inf in an unguarded path, PathTracer.cpp:277,288; DESIGN.md NaN fidelity)"}}
         if world > 1:
             line["multi_gpu"] = {"split": split, "combine_ms_last_frame_rank0": combine_ms,

@@ -41,7 +41,6 @@ RB_HD V3 cross3(V3 x, V3 y) { return V3{x.y * y.z - y.y * x.z, x.z * y.x - y.z *
 RB_HD float rsqrt_glm(float x) { return 1.0f / sqrtf(x); }
 RB_HD V3 normalize3(V3 v) { return v * rsqrt_glm(dot3(v, v)); }
 RB_HD float length3(V3 v) { return sqrtf(dot3(v, v)); }
-
 // Literal comparison forms (NaN-faithful): do not replace with fminf/fmaxf.
 RB_HD float glm_min(float x, float y) { return (y < x) ? y : x; }
 RB_HD float glm_max(float x, float y) { return (x < y) ? y : x; }

@@ -19,8 +19,21 @@
 
 #define RB_PT_BLOCK 128
 #ifndef RB_PT_SHADE_MIN_BLOCKS
-#define RB_PT_SHADE_MIN_BLOCKS 6 // caps the shade kernel at 80 registers: it is latency bound, occupancy matters more than spills
+#define RB_PT_SHADE_MIN_BLOCKS 7 // caps the shade kernel at 72 registers (10 bytes of spills): it is latency bound, occupancy matters
+								 // more; same-box A/B of the frame: 5 blocks (96 regs) -0.4 %, 6 (80) 0, 7 (72) +1.2 %, 8 (64, 58 B spilled) -1.6 %
 #endif
+
+// Exact division of a 32-bit number by a run-time constant d: floor(n / d) = floor(m * n / 2^64) with m = ceil(2^64 / d)
+// (Lemire, Kaser, Kurz 2019: exact for every 32-bit n and d because 64 >= 32 + 32). m does not fit for d = 1: stored as 0.
+// A hardware-free u32 division is ~20 instructions; every kernel that maps a path slot to (pixel, sample) did four.
+RB_HD uint64_t rb_div_magic(uint32_t d) { return d > 1u ? 0xFFFFFFFFFFFFFFFFull / d + 1ull : 0ull; }
+RB_HD uint32_t rb_div(uint32_t n, uint64_t m) {
+#ifdef __CUDA_ARCH__
+	return m ? uint32_t(__umul64hi(m, uint64_t(n))) : n;
+#else
+	return m ? uint32_t((unsigned __int128)m * n >> 64) : n;
+#endif
+}
 
 struct RbFrame {
 	float eye[3], corner[3], dx[3], dy[3];
@@ -33,6 +46,7 @@ struct RbFrame {
 	uint32_t tileRows, tileIndex, tileCount; // rows rendered by this call
 	uint32_t sampleIndex, sampleCount;		 // stratification cells traced by this call
 	uint32_t localRows;						 // number of rows selected by the tile split
+	uint64_t mWidth, mTileRows, mCellsX;	 // rb_div_magic of width, tileRows, cellsX
 };
 
 struct RbBatch {
@@ -40,6 +54,7 @@ struct RbBatch {
 	uint32_t npixels; // pixels in this batch
 	uint32_t sample0; // first local sample
 	uint32_t schunk;  // samples per pixel in this batch
+	uint64_t mSchunk; // rb_div_magic(schunk)
 };
 
 struct RbPathBuffers {
@@ -64,8 +79,8 @@ RB_HD uint32_t rb_cnt_cursor_s(uint32_t did) { return 4 * did + 3; }
 // Local row -> image row for the tile split (rows come in bands of tileRows, dealt round-robin to tileCount ranks).
 RB_HD uint32_t rb_tile_row(const RbFrame & f, uint32_t localRow) {
 	if(f.tileCount <= 1) return localRow;
-	const uint32_t band = localRow / f.tileRows;
-	return (band * f.tileCount + f.tileIndex) * f.tileRows + localRow % f.tileRows;
+	const uint32_t band = rb_div(localRow, f.mTileRows);
+	return (band * f.tileCount + f.tileIndex) * f.tileRows + (localRow - band * f.tileRows);
 }
 
 struct RbPathId {
@@ -73,11 +88,12 @@ struct RbPathId {
 };
 
 RB_D RbPathId rb_path_id(const RbFrame & f, const RbBatch & b, uint32_t slot) {
-	const uint32_t p	  = b.pixel0 + slot / b.schunk;
-	const uint32_t s	  = b.sample0 + slot % b.schunk;
-	const uint32_t lrow = p / f.width;
+	const uint32_t q	  = rb_div(slot, b.mSchunk);
+	const uint32_t p	  = b.pixel0 + q;
+	const uint32_t s	  = b.sample0 + (slot - q * b.schunk);
+	const uint32_t lrow = rb_div(p, f.mWidth);
 	RbPathId id;
-	id.x	 = p % f.width;
+	id.x	 = p - lrow * f.width;
 	id.y	 = rb_tile_row(f, lrow);
 	id.pixel = id.y * f.width + id.x;
 	id.sid	 = f.sampleIndex + s * f.sampleCount;
@@ -86,8 +102,8 @@ RB_D RbPathId rb_path_id(const RbFrame & f, const RbBatch & b, uint32_t slot) {
 
 // getSamplePosition (PathTracer.cpp:71-84) + the screen -> NDC step of render (:191-193).
 RB_D void rb_sample_ndc(const RbFrame & f, const RbPathId & id, uint64_t key, float & ndcx, float & ndcy) {
-	const int sidy = int(id.sid) / int(f.cellsX);
-	const int sidx = int(id.sid) % int(f.cellsX);
+	const int sidy = int(rb_div(id.sid, f.mCellsX)); // sid and cellsX are non-negative: same quotient as the int division
+	const int sidx = int(id.sid) - sidy * int(f.cellsX);
 	const float jx = rb_rng_float(key, 0);
 	const float jy = rb_rng_float(key, 1);
 	const float gx = float(sidx) + jx, gy = float(sidy) + jy;
@@ -111,8 +127,11 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_raygen(RbFrame f, RbBatch
 		const V3 rayDir	  = normalize3(worldPos - eye);		 // :198
 		pb.rayO[slot]	  = make_float4(eye.x, eye.y, eye.z, 0.0f);
 		pb.rayD[slot]	  = make_float4(rayDir.x, rayDir.y, rayDir.z, 0.0f);
-		pb.atten[slot]	  = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
-		pb.color[slot]	  = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		// The path's RNG key rides in the two spare words of its state (attenuation.w, colour.w): shading reads and writes
+		// those vectors anyway, and deriving the key again at every bounce (slot -> pixel, sample -> two hash rounds) was
+		// 7 % of the shade kernel's instructions.
+		pb.atten[slot]	  = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(uint32_t(key)));
+		pb.color[slot]	  = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(uint32_t(key >> 32)));
 		pb.queue[0][slot] = slot;
 	}
 	if(blockIdx.x == 0 && threadIdx.x == 0) pb.counters[rb_cnt_queue(0)] = n;
@@ -289,8 +308,9 @@ RB_D void rb_queue_push(uint32_t * queue, uint32_t * counter, bool want, uint32_
 
 __global__ void __launch_bounds__(RB_PT_BLOCK, RB_PT_SHADE_MIN_BLOCKS) rb_k_pt_shade(RbFrame f, RbBatch b, RbPathBuffers pb, RbSceneDev sc, uint32_t did, unsigned long long * __restrict__ stats) {
 	const uint32_t n		 = pb.counters[rb_cnt_queue(did)];
-	const uint32_t * queue	 = pb.queue[did & 1u];
-	uint32_t * nextQueue	 = pb.queue[(did + 1u) & 1u];
+	// (selected, not indexed: a run-time index into an array inside a kernel parameter costs a local-memory copy of it)
+	const uint32_t * queue	 = (did & 1u) ? pb.queue[1] : pb.queue[0];
+	uint32_t * nextQueue	 = (did & 1u) ? pb.queue[0] : pb.queue[1];
 	uint32_t * nextCounter	 = pb.counters + rb_cnt_queue(did + 1u);
 	uint32_t * shadowCounter = pb.counters + rb_cnt_shadow(did);
 	const bool lastBounce	 = (did + 1u >= f.depth);
@@ -307,15 +327,14 @@ __global__ void __launch_bounds__(RB_PT_BLOCK, RB_PT_SHADE_MIN_BLOCKS) rb_k_pt_s
 			const float4 ro = pb.rayO[slot], rd = pb.rayD[slot], at = pb.atten[slot], cl = pb.color[slot];
 			V3 rayPos = V3{ro.x, ro.y, ro.z}, rayDir = V3{rd.x, rd.y, rd.z};
 			V3 attenuation = V3{at.x, at.y, at.z}, sampleColor = V3{cl.x, cl.y, cl.z};
-			const RbPathId id  = rb_path_id(f, b, slot);
-			const uint64_t key = rb_rng_key(f.seed, id.pixel, id.sid);
+			const uint64_t key = (uint64_t(__float_as_uint(cl.w)) << 32) | uint64_t(__float_as_uint(at.w)); // written by raygen
 			const int tri	   = __float_as_int(h.w);
 			if(tri < 0) {
 				// No hit: background, then the path ends (PathTracer.cpp:206-209).
 				float ndcx = 0.0f, ndcy = 0.0f;
-				if(did == 0 && sc.bgMode == RB_BG_IMAGE) rb_sample_ndc(f, id, key, ndcx, ndcy);
+				if(did == 0 && sc.bgMode == RB_BG_IMAGE) rb_sample_ndc(f, rb_path_id(f, b, slot), key, ndcx, ndcy);
 				sampleColor += attenuation * rb_eval_background(sc, rayDir, rayPos, ndcx, ndcy, did == 0);
-				pb.color[slot] = make_float4(sampleColor.x, sampleColor.y, sampleColor.z, 0.0f);
+				pb.color[slot] = make_float4(sampleColor.x, sampleColor.y, sampleColor.z, cl.w);
 			} else {
 				RbSurface surf;
 				uint32_t meshId;
@@ -334,7 +353,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK, RB_PT_SHADE_MIN_BLOCKS) rb_k_pt_s
 					continues	  = !lastBounce;
 				} else if(obj.flags & RB_OBJ_EMISSIVE) {
 					sampleColor += attenuation * V3{bCol.x, bCol.y, bCol.z}; // :228-234
-					pb.color[slot] = make_float4(sampleColor.x, sampleColor.y, sampleColor.z, 0.0f);
+					pb.color[slot] = make_float4(sampleColor.x, sampleColor.y, sampleColor.z, cl.w);
 				} else {
 					const M3 tbn		 = rb_build_local_frame(sc, obj, surf, rayDir);
 					const V3 wo			 = normalize3(mulT(tbn, -rayDir));									// :241
@@ -352,7 +371,10 @@ __global__ void __launch_bounds__(RB_PT_BLOCK, RB_PT_SHADE_MIN_BLOCKS) rb_k_pt_s
 						const V3 direction = rb_light_sample(light, pShift, maxDist, falloff);
 						if(falloff > 0.0f) {
 							const V3 lwi		= normalize3(mulT(tbn, direction));
-							const V3 evalLight	= rb_ggx_eval(wo, baseColor, rmao.x, rmao.y, lwi);
+							// (The wi-independent terms are computed at each of the two uses: hoisted above the light
+							// block they stay live across it and the kernel spills — measured, 1 % slower.)
+							const RbGgxSurface gs = rb_ggx_surface(wo, baseColor, rmao.x, rmao.y);
+							const V3 evalLight	= rb_ggx_eval(gs, lwi);
 							const float lightPdf = 1.0f / float(sc.nLights);
 							const V3 illumination = ((falloff * evalLight) * V3{light.intensity[0], light.intensity[1], light.intensity[2]}) / lightPdf;
 							const V3 contrib	  = attenuation * illumination;
@@ -373,16 +395,17 @@ __global__ void __launch_bounds__(RB_PT_BLOCK, RB_PT_SHADE_MIN_BLOCKS) rb_k_pt_s
 						// Next direction from the BSDF (:274-285). On the last level the reference still draws it but
 						// never uses the result.
 						V3 wi;
-						const V3 eval = rb_ggx_sample_and_eval(wo, baseColor, rmao.x, rmao.y, rb_rng_float(key, dim0 + 1u), rb_rng_float(key, dim0 + 2u), rb_rng_float(key, dim0 + 3u), wi);
+						const RbGgxSurface gs = rb_ggx_surface(wo, baseColor, rmao.x, rmao.y);
+						const V3 eval = rb_ggx_sample_and_eval(gs, baseColor, rmao.y, rb_rng_float(key, dim0 + 1u), rb_rng_float(key, dim0 + 2u), rb_rng_float(key, dim0 + 3u), wi);
 						const V3 nextRayDir = normalize3(mul(tbn, wi));
 						attenuation *= eval;
 						const V3 newDir = normalize3(nextRayDir);
 						pb.rayO[slot]	= make_float4(p.x, p.y, p.z, 0.0f);
 						pb.rayD[slot]	= make_float4(newDir.x, newDir.y, newDir.z, 0.0f);
-						pb.atten[slot]	= make_float4(attenuation.x, attenuation.y, attenuation.z, 0.0f);
+						pb.atten[slot]	= make_float4(attenuation.x, attenuation.y, attenuation.z, at.w);
 						continues		= (attenuation.x != 0.0f || attenuation.y != 0.0f || attenuation.z != 0.0f);
 					}
-					pb.color[slot] = make_float4(sampleColor.x, sampleColor.y, sampleColor.z, 0.0f);
+					pb.color[slot] = make_float4(sampleColor.x, sampleColor.y, sampleColor.z, cl.w);
 				}
 			}
 		}
@@ -640,8 +663,9 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_accumulate(RbFrame f, RbB
 		}
 		if(lane == 0) {
 			const uint32_t lp	= b.pixel0 + p;
-			const uint32_t y	= rb_tile_row(f, lp / f.width);
-			const size_t pixel = size_t(y) * f.width + lp % f.width;
+			const uint32_t lr	= rb_div(lp, f.mWidth);
+			const uint32_t y	= rb_tile_row(f, lr);
+			const size_t pixel = size_t(y) * f.width + (lp - lr * f.width);
 			sum[3 * pixel + 0] += r;
 			sum[3 * pixel + 1] += g;
 			sum[3 * pixel + 2] += bl;
@@ -653,8 +677,9 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_accumulate(RbFrame f, RbB
 __global__ void rb_k_pt_resolve(RbFrame f, const float * __restrict__ sum, uint32_t components, float * __restrict__ pixels) {
 	const uint32_t n = f.localRows * f.width;
 	for(uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < n; lp += gridDim.x * blockDim.x) {
-		const uint32_t y   = rb_tile_row(f, lp / f.width);
-		const size_t pixel = size_t(y) * f.width + lp % f.width;
+		const uint32_t lr  = rb_div(lp, f.mWidth);
+		const uint32_t y   = rb_tile_row(f, lr);
+		const size_t pixel = size_t(y) * f.width + (lp - lr * f.width);
 		for(int c = 0; c < 3; ++c) {
 			const float v = pixels[pixel * components + c] + sum[3 * pixel + c];
 			pixels[pixel * components + c] = v / float(f.samples);
@@ -841,6 +866,9 @@ static rb_status rb_pt_frame(const rb_camera * cam, uint32_t width, uint32_t hei
 		if(f.tileCount <= 1 || (y / f.tileRows) % f.tileCount == f.tileIndex) ++rows;
 	}
 	f.localRows = rows;
+	f.mWidth	= rb_div_magic(f.width);
+	f.mTileRows = rb_div_magic(f.tileRows);
+	f.mCellsX	= rb_div_magic(f.cellsX);
 	return RB_OK;
 }
 
@@ -972,6 +1000,7 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 				b.npixels = uint32_t((localPixels - pixel0 < pixelsPerBatch) ? (localPixels - pixel0) : pixelsPerBatch);
 				b.sample0 = sample0;
 				b.schunk  = sc_n;
+				b.mSchunk = rb_div_magic(sc_n);
 				const int l				 = lanes > 1 ? int(batch % lanes) : 0;
 				const cudaStream_t ls	 = lanes > 1 ? pt->lane[l] : s;
 				const RbPathBuffers & pb = pt->pb[l];

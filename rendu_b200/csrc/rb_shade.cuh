@@ -84,8 +84,10 @@ RB_D void rb_wrap_pair(int x, int w, int & a, int & b) {
 }
 
 // Image::rgbal (Image.cpp:86-106): wrap-around bilinear, texel-corner convention (no half-texel offset).
-RB_D float4 rb_image_rgbal(const RbSceneDev & sc, int tex, float x, float y) {
-	const RbTexInfo ti = sc.textures[tex];
+// (Measured and not kept: this body, rb_ggx, powf and the 1/sqrt of normalize as out-of-line calls shrink the shade kernel
+// from 5.7 K to 3.9 K instructions and make it 2-8 % SLOWER each — profiles/r02_shade_diet.txt.)
+RB_D float4 rb_image_rgbal_p(const float4 * __restrict__ texels, const RbTexInfo * __restrict__ textures, int tex, float x, float y) {
+	const RbTexInfo ti = textures[tex];
 	const float xi = x * float(ti.width);
 	const float yi = y * float(ti.height);
 	const float xb = floorf(xi);
@@ -95,7 +97,7 @@ RB_D float4 rb_image_rgbal(const RbSceneDev & sc, int tex, float x, float y) {
 	int x0, x1, y0, y1;
 	rb_wrap_pair(int(xb), int(ti.width), x0, x1);
 	rb_wrap_pair(int(yb), int(ti.height), y0, y1);
-	const float4 * base = sc.texels + ti.offset;
+	const float4 * base = texels + ti.offset;
 	const float4 p00 = __ldg(base + size_t(y0) * ti.width + x0);
 	const float4 p01 = __ldg(base + size_t(y1) * ti.width + x0);
 	const float4 p10 = __ldg(base + size_t(y0) * ti.width + x1);
@@ -108,6 +110,9 @@ RB_D float4 rb_image_rgbal(const RbSceneDev & sc, int tex, float x, float y) {
 	r.w = ax * (ay * p00.w + dy * p01.w) + dx * (ay * p10.w + dy * p11.w);
 	return r;
 }
+RB_D float4 rb_image_rgbal(const RbSceneDev & sc, int tex, float x, float y) {
+	return rb_image_rgbal_p(sc.texels, sc.textures, tex, x, y);
+}
 // Image::rgbl (Image.cpp:64-84): same taps, rgb only.
 RB_D V3 rb_image_rgbl(const RbSceneDev & sc, int tex, float x, float y) {
 	const float4 r = rb_image_rgbal(sc, tex, x, y);
@@ -117,28 +122,30 @@ RB_D V3 rb_image_rgbl(const RbSceneDev & sc, int tex, float x, float y) {
 // Texture::sampleCubemap (Texture.cpp:141-191): faces px,nx,py,ny,pz,nz; one-texel clamp; bilinear on the face.
 RB_D V3 rb_sample_cubemap(const RbSceneDev & sc, const int32_t * faces, V3 dir) {
 	const float ax = fabsf(dir.x), ay = fabsf(dir.y), az = fabsf(dir.z);
-	int side = 0;
+	// The face is picked with constant indices: `faces` is an array inside a kernel parameter, and a run-time index into it
+	// makes the compiler copy the whole parameter block into local memory at the start of the kernel.
+	int tex = faces[0];
 	float x = 0.0f, y = 0.0f, denom = 1.0f;
 	if(ax >= ay && ax >= az) {
 		denom = ax;
 		y	  = dir.y;
-		if(dir.x >= 0.0f) { side = 0; x = -dir.z; } else { side = 1; x = dir.z; }
+		if(dir.x >= 0.0f) { tex = faces[0]; x = -dir.z; } else { tex = faces[1]; x = dir.z; }
 	} else if(ay >= ax && ay >= az) {
 		denom = ay;
 		x	  = dir.x;
-		if(dir.y >= 0.0f) { side = 2; y = -dir.z; } else { side = 3; y = dir.z; }
+		if(dir.y >= 0.0f) { tex = faces[2]; y = -dir.z; } else { tex = faces[3]; y = dir.z; }
 	} else if(az >= ax && az >= ay) {
 		denom = az;
 		y	  = dir.y;
-		if(dir.z >= 0.0f) { side = 4; x = dir.x; } else { side = 5; x = -dir.x; }
+		if(dir.z >= 0.0f) { tex = faces[4]; x = dir.x; } else { tex = faces[5]; x = -dir.x; }
 	}
 	x = 0.5f * (x / denom) + 0.5f;
 	y = 0.5f * (-y / denom) + 0.5f;
-	const RbTexInfo ti = sc.textures[faces[side]];
+	const RbTexInfo ti = sc.textures[tex];
 	const float eps	   = 1.0f / float(min(ti.width, ti.height));
 	x = glm_clamp(x, 0.0f + eps, 1.0f - eps);
 	y = glm_clamp(y, 0.0f + eps, 1.0f - eps);
-	return rb_image_rgbl(sc, faces[side], x, y);
+	return rb_image_rgbl(sc, tex, x, y);
 }
 
 // ---------------------------------------------------------------------------------------------- lights
@@ -200,32 +207,60 @@ RB_D float rb_ggx_V(float NdotL, float NdotV, float alpha) {
 	return 0.5f / std_max(0.0001f, visV + visL);
 }
 // MaterialGGX::GGX (MaterialGGX.cpp:30-52) including the wo/wi naming swap (NdotL = wo.z, NdotV = wi.z) and the
-// multi-scattering adjustment.
-RB_D V3 rb_ggx(V3 wo, V3 baseColor, float alpha, float metallic, V3 wi, float * pdf) {
-	const V3 h		  = normalize3(wi + wo);
+// multi-scattering adjustment. A shaded hit evaluates it twice with the same (wo, baseColor, roughness, metallic) — once
+// towards the light, once along the sampled direction — so everything that does not depend on wi is computed once
+// (RbGgxSurface: same expressions, same rounding; it only is not repeated).
+struct RbGgxSurface {
+	V3 wo, F0, oneMinusF0, diffuse;
+	float alpha, alpha2, twoAlpha2, NdotL, rootL;
+};
+RB_D RbGgxSurface rb_ggx_surface(V3 wo, V3 baseColor, float roughness, float metallic) {
+	RbGgxSurface g;
+	g.wo		 = wo;
+	g.alpha		 = rb_alpha_from_roughness(roughness);
+	g.alpha2	 = g.alpha * g.alpha;
+	g.twoAlpha2	 = 2.0f * g.alpha * g.alpha;
+	g.NdotL		 = std_max(wo.z, 0.0f);
+	g.rootL		 = sqrtf((-g.NdotL * g.alpha2 + g.NdotL) * g.NdotL + g.alpha2); // the wi-independent root of MaterialGGX::V
+	g.F0		 = glm_mix(v3(0.04f), baseColor, metallic);
+	g.oneMinusF0 = v3(1.0f) - g.F0;
+	g.diffuse	 = ((1.0f - metallic) * RB_ONE_OVER_PI) * baseColor * g.oneMinusF0;
+	return g;
+}
+// Returns (brdf, pdf of the specular lobe): eval ignores the pdf, sampleAndEval uses it.
+RB_D float4 rb_ggx(const RbGgxSurface & g, V3 wi) {
+	const V3 h		  = normalize3(wi + g.wo);
 	const float NdotH = std_max(h.z, 0.0f);
 	const float VdotH = std_max(dot3(wi, h), 0.0f);
-	const float NdotL = std_max(wo.z, 0.0f);
 	const float NdotV = std_max(wi.z, 0.0f);
-	const float Dh	  = rb_ggx_D(NdotH, alpha);
-	if(pdf) {
-		const float hPdf = Dh * NdotH;
-		*pdf			 = hPdf / (4.0f * std_max(0.0001f, VdotH));
-	}
-	const V3 F0		  = glm_mix(v3(0.04f), baseColor, metallic);
-	const float fres  = powf(1.0f - VdotH, 5.0f);
-	const V3 F		  = F0 + fres * (v3(1.0f) - F0);								   // MaterialGGX::F (:5-7)
-	const V3 specular = (Dh * rb_ggx_V(NdotL, NdotV, alpha)) * F;
-	const V3 diffuse  = ((1.0f - metallic) * RB_ONE_OVER_PI) * baseColor * (v3(1.0f) - F0);
-	const V3 multiAdj = v3(1.0f) + (2.0f * alpha * alpha * NdotV) * F0;
-	return (diffuse + specular * multiAdj) * NdotV;
+	const float Dh	  = rb_ggx_D(NdotH, g.alpha);
+	const float hPdf  = Dh * NdotH;
+	const float pdf	  = hPdf / (4.0f * std_max(0.0001f, VdotH));
+	// pow(1 - VdotH, 5) (MaterialGGX.cpp:6) as x^2 * x^2 * x: three roundings, within 1.5 ulp of the exact power — tighter than
+	// the bound of CUDA's powf, which stood here before at ~95 instructions per call, two calls per shaded hit.
+	const float fm	  = 1.0f - VdotH;
+	const float fm2	  = fm * fm;
+	const float fres  = (fm2 * fm2) * fm;
+	const V3 F		  = g.F0 + fres * g.oneMinusF0;									   // MaterialGGX::F (:5-7)
+	// MaterialGGX::V (:15-21)
+	const float visL  = NdotV * g.rootL;
+	const float visV  = g.NdotL * sqrtf((-NdotV * g.alpha2 + NdotV) * NdotV + g.alpha2);
+	const float Vis	  = 0.5f / std_max(0.0001f, visV + visL);
+	const V3 specular = (Dh * Vis) * F;
+	const V3 multiAdj = v3(1.0f) + (g.twoAlpha2 * NdotV) * g.F0;
+	const V3 brdf	  = (g.diffuse + specular * multiAdj) * NdotV;
+	return make_float4(brdf.x, brdf.y, brdf.z, pdf);
 }
 // MaterialGGX::eval (MaterialGGX.cpp:94-101)
-RB_D V3 rb_ggx_eval(V3 wo, V3 baseColor, float roughness, float metallic, V3 wi) {
+RB_D V3 rb_ggx_eval(const RbGgxSurface & g, V3 wi) {
 	if(wi.z < 0.0f) {
 		return v3(0.0f);
 	}
-	return rb_ggx(wo, baseColor, rb_alpha_from_roughness(roughness), metallic, wi, nullptr);
+	const float4 r = rb_ggx(g, wi);
+	return V3{r.x, r.y, r.z};
+}
+RB_D V3 rb_ggx_eval(V3 wo, V3 baseColor, float roughness, float metallic, V3 wi) {
+	return rb_ggx_eval(rb_ggx_surface(wo, baseColor, roughness, metallic), wi);
 }
 // Random::sampleDisk + sampleCosineHemisphere (Random.cpp:41-70) on two given uniforms.
 RB_D V3 rb_cosine_hemisphere(float u0, float u1) {
@@ -249,11 +284,11 @@ RB_D V3 rb_cosine_hemisphere(float u0, float u1) {
 }
 // MaterialGGX::sampleAndEval (MaterialGGX.cpp:54-92). u0 picks the lobe; (u1,u2) sample it. The reference draws its
 // uniforms in this order: lobe pick, then either (x, phi) for the specular lobe or the two disk coordinates.
-RB_D V3 rb_ggx_sample_and_eval(V3 wo, V3 baseColor, float roughness, float metallic, float u0, float u1, float u2, V3 & wi) {
+RB_D V3 rb_ggx_sample_and_eval(const RbGgxSurface & gs, V3 baseColor, float metallic, float u0, float u1, float u2, V3 & wi) {
+	const V3 wo = gs.wo;
 	const float probaSpecular = glm_mix(1.0f / (dot3(baseColor, v3(1.0f)) / 3.0f + 1.0f), 1.0f, metallic);
-	const float alpha		  = rb_alpha_from_roughness(roughness);
 	if(u0 < probaSpecular) {
-		const float a2			 = alpha * alpha;
+		const float a2			 = gs.alpha2;
 		const float x			 = u1;
 		const float phiH		 = u2 * RB_TWO_PI;
 		const float cosThetaHSqr = std_min((1.0f - x) / ((a2 - 1.0f) * x + 1.0f), 1.0f);
@@ -274,13 +309,17 @@ RB_D V3 rb_ggx_sample_and_eval(V3 wo, V3 baseColor, float roughness, float metal
 	if(wi.z < 0.0f) {
 		return v3(0.0f);
 	}
-	float pdfSpec = 0.0f;
-	const V3 brdf = rb_ggx(wo, baseColor, alpha, metallic, wi, &pdfSpec);
-	const float pdf = glm_mix(RB_ONE_OVER_PI * std_max(wi.z, 0.0f), pdfSpec, probaSpecular);
+	const float4 g = rb_ggx(gs, wi);
+	const V3 brdf  = V3{g.x, g.y, g.z};
+	const float pdf = glm_mix(RB_ONE_OVER_PI * std_max(wi.z, 0.0f), g.w, probaSpecular);
 	if(pdf == 0.0f) {
 		return v3(0.0f);
 	}
 	return brdf / pdf;
+}
+
+RB_D V3 rb_ggx_sample_and_eval(V3 wo, V3 baseColor, float roughness, float metallic, float u0, float u1, float u2, V3 & wi) {
+	return rb_ggx_sample_and_eval(rb_ggx_surface(wo, baseColor, roughness, metallic), baseColor, metallic, u0, u1, u2, wi);
 }
 
 // ---------------------------------------------------------------------------------------------- sky
