@@ -282,6 +282,9 @@ RB_D V3 rb_cosine_hemisphere(float u0, float u1) {
 	const float z = sqrtf(std_max(0.0f, 1.0f - dx * dx - dy * dy));
 	return V3{dx, dy, z};
 }
+// sincos(double) out of line: its argument-reduction slow path (never taken for an angle in [0, 2 pi)) is a few hundred
+// instructions in the middle of the specular branch otherwise.
+static __device__ __noinline__ double2 rb_sincos_call(double x) { double s, c; sincos(x, &s, &c); return make_double2(s, c); }
 // MaterialGGX::sampleAndEval (MaterialGGX.cpp:54-92). u0 picks the lobe; (u1,u2) sample it. The reference draws its
 // uniforms in this order: lobe pick, then either (x, phi) for the specular lobe or the two disk coordinates.
 RB_D V3 rb_ggx_sample_and_eval(const RbGgxSurface & gs, V3 baseColor, float metallic, float u0, float u1, float u2, V3 & wi) {
@@ -297,7 +300,8 @@ RB_D V3 rb_ggx_sample_and_eval(const RbGgxSurface & gs, V3 baseColor, float meta
 		// The reference calls the unqualified C cos/sin here (MaterialGGX.cpp:69): evaluated in double, multiplied by
 		// sinThetaH in double, narrowed to float by the vec3 constructor. One fp64 sincos per bounce is noise on B200.
 		double sphi, cphi;
-		sincos((double)phiH, &sphi, &cphi);
+		const double2 sc2 = rb_sincos_call((double)phiH);
+		sphi = sc2.x; cphi = sc2.y;
 		const V3 lh = V3{(float)((double)sinThetaH * cphi), (float)((double)sinThetaH * sphi), cosThetaH};
 		wi = (2.0f * dot3(wo, lh)) * lh - wo;
 	} else {
@@ -338,7 +342,11 @@ RB_D bool rb_sphere(V3 rayOrigin, V3 rayDir, float radius, float & r0, float & r
 	return true;
 }
 // MaterialSky::eval (MaterialSky.cpp:6-87) with Sky::AtmosphereParameters defaults (Sky.hpp:53-65).
-RB_D V3 rb_sky_eval(const RbSceneDev & sc, V3 rayOrigin, V3 rayDir, V3 sunDir) {
+// Out of line: 550 instructions that only scenes with an atmosphere background execute, and then only for rays that
+// leave the scene; kept out of the shade kernel's straight-line code (together with the fp64 sincos below: shade -1.5 %).
+static __device__ __noinline__ V3 rb_sky_eval_p(const float4 * __restrict__ texels, const RbTexInfo * __restrict__ textures, int skyLut, V3 rayOrigin, V3 rayDir, V3 sunDir);
+RB_D V3 rb_sky_eval(const RbSceneDev & sc, V3 rayOrigin, V3 rayDir, V3 sunDir) { return rb_sky_eval_p(sc.texels, sc.textures, sc.skyLut, rayOrigin, rayDir, sunDir); }
+static __device__ __noinline__ V3 rb_sky_eval_p(const float4 * __restrict__ texels, const RbTexInfo * __restrict__ textures, int skyLut, V3 rayOrigin, V3 rayDir, V3 sunDir) {
 	const V3 sunColor	   = V3{1.474f, 1.8504f, 1.91198f};
 	const V3 kRayleigh	   = V3{5.5e-6f, 13.0e-6f, 22.4e-6f};
 	const float groundRadius = 6371e3f, topRadius = 6471e3f, sunIntensity = 20.0f, kMie = 21e-6f;
@@ -374,7 +382,8 @@ RB_D V3 rb_sky_eval(const RbSceneDev & sc, V3 rayOrigin, V3 rayDir, V3 sunDir) {
 		float uvy = (511.0f / 512.0f) * relativeCosAngle + 0.5f / 512.0f;
 		uvx = glm_clamp(uvx, 0.5f / 512.0f, 511.0f / 512.0f);
 		uvy = glm_clamp(uvy, 0.5f / 512.0f, 511.0f / 512.0f);
-		const V3 secondaryAttenuation = rb_image_rgbl(sc, sc.skyLut, uvx, uvy);
+		const float4 lut = rb_image_rgbal_p(texels, textures, skyLut, uvx, uvy);
+		const V3 secondaryAttenuation = V3{lut.x, lut.y, lut.z};
 		const V3 attenuation		  = directAttenuation * secondaryAttenuation;
 		rayleighScatt += rayleighStep * attenuation;
 		mieScatt += mieStep * attenuation;
