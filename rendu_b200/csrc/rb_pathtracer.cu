@@ -229,6 +229,128 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_trace(RbDeviceBvh bvh, Rb
 	if(COUNT && stats) rb_pt_flush_work(work, lane, stats, 4);
 }
 
+// ------------------------------------------------------------------------------------------------ asynchronous work feed
+// The persistent wavefront kernels above fetch work when lanes run idle: one atomic on the queue cursor, then the queue
+// entry, then the ray — three dependent trips to the L2 / HBM during which the whole warp waits (the live lanes too), for
+// rays that take fewer than ten node steps. The *_feed kernels take the memory out of that path. Every warp owns a small
+// staging area in shared memory and keeps a pipeline of 32-ray chunks in flight with cp.async (LDGSTS): while chunk c is
+// handed out to idle lanes, the rays of chunk c + 1 and the queue entries of chunk c + 2 are on their way, and the atomic
+// that reserves chunk c + 3 has been issued (its result is read one chunk later, from lane 0). A refill is then two
+// ld.shared.v4 per lane. Per ray nothing changes — same box tests, same order — so the hits are the same bits.
+RB_D void rb_cp_async4(unsigned int dst, const void * src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory"); }
+RB_D void rb_cp_async16(unsigned int dst, const void * src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
+RB_D void rb_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+RB_D float4 rb_lds128(unsigned int a) {
+	float4 v;
+	asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+	return v;
+}
+#define RB_FEED_NONE 0xffffffffu
+#define RB_FEED_TRACE_BYTES (3 * 32 * 4 + 2 * 32 * 2 * 16)	// per warp: three chunks of queue entries, two chunks of (origin, direction)
+#define RB_FEED_SHADOW_BYTES (2 * 32 * 3 * 16)				// per warp: two chunks of (origin+maxDist, direction+slot, contribution)
+
+template<bool ORDERED, int ROOTS>
+__global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_trace_feed(RbDeviceBvh bvh, RbPathBuffers pb, const uint32_t * __restrict__ queue, uint32_t did, int threshold, int leafVotes, int nodeSteps, unsigned long long * __restrict__ stats) {
+	extern __shared__ int s_stack[];
+	const RbStack st		 = rb_make_stack(s_stack + threadIdx.x, blockDim.x);
+	const unsigned int lane	 = threadIdx.x & 31u;
+	const unsigned int below = (1u << lane) - 1u;
+	const unsigned int n	 = pb.counters[rb_cnt_queue(did)];
+	unsigned int * cursor	 = pb.counters + rb_cnt_cursor_t(did);
+	if(blockIdx.x == 0 && threadIdx.x == 0 && stats) atomicAdd(stats + 0, (unsigned long long)n);
+	// Staging area of this warp, behind the traversal stacks.
+	const unsigned int area	  = (unsigned int)__cvta_generic_to_shared(s_stack) + (unsigned int)(bvh.stackDepth > 0 ? bvh.stackDepth : 1) * blockDim.x * 4u + (threadIdx.x >> 5) * RB_FEED_TRACE_BYTES;
+	const unsigned int sSlots = area;				// [3][32] u32
+	const unsigned int sRays  = area + 3u * 32u * 4u; // [2][32][2] float4
+	auto issueSlots = [&](unsigned int buf, unsigned int base) {
+		if(base < n && base + lane < n) rb_cp_async4(sSlots + (buf * 32u + lane) * 4u, queue + base + lane);
+	};
+	auto issueRays = [&](unsigned int rbuf, unsigned int sbuf, unsigned int base) {
+		if(base < n && base + lane < n) {
+			const unsigned int sl = rb_lds(sSlots + (sbuf * 32u + lane) * 4u);
+			rb_cp_async16(sRays + ((rbuf * 32u + lane) * 2u + 0u) * 16u, pb.rayO + sl);
+			rb_cp_async16(sRays + ((rbuf * 32u + lane) * 2u + 1u) * 16u, pb.rayD + sl);
+		}
+	};
+	// Prologue: three chunks reserved at once, their queue entries, then the rays of the first two.
+	unsigned int nb = 0;
+	if(lane == 0) nb = atomicAdd(cursor, 96u);
+	unsigned int b0 = __shfl_sync(0xffffffffu, nb, 0), b1 = b0 + 32u, b2 = b0 + 64u;
+	issueSlots(0u, b0); issueSlots(1u, b1); issueSlots(2u, b2);
+	rb_cp_async_wait_all();
+	__syncwarp();
+	issueRays(0u, 0u, b0); issueRays(1u, 1u, b1);
+	if(lane == 0 && b2 < n) nb = atomicAdd(cursor, 32u); // chunk 3
+	rb_cp_async_wait_all();
+	__syncwarp();
+	unsigned int c = 0, c3 = 0; // chunk being handed out, and c mod 3
+	unsigned int head = 0, count = b0 < n ? min(32u, n - b0) : 0u;
+	bool drained = count == 0u;
+
+	bool active = false;
+	unsigned int slot = 0;
+	RbRay ray;
+	RbTraversal T;
+	for(;;) {
+		unsigned int idle = __ballot_sync(0xffffffffu, !active);
+		while(idle != 0u && !drained) {
+			if(count == 0u) {
+				// Chunk c is used up: move on. Everything issued one chunk ago has had a chunk's worth of traversal to land.
+				__syncwarp();
+				const unsigned int reserved = __shfl_sync(0xffffffffu, nb, 0);
+				c += 1u; c3 = c3 == 2u ? 0u : c3 + 1u;
+				b0 = b1; b1 = b2; b2 = (b2 < n) ? reserved : RB_FEED_NONE;
+				rb_cp_async_wait_all();
+				__syncwarp();
+				head  = 0u;
+				count = b0 < n ? min(32u, n - b0) : 0u;
+				if(count == 0u) { drained = true; break; }
+				issueRays((c + 1u) & 1u, c3 == 2u ? 0u : c3 + 1u, b1);
+				issueSlots(c3 == 0u ? 2u : c3 - 1u, b2); // (c + 2) mod 3
+				if(lane == 0 && b2 < n) nb = atomicAdd(cursor, 32u);
+			}
+			const unsigned int take = min((unsigned int)__popc(idle), count);
+			const unsigned int rank = __popc(idle & below);
+			if(!active && rank < take) {
+				const unsigned int e = head + rank;
+				slot			 = rb_lds(sSlots + (c3 * 32u + e) * 4u);
+				const float4 o	 = rb_lds128(sRays + (((c & 1u) * 32u + e) * 2u + 0u) * 16u);
+				const float4 d	 = rb_lds128(sRays + (((c & 1u) * 32u + e) * 2u + 1u) * 16u);
+				ray = rb_make_ray(V3{o.x, o.y, o.z}, V3{d.x, d.y, d.z});
+				rb_traversal_init(T, bvh, 0.0001f, 1e8f, st);
+				if(ROOTS == RB_ROOTS_MASK) T.root = int(rb_roots_pretest<false>(bvh, ray, 0.0001f, 1e8f, nullptr));
+				active = true;
+			}
+			head += take;
+			count -= take;
+			idle = __ballot_sync(0xffffffffu, !active);
+		}
+		unsigned int activeM = __ballot_sync(0xffffffffu, active);
+		if(activeM == 0u) break;
+		bool more;
+		do {
+			const bool wantsLeaf	 = active && rb_wants_leaf(T);
+			const unsigned int leafM = __ballot_sync(0xffffffffu, wantsLeaf);
+			const unsigned int nodeM = activeM & ~leafM;
+			bool finished = false;
+			if(__popc(leafM) >= leafVotes || nodeM == 0u) {
+				if(wantsLeaf) finished = rb_phase_leaf<false, false>(T, bvh, ray, nullptr);
+			} else if(active && !wantsLeaf) {
+				for(int k = 0; k < nodeSteps; ++k) {
+					finished = rb_phase_node<false, ORDERED, ROOTS>(T, bvh, ray, st, nullptr);
+					if(finished || rb_wants_leaf(T)) break;
+				}
+			}
+			if(finished) {
+				rb_st(pb.hit + slot, make_float4(T.best.t, T.best.u, T.best.v, __int_as_float(T.best.tri)));
+				active = false;
+			}
+			activeM = __ballot_sync(0xffffffffu, active);
+			more	= drained ? (activeM != 0u) : (__popc(activeM) >= threshold);
+		} while(more);
+	}
+}
+
 // The closest-hit wavefront on the eight-wide quantised tree (rb_render_opts.trace_mode = RB_TRACE_WIDE; experiment, see
 // rb_wide.h): the queue handling of rb_k_pt_trace around the phase-split wide steps. Path rays are regular except for
 // exact axis-parallel directions; those walk the binary tree on the spot, as in rb_k_trace_wide.
@@ -556,6 +678,150 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shadow(RbDeviceBvh bvh, R
 		for(int off = 16; off > 0; off >>= 1) queries += __shfl_down_sync(0xffffffffu, queries, off);
 		if(lane == 0 && queries) atomicAdd(stats + 1, (unsigned long long)queries);
 		if(COUNT) rb_pt_flush_work(work, lane, stats, 7);
+	}
+}
+
+// The shadow wavefront fed the same way. Its entries are dense (the shade kernel appends them), so the pipeline is one
+// stage shorter: chunk c handed out, the entries of chunk c + 1 in flight, the atomic for chunk c + 2 issued.
+template<bool MASKED, bool ORDERED, int ROOTS>
+__global__ void __launch_bounds__(RB_PT_BLOCK, 8) rb_k_pt_shadow_feed(RbDeviceBvh bvh, RbPathBuffers pb, RbSceneDev sc, uint32_t did, int threshold, int leafVotes, int nodeSteps, unsigned long long * __restrict__ stats) {
+	extern __shared__ int s_stack[];
+	const RbStack st		 = rb_make_stack(s_stack + threadIdx.x, blockDim.x);
+	const unsigned int lane	 = threadIdx.x & 31u;
+	const unsigned int below = (1u << lane) - 1u;
+	const unsigned int n	 = pb.counters[rb_cnt_shadow(did)];
+	unsigned int * cursor	 = pb.counters + rb_cnt_cursor_s(did);
+	const unsigned int sEnt	 = (unsigned int)__cvta_generic_to_shared(s_stack) + (unsigned int)(bvh.stackDepth > 0 ? bvh.stackDepth : 1) * blockDim.x * 4u + (threadIdx.x >> 5) * RB_FEED_SHADOW_BYTES; // [2][32][3] float4
+	auto issue = [&](unsigned int buf, unsigned int base) {
+		if(base < n && base + lane < n) {
+			const unsigned int d = sEnt + ((buf * 32u + lane) * 3u) * 16u;
+			rb_cp_async16(d, pb.shO + base + lane);
+			rb_cp_async16(d + 16u, pb.shD + base + lane);
+			rb_cp_async16(d + 32u, pb.shC + base + lane);
+		}
+	};
+	unsigned int nb = 0;
+	if(lane == 0) nb = atomicAdd(cursor, 64u);
+	unsigned int b0 = __shfl_sync(0xffffffffu, nb, 0), b1 = b0 + 32u;
+	issue(0u, b0); issue(1u, b1);
+	if(lane == 0 && b1 < n) nb = atomicAdd(cursor, 32u); // chunk 2
+	rb_cp_async_wait_all();
+	__syncwarp();
+	unsigned int c = 0, head = 0, count = b0 < n ? min(32u, n - b0) : 0u;
+	bool drained = count == 0u;
+
+	bool active = false;
+	unsigned int slot = 0;
+	unsigned int queries = 0;
+	V3 lpos = v3(0.0f), dir = v3(0.0f), contrib = v3(0.0f);
+	float maxDist = 0.0f;
+	RbRay ray;
+	RbTraversal T;
+	for(;;) {
+		unsigned int idle = __ballot_sync(0xffffffffu, !active);
+		while(idle != 0u && !drained) {
+			if(count == 0u) {
+				__syncwarp();
+				const unsigned int reserved = __shfl_sync(0xffffffffu, nb, 0);
+				c += 1u;
+				b0 = b1; b1 = (b1 < n) ? reserved : RB_FEED_NONE;
+				rb_cp_async_wait_all();
+				__syncwarp();
+				head  = 0u;
+				count = b0 < n ? min(32u, n - b0) : 0u;
+				if(count == 0u) { drained = true; break; }
+				issue((c + 1u) & 1u, b1);
+				if(lane == 0 && b1 < n) nb = atomicAdd(cursor, 32u);
+			}
+			const unsigned int take = min((unsigned int)__popc(idle), count);
+			const unsigned int rank = __popc(idle & below);
+			if(!active && rank < take) {
+				const unsigned int a = sEnt + (((c & 1u) * 32u + head + rank) * 3u) * 16u;
+				const float4 o = rb_lds128(a), d = rb_lds128(a + 16u), cc = rb_lds128(a + 32u);
+				lpos	= V3{o.x, o.y, o.z};
+				maxDist = o.w;
+				dir		= V3{d.x, d.y, d.z};
+				slot	= __float_as_uint(d.w);
+				contrib = V3{cc.x, cc.y, cc.z};
+				if(maxDist > 0.0f) {
+					ray = rb_make_ray(lpos, dir);
+					rb_traversal_init(T, bvh, 0.001f, maxDist, st);
+					if(ROOTS == RB_ROOTS_MASK) T.root = int(rb_roots_pretest<false>(bvh, ray, 0.001f, maxDist, nullptr));
+					active = true;
+					++queries;
+				} else {
+					// `while(maxDist > 0.0f)` never entered: visible (:127, :156).
+					float4 cl = rb_ld(pb.color + slot);
+					cl.x += contrib.x; cl.y += contrib.y; cl.z += contrib.z;
+					rb_st(pb.color + slot, cl);
+				}
+			}
+			head += take;
+			count -= take;
+			idle = __ballot_sync(0xffffffffu, !active);
+		}
+		unsigned int activeM = __ballot_sync(0xffffffffu, active);
+		if(activeM == 0u) {
+			if(drained) break;
+			continue; // every entry taken was visible without a query: fetch more
+		}
+		bool more;
+		do {
+			const bool wantsLeaf	 = active && rb_wants_leaf(T);
+			const unsigned int leafM = __ballot_sync(0xffffffffu, wantsLeaf);
+			const unsigned int nodeM = activeM & ~leafM;
+			bool done = false;
+			if(__popc(leafM) >= leafVotes || nodeM == 0u) {
+				if(wantsLeaf) done = rb_phase_leaf<!MASKED, false>(T, bvh, ray, nullptr);
+			} else if(active && !wantsLeaf) {
+				for(int k = 0; k < nodeSteps; ++k) {
+					done = rb_phase_node<false, ORDERED, ROOTS>(T, bvh, ray, st, nullptr);
+					if(done || rb_wants_leaf(T)) break;
+				}
+			}
+			if(done) {
+				bool visible = false, finished = true;
+				if(T.best.tri < 0) {
+					visible = true;
+				} else if(MASKED) {
+					uint32_t meshId	   = __float_as_uint(rb_ldg4(bvh.tris + 3 * size_t(T.best.tri) + 1).w); // just read by the traversal
+					const RbObject obj = sc.objects[meshId];
+					if((obj.flags & RB_OBJ_MASKED) && (obj.flags & RB_OBJ_USE_UV)) {
+						float lu, lv;
+						rb_fetch_uv(sc, T.best.tri, T.best.u, T.best.v, lu, lv, meshId);
+						const float alpha = rb_image_rgbal(sc, obj.texAlbedo, lu, lv).w;
+						if(alpha < 0.01f) {
+							// Transparent texel: shift to the hit, shorten the segment, cast again (:149-151).
+							maxDist = maxDist - T.best.t;
+							lpos	= lpos + T.best.t * dir;
+							if(maxDist > 0.0f) {
+								ray = rb_make_ray(lpos, dir);
+								rb_traversal_init(T, bvh, 0.001f, maxDist, st);
+								if(ROOTS == RB_ROOTS_MASK) T.root = int(rb_roots_pretest<false>(bvh, ray, 0.001f, maxDist, nullptr));
+								finished = false;
+								++queries;
+							} else {
+								visible = true;
+							}
+						}
+					}
+				}
+				if(finished) {
+					if(visible) {
+						float4 cl = rb_ld(pb.color + slot);
+						cl.x += contrib.x; cl.y += contrib.y; cl.z += contrib.z;
+						rb_st(pb.color + slot, cl);
+					}
+					active = false;
+				}
+			}
+			activeM = __ballot_sync(0xffffffffu, active);
+			more	= drained ? (activeM != 0u) : (__popc(activeM) >= threshold);
+		} while(more);
+	}
+	if(stats) {
+		for(int off = 16; off > 0; off >>= 1) queries += __shfl_down_sync(0xffffffffu, queries, off);
+		if(lane == 0 && queries) atomicAdd(stats + 1, (unsigned long long)queries);
 	}
 }
 
@@ -975,7 +1241,16 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 		auto kTrace = blocks ? (ordered ? rb_k_pt_trace<true, RB_ROOTS_BLOCKS> : rb_k_pt_trace<false, RB_ROOTS_BLOCKS>)
 							 : (ordered ? rb_k_pt_trace<true, RB_ROOTS_LAZY> : (maskRoots ? rb_k_pt_trace<false, RB_ROOTS_MASK> : rb_k_pt_trace<false, RB_ROOTS_LAZY>));
 		if(profCounting) kTrace = ordered ? rb_k_pt_trace<true, RB_ROOTS_LAZY, true> : (maskRoots ? rb_k_pt_trace<false, RB_ROOTS_MASK, true> : rb_k_pt_trace<false, RB_ROOTS_LAZY, true>); // (block skipping: plain root loop, same hits, counted)
-		st = rb_pt_grid(kTrace, smem, pt->sms, gridTrace);
+		// The cp.async-fed forms of the two wavefront kernels (see "asynchronous work feed"); the counting copies of the
+		// profile pass keep the plain form.
+		const bool feed = !profCounting && std::getenv("RB_PT_FEED") != nullptr;
+		size_t smemTrace = smem, smemShadow = smem;
+		if(feed) {
+			kTrace = blocks ? (ordered ? rb_k_pt_trace_feed<true, RB_ROOTS_BLOCKS> : rb_k_pt_trace_feed<false, RB_ROOTS_BLOCKS>)
+							: (ordered ? rb_k_pt_trace_feed<true, RB_ROOTS_LAZY> : (maskRoots ? rb_k_pt_trace_feed<false, RB_ROOTS_MASK> : rb_k_pt_trace_feed<false, RB_ROOTS_LAZY>));
+			smemTrace = smem + (RB_PT_BLOCK / 32) * RB_FEED_TRACE_BYTES;
+		}
+		st = rb_pt_grid(kTrace, smemTrace, pt->sms, gridTrace);
 		if(st) return st;
 		const bool masked = sc->dev.anyMasked != 0;
 		// Unmasked scenes use any-hit shadow rays, whose result is order independent: always near-child-first.
@@ -984,7 +1259,12 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 		auto kShadow = blocks ? (masked ? (ordered ? rb_k_pt_shadow<true, true, RB_ROOTS_BLOCKS> : rb_k_pt_shadow<true, false, RB_ROOTS_BLOCKS>) : rb_k_pt_shadow<false, true, RB_ROOTS_BLOCKS>)
 							  : (masked ? (ordered ? rb_k_pt_shadow<true, true, RB_ROOTS_LAZY> : rb_k_pt_shadow<true, false, RB_ROOTS_LAZY>) : rb_k_pt_shadow<false, true, RB_ROOTS_LAZY>);
 		if(profCounting) kShadow = masked ? (ordered ? rb_k_pt_shadow<true, true, RB_ROOTS_LAZY, true> : rb_k_pt_shadow<true, false, RB_ROOTS_LAZY, true>) : rb_k_pt_shadow<false, true, RB_ROOTS_LAZY, true>;
-		st = rb_pt_grid(kShadow, smem, pt->sms, gridShadow);
+		if(feed) {
+			kShadow = blocks ? (masked ? (ordered ? rb_k_pt_shadow_feed<true, true, RB_ROOTS_BLOCKS> : rb_k_pt_shadow_feed<true, false, RB_ROOTS_BLOCKS>) : rb_k_pt_shadow_feed<false, true, RB_ROOTS_BLOCKS>)
+							 : (masked ? (ordered ? rb_k_pt_shadow_feed<true, true, RB_ROOTS_LAZY> : rb_k_pt_shadow_feed<true, false, RB_ROOTS_LAZY>) : rb_k_pt_shadow_feed<false, true, RB_ROOTS_LAZY>);
+			smemShadow = smem + (RB_PT_BLOCK / 32) * RB_FEED_SHADOW_BYTES;
+		}
+		st = rb_pt_grid(kShadow, smemShadow, pt->sms, gridShadow);
 		if(st) return st;
 		const bool wideShadow  = wideTrace && !masked; // masked scenes need the closest occluder: binary kernel
 		unsigned gridShadowWide = 0;
@@ -1024,7 +1304,7 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 				for(uint32_t did = 0; did < depth; ++did) {
 					RB_CUDA(mark(1, ls));
 					if(wideTrace) rb_k_pt_trace_wide<<<gridTraceWide, RB_PT_BLOCK, smemWide, ls>>>(rc->dev, rc->devWide, pb, pb.queue[did & 1u], did, threshold, votes > 32 ? 6 : votes, pt->d_stats);
-					else kTrace<<<gridTrace, RB_PT_BLOCK, smem, ls>>>(rc->dev, pb, pb.queue[did & 1u], did, threshold, votes, steps, pt->d_stats);
+					else kTrace<<<gridTrace, RB_PT_BLOCK, smemTrace, ls>>>(rc->dev, pb, pb.queue[did & 1u], did, threshold, votes, steps, pt->d_stats);
 					if(shadowPending) RB_CUDA(cudaStreamWaitEvent(ls, pt->shadowed[l], 0)); // shade overwrites the shadow entries
 					RB_CUDA(mark(2, ls));
 					rb_k_pt_shade<<<gridShade, RB_PT_BLOCK, 0, ls>>>(f, b, pb, sc->dev, did, pt->d_stats);
@@ -1036,7 +1316,7 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 						}
 						RB_CUDA(mark(3, ss));
 						if(wideShadow) rb_k_pt_shadow_wide<<<gridShadowWide, RB_PT_BLOCK, smemWide, ss>>>(rc->dev, rc->devWide, pb, did, threshold, votes > 32 ? 6 : votes, pt->d_stats);
-						else kShadow<<<gridShadow, RB_PT_BLOCK, smem, ss>>>(rc->dev, pb, sc->dev, did, threshold, votes, steps, pt->d_stats);
+						else kShadow<<<gridShadow, RB_PT_BLOCK, smemShadow, ss>>>(rc->dev, pb, sc->dev, did, threshold, votes, steps, pt->d_stats);
 						if(ss != ls) {
 							RB_CUDA(cudaEventRecord(pt->shadowed[l], ss));
 							shadowPending = true;

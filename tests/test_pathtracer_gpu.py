@@ -258,6 +258,27 @@ def test_batches_and_lanes_do_not_change_the_image(monkeypatch):
     np.testing.assert_allclose(chunked, whole, rtol=2e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("name", ["cornellbox", "cornellbox-cutout"])
+def test_cp_async_fed_wavefronts_return_the_same_image(monkeypatch, name):
+    """RB_PT_FEED=1 selects the wavefront kernels that stage their rays through shared memory with cp.async (an
+    experiment that did not pay, kept opt-in): per ray nothing changes, so the image must not change by one bit —
+    with the any-hit shadow walk (cornellbox) and the masked one (cutout), small and ragged queue sizes included."""
+    if name == "cornellbox-cutout" and not ref.available():
+        pytest.skip("bundled scenes need oracle/_ref/resources")
+    if name == "cornellbox":
+        desc, cam, _ = golden_scene(name)
+    else:
+        rs = ref.RefScene(name)
+        desc, cam = rs.flatten(), rs.camera(1.0)
+    for w, h, spp, depth in ((200, 150, 8, 5), (7, 5, 2, 3), (1, 1, 1, 2)):
+        monkeypatch.delenv("RB_PT_FEED", raising=False)
+        plain, _ = gpu_render(desc, cam, w, h, spp, depth, seed=3)
+        monkeypatch.setenv("RB_PT_FEED", "1")
+        fed, pt = gpu_render(desc, cam, w, h, spp, depth, seed=3)
+        assert pt.stats()["samples"] == w * h * spp
+        assert np.array_equal(fed.view(np.uint32), plain.view(np.uint32))
+
+
 def test_lights_and_background_follow_edits_between_renders():
     """The reference reads scene->lights and the background through the shared Scene inside render(), so an edit between
     two frames shows in the next one. Here: rb_scene_clear_lights / add_light / set_background + rb_scene_sync on a
