@@ -23,6 +23,7 @@
 rb_scene * rb_pt_scene(rb_pathtracer * pt);
 void ** rb_pt_multi_slot(rb_pathtracer * pt);
 void rb_pt_set_stats(rb_pathtracer * pt, const rb_render_stats & s);
+uint32_t rb_pt_round_samples(uint32_t samples);
 
 namespace {
 
@@ -332,7 +333,8 @@ rb_status rb_pt_multi_render(rb_pathtracer * pt, const rb_camera * camera, uint3
 			}
 		}
 	} else if(p2pReduce) {
-		rb_k_resolve_peers<<<1184, 256, 0, root.stream>>>(m->d_sumTable, int(gpus), uint32_t(npx), components, float(samples), m->d_pixels);
+		// (the sample count render() rounds to, PathTracer.cpp:169-170 — what the ordinary resolve divides by)
+		rb_k_resolve_peers<<<1184, 256, 0, root.stream>>>(m->d_sumTable, int(gpus), uint32_t(npx), components, float(rb_pt_round_samples(samples)), m->d_pixels);
 		RB_CUDA(cudaGetLastError());
 		resolved = true;
 	} else {

@@ -511,10 +511,25 @@ __global__ void __launch_bounds__(RB_PT_BLOCK, RB_PT_SHADE_MIN_BLOCKS) rb_k_pt_s
 							if(light.castsShadow) {
 								// The visibility walk runs in the shadow kernel; a contribution of exactly zero needs no ray.
 								if(contrib.x != 0.0f || contrib.y != 0.0f || contrib.z != 0.0f) {
+#ifdef RB_SHADOW_PUSH_EARLY
+									// Appended on the spot, aggregated over the lanes that are here together: held until the end of
+									// the iteration the entry would occupy twelve registers across the BSDF sampling below.
+									const unsigned int am	= __activemask();
+									const unsigned int ln	= threadIdx.x & 31u;
+									const int leader		= __ffs(am) - 1;
+									unsigned int base		= 0;
+									if((int)ln == leader) base = atomicAdd(pb.counters + rb_cnt_shadow(did), (unsigned int)__popc(am));
+									base					= __shfl_sync(am, base, leader);
+									const unsigned int e	= base + __popc(am & ((1u << ln) - 1u));
+									pb.shO[e] = make_float4(pShift.x, pShift.y, pShift.z, maxDist);
+									pb.shD[e] = make_float4(direction.x, direction.y, direction.z, __uint_as_float(slot));
+									pb.shC[e] = make_float4(contrib.x, contrib.y, contrib.z, 0.0f);
+#else
 									wantShadow = true;
 									shO = make_float4(pShift.x, pShift.y, pShift.z, maxDist);
 									shD = make_float4(direction.x, direction.y, direction.z, __uint_as_float(slot));
 									shC = make_float4(contrib.x, contrib.y, contrib.z, 0.0f);
+#endif
 								}
 							} else {
 								sampleColor += contrib;
@@ -1100,7 +1115,7 @@ extern "C" void rb_pathtracer_destroy(rb_pathtracer * pt) {
 	delete pt;
 }
 
-static uint32_t rb_round_samples(uint32_t samples) {
+uint32_t rb_pt_round_samples(uint32_t samples) { // (also used by rb_multi.cu: the peer-memory resolve divides by the same count)
 	// size_t(std::pow(2, std::round(std::log2(float(samples))))) (PathTracer.cpp:169-170)
 	if(samples == 0) return 1;
 	return uint32_t(std::pow(2.0, std::round(std::log2(float(samples)))));
@@ -1116,7 +1131,7 @@ static rb_status rb_pt_frame(const rb_camera * cam, uint32_t width, uint32_t hei
 	std::memcpy(f.dy, cam->dy, sizeof(f.dy));
 	f.width	  = width;
 	f.height  = height;
-	f.samples = rb_round_samples(samples);
+	f.samples = rb_pt_round_samples(samples);
 	// getSampleGrid (PathTracer.cpp:57-69)
 	const int k = int(std::floor(std::log2(double(f.samples))));
 	f.cellsX = f.cellsY = uint32_t(std::pow(2, k / 2));

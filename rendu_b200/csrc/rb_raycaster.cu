@@ -1304,6 +1304,12 @@ struct HostPipe {
 		if(ready && dev == device) return RB_OK;
 		release();
 		device = dev;
+		const rb_status st = create();
+		if(st) release(); // a ring that came up half way (out of memory at slot 2) is taken down again, nothing leaks
+		else ready = true;
+		return st;
+	}
+	rb_status create() {
 		for(int k = 0; k < kPipeSlots; ++k) {
 			RB_CUDA(cudaStreamCreateWithFlags(&stream[k], cudaStreamNonBlocking));
 			RB_CUDA(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
@@ -1311,17 +1317,16 @@ struct HostPipe {
 			RB_CUDA(cudaMalloc(&d_dir[k], kPipeChunk * 3 * sizeof(float)));
 			RB_CUDA(cudaMalloc(&d_out[k], kPipeChunk * sizeof(rb_hit)));
 		}
-		ready = true;
 		return RB_OK;
 	}
 	void release() {
-		if(!ready) return;
-		for(int k = 0; k < kPipeSlots; ++k) {
-			cudaStreamDestroy(stream[k]);
-			cudaEventDestroy(done[k]);
+		for(int k = 0; k < kPipeSlotsMax; ++k) {
+			if(stream[k]) cudaStreamDestroy(stream[k]);
+			if(done[k]) cudaEventDestroy(done[k]);
 			cudaFree(d_org[k]);
 			cudaFree(d_dir[k]);
 			cudaFree(d_out[k]);
+			stream[k] = nullptr; done[k] = nullptr; d_org[k] = d_dir[k] = nullptr; d_out[k] = nullptr;
 		}
 		ready = false;
 	}

@@ -49,6 +49,15 @@ def test_multi_gpu_render_through_the_abi(monkeypatch):
         monkeypatch.delenv("RB_SAMPLE_REDUCE")
         assert not pt.multi_stats()["used_nccl"]
         assert np.abs(p2p - one).max() <= 2e-6 * max(1.0, float(one.max()))
+    # A sample count that is not a power of two is rounded like the reference does (12 -> 16, PathTracer.cpp:169-170); every
+    # combine divides by the rounded count (the peer-memory resolve once divided by the caller's).
+    one12 = _render(pt, cam, 160, 90, 12, 5)
+    assert np.array_equal(one12, one)
+    monkeypatch.setenv("RB_SAMPLE_REDUCE", "p2p")
+    p2p12 = _render(pt, cam, 160, 90, 12, 5, gpus=2, split=rpt.SPLIT_SAMPLE)
+    monkeypatch.delenv("RB_SAMPLE_REDUCE")
+    assert np.abs(p2p12 - one).max() <= 2e-6 * max(1.0, float(one.max()))
+    assert np.array_equal(_render(pt, cam, 160, 90, 12, 5, gpus=2, split=rpt.SPLIT_TILE), one)
     st = pt.stats()
     assert st["samples"] == 160 * 90 * 16
     # a scene edit invalidates the replicas: the next multi-GPU frame sees the new light on every GPU
