@@ -442,15 +442,13 @@ __global__ void __launch_bounds__(RB_PT_BLOCK, RB_PT_SHADE_MIN_BLOCKS) rb_k_pt_s
 	const uint32_t * queue	 = (did & 1u) ? pb.queue[1] : pb.queue[0];
 	uint32_t * nextQueue	 = (did & 1u) ? pb.queue[0] : pb.queue[1];
 	uint32_t * nextCounter	 = pb.counters + rb_cnt_queue(did + 1u);
-	uint32_t * shadowCounter = pb.counters + rb_cnt_shadow(did);
 	const bool lastBounce	 = (did + 1u >= f.depth);
 	// Whole warps iterate together so that the warp-aggregated pushes see converged lanes.
 	const uint32_t nRounded = (n + 31u) & ~31u;
 	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nRounded; i += gridDim.x * blockDim.x) {
 		const bool valid = i < n;
-		bool continues = false, wantShadow = false;
+		bool continues = false;
 		uint32_t slot = 0;
-		float4 shO = make_float4(0, 0, 0, 0), shD = shO, shC = shO;
 		if(valid) {
 			slot = queue[i];
 			const float4 h	= pb.hit[slot];
@@ -511,7 +509,6 @@ __global__ void __launch_bounds__(RB_PT_BLOCK, RB_PT_SHADE_MIN_BLOCKS) rb_k_pt_s
 							if(light.castsShadow) {
 								// The visibility walk runs in the shadow kernel; a contribution of exactly zero needs no ray.
 								if(contrib.x != 0.0f || contrib.y != 0.0f || contrib.z != 0.0f) {
-#ifdef RB_SHADOW_PUSH_EARLY
 									// Appended on the spot, aggregated over the lanes that are here together: held until the end of
 									// the iteration the entry would occupy twelve registers across the BSDF sampling below.
 									const unsigned int am	= __activemask();
@@ -524,12 +521,6 @@ __global__ void __launch_bounds__(RB_PT_BLOCK, RB_PT_SHADE_MIN_BLOCKS) rb_k_pt_s
 									pb.shO[e] = make_float4(pShift.x, pShift.y, pShift.z, maxDist);
 									pb.shD[e] = make_float4(direction.x, direction.y, direction.z, __uint_as_float(slot));
 									pb.shC[e] = make_float4(contrib.x, contrib.y, contrib.z, 0.0f);
-#else
-									wantShadow = true;
-									shO = make_float4(pShift.x, pShift.y, pShift.z, maxDist);
-									shD = make_float4(direction.x, direction.y, direction.z, __uint_as_float(slot));
-									shC = make_float4(contrib.x, contrib.y, contrib.z, 0.0f);
-#endif
 								}
 							} else {
 								sampleColor += contrib;
@@ -555,23 +546,6 @@ __global__ void __launch_bounds__(RB_PT_BLOCK, RB_PT_SHADE_MIN_BLOCKS) rb_k_pt_s
 			}
 		}
 		rb_queue_push(nextQueue, nextCounter, continues, slot);
-		// Shadow entries: same aggregation, three float4 per entry.
-		{
-			const unsigned int mask = __ballot_sync(0xffffffffu, wantShadow);
-			if(mask) {
-				const unsigned int lane = threadIdx.x & 31u;
-				const int leader		= __ffs(mask) - 1;
-				unsigned int base		= 0;
-				if((int)lane == leader) base = atomicAdd(shadowCounter, (unsigned int)__popc(mask));
-				base = __shfl_sync(0xffffffffu, base, leader);
-				if(wantShadow) {
-					const unsigned int e = base + __popc(mask & ((1u << lane) - 1u));
-					pb.shO[e] = shO;
-					pb.shD[e] = shD;
-					pb.shC[e] = shC;
-				}
-			}
-		}
 	}
 	if(blockIdx.x == 0 && threadIdx.x == 0 && stats) atomicAdd(stats + 2, (unsigned long long)n);
 }
