@@ -853,6 +853,7 @@ def run_lbvh(args):
     out.update(rc.build_times())
     out["build_device_ms"] = min(dev_ms)  # the first build of the process (rc) also pays module load and first-touch allocation
     out["depth"] = rc.sizes()["depth"]
+    out["nodes"] = rc.sizes()["nodes"]
     co, cd = wl.coherent_rays(RES)
     n = co.shape[0]
     d_o, d_d = torch.from_numpy(co).to(dev), torch.from_numpy(cd).to(dev)

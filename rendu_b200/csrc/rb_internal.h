@@ -110,6 +110,7 @@ struct rb_raycaster {
 	uint32_t * d_triIds	  = nullptr; // (localId, meshId) per triangle in hierarchy order
 	size_t nVerts	   = 0;
 	size_t nLeaves	   = 0;
+	size_t lbvhLeaves  = 0;			 // LBVH trees: leaves of the finished tree (ranges of up to RB_LBVH_LEAF triangles)
 	int buildMode	   = RB_BUILD_REFERENCE;
 
 	// Eight-wide quantised copy of the host-built tree (rb_wide.h; RB_TRACE_WIDE): host arrays and device copy.

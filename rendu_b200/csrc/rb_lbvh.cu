@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <climits>
 #include <memory>
 #include <chrono>
 #include <cstdlib>
@@ -246,7 +247,12 @@ RB_D uint64_t rb_expand21(uint64_t v) { // spread 21 bits so that two zero bits 
 	return v;
 }
 
-__global__ void rb_k_lbvh_morton(const float * __restrict__ verts, const uint32_t * __restrict__ triVerts, uint32_t ntris, const unsigned int * __restrict__ bounds6, uint64_t * __restrict__ keys, uint32_t * __restrict__ vals) {
+// `cubic`: all three axes are quantised with the cell size of the LONGEST one, so the grid cells are cubes. With per-axis
+// cell sizes a flat scene (a terrain: C5's displaced grid is 2 x 0.1 x 2) spends every third level of the tree splitting its
+// thin axis — two children that cover the same footprint, both of which every ray below them has to enter. In the cubic
+// grid the high bits of the thin axis are equal for all triangles; Karras' construction splits on the highest DIFFERING bit
+// of a range, so those levels simply do not exist.
+__global__ void rb_k_lbvh_morton(const float * __restrict__ verts, const uint32_t * __restrict__ triVerts, uint32_t ntris, const unsigned int * __restrict__ bounds6, uint64_t * __restrict__ keys, uint32_t * __restrict__ vals, int cubic) {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= ntris) return;
 	V3 lo, hi;
@@ -254,7 +260,8 @@ __global__ void rb_k_lbvh_morton(const float * __restrict__ verts, const uint32_
 	const V3 c	= 0.5f * (lo + hi);
 	const V3 bl = V3{rb_float_unordered(bounds6[0]), rb_float_unordered(bounds6[1]), rb_float_unordered(bounds6[2])};
 	const V3 bh = V3{rb_float_unordered(bounds6[3]), rb_float_unordered(bounds6[4]), rb_float_unordered(bounds6[5])};
-	const float ex = fmaxf(bh.x - bl.x, 1e-30f), ey = fmaxf(bh.y - bl.y, 1e-30f), ez = fmaxf(bh.z - bl.z, 1e-30f);
+	float ex = fmaxf(bh.x - bl.x, 1e-30f), ey = fmaxf(bh.y - bl.y, 1e-30f), ez = fmaxf(bh.z - bl.z, 1e-30f);
+	if(cubic) ex = ey = ez = fmaxf(ex, fmaxf(ey, ez));
 	const double scale = 2097151.0; // 2^21 - 1
 	const uint64_t qx = uint64_t(fmin(fmax(double(c.x - bl.x) / double(ex) * scale, 0.0), scale));
 	const uint64_t qy = uint64_t(fmin(fmax(double(c.y - bl.y) / double(ey) * scale, 0.0), scale));
@@ -271,8 +278,22 @@ RB_D int rb_delta(const uint64_t * __restrict__ keys, int n, int i, int j) {
 	return __clzll((long long)(a ^ b));
 }
 
+#define RB_LBVH_DEAD INT_MIN
+// Leaves of the finished tree = entries of the leaf table that carry a code.
+__global__ void rb_k_lbvh_count_leaves(const int * __restrict__ leafCode, int n, unsigned int * __restrict__ out) {
+	unsigned int c = 0;
+	for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) c += leafCode[i] >= 0 ? 1u : 0u;
+	for(int off = 16; off > 0; off >>= 1) c += __shfl_down_sync(0xffffffffu, c, off);
+	if((threadIdx.x & 31u) == 0 && c) atomicAdd(out, c);
+}
+
 // One thread per internal node: children and parent links. Child references use the traversal encoding (rb_types.h).
-__global__ void rb_k_lbvh_hierarchy(const uint64_t * __restrict__ keys, int n, int * __restrict__ childRefs /* 2 per internal */, int * __restrict__ interiorParent, int * __restrict__ leafParent) {
+// `leafMax` (1..8) collapses the bottom of the tree: a child whose range holds at most that many triangles becomes ONE leaf
+// (the triangles of a range are contiguous in the sorted order, which is all a leaf code needs), so a ray pays one node
+// visit for them instead of a little binary tree of visits, and the part of the 64-byte node array that is ever touched
+// shrinks by the same factor — at 10 M triangles the tree is several times the L2. Internal nodes inside a collapsed range
+// are dead: they keep valid references (a download stays well formed) but link to nobody and are never fitted.
+__global__ void rb_k_lbvh_hierarchy(const uint64_t * __restrict__ keys, int n, int leafMax, int * __restrict__ childRefs /* 2 per internal */, int * __restrict__ interiorParent, int * __restrict__ leafParent, int * __restrict__ leafCode) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= n - 1) return;
 	const int d		  = (rb_delta(keys, n, i, i + 1) - rb_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
@@ -293,11 +314,31 @@ __global__ void rb_k_lbvh_hierarchy(const uint64_t * __restrict__ keys, int n, i
 	} while(t > 1);
 	const int split = i + s * d + min(d, 0);
 	const int lo = min(i, j), hi = max(i, j);
-	const bool leftLeaf = (lo == split), rightLeaf = (hi == split + 1);
-	childRefs[2 * i + 0] = leftLeaf ? ~(split << RB_LEAF_BITS) : split;
-	childRefs[2 * i + 1] = rightLeaf ? ~((split + 1) << RB_LEAF_BITS) : (split + 1);
-	if(leftLeaf) leafParent[split] = (i << 1) | 0; else interiorParent[split] = (i << 1) | 0;
-	if(rightLeaf) leafParent[split + 1] = (i << 1) | 1; else interiorParent[split + 1] = (i << 1) | 1;
+	const int countL = split - lo + 1, countR = hi - split;
+	const bool leftLeaf = countL <= leafMax, rightLeaf = countR <= leafMax;
+	childRefs[2 * i + 0] = leftLeaf ? ~((lo << RB_LEAF_BITS) | (countL - 1)) : split;
+	childRefs[2 * i + 1] = rightLeaf ? ~(((split + 1) << RB_LEAF_BITS) | (countR - 1)) : (split + 1);
+	if(i != 0 && hi - lo + 1 <= leafMax) {
+		// inside a collapsed range: some ancestor holds these triangles as one leaf. Nobody else writes this node's parent
+		// link (its parent is dead too, or holds it as a leaf), so the mark below is what tells a download to skip it.
+		interiorParent[i] = RB_LBVH_DEAD;
+		return;
+	}
+	// Leaf table (what the fit kernel walks): entry `first triangle` carries the leaf, the other triangles of it are blank.
+	if(leftLeaf) {
+		leafParent[lo] = (i << 1) | 0;
+		leafCode[lo]   = (lo << RB_LEAF_BITS) | (countL - 1);
+		for(int k = 1; k < countL; ++k) leafCode[lo + k] = -1;
+	} else {
+		interiorParent[split] = (i << 1) | 0;
+	}
+	if(rightLeaf) {
+		leafParent[split + 1] = (i << 1) | 1;
+		leafCode[split + 1]	  = ((split + 1) << RB_LEAF_BITS) | (countR - 1);
+		for(int k = 1; k < countR; ++k) leafCode[split + 1 + k] = -1;
+	} else {
+		interiorParent[split + 1] = (i << 1) | 1;
+	}
 	if(i == 0) interiorParent[0] = ~0; // root slot 0
 }
 
@@ -329,6 +370,7 @@ __global__ void rb_k_fit(const float * __restrict__ verts, const uint32_t * __re
 	const int leaf = blockIdx.x * blockDim.x + threadIdx.x;
 	if(leaf >= nleaves) return;
 	const int code	= leafCode[leaf];
+	if(code < 0) return; // blank entry of the leaf table (a triangle inside a collapsed LBVH leaf that is not its first)
 	const int first = code >> RB_LEAF_BITS;
 	const int count = (code & (RB_LEAF_MAX_TRIS - 1)) + 1;
 	V3 lo = v3(0.0f), hi = v3(0.0f);
@@ -566,16 +608,28 @@ rb_status rb_lbvh_build(rb_raycaster * rc) {
 	cudaEventCreate(&ev1);
 	cudaEventRecord(ev0, s);
 	rb_k_lbvh_bounds<<<std::min<unsigned>(rb_blocks(n, 256), 148u * 8u), 256, 0, s>>>(rc->d_verts, d_tvIn, n, d_bounds);
-	rb_k_lbvh_morton<<<rb_blocks(n, 256), 256, 0, s>>>(rc->d_verts, d_tvIn, n, d_bounds, d_keys, d_vals);
+	static const int cubic = [] { const char * e = getenv("RB_LBVH_QUANT"); return (e && std::string(e) == "axis") ? 0 : 1; }();
+	rb_k_lbvh_morton<<<rb_blocks(n, 256), 256, 0, s>>>(rc->d_verts, d_tvIn, n, d_bounds, d_keys, d_vals, cubic);
 	launches += 2;
 	rb_status st = rb_radix_sort(d_keys, d_vals, n, 63, s, &launches);
+	unsigned int liveLeaves = (unsigned int)n; // one triangle per leaf unless the hierarchy kernel collapses ranges
 	if(st == RB_OK) {
 		rb_k_lbvh_gather<<<rb_blocks(n, 256), 256, 0, s>>>(d_vals, d_tvIn, d_idIn, n, rc->d_triVerts, rc->d_triIds, rc->d_leafCode);
 		++launches;
 		if(n > 1) {
-			rb_k_lbvh_hierarchy<<<rb_blocks(n - 1, 128), 128, 0, s>>>(d_keys, int(n), d_childRefs, rc->d_parent, rc->d_leafParent);
+			// Triangles per leaf: RB_LBVH_LEAF=1..8 overrides the default of 2 (measured on C5, profiles/r02_lbvh_quality.json:
+			// closest-hit 1.64 / 1.79 / 1.76 / 1.79 / 1.68 / 1.59 Grays/s and 480 / 495 / 490 / 471 / 443 / 418 spp/s at 1 / 2 / 3 / 4 / 6 / 8).
+			static const int leafMax = [] { const char * e = getenv("RB_LBVH_LEAF"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= RB_LEAF_MAX_TRIS) ? v : 2; }();
+			rb_k_lbvh_hierarchy<<<rb_blocks(n - 1, 128), 128, 0, s>>>(d_keys, int(n), leafMax, d_childRefs, rc->d_parent, rc->d_leafParent, rc->d_leafCode);
 			rb_k_lbvh_write_refs<<<rb_blocks(n - 1, 256), 256, 0, s>>>(d_childRefs, int(n - 1), rc->d_nodes);
 			launches += 2;
+			if(leafMax > 1) {
+				// (the bounds words are free again once the codes exist)
+				RB_CUDA(cudaMemsetAsync(d_bounds, 0, sizeof(unsigned int), s));
+				rb_k_lbvh_count_leaves<<<std::min<unsigned>(rb_blocks(n, 256), 148u * 8u), 256, 0, s>>>(rc->d_leafCode, int(n), d_bounds);
+				RB_CUDA(cudaMemcpyAsync(&liveLeaves, d_bounds, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+				++launches;
+			}
 		}
 		// Leaf table (leaf j holds triangle j) was written by the gather kernel. A single triangle is a root that is
 		// itself a leaf.
@@ -599,6 +653,7 @@ rb_status rb_lbvh_build(rb_raycaster * rc) {
 	float buildMs = 0.0f;
 	cudaEventElapsedTime(&buildMs, ev0, ev1);
 	rc->buildDeviceMs = buildMs;
+	rc->lbvhLeaves	  = liveLeaves; // (read back before the event above completed)
 	cudaEventDestroy(ev0);
 	cudaEventDestroy(ev1);
 	lap("build kernels", t0);
@@ -682,9 +737,18 @@ rb_status rb_lbvh_download(const rb_raycaster * rc, rb_node * nodesOut, rb_tri *
 		});
 	}
 	if(nodesOut) {
-		// Numbering: roots in slots [0, nr); the two children of device interior node i in slots nr + 2i and nr + 2i + 1.
+		// Numbering: roots in slots [0, nr); the two children of the k-th LIVE device interior node in slots nr + 2k and
+		// nr + 2k + 1 (nodes inside a collapsed leaf range are dead and get no record: the output is a proper binary tree).
 		// Every record then depends on one device node only, so the conversion runs on all host threads (the reference's
 		// consumers follow left/right indices and never assume an order).
+		std::unique_ptr<int[]> parent(new int[ni + 1]);
+		std::unique_ptr<uint32_t[]> rank(new uint32_t[ni + 1]);
+		if(ni) RB_CUDA(cudaMemcpy(parent.get(), rc->d_parent, ni * sizeof(int), cudaMemcpyDeviceToHost));
+		uint32_t live = 0;
+		for(size_t i = 0; i < ni; ++i) {
+			rank[i] = live;
+			if(parent[i] != RB_LBVH_DEAD) ++live;
+		}
 		auto fill = [&](rb_node & nd, int ref, const float * lo, const float * hi) {
 			std::memset(&nd, 0, sizeof(nd));
 			std::memcpy(nd.bmin, lo, 12);
@@ -698,8 +762,8 @@ rb_status rb_lbvh_download(const rb_raycaster * rc, rb_node * nodesOut, rb_tri *
 				}
 			} else {
 				nd.leaf	 = 0;
-				nd.left	 = nr + 2 * size_t(ref);
-				nd.right = nr + 2 * size_t(ref) + 1;
+				nd.left	 = nr + 2 * size_t(rank[ref]);
+				nd.right = nr + 2 * size_t(rank[ref]) + 1;
 			}
 		};
 		for(size_t r = 0; r < nr; ++r) {
@@ -709,12 +773,13 @@ rb_status rb_lbvh_download(const rb_raycaster * rc, rb_node * nodesOut, rb_tri *
 		}
 		rb_parallel_for(ni, size_t(1) << 15, [&](size_t begin, size_t end) {
 			for(size_t i = begin; i < end; ++i) {
+				if(parent[i] == RB_LBVH_DEAD) continue;
 				const float * f = &nodes[i * 16];
 				int refL, refR;
 				std::memcpy(&refL, &f[12], 4);
 				std::memcpy(&refR, &f[13], 4);
-				fill(nodesOut[nr + 2 * i], refL, f, f + 3);
-				fill(nodesOut[nr + 2 * i + 1], refR, f + 6, f + 9);
+				fill(nodesOut[nr + 2 * size_t(rank[i])], refL, f, f + 3);
+				fill(nodesOut[nr + 2 * size_t(rank[i]) + 1], refR, f + 6, f + 9);
 			}
 		});
 	}

@@ -993,8 +993,8 @@ extern "C" rb_status rb_raycaster_upload_bvh(rb_raycaster * rc, const rb_node * 
 extern "C" rb_status rb_raycaster_sizes(const rb_raycaster * rc, uint64_t out[5]) {
 	if(!rc || !out) return rb_fail(RB_ERR_INVALID, "rb_raycaster_sizes: null argument");
 	if(rc->buildMode == RB_BUILD_LBVH && rc->built) {
-		const uint64_t nt = rc->nTris;
-		out[0] = nt ? 2 * nt - 1 : 0;
+		const uint64_t nl = rc->lbvhLeaves; // a proper binary tree: one record per leaf and per live interior node
+		out[0] = nl ? 2 * nl - 1 : 0;
 		out[3] = 1; // one tree over all meshes
 	} else {
 		out[0] = rc->nodes.size();
