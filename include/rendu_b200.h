@@ -450,6 +450,9 @@ RB_API rb_status rb_kat_image_sample(const float * rgba, uint32_t width, uint32_
 RB_API rb_status rb_kat_cubemap_sample(const float * faces, uint32_t width, uint32_t height, const float * dirs, size_t n, float * out3);
 RB_API rb_status rb_kat_light_sample(const rb_light_desc * light, const float * positions, size_t n, float * out5);
 RB_API rb_status rb_kat_sky_eval(const float * lut_rgba, uint32_t width, uint32_t height, const float * origins, const float * dirs, const float sun[3], size_t n, float * out3);
+/* The exact multiply-high division of the path-tracer kernels (slot -> pixel, sample; replaces the u32 divisions the
+ * reference's nested loops never needed): out2[2i] = that division, out2[2i+1] = the device's own n / d. */
+RB_API rb_status rb_kat_div(const uint32_t * numerators, const uint32_t * denominators, size_t n, uint32_t * out2);
 RB_API rb_status rb_kat_box_test(const float * origins, const float * dirs, const float * boxes6, float mini, float maxi, size_t n, uint8_t * out);
 /* Raycaster::intersects(const Ray &, const TriangleInfos &, mini, maxi) (Raycaster.cpp:232-262; private, reached by the friend
  * RaycasterVisualisation): n (ray, triangle) pairs. positions / dirs are a Ray's `pos` and already-normalised `dir`, used as

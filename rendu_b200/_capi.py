@@ -154,6 +154,7 @@ def lib():
         "rb_kat_sky_eval": (C.c_int, [vp, u32, u32, vp, vp, vp, sz, vp]),
         "rb_kat_box_test": (C.c_int, [vp, vp, vp, f32, f32, sz, vp]),
         "rb_kat_triangle_test": (C.c_int, [vp, vp, vp, f32, f32, sz, vp]),
+        "rb_kat_div": (C.c_int, [vp, vp, sz, vp]),
     }
     missing = []
     for name, (res, args) in protos.items():

@@ -170,3 +170,27 @@ extern "C" rb_status rb_kat_sky_eval(const float * lut_rgba, uint32_t width, uin
 	KAT_END(out3, d_out, 3 * n)
 	return RB_OK;
 }
+
+// rb_div (rb_math.cuh): the exact multiply-high division the path-tracer kernels map slots to pixels and samples with,
+// against the device's own u32 division, element by element.
+__global__ void rb_k_kat_div(const uint32_t * num, const uint32_t * den, size_t n, uint32_t * out2) {
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	out2[2 * i]		= rb_div(num[i], rb_div_magic(den[i]));
+	out2[2 * i + 1] = num[i] / den[i];
+}
+
+extern "C" rb_status rb_kat_div(const uint32_t * numerators, const uint32_t * denominators, size_t n, uint32_t * out2) {
+	KAT_BEGIN(div)
+	if(!numerators || !denominators || !out2) return rb_fail(RB_ERR_INVALID, "rb_kat_div: null argument");
+	for(size_t i = 0; i < n; ++i) {
+		if(denominators[i] == 0) return rb_fail(RB_ERR_INVALID, "rb_kat_div: denominator %zu is zero", i);
+	}
+	uint32_t *d_n, *d_d, *d_o;
+	RB_CUDA(mem.up(&d_n, numerators, n)); RB_CUDA(mem.up(&d_d, denominators, n)); RB_CUDA(mem.up(&d_o, (const uint32_t *)nullptr, 2 * n));
+	rb_k_kat_div<<<blocks(n), 128>>>(d_n, d_d, n, d_o);
+	RB_CUDA(cudaGetLastError());
+	RB_CUDA(cudaDeviceSynchronize());
+	RB_CUDA(cudaMemcpy(out2, d_o, 2 * n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	return RB_OK;
+}

@@ -68,3 +68,16 @@ RB_HD V3 mulT(const M3 & m, V3 v) {
 			  m.c[1].x * v.x + m.c[1].y * v.y + m.c[1].z * v.z,
 			  m.c[2].x * v.x + m.c[2].y * v.y + m.c[2].z * v.z};
 }
+
+#include <stdint.h>
+// Exact division of a 32-bit number by a run-time constant d: floor(n / d) = floor(m * n / 2^64) with m = ceil(2^64 / d)
+// (Lemire, Kaser, Kurz 2019: exact for every 32-bit n and d because 64 >= 32 + 32). m does not fit for d = 1: stored as 0.
+// A hardware-free u32 division is ~20 instructions; every kernel that maps a path slot to (pixel, sample) did four.
+RB_HD uint64_t rb_div_magic(uint32_t d) { return d > 1u ? 0xFFFFFFFFFFFFFFFFull / d + 1ull : 0ull; }
+RB_HD uint32_t rb_div(uint32_t n, uint64_t m) {
+#ifdef __CUDA_ARCH__
+	return m ? uint32_t(__umul64hi(m, uint64_t(n))) : n;
+#else
+	return m ? uint32_t((unsigned __int128)m * n >> 64) : n;
+#endif
+}

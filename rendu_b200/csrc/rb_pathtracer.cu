@@ -23,18 +23,6 @@
 								 // more; same-box A/B of the frame: 5 blocks (96 regs) -0.4 %, 6 (80) 0, 7 (72) +1.2 %, 8 (64, 58 B spilled) -1.6 %
 #endif
 
-// Exact division of a 32-bit number by a run-time constant d: floor(n / d) = floor(m * n / 2^64) with m = ceil(2^64 / d)
-// (Lemire, Kaser, Kurz 2019: exact for every 32-bit n and d because 64 >= 32 + 32). m does not fit for d = 1: stored as 0.
-// A hardware-free u32 division is ~20 instructions; every kernel that maps a path slot to (pixel, sample) did four.
-RB_HD uint64_t rb_div_magic(uint32_t d) { return d > 1u ? 0xFFFFFFFFFFFFFFFFull / d + 1ull : 0ull; }
-RB_HD uint32_t rb_div(uint32_t n, uint64_t m) {
-#ifdef __CUDA_ARCH__
-	return m ? uint32_t(__umul64hi(m, uint64_t(n))) : n;
-#else
-	return m ? uint32_t((unsigned __int128)m * n >> 64) : n;
-#endif
-}
-
 struct RbFrame {
 	float eye[3], corner[3], dx[3], dy[3];
 	uint32_t width, height;

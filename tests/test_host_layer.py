@@ -168,3 +168,17 @@ def test_workload_shapes():
     assert pos.shape == (502681, 3) and idx.size == 3 * 1002528
     o, d = wl.coherent_rays(64, rows=(3, 5))
     assert o.shape == (128, 3) and d.dtype == np.float32
+
+
+def test_multiply_high_division_identity():
+    """The identity behind rb_div (rb_math.cuh): floor(n / d) = floor(n * ceil(2^64 / d) / 2^64) for all 32-bit n and d > 1
+    (the device test runs the kernel's own code; this states the arithmetic with Python integers, edge values included)."""
+    import random
+    rnd = random.Random(7)
+    edge = [1, 2, 3, 255, 256, 257, 1920, 65535, 65536, 2**31 - 1, 2**31, 2**31 + 1, 2**32 - 2, 2**32 - 1]
+    pairs = [(n, d) for n in edge + [0] for d in edge] + [(rnd.randrange(2**32), rnd.randrange(1, 2**32)) for _ in range(200000)]
+    pairs += [(rnd.randrange(2**32), rnd.randrange(1, 5000)) for _ in range(100000)]
+    for n, d in pairs:
+        m = (2**64 - 1) // d + 1 if d > 1 else 0  # rb_div_magic
+        q = (m * n) >> 64 if m else n  # rb_div
+        assert q == n // d, (n, d)

@@ -107,6 +107,21 @@ def test_kat_sky_eval():
 
 
 # ------------------------------------------------------------------------------------------------ renders
+def test_kat_exact_division():
+    """rb_div (slot -> pixel / sample in every path-tracer kernel) equals the u32 division for every operand: edge values
+    (1, powers of two and their neighbours, 2^32 - 1, equal operands) against each other, and a million random pairs."""
+    edge = np.array([1, 2, 3, 5, 7, 10, 255, 256, 257, 1080, 1920, 4095, 4096, 4097, 65535, 65536, 65537, 2**24 - 1, 2**24, 2**25, 2**31 - 1, 2**31,
+                     2**31 + 1, 2**32 - 2, 2**32 - 1, 33554432, 2073600, 530841600 % 2**32], np.uint64)
+    nn, dd = np.meshgrid(np.concatenate([edge, [0]]), edge)
+    rng = np.random.RandomState(4)
+    num = np.concatenate([nn.ravel(), rng.randint(0, 2**32, 1 << 20, dtype=np.uint64), rng.randint(0, 2**32, 1 << 18, dtype=np.uint64)]).astype(np.uint32)
+    den = np.concatenate([dd.ravel(), rng.randint(1, 2**32, 1 << 20, dtype=np.uint64), rng.randint(1, 5000, 1 << 18, dtype=np.uint64)]).astype(np.uint32)
+    out = np.zeros((num.size, 2), np.uint32)
+    check(lib().rb_kat_div(ptr(num), ptr(den), num.size, ptr(out)))
+    assert np.array_equal(out[:, 0], (num.astype(np.uint64) // den.astype(np.uint64)).astype(np.uint32))
+    assert np.array_equal(out[:, 1], out[:, 0])
+
+
 @pytest.mark.parametrize("name", ["cornellbox", "cornellbox-emissive"])
 def test_render_matches_oracle_path_for_path(name):
     desc, cam, _ = golden_scene(name)
