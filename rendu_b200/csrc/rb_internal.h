@@ -97,6 +97,8 @@ struct rb_raycaster {
 	float4 * d_rootBlocks = nullptr; // union boxes of aligned root blocks (many-mesh scenes), see rb_next_root
 	bool rootBlocksWanted = false;	  // decided at upload (rb_root_blocks_worthwhile), kept across refits
 	size_t rootBlocksCapacity = 0;	  // entries d_rootBlocks was allocated for
+	float4 * d_rootTree	  = nullptr; // tree over the root boxes (9..64 meshes): nroots - 1 nodes of 4 float4, re-fitted with the roots
+	int rootTreeNodes	  = 0;
 	size_t nInterior  = 0;
 	size_t nTris	  = 0;
 	RbDeviceBvh dev	  = {};
@@ -172,6 +174,7 @@ rb_status rb_lbvh_download(const rb_raycaster * rc, rb_node * nodes, rb_tri * tr
 // (Re)builds the root-block boxes from the root table on the device; called after an upload and after every fit.
 rb_status rb_build_root_levels(rb_raycaster * rc, cudaStream_t s);
 bool rb_root_blocks_worthwhile(const float * roots8, size_t nroots);
+rb_status rb_root_tree_topology(rb_raycaster * rc, const float * roots8, size_t nroots); // at upload; boxes by rb_build_root_levels
 
 #define RB_TRACE_BLOCK_THREADS 128
 #define RB_CURSOR_RING 1024

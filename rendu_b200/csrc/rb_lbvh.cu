@@ -483,8 +483,100 @@ bool rb_root_blocks_worthwhile(const float * roots8, size_t nroots) {
 	return npairs > 0 && scene > 0.0 && (pairs / double(npairs)) < 0.02 * scene;
 }
 
+// ------------------------------------------------------------------------------------------------ root tree
+// The reference box-tests EVERY root before it pops the first (Raycaster.cpp:149-155): 52 tests per ray in its largest
+// bundled scene, more than the nodes the ray then visits inside the meshes. Which roots a ray enters is a set, whatever the
+// order the tests are made in, and the slab test is monotone in the box (rb_next_root): a union box that the ray misses
+// hides no root it would enter. So scenes of 9..64 meshes get a small binary tree over their root boxes — topology from
+// the boxes at upload (median split of the centroids), boxes re-computed on the device after every fit — and the path
+// tracer's wavefronts walk it once per ray (rb_roots_tree_pretest) for the bit mask of entered roots, then visit those
+// last mesh first as before: the same hits, bit for bit (irregular rays test every root with the NaN-faithful form).
+static int rb_root_tree_split(std::vector<int> & ids, int begin, int end, const float * roots8, std::vector<int> & refs) {
+	// returns the reference of the subtree over ids[begin, end): ~root for one root, else the index of a new node
+	if(end - begin == 1) return ~ids[begin];
+	float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+	auto centre = [&](int r, int k) { return 0.5f * (roots8[8 * r + k] + roots8[8 * r + 4 + k]); };
+	for(int i = begin; i < end; ++i) {
+		for(int k = 0; k < 3; ++k) {
+			lo[k] = std::min(lo[k], centre(ids[i], k));
+			hi[k] = std::max(hi[k], centre(ids[i], k));
+		}
+	}
+	int axis = 0;
+	if(hi[1] - lo[1] > hi[axis] - lo[axis]) axis = 1;
+	if(hi[2] - lo[2] > hi[axis] - lo[axis]) axis = 2;
+	const int mid = (begin + end) / 2;
+	std::nth_element(ids.begin() + begin, ids.begin() + mid, ids.begin() + end, [&](int a, int b) {
+		const float ca = centre(a, axis), cb = centre(b, axis);
+		return ca < cb || (ca == cb && a < b);
+	});
+	const int node = int(refs.size() / 2);
+	refs.push_back(0);
+	refs.push_back(0); // preorder: a parent's index is smaller than its children's
+	const int l = rb_root_tree_split(ids, begin, mid, roots8, refs);
+	const int r = rb_root_tree_split(ids, mid, end, roots8, refs);
+	refs[2 * node]	   = l;
+	refs[2 * node + 1] = r;
+	return node;
+}
+
+rb_status rb_root_tree_topology(rb_raycaster * rc, const float * roots8, size_t nroots) {
+	cudaFree(rc->d_rootTree);
+	rc->d_rootTree	  = nullptr;
+	rc->rootTreeNodes = 0;
+	const char * e	  = std::getenv("RB_ROOT_TREE_MIN"); // (A/B aid: smallest mesh count that gets a tree; below it the mask pretest tests every root)
+	const size_t least = e ? size_t(std::max(2, std::atoi(e))) : size_t(RB_ROOT_TREE_MIN);
+	if(nroots < least || nroots > RB_ROOT_TREE_MAX || std::getenv("RB_NO_ROOT_TREE")) return RB_OK;
+	std::vector<int> ids(nroots), refs;
+	for(size_t r = 0; r < nroots; ++r) ids[r] = int(r);
+	rb_root_tree_split(ids, 0, int(nroots), roots8, refs);
+	const int nnodes = int(refs.size() / 2);
+	std::vector<float> nodes(size_t(nnodes) * 16, 0.0f);
+	for(int i = 0; i < nnodes; ++i) {
+		std::memcpy(&nodes[size_t(i) * 16 + 12], &refs[2 * i], 4);
+		std::memcpy(&nodes[size_t(i) * 16 + 13], &refs[2 * i + 1], 4);
+	}
+	RB_CUDA(cudaMalloc(&rc->d_rootTree, nodes.size() * sizeof(float) + 64));
+	RB_CUDA(cudaMemcpy(rc->d_rootTree, nodes.data(), nodes.size() * sizeof(float), cudaMemcpyHostToDevice));
+	rc->rootTreeNodes = nnodes;
+	return RB_OK;
+}
+
+// Child boxes of the root tree from the current root boxes: 63 nodes at most, children behind their parent — one thread
+// walks them backwards (a few microseconds, after a fit that took a millisecond).
+__global__ void rb_k_root_tree_fit(const float4 * __restrict__ roots, float4 * __restrict__ tree, int nnodes) {
+	if(blockIdx.x != 0 || threadIdx.x != 0) return;
+	for(int i = nnodes - 1; i >= 0; --i) {
+		float * f = reinterpret_cast<float *>(tree + 4 * size_t(i));
+		for(int side = 0; side < 2; ++side) {
+			const int ref = __float_as_int(f[12 + side]);
+			float lo[3], hi[3];
+			if(ref < 0) {
+				const float4 a = roots[2 * (~ref)], b = roots[2 * (~ref) + 1];
+				lo[0] = a.x; lo[1] = a.y; lo[2] = a.z; hi[0] = b.x; hi[1] = b.y; hi[2] = b.z;
+			} else {
+				const float * c = reinterpret_cast<const float *>(tree + 4 * size_t(ref));
+				for(int k = 0; k < 3; ++k) {
+					lo[k] = fminf(c[k], c[6 + k]);
+					hi[k] = fmaxf(c[3 + k], c[9 + k]);
+				}
+			}
+			for(int k = 0; k < 3; ++k) {
+				f[6 * side + k]		= lo[k];
+				f[6 * side + 3 + k] = hi[k];
+			}
+		}
+	}
+}
+
 rb_status rb_build_root_levels(rb_raycaster * rc, cudaStream_t s) {
 	const int n = rc->dev.nroots;
+	rc->dev.rootTree = nullptr;
+	if(rc->d_rootTree && rc->rootTreeNodes == n - 1) {
+		rb_k_root_tree_fit<<<1, 32, 0, s>>>(rc->d_roots, rc->d_rootTree, rc->rootTreeNodes);
+		RB_CUDA(cudaGetLastError());
+		rc->dev.rootTree = rc->d_rootTree;
+	}
 	rc->dev.rootLevels = 0;
 	rc->dev.rootBlocks = nullptr;
 	if(!rc->rootBlocksWanted || n < 16) return RB_OK;

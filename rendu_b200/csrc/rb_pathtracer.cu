@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_trace(RbDeviceBvh bvh, Rb
 						ray = rb_make_ray(V3{o.x, o.y, o.z}, V3{d.x, d.y, d.z});
 						rb_traversal_init(T, bvh, 0.0001f, 1e8f, st);
 						if(ROOTS == RB_ROOTS_MASK) T.root = int(rb_roots_pretest<COUNT>(bvh, ray, 0.0001f, 1e8f, wp));
+						if(ROOTS == RB_ROOTS_TREE) rb_roots_tree_pretest<COUNT>(T, bvh, ray, st, 0.0001f, 1e8f, wp);
 						active = true;
 					}
 				}
@@ -581,6 +582,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shadow(RbDeviceBvh bvh, R
 							ray = rb_make_ray(lpos, dir);
 							rb_traversal_init(T, bvh, 0.001f, maxDist, st);
 							if(ROOTS == RB_ROOTS_MASK) T.root = int(rb_roots_pretest<COUNT>(bvh, ray, 0.001f, maxDist, wp));
+							if(ROOTS == RB_ROOTS_TREE) rb_roots_tree_pretest<COUNT>(T, bvh, ray, st, 0.001f, maxDist, wp);
 							active = true;
 							++queries;
 						} else {
@@ -630,6 +632,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shadow(RbDeviceBvh bvh, R
 								ray = rb_make_ray(lpos, dir);
 								rb_traversal_init(T, bvh, 0.001f, maxDist, st);
 								if(ROOTS == RB_ROOTS_MASK) T.root = int(rb_roots_pretest<COUNT>(bvh, ray, 0.001f, maxDist, wp));
+								if(ROOTS == RB_ROOTS_TREE) rb_roots_tree_pretest<COUNT>(T, bvh, ray, st, 0.001f, maxDist, wp);
 								finished = false;
 								++queries;
 							} else {
@@ -1214,13 +1217,18 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 		const bool blocks = rc->dev.rootLevels > 0; // many-mesh scenes: kernels compiled with the root-block skipping
 		// A handful of roots (<= 32): all box-tested when a ray starts instead of lazily in the middle of its traversal.
 		// Not in the near-child-first order of closest-hit rays, which tests roots against the shrinking maxi.
-		const bool maskRoots = !blocks && rc->dev.nroots >= 2 && rc->dev.nroots <= 32 && !std::getenv("RB_PT_LAZY_ROOTS");
+		// 9..64 roots: the set of entered roots comes from one walk of the tree over the root boxes (rb_roots_tree_pretest)
+		// instead of one test per root — 52 per ray in the reference's largest bundled scene. Wins over mask and blocks.
+		const bool lazyRoots = std::getenv("RB_PT_LAZY_ROOTS") != nullptr;
+		const bool treeRoots = !lazyRoots && rc->dev.rootTree != nullptr;
+		const bool maskRoots = !treeRoots && !blocks && rc->dev.nroots >= 2 && rc->dev.nroots <= 32 && !lazyRoots;
 		auto kTrace = blocks ? (ordered ? rb_k_pt_trace<true, RB_ROOTS_BLOCKS> : rb_k_pt_trace<false, RB_ROOTS_BLOCKS>)
 							 : (ordered ? rb_k_pt_trace<true, RB_ROOTS_LAZY> : (maskRoots ? rb_k_pt_trace<false, RB_ROOTS_MASK> : rb_k_pt_trace<false, RB_ROOTS_LAZY>));
-		if(profCounting) kTrace = ordered ? rb_k_pt_trace<true, RB_ROOTS_LAZY, true> : (maskRoots ? rb_k_pt_trace<false, RB_ROOTS_MASK, true> : rb_k_pt_trace<false, RB_ROOTS_LAZY, true>); // (block skipping: plain root loop, same hits, counted)
+		if(treeRoots && !ordered) kTrace = rb_k_pt_trace<false, RB_ROOTS_TREE>;
+		if(profCounting) kTrace = ordered ? rb_k_pt_trace<true, RB_ROOTS_LAZY, true> : (treeRoots ? rb_k_pt_trace<false, RB_ROOTS_TREE, true> : (maskRoots ? rb_k_pt_trace<false, RB_ROOTS_MASK, true> : rb_k_pt_trace<false, RB_ROOTS_LAZY, true>)); // (block skipping: plain root loop, same hits, counted)
 		// The cp.async-fed forms of the two wavefront kernels (see "asynchronous work feed"); the counting copies of the
 		// profile pass keep the plain form.
-		const bool feed = !profCounting && std::getenv("RB_PT_FEED") != nullptr;
+		const bool feed = !profCounting && !treeRoots && std::getenv("RB_PT_FEED") != nullptr;
 		size_t smemTrace = smem, smemShadow = smem;
 		if(feed) {
 			kTrace = blocks ? (ordered ? rb_k_pt_trace_feed<true, RB_ROOTS_BLOCKS> : rb_k_pt_trace_feed<false, RB_ROOTS_BLOCKS>)
@@ -1235,7 +1243,12 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 		// are looked at (measured: +5 % with the pretest, against -3 % for the closest-hit wavefront).
 		auto kShadow = blocks ? (masked ? (ordered ? rb_k_pt_shadow<true, true, RB_ROOTS_BLOCKS> : rb_k_pt_shadow<true, false, RB_ROOTS_BLOCKS>) : rb_k_pt_shadow<false, true, RB_ROOTS_BLOCKS>)
 							  : (masked ? (ordered ? rb_k_pt_shadow<true, true, RB_ROOTS_LAZY> : rb_k_pt_shadow<true, false, RB_ROOTS_LAZY>) : rb_k_pt_shadow<false, true, RB_ROOTS_LAZY>);
-		if(profCounting) kShadow = masked ? (ordered ? rb_k_pt_shadow<true, true, RB_ROOTS_LAZY, true> : rb_k_pt_shadow<true, false, RB_ROOTS_LAZY, true>) : rb_k_pt_shadow<false, true, RB_ROOTS_LAZY, true>;
+		// With a root tree the shadow wavefront uses it too wherever its root tests see a fixed maxi (any-hit walks, and the
+		// masked walk in the reference's order): a visible sample otherwise tests every root of the scene.
+		const bool treeShadow = treeRoots && !(masked && ordered) && !std::getenv("RB_PT_SHADOW_LAZY");
+		if(treeShadow) kShadow = masked ? rb_k_pt_shadow<true, false, RB_ROOTS_TREE> : rb_k_pt_shadow<false, true, RB_ROOTS_TREE>;
+		if(profCounting) kShadow = masked ? (ordered ? rb_k_pt_shadow<true, true, RB_ROOTS_LAZY, true> : (treeShadow ? rb_k_pt_shadow<true, false, RB_ROOTS_TREE, true> : rb_k_pt_shadow<true, false, RB_ROOTS_LAZY, true>))
+										  : (treeShadow ? rb_k_pt_shadow<false, true, RB_ROOTS_TREE, true> : rb_k_pt_shadow<false, true, RB_ROOTS_LAZY, true>);
 		if(feed) {
 			kShadow = blocks ? (masked ? (ordered ? rb_k_pt_shadow_feed<true, true, RB_ROOTS_BLOCKS> : rb_k_pt_shadow_feed<true, false, RB_ROOTS_BLOCKS>) : rb_k_pt_shadow_feed<false, true, RB_ROOTS_BLOCKS>)
 							 : (masked ? (ordered ? rb_k_pt_shadow_feed<true, true, RB_ROOTS_LAZY> : rb_k_pt_shadow_feed<true, false, RB_ROOTS_LAZY>) : rb_k_pt_shadow_feed<false, true, RB_ROOTS_LAZY>);

@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_persistent(RbDevice
 // Phase-voting scheduler. Every live lane is waiting either for a node step or for a leaf step; the warp executes
 // the leaf phase once at least `leafVotes` lanes wait for it (or nobody wants a node), otherwise the node phase. Lanes
 // of the other kind idle for that iteration instead of the whole warp running at the pace of one lane's descent.
-template<bool ANY, bool ORDERED, bool BLOCKS>
+template<bool ANY, bool ORDERED, bool BLOCKS, bool TREE = false>
 __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_phased(RbDeviceBvh bvh, const float * __restrict__ org, const float * __restrict__ dir, float mini, float maxi, unsigned int n, void * __restrict__ out, unsigned int * __restrict__ cursor, int threshold, int leafVotes, int nodeSteps) {
 	extern __shared__ int s_stack[];
 	const RbStack st		= rb_make_stack(s_stack + threadIdx.x, blockDim.x);
@@ -231,6 +231,9 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_phased(RbDeviceBvh 
 						rb_load_ray(org, dir, idx, o, d);
 						ray = rb_make_ray(o, d);
 						rb_traversal_init(T, bvh, mini, maxi, st);
+						// TREE: scenes of 9..64 meshes — the roots this ray enters from one walk of the tree over the root
+						// boxes (rb_roots_tree_pretest) instead of one test per root; same set, same visiting order.
+						if(TREE) rb_roots_tree_pretest<false>(T, bvh, ray, st, mini, maxi, nullptr);
 						rayIdx = idx;
 						active = true;
 					}
@@ -253,7 +256,7 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_phased(RbDeviceBvh 
 				// Up to `nodeSteps` descents per vote: the vote, executed by all 32 lanes, costs about as much as a
 				// node step; a lane that reaches a leaf (or finishes) early sits out the remaining steps.
 				for(int k = 0; k < nodeSteps; ++k) {
-					finished = rb_phase_node<false, ORDERED, BLOCKS>(T, bvh, ray, st, nullptr);
+					finished = rb_phase_node<false, ORDERED, TREE ? RB_ROOTS_TREE : (BLOCKS ? RB_ROOTS_BLOCKS : RB_ROOTS_LAZY)>(T, bvh, ray, st, nullptr);
 					if(finished || rb_wants_leaf(T)) break;
 				}
 			}
@@ -703,6 +706,10 @@ void rb_raycaster_free_device(rb_raycaster * rc) {
 	rb_wide_free_device(rc);
 	cudaFree(rc->d_rootBlocks);
 	rc->d_rootBlocks   = nullptr;
+	cudaFree(rc->d_rootTree);
+	rc->d_rootTree	   = nullptr;
+	rc->rootTreeNodes  = 0;
+	rc->dev.rootTree   = nullptr;
 	rc->rootBlocksCapacity = 0;
 	rc->dev.rootBlocks = nullptr;
 	rc->dev.rootLevels = 0;
@@ -758,7 +765,9 @@ rb_status rb_raycaster_upload_flat(rb_raycaster * rc, const RbFlatBvh & flat) {
 	rc->dev.nroots	   = int(rc->meshCount);
 	rc->dev.stackDepth = rc->maxDepth + 1;
 	rc->rootBlocksWanted = rb_root_blocks_worthwhile(flat.roots.data(), flat.roots.size() / 8);
-	rb_status st		 = rb_build_root_levels(rc, cudaStreamPerThread);
+	rb_status st		 = rb_root_tree_topology(rc, flat.roots.data(), flat.roots.size() / 8);
+	if(st) return st;
+	st = rb_build_root_levels(rc, cudaStreamPerThread);
 	if(st) return st;
 	RB_CUDA(cudaStreamSynchronize(cudaStreamPerThread));
 	rc->built		   = true;
@@ -1188,6 +1197,9 @@ static rb_status rb_launch_trace(const rb_raycaster * rc, const float * d_origin
 		// Handles that carry root blocks (many meshes in a spatially coherent order) use the kernels compiled with them.
 		auto kernel = rc->dev.rootLevels > 0 ? (ordered ? rb_k_trace_phased<ANY, true, true> : rb_k_trace_phased<ANY, false, true>)
 											 : (ordered ? rb_k_trace_phased<ANY, true, false> : rb_k_trace_phased<ANY, false, false>);
+		// A root tree (9..64 meshes) serves every query whose root tests see a fixed maxi: any-hit, and closest-hit in the
+		// reference's order (the near-child-first closest-hit order tests roots against the shrinking maxi: lazy loop).
+		if(rc->dev.rootTree && (ANY || !ordered)) kernel = ordered ? rb_k_trace_phased<ANY, true, false, true> : rb_k_trace_phased<ANY, false, false, true>;
 		return rb_launch_persistent<ANY>(rc, kernel, smem, 1, d_origins, d_directions, mini, maxi, nrays, d_out, s, rc->fetchThreshold, rc->leafVotes, rc->nodeSteps > 0 ? rc->nodeSteps : 1);
 	}
 	if(rc->persistent) {

@@ -169,6 +169,7 @@ struct RbTraversal {
 	float mini, maxi, maxi0;
 	int cur, root;
 	unsigned int top; // shared-memory address of the next free stack entry (== base when the stack is empty)
+	int rootHi;		  // RB_ROOTS_TREE only: roots 32..63 of the mask of entered roots (`root` holds 0..31)
 };
 
 // The stack is addressed in the shared window directly (st.shared / ld.shared on a 32-bit address kept in a register):
@@ -205,6 +206,7 @@ RB_D void rb_traversal_init(RbTraversal & T, const RbDeviceBvh & bvh, float mini
 	T.cur	   = RB_REF_NONE;
 	T.top	   = st.base;
 	T.root	   = bvh.nroots;
+	T.rootHi   = 0;
 }
 
 // Next root whose box the ray enters, last mesh first: the reference tests every root against the caller's (mini, maxi)
@@ -219,6 +221,7 @@ RB_D void rb_traversal_init(RbTraversal & T, const RbDeviceBvh & bvh, float mini
 #define RB_ROOTS_LAZY 0	  // every root box-tested when the ray gets to it
 #define RB_ROOTS_BLOCKS 1 // ... with whole blocks of consecutive roots skipped on a miss (many-mesh scenes)
 #define RB_ROOTS_MASK 2	  // at most 32 roots, all box-tested when the ray starts (rb_roots_pretest): T.root is the bit mask of those entered
+#define RB_ROOTS_TREE 3	  // 9..64 roots: the mask (T.root, T.rootHi) comes from one walk of the tree over the root boxes (rb_roots_tree_pretest)
 
 // The reference box-tests EVERY root against the caller's (mini, maxi) before it pops the first one (Raycaster.cpp:149-155).
 // For a handful of roots the same is done here, up front: the tests are independent (their loads overlap), where the lazy
@@ -241,6 +244,57 @@ RB_D unsigned int rb_roots_pretest(const RbDeviceBvh & bvh, const RbRay & ray, f
 	return ray.regular ? rb_roots_pretest_t<true, COUNT>(bvh, ray, mini, maxi, work) : rb_roots_pretest_t<false, COUNT>(bvh, ray, mini, maxi, work);
 }
 
+// The same set of entered roots from the tree over the root boxes (RbDeviceBvh::rootTree; rb_lbvh.cu "root tree"): a node
+// carries the boxes of its two children, so one visit is two slab tests with the packed arithmetic of rb_node_test, and a
+// child that is a root is tested against exactly its own box with the caller's (mini, maxi) — what the reference does for
+// it. A union box the ray misses hides no root it would enter (the test is monotone in the box for regular rays). The
+// ray's own stack column is empty at this point and serves the walk. Irregular rays (NaNs in the slab arithmetic) test every
+// root with the literal form, like rb_roots_pretest.
+template<bool COUNT>
+RB_D void rb_roots_tree_pretest(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ray, const RbStack & st, float mini, float maxi, RbWork * work) {
+	unsigned int lo = 0u, hi = 0u;
+	if(!ray.regular) {
+		for(int r = 0; r < bvh.nroots; ++r) {
+			const float4 r0 = rb_ldg4(bvh.roots + 2 * r);
+			const float4 r1 = rb_ldg4(bvh.roots + 2 * r + 1);
+			if(rb_box_test_t<false>(ray, r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, mini, maxi)) {
+				if(r < 32) lo |= 1u << r; else hi |= 1u << (r - 32);
+			}
+		}
+		if(COUNT) work->roots += (unsigned int)bvh.nroots;
+	} else {
+		int cur = 0;
+		for(;;) {
+			float4 n0, n1, n2, n3;
+			rb_ldg_node(bvh.rootTree + 4 * (size_t)cur, n0, n1, n2, n3);
+			if(COUNT) work->roots += 2u;
+			bool hitL, hitR;
+			float dL, dR;
+			rb_node_test<true>(ray, n0, n1, n2, mini, maxi, hitL, hitR, dL, dR);
+			const int refL = __float_as_int(n3.x), refR = __float_as_int(n3.y);
+			int next = RB_REF_NONE;
+			if(hitL) {
+				if(refL < 0) { const int r = ~refL; if(r < 32) lo |= 1u << r; else hi |= 1u << (r - 32); }
+				else next = refL;
+			}
+			if(hitR) {
+				if(refR < 0) { const int r = ~refR; if(r < 32) lo |= 1u << r; else hi |= 1u << (r - 32); }
+				else {
+					if(next != RB_REF_NONE) rb_push(T, st, next);
+					next = refR;
+				}
+			}
+			if(next == RB_REF_NONE) {
+				if(rb_stack_empty(T, st)) break;
+				next = rb_pop(T, st);
+			}
+			cur = next;
+		}
+	}
+	T.root	 = int(lo);
+	T.rootHi = int(hi);
+}
+
 template<bool REGULAR, bool COUNT, int ROOTS>
 RB_D int rb_next_root(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ray, float maxi, RbWork * work) {
 	if(ROOTS == RB_ROOTS_MASK) {
@@ -248,6 +302,21 @@ RB_D int rb_next_root(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ra
 		if(mask == 0u) return RB_REF_NONE;
 		const int r = 31 - __clz(mask); // last mesh first
 		T.root		= int(mask & ~(1u << r));
+		return __float_as_int(rb_ldg4(bvh.roots + 2 * r).w);
+	}
+	if(ROOTS == RB_ROOTS_TREE) {
+		const unsigned int hi = (unsigned int)T.rootHi, lo = (unsigned int)T.root;
+		int r;
+		if(hi != 0u) {
+			r		 = 31 - __clz(hi);
+			T.rootHi = int(hi & ~(1u << r));
+			r += 32;
+		} else if(lo != 0u) {
+			r	   = 31 - __clz(lo);
+			T.root = int(lo & ~(1u << r));
+		} else {
+			return RB_REF_NONE;
+		}
 		return __float_as_int(rb_ldg4(bvh.roots + 2 * r).w);
 	}
 	const bool BLOCKS = ROOTS == RB_ROOTS_BLOCKS;

@@ -16,7 +16,13 @@ struct RbDeviceBvh {
 	const float4 * rootBlocks;
 	int rootLevels;
 	int rootLevelOffset[RB_MAX_ROOT_LEVELS + 1];
+	// Scenes with 9..64 meshes: a small binary tree over the root boxes in the interior-node layout (child boxes and
+	// references in the parent; reference < 0: root ~reference). rb_roots_tree_pretest walks it once per ray and returns
+	// the bit mask of the roots whose box the ray enters. nullptr: not built.
+	const float4 * rootTree;
 };
+#define RB_ROOT_TREE_MIN 9
+#define RB_ROOT_TREE_MAX 64
 
 #define RB_REF_NONE 0x7fffffff
 #define RB_LEAF_BITS 3

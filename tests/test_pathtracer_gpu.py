@@ -294,6 +294,50 @@ def test_cp_async_fed_wavefronts_return_the_same_image(monkeypatch, name):
         assert np.array_equal(fed.view(np.uint32), plain.view(np.uint32))
 
 
+@pytest.mark.parametrize("extra", [2, 5, 33, 57])
+def test_root_tree_returns_the_same_image_as_the_root_loop(monkeypatch, extra):
+    """Scenes of 9..64 meshes find the roots a ray enters with one walk of a tree over the root boxes instead of one test
+    per root (RB_ROOTS_TREE, rb_roots_tree_pretest) — closest-hit and shadow wavefronts. The set of entered roots and the
+    order they are visited in are the reference's, so the image equals the one of the lazy root loop (RB_PT_LAZY_ROOTS=1)
+    bit for bit: 7 + `extra` meshes = 9 (smallest tree), 12, 40 (both mask words), 64 (largest); overlapping boxes, meshes
+    that share a position; also after a transform edit re-fits the roots."""
+    import copy
+    desc = wl.cornell_synthetic(24, 16, 16)
+    cam = wl.cornell_camera(4 / 3)
+    rng = np.random.RandomState(extra)
+    proto = desc["objects"][0]
+    for k in range(extra):
+        o = copy.deepcopy(desc["objects"][1 + k % (len(desc["objects"]) - 1)])
+        m = np.eye(4, dtype=np.float32)
+        m[0, 0] = m[1, 1] = m[2, 2] = np.float32(rng.uniform(0.08, 0.3))
+        m[3, :3] = rng.uniform(-0.7, 0.7, 3).astype(np.float32) + np.array([0, 1.0, 0], np.float32)
+        if k % 7 == 3:
+            m[3, :3] = desc_shift  # two meshes at the same place
+        desc_shift = m[3, :3].copy()
+        o["model"] = m.reshape(16)
+        desc["objects"].append(o)
+    assert len(desc["objects"]) == 7 + extra and proto is desc["objects"][0]
+    imgs = {}
+    for mode in ("tree", "lazy"):
+        if mode == "lazy":
+            monkeypatch.setenv("RB_PT_LAZY_ROOTS", "1")
+        else:
+            monkeypatch.delenv("RB_PT_LAZY_ROOTS", raising=False)
+        sc = rpt.Scene(desc)
+        pt = rpt.PathTracer(sc)
+        img = np.zeros((90, 120, 3), np.float32)
+        pt.render(cam, 16, 6, img, rpt.make_opts(seed=5))
+        moved = np.array(desc["objects"][-1]["model"], np.float32).copy()
+        moved[12:15] += np.array([0.2, -0.1, 0.15], np.float32)
+        sc.set_object_transform(len(desc["objects"]) - 1, moved)
+        img2 = np.zeros((90, 120, 3), np.float32)
+        pt.render(cam, 16, 6, img2, rpt.make_opts(seed=5))
+        imgs[mode] = (img, img2)
+        assert np.isfinite(img).all() and img.mean() > 0.01 and not np.array_equal(img, img2)
+    assert np.array_equal(imgs["tree"][0].view(np.uint32), imgs["lazy"][0].view(np.uint32))
+    assert np.array_equal(imgs["tree"][1].view(np.uint32), imgs["lazy"][1].view(np.uint32))
+
+
 def test_lights_and_background_follow_edits_between_renders():
     """The reference reads scene->lights and the background through the shared Scene inside render(), so an edit between
     two frames shows in the next one. Here: rb_scene_clear_lights / add_light / set_background + rb_scene_sync on a

@@ -48,8 +48,9 @@ def main(reps):
         h, u, data = rows(rep)
         recs = [record(h, u, r) for r in data]
         if "raycast" in rep:  # rb_k_trace_phased<ANY, ORDERED, BLOCKS>: closest = <0, 0, 0>, any = <1, 1, 0>; of each kind the longer launch is the incoherent set
-            for kind, tag in (("closest", "<0, 0, 0>"), ("any", "<1, 1, 0>")):
-                c = sorted([r for r in recs if tag in r["kernel"] or tag.replace("0", "(bool)0").replace("1", "(bool)1") in r["kernel"]], key=lambda r: r.get("duration_ms", 0))
+            import re
+            for kind, first in (("closest", "0"), ("any", "1")):  # the first template argument is ANY, printed as `0` or `(bool)0`
+                c = sorted([r for r in recs if re.search(r"rb_k_trace_phased<(?:\(bool\))?" + first + r"\b", r["kernel"])], key=lambda r: r.get("duration_ms", 0))
                 if len(c) >= 2:
                     out["raycast_%s_coherent" % kind], out["raycast_%s_incoherent" % kind] = c[0], c[-1]
         else:  # path tracer: the longest launch of each kernel class (the first bounce of a full batch)

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Developer probe (GPU box): many-mesh scenes. Closest-hit throughput with and without the root-block skipping
-(RB_NO_ROOT_BLOCKS=1), results compared bit for bit."""
+(RB_NO_ROOT_BLOCKS=1) and, for 9..64 meshes, with and without the tree over the root boxes (RB_NO_ROOT_TREE=1), results
+compared bit for bit."""
 import os, sys
 import numpy as np
 import torch
@@ -47,3 +48,30 @@ for nmesh, ordered in ((64, True), (443, True), (2000, True), (443, False)):
         outs[name] = (e0.elapsed_time(e1) / 5, d_h.clone())
     same = bool((outs["blocks"][1] == outs["linear"][1]).all())
     print("%s order, %5d meshes: with root blocks %.3f ms, linear root loop %.3f ms (%.1fx), identical hit records: %s" % ("row" if ordered else "random", nmesh, outs["blocks"][0], outs["linear"][0], outs["linear"][0] / outs["blocks"][0], same), flush=True)
+
+# 9..64 meshes: the root tree (rb_roots_tree_pretest) against the plain root loop; random mesh order (no blocks either way)
+for nmesh in (12, 24, 52, 64):
+    outs = {}
+    for name, env in (("tree", None), ("linear", "1")):
+        if env: os.environ["RB_NO_ROOT_TREE"] = env
+        else: os.environ.pop("RB_NO_ROOT_TREE", None)
+        os.environ["RB_NO_ROOT_BLOCKS"] = "1"
+        r = build(nmesh, False)
+        d_h = torch.empty(n * 48, dtype=torch.uint8, device=dev)
+        d_a = torch.empty(n, dtype=torch.uint8, device=dev)
+        for _ in range(3):
+            r.intersects_device(d_o.data_ptr(), d_d.data_ptr(), n, d_h.data_ptr(), 1e-4, 1e8, sh)
+        torch.cuda.synchronize()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        for _ in range(5):
+            r.intersects_device(d_o.data_ptr(), d_d.data_ptr(), n, d_h.data_ptr(), 1e-4, 1e8, sh)
+        e1.record()
+        for _ in range(5):
+            r.intersectsAny_device(d_o.data_ptr(), d_d.data_ptr(), n, d_a.data_ptr(), 1e-4, 1e8, sh)
+        e2.record(); torch.cuda.synchronize()
+        outs[name] = (e0.elapsed_time(e1) / 5, e1.elapsed_time(e2) / 5, d_h.clone(), d_a.clone())
+    same = bool((outs["tree"][2] == outs["linear"][2]).all()) and bool((outs["tree"][3] == outs["linear"][3]).all())
+    print("random order, %5d meshes: closest-hit with the root tree %.3f ms, root loop %.3f ms (%.2fx); any-hit %.3f / %.3f ms (%.2fx); identical records: %s"
+          % (nmesh, outs["tree"][0], outs["linear"][0], outs["linear"][0] / outs["tree"][0], outs["tree"][1], outs["linear"][1], outs["linear"][1] / outs["tree"][1], same), flush=True)
+os.environ.pop("RB_NO_ROOT_TREE", None); os.environ.pop("RB_NO_ROOT_BLOCKS", None)
