@@ -99,6 +99,7 @@ struct rb_raycaster {
 	size_t rootBlocksCapacity = 0;	  // entries d_rootBlocks was allocated for
 	float4 * d_rootTree	  = nullptr; // tree over the root boxes (9..64 meshes): nroots - 1 nodes of 4 float4, re-fitted with the roots
 	int rootTreeNodes	  = 0;
+	int rootTreeDepth	  = 0;		 // interior levels of that tree (stack entries its walk may need)
 	size_t nInterior  = 0;
 	size_t nTris	  = 0;
 	RbDeviceBvh dev	  = {};
@@ -174,6 +175,11 @@ rb_status rb_lbvh_download(const rb_raycaster * rc, rb_node * nodes, rb_tri * tr
 // (Re)builds the root-block boxes from the root table on the device; called after an upload and after every fit.
 rb_status rb_build_root_levels(rb_raycaster * rc, cudaStream_t s);
 bool rb_root_blocks_worthwhile(const float * roots8, size_t nroots);
+// Entries of a ray's stack column: the deepest hierarchy, or the walk of the root tree (one pending node per level) if that is
+// deeper (many tiny meshes), behind the mask words of a big root tree.
+inline int rb_stack_entries(const rb_raycaster * rc) {
+	return rc->dev.rootWords + (rc->maxDepth + 1 > rc->rootTreeDepth + 1 ? rc->maxDepth + 1 : rc->rootTreeDepth + 1);
+}
 rb_status rb_root_tree_topology(rb_raycaster * rc, const float * roots8, size_t nroots); // at upload; boxes by rb_build_root_levels
 
 #define RB_TRACE_BLOCK_THREADS 128

@@ -491,9 +491,11 @@ bool rb_root_blocks_worthwhile(const float * roots8, size_t nroots) {
 // the boxes at upload (median split of the centroids), boxes re-computed on the device after every fit — and the path
 // tracer's wavefronts walk it once per ray (rb_roots_tree_pretest) for the bit mask of entered roots, then visit those
 // last mesh first as before: the same hits, bit for bit (irregular rays test every root with the NaN-faithful form).
-static int rb_root_tree_split(std::vector<int> & ids, int begin, int end, const float * roots8, std::vector<int> & refs) {
+// Up to 64 meshes the mask is two registers; up to 512 it lives in the first entries of the ray's stack column.
+static int rb_root_tree_split(std::vector<int> & ids, int begin, int end, const float * roots8, std::vector<int> & refs, int level, int & depth) {
 	// returns the reference of the subtree over ids[begin, end): ~root for one root, else the index of a new node
 	if(end - begin == 1) return ~ids[begin];
+	depth = std::max(depth, level + 1);
 	float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
 	auto centre = [&](int r, int k) { return 0.5f * (roots8[8 * r + k] + roots8[8 * r + 4 + k]); };
 	for(int i = begin; i < end; ++i) {
@@ -513,8 +515,8 @@ static int rb_root_tree_split(std::vector<int> & ids, int begin, int end, const 
 	const int node = int(refs.size() / 2);
 	refs.push_back(0);
 	refs.push_back(0); // preorder: a parent's index is smaller than its children's
-	const int l = rb_root_tree_split(ids, begin, mid, roots8, refs);
-	const int r = rb_root_tree_split(ids, mid, end, roots8, refs);
+	const int l = rb_root_tree_split(ids, begin, mid, roots8, refs, level + 1, depth);
+	const int r = rb_root_tree_split(ids, mid, end, roots8, refs, level + 1, depth);
 	refs[2 * node]	   = l;
 	refs[2 * node + 1] = r;
 	return node;
@@ -524,12 +526,17 @@ rb_status rb_root_tree_topology(rb_raycaster * rc, const float * roots8, size_t 
 	cudaFree(rc->d_rootTree);
 	rc->d_rootTree	  = nullptr;
 	rc->rootTreeNodes = 0;
+	rc->rootTreeDepth = 0;
+	rc->dev.rootWords = 0;
 	const char * e	  = std::getenv("RB_ROOT_TREE_MIN"); // (A/B aid: smallest mesh count that gets a tree; below it the mask pretest tests every root)
 	const size_t least = e ? size_t(std::max(2, std::atoi(e))) : size_t(RB_ROOT_TREE_MIN);
-	if(nroots < least || nroots > RB_ROOT_TREE_MAX || std::getenv("RB_NO_ROOT_TREE")) return RB_OK;
+	if(nroots < least || nroots > RB_ROOT_TREE_BIG_MAX || std::getenv("RB_NO_ROOT_TREE")) return RB_OK;
 	std::vector<int> ids(nroots), refs;
 	for(size_t r = 0; r < nroots; ++r) ids[r] = int(r);
-	rb_root_tree_split(ids, 0, int(nroots), roots8, refs);
+	int depth = 0;
+	rb_root_tree_split(ids, 0, int(nroots), roots8, refs, 0, depth);
+	rc->rootTreeDepth = depth; // interior levels: the walk keeps at most one pending node per level on the ray's stack
+	rc->dev.rootWords = nroots > RB_ROOT_TREE_MAX ? int((nroots + 31) / 32) : 0;
 	const int nnodes = int(refs.size() / 2);
 	std::vector<float> nodes(size_t(nnodes) * 16, 0.0f);
 	for(int i = 0; i < nnodes; ++i) {
@@ -626,7 +633,7 @@ static rb_status rb_run_fit(rb_raycaster * rc, cudaStream_t s) {
 	if(e == cudaSuccess) e = cudaStreamSynchronize(s);
 	if(e != cudaSuccess) return rb_fail(RB_ERR_CUDA, "hierarchy fit failed: %s", cudaGetErrorString(e));
 	rc->maxDepth	   = int(depth);
-	rc->dev.stackDepth = rc->maxDepth + 1;
+	rc->dev.stackDepth = rb_stack_entries(rc);
 	return rb_build_root_levels(rc, s); // root boxes may have moved
 }
 

@@ -154,7 +154,7 @@ RB_D void rb_pt_flush_work(const RbWork & w, unsigned int lane, unsigned long lo
 template<bool ORDERED, int ROOTS, bool COUNT = false>
 __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_trace(RbDeviceBvh bvh, RbPathBuffers pb, const uint32_t * __restrict__ queue, uint32_t did, int threshold, int leafVotes, int nodeSteps, unsigned long long * __restrict__ stats) {
 	extern __shared__ int s_stack[];
-	const RbStack st		= rb_make_stack(s_stack + threadIdx.x, blockDim.x);
+	const RbStack st		= rb_make_stack(s_stack + threadIdx.x + (ROOTS == RB_ROOTS_TREE_BIG ? bvh.rootWords * blockDim.x : 0), blockDim.x);
 	const unsigned int lane = threadIdx.x & 31u;
 	const unsigned int n	= pb.counters[rb_cnt_queue(did)];
 	unsigned int * cursor	= pb.counters + rb_cnt_cursor_t(did);
@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_trace(RbDeviceBvh bvh, Rb
 						rb_traversal_init(T, bvh, 0.0001f, 1e8f, st);
 						if(ROOTS == RB_ROOTS_MASK) T.root = int(rb_roots_pretest<COUNT>(bvh, ray, 0.0001f, 1e8f, wp));
 						if(ROOTS == RB_ROOTS_TREE) rb_roots_tree_pretest<COUNT>(T, bvh, ray, st, 0.0001f, 1e8f, wp);
+						if(ROOTS == RB_ROOTS_TREE_BIG) rb_roots_tree_pretest_big<COUNT>(T, bvh, ray, st, 0.0001f, 1e8f, wp);
 						active = true;
 					}
 				}
@@ -547,7 +548,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK, RB_PT_SHADE_MIN_BLOCKS) rb_k_pt_s
 template<bool MASKED, bool ORDERED, int ROOTS, bool COUNT = false>
 __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shadow(RbDeviceBvh bvh, RbPathBuffers pb, RbSceneDev sc, uint32_t did, int threshold, int leafVotes, int nodeSteps, unsigned long long * __restrict__ stats) {
 	extern __shared__ int s_stack[];
-	const RbStack st		= rb_make_stack(s_stack + threadIdx.x, blockDim.x);
+	const RbStack st		= rb_make_stack(s_stack + threadIdx.x + (ROOTS == RB_ROOTS_TREE_BIG ? bvh.rootWords * blockDim.x : 0), blockDim.x);
 	const unsigned int lane = threadIdx.x & 31u;
 	const unsigned int n	= pb.counters[rb_cnt_shadow(did)];
 	unsigned int * cursor	= pb.counters + rb_cnt_cursor_s(did);
@@ -583,6 +584,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shadow(RbDeviceBvh bvh, R
 							rb_traversal_init(T, bvh, 0.001f, maxDist, st);
 							if(ROOTS == RB_ROOTS_MASK) T.root = int(rb_roots_pretest<COUNT>(bvh, ray, 0.001f, maxDist, wp));
 							if(ROOTS == RB_ROOTS_TREE) rb_roots_tree_pretest<COUNT>(T, bvh, ray, st, 0.001f, maxDist, wp);
+							if(ROOTS == RB_ROOTS_TREE_BIG) rb_roots_tree_pretest_big<COUNT>(T, bvh, ray, st, 0.001f, maxDist, wp);
 							active = true;
 							++queries;
 						} else {
@@ -633,6 +635,8 @@ __global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shadow(RbDeviceBvh bvh, R
 								rb_traversal_init(T, bvh, 0.001f, maxDist, st);
 								if(ROOTS == RB_ROOTS_MASK) T.root = int(rb_roots_pretest<COUNT>(bvh, ray, 0.001f, maxDist, wp));
 								if(ROOTS == RB_ROOTS_TREE) rb_roots_tree_pretest<COUNT>(T, bvh, ray, st, 0.001f, maxDist, wp);
+								if(ROOTS == RB_ROOTS_TREE_BIG) rb_roots_tree_pretest_big<COUNT>(T, bvh, ray, st, 0.001f, maxDist, wp);
+							if(ROOTS == RB_ROOTS_TREE_BIG) rb_roots_tree_pretest_big<COUNT>(T, bvh, ray, st, 0.001f, maxDist, wp);
 								finished = false;
 								++queries;
 							} else {
@@ -1224,8 +1228,9 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 		const bool maskRoots = !treeRoots && !blocks && rc->dev.nroots >= 2 && rc->dev.nroots <= 32 && !lazyRoots;
 		auto kTrace = blocks ? (ordered ? rb_k_pt_trace<true, RB_ROOTS_BLOCKS> : rb_k_pt_trace<false, RB_ROOTS_BLOCKS>)
 							 : (ordered ? rb_k_pt_trace<true, RB_ROOTS_LAZY> : (maskRoots ? rb_k_pt_trace<false, RB_ROOTS_MASK> : rb_k_pt_trace<false, RB_ROOTS_LAZY>));
-		if(treeRoots && !ordered) kTrace = rb_k_pt_trace<false, RB_ROOTS_TREE>;
-		if(profCounting) kTrace = ordered ? rb_k_pt_trace<true, RB_ROOTS_LAZY, true> : (treeRoots ? rb_k_pt_trace<false, RB_ROOTS_TREE, true> : (maskRoots ? rb_k_pt_trace<false, RB_ROOTS_MASK, true> : rb_k_pt_trace<false, RB_ROOTS_LAZY, true>)); // (block skipping: plain root loop, same hits, counted)
+		const bool bigTree = treeRoots && rc->dev.rootWords > 0; // 65..512 meshes: the mask of entered roots in the stack column
+		if(treeRoots && !ordered) kTrace = bigTree ? rb_k_pt_trace<false, RB_ROOTS_TREE_BIG> : rb_k_pt_trace<false, RB_ROOTS_TREE>;
+		if(profCounting) kTrace = ordered ? rb_k_pt_trace<true, RB_ROOTS_LAZY, true> : (treeRoots ? (bigTree ? rb_k_pt_trace<false, RB_ROOTS_TREE_BIG, true> : rb_k_pt_trace<false, RB_ROOTS_TREE, true>) : (maskRoots ? rb_k_pt_trace<false, RB_ROOTS_MASK, true> : rb_k_pt_trace<false, RB_ROOTS_LAZY, true>)); // (block skipping: plain root loop, same hits, counted)
 		// The cp.async-fed forms of the two wavefront kernels (see "asynchronous work feed"); the counting copies of the
 		// profile pass keep the plain form.
 		const bool feed = !profCounting && !treeRoots && std::getenv("RB_PT_FEED") != nullptr;
@@ -1246,9 +1251,10 @@ extern "C" rb_status rb_pathtracer_render_device(rb_pathtracer * pt, const rb_ca
 		// With a root tree the shadow wavefront uses it too wherever its root tests see a fixed maxi (any-hit walks, and the
 		// masked walk in the reference's order): a visible sample otherwise tests every root of the scene.
 		const bool treeShadow = treeRoots && !(masked && ordered) && !std::getenv("RB_PT_SHADOW_LAZY");
-		if(treeShadow) kShadow = masked ? rb_k_pt_shadow<true, false, RB_ROOTS_TREE> : rb_k_pt_shadow<false, true, RB_ROOTS_TREE>;
-		if(profCounting) kShadow = masked ? (ordered ? rb_k_pt_shadow<true, true, RB_ROOTS_LAZY, true> : (treeShadow ? rb_k_pt_shadow<true, false, RB_ROOTS_TREE, true> : rb_k_pt_shadow<true, false, RB_ROOTS_LAZY, true>))
-										  : (treeShadow ? rb_k_pt_shadow<false, true, RB_ROOTS_TREE, true> : rb_k_pt_shadow<false, true, RB_ROOTS_LAZY, true>);
+		if(treeShadow) kShadow = masked ? (bigTree ? rb_k_pt_shadow<true, false, RB_ROOTS_TREE_BIG> : rb_k_pt_shadow<true, false, RB_ROOTS_TREE>)
+										: (bigTree ? rb_k_pt_shadow<false, true, RB_ROOTS_TREE_BIG> : rb_k_pt_shadow<false, true, RB_ROOTS_TREE>);
+		if(profCounting) kShadow = masked ? (ordered ? rb_k_pt_shadow<true, true, RB_ROOTS_LAZY, true> : (treeShadow ? (bigTree ? rb_k_pt_shadow<true, false, RB_ROOTS_TREE_BIG, true> : rb_k_pt_shadow<true, false, RB_ROOTS_TREE, true>) : rb_k_pt_shadow<true, false, RB_ROOTS_LAZY, true>))
+										  : (treeShadow ? (bigTree ? rb_k_pt_shadow<false, true, RB_ROOTS_TREE_BIG, true> : rb_k_pt_shadow<false, true, RB_ROOTS_TREE, true>) : rb_k_pt_shadow<false, true, RB_ROOTS_LAZY, true>);
 		if(feed) {
 			kShadow = blocks ? (masked ? (ordered ? rb_k_pt_shadow_feed<true, true, RB_ROOTS_BLOCKS> : rb_k_pt_shadow_feed<true, false, RB_ROOTS_BLOCKS>) : rb_k_pt_shadow_feed<false, true, RB_ROOTS_BLOCKS>)
 							 : (masked ? (ordered ? rb_k_pt_shadow_feed<true, true, RB_ROOTS_LAZY> : rb_k_pt_shadow_feed<true, false, RB_ROOTS_LAZY>) : rb_k_pt_shadow_feed<false, true, RB_ROOTS_LAZY>);

@@ -206,10 +206,10 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_persistent(RbDevice
 // Phase-voting scheduler. Every live lane is waiting either for a node step or for a leaf step; the warp executes
 // the leaf phase once at least `leafVotes` lanes wait for it (or nobody wants a node), otherwise the node phase. Lanes
 // of the other kind idle for that iteration instead of the whole warp running at the pace of one lane's descent.
-template<bool ANY, bool ORDERED, bool BLOCKS, bool TREE = false>
+template<bool ANY, bool ORDERED, bool BLOCKS, int TREE = 0> // TREE: 0 none, RB_ROOTS_TREE (register mask), RB_ROOTS_TREE_BIG (mask in the stack column)
 __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_phased(RbDeviceBvh bvh, const float * __restrict__ org, const float * __restrict__ dir, float mini, float maxi, unsigned int n, void * __restrict__ out, unsigned int * __restrict__ cursor, int threshold, int leafVotes, int nodeSteps) {
 	extern __shared__ int s_stack[];
-	const RbStack st		= rb_make_stack(s_stack + threadIdx.x, blockDim.x);
+	const RbStack st		= rb_make_stack(s_stack + threadIdx.x + (TREE == RB_ROOTS_TREE_BIG ? bvh.rootWords * blockDim.x : 0), blockDim.x);
 	const unsigned int lane = threadIdx.x & 31u;
 	bool active = false, exhausted = false;
 	unsigned int rayIdx = 0;
@@ -233,7 +233,8 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_phased(RbDeviceBvh 
 						rb_traversal_init(T, bvh, mini, maxi, st);
 						// TREE: scenes of 9..64 meshes — the roots this ray enters from one walk of the tree over the root
 						// boxes (rb_roots_tree_pretest) instead of one test per root; same set, same visiting order.
-						if(TREE) rb_roots_tree_pretest<false>(T, bvh, ray, st, mini, maxi, nullptr);
+						if(TREE == RB_ROOTS_TREE) rb_roots_tree_pretest<false>(T, bvh, ray, st, mini, maxi, nullptr);
+						if(TREE == RB_ROOTS_TREE_BIG) rb_roots_tree_pretest_big<false>(T, bvh, ray, st, mini, maxi, nullptr);
 						rayIdx = idx;
 						active = true;
 					}
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(RB_TRACE_BLOCK) rb_k_trace_phased(RbDeviceBvh 
 				// Up to `nodeSteps` descents per vote: the vote, executed by all 32 lanes, costs about as much as a
 				// node step; a lane that reaches a leaf (or finishes) early sits out the remaining steps.
 				for(int k = 0; k < nodeSteps; ++k) {
-					finished = rb_phase_node<false, ORDERED, TREE ? RB_ROOTS_TREE : (BLOCKS ? RB_ROOTS_BLOCKS : RB_ROOTS_LAZY)>(T, bvh, ray, st, nullptr);
+					finished = rb_phase_node<false, ORDERED, TREE ? TREE : (BLOCKS ? RB_ROOTS_BLOCKS : RB_ROOTS_LAZY)>(T, bvh, ray, st, nullptr);
 					if(finished || rb_wants_leaf(T)) break;
 				}
 			}
@@ -710,6 +711,8 @@ void rb_raycaster_free_device(rb_raycaster * rc) {
 	rc->d_rootTree	   = nullptr;
 	rc->rootTreeNodes  = 0;
 	rc->dev.rootTree   = nullptr;
+	rc->dev.rootWords  = 0;
+	rc->rootTreeDepth  = 0;
 	rc->rootBlocksCapacity = 0;
 	rc->dev.rootBlocks = nullptr;
 	rc->dev.rootLevels = 0;
@@ -767,6 +770,9 @@ rb_status rb_raycaster_upload_flat(rb_raycaster * rc, const RbFlatBvh & flat) {
 	rc->rootBlocksWanted = rb_root_blocks_worthwhile(flat.roots.data(), flat.roots.size() / 8);
 	rb_status st		 = rb_root_tree_topology(rc, flat.roots.data(), flat.roots.size() / 8);
 	if(st) return st;
+	// The ray's stack column also serves the walk of the root tree (one pending node per level) and, beyond 64 meshes,
+	// holds the mask of entered roots in front of the stack proper.
+	rc->dev.stackDepth = rb_stack_entries(rc);
 	st = rb_build_root_levels(rc, cudaStreamPerThread);
 	if(st) return st;
 	RB_CUDA(cudaStreamSynchronize(cudaStreamPerThread));
@@ -1199,7 +1205,10 @@ static rb_status rb_launch_trace(const rb_raycaster * rc, const float * d_origin
 											 : (ordered ? rb_k_trace_phased<ANY, true, false> : rb_k_trace_phased<ANY, false, false>);
 		// A root tree (9..64 meshes) serves every query whose root tests see a fixed maxi: any-hit, and closest-hit in the
 		// reference's order (the near-child-first closest-hit order tests roots against the shrinking maxi: lazy loop).
-		if(rc->dev.rootTree && (ANY || !ordered)) kernel = ordered ? rb_k_trace_phased<ANY, true, false, true> : rb_k_trace_phased<ANY, false, false, true>;
+		if(rc->dev.rootTree && (ANY || !ordered)) {
+			if(rc->dev.rootWords > 0) kernel = ordered ? rb_k_trace_phased<ANY, true, false, RB_ROOTS_TREE_BIG> : rb_k_trace_phased<ANY, false, false, RB_ROOTS_TREE_BIG>;
+			else kernel = ordered ? rb_k_trace_phased<ANY, true, false, RB_ROOTS_TREE> : rb_k_trace_phased<ANY, false, false, RB_ROOTS_TREE>;
+		}
 		return rb_launch_persistent<ANY>(rc, kernel, smem, 1, d_origins, d_directions, mini, maxi, nrays, d_out, s, rc->fetchThreshold, rc->leafVotes, rc->nodeSteps > 0 ? rc->nodeSteps : 1);
 	}
 	if(rc->persistent) {

@@ -222,6 +222,7 @@ RB_D void rb_traversal_init(RbTraversal & T, const RbDeviceBvh & bvh, float mini
 #define RB_ROOTS_BLOCKS 1 // ... with whole blocks of consecutive roots skipped on a miss (many-mesh scenes)
 #define RB_ROOTS_MASK 2	  // at most 32 roots, all box-tested when the ray starts (rb_roots_pretest): T.root is the bit mask of those entered
 #define RB_ROOTS_TREE 3	  // 9..64 roots: the mask (T.root, T.rootHi) comes from one walk of the tree over the root boxes (rb_roots_tree_pretest)
+#define RB_ROOTS_TREE_BIG 4 // 65..512 roots: the same walk, the mask in the first bvh.rootWords entries of the ray's stack column (T.root = word index)
 
 // The reference box-tests EVERY root against the caller's (mini, maxi) before it pops the first one (Raycaster.cpp:149-155).
 // For a handful of roots the same is done here, up front: the tests are independent (their loads overlap), where the lazy
@@ -293,6 +294,72 @@ RB_D void rb_roots_tree_pretest(RbTraversal & T, const RbDeviceBvh & bvh, const 
 	}
 	T.root	 = int(lo);
 	T.rootHi = int(hi);
+}
+
+// RB_ROOTS_TREE_BIG: the mask of entered roots in shared memory. `st` is the traversal stack proper; the mask words sit in
+// the bvh.rootWords entries in front of it (the kernels shift the stack base by that many entries), private to the ray.
+RB_D unsigned int rb_roots_word_address(const RbDeviceBvh & bvh, const RbStack & st, int word) {
+	return st.base - (unsigned int)((bvh.rootWords - word) * st.strideBytes);
+}
+RB_D void rb_roots_set_bit(const RbDeviceBvh & bvh, const RbStack & st, int r) {
+	const unsigned int a = rb_roots_word_address(bvh, st, r >> 5);
+	rb_sts(a, rb_lds(a) | (1u << (r & 31)));
+}
+template<bool COUNT>
+RB_D void rb_roots_tree_pretest_big(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay & ray, const RbStack & st, float mini, float maxi, RbWork * work) {
+	for(int w = 0; w < bvh.rootWords; ++w) rb_sts(rb_roots_word_address(bvh, st, w), 0u);
+	if(!ray.regular) {
+		for(int r = 0; r < bvh.nroots; ++r) {
+			const float4 r0 = rb_ldg4(bvh.roots + 2 * r);
+			const float4 r1 = rb_ldg4(bvh.roots + 2 * r + 1);
+			if(rb_box_test_t<false>(ray, r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, mini, maxi)) rb_roots_set_bit(bvh, st, r);
+		}
+		if(COUNT) work->roots += (unsigned int)bvh.nroots;
+	} else {
+		int cur = 0;
+		for(;;) {
+			float4 n0, n1, n2, n3;
+			rb_ldg_node(bvh.rootTree + 4 * (size_t)cur, n0, n1, n2, n3);
+			if(COUNT) work->roots += 2u;
+			bool hitL, hitR;
+			float dL, dR;
+			rb_node_test<true>(ray, n0, n1, n2, mini, maxi, hitL, hitR, dL, dR);
+			const int refL = __float_as_int(n3.x), refR = __float_as_int(n3.y);
+			int next = RB_REF_NONE;
+			if(hitL) {
+				if(refL < 0) rb_roots_set_bit(bvh, st, ~refL);
+				else next = refL;
+			}
+			if(hitR) {
+				if(refR < 0) rb_roots_set_bit(bvh, st, ~refR);
+				else {
+					if(next != RB_REF_NONE) rb_push(T, st, next);
+					next = refR;
+				}
+			}
+			if(next == RB_REF_NONE) {
+				if(rb_stack_empty(T, st)) break;
+				next = rb_pop(T, st);
+			}
+			cur = next;
+		}
+	}
+	T.root = bvh.rootWords - 1; // highest word that may still hold a root
+}
+// Next entered root, last mesh first: the highest bit of the highest non-empty word.
+RB_D int rb_next_root_big(RbTraversal & T, const RbDeviceBvh & bvh, const RbStack & st) {
+	for(int w = T.root; w >= 0; --w) {
+		const unsigned int a	= rb_roots_word_address(bvh, st, w);
+		const unsigned int word = rb_lds(a);
+		if(word != 0u) {
+			const int b = 31 - __clz(word);
+			rb_sts(a, word & ~(1u << b));
+			T.root = w;
+			return __float_as_int(rb_ldg4(bvh.roots + 2 * (32 * w + b)).w);
+		}
+	}
+	T.root = -1;
+	return RB_REF_NONE;
 }
 
 template<bool REGULAR, bool COUNT, int ROOTS>
@@ -551,7 +618,8 @@ RB_D bool rb_phase_node_t(RbTraversal & T, const RbDeviceBvh & bvh, const RbRay 
 		if(!rb_stack_empty(T, st)) {
 			cur = rb_pop(T, st);
 		} else {
-			cur = rb_next_root<REGULAR, COUNT, ROOTS>(T, bvh, ray, ORDERED ? T.maxi : T.maxi0, work);
+			if(ROOTS == RB_ROOTS_TREE_BIG) cur = rb_next_root_big(T, bvh, st);
+			else cur = rb_next_root<REGULAR, COUNT, ROOTS>(T, bvh, ray, ORDERED ? T.maxi : T.maxi0, work);
 			if(cur == RB_REF_NONE) return true;
 		}
 	}

@@ -20,9 +20,13 @@ struct RbDeviceBvh {
 	// references in the parent; reference < 0: root ~reference). rb_roots_tree_pretest walks it once per ray and returns
 	// the bit mask of the roots whose box the ray enters. nullptr: not built.
 	const float4 * rootTree;
+	// 65..512 meshes: the mask does not fit two registers; it lives in the first `rootWords` entries of the ray's stack
+	// column (the traversal stack proper starts behind them). 0: register mask.
+	int rootWords;
 };
 #define RB_ROOT_TREE_MIN 9
-#define RB_ROOT_TREE_MAX 64
+#define RB_ROOT_TREE_MAX 64		// register mask up to here ...
+#define RB_ROOT_TREE_BIG_MAX 512 // ... shared-memory mask up to here (16 stack entries per ray)
 
 #define RB_REF_NONE 0x7fffffff
 #define RB_LEAF_BITS 3

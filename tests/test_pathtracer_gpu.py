@@ -294,12 +294,13 @@ def test_cp_async_fed_wavefronts_return_the_same_image(monkeypatch, name):
         assert np.array_equal(fed.view(np.uint32), plain.view(np.uint32))
 
 
-@pytest.mark.parametrize("extra", [2, 5, 33, 57])
+@pytest.mark.parametrize("extra", [2, 5, 33, 57, 58, 250, 505])
 def test_root_tree_returns_the_same_image_as_the_root_loop(monkeypatch, extra):
     """Scenes of 9..64 meshes find the roots a ray enters with one walk of a tree over the root boxes instead of one test
     per root (RB_ROOTS_TREE, rb_roots_tree_pretest) — closest-hit and shadow wavefronts. The set of entered roots and the
     order they are visited in are the reference's, so the image equals the one of the lazy root loop (RB_PT_LAZY_ROOTS=1)
-    bit for bit: 7 + `extra` meshes = 9 (smallest tree), 12, 40 (both mask words), 64 (largest); overlapping boxes, meshes
+    bit for bit: 7 + `extra` meshes = 9 (smallest tree), 12, 40 (both mask registers), 64 (largest register mask), 65, 257 and
+    512 (the mask in the ray's stack column: 3, 9 and 16 words); overlapping boxes, meshes
     that share a position; also after a transform edit re-fits the roots."""
     import copy
     desc = wl.cornell_synthetic(24, 16, 16)

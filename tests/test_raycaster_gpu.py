@@ -203,6 +203,57 @@ def test_many_roots_and_leaf_roots():
     assert len(set(h["meshId"][h["hit"] == 1].tolist())) > 20
 
 
+@pytest.mark.parametrize("nmesh", [9, 40, 64, 65, 300, 512, 513])
+def test_root_tree_with_tiny_meshes_edge_rays_and_refit(monkeypatch, nmesh):
+    """The tree over the root boxes (9..64 meshes: mask of entered roots in two registers; 65..512: in the ray's stack
+    column; beyond: the root loop) against the reference's one-test-per-root loop and against the oracle: meshes of one or
+    two triangles — every hierarchy is shallower than the root tree, so the walk of that tree is what sizes the stack —
+    with axis-parallel and grazing rays among the queries, closest and any hit, before and after a refit that moves half
+    the meshes (the tree keeps its topology and gets new boxes)."""
+    rng = np.random.RandomState(nmesh)
+    meshes = []
+    for k in range(nmesh):
+        c = rng.uniform(-1, 1, 3).astype(np.float32)
+        if k % 2:
+            p = (c + rng.uniform(-0.15, 0.15, (3, 3))).astype(np.float32)
+            meshes.append((p, np.array([0, 1, 2], np.uint32)))
+        else:
+            e = np.float32(rng.uniform(0.05, 0.2))
+            p = np.array([c + [-e, 0, -e], c + [e, 0, -e], c + [e, 0, e], c + [-e, 0, e]], np.float32)  # axis-aligned quad: boxes of zero height
+            meshes.append((p, np.array([0, 1, 2, 0, 2, 3], np.uint32)))
+    org, dirs = wl.random_rays(30000, nmesh)
+    org[:200] = np.round(org[:200] * 4) / 4
+    dirs[:100] = np.array([0, -1, 0], np.float32)  # axis parallel: irregular rays (0 * inf in the slab arithmetic)
+    dirs[100:200] = np.array([1, 0, 0], np.float32)  # ... and parallel to the quads, in their planes for some
+    org[100:200, 1] = np.array([meshes[2 * (k % (nmesh // 2))][0][0, 1] for k in range(100)], np.float32)
+    o = oracle_from_meshes([(p, i, None) for p, i in meshes])
+    ho = o.intersect(org, dirs, threads=4)
+    ao = o.intersect_any(org, dirs, threads=4)
+    results = {}
+    for mode in ("tree", "loop"):
+        if mode == "loop":
+            monkeypatch.setenv("RB_NO_ROOT_TREE", "1")
+        else:
+            monkeypatch.delenv("RB_NO_ROOT_TREE", raising=False)
+        r = rb.Raycaster()
+        for p, i in meshes:
+            r.addMesh(p, i)
+        r.updateHierarchy()
+        h, a = r.intersects(org, dirs), r.intersectsAny(org, dirs)
+        assert_hits_equal(h, ho["hit"], ho["dist"], ho["u"], ho["v"], ho["w"], ho["localId"], ho["meshId"], "root tree " + mode)
+        assert np.array_equal(a.astype(np.uint8), ao)
+        moved = []
+        for k, (p, i) in enumerate(meshes):
+            q = (p + np.array([0.3, -0.2, 0.1], np.float32)).astype(np.float32) if k % 2 == 0 else p
+            moved.append(q)
+            r.update_mesh(k, q)
+        r.refit()
+        results[mode] = (h, a, r.intersects(org, dirs), r.intersectsAny(org, dirs))
+    for x, y in zip(results["tree"], results["loop"]):
+        assert x.tobytes() == y.tobytes()
+    assert (results["tree"][2]["hit"] == 1).sum() > 100 and results["tree"][2].tobytes() != results["tree"][0].tobytes()
+
+
 def test_single_ray_and_empty_batch_and_interpolation():
     pos, idx = wl.displaced_grid(8)
     r = rb.Raycaster()

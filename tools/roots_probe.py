@@ -49,8 +49,8 @@ for nmesh, ordered in ((64, True), (443, True), (2000, True), (443, False)):
     same = bool((outs["blocks"][1] == outs["linear"][1]).all())
     print("%s order, %5d meshes: with root blocks %.3f ms, linear root loop %.3f ms (%.1fx), identical hit records: %s" % ("row" if ordered else "random", nmesh, outs["blocks"][0], outs["linear"][0], outs["linear"][0] / outs["blocks"][0], same), flush=True)
 
-# 9..64 meshes: the root tree (rb_roots_tree_pretest) against the plain root loop; random mesh order (no blocks either way)
-for nmesh in (12, 24, 52, 64):
+# 9..512 meshes: the root tree (rb_roots_tree_pretest) against the plain root loop; random mesh order (no blocks either way)
+for nmesh in (12, 24, 52, 64, 65, 128, 443, 512):
     outs = {}
     for name, env in (("tree", None), ("linear", "1")):
         if env: os.environ["RB_NO_ROOT_TREE"] = env
