@@ -1,13 +1,13 @@
 #!/bin/bash
 # The C++ drop-in (reference engine + GPU classes) on 1 / 2 / 4 / 8 GPUs of one box, both splits: rendering time of the
-# second frame (the first also builds the replicas).   gpurun --gpus 8 --timeout 600 -- 'bash tools/dropin_scaling.sh'
+# second frame (the first also builds the replicas).   gpurun --gpus 8 --timeout 600 -- 'bash tools/dropin_scaling.sh'   (GPUS="1 8" for a subset)
 set -u
 mkdir -p gpurun_out
 B=build/pathtracer_b200; R=oracle/_ref/resources
 N=$(nvidia-smi -L | wc -l)
 echo "{" > gpurun_out/r02_dropin_scaling.json
 first=1
-for g in 1 2 4 8; do
+for g in ${GPUS:-1 2 4 8}; do
   [ $g -le $N ] || continue
   for split in tile sample; do
     [ $g -eq 1 ] && [ $split = sample ] && continue
