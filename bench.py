@@ -621,7 +621,7 @@ def pt_roofline(pt, cam, opts, rays_scale=1.0):
             "traffic": (cnt or {}).get("dram_bytes"), "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo[dom] / max(p["launches"][dom], 1)),
             "avg_launch_ms": kernels[dom]["avg_launch_ms"], "profiled_frame": "1920x1080, %d spp, depth %d, single stream" % (spp, PT_DEPTH), "per_ray": per_ray, "kernels": kernels,
             "limiter": "not HBM for the traversal wavefronts (the tree is L2-resident: L1 data pipe and issue slots, as in the raycast block); shading is a chain of dependent "
-                       "loads at low occupancy (80 registers) — see `counters`",
+                       "loads at 42 % occupancy (72 registers, 7 CTAs per SM) — see `counters`",
             "counters": cnt, "counters_source": "profiles/r02_counters.json (ncu --set full --clock-control none, this round)" if cnt else None}
 
 
