@@ -208,3 +208,54 @@ def test_root_block_skipping_visits_the_same_roots_in_the_same_order():
         skipped_total += n - tests
     assert skipped_total > 0.5 * n * org.shape[0]  # most root tests are saved on a row-ordered scene
 
+
+@pytest.mark.parametrize("n", [9, 52, 64, 65, 443])
+def test_root_tree_walk_enters_the_same_roots_as_the_root_loop(n):
+    """Model of rb_roots_tree_pretest (rendu_b200/csrc/rb_trace.cuh) and of the tree it walks (rb_root_tree_split / rb_k_root_tree_fit,
+    rb_lbvh.cu) on the oracle's bit-exact box test: a median-split tree over the root boxes whose nodes carry the exact fp32
+    unions of their children; a ray descends into a child only if it passes the child's box and collects the roots it reaches.
+    That set equals the set of the reference's loop over every root (Raycaster.cpp:149-155), so visiting it from the highest
+    index down is the reference's order. Overlapping, nested, flat (zero-height) and duplicate boxes; rays without NaNs (the
+    others test every root in the product)."""
+    rng = np.random.RandomState(n)
+    lo = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+    hi = (lo + rng.uniform(0.0, 0.5, (n, 3)) * (rng.uniform(size=(n, 3)) > 0.15)).astype(np.float32)  # some zero extents
+    lo[n // 2], hi[n // 2] = lo[0], hi[0]  # a duplicate
+    lo[n // 3], hi[n // 3] = np.float32([-2, -2, -2]), np.float32([2, 2, 2])  # one that contains everything
+
+    def build(ids):
+        if len(ids) == 1:
+            return ~ids[0], lo[ids[0]], hi[ids[0]]
+        c = 0.5 * (lo[ids] + hi[ids])
+        axis = int(np.argmax(c.max(0) - c.min(0)))
+        order = sorted(ids, key=lambda r: (0.5 * (lo[r, axis] + hi[r, axis]), r))
+        mid = len(order) // 2
+        left, right = build(order[:mid]), build(order[mid:])
+        node = (left, right)
+        return node, np.minimum(left[1], right[1]), np.maximum(left[2], right[2])
+
+    tree = build(list(range(n)))
+    org, dirs = wl.random_rays(150, n)
+    co, cd = wl.coherent_rays(8)
+    org, dirs = np.concatenate([org, co]), np.concatenate([dirs, cd])
+
+    def passes(i, blo, bhi, mini, maxi):
+        return bool(orc.box_test(org[i:i + 1], dirs[i:i + 1], np.concatenate([blo, bhi])[None].astype(np.float32), mini, maxi)[0][0])
+
+    saved = 0
+    for mini, maxi in ((1e-4, 1e8), (1e-3, 0.7)):
+        for i in range(org.shape[0]):
+            plain = {r for r in range(n) if passes(i, lo[r], hi[r], mini, maxi)}
+            entered, tests, stack = set(), 0, [tree[0]]
+            while stack:
+                node = stack.pop()
+                for child in node:
+                    tests += 1
+                    if passes(i, child[1], child[2], mini, maxi):
+                        if isinstance(child[0], tuple):
+                            stack.append(child[0])
+                        else:
+                            entered.add(~child[0])
+            assert entered == plain, "ray %d" % i
+            saved += n - tests
+    assert n < 16 or saved > 0
