@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(RB_PT_BLOCK, RB_PT_SHADE_MIN_BLOCKS) rb_k_pt_s
 // alpha < 0.01. When no object of the scene is masked the walk degenerates to "is there any hit", so the any-hit
 // traversal (identical accept/reject decisions, early exit) is used instead (MASKED = false).
 template<bool MASKED, bool ORDERED, int ROOTS, bool COUNT = false>
-__global__ void __launch_bounds__(RB_PT_BLOCK) rb_k_pt_shadow(RbDeviceBvh bvh, RbPathBuffers pb, RbSceneDev sc, uint32_t did, int threshold, int leafVotes, int nodeSteps, unsigned long long * __restrict__ stats) {
+__global__ void __launch_bounds__(RB_PT_BLOCK, (!MASKED && !COUNT && ROOTS >= RB_ROOTS_TREE) ? 8 : 0) rb_k_pt_shadow(RbDeviceBvh bvh, RbPathBuffers pb, RbSceneDev sc, uint32_t did, int threshold, int leafVotes, int nodeSteps, unsigned long long * __restrict__ stats) {
 	extern __shared__ int s_stack[];
 	const RbStack st		= rb_make_stack(s_stack + threadIdx.x + (ROOTS == RB_ROOTS_TREE_BIG ? bvh.rootWords * blockDim.x : 0), blockDim.x);
 	const unsigned int lane = threadIdx.x & 31u;
