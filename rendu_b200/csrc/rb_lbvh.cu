@@ -488,7 +488,7 @@ bool rb_root_blocks_worthwhile(const float * roots8, size_t nroots) {
 // bundled scene, more than the nodes the ray then visits inside the meshes. Which roots a ray enters is a set, whatever the
 // order the tests are made in, and the slab test is monotone in the box (rb_next_root): a union box that the ray misses
 // hides no root it would enter. So scenes of 9..64 meshes get a small binary tree over their root boxes — topology from
-// the boxes at upload (median split of the centroids), boxes re-computed on the device after every fit — and the path
+// the boxes at upload (surface-area sweep over the box centres), boxes re-computed on the device after every fit — and the path
 // tracer's wavefronts walk it once per ray (rb_roots_tree_pretest) for the bit mask of entered roots, then visit those
 // last mesh first as before: the same hits, bit for bit (irregular rays test every root with the NaN-faithful form).
 // Up to 64 meshes the mask is two registers; up to 512 it lives in the first entries of the ray's stack column.
@@ -496,22 +496,51 @@ static int rb_root_tree_split(std::vector<int> & ids, int begin, int end, const 
 	// returns the reference of the subtree over ids[begin, end): ~root for one root, else the index of a new node
 	if(end - begin == 1) return ~ids[begin];
 	depth = std::max(depth, level + 1);
-	float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
 	auto centre = [&](int r, int k) { return 0.5f * (roots8[8 * r + k] + roots8[8 * r + 4 + k]); };
-	for(int i = begin; i < end; ++i) {
-		for(int k = 0; k < 3; ++k) {
-			lo[k] = std::min(lo[k], centre(ids[i], k));
-			hi[k] = std::max(hi[k], centre(ids[i], k));
+	auto area = [](const float * lo, const float * hi) {
+		const float dx = std::max(hi[0] - lo[0], 0.0f), dy = std::max(hi[1] - lo[1], 0.0f), dz = std::max(hi[2] - lo[2], 0.0f);
+		return dx * dy + dy * dz + dz * dx;
+	};
+	// Sweep of the surface-area cost along each axis over the roots sorted by box centre (at most 512 of them, once per
+	// upload): the split that leaves the two smallest boxes for the most roots. RB_ROOT_TREE_SPLIT=median: the middle one.
+	static const bool median = [] { const char * e = std::getenv("RB_ROOT_TREE_SPLIT"); return e && std::string(e) == "median"; }();
+	const int n = end - begin;
+	int bestAxis = 0, bestAt = n / 2;
+	float bestCost = FLT_MAX;
+	std::vector<int> order(n), bestOrder;
+	std::vector<float> rightArea(n);
+	for(int axis = 0; axis < 3; ++axis) {
+		for(int i = 0; i < n; ++i) order[i] = ids[begin + i];
+		std::sort(order.begin(), order.end(), [&](int a, int b) {
+			const float ca = centre(a, axis), cb = centre(b, axis);
+			return ca < cb || (ca == cb && a < b);
+		});
+		float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+		for(int i = n - 1; i >= 1; --i) {
+			for(int k = 0; k < 3; ++k) {
+				lo[k] = std::min(lo[k], roots8[8 * order[i] + k]);
+				hi[k] = std::max(hi[k], roots8[8 * order[i] + 4 + k]);
+			}
+			rightArea[i] = area(lo, hi);
+		}
+		float llo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, lhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+		for(int i = 1; i < n; ++i) { // left = order[0, i), right = order[i, n)
+			for(int k = 0; k < 3; ++k) {
+				llo[k] = std::min(llo[k], roots8[8 * order[i - 1] + k]);
+				lhi[k] = std::max(lhi[k], roots8[8 * order[i - 1] + 4 + k]);
+			}
+			// (no side below a quarter of the roots: the depth of the tree — stack entries of every ray — stays logarithmic)
+			if(i < std::max(1, n / 4) || n - i < std::max(1, n / 4)) continue;
+			const float cost = median ? (i == n / 2 ? float(axis == 0 ? 0 : 1) + 1.0f : FLT_MAX) : area(llo, lhi) * float(i) + rightArea[i] * float(n - i);
+			if(cost < bestCost) {
+				bestCost = cost; bestAxis = axis; bestAt = i;
+				bestOrder = order;
+			}
 		}
 	}
-	int axis = 0;
-	if(hi[1] - lo[1] > hi[axis] - lo[axis]) axis = 1;
-	if(hi[2] - lo[2] > hi[axis] - lo[axis]) axis = 2;
-	const int mid = (begin + end) / 2;
-	std::nth_element(ids.begin() + begin, ids.begin() + mid, ids.begin() + end, [&](int a, int b) {
-		const float ca = centre(a, axis), cb = centre(b, axis);
-		return ca < cb || (ca == cb && a < b);
-	});
+	(void)bestAxis;
+	for(int i = 0; i < n; ++i) ids[begin + i] = bestOrder[i];
+	const int mid = begin + bestAt;
 	const int node = int(refs.size() / 2);
 	refs.push_back(0);
 	refs.push_back(0); // preorder: a parent's index is smaller than its children's
