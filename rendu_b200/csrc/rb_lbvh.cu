@@ -539,7 +539,10 @@ static int rb_root_tree_split(std::vector<int> & ids, int begin, int end, const 
 		}
 	}
 	(void)bestAxis;
-	for(int i = 0; i < n; ++i) ids[begin + i] = bestOrder[i];
+	// (boxes with NaNs or infinities — a mesh with broken vertices — make every cost unordered: the roots stay as they are
+	// and are cut in the middle; any topology gives the right hits)
+	if(bestOrder.empty()) bestAt = n / 2;
+	else for(int i = 0; i < n; ++i) ids[begin + i] = bestOrder[i];
 	const int mid = begin + bestAt;
 	const int node = int(refs.size() / 2);
 	refs.push_back(0);
